@@ -1,0 +1,179 @@
+/*
+ * ood_b200.h -- C ABI of libood_b200.so: the B200 (sm_100a) hot path of OOD-GAN-inversion.
+ *
+ * Drop-in boundary.  The reference reaches its native code through two pybind/torch extensions
+ * ("boundary #2"):
+ *     upfirdn2d_op.upfirdn2d(input[N,H,W,minor], kernel, up_x, up_y, down_x, down_y, pad_x0, pad_x1, pad_y0, pad_y1)
+ *                                                  -- /root/reference/src/ops/op/upfirdn2d.cpp:12-23
+ *     fused.fused_bias_act(input, bias, refer, act, grad, alpha, scale)
+ *                                                  -- /root/reference/src/ops/op/fused_bias_act.cpp:11-21
+ * and everything else on the path (modulated conv, ToRGB, warp, mask, blend) through ATen library calls
+ * made by src/ops/StyleGAN/model.py, src/ops/SAMM/helpers.py and src/archs/OOD_faceGAN_e4e_arch.py.
+ * This header replaces both: plain pointers and sizes, no torch types, no exceptions across the boundary.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - the caller owns and pre-allocates every buffer (no hidden allocation, no hidden synchronisation);
+ *   - `stream` is a cudaStream_t passed as void* (torch.cuda.current_stream().cuda_stream);
+ *   - return value 0 = launched; negative = error, text in ood_last_error() (thread local);
+ *   - dtype: OOD_F32 or OOD_BF16 is the STORAGE type of activations; arithmetic is always fp32
+ *     (tensor-core paths: bf16 x bf16 -> fp32 accumulate);
+ *   - "NHWC" activations are [B][H][W][C] with C innermost (== torch channels_last of a [B,C,H,W] tensor);
+ *     "NCHW" planes are [B*C][H][W].
+ */
+#ifndef OOD_B200_H_
+#define OOD_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OOD_F32 0
+#define OOD_BF16 1
+
+#define OOD_OK 0
+#define OOD_ERR_ARG (-1)      /* bad argument / unsupported configuration (never a silent no-op) */
+#define OOD_ERR_CUDA (-2)     /* CUDA runtime / driver error at launch                          */
+#define OOD_ERR_DEVICE (-3)   /* device is not sm_100                                            */
+
+int ood_version(void);
+const char *ood_last_error(void);
+/* 1 if the current device is compute capability 10.x (tcgen05/TMEM/TMA paths usable). */
+int ood_device_is_sm100(void);
+
+/* ---- a1. upfirdn2d on NCHW planes: replaces upfirdn2d_op.upfirdn2d (upfirdn2d.cpp:12-23) with minor==1,
+ *      which is the only form the Python wrapper issues (upfirdn2d.py:103).  Generic in every parameter
+ *      (the reference kernel silently returns garbage for unsupported modes, SURVEY finding 11).
+ *      out_h = (in_h*up_y + pad_y0 + pad_y1 - kh)/down_y + 1, likewise out_w.  kernel: fp32 [kh][kw]. */
+int ood_upfirdn2d(const void *in, void *out, const float *kernel, int64_t planes, int in_h, int in_w,
+                  int kh, int kw, int up_x, int up_y, int down_x, int down_y, int pad_x0, int pad_x1,
+                  int pad_y0, int pad_y1, int dtype, void *stream);
+
+/* ---- a2. fused bias + leaky-ReLU: replaces fused.fused_bias_act (fused_bias_act.cpp:11-21).
+ *      act must be 3 (leaky relu).  grad 0: out = lrelu(in + bias[(i/inner)%channels], alpha)*scale
+ *      grad 1: out = in * (refer>0 ? 1 : alpha) * scale        (bias ignored; refer = saved forward output)
+ *      grad 2: out = 0.                                       bias / refer may be NULL where unused. */
+int ood_fused_bias_act(const void *in, const void *bias, const void *refer, void *out, int64_t numel,
+                       int channels, int64_t inner, int act, int grad, float alpha, float scale, int dtype,
+                       void *stream);
+/* grad_bias[c] = sum over batch and inner of g[b][c][inner]; fp32 output.  (fused_act.py:38-43) */
+int ood_bias_grad(const void *g, float *grad_bias, int64_t batch, int channels, int64_t inner, int dtype,
+                  void *stream);
+
+/* ---- layout: NCHW fp32 <-> NHWC storage type, optional per-(b,c) scale (the style modulation of the NEXT conv).
+ *      in_batch_stride 0 broadcasts one sample (ConstantInput, model.py:295-305). */
+int ood_nchw_to_nhwc(const float *in, int64_t in_batch_stride, const float *scale_bc, void *out, int batch,
+                     int channels, int h, int w, int dtype, void *stream);
+int ood_nhwc_to_nchw(const void *in, float *out, int batch, int channels, int h, int w, int dtype, void *stream);
+/* out[b,p,c] = in[b,p,c] * scale_bc[b,c]   (NHWC, either storage type) */
+int ood_nhwc_scale(const void *in, const float *scale_bc, void *out, int batch, int channels, int64_t pixels,
+                   int dtype, void *stream);
+
+/* ---- a4/a5. style modulation and demodulation coefficients (model.py:129-163, 236-241).
+ *      s[b,i]  = sum_j latent[b,j]*mod_w[i,j]/sqrt(style_dim) + mod_b[i]
+ *      d[b,o]  = conv_scale * rsqrt(conv_scale^2 * sum_i s[b,i]^2 * wsq[o,i] + 1e-8)   (demodulate)
+ *              = conv_scale                                                             (wsq == NULL)
+ *      wsq[o,i] = sum_k W[o,i,k]^2 (ood_weight_sumsq).  latent rows are latent + b*latent_stride. */
+int ood_modulation(const float *latent, int64_t latent_stride, const float *mod_w, const float *mod_b,
+                   const float *wsq, float conv_scale, float *s_out, float *d_out, int batch, int style_dim,
+                   int cin, int cout, void *stream);
+int ood_weight_sumsq(const float *w /*[Co][Ci][k*k]*/, float *wsq /*[Co][Ci]*/, int cout, int cin, int taps,
+                     void *stream);
+/* weight repack W[Co][Ci][ky][kx] fp32 -> [tap][Co][Ci] in `dtype` (tensor-core B operand, K-major)
+ *                                     or -> [tap][Ci][Co] fp32 when ci_major_out != 0 (SIMT path). */
+int ood_pack_conv_weight(const float *w, void *out, int cout, int cin, int taps, int ci_major_out, int dtype,
+                         void *stream);
+
+/* ---- a5. 3x3 convolution of pre-modulated NHWC activations with SHARED weights.
+ *      Uses (W*s*d) (*) x == d . (W (*) (s . x))  (SURVEY.md section 7 step 4): `in` already carries s.
+ *      transposed == 0: stride-1, pad-1 conv, out [B,H,W,Co]           (model.py:268-272)
+ *      transposed == 1: stride-2 transposed conv, out [B,2H+1,2W+1,Co]  (model.py:246-256), raw accumulators.
+ *      Epilogue (stride-1 only; any pointer may be NULL to skip that term):
+ *          v  = acc * d[b,o] + noise_w * noise[b,y,x] + bias[o];  y = act ? lrelu(v,0.2)*sqrt2 : v
+ *          out_y  = y            out_ys = y * s_next[b,o]
+ *      impl 0: tcgen05/TMEM/TMA implicit GEMM (dtype must be OOD_BF16, weights from ood_pack_conv_weight bf16)
+ *      impl 1: fp32 SIMT implicit GEMM (dtype OOD_F32, weights packed ci_major_out=1).
+ *      noise: fp32 [B or 1][H][W] with batch stride noise_bstride (0 = shared).  noise_w: device scalar. */
+typedef struct {
+    const void *in;        /* NHWC [B,H,W,Ci], pre-modulated */
+    const void *weight;    /* packed */
+    void *out_y;           /* NHWC [B,OH,OW,Co] or NULL */
+    void *out_ys;          /* NHWC or NULL */
+    const float *d;        /* [B,Co] or NULL (=1) */
+    const float *noise;    /* or NULL */
+    int64_t noise_bstride;
+    const float *noise_w;  /* device scalar or NULL */
+    const float *bias;     /* [Co] or NULL */
+    const float *s_next;   /* [B,Co]; required iff out_ys */
+    int batch, h, w, cin, cout;
+    int transposed;        /* 0 | 1 */
+    int act;               /* 0 | 1 */
+    int impl;              /* 0 tcgen05 | 1 simt */
+    int dtype;             /* storage type of in / out */
+    int out_f32;           /* 1: out_y is fp32 regardless of dtype (raw accumulators of the transposed conv) */
+} ood_conv3x3_args;
+int ood_conv3x3(const ood_conv3x3_args *args_host, void *stream);
+
+/* ---- a1+a2+a6 fused: FIR blur (4x4 separable taps, pad (1,1)) of the transposed-conv output
+ *      [B,2h+1,2w+1,C] -> [B,2h,2w,C], then the StyledConv epilogue (model.py:257, 283-292, fused_act.py:96):
+ *          img = blur(t) * d[b,c]
+ *          out_img (optional) = img                      (what the alignment callback sees, model.py:288-290)
+ *          v = img + noise_w*noise + bias ; y = lrelu(v)*sqrt2 ; out_y = y ; out_ys = y*s_next[b,c]
+ *      taps: 4 fp32 HOST values of the 1-D FIR (already including the gain, e.g. [1,3,3,1]/8*2). */
+typedef struct {
+    const void *in;       /* NHWC [B,IH,IW,C] */
+    int in_f32;           /* 1: `in` is fp32 regardless of dtype */
+    void *out_img;        /* NHWC [B,IH-1,IW-1,C] storage dtype, or NULL */
+    void *out_y, *out_ys; /* NHWC or NULL */
+    const float *d, *noise, *noise_w, *bias, *s_next;
+    int64_t noise_bstride;
+    float taps[4];
+    int batch, ih, iw, channels;
+    int act;              /* 0: stop after img (out_y/out_ys must be NULL) */
+    int dtype;
+} ood_blur_act_args;
+int ood_blur_act(const ood_blur_act_args *args_host, void *stream);
+
+/* ---- a6+a2 on NHWC: y = lrelu(img + noise_w*noise + bias)*sqrt2 ; out_y, out_ys as above.
+ *      Used after the alignment callback replaced `img` (e4e_arch.py:224-242: image := aligned + w*noise). */
+int ood_noise_act(const void *img, void *out_y, void *out_ys, const float *noise, int64_t noise_bstride,
+                  const float *noise_w, const float *bias, const float *s_next, int batch, int64_t pixels,
+                  int channels, int dtype, void *stream);
+
+/* ---- a8. ToRGB: 1x1 modulated conv without demodulation + bias + FIR-upsampled skip (model.py:363-372).
+ *      wrgb[b,k,c] = W[k,c]*s[b,c]/sqrt(C) (fp32, from ood_torgb_weight); y is the UNscaled NHWC activation.
+ *      out[b,k,Y,X] = sum_c y[b,Y,X,c]*wrgb[b,k,c] + bias[k] + up2fir(skip)[b,k,Y,X]     (NCHW fp32)
+ *      skip: [B,3,H/2,W/2] fp32 or NULL.  taps_up: 4 host values of the 1-D up-FIR ([1,3,3,1]/8*2). */
+int ood_torgb_weight(const float *w /*[3][C]*/, const float *s /*[B][C]*/, float *wrgb, int batch, int channels,
+                     void *stream);
+int ood_torgb(const void *y, const float *wrgb, const float *bias, const float *skip, float *out,
+              const float *taps_up_host, int batch, int h, int w, int channels, int dtype, void *stream);
+
+/* ---- a11. alignment-field step (SAMM/helpers.py:104-107, 129-147, 154-166), all fp32 NCHW [B,3,R,R]:
+ *      f = blur_{pad(2,1)}([tanh(z0)*scale, tanh(z1)*scale, sigmoid(z2)])   (taps: 4 host values, [1,3,3,1]/8)
+ *      prev == NULL: acc = f
+ *      else acc = [clip(prev0+f0,+-scale), clip(prev1+f1,+-scale), clip(PRM(prev2, f2),0,1)]
+ *      coarse != NULL (last cycle of a finer level): acc2 = clip(PRM(bicubic_up(coarse2), acc2),0,1)
+ *      PRM(x,y) = y*x + x*(1-x).  coarse is [B,3,Rc,Rc]; bicubic align_corners=True (helpers.py:69-70). */
+int ood_field_step(const float *z, const float *prev, const float *coarse, float *acc, const float *taps_host,
+                   float scale, int batch, int r, int rc, void *stream);
+
+/* ---- a11. warp + alpha mix (helpers.py:168-177) on NHWC features:
+ *      out[b,y,x,:] = bilinear(gen[b], lin_x[x]+dx, lin_y[y]+dy)*alpha + gen[b,y,x,:]*(1-alpha)
+ *      lin = linspace(-1,1,R); sampling with zeros padding, align_corners=False.  field fp32 [B,3,R,R]. */
+int ood_warp_mix(const void *gen, const float *field, void *out, int batch, int h, int w, int channels,
+                 int dtype, void *stream);
+
+/* ---- a12. mask compose + blend (e4e_arch.py:315-347): A = up(a_1); A = up(a_k)*A + A*(1-A); clip;
+ *      out = A*x + gen*(1-A).  fields[k]: fp32 [B,3,r_k,r_k] (alpha = channel 2), ascending size;
+ *      bilinear align_corners=False to size x size.  x, gen, out: NCHW fp32 [B,3,size,size];
+ *      alpha_out: [B,1,size,size] or NULL. */
+int ood_mask_blend(const float *const *fields_host, const int *field_sizes_host, int n_fields, const float *x,
+                   const float *gen, float *out, float *alpha_out, int batch, int size, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OOD_B200_H_ */

@@ -1,0 +1,82 @@
+"""ctypes binding of libood_b200.so (the C ABI declared in include/ood_b200.h).
+
+There is no fallback: if the library is missing or a call fails, a RuntimeError is raised.
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, 'libood_b200.so')
+
+F32, BF16 = 0, 1
+
+c_void_p, c_int, c_i64, c_float = C.c_void_p, C.c_int, C.c_int64, C.c_float
+
+
+class ConvArgs(C.Structure):
+    _fields_ = [('inp', c_void_p), ('weight', c_void_p), ('out_y', c_void_p), ('out_ys', c_void_p), ('d', c_void_p),
+                ('noise', c_void_p), ('noise_bstride', c_i64), ('noise_w', c_void_p), ('bias', c_void_p),
+                ('s_next', c_void_p), ('batch', c_int), ('h', c_int), ('w', c_int), ('cin', c_int), ('cout', c_int),
+                ('transposed', c_int), ('act', c_int), ('impl', c_int), ('dtype', c_int), ('out_f32', c_int)]
+
+
+class BlurActArgs(C.Structure):
+    _fields_ = [('inp', c_void_p), ('in_f32', c_int), ('out_img', c_void_p), ('out_y', c_void_p), ('out_ys', c_void_p),
+                ('d', c_void_p), ('noise', c_void_p), ('noise_w', c_void_p), ('bias', c_void_p), ('s_next', c_void_p),
+                ('noise_bstride', c_i64), ('taps', c_float * 4), ('batch', c_int), ('ih', c_int), ('iw', c_int),
+                ('channels', c_int), ('act', c_int), ('dtype', c_int)]
+
+
+_SIGS = {
+    'ood_version': ([], c_int),
+    'ood_last_error': ([], C.c_char_p),
+    'ood_device_is_sm100': ([], c_int),
+    'ood_upfirdn2d': ([c_void_p, c_void_p, c_void_p, c_i64] + [c_int] * 12 + [c_int, c_void_p], c_int),
+    'ood_fused_bias_act': ([c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_int, c_i64, c_int, c_int, c_float, c_float,
+                            c_int, c_void_p], c_int),
+    'ood_bias_grad': ([c_void_p, c_void_p, c_i64, c_int, c_i64, c_int, c_void_p], c_int),
+    'ood_nchw_to_nhwc': ([c_void_p, c_i64, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p], c_int),
+    'ood_nhwc_to_nchw': ([c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p], c_int),
+    'ood_nhwc_scale': ([c_void_p, c_void_p, c_void_p, c_int, c_int, c_i64, c_int, c_void_p], c_int),
+    'ood_modulation': ([c_void_p, c_i64, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_int, c_int, c_int,
+                        c_int, c_void_p], c_int),
+    'ood_weight_sumsq': ([c_void_p, c_void_p, c_int, c_int, c_int, c_void_p], c_int),
+    'ood_pack_conv_weight': ([c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p], c_int),
+    'ood_conv3x3': ([C.POINTER(ConvArgs), c_void_p], c_int),
+    'ood_blur_act': ([C.POINTER(BlurActArgs), c_void_p], c_int),
+    'ood_noise_act': ([c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_void_p, c_void_p, c_int, c_i64, c_int,
+                       c_int, c_void_p], c_int),
+    'ood_torgb_weight': ([c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p], c_int),
+    'ood_torgb': ([c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, C.POINTER(c_float), c_int, c_int, c_int, c_int, c_int,
+                   c_void_p], c_int),
+    'ood_field_step': ([c_void_p, c_void_p, c_void_p, c_void_p, C.POINTER(c_float), c_float, c_int, c_int, c_int,
+                        c_void_p], c_int),
+    'ood_warp_mix': ([c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p], c_int),
+    'ood_mask_blend': ([C.POINTER(c_void_p), C.POINTER(c_int), c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                        c_void_p], c_int),
+}
+
+EXPORTS = tuple(_SIGS)
+_lib = None
+
+
+def lib():
+    """The loaded library; raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f'{LIB_PATH} is missing: run `python -c "import __graft_entry__ as g; g.build()"` '
+                               '(ood_gan_inversion_b200 has no CPU or PyTorch fallback)')
+        handle = C.CDLL(LIB_PATH)
+        for name, (args, res) in _SIGS.items():
+            fn = getattr(handle, name)      # AttributeError if the symbol is not exported
+            fn.argtypes = args
+            fn.restype = res
+        _lib = handle
+    return _lib
+
+
+def check(rc, what=''):
+    if rc != 0:
+        msg = lib().ood_last_error().decode('utf-8', 'replace')
+        raise RuntimeError(f'libood_b200 {what} failed (code {rc}): {msg}')

@@ -1,0 +1,86 @@
+// Shared helpers for libood_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+
+#include "../../include/ood_b200.h"
+
+namespace ood {
+
+void set_error(const char *fmt, ...);
+int check_launch(const char *what);
+
+#define OOD_REQUIRE(cond, ...)              \
+    do {                                    \
+        if (!(cond)) {                      \
+            ood::set_error(__VA_ARGS__);    \
+            return OOD_ERR_ARG;             \
+        }                                   \
+    } while (0)
+
+constexpr int kNumSMs = 148;
+constexpr float kSqrt2 = 1.4142135623730951f;
+
+static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// ---- storage-type traits: T in {float, __nv_bfloat16}; arithmetic is fp32 ----
+template <typename T> struct Vec;   // 16-byte vector of T
+template <> struct Vec<float> {
+    static constexpr int N = 4;
+    float v[4];
+};
+template <> struct Vec<__nv_bfloat16> {
+    static constexpr int N = 8;
+    float v[8];
+};
+
+__device__ __forceinline__ float to_f32(float x) { return x; }
+__device__ __forceinline__ float to_f32(__nv_bfloat16 x) { return __bfloat162float(x); }
+template <typename T> __device__ __forceinline__ T from_f32(float x);
+template <> __device__ __forceinline__ float from_f32<float>(float x) { return x; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float x) { return __float2bfloat16_rn(x); }
+
+// 16-byte global load of T, unpacked to fp32 lanes.
+template <typename T> __device__ __forceinline__ Vec<T> load_vec(const T *p);
+template <> __device__ __forceinline__ Vec<float> load_vec<float>(const float *p) {
+    float4 r = __ldg(reinterpret_cast<const float4 *>(p));
+    Vec<float> o;
+    o.v[0] = r.x; o.v[1] = r.y; o.v[2] = r.z; o.v[3] = r.w;
+    return o;
+}
+template <> __device__ __forceinline__ Vec<__nv_bfloat16> load_vec<__nv_bfloat16>(const __nv_bfloat16 *p) {
+    uint4 r = __ldg(reinterpret_cast<const uint4 *>(p));
+    Vec<__nv_bfloat16> o;
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        o.v[2 * i] = __uint_as_float(w[i] << 16);
+        o.v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+    return o;
+}
+template <typename T> __device__ __forceinline__ void store_vec(T *p, const Vec<T> &x);
+template <> __device__ __forceinline__ void store_vec<float>(float *p, const Vec<float> &x) {
+    *reinterpret_cast<float4 *>(p) = make_float4(x.v[0], x.v[1], x.v[2], x.v[3]);
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t *>(&h);
+}
+template <> __device__ __forceinline__ void store_vec<__nv_bfloat16>(__nv_bfloat16 *p, const Vec<__nv_bfloat16> &x) {
+    uint4 r;
+    r.x = pack_bf16x2(x.v[0], x.v[1]);
+    r.y = pack_bf16x2(x.v[2], x.v[3]);
+    r.z = pack_bf16x2(x.v[4], x.v[5]);
+    r.w = pack_bf16x2(x.v[6], x.v[7]);
+    *reinterpret_cast<uint4 *>(p) = r;
+}
+
+__device__ __forceinline__ float lrelu_sqrt2(float v) { return fmaxf(v, 0.2f * v) * kSqrt2; }
+
+}  // namespace ood

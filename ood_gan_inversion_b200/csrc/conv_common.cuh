@@ -1,0 +1,70 @@
+// Shared description of a 3x3 convolution as "phases" of an implicit GEMM.
+//
+// A phase is a dense problem  out[b, oy*sy+py, ox*sx+px, :] = sum_t  W[tap_w[t]] . in[b, oy+dy[t], ox+dx[t], :]
+// with zero padding outside the input.  The stride-1 pad-1 convolution (model.py:268-272) is one phase with nine
+// taps; the stride-2 transposed convolution (model.py:246-256) is four phases (output row/column parity) with
+// 4 + 2 + 2 + 1 = 9 taps in total -- the same FLOPs as the reference, no multiplications by inserted zeros.
+#pragma once
+#include "common.cuh"
+
+namespace ood {
+
+struct ConvPhase {
+    int oh, ow;           // phase output grid
+    int py, px;           // output offset
+    int ntaps;
+    int dy[9], dx[9], wt[9];
+    int m_total;          // batch * oh * ow
+};
+
+struct ConvGeom {
+    int batch, h, w, cin, cout;
+    int OH, OW;           // full output size
+    int sy, sx;           // output stride of a phase (1 or 2)
+    int nphases;
+    ConvPhase ph[4];
+};
+
+static inline ConvGeom make_geom(int batch, int h, int w, int cin, int cout, int transposed) {
+    ConvGeom g{};
+    g.batch = batch; g.h = h; g.w = w; g.cin = cin; g.cout = cout;
+    if (!transposed) {
+        g.OH = h; g.OW = w; g.sy = g.sx = 1; g.nphases = 1;
+        ConvPhase &p = g.ph[0];
+        p.oh = h; p.ow = w; p.py = p.px = 0; p.ntaps = 9;
+        for (int ky = 0; ky < 3; ++ky)
+            for (int kx = 0; kx < 3; ++kx) {
+                const int t = ky * 3 + kx;
+                p.dy[t] = ky - 1; p.dx[t] = kx - 1; p.wt[t] = t;
+            }
+        p.m_total = batch * h * w;
+    } else {
+        // out[Y,X] += in[y,x] * W[ky,kx] with Y = 2y+ky, X = 2x+kx  (conv_transpose2d, stride 2, no padding)
+        g.OH = 2 * h + 1; g.OW = 2 * w + 1; g.sy = g.sx = 2; g.nphases = 4;
+        for (int py = 0; py < 2; ++py)
+            for (int px = 0; px < 2; ++px) {
+                ConvPhase &p = g.ph[py * 2 + px];
+                p.oh = h + 1 - py; p.ow = w + 1 - px; p.py = py; p.px = px; p.ntaps = 0;
+                for (int ky = py; ky < 3; ky += 2)          // ky parity == Y parity
+                    for (int kx = px; kx < 3; kx += 2) {
+                        const int t = p.ntaps++;
+                        p.dy[t] = (ky == 2) ? -1 : 0;       // Y = 2*oy (+py): ky=0 -> y=oy, ky=2 -> y=oy-1, ky=1 -> y=oy
+                        p.dx[t] = (kx == 2) ? -1 : 0;
+                        p.wt[t] = ky * 3 + kx;
+                    }
+                p.m_total = batch * p.oh * p.ow;
+            }
+    }
+    return g;
+}
+
+// Fused StyledConv epilogue parameters (any pointer may be null).
+struct ConvEpilogue {
+    void *out_y, *out_ys;
+    const float *d, *noise, *noise_w, *bias, *s_next;
+    int64_t noise_bstride;
+    int act;
+    int out_f32;
+};
+
+}  // namespace ood

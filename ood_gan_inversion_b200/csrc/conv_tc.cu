@@ -1,0 +1,445 @@
+// 3x3 (transposed) convolution as an implicit GEMM on the 5th-generation tensor cores (sm_100a):
+//   tcgen05.mma (bf16 x bf16 -> fp32) issued by one thread, accumulators in TMEM (double buffered),
+//   operands staged by TMA into 128B/64B-swizzled shared memory through an mbarrier ring,
+//   persistent CTAs (one per SM) with warp roles: TMA producer / MMA issuer / 4 epilogue warps.
+//
+// Reference op: ModulatedConv2d.forward (src/ops/StyleGAN/model.py:233-274) -- there a cuDNN grouped conv over
+// B x Co x Ci x 3 x 3 materialised weights.  Here: M = output pixels of a phase (128-pixel rectangular patches so
+// that one TMA box [NB,TH,TW,BK] per tap IS the im2col tile; out-of-bounds box elements are zero-filled by TMA,
+// which implements the padding), N = Co, K = taps x Ci; weights are shared ([tap][Co][Ci] bf16, K-major), the
+// style modulation rides on the activations and demodulation / noise / bias / leaky-ReLU / next-layer style are
+// applied in the TMEM->register epilogue.
+#include <cuda.h>
+
+#include "conv_common.cuh"
+
+namespace ood {
+
+constexpr int TBM = 128;            // UMMA M
+constexpr int kTcThreads = 192;     // warp0 TMA, warp1 MMA (+TMEM alloc), warps 2..5 epilogue
+
+struct TcPhase {
+    int oh, ow, py, px, ntaps;
+    int dy[9], dx[9], wt[9];
+    int tiles_x, tiles_y, tiles_b;
+    int tile_begin;                 // first global tile id of this phase
+};
+
+struct TcParams {
+    int batch, h, w, cin, cout, OH, OW, sy, sx;
+    int TW, TH, NB;                 // pixel patch of one M tile: NB*TH*TW == 128
+    int nphases, n_tiles_n, total_tiles;
+    TcPhase ph[4];
+    ConvEpilogue ep;
+    int out_bf16;                   // storage type of out_y / out_ys
+};
+
+// ---------------------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t *holder_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(holder_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16 inputs, fp32 accumulate
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t *r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major operand tile, rows of SWZ bytes (SWZ = 128 or 64), 8-row swizzle atoms stacked contiguously.
+template <int SWZ>
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);                 // start address
+    d |= (uint64_t)1 << 16;                                 // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)((8 * SWZ) >> 4) << 32;                  // stride byte offset: one 8-row atom
+    d |= (uint64_t)1 << 46;                                 // descriptor version (sm_100)
+    d |= (uint64_t)(SWZ == 128 ? 2 : 4) << 61;              // SWIZZLE_128B / SWIZZLE_64B
+    return d;
+}
+
+template <int BN, int BK>
+struct TcCfg {
+    static constexpr int kABytes = TBM * BK * 2;
+    static constexpr int kBBytes = BN * BK * 2;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kStages = (200 * 1024 / kStageBytes) > 8 ? 8 : (200 * 1024 / kStageBytes);
+    static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
+};
+
+struct TileCoord {
+    int phase, b0, y0, x0, n0;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const TcParams &p, int tile, int BN) {
+    TileCoord tc;
+    int ph = 0;
+#pragma unroll
+    for (int i = 1; i < 4; ++i)
+        if (i < p.nphases && tile >= p.ph[i].tile_begin) ph = i;
+    const TcPhase &P = p.ph[ph];
+    const int local = tile - P.tile_begin;
+    const int nt = local % p.n_tiles_n, mt = local / p.n_tiles_n;
+    const int tx = mt % P.tiles_x, ty = (mt / P.tiles_x) % P.tiles_y, tb = mt / (P.tiles_x * P.tiles_y);
+    tc.phase = ph; tc.b0 = tb * p.NB; tc.y0 = ty * p.TH; tc.x0 = tx * p.TW; tc.n0 = nt * BN;
+    return tc;
+}
+
+template <int BN, int BK>
+__global__ void __launch_bounds__(kTcThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+    using Cfg = TcCfg<BN, BK>;
+    constexpr int S = Cfg::kStages;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t *sA = smem;
+    uint8_t *sB = smem + S * Cfg::kABytes;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + S * Cfg::kStageBytes);
+    uint64_t *full = bars, *empty = bars + S, *tfull = bars + 2 * S, *tempty = bars + 2 * S + 2;
+    uint32_t *tmem_holder = reinterpret_cast<uint32_t *>(bars + 2 * S + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kchunks = p.cin / BK;
+
+    if (warp == 0 && lane == 0) {
+        for (int i = 0; i < S; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+        fence_barrier_init();
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    }
+    if (warp == 1) tmem_alloc(tmem_holder, Cfg::kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+
+    if (warp == 0) {
+        // ===================================================== TMA producer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                const TileCoord tc = decode_tile(p, tile, BN);
+                const TcPhase &P = p.ph[tc.phase];
+                for (int t = 0; t < P.ntaps; ++t) {
+                    for (int kc = 0; kc < kchunks; ++kc) {
+                        mbar_wait(&empty[stage], phase ^ 1);
+                        mbar_expect_tx(&full[stage], Cfg::kStageBytes);
+                        tma_load_4d(sA + stage * Cfg::kABytes, &tmA, &full[stage], kc * BK, tc.x0 + P.dx[t], tc.y0 + P.dy[t], tc.b0);
+                        tma_load_3d(sB + stage * Cfg::kBBytes, &tmB, &full[stage], kc * BK, tc.n0, P.wt[t]);
+                        if (++stage == S) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================================== MMA issuer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                const TileCoord tc = decode_tile(p, tile, BN);
+                const int kiters = p.ph[tc.phase].ntaps * kchunks;
+                mbar_wait(&tempty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int it = 0; it < kiters; ++it) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint64_t da = make_smem_desc<BK * 2>(smem_u32(sA + stage * Cfg::kABytes));
+                    const uint64_t db = make_smem_desc<BK * 2>(smem_u32(sB + stage * Cfg::kBBytes));
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k)
+                        umma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), Cfg::kIdesc, (it | k) != 0);
+                    umma_commit(&empty[stage]);          // frees the smem slot when these MMAs retire
+                    if (++stage == S) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tfull[acc]);                // accumulator complete -> epilogue
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ===================================================== epilogue warps (TMEM lane quadrant = warp % 4)
+        const int quad = warp & 3;
+        const int row = quad * 32 + lane;
+        const int nb = row / (p.TH * p.TW), ty = (row / p.TW) % p.TH, tx = row % p.TW;
+        const float nw = (p.ep.noise && p.ep.noise_w) ? *p.ep.noise_w : 0.f;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            const TileCoord tc = decode_tile(p, tile, BN);
+            const TcPhase &P = p.ph[tc.phase];
+            const int b = tc.b0 + nb, oy = tc.y0 + ty, ox = tc.x0 + tx;
+            const bool valid = b < p.batch && oy < P.oh && ox < P.ow;
+            const int Y = oy * p.sy + P.py, X = ox * p.sx + P.px;
+            const int64_t pix = ((int64_t)b * p.OH + Y) * p.OW + X;
+            float nz = 0.f;
+            if (valid && p.ep.noise) nz = nw * __ldg(p.ep.noise + b * p.ep.noise_bstride + (int64_t)Y * p.OW + X);
+            mbar_wait(&tfull[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN;
+#pragma unroll 1
+            for (int ch = 0; ch < BN / 32; ++ch) {
+                uint32_t r[32];
+                tmem_ld32(taddr + ch * 32, r);
+                tmem_ld_wait();
+                if (valid) {
+                    const int n = tc.n0 + ch * 32;
+                    float v[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                    if (p.ep.d) {
+                        const float4 *dp = reinterpret_cast<const float4 *>(p.ep.d + (int64_t)b * p.cout + n);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 t = __ldg(dp + j);
+                            v[4 * j] *= t.x; v[4 * j + 1] *= t.y; v[4 * j + 2] *= t.z; v[4 * j + 3] *= t.w;
+                        }
+                    }
+                    if (p.ep.bias) {
+                        const float4 *bp = reinterpret_cast<const float4 *>(p.ep.bias + n);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 t = __ldg(bp + j);
+                            v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
+                        }
+                    }
+                    if (p.ep.act) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = lrelu_sqrt2(v[j] + nz);
+                    } else if (p.ep.noise) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] += nz;
+                    }
+                    if (p.ep.out_y) {
+                        if (p.ep.out_f32) {
+                            float4 *o = reinterpret_cast<float4 *>((float *)p.ep.out_y + pix * p.cout + n);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                        } else {
+                            uint4 *o = reinterpret_cast<uint4 *>((__nv_bfloat16 *)p.ep.out_y + pix * p.cout + n);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                o[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                                                  pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+                        }
+                    }
+                    if (p.ep.out_ys) {
+                        const float4 *sp = reinterpret_cast<const float4 *>(p.ep.s_next + (int64_t)b * p.cout + n);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 t = __ldg(sp + j);
+                            v[4 * j] *= t.x; v[4 * j + 1] *= t.y; v[4 * j + 2] *= t.z; v[4 * j + 3] *= t.w;
+                        }
+                        uint4 *o = reinterpret_cast<uint4 *>((__nv_bfloat16 *)p.ep.out_ys + pix * p.cout + n);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            o[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                                              pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+static int pow2_ceil(int v) { int r = 1; while (r < v) r <<= 1; return r; }
+
+template <int BN, int BK>
+static int launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, const TcParams &p, cudaStream_t st) {
+    using Cfg = TcCfg<BN, BK>;
+    auto kern = conv_tc_kernel<BN, BK>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+        if (e != cudaSuccess) { set_error("conv3x3 tc: smem attribute: %s", cudaGetErrorString(e)); return OOD_ERR_CUDA; }
+        attr_set = true;
+    }
+    int dev = 0, sms = kNumSMs;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int grid = std::min(p.total_tiles, sms);
+    kern<<<grid, kTcThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, p);
+    return check_launch("conv3x3 tc");
+}
+
+int conv3x3_tc(const ood_conv3x3_args &a, cudaStream_t st) {
+    OOD_REQUIRE(a.dtype == OOD_BF16, "conv3x3 tc: storage type must be bf16");
+    OOD_REQUIRE(a.cin % 32 == 0 && a.cout % 32 == 0, "conv3x3 tc: cin and cout must be multiples of 32 (got %d, %d)", a.cin, a.cout);
+    OOD_REQUIRE(((uintptr_t)a.in % 16 == 0) && ((uintptr_t)a.weight % 16 == 0), "conv3x3 tc: operands must be 16-byte aligned");
+    EncodeTiledFn encode = get_encode_fn();
+    if (!encode) { set_error("conv3x3 tc: cuTensorMapEncodeTiled is unavailable"); return OOD_ERR_CUDA; }
+
+    const ConvGeom g = make_geom(a.batch, a.h, a.w, a.cin, a.cout, a.transposed);
+    const int BK = (a.cin % 64 == 0) ? 64 : 32;
+    const int BN = a.cout % 256 == 0 ? 256 : (a.cout % 128 == 0 ? 128 : (a.cout % 64 == 0 ? 64 : 32));
+
+    TcParams p{};
+    p.batch = g.batch; p.h = g.h; p.w = g.w; p.cin = g.cin; p.cout = g.cout; p.OH = g.OH; p.OW = g.OW; p.sy = g.sy; p.sx = g.sx;
+    int ohm = 0, owm = 0;
+    for (int i = 0; i < g.nphases; ++i) { ohm = std::max(ohm, g.ph[i].oh); owm = std::max(owm, g.ph[i].ow); }
+    p.TW = std::min(pow2_ceil(owm), TBM);
+    p.TH = std::min(pow2_ceil(ohm), TBM / p.TW);
+    p.NB = TBM / (p.TW * p.TH);
+    p.nphases = g.nphases;
+    p.n_tiles_n = a.cout / BN;
+    int tiles = 0;
+    for (int i = 0; i < g.nphases; ++i) {
+        TcPhase &P = p.ph[i];
+        const ConvPhase &G = g.ph[i];
+        P.oh = G.oh; P.ow = G.ow; P.py = G.py; P.px = G.px; P.ntaps = G.ntaps;
+        for (int t = 0; t < 9; ++t) { P.dy[t] = G.dy[t]; P.dx[t] = G.dx[t]; P.wt[t] = G.wt[t]; }
+        P.tiles_x = ceil_div(G.ow, p.TW); P.tiles_y = ceil_div(G.oh, p.TH); P.tiles_b = ceil_div(g.batch, p.NB);
+        P.tile_begin = tiles;
+        tiles += P.tiles_x * P.tiles_y * P.tiles_b * p.n_tiles_n;
+    }
+    p.total_tiles = tiles;
+    p.ep = ConvEpilogue{a.out_y, a.out_ys, a.d, a.noise, a.noise_w, a.bias, a.s_next, a.noise_bstride, a.act, a.out_f32};
+    p.out_bf16 = 1;
+
+    CUtensorMap tmA, tmB;
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)a.cin, (cuuint64_t)a.w, (cuuint64_t)a.h, (cuuint64_t)a.batch};
+        cuuint64_t strides[3] = {(cuuint64_t)a.cin * 2, (cuuint64_t)a.w * a.cin * 2, (cuuint64_t)a.h * a.w * a.cin * 2};
+        cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)p.TW, (cuuint32_t)p.TH, (cuuint32_t)p.NB};
+        cuuint32_t es[4] = {1, 1, 1, 1};
+        CUresult r = encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(a.in), dims, strides, box, es,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("conv3x3 tc: activation tensor map encode failed (%d)", (int)r); return OOD_ERR_CUDA; }
+    }
+    {
+        cuuint64_t dims[3] = {(cuuint64_t)a.cin, (cuuint64_t)a.cout, 9};
+        cuuint64_t strides[2] = {(cuuint64_t)a.cin * 2, (cuuint64_t)a.cout * a.cin * 2};
+        cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)BN, 1};
+        cuuint32_t es[3] = {1, 1, 1};
+        CUresult r = encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void *>(a.weight), dims, strides, box, es,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("conv3x3 tc: weight tensor map encode failed (%d)", (int)r); return OOD_ERR_CUDA; }
+    }
+#define OOD_TC_CASE(bn, bk) if (BN == bn && BK == bk) return launch_tc<bn, bk>(tmA, tmB, p, st)
+    OOD_TC_CASE(256, 64); OOD_TC_CASE(128, 64); OOD_TC_CASE(64, 64); OOD_TC_CASE(32, 64);
+    OOD_TC_CASE(256, 32); OOD_TC_CASE(128, 32); OOD_TC_CASE(64, 32); OOD_TC_CASE(32, 32);
+#undef OOD_TC_CASE
+    set_error("conv3x3 tc: no kernel for BN=%d BK=%d", BN, BK);
+    return OOD_ERR_ARG;
+}
+
+}  // namespace ood
+
+namespace ood { int conv3x3_simt(const ood_conv3x3_args &a, cudaStream_t st); }
+
+extern "C" int ood_conv3x3(const ood_conv3x3_args *a, void *stream) {
+    using namespace ood;
+    OOD_REQUIRE(a && a->in && a->weight, "conv3x3: null pointer");
+    OOD_REQUIRE(a->batch > 0 && a->h > 0 && a->w > 0 && a->cin > 0 && a->cout > 0, "conv3x3: bad sizes");
+    OOD_REQUIRE(a->out_y || a->out_ys, "conv3x3: no output requested");
+    OOD_REQUIRE(!a->out_ys || a->s_next, "conv3x3: out_ys needs s_next");
+    OOD_REQUIRE(!a->transposed || (!a->out_ys && !a->act && !a->noise && !a->bias),
+                "conv3x3: the transposed form writes raw accumulators (the epilogue follows the blur)");
+    OOD_REQUIRE(!(a->out_f32 && a->out_ys), "conv3x3: out_f32 applies to out_y only");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (a->impl == 1) return conv3x3_simt(*a, st);
+    OOD_REQUIRE(a->impl == 0, "conv3x3: impl must be 0 (tcgen05) or 1 (simt)");
+    if (!ood_device_is_sm100()) { set_error("conv3x3: the tcgen05 path needs an sm_100 device"); return OOD_ERR_DEVICE; }
+    return conv3x3_tc(*a, st);
+}

@@ -1,0 +1,35 @@
+// Error state, version and device probe of libood_b200.
+#include "common.cuh"
+
+namespace ood {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int check_launch(const char *what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("%s: %s", what, cudaGetErrorString(e));
+        return OOD_ERR_CUDA;
+    }
+    return OOD_OK;
+}
+
+}  // namespace ood
+
+extern "C" int ood_version(void) { return 100; }
+
+extern "C" const char *ood_last_error(void) { return ood::g_err; }
+
+extern "C" int ood_device_is_sm100(void) {
+    int dev = 0, major = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
+    return major == 10;
+}

@@ -1,0 +1,236 @@
+// Spatial-alignment kernels: alignment-field step, flow warp + alpha mix, invertibility-mask compose + blend.
+// Reference: src/ops/SAMM/helpers.py:62-77 (new_PRM), :104-107 (tanh/sigmoid heads), :129-147 (add /
+// upsample_add), :154 (field blur), :168-177 (grid, grid_sample, mix); src/archs/OOD_faceGAN_e4e_arch.py:315-347
+// (blending_mask, blend).  All HBM-bound gathers / elementwise chains fused into one pass each.
+#include "common.cuh"
+
+namespace ood {
+
+// ------------------------------------------------------------------ field step
+constexpr int FT = 16;   // output tile edge
+
+__device__ __forceinline__ float cubic1(float x, float A) { return ((A + 2.f) * x - (A + 3.f)) * x * x + 1.f; }
+__device__ __forceinline__ float cubic2(float x, float A) { return ((A * x - 5.f * A) * x + 8.f * A) * x - 4.f * A; }
+
+// bicubic, align_corners=True, clamped taps (ATen UpSampleBicubic2d semantics)
+__device__ float bicubic_ac(const float *__restrict__ src, int rc, int r, int y, int x) {
+    const float A = -0.75f;
+    const float sc = (r > 1) ? (float)(rc - 1) / (float)(r - 1) : 0.f;
+    const float ry = sc * y, rx = sc * x;
+    const int iy = (int)floorf(ry), ix = (int)floorf(rx);
+    const float ty = ry - iy, tx = rx - ix;
+    const float cx[4] = {cubic2(tx + 1.f, A), cubic1(tx, A), cubic1(1.f - tx, A), cubic2(2.f - tx, A)};
+    const float cy[4] = {cubic2(ty + 1.f, A), cubic1(ty, A), cubic1(1.f - ty, A), cubic2(2.f - ty, A)};
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int yy = min(max(iy - 1 + j, 0), rc - 1);
+        float row = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int xx = min(max(ix - 1 + i, 0), rc - 1);
+            row += cx[i] * __ldg(src + (int64_t)yy * rc + xx);
+        }
+        acc += cy[j] * row;
+    }
+    return acc;
+}
+
+__global__ void __launch_bounds__(FT * FT) field_step_kernel(const float *__restrict__ z, const float *__restrict__ prev,
+                                                              const float *__restrict__ coarse, float *__restrict__ acc,
+                                                              float k0, float k1, float k2, float k3, float scale, int R,
+                                                              int Rc) {
+    __shared__ float sa[3][FT + 3][FT + 4];
+    const int b = blockIdx.z;
+    const int y0 = blockIdx.y * FT, x0 = blockIdx.x * FT;
+    const float *zb = z + (int64_t)b * 3 * R * R;
+    for (int i = threadIdx.x; i < 3 * (FT + 3) * (FT + 3); i += FT * FT) {
+        const int ch = i / ((FT + 3) * (FT + 3));
+        const int r = i % ((FT + 3) * (FT + 3));
+        const int ty = r / (FT + 3), tx = r % (FT + 3);
+        const int y = y0 + ty - 2, x = x0 + tx - 2;
+        float v = 0.f;
+        if (y >= 0 && y < R && x >= 0 && x < R) {
+            const float t = zb[((int64_t)ch * R + y) * R + x];
+            v = (ch < 2) ? tanhf(t) * scale : 1.f / (1.f + expf(-t));
+        }
+        sa[ch][ty][tx] = v;
+    }
+    __syncthreads();
+    const int ty = threadIdx.x / FT, tx = threadIdx.x % FT;
+    const int y = y0 + ty, x = x0 + tx;
+    if (y >= R || x >= R) return;
+    const float kf[4] = {k0, k1, k2, k3};
+    float f[3];
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+        float s = 0.f;
+#pragma unroll
+        for (int ky = 0; ky < 4; ++ky) {
+            float row = 0.f;
+#pragma unroll
+            for (int kx = 0; kx < 4; ++kx) row = fmaf(kf[kx], sa[ch][ty + ky][tx + kx], row);
+            s = fmaf(kf[ky], row, s);
+        }
+        f[ch] = s;
+    }
+    const int64_t o = (int64_t)b * 3 * R * R + (int64_t)y * R + x;
+    const int64_t pl = (int64_t)R * R;
+    if (prev) {
+        const float p0 = prev[o], p1 = prev[o + pl], p2 = prev[o + 2 * pl];
+        f[0] = fminf(fmaxf(p0 + f[0], -scale), scale);
+        f[1] = fminf(fmaxf(p1 + f[1], -scale), scale);
+        f[2] = fminf(fmaxf(f[2] * p2 + p2 * (1.f - p2), 0.f), 1.f);
+    }
+    if (coarse) {
+        const float u = bicubic_ac(coarse + ((int64_t)b * 3 + 2) * Rc * Rc, Rc, R, y, x);
+        f[2] = fminf(fmaxf(f[2] * u + u * (1.f - u), 0.f), 1.f);
+    }
+    acc[o] = f[0];
+    acc[o + pl] = f[1];
+    acc[o + 2 * pl] = f[2];
+}
+
+// ------------------------------------------------------------------ warp + alpha mix
+template <typename T>
+__global__ void __launch_bounds__(256) warp_mix_kernel(const T *__restrict__ gen, const float *__restrict__ field,
+                                                        T *__restrict__ out, int H, int W, int C) {
+    constexpr int N = Vec<T>::N;
+    const int cv = C / N;
+    const int b = blockIdx.y;
+    const int64_t P = (int64_t)H * W;
+    const float *fb = field + (int64_t)b * 3 * P;
+    const T *gb = gen + (int64_t)b * P * C;
+    const float stepx = W > 1 ? 2.f / (float)(W - 1) : 0.f, stepy = H > 1 ? 2.f / (float)(H - 1) : 0.f;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < P * cv; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t pix = i / cv;
+        const int c = (int)(i - pix * cv) * N;
+        const int y = (int)(pix / W), x = (int)(pix - (int64_t)y * W);
+        // torch.linspace(-1, 1, n): start + i*step in the first half, end - (n-1-i)*step in the second
+        const float lx = (x < W / 2) ? (-1.f + stepx * x) : (1.f - stepx * (W - 1 - x));
+        const float ly = (y < H / 2) ? (-1.f + stepy * y) : (1.f - stepy * (H - 1 - y));
+        const float gx = lx + __ldg(fb + pix), gy = ly + __ldg(fb + P + pix);
+        const float alpha = __ldg(fb + 2 * P + pix);
+        const float ix = ((gx + 1.f) * W - 1.f) * 0.5f, iy = ((gy + 1.f) * H - 1.f) * 0.5f;   // align_corners=False
+        const float fx0 = floorf(ix), fy0 = floorf(iy);
+        const int x0i = (int)fx0, y0i = (int)fy0;
+        const float wx1 = ix - fx0, wy1 = iy - fy0, wx0 = 1.f - wx1, wy0 = 1.f - wy1;
+        float accv[N];
+#pragma unroll
+        for (int j = 0; j < N; ++j) accv[j] = 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int xx = x0i + (q & 1), yy = y0i + (q >> 1);
+            if (xx < 0 || xx >= W || yy < 0 || yy >= H) continue;     // zeros padding
+            const float wgt = ((q & 1) ? wx1 : wx0) * ((q >> 1) ? wy1 : wy0);
+            const Vec<T> v = load_vec<T>(gb + ((int64_t)yy * W + xx) * C + c);
+#pragma unroll
+            for (int j = 0; j < N; ++j) accv[j] = fmaf(wgt, v.v[j], accv[j]);
+        }
+        const Vec<T> g = load_vec<T>(gb + pix * C + c);
+        Vec<T> o;
+#pragma unroll
+        for (int j = 0; j < N; ++j) o.v[j] = accv[j] * alpha + g.v[j] * (1.f - alpha);
+        store_vec<T>(out + ((int64_t)b * P + pix) * C + c, o);
+    }
+}
+
+// ------------------------------------------------------------------ mask compose + blend
+struct MaskParams {
+    const float *f[4];
+    int r[4];
+    int n;
+};
+
+__device__ __forceinline__ float bilinear_up(const float *__restrict__ a, int r, float scale, int y, int x) {
+    // ATen upsample_bilinear2d, align_corners=False
+    float sy = fmaxf(((float)y + 0.5f) * scale - 0.5f, 0.f), sx = fmaxf(((float)x + 0.5f) * scale - 0.5f, 0.f);
+    const int y0 = (int)sy, x0 = (int)sx;
+    const int y1 = y0 + (y0 < r - 1), x1 = x0 + (x0 < r - 1);
+    const float ly1 = sy - y0, lx1 = sx - x0, ly0 = 1.f - ly1, lx0 = 1.f - lx1;
+    return ly0 * (lx0 * __ldg(a + (int64_t)y0 * r + x0) + lx1 * __ldg(a + (int64_t)y0 * r + x1)) +
+           ly1 * (lx0 * __ldg(a + (int64_t)y1 * r + x0) + lx1 * __ldg(a + (int64_t)y1 * r + x1));
+}
+
+__global__ void __launch_bounds__(256) mask_blend_kernel(const MaskParams mp, const float *__restrict__ xin,
+                                                          const float *__restrict__ gen, float *__restrict__ out,
+                                                          float *__restrict__ alpha_out, int S) {
+    const int b = blockIdx.y;
+    const int64_t P = (int64_t)S * S;
+    const int64_t nq = P / 4;    // S % 4 == 0
+    for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < nq; q += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t pix = q * 4;
+        const int y = (int)(pix / S), x = (int)(pix - (int64_t)y * S);
+        float A[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float a = 0.f;
+            for (int k = 0; k < mp.n; ++k) {
+                const int r = mp.r[k];
+                const float u = bilinear_up(mp.f[k] + ((int64_t)b * 3 + 2) * r * r, r, (float)r / (float)S, y, x + j);
+                a = (k == 0) ? u : (u * a + a * (1.f - a));
+            }
+            A[j] = fminf(fmaxf(a, 0.f), 1.f);
+        }
+        if (alpha_out) *reinterpret_cast<float4 *>(alpha_out + (int64_t)b * P + pix) = make_float4(A[0], A[1], A[2], A[3]);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const int64_t o = ((int64_t)b * 3 + k) * P + pix;
+            const float4 xv = __ldg(reinterpret_cast<const float4 *>(xin + o));
+            const float4 gv = __ldg(reinterpret_cast<const float4 *>(gen + o));
+            float4 r;
+            r.x = A[0] * xv.x + gv.x * (1.f - A[0]);
+            r.y = A[1] * xv.y + gv.y * (1.f - A[1]);
+            r.z = A[2] * xv.z + gv.z * (1.f - A[2]);
+            r.w = A[3] * xv.w + gv.w * (1.f - A[3]);
+            *reinterpret_cast<float4 *>(out + o) = r;
+        }
+    }
+}
+
+}  // namespace ood
+
+extern "C" int ood_field_step(const float *z, const float *prev, const float *coarse, float *acc, const float *taps_host,
+                              float scale, int batch, int r, int rc, void *stream) {
+    using namespace ood;
+    OOD_REQUIRE(z && acc && taps_host && batch > 0 && batch <= 65535 && r > 0, "field_step: bad arguments");
+    OOD_REQUIRE(!coarse || rc > 0, "field_step: coarse needs its size");
+    dim3 grid(ceil_div(r, FT), ceil_div(r, FT), batch);
+    // correlation with the flipped taps (upfirdn2d.py:179)
+    field_step_kernel<<<grid, FT * FT, 0, (cudaStream_t)stream>>>(z, prev, coarse, acc, taps_host[3], taps_host[2],
+                                                                   taps_host[1], taps_host[0], scale, r, rc);
+    return check_launch("field_step");
+}
+
+extern "C" int ood_warp_mix(const void *gen, const float *field, void *out, int batch, int h, int w, int channels,
+                            int dtype, void *stream) {
+    using namespace ood;
+    OOD_REQUIRE(gen && field && out && batch > 0 && batch <= 65535 && h > 0 && w > 0, "warp_mix: bad arguments");
+    OOD_REQUIRE(dtype == OOD_F32 || dtype == OOD_BF16, "warp_mix: bad dtype");
+    const int N = dtype == OOD_F32 ? 4 : 8;
+    OOD_REQUIRE(channels % N == 0, "warp_mix: channels (%d) must be a multiple of %d", channels, N);
+    const int64_t work = (int64_t)h * w * (channels / N);
+    dim3 grid((unsigned)std::min<int64_t>((work + 255) / 256, kNumSMs * 16), batch);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == OOD_F32) warp_mix_kernel<float><<<grid, 256, 0, st>>>((const float *)gen, field, (float *)out, h, w, channels);
+    else warp_mix_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16 *)gen, field, (__nv_bfloat16 *)out, h, w, channels);
+    return check_launch("warp_mix");
+}
+
+extern "C" int ood_mask_blend(const float *const *fields_host, const int *field_sizes_host, int n_fields, const float *x,
+                              const float *gen, float *out, float *alpha_out, int batch, int size, void *stream) {
+    using namespace ood;
+    OOD_REQUIRE(fields_host && field_sizes_host && n_fields >= 1 && n_fields <= 4, "mask_blend: 1..4 fields supported");
+    OOD_REQUIRE(x && gen && out && batch > 0 && batch <= 65535 && size > 0 && size % 4 == 0, "mask_blend: bad arguments");
+    MaskParams mp{};
+    mp.n = n_fields;
+    for (int i = 0; i < n_fields; ++i) {
+        OOD_REQUIRE(fields_host[i] && field_sizes_host[i] > 0, "mask_blend: bad field %d", i);
+        mp.f[i] = fields_host[i];
+        mp.r[i] = field_sizes_host[i];
+    }
+    const int64_t nq = (int64_t)size * size / 4;
+    dim3 grid((unsigned)std::min<int64_t>((nq + 255) / 256, kNumSMs * 16), batch);
+    mask_blend_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(mp, x, gen, out, alpha_out, size);
+    return check_launch("mask_blend");
+}

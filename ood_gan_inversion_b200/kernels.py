@@ -1,0 +1,276 @@
+"""Tensor-level wrappers over the C ABI (include/ood_b200.h).  PyTorch is only the allocator / stream provider here.
+
+All functions require CUDA tensors; NHWC activations are plain contiguous [B,H,W,C] tensors (fp32 or bf16).
+"""
+import ctypes as C
+import math
+
+import torch
+
+from . import _lib
+from ._lib import BF16, F32, BlurActArgs, ConvArgs, check
+
+FIR_1331 = (1.0, 3.0, 3.0, 1.0)
+
+
+def _dt(t):
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise RuntimeError(f'ood_gan_inversion_b200: unsupported dtype {t.dtype} (float32 and bfloat16 only)')
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError('ood_gan_inversion_b200 is CUDA-only: got a CPU tensor (there is no CPU fallback)')
+
+
+def _f32c(t):
+    return None if t is None else t.detach().to(torch.float32).contiguous()
+
+
+def fir_taps(taps=FIR_1331, gain=1.0):
+    """1-D FIR taps normalised to sum `gain` (2-D kernel = outer product; model.py:19-27)."""
+    s = float(sum(taps))
+    return [float(t) / s * gain for t in taps]
+
+
+# ----------------------------------------------------------------------------------------------- boundary #2
+def upfirdn2d_nchw(x, kernel, up_x, up_y, down_x, down_y, px0, px1, py0, py1):
+    _cuda(x, kernel)
+    b, c, h, w = x.shape
+    kh, kw = kernel.shape
+    x = x.contiguous()
+    k = _f32c(kernel)
+    oh = (h * up_y + py0 + py1 - kh) // down_y + 1
+    ow = (w * up_x + px0 + px1 - kw) // down_x + 1
+    if oh <= 0 or ow <= 0:
+        raise RuntimeError(f'upfirdn2d: empty output {oh}x{ow}')
+    out = torch.empty(b, c, oh, ow, device=x.device, dtype=x.dtype)
+    check(_lib.lib().ood_upfirdn2d(_ptr(x), _ptr(out), _ptr(k), b * c, h, w, kh, kw, up_x, up_y, down_x, down_y,
+                                   px0, px1, py0, py1, _dt(x), _stream()), 'upfirdn2d')
+    return out
+
+
+def fused_bias_act(x, bias, refer, grad, alpha, scale):
+    """x: [B,C,...] contiguous; bias fp32 [C] or None; refer like x or None."""
+    _cuda(x, bias, refer)
+    x = x.contiguous()
+    out = torch.empty_like(x)
+    channels = x.shape[1] if x.dim() > 1 else 1
+    inner = 1
+    for s in x.shape[2:]:
+        inner *= s
+    bias = _f32c(bias)
+    refer = None if refer is None else refer.contiguous()
+    check(_lib.lib().ood_fused_bias_act(_ptr(x), _ptr(bias), _ptr(refer), _ptr(out), x.numel(), channels, inner, 3, grad,
+                                        float(alpha), float(scale), _dt(x), _stream()), 'fused_bias_act')
+    return out
+
+
+def bias_grad(g):
+    _cuda(g)
+    g = g.contiguous()
+    channels = g.shape[1]
+    inner = 1
+    for s in g.shape[2:]:
+        inner *= s
+    out = torch.empty(channels, device=g.device, dtype=torch.float32)
+    check(_lib.lib().ood_bias_grad(_ptr(g), _ptr(out), g.shape[0], channels, inner, _dt(g), _stream()), 'bias_grad')
+    return out
+
+
+# ----------------------------------------------------------------------------------------------- layout
+def nchw_to_nhwc(x, scale_bc=None, dtype=torch.bfloat16, batch=None):
+    """x: fp32 [B,C,H,W] (or [1,C,H,W] broadcast to `batch`) -> [B,H,W,C] `dtype`, times scale_bc[b,c]."""
+    _cuda(x, scale_bc)
+    x = _f32c(x)
+    b0, c, h, w = x.shape
+    b = batch or b0
+    bstride = 0 if (b0 == 1 and b > 1) else c * h * w
+    out = torch.empty(b, h, w, c, device=x.device, dtype=dtype)
+    check(_lib.lib().ood_nchw_to_nhwc(_ptr(x), bstride, _ptr(_f32c(scale_bc)), _ptr(out), b, c, h, w, _dt(out), _stream()),
+          'nchw_to_nhwc')
+    return out
+
+
+def nhwc_to_nchw(x):
+    _cuda(x)
+    x = x.contiguous()
+    b, h, w, c = x.shape
+    out = torch.empty(b, c, h, w, device=x.device, dtype=torch.float32)
+    check(_lib.lib().ood_nhwc_to_nchw(_ptr(x), _ptr(out), b, c, h, w, _dt(x), _stream()), 'nhwc_to_nchw')
+    return out
+
+
+def nhwc_scale(x, scale_bc):
+    _cuda(x, scale_bc)
+    x = x.contiguous()
+    b, h, w, c = x.shape
+    out = torch.empty_like(x)
+    check(_lib.lib().ood_nhwc_scale(_ptr(x), _ptr(_f32c(scale_bc)), _ptr(out), b, c, h * w, _dt(x), _stream()), 'nhwc_scale')
+    return out
+
+
+# ----------------------------------------------------------------------------------------------- modulation
+def weight_sumsq(w):
+    """w fp32 [Co,Ci,kh,kw] -> [Co,Ci]"""
+    _cuda(w)
+    w = _f32c(w)
+    co, ci = w.shape[:2]
+    out = torch.empty(co, ci, device=w.device, dtype=torch.float32)
+    check(_lib.lib().ood_weight_sumsq(_ptr(w), _ptr(out), co, ci, w.shape[2] * w.shape[3], _stream()), 'weight_sumsq')
+    return out
+
+
+def pack_conv_weight(w, dtype, ci_major):
+    """w fp32 [Co,Ci,kh,kw] -> [taps,Co,Ci] (`dtype`) or [taps,Ci,Co] fp32 (ci_major)."""
+    _cuda(w)
+    w = _f32c(w)
+    co, ci = w.shape[:2]
+    taps = w.shape[2] * w.shape[3]
+    shape = (taps, ci, co) if ci_major else (taps, co, ci)
+    out = torch.empty(shape, device=w.device, dtype=dtype)
+    check(_lib.lib().ood_pack_conv_weight(_ptr(w), _ptr(out), co, ci, taps, int(ci_major), _dt(out), _stream()),
+          'pack_conv_weight')
+    return out
+
+
+def modulation(latent, mod_w, mod_b, wsq, conv_scale, cout, want_d=True):
+    """latent [B,D] fp32 (row stride may exceed D) -> s [B,Ci], d [B,Co] (or None)."""
+    _cuda(latent, mod_w, mod_b, wsq)
+    assert latent.dim() == 2 and latent.stride(1) == 1 and latent.dtype == torch.float32
+    b, dim = latent.shape
+    cin = mod_w.shape[0]
+    s = torch.empty(b, cin, device=latent.device, dtype=torch.float32)
+    d = torch.empty(b, cout, device=latent.device, dtype=torch.float32) if want_d else None
+    check(_lib.lib().ood_modulation(_ptr(latent), latent.stride(0), _ptr(mod_w), _ptr(mod_b), _ptr(wsq), float(conv_scale),
+                                    _ptr(s), _ptr(d), b, dim, cin, cout, _stream()), 'modulation')
+    return s, d
+
+
+def torgb_weight(w, s):
+    """w fp32 [3,C], s [B,C] -> [B,3,C] = w*s/sqrt(C)"""
+    _cuda(w, s)
+    b, c = s.shape
+    out = torch.empty(b, 3, c, device=s.device, dtype=torch.float32)
+    check(_lib.lib().ood_torgb_weight(_ptr(w), _ptr(s), _ptr(out), b, c, _stream()), 'torgb_weight')
+    return out
+
+
+# ----------------------------------------------------------------------------------------------- convolution
+def conv3x3(x, weight, cout, transposed=False, impl=0, d=None, noise=None, noise_w=None, bias=None, s_next=None,
+            act=False, want_y=True, want_ys=False, out_f32=False):
+    """x NHWC [B,H,W,Ci] pre-modulated; weight packed for `impl`.  Returns (y, ys) (None where not requested)."""
+    _cuda(x, weight, d, noise, noise_w, bias, s_next)
+    assert x.is_contiguous()
+    b, h, w, cin = x.shape
+    oh, ow = (2 * h + 1, 2 * w + 1) if transposed else (h, w)
+    y = torch.empty(b, oh, ow, cout, device=x.device, dtype=torch.float32 if out_f32 else x.dtype) if want_y else None
+    ys = torch.empty(b, oh, ow, cout, device=x.device, dtype=x.dtype) if want_ys else None
+    nbs = 0
+    if noise is not None:
+        assert noise.dtype == torch.float32 and noise.is_contiguous() and noise.shape[-2:] == (oh, ow)
+        nbs = 0 if noise.shape[0] == 1 else oh * ow
+    a = ConvArgs(_ptr(x), _ptr(weight), _ptr(y), _ptr(ys), _ptr(d), _ptr(noise), nbs, _ptr(noise_w), _ptr(bias), _ptr(s_next),
+                 b, h, w, cin, cout, int(transposed), int(act), impl, _dt(x), int(out_f32))
+    check(_lib.lib().ood_conv3x3(C.byref(a), _stream()), 'conv3x3')
+    return y, ys
+
+
+def blur_act(t, taps, d=None, noise=None, noise_w=None, bias=None, s_next=None, act=True, want_img=False, want_y=True,
+             want_ys=False, dtype=None):
+    """t NHWC [B,IH,IW,C] (fp32 or storage dtype) -> blurred [B,IH-1,IW-1,C] (+ fused StyledConv tail)."""
+    _cuda(t, d, noise, noise_w, bias, s_next)
+    assert t.is_contiguous()
+    b, ih, iw, c = t.shape
+    dtype = dtype or t.dtype
+    mk = lambda: torch.empty(b, ih - 1, iw - 1, c, device=t.device, dtype=dtype)
+    img = mk() if want_img else None
+    y = mk() if (act and want_y) else None
+    ys = mk() if (act and want_ys) else None
+    nbs = 0
+    if noise is not None:
+        assert noise.dtype == torch.float32 and noise.is_contiguous()
+        nbs = 0 if noise.shape[0] == 1 else (ih - 1) * (iw - 1)
+    a = BlurActArgs(_ptr(t), int(t.dtype == torch.float32 and dtype != torch.float32), _ptr(img), _ptr(y), _ptr(ys), _ptr(d),
+                    _ptr(noise), _ptr(noise_w), _ptr(bias), _ptr(s_next), nbs, (C.c_float * 4)(*taps), b, ih, iw, c,
+                    int(act), F32 if dtype == torch.float32 else BF16)
+    check(_lib.lib().ood_blur_act(C.byref(a), _stream()), 'blur_act')
+    return img, y, ys
+
+
+def noise_act(img, noise, noise_w, bias, s_next=None, want_y=True, want_ys=False):
+    _cuda(img, noise, noise_w, bias, s_next)
+    assert img.is_contiguous()
+    b, h, w, c = img.shape
+    y = torch.empty_like(img) if want_y else None
+    ys = torch.empty_like(img) if want_ys else None
+    nbs = 0 if (noise is None or noise.shape[0] == 1) else h * w
+    check(_lib.lib().ood_noise_act(_ptr(img), _ptr(y), _ptr(ys), _ptr(noise), nbs, _ptr(noise_w), _ptr(bias), _ptr(s_next),
+                                   b, h * w, c, _dt(img), _stream()), 'noise_act')
+    return y, ys
+
+
+def torgb(y, wrgb, bias, skip=None, taps_up=None):
+    """y NHWC [B,H,W,C]; wrgb [B,3,C]; bias [3]; skip NCHW fp32 [B,3,H/2,W/2] -> NCHW fp32 [B,3,H,W]"""
+    _cuda(y, wrgb, bias, skip)
+    assert y.is_contiguous()
+    b, h, w, c = y.shape
+    out = torch.empty(b, 3, h, w, device=y.device, dtype=torch.float32)
+    taps = (C.c_float * 4)(*(taps_up or fir_taps(gain=2.0)))
+    check(_lib.lib().ood_torgb(_ptr(y), _ptr(wrgb), _ptr(_f32c(bias).reshape(-1)), _ptr(skip), _ptr(out), taps, b, h, w, c,
+                               _dt(y), _stream()), 'torgb')
+    return out
+
+
+# ----------------------------------------------------------------------------------------------- SAMM
+def field_step(z, prev, coarse, scale, taps=None):
+    _cuda(z, prev, coarse)
+    z = _f32c(z)
+    b, _, r, _ = z.shape
+    acc = torch.empty_like(z)
+    rc = coarse.shape[-1] if coarse is not None else 0
+    t = (C.c_float * 4)(*(taps or fir_taps()))
+    check(_lib.lib().ood_field_step(_ptr(z), _ptr(_f32c(prev)), _ptr(_f32c(coarse)), _ptr(acc), t, float(scale), b, r, rc,
+                                    _stream()), 'field_step')
+    return acc
+
+
+def warp_mix(gen, field):
+    """gen NHWC [B,H,W,C]; field fp32 [B,3,H,W] -> NHWC"""
+    _cuda(gen, field)
+    assert gen.is_contiguous()
+    b, h, w, c = gen.shape
+    out = torch.empty_like(gen)
+    check(_lib.lib().ood_warp_mix(_ptr(gen), _ptr(_f32c(field)), _ptr(out), b, h, w, c, _dt(gen), _stream()), 'warp_mix')
+    return out
+
+
+def mask_blend(fields, x, gen, want_alpha=True):
+    """fields: list of fp32 [B,3,r,r] ascending; x, gen NCHW fp32 [B,3,S,S] -> (out, alpha [B,1,S,S])"""
+    _cuda(x, gen, *fields)
+    fields = [_f32c(f) for f in fields]
+    x, gen = _f32c(x), _f32c(gen)
+    b, _, s, _ = x.shape
+    out = torch.empty_like(x)
+    alpha = torch.empty(b, 1, s, s, device=x.device, dtype=torch.float32) if want_alpha else None
+    n = len(fields)
+    ptrs = (C.c_void_p * n)(*[f.data_ptr() for f in fields])
+    sizes = (C.c_int * n)(*[f.shape[-1] for f in fields])
+    check(_lib.lib().ood_mask_blend(ptrs, sizes, n, _ptr(x), _ptr(gen), _ptr(out), _ptr(alpha), b, s, _stream()), 'mask_blend')
+    return out, alpha
+
+
+def conv_scale(cin, k):
+    return 1.0 / math.sqrt(cin * k * k)

@@ -1,0 +1,354 @@
+"""GPU parity tests: every C-ABI kernel against the oracle (oracle/) on seeded inputs.  Run with -m gpu on a B200."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import ops as oops, samm as osamm, stylegan as ostyle
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+
+
+@pytest.fixture(scope='module', autouse=True)
+def _no_tf32():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+
+
+def K():
+    from ood_gan_inversion_b200 import kernels
+    return kernels
+
+
+def g(seed):
+    return torch.Generator().manual_seed(seed)
+
+
+def rnd(*shape, seed=0):
+    return torch.randn(*shape, generator=g(seed))
+
+
+def nhwc(x, dtype):
+    return x.permute(0, 2, 3, 1).contiguous().to(dtype).to(DEV)
+
+
+def nchw(x):
+    return x.float().permute(0, 3, 1, 2).contiguous().cpu()
+
+
+# ----------------------------------------------------------------------------------------------- upfirdn2d
+def test_upfirdn2d_golden_cases(golden):
+    for c in golden('ops.pt')['upfirdn2d']:
+        p = c['pad']
+        y = K().upfirdn2d_nchw(c['x'].to(DEV), c['k'].to(DEV), c['up'], c['up'], c['down'], c['down'], p[0], p[1], p[0], p[1])
+        torch.testing.assert_close(y.cpu(), c['y'], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize('cfg', [
+    dict(shape=(2, 3, 65, 65), up=1, down=1, pad=(1, 1), gain=4.0),       # conv-up blur, odd width
+    dict(shape=(2, 3, 32, 32), up=2, down=1, pad=(2, 1), gain=4.0),       # rgb skip upsample
+    dict(shape=(1, 4, 64, 48), up=1, down=2, pad=(1, 1), gain=1.0),       # down2
+    dict(shape=(1, 2, 100, 130), up=1, down=1, pad=(2, 1), gain=1.0),     # multi-tile, ragged
+    dict(shape=(1, 2, 19, 23), up=3, down=2, pad=(4, 3), gain=9.0),       # generic path
+    dict(shape=(1, 1, 1, 1), up=2, down=1, pad=(2, 1), gain=4.0),         # smallest input
+])
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_upfirdn2d_vs_oracle(cfg, dtype):
+    x = rnd(*cfg['shape'], seed=3).to(dtype)
+    k = oops.fir_kernel([1, 3, 3, 1], cfg['gain'])
+    ref = oops.upfirdn2d(x.float(), k, cfg['up'], cfg['down'], cfg['pad'])
+    p = cfg['pad']
+    y = K().upfirdn2d_nchw(x.to(DEV), k.to(DEV), cfg['up'], cfg['up'], cfg['down'], cfg['down'], p[0], p[1], p[0], p[1])
+    assert y.dtype == dtype and y.shape == ref.shape
+    tol = dict(rtol=1e-5, atol=1e-5) if dtype == torch.float32 else dict(rtol=1e-2, atol=1e-2)
+    torch.testing.assert_close(y.float().cpu(), ref, **tol)
+
+
+def test_upfirdn2d_asymmetric_kernel_and_axes():
+    x = rnd(2, 2, 11, 9, seed=5)
+    k = rnd(3, 5, seed=6)
+    ref = oops.upfirdn2d_xy(x, k, 2, 1, 1, 2, 3, 1, 0, 2)
+    y = K().upfirdn2d_nchw(x.to(DEV), k.to(DEV), 2, 1, 1, 2, 3, 1, 0, 2)
+    torch.testing.assert_close(y.cpu(), ref, rtol=1e-5, atol=1e-5)
+
+
+def test_upfirdn2d_linearity_at_full_size():
+    # size-independent property at a BASELINE size: up2(a*x + y) == a*up2(x) + up2(y)
+    x, y = torch.randn(1, 3, 512, 512, device=DEV), torch.randn(1, 3, 512, 512, device=DEV)
+    k = oops.fir_kernel([1, 3, 3, 1], 4.0).to(DEV)
+    f = lambda t: K().upfirdn2d_nchw(t, k, 2, 2, 1, 1, 2, 1, 2, 1)
+    torch.testing.assert_close(f(2.5 * x + y), 2.5 * f(x) + f(y), rtol=1e-4, atol=1e-4)
+    assert f(x).shape == (1, 3, 1024, 1024)
+    # DC gain: a constant image stays constant away from the border
+    c = f(torch.ones(1, 1, 64, 64, device=DEV))
+    torch.testing.assert_close(c[..., 4:-4, 4:-4], torch.ones_like(c[..., 4:-4, 4:-4]))
+
+
+# ----------------------------------------------------------------------------------------------- bias act
+@pytest.mark.parametrize('shape', [(2, 6, 5, 7), (3, 8), (2, 4, 16, 16), (1, 3, 1, 1)])
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_fused_bias_act(shape, dtype):
+    x = rnd(*shape, seed=1).to(dtype)
+    b = rnd(shape[1], seed=2)
+    ref = oops.fused_leaky_relu(x.float(), b)
+    y = K().fused_bias_act(x.to(DEV), b.to(DEV), None, 0, 0.2, math.sqrt(2))
+    tol = dict(rtol=1e-6, atol=1e-6) if dtype == torch.float32 else dict(rtol=1e-2, atol=1e-2)
+    torch.testing.assert_close(y.float().cpu(), ref, **tol)
+    if dtype == torch.float32:
+        gout = rnd(*shape, seed=4)
+        gx_ref, gb_ref = oops.fused_leaky_relu_backward(gout, ref)
+        gx = K().fused_bias_act(gout.to(DEV), None, y, 1, 0.2, math.sqrt(2))
+        torch.testing.assert_close(gx.cpu(), gx_ref, rtol=1e-6, atol=1e-6)
+        torch.testing.assert_close(K().bias_grad(gx).cpu(), gb_ref, rtol=1e-4, atol=1e-5)
+        assert float(K().fused_bias_act(gout.to(DEV), None, y, 2, 0.2, 1.0).abs().max()) == 0.0
+
+
+def test_fused_bias_act_golden(golden):
+    for c in golden('ops.pt')['fused_leaky_relu']:
+        y = K().fused_bias_act(c['x'].to(DEV), c['b'].to(DEV), None, 0, 0.2, math.sqrt(2))
+        torch.testing.assert_close(y.cpu(), c['y'], rtol=1e-6, atol=1e-6)
+
+
+# ----------------------------------------------------------------------------------------------- layout / modulation
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_layout_roundtrip_and_scale(dtype):
+    x = rnd(3, 40, 5, 7, seed=1)
+    s = rnd(3, 40, seed=2)
+    y = K().nchw_to_nhwc(x.to(DEV), s.to(DEV), dtype)
+    ref = (x * s[:, :, None, None]).permute(0, 2, 3, 1)
+    tol = dict(rtol=1e-6, atol=1e-6) if dtype == torch.float32 else dict(rtol=1e-2, atol=1e-2)
+    torch.testing.assert_close(y.float().cpu(), ref, **tol)
+    back = K().nhwc_to_nchw(K().nchw_to_nhwc(x.to(DEV), None, dtype))
+    torch.testing.assert_close(back.cpu(), x.to(dtype).float())
+    const = rnd(1, 64, 4, 4, seed=3)
+    yb = K().nchw_to_nhwc(const.to(DEV), rnd(5, 64, seed=4).to(DEV), dtype, batch=5)
+    assert yb.shape == (5, 4, 4, 64)
+    z = K().nhwc_scale(y, s.to(DEV))
+    torch.testing.assert_close(z.float().cpu(), (y.float().cpu() * s[:, None, None, :]).to(dtype).float(), **tol)
+
+
+def test_modulation_and_demod():
+    b, D, ci, co = 3, 512, 96, 64
+    lat = rnd(b, 18, D, seed=1).to(DEV)
+    mw, mb, w = rnd(ci, D, seed=2), 1 + 0.1 * rnd(ci, seed=3), rnd(co, ci, 3, 3, seed=4)
+    wsq = K().weight_sumsq(w.to(DEV))
+    torch.testing.assert_close(wsq.cpu(), w.pow(2).sum([2, 3]), rtol=1e-5, atol=1e-5)
+    cs = 1 / math.sqrt(ci * 9)
+    s, d = K().modulation(lat[:, 5], mw.to(DEV), mb.to(DEV), wsq, cs, co)
+    s_ref = ostyle.equal_linear(lat[:, 5].cpu(), mw, mb)
+    wb = cs * w[None] * s_ref[:, None, :, None, None]
+    d_ref = cs * torch.rsqrt(wb.pow(2).sum([2, 3, 4]) + 1e-8)
+    torch.testing.assert_close(s.cpu(), s_ref, rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(d.cpu(), d_ref, rtol=1e-4, atol=1e-7)
+    _, d1 = K().modulation(lat[:, 5], mw.to(DEV), mb.to(DEV), None, cs, co)
+    torch.testing.assert_close(d1.cpu(), torch.full((b, co), cs))
+    for ci_major in (False, True):
+        pk = K().pack_conv_weight(w.to(DEV), torch.float32, ci_major).cpu()
+        ref = w.reshape(co, ci, 9).permute(2, 1, 0) if ci_major else w.reshape(co, ci, 9).permute(2, 0, 1)
+        torch.testing.assert_close(pk, ref.contiguous())
+
+
+# ----------------------------------------------------------------------------------------------- convolution
+CONV_CASES = [
+    dict(b=2, h=16, w=16, ci=64, co=64),
+    dict(b=3, h=4, w=4, ci=128, co=64),        # several samples per 128-pixel tile
+    dict(b=1, h=32, w=32, ci=128, co=256),     # BN = 256
+    dict(b=2, h=20, w=12, ci=64, co=128),      # ragged patch grid
+    dict(b=1, h=8, w=136, ci=32, co=32),       # BK = 32 (64B swizzle), 128-wide row tiles + remainder
+    dict(b=5, h=8, w=8, ci=64, co=96),         # BN = 32 path with 3 N tiles, batch remainder
+]
+
+
+def conv_ref(x, w, transposed):
+    if transposed:
+        return F.conv_transpose2d(x, w.transpose(0, 1), stride=2)
+    return F.conv2d(x, w, padding=1)
+
+
+@pytest.mark.parametrize('case', CONV_CASES)
+@pytest.mark.parametrize('transposed', [False, True])
+def test_conv3x3_simt_raw(case, transposed):
+    b, h, w_, ci, co = case['b'], case['h'], case['w'], case['ci'], case['co']
+    if ci % 16 or co % 4:
+        pytest.skip('simt alignment')
+    x, w = rnd(b, ci, h, w_, seed=1), rnd(co, ci, 3, 3, seed=2)
+    wp = K().pack_conv_weight(w.to(DEV), torch.float32, True)
+    y, _ = K().conv3x3(nhwc(x, torch.float32), wp, co, transposed=transposed, impl=1)
+    ref = conv_ref(x.double(), w.double(), transposed).float()
+    torch.testing.assert_close(nchw(y), ref, rtol=1e-4, atol=1e-3)
+
+
+@pytest.mark.parametrize('case', CONV_CASES)
+@pytest.mark.parametrize('transposed', [False, True])
+def test_conv3x3_tcgen05_raw(case, transposed):
+    b, h, w_, ci, co = case['b'], case['h'], case['w'], case['ci'], case['co']
+    x, w = rnd(b, ci, h, w_, seed=1).bfloat16().float(), rnd(co, ci, 3, 3, seed=2).bfloat16().float()
+    wp = K().pack_conv_weight(w.to(DEV), torch.bfloat16, False)
+    y, _ = K().conv3x3(nhwc(x, torch.bfloat16), wp, co, transposed=transposed, impl=0, out_f32=True)
+    ref = conv_ref(x.double(), w.double(), transposed).float()      # same bf16-rounded operands, exact products
+    torch.testing.assert_close(nchw(y), ref, rtol=1e-4, atol=2e-3)
+    yb, _ = K().conv3x3(nhwc(x, torch.bfloat16), wp, co, transposed=transposed, impl=0)
+    assert yb.dtype == torch.bfloat16
+    torch.testing.assert_close(nchw(yb), ref, rtol=1e-2, atol=0.15)
+
+
+@pytest.mark.parametrize('impl', [0, 1])
+def test_conv3x3_fused_epilogue(impl):
+    b, h, w_, ci, co = 3, 16, 16, 64, 128
+    dt = torch.bfloat16 if impl == 0 else torch.float32
+    x, w = rnd(b, ci, h, w_, seed=1).to(dt).float(), rnd(co, ci, 3, 3, seed=2).to(dt).float()
+    d, bias, s_next = 0.05 * (1 + rnd(b, co, seed=3).abs()), rnd(co, seed=4), 1 + 0.3 * rnd(b, co, seed=5)
+    noise, nw = rnd(b, 1, h, w_, seed=6), torch.tensor([0.37])
+    wp = K().pack_conv_weight(w.to(DEV), dt, impl == 1)
+    y, ys = K().conv3x3(nhwc(x, dt), wp, co, impl=impl, d=d.to(DEV), noise=noise.to(DEV), noise_w=nw.to(DEV),
+                        bias=bias.to(DEV), s_next=s_next.to(DEV), act=True, want_y=True, want_ys=True)
+    ref = F.conv2d(x.double(), w.double(), padding=1).float() * d[:, :, None, None] + nw * noise
+    ref = oops.fused_leaky_relu(ref, bias)
+    tol = dict(rtol=2e-2, atol=3e-2) if impl == 0 else dict(rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(nchw(y), ref, **tol)
+    torch.testing.assert_close(nchw(ys), ref * s_next[:, :, None, None], **tol)
+    # shared noise plane (registered buffers, batch stride 0)
+    y1, _ = K().conv3x3(nhwc(x, dt), wp, co, impl=impl, d=d.to(DEV), noise=noise[:1].contiguous().to(DEV), noise_w=nw.to(DEV),
+                        bias=bias.to(DEV), act=True)
+    ref1 = oops.fused_leaky_relu(F.conv2d(x.double(), w.double(), padding=1).float() * d[:, :, None, None] + nw * noise[:1], bias)
+    torch.testing.assert_close(nchw(y1), ref1, **tol)
+
+
+def test_conv3x3_tc_matches_simt_large():
+    # tensor-core path against the fp32 SIMT path on the device at a generator-sized layer (64x64, 512 channels)
+    b, h, ci, co = 2, 64, 512, 512
+    x = torch.randn(b, h, h, ci, device=DEV).bfloat16()
+    w = torch.randn(co, ci, 3, 3, device=DEV).bfloat16().float()
+    y_tc, _ = K().conv3x3(x, K().pack_conv_weight(w, torch.bfloat16, False), co, impl=0, out_f32=True)
+    y_si, _ = K().conv3x3(x.float(), K().pack_conv_weight(w, torch.float32, True), co, impl=1)
+    torch.testing.assert_close(y_tc, y_si, rtol=1e-3, atol=2e-2)
+    t_tc, _ = K().conv3x3(x, K().pack_conv_weight(w, torch.bfloat16, False), co, transposed=True, impl=0, out_f32=True)
+    t_si, _ = K().conv3x3(x.float(), K().pack_conv_weight(w, torch.float32, True), co, transposed=True, impl=1)
+    torch.testing.assert_close(t_tc, t_si, rtol=1e-3, atol=2e-2)
+
+
+def test_modulated_conv_identity_vs_oracle():
+    # (W*s*d) (*) x == d . (W (*) (s . x)): the kernels' formulation against the reference's (oracle) formulation
+    b, ci, co, h = 2, 64, 32, 12
+    x, style = rnd(b, ci, h, h, seed=1), rnd(b, 512, seed=2)
+    w, mw, mb = rnd(1, co, ci, 3, 3, seed=3), rnd(ci, 512, seed=4), torch.ones(ci)
+    ref = ostyle.modulated_conv2d(x, style, w, mw, mb)
+    wsq = K().weight_sumsq(w[0].to(DEV))
+    s, d = K().modulation(style.to(DEV), mw.to(DEV), mb.to(DEV), wsq, 1 / math.sqrt(ci * 9), co)
+    xs = K().nchw_to_nhwc(x.to(DEV), s, torch.float32)
+    y, _ = K().conv3x3(xs, K().pack_conv_weight(w[0].to(DEV), torch.float32, True), co, impl=1, d=d)
+    torch.testing.assert_close(nchw(y), ref, rtol=1e-4, atol=1e-4)
+    ref_up = ostyle.modulated_conv2d(x, style, w, mw, mb, upsample=True, blur_k=oops.fir_kernel([1, 3, 3, 1], 4.0), blur_pad=(1, 1))
+    t, _ = K().conv3x3(xs, K().pack_conv_weight(w[0].to(DEV), torch.float32, True), co, transposed=True, impl=1)
+    img, _, _ = K().blur_act(t, K().fir_taps(gain=2.0), d=d, act=False, want_img=True)
+    torch.testing.assert_close(nchw(img), ref_up, rtol=1e-4, atol=1e-4)
+
+
+# ----------------------------------------------------------------------------------------------- blur + epilogue, torgb
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('shape', [(2, 32, 9, 9), (1, 64, 33, 17), (2, 8, 65, 65)])
+def test_blur_act(dtype, shape):
+    b, c, ih, iw = shape
+    if dtype == torch.float32 and c % 4 or dtype == torch.bfloat16 and c % 8:
+        pytest.skip('vector width')
+    t = rnd(b, c, ih, iw, seed=1).to(dtype).float()
+    d, bias, s_next = 0.5 + rnd(b, c, seed=2).abs(), rnd(c, seed=3), 1 + 0.3 * rnd(b, c, seed=4)
+    noise, nw = rnd(b, 1, ih - 1, iw - 1, seed=5), torch.tensor([0.21])
+    img_ref = oops.upfirdn2d(t, oops.fir_kernel([1, 3, 3, 1], 4.0), pad=(1, 1)) * d[:, :, None, None]
+    y_ref = oops.fused_leaky_relu(img_ref + nw * noise, bias)
+    img, y, ys = K().blur_act(nhwc(t, dtype), K().fir_taps(gain=2.0), d=d.to(DEV), noise=noise.to(DEV), noise_w=nw.to(DEV),
+                              bias=bias.to(DEV), s_next=s_next.to(DEV), act=True, want_img=True, want_y=True, want_ys=True)
+    tol = dict(rtol=1e-5, atol=1e-5) if dtype == torch.float32 else dict(rtol=2e-2, atol=2e-2)
+    torch.testing.assert_close(nchw(img), img_ref, **tol)
+    torch.testing.assert_close(nchw(y), y_ref, **tol)
+    torch.testing.assert_close(nchw(ys), y_ref * s_next[:, :, None, None], **tol)
+    if dtype == torch.bfloat16:   # fp32 accumulators in, bf16 activations out
+        _, y2, _ = K().blur_act(nhwc(t, torch.float32), K().fir_taps(gain=2.0), d=d.to(DEV), noise=noise.to(DEV),
+                                noise_w=nw.to(DEV), bias=bias.to(DEV), act=True, dtype=torch.bfloat16)
+        assert y2.dtype == torch.bfloat16
+        torch.testing.assert_close(nchw(y2), y_ref, **tol)
+    y3, ys3 = K().noise_act(nhwc(img_ref, dtype), noise.to(DEV), nw.to(DEV), bias.to(DEV), s_next.to(DEV), True, True)
+    torch.testing.assert_close(nchw(y3), y_ref, **tol)
+    torch.testing.assert_close(nchw(ys3), y_ref * s_next[:, :, None, None], **tol)
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('c,h', [(32, 16), (512, 8), (64, 34)])
+def test_torgb(dtype, c, h):
+    b = 2
+    y = rnd(b, c, h, h, seed=1).to(dtype).float()
+    w, s, bias, skip = rnd(3, c, seed=2), 1 + 0.3 * rnd(b, c, seed=3), rnd(3, seed=4), rnd(b, 3, h // 2, h // 2, seed=5)
+    wrgb = K().torgb_weight(w.to(DEV), s.to(DEV))
+    ref = torch.einsum('bchw,bkc->bkhw', y, w[None] * s[:, None, :] / math.sqrt(c)) + bias.reshape(1, 3, 1, 1)
+    out0 = K().torgb(nhwc(y, dtype), wrgb, bias.to(DEV))
+    tol = dict(rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(out0.cpu(), ref, **tol)
+    ref = ref + oops.upfirdn2d(skip, oops.fir_kernel([1, 3, 3, 1], 4.0), up=2, pad=(2, 1))
+    out = K().torgb(nhwc(y, dtype), wrgb, bias.to(DEV), skip.to(DEV))
+    torch.testing.assert_close(out.cpu(), ref, **tol)
+
+
+# ----------------------------------------------------------------------------------------------- SAMM kernels
+@pytest.mark.parametrize('r', [12, 32, 50])
+def test_field_step(r):
+    b, scale = 2, 0.08
+    z, prev = rnd(b, 3, r, r, seed=1), None
+    k = oops.fir_kernel([1, 3, 3, 1])
+
+    def heads(z):
+        return torch.cat([torch.tanh(z[:, 0:1]) * scale, torch.tanh(z[:, 1:2]) * scale, torch.sigmoid(z[:, 2:])], 1)
+
+    f1 = oops.upfirdn2d(heads(z), k, pad=(2, 1))
+    a1 = K().field_step(z.to(DEV), None, None, scale)
+    torch.testing.assert_close(a1.cpu(), f1, rtol=1e-5, atol=1e-6)
+    z2 = rnd(b, 3, r, r, seed=2)
+    f2 = oops.upfirdn2d(heads(z2), k, pad=(2, 1))
+    acc = torch.cat([torch.clip(f1[:, 0:1] + f2[:, 0:1], -scale, scale), torch.clip(f1[:, 1:2] + f2[:, 1:2], -scale, scale),
+                     torch.clip(osamm.prm(f1[:, 2:], f2[:, 2:]), 0, 1)], 1)
+    coarse = torch.rand(b, 3, r // 2, r // 2, generator=g(3))
+    acc_c = torch.cat([acc[:, :2], torch.clip(osamm.prm(coarse[:, 2:], acc[:, 2:]), 0, 1)], 1)
+    a2 = K().field_step(z2.to(DEV), a1, None, scale)
+    torch.testing.assert_close(a2.cpu(), acc, rtol=1e-5, atol=1e-6)
+    a3 = K().field_step(z2.to(DEV), a1, coarse.to(DEV), scale)
+    torch.testing.assert_close(a3.cpu(), acc_c, rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('shape', [(2, 16, 12, 12), (1, 64, 32, 20)])
+def test_warp_mix(dtype, shape):
+    b, c, h, w = shape
+    gen = rnd(b, c, h, w, seed=1).to(dtype).float()
+    field = torch.cat([0.3 * rnd(b, 2, h, w, seed=2), torch.rand(b, 1, h, w, generator=g(3))], 1)   # large flow: hits the border
+    ref = osamm.warp_mix(gen, field)
+    out = K().warp_mix(nhwc(gen, dtype), field.to(DEV))
+    tol = dict(rtol=1e-4, atol=1e-4) if dtype == torch.float32 else dict(rtol=2e-2, atol=2e-2)
+    torch.testing.assert_close(nchw(out), ref, **tol)
+
+
+def test_mask_blend():
+    b, size = 2, 64
+    fields = [torch.rand(b, 3, r, r, generator=g(r)) for r in (4, 8, 16, 32)]
+    x, gen = rnd(b, 3, size, size, seed=1), rnd(b, 3, size, size, seed=2)
+    alpha = osamm.compose_masks(fields, size)
+    ref = osamm.blend(alpha, x, gen)
+    out, a = K().mask_blend([f.to(DEV) for f in fields], x.to(DEV), gen.to(DEV))
+    torch.testing.assert_close(a.cpu(), alpha, rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(out.cpu(), ref, rtol=1e-5, atol=1e-5)
+    out1, a1 = K().mask_blend([fields[1].to(DEV)], x.to(DEV), gen.to(DEV))
+    torch.testing.assert_close(a1.cpu(), osamm.compose_masks(fields[1:2], size), rtol=1e-5, atol=1e-5)
+    # idempotence-style property: blending an image with itself returns it
+    same, _ = K().mask_blend([f.to(DEV) for f in fields], x.to(DEV), x.to(DEV))
+    torch.testing.assert_close(same.cpu(), x, rtol=1e-6, atol=1e-6)
+
+
+def test_errors_are_loud():
+    with pytest.raises(RuntimeError):
+        K().upfirdn2d_nchw(torch.zeros(1, 1, 4, 4), torch.ones(2, 2), 1, 1, 1, 1, 0, 0, 0, 0)      # CPU tensor
+    with pytest.raises(RuntimeError):
+        K().upfirdn2d_nchw(torch.zeros(1, 1, 2, 2, device=DEV), torch.ones(4, 4, device=DEV), 1, 1, 1, 1, 0, 0, 0, 0)  # empty
+    with pytest.raises(RuntimeError):
+        K().conv3x3(torch.zeros(1, 4, 4, 24, device=DEV, dtype=torch.bfloat16), torch.zeros(9, 32, 24, device=DEV,
+                    dtype=torch.bfloat16), 32, impl=0)                                              # cin % 32
