@@ -1,0 +1,158 @@
+"""Drop-in for the reference's Spatial Alignment & Masking Module (src/ops/SAMM/helpers.py).
+
+Same module tree and state-dict keys (`alignment.body.body.{0,1}.{res_layer,shortcut_layer}.*`, `alignment.blur.kernel`,
+`weight`, `noiseInj.weight`).  The field head (tanh/sigmoid + FIR blur + accumulate/PRM/clip + coarse-level bicubic PRM),
+the flow warp + alpha mix and (in arch.py) the mask compose + blend are single fused sm_100a kernels; the AlignNet
+convolution stacks stay cuDNN library calls in this round ("next").
+"""
+import torch
+from torch import nn
+from torch.nn import functional as F
+
+from . import kernels as K
+from . import stylegan as sg
+from .stylegan import Blur, NoiseInjection
+
+
+def BN(depth, bn=True):
+    """src/ops/e4e/encoders/helpers.py:93-99"""
+    if bn == 'InstanceNorm':
+        return nn.InstanceNorm2d(depth, affine=True)
+    if bn == 'BatchNorm' or bn is True:
+        return nn.BatchNorm2d(depth)
+    return nn.Identity()
+
+
+class bottleneck_IR(nn.Module):
+    """src/ops/e4e/encoders/helpers.py:426-448"""
+
+    def __init__(self, in_channel, depth, stride, bn=True, bias=False):
+        super().__init__()
+        if in_channel == depth:
+            self.shortcut_layer = nn.MaxPool2d(1, stride)
+        else:
+            self.shortcut_layer = nn.Sequential(nn.Conv2d(in_channel, depth, (1, 1), stride, bias=bias), BN(depth, bn=bn))
+        self.res_layer = nn.Sequential(BN(in_channel, bn=bn), nn.Conv2d(in_channel, depth, (3, 3), (1, 1), 1, bias=bias),
+                                       nn.PReLU(depth), nn.Conv2d(depth, depth, (3, 3), stride, 1, bias=bias), BN(depth, bn=bn))
+
+    def forward(self, x):
+        return self.res_layer(x) + self.shortcut_layer(x)
+
+
+def scaleNshiftBlock(in_chn, out_chn, norm_type=False, bias=False):
+    """src/ops/SAMM/helpers.py:58-60"""
+    return nn.Sequential(bottleneck_IR(in_chn, in_chn, 1, bn=norm_type, bias=bias),
+                         bottleneck_IR(in_chn, out_chn, 1, bn=norm_type, bias=bias))
+
+
+def new_PRM(x, y, **kwargs):
+    """src/ops/SAMM/helpers.py:62-77 (torch form, API parity; the hot path uses ood_field_step)."""
+    if x.shape[-2:] != y.shape[-2:]:
+        x = F.interpolate(x, size=y.shape[-2:], mode='bicubic', align_corners=True)
+    return y * x + x * (1 - x)
+
+
+class AlignNet(nn.Module):
+    """src/ops/SAMM/helpers.py:85-109"""
+
+    def __init__(self, in_chn, out_chn=3, scale=1., blur_kernel=[1, 3, 3, 1], **kwargs):
+        super().__init__()
+        self.norm = nn.InstanceNorm2d(in_chn)
+        self.body = scaleNshiftBlock(in_chn * 2, out_chn, 'InstanceNorm', kwargs.get('bias', False))
+        self.tanh = nn.Tanh()
+        self.sigmoid = nn.Sigmoid()
+        self.scale = scale
+        self.diff_fAndg = kwargs.get('diff_fAndg', True)
+
+    def raw(self, source, target):
+        """Pre-activation 3-channel output (fp32); the heads are fused into ood_field_step."""
+        bf16 = source.dtype == torch.bfloat16
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False), \
+                torch.autocast('cuda', dtype=torch.bfloat16, enabled=bf16):
+            source, target = self.norm(source), self.norm(target)
+            z = torch.cat([source - target, target] if self.diff_fAndg else [source, target], dim=1)
+            z = self.body(z)
+        return z.float()
+
+    def forward(self, source, target, **kwargs):
+        z = self.raw(source, target)
+        return torch.cat([self.tanh(z[:, 0:1]) * self.scale, self.tanh(z[:, 1:2]) * self.scale, self.sigmoid(z[:, 2:])], dim=1)
+
+
+def weight_init(m):
+    """src/ops/SAMM/helpers.py:79-83"""
+    if isinstance(m, nn.Conv2d):
+        nn.init.constant_(m.weight, 0)
+        if m.bias is not None:
+            nn.init.constant_(m.bias, 0)
+
+
+class SPM_Warp(nn.Module):
+    """src/ops/SAMM/helpers.py:111-179"""
+
+    def __init__(self, in_chn, scale=0.1, style_dim=512, blur_kernel=[1, 3, 3, 1], cycle_align=1, **kwargs):
+        super().__init__()
+        self.body = AlignNet(in_chn, 3, scale=scale, style_dim=style_dim, blur_kernel=blur_kernel, **kwargs)
+        self.body.apply(weight_init)
+        self.scale = scale
+        self.cycle_align = cycle_align
+        self.weight_init()
+        self.blur = Blur(kernel=blur_kernel, pad=(2, 1))
+
+    def weight_init(self):
+        for module in self.modules():
+            if isinstance(module, (nn.Conv2d, sg.ModulatedConv2d, nn.Linear)):
+                nn.init.xavier_normal_(module.weight)
+
+    def forward_nhwc(self, source, target_nhwc, aligned=None):
+        """source: encoder features, logical [B,C,R,R] (any memory format); target_nhwc: generator features
+        [B,R,R,C] in the pipeline's storage type; aligned: coarser level's field or None.
+        Returns (aligned features NHWC, field fp32 [B,3,R,R])."""
+        if self.blur.taps is None:
+            raise NotImplementedError('ood_gan_inversion_b200: SPM_Warp needs a 4-tap blur kernel')
+        src = source.to(target_nhwc.dtype)
+        cur, acc = target_nhwc, None
+        for k in range(self.cycle_align):
+            z = self.body.raw(cur.permute(0, 3, 1, 2), src)          # NHWC storage viewed as channels_last NCHW
+            last = k == self.cycle_align - 1
+            acc = K.field_step(z, acc, aligned if last else None, self.scale, self.blur.taps)
+            cur = K.warp_mix(target_nhwc, acc)
+        return cur, acc
+
+    def forward(self, source, target, style=None, aligned=None):
+        """Reference contract: NCHW fp32 in, (aligned_target NCHW fp32, field) out."""
+        t = K.nchw_to_nhwc(target, None, sg._act_dtype())
+        cur, acc = self.forward_nhwc(source, t, aligned)
+        return K.nhwc_to_nchw(cur), acc
+
+
+class StyledscaleNshfitBlock(nn.Module):
+    """src/ops/SAMM/helpers.py:182-216 (default configuration: identity btn1, alignment on)."""
+
+    def __init__(self, in_chn, out_chn, style_dim, alignment=True, btn='style_bottleneck_IR', **kwargs):
+        super().__init__()
+        if btn is not None:
+            raise NotImplementedError("ood_gan_inversion_b200: only mod_btn=None (identity btn1) is implemented; no shipped "
+                                      'config sets mod_btn (SURVEY appendix B.5)')
+        self.btn1 = lambda x, y: x
+        out_chn = in_chn
+        if alignment:
+            self.alignment = SPM_Warp(out_chn, **kwargs)
+        else:
+            self.alignment = None
+        self.weight = nn.Parameter(torch.ones(1), requires_grad=False)
+        self.noiseInj = NoiseInjection()
+
+    def forward_nhwc(self, x, image_nhwc, aligned=None):
+        if self.alignment is None:
+            return x, None
+        return self.alignment.forward_nhwc(x, image_nhwc, aligned)
+
+    def forward(self, x, styles, **kwargs):
+        gen_feat = kwargs.get('image', None)
+        assert gen_feat is not None
+        if kwargs.get('transform', None) is not None:
+            x = kwargs['transform'](x)
+        if self.alignment is None:
+            return x, None
+        return self.alignment(x, gen_feat, styles, kwargs.get('aligned', None))

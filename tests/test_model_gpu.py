@@ -1,0 +1,217 @@
+"""GPU parity of the module API and of the full pipeline against the oracle (run on the same device, TF32 off,
+same seed => identical noise; SURVEY.md section 8c protocol).  Tolerances are BASELINE.json's: fp32 max-abs 1e-3 on the
+[-1,1] image; bf16 max-abs 2e-2 and PSNR >= 40 dB against the fp32 oracle."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import ood as oood, ops as oops, samm as osamm, stylegan as ostyle
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+
+
+@pytest.fixture(autouse=True)
+def _setup():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.set_grad_enabled(False)
+    yield
+    torch.set_grad_enabled(True)
+
+
+def sg():
+    import ood_gan_inversion_b200.stylegan as m
+    return m
+
+
+def to_dev(sd):
+    return {k: v.to(DEV) for k, v in sd.items()}
+
+
+def psnr(a, b, peak=2.0):
+    return 10 * math.log10(peak ** 2 / float(((a - b) ** 2).mean()))
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+def test_modules_against_reference_golden(golden, precision):
+    """ModulatedConv2d / StyledConv / ToRGB with the reference's own tiny odd-channel cases (zero-padding path)."""
+    m = sg()
+    m.set_precision(precision)
+    tol = dict(rtol=1e-4, atol=1e-4) if precision == 'fp32' else dict(rtol=5e-2, atol=5e-2)
+    G = golden('modconv.pt')
+    for c in G['cases']:
+        mod = m.ModulatedConv2d(c['ci'], c['co'], c['k'], 8, **c['kw']).to(DEV)
+        mod.load_state_dict(c['sd'])
+        y = mod(c['x'].to(DEV), c['style'].to(DEV))
+        assert y.shape == c['y'].shape
+        torch.testing.assert_close(y.cpu(), c['y'], **tol)
+    s = G['styled']
+    sc = m.StyledConv(6, 8, 3, 8, upsample=True).to(DEV)
+    sc.load_state_dict(s['sd'])
+    torch.testing.assert_close(sc(s['x'].to(DEV), s['style'].to(DEV), noise=s['noise'].to(DEV)).cpu(), s['y'], **tol)
+    t = G['torgb']
+    tr = m.ToRGB(8, 8).to(DEV)
+    tr.load_state_dict(t['sd'])
+    torch.testing.assert_close(tr(t['x'].to(DEV), t['style'].to(DEV), t['skip'].to(DEV)).cpu(), t['y'], **tol)
+    m.set_precision('bf16')
+
+
+def test_op_api_and_autograd():
+    from ood_gan_inversion_b200.op import FusedLeakyReLU, fused_leaky_relu, upfirdn2d
+    torch.set_grad_enabled(True)
+    k = oops.fir_kernel([1, 3, 3, 1], 4.0)
+    for up, down, pad in [(1, 1, (1, 1)), (2, 1, (2, 1)), (1, 2, (1, 1)), (1, 2, (2, 2))]:
+        x = torch.randn(2, 3, 10, 10, device=DEV, requires_grad=True)
+        xr = x.detach().cpu().requires_grad_(True)
+        y = upfirdn2d(x, k.to(DEV), up=up, down=down, pad=pad)
+        yr = oops.upfirdn2d(xr, k, up, down, pad)
+        torch.testing.assert_close(y.detach().cpu(), yr.detach(), rtol=1e-5, atol=1e-5)
+        g = torch.randn_like(yr)
+        gx, = torch.autograd.grad(y, x, g.to(DEV), create_graph=True)
+        gxr, = torch.autograd.grad(yr, xr, g)
+        torch.testing.assert_close(gx.detach().cpu(), gxr, rtol=1e-5, atol=1e-5)
+        # double backward (upfirdn2d.py:66-89): d<gx, v>/dg == upfirdn2d(v)
+        gy = torch.randn_like(yr).to(DEV).requires_grad_(True)
+        gx2, = torch.autograd.grad(upfirdn2d(x, k.to(DEV), up=up, down=down, pad=pad), x, gy, create_graph=True)
+        v = torch.randn_like(gx2)
+        ggo, = torch.autograd.grad(gx2, gy, v)
+        torch.testing.assert_close(ggo.cpu(), oops.upfirdn2d(v.cpu(), k, up, down, pad), rtol=1e-5, atol=1e-5)
+    act = FusedLeakyReLU(5).to(DEV)
+    act.bias.data.normal_()
+    x = torch.randn(2, 5, 4, 4, device=DEV, requires_grad=True)
+    y = act(x)
+    xr, br = x.detach().cpu().requires_grad_(True), act.bias.detach().cpu().requires_grad_(True)
+    yr = oops.fused_leaky_relu(xr, br)
+    torch.testing.assert_close(y.detach().cpu(), yr.detach(), rtol=1e-6, atol=1e-6)
+    g = torch.randn_like(yr)
+    gx, gb = torch.autograd.grad(y, [x, act.bias], g.to(DEV))
+    gxr, gbr = torch.autograd.grad(yr, [xr, br], g)
+    torch.testing.assert_close(gx.cpu(), gxr, rtol=1e-6, atol=1e-6)
+    torch.testing.assert_close(gb.cpu(), gbr, rtol=1e-4, atol=1e-5)
+    y2 = fused_leaky_relu(torch.randn(3, 5, device=DEV), act.bias)      # 2-D input (style MLP)
+    assert y2.shape == (3, 5)
+    torch.set_grad_enabled(False)
+
+
+@pytest.mark.parametrize('size,batch', [(16, 2), (64, 2), (256, 1)])
+def test_generator_fp32_vs_oracle(golden, size, batch):
+    m = sg()
+    m.set_precision('fp32')
+    sd = ostyle.synthetic_generator_state(size, seed=size)
+    gen = m.Generator(size, 512, 8).to(DEV)
+    gen.load_state_dict(sd, strict=True)
+    gen.eval()
+    G = golden('generator.pt')[size]
+    lat = torch.randn(G['batch'], G['n_latent'], 512, generator=torch.Generator().manual_seed(1))
+    img, _ = gen(lat.to(DEV), input_is_tensor=True, input_is_latent=True, randomize_noise=False)
+    st = G['step']
+    # against the frozen output of the unmodified reference (CPU) ...
+    assert (img[:, :, ::st, ::st].cpu() - G['img']).abs().max() < 1e-3
+    # ... and against the oracle on this device, every pixel, incl. returned features and random noise with one seed
+    ref, feat_ref = ostyle.generator_forward(to_dev(sd), lat.to(DEV), size, randomize_noise=False, return_features=True)
+    assert (img - ref).abs().max() < 1e-3
+    _, feat = gen(lat.to(DEV), input_is_tensor=True, input_is_latent=True, randomize_noise=False, return_features=True)
+    torch.testing.assert_close(feat, feat_ref, rtol=1e-3, atol=1e-3)
+    torch.manual_seed(5)
+    a, _ = gen(lat.to(DEV), input_is_tensor=True, input_is_latent=True)
+    torch.manual_seed(5)
+    b_ = ostyle.generator_forward(to_dev(sd), lat.to(DEV), size)
+    assert (a - b_).abs().max() < 1e-3
+    # z-space entry through the mapping network (style MLP + fused lrelu kernel)
+    z = torch.randn(batch, 512, generator=torch.Generator().manual_seed(2)).to(DEV)
+    torch.testing.assert_close(gen.style(z)[:, :16].cpu(), G['mapping'][:batch], rtol=1e-3, atol=1e-4)
+    m.set_precision('bf16')
+
+
+@pytest.mark.parametrize('size,batch', [(64, 2), (256, 2), (1024, 1)])
+def test_generator_bf16_vs_oracle(size, batch):
+    m = sg()
+    m.set_precision('bf16')
+    sd = ostyle.synthetic_generator_state(size, seed=size)
+    gen = m.Generator(size, 512, 8).to(DEV)
+    gen.load_state_dict(sd, strict=True)
+    lat = torch.randn(batch, gen.n_latent, 512, generator=torch.Generator().manual_seed(1)).to(DEV)
+    img, _ = gen(lat, input_is_tensor=True, input_is_latent=True, randomize_noise=False)
+    ref = ostyle.generator_forward(to_dev(sd), lat, size, randomize_noise=False)
+    err = float((img - ref).abs().max())
+    p = psnr(img, ref)
+    print(f'bf16 generator {size}: max-abs {err:.4g}, PSNR {p:.1f} dB, range [{float(ref.min()):.2f}, {float(ref.max()):.2f}]')
+    assert err < 2e-2 and p >= 40.0
+
+
+def build_ood(precision, strict_rng=True):
+    from ood_gan_inversion_b200.arch import ood_faceGAN_e4e
+    sg().set_precision(precision)
+    sd = oood.synthetic_ood_state(1024, seed=0)
+    net = ood_faceGAN_e4e(out_size=1024, style_dim=512, encoder='E4E', enable_modulation=True, warp_scale=0.08,
+                          cycle_align=2, blend_with_gen=True, ModSize=256)
+    net.load_state_dict(sd, strict=True)
+    net = net.to(DEV).eval()
+    net.strict_rng = strict_rng
+    return net, sd
+
+
+def make_input(batch, seed=2):
+    x = torch.randn(batch, 3, 64, 64, generator=torch.Generator().manual_seed(seed))
+    return F.interpolate(x, (1024, 1024), mode='bicubic', align_corners=False).clamp(-1, 1).to(DEV)
+
+
+def test_ood_pipeline_fp32_vs_oracle():
+    net, sd = build_ood('fp32')
+    x = make_input(1)
+    torch.manual_seed(123)
+    out, lats = net(x)
+    torch.manual_seed(123)
+    ref, rlats, raligns = oood.ood_forward(to_dev(sd), x)
+    torch.testing.assert_close(lats, rlats, rtol=1e-4, atol=1e-4)
+    for k in (1, 2, 3, 4):
+        assert (net.aligns[k] - raligns[k]).abs().max() < 1e-3, k
+    assert (net.aligns[1024] - raligns[1024]).abs().max() < 1e-3
+    err = float((out - ref).abs().max())
+    print(f'fp32 OOD pipeline: max-abs {err:.3g}')
+    assert err < 1e-3
+    sg().set_precision('bf16')
+
+
+def test_ood_pipeline_bf16_vs_oracle():
+    net, sd = build_ood('bf16')
+    x = make_input(2)
+    torch.manual_seed(123)
+    out, lats = net(x)
+    torch.manual_seed(123)
+    ref, rlats, raligns = oood.ood_forward(to_dev(sd), x)
+    err, p = float((out - ref).abs().max()), psnr(out, ref)
+    print(f'bf16 OOD pipeline: max-abs {err:.4g}, PSNR {p:.1f} dB; alpha err {float((net.aligns[1024] - raligns[1024]).abs().max()):.3g}')
+    assert net.aligns[1024].shape == (2, 3, 1024, 1024)
+    assert err < 2e-2 and p >= 40.0
+
+
+def test_generic_callback_protocol():
+    """A foreign (reference-style) callback: NCHW image in, replacement noise out (model.py:288-292)."""
+    m = sg()
+    m.set_precision('fp32')
+    size = 32
+    sd = ostyle.synthetic_generator_state(size, seed=7)
+    gen = m.Generator(size, 512, 8).to(DEV)
+    gen.load_state_dict(sd)
+    lat = torch.randn(2, gen.n_latent, 512, generator=torch.Generator().manual_seed(1)).to(DEV)
+    seen = []
+
+    def cb(image, **kw):
+        seen.append((kw['index'], tuple(image.shape)))
+        return 0.5 * kw['noise'] + 0.01 * image        # arbitrary function of both
+
+    torch.manual_seed(9)
+    img, _ = gen(lat, input_is_tensor=True, input_is_latent=True, conditions=[[None, None]], cond_layers=[5],
+                 cond_type='NOISE', callback=cb)
+
+    def hook(ci, image, noise, nw, style):
+        return 0.5 * noise + 0.01 * image
+    torch.manual_seed(9)
+    ref = ostyle.generator_forward(to_dev(sd), lat, size, cond_layers=[5], hook=hook)
+    assert seen == [(0, (2, 512, 32, 32))]
+    assert (img - ref).abs().max() < 1e-3
+    m.set_precision('bf16')
