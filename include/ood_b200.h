@@ -143,11 +143,11 @@ int ood_noise_act(const void *img, void *out_y, void *out_ys, const float *noise
                   int channels, int dtype, void *stream);
 
 /* ---- a8. ToRGB: 1x1 modulated conv without demodulation + bias + FIR-upsampled skip (model.py:363-372).
- *      wrgb[b,k,c] = W[k,c]*s[b,c]/sqrt(C) (fp32, from ood_torgb_weight); y is the UNscaled NHWC activation.
+ *      wrgb[b,k,c] = W[k,c]*s[b,c]*scale (fp32, from ood_torgb_weight; scale = 1/sqrt(C)); y is the UNscaled NHWC activation.
  *      out[b,k,Y,X] = sum_c y[b,Y,X,c]*wrgb[b,k,c] + bias[k] + up2fir(skip)[b,k,Y,X]     (NCHW fp32)
  *      skip: [B,3,H/2,W/2] fp32 or NULL.  taps_up: 4 host values of the 1-D up-FIR ([1,3,3,1]/8*2). */
-int ood_torgb_weight(const float *w /*[3][C]*/, const float *s /*[B][C]*/, float *wrgb, int batch, int channels,
-                     void *stream);
+int ood_torgb_weight(const float *w /*[3][C]*/, const float *s /*[B][C]*/, float *wrgb, float scale /* 1/sqrt(fan_in) */,
+                     int batch, int channels, void *stream);
 int ood_torgb(const void *y, const float *wrgb, const float *bias, const float *skip, float *out,
               const float *taps_up_host, int batch, int h, int w, int channels, int dtype, void *stream);
 

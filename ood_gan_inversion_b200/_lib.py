@@ -46,7 +46,7 @@ _SIGS = {
     'ood_blur_act': ([C.POINTER(BlurActArgs), c_void_p], c_int),
     'ood_noise_act': ([c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_void_p, c_void_p, c_int, c_i64, c_int,
                        c_int, c_void_p], c_int),
-    'ood_torgb_weight': ([c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p], c_int),
+    'ood_torgb_weight': ([c_void_p, c_void_p, c_void_p, c_float, c_int, c_int, c_void_p], c_int),
     'ood_torgb': ([c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, C.POINTER(c_float), c_int, c_int, c_int, c_int, c_int,
                    c_void_p], c_int),
     'ood_field_step': ([c_void_p, c_void_p, c_void_p, c_void_p, C.POINTER(c_float), c_float, c_int, c_int, c_int,

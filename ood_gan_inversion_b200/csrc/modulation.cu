@@ -117,11 +117,11 @@ extern "C" int ood_pack_conv_weight(const float *w, void *out, int cout, int cin
     return check_launch("pack_conv_weight");
 }
 
-extern "C" int ood_torgb_weight(const float *w, const float *s, float *wrgb, int batch, int channels, void *stream) {
+extern "C" int ood_torgb_weight(const float *w, const float *s, float *wrgb, float scale, int batch, int channels,
+                                void *stream) {
     using namespace ood;
     OOD_REQUIRE(w && s && wrgb && batch > 0 && channels > 0, "torgb_weight: bad arguments");
     const int64_t n = (int64_t)batch * 3 * channels;
-    torgb_weight_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(w, s, wrgb, batch, channels,
-                                                                            1.0f / sqrtf((float)channels));
+    torgb_weight_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(w, s, wrgb, batch, channels, scale);
     return check_launch("torgb_weight");
 }

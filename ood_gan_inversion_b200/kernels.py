@@ -159,12 +159,13 @@ def modulation(latent, mod_w, mod_b, wsq, conv_scale, cout, want_d=True):
     return s, d
 
 
-def torgb_weight(w, s):
-    """w fp32 [3,C], s [B,C] -> [B,3,C] = w*s/sqrt(C)"""
+def torgb_weight(w, s, scale=None):
+    """w fp32 [3,C], s [B,C] -> [B,3,C] = w*s*scale (scale defaults to 1/sqrt(C))"""
     _cuda(w, s)
     b, c = s.shape
     out = torch.empty(b, 3, c, device=s.device, dtype=torch.float32)
-    check(_lib.lib().ood_torgb_weight(_ptr(w), _ptr(s), _ptr(out), b, c, _stream()), 'torgb_weight')
+    scale = 1.0 / math.sqrt(c) if scale is None else float(scale)
+    check(_lib.lib().ood_torgb_weight(_ptr(w), _ptr(s), _ptr(out), scale, b, c, _stream()), 'torgb_weight')
     return out
 
 

@@ -238,7 +238,7 @@ class ModulatedConv2d(nn.Module):
             s, _ = self.coeffs(style)
             y = _to_nhwc(input, None, self.cin_p)
             zero = torch.zeros(3, device=input.device)
-            return K.torgb(y, K.torgb_weight(wp, s), zero)
+            return K.torgb(y, K.torgb_weight(wp, s, self.scale), zero)
         if self.kernel_size != 3:
             raise NotImplementedError('ood_gan_inversion_b200: ModulatedConv2d supports kernel_size 3 (and the 1x1 ToRGB form)')
         wp, _, _, _ = self.packed()
@@ -389,7 +389,7 @@ class ToRGB(nn.Module):
         s, _ = self.conv.coeffs(style)
         if skip is not None and len(self.taps_up) != 4:
             raise NotImplementedError('ood_gan_inversion_b200: fused ToRGB skip needs a 4-tap blur kernel')
-        return K.torgb(y, K.torgb_weight(wp, s), self.bias.detach().float().reshape(3).contiguous(),
+        return K.torgb(y, K.torgb_weight(wp, s, self.conv.scale), self.bias.detach().float().reshape(3).contiguous(),
                        None if skip is None else skip.float().contiguous(), self.taps_up)
 
     def forward(self, input, style, skip=None):

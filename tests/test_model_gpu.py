@@ -121,8 +121,8 @@ def test_generator_fp32_vs_oracle(golden, size, batch):
     b_ = ostyle.generator_forward(to_dev(sd), lat.to(DEV), size)
     assert (a - b_).abs().max() < 1e-3
     # z-space entry through the mapping network (style MLP + fused lrelu kernel)
-    z = torch.randn(batch, 512, generator=torch.Generator().manual_seed(2)).to(DEV)
-    torch.testing.assert_close(gen.style(z)[:, :16].cpu(), G['mapping'][:batch], rtol=1e-3, atol=1e-4)
+    z = torch.randn(G['batch'], 512, generator=torch.Generator().manual_seed(2)).to(DEV)
+    torch.testing.assert_close(gen.style(z)[:, :16].cpu(), G['mapping'], rtol=1e-3, atol=1e-4)
     m.set_precision('bf16')
 
 
