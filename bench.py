@@ -1,0 +1,259 @@
+#!/usr/bin/env python
+"""bench.py -- 1024px OOD inversion throughput on B200 (BASELINE.json metric), one JSON line on rank 0.
+
+    python bench.py --gpus 1 --steps K --warmup W            # this repo's sm_100a path
+    python bench.py --impl reference --steps K --warmup W    # the reference's CPU arithmetic (oracle port) on host cores
+    torchrun --nproc-per-node N ... bench.py --gpus N ...    # one rank per GPU, independent image shards (no collective)
+
+A step = one forward of the full pipeline (E4E encode -> StyleGAN2 1024 synthesis with 4 alignment levels x 2
+cycles -> invertibility mask -> ID/OOD blend) over a batch of 16 synthetic 1024x1024 faces per GPU, bf16 storage on
+the tcgen05 path (BASELINE.json configs[1]).  `value` times it with the batch resident in HBM; `e2e` times the public
+call `net(x)` with pinned-host input, H2D and D2H of the result inside the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = '1024px inversion images/sec'
+UNIT = 'images/s'
+BATCH = 16
+SIZE = 1024
+ARCH_KW = dict(out_size=SIZE, style_dim=512, encoder='E4E', enable_modulation=True, warp_scale=0.08, cycle_align=2,
+               blend_with_gen=True, ModSize=256)
+WORKLOAD = 'E4E encoder + StyleGAN2 1024px forward + invertibility-mask blend, batch 16 bf16 per GPU (BASELINE configs[1])'
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d['hbm_gbs'], tf_burst=d['bf16_tflops'], tf_sus=d.get('bf16_tflops_sustained', d['bf16_tflops']),
+                    src='measured (MEASURED_PEAKS.json)')
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sus=1400.0, src='fallback (B200_PROFILING.md)')
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index):
+        self.index, self.rows, self.stop = index, [], False
+        self.t = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        while not self.stop:
+            try:
+                o = subprocess.run(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.Q}', '--format=csv,noheader,nounits'],
+                                   capture_output=True, text=True, timeout=5).stdout.strip()
+                if o:
+                    self.rows.append([c.strip() for c in o.split(',')])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop = True
+        self.t.join(timeout=6)
+
+    def summary(self):
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace('.', '').isdigit())
+        if not sm:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['unavailable'])
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower() == 'active' for r in self.rows)]
+        return dict(sm_mhz=sm[len(sm) // 2], sm_max_mhz=float(self.rows[0][1]), samples=len(sm), reasons=reasons)
+
+
+def cpu_reference(steps, warmup, images_per_step=1, state=None):
+    """The reference's arithmetic for the path (oracle port: plain PyTorch fp32, native upfirdn2d / fused_act branch) on
+    the host cores.  A step = `images_per_step` images of the same 1024px pipeline (bounded sample)."""
+    import torch
+    from oracle import ood as oood
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_grad_enabled(False)
+    sd = state if state is not None else oood.synthetic_ood_state(SIZE, seed=0)
+    from ood_gan_inversion_b200.synth import synthetic_faces
+    x = synthetic_faces(images_per_step, SIZE)
+    times = []
+    for i in range(warmup + steps):
+        torch.manual_seed(123)
+        t0 = time.perf_counter()
+        oood.ood_forward(sd, x, size=SIZE, strict_rng=False)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    total = sum(times)
+    return dict(value=images_per_step * len(times) / total, ms_per_step=1e3 * total / len(times), cores=torch.get_num_threads(),
+                sample=f'{len(times)} step(s) x {images_per_step} image(s) of the 1024px pipeline, fp32, after {warmup} warm-up')
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--batch', type=int, default=BATCH)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--profile', action='store_true', help='print a torch.profiler kernel table for one step (not a bench value)')
+    args = ap.parse_args()
+    rank = int(os.environ.get('RANK', 0))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+
+    if args.impl == 'reference':
+        if rank != 0:
+            return 0
+        r = cpu_reference(max(1, args.steps), max(0, min(args.warmup, 1)))
+        line = dict(metric=METRIC, value=r['value'], unit=UNIT, impl='reference', n_gpus=args.gpus, steps=args.steps,
+                    warmup=min(args.warmup, 1), ms_per_step=r['ms_per_step'], higher_is_better=True, scaling='weak',
+                    vs_baseline=None, dtype='f32', data='synthetic',
+                    config=dict(workload=WORKLOAD, note='reference arm: the reference\'s own CPU arithmetic (native upfirdn2d / '
+                                'fused_act branch, oracle port) on the host cores, 1 image per step'),
+                    cpu_baseline=dict(value=r['value'], unit=UNIT, cores=r['cores'], kind='port', sample=r['sample']),
+                    e2e=dict(value=r['value'], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise RuntimeError('bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm')
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    torch.backends.cudnn.benchmark = True
+    torch.set_grad_enabled(False)
+
+    from ood_gan_inversion_b200 import _lib, kernels as K, stylegan as sg
+    from ood_gan_inversion_b200.arch import ood_faceGAN_e4e
+    from ood_gan_inversion_b200.synth import synthetic_faces, synthetic_init
+    _lib.lib()                                    # fail loudly before anything else if the CUDA library is missing
+    sg.set_precision('bf16')
+    torch.manual_seed(0)
+    net = synthetic_init(ood_faceGAN_e4e(**ARCH_KW), seed=0).to(dev).eval()
+    B = args.batch
+    x_host = synthetic_faces(B, SIZE, seed=2 + rank, pin=True)
+    x_dev = x_host.to(dev)
+    out_host = torch.empty(B, 3, SIZE, SIZE, dtype=torch.float32).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        torch.manual_seed(1000 + rank)
+        return net(x_dev)[0]
+
+    def step_e2e():
+        torch.manual_seed(1000 + rank)
+        xd = x_host.to(dev, non_blocking=True)
+        out = net(xd)[0]
+        out_host.copy_(out, non_blocking=True)
+        return out
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    barrier()
+
+    if args.profile and rank == 0:
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+            step_resident()
+            torch.cuda.synchronize()
+        print(prof.key_averages().table(sort_by='cuda_time_total', row_limit=40, max_name_column_width=70), file=sys.stderr)
+
+    # ---------------- timed region 1: inputs resident in HBM (inputs are 201 MB > 126 MB L2: no explicit flush) ----
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = _lib.lib().ood_launch_count()
+    K.profile_begin()
+    with ClockSampler(local_rank) as clk:
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            out = step_resident()
+        e1.record()
+        barrier()
+    prof = K.profile_end()
+    launches = _lib.lib().ood_launch_count() - launches0
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    if not torch.isfinite(out).all():
+        raise RuntimeError('bench: non-finite output')
+
+    # ---------------- timed region 2: end to end through the public call, host buffers ---------------------------
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step_e2e()
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_e2e = float(t.item())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    pk = peaks()
+    conv = prof.get('conv3x3_tc', dict(ms=0.0, work=0.0, launches=0))
+    blur = prof.get('blur_act', dict(ms=0.0, work=0.0, launches=0))
+    conv_tf = conv['work'] / (conv['ms'] * 1e-3) / 1e12 if conv['ms'] > 0 else 0.0
+    blur_gbs = blur['work'] / (blur['ms'] * 1e-3) / 1e9 if blur['ms'] > 0 else 0.0
+    step_ms = ms_max / args.steps
+    kern = {k: dict(ms_per_step=v['ms'] / args.steps, launches_per_step=v['launches'] / args.steps,
+                    achieved=(v['work'] / (v['ms'] * 1e-3) / (1e12 if k.startswith('conv') else 1e9)) if v['ms'] > 0 else 0.0,
+                    unit='TFLOP/s' if k.startswith('conv') else 'GB/s') for k, v in prof.items()}
+    line = dict(metric=METRIC, value=world * args.steps * B / (ms_max * 1e-3), unit=UNIT, n_gpus=world, steps=args.steps,
+                warmup=max(args.warmup, 3), ms_per_step=step_ms, higher_is_better=True, scaling='weak', vs_baseline=None,
+                dtype='bf16', data='synthetic',
+                config=dict(workload=WORKLOAD, batch_per_gpu=B, global_batch=B * world, size=SIZE, cycle_align=2, mod_size=256,
+                            l2='inputs (201 MB/step) exceed the 126 MB L2', parallelism=f'independent image shards x{world}, no collective',
+                            weights='random-init (reference init + non-zero noise weights), synthetic smooth faces'),
+                clocks=clk.summary(),
+                e2e=dict(value=world * args.steps * B / (ms_e2e * 1e-3), unit=UNIT, h2d_bytes_per_step=x_host.numel() * 4,
+                         d2h_bytes_per_step=out_host.numel() * 4, ms_per_step=ms_e2e / args.steps),
+                gpu_launches=int(launches),
+                roofline=dict(kernel='conv_tc_kernel (tcgen05 implicit-GEMM 3x3 modulated conv)', bound='tensor', achieved=conv_tf,
+                              peak=pk['tf_sus'], unit='TFLOP/s', frac=conv_tf / pk['tf_sus'], traffic=None,
+                              peak_source=pk['src'] + ', sustained figure (kernel timed inside a long step)',
+                              share_of_step=conv['ms'] / max(ms, 1e-9), launches_per_step=conv['launches'] / args.steps),
+                roofline_hbm=dict(kernel='blur_act_kernel (FIR blur + demod + noise + bias + lrelu + next style)', bound='hbm',
+                                  achieved=blur_gbs, peak=pk['hbm'], unit='GB/s', frac=blur_gbs / pk['hbm'], traffic=None,
+                                  share_of_step=blur['ms'] / max(ms, 1e-9)),
+                kernels=kern)
+    if world == 1 and not args.no_cpu_baseline:
+        sd = {k: v.detach().float().cpu() for k, v in net.state_dict().items()}
+        r = cpu_reference(2, 1, 1, state=sd)
+        line['cpu_baseline'] = dict(value=r['value'], unit=UNIT, cores=r['cores'], kind='port', sample=r['sample'])
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == '__main__':
+    sys.exit(main())

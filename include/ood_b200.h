@@ -42,6 +42,8 @@ int ood_version(void);
 const char *ood_last_error(void);
 /* 1 if the current device is compute capability 10.x (tcgen05/TMEM/TMA paths usable). */
 int ood_device_is_sm100(void);
+/* number of kernels this library has launched in this process (monotonic; bench.py reports the difference). */
+unsigned long long ood_launch_count(void);
 
 /* ---- a1. upfirdn2d on NCHW planes: replaces upfirdn2d_op.upfirdn2d (upfirdn2d.cpp:12-23) with minor==1,
  *      which is the only form the Python wrapper issues (upfirdn2d.py:103).  Generic in every parameter
@@ -159,6 +161,11 @@ int ood_torgb(const void *y, const float *wrgb, const float *bias, const float *
  *      PRM(x,y) = y*x + x*(1-x).  coarse is [B,3,Rc,Rc]; bicubic align_corners=True (helpers.py:69-70). */
 int ood_field_step(const float *z, const float *prev, const float *coarse, float *acc, const float *taps_host,
                    float scale, int batch, int r, int rc, void *stream);
+
+/* ---- a13 (encoder FPN merge, e4e/encoders/helpers.py:504-521): out = bicubic_up(x, align_corners=True) + y on NHWC.
+ *      x [B,h,w,C], y / out [B,H,W,C] (y may be NULL).  ATen's channels-last bicubic costs 40 ms per call at B=16. */
+int ood_bicubic_up_add(const void *x, const void *y, void *out, int batch, int h, int w, int H, int W, int channels,
+                       int dtype, void *stream);
 
 /* ---- a11. warp + alpha mix (helpers.py:168-177) on NHWC features:
  *      out[b,y,x,:] = bilinear(gen[b], lin_x[x]+dx, lin_y[y]+dy)*alpha + gen[b,y,x,:]*(1-alpha)

@@ -31,6 +31,7 @@ _SIGS = {
     'ood_version': ([], c_int),
     'ood_last_error': ([], C.c_char_p),
     'ood_device_is_sm100': ([], c_int),
+    'ood_launch_count': ([], C.c_ulonglong),
     'ood_upfirdn2d': ([c_void_p, c_void_p, c_void_p, c_i64] + [c_int] * 12 + [c_int, c_void_p], c_int),
     'ood_fused_bias_act': ([c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_int, c_i64, c_int, c_int, c_float, c_float,
                             c_int, c_void_p], c_int),
@@ -51,6 +52,7 @@ _SIGS = {
                    c_void_p], c_int),
     'ood_field_step': ([c_void_p, c_void_p, c_void_p, c_void_p, C.POINTER(c_float), c_float, c_int, c_int, c_int,
                         c_void_p], c_int),
+    'ood_bicubic_up_add': ([c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p], c_int),
     'ood_warp_mix': ([c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p], c_int),
     'ood_mask_blend': ([C.POINTER(c_void_p), C.POINTER(c_int), c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                         c_void_p], c_int),

@@ -13,7 +13,7 @@
 namespace ood {
 
 void set_error(const char *fmt, ...);
-int check_launch(const char *what);
+int check_launch(const char *what, int kernels = 1);
 
 #define OOD_REQUIRE(cond, ...)              \
     do {                                    \

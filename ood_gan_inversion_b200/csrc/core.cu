@@ -12,7 +12,10 @@ void set_error(const char *fmt, ...) {
     va_end(ap);
 }
 
-int check_launch(const char *what) {
+static unsigned long long g_launches = 0;
+
+int check_launch(const char *what, int kernels) {
+    g_launches += (unsigned long long)kernels;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         set_error("%s: %s", what, cudaGetErrorString(e));
@@ -24,6 +27,8 @@ int check_launch(const char *what) {
 }  // namespace ood
 
 extern "C" int ood_version(void) { return 100; }
+
+extern "C" unsigned long long ood_launch_count(void) { return ood::g_launches; }
 
 extern "C" const char *ood_last_error(void) { return ood::g_err; }
 

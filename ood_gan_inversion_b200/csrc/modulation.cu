@@ -94,7 +94,7 @@ extern "C" int ood_modulation(const float *latent, int64_t latent_stride, const 
         if (wsq) demod_kernel<<<ceil_div(n, 8), 256, 0, st>>>(s_out, wsq, d_out, batch, cin, cout, conv_scale);
         else fill_kernel<<<ceil_div(n, 256), 256, 0, st>>>(d_out, n, conv_scale);
     }
-    return check_launch("modulation");
+    return check_launch("modulation", d_out ? 2 : 1);
 }
 
 extern "C" int ood_weight_sumsq(const float *w, float *wsq, int cout, int cin, int taps, void *stream) {

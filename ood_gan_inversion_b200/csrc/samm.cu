@@ -188,7 +188,75 @@ __global__ void __launch_bounds__(256) mask_blend_kernel(const MaskParams mp, co
     }
 }
 
+// ------------------------------------------------------------------ bicubic upsample (align_corners=True) + add, NHWC
+// FPN top-down merge of the encoder (src/ops/e4e/encoders/helpers.py:504-521): out = bicubic_up(x) + y.
+template <typename T>
+__global__ void __launch_bounds__(256) bicubic_up_add_kernel(const T *__restrict__ x, const T *__restrict__ y,
+                                                              T *__restrict__ out, int h, int w, int H, int W, int C) {
+    constexpr int N = Vec<T>::N;
+    const int cv = C / N;
+    const int b = blockIdx.y;
+    const float A = -0.75f;
+    const float sy = H > 1 ? (float)(h - 1) / (float)(H - 1) : 0.f, sx = W > 1 ? (float)(w - 1) / (float)(W - 1) : 0.f;
+    const T *xb = x + (int64_t)b * h * w * C;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < (int64_t)H * W * cv; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t pix = i / cv;
+        const int c = (int)(i - pix * cv) * N;
+        const int Y = (int)(pix / W), X = (int)(pix - (int64_t)Y * W);
+        const float ry = sy * Y, rx = sx * X;
+        const int iy = (int)floorf(ry), ix = (int)floorf(rx);
+        const float ty = ry - iy, tx = rx - ix;
+        const float cx[4] = {cubic2(tx + 1.f, A), cubic1(tx, A), cubic1(1.f - tx, A), cubic2(2.f - tx, A)};
+        const float cy[4] = {cubic2(ty + 1.f, A), cubic1(ty, A), cubic1(1.f - ty, A), cubic2(2.f - ty, A)};
+        float acc[N];
+#pragma unroll
+        for (int j = 0; j < N; ++j) acc[j] = 0.f;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int yy = min(max(iy - 1 + r, 0), h - 1);
+            float row[N];
+#pragma unroll
+            for (int j = 0; j < N; ++j) row[j] = 0.f;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int xx = min(max(ix - 1 + q, 0), w - 1);
+                const Vec<T> v = load_vec<T>(xb + ((int64_t)yy * w + xx) * C + c);
+#pragma unroll
+                for (int j = 0; j < N; ++j) row[j] = fmaf(cx[q], v.v[j], row[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < N; ++j) acc[j] = fmaf(cy[r], row[j], acc[j]);
+        }
+        const int64_t off = ((int64_t)b * H * W + pix) * C + c;
+        Vec<T> o;
+        if (y) {
+            const Vec<T> yv = load_vec<T>(y + off);
+#pragma unroll
+            for (int j = 0; j < N; ++j) o.v[j] = acc[j] + yv.v[j];
+        } else {
+#pragma unroll
+            for (int j = 0; j < N; ++j) o.v[j] = acc[j];
+        }
+        store_vec<T>(out + off, o);
+    }
+}
+
 }  // namespace ood
+
+extern "C" int ood_bicubic_up_add(const void *x, const void *y, void *out, int batch, int h, int w, int H, int W,
+                                  int channels, int dtype, void *stream) {
+    using namespace ood;
+    OOD_REQUIRE(x && out && batch > 0 && batch <= 65535 && h > 0 && w > 0 && H > 0 && W > 0, "bicubic_up_add: bad arguments");
+    OOD_REQUIRE(dtype == OOD_F32 || dtype == OOD_BF16, "bicubic_up_add: bad dtype");
+    const int N = dtype == OOD_F32 ? 4 : 8;
+    OOD_REQUIRE(channels % N == 0, "bicubic_up_add: channels (%d) must be a multiple of %d", channels, N);
+    const int64_t work = (int64_t)H * W * (channels / N);
+    dim3 grid((unsigned)std::min<int64_t>((work + 255) / 256, kNumSMs * 16), batch);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == OOD_F32) bicubic_up_add_kernel<float><<<grid, 256, 0, st>>>((const float *)x, (const float *)y, (float *)out, h, w, H, W, channels);
+    else bicubic_up_add_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16 *)x, (const __nv_bfloat16 *)y, (__nv_bfloat16 *)out, h, w, H, W, channels);
+    return check_launch("bicubic_up_add");
+}
 
 extern "C" int ood_field_step(const float *z, const float *prev, const float *coarse, float *acc, const float *taps_host,
                               float scale, int batch, int r, int rc, void *stream) {

@@ -12,6 +12,7 @@ import torch
 from torch import nn
 from torch.nn import functional as F
 
+from . import kernels as K
 from .samm import BN
 from .stylegan import EqualLinear
 
@@ -84,6 +85,9 @@ class bottleneck_IR_SE(nn.Module):
                                        BN(depth, bn=bn), SEModule(depth, 16))
 
     def forward(self, x):
+        if isinstance(self.shortcut_layer, nn.MaxPool2d):       # MaxPool2d(1, s) == strided subsampling: no kernel needed
+            s = self.shortcut_layer.stride
+            return self.res_layer(x) + (x if s == 1 else x[:, :, ::s, ::s])
         return self.res_layer(x) + self.shortcut_layer(x)
 
 
@@ -108,8 +112,14 @@ class GradualStyleBlock(nn.Module):
 
 
 def _upsample_add(x, y):
-    """helpers.py:504-521"""
-    return F.interpolate(x, size=y.shape[-2:], mode='bicubic', align_corners=True) + y
+    """helpers.py:504-521: bicubic (align_corners=True) upsample of the top feature map + lateral map; fused NHWC kernel
+    (ATen's bicubic on channels_last tensors takes 40 ms per call at batch 16)."""
+    if not x.is_cuda:
+        raise RuntimeError('ood_gan_inversion_b200 is CUDA-only')
+    dt = y.dtype if y.dtype in (torch.float32, torch.bfloat16) else torch.float32
+    xn = x.to(dt).permute(0, 2, 3, 1).contiguous()
+    yn = y.to(dt).permute(0, 2, 3, 1).contiguous()
+    return K.bicubic_up_add(xn, yn).permute(0, 3, 1, 2)          # channels_last view of the NHWC result
 
 
 class Encoder4Editing(nn.Module):

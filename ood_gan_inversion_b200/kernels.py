@@ -12,6 +12,47 @@ from ._lib import BF16, F32, BlurActArgs, ConvArgs, check
 
 FIR_1331 = (1.0, 3.0, 3.0, 1.0)
 
+# ---- optional per-launch timing (bench.py roofline): CUDA events on the launching stream ------------------------
+_prof = None
+
+
+def profile_begin():
+    global _prof
+    _prof = []
+
+
+def profile_end():
+    """-> {name: dict(ms=total device ms, work=total algorithmic flops or bytes, launches=n)}; call after a sync."""
+    global _prof
+    rec, _prof = _prof, None
+    out = {}
+    for name, e0, e1, work in rec or []:
+        d = out.setdefault(name, dict(ms=0.0, work=0.0, launches=0))
+        d['ms'] += e0.elapsed_time(e1)
+        d['work'] += work
+        d['launches'] += 1
+    return out
+
+
+class _timed:
+    def __init__(self, name, work):
+        self.name, self.work = name, work
+
+    def __enter__(self):
+        if _prof is not None:
+            self.e0, self.e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *exc):
+        if _prof is not None:
+            self.e1.record()
+            _prof.append((self.name, self.e0, self.e1, self.work))
+        return False
+
+
+def _esize(t):
+    return t.element_size()
+
 
 def _dt(t):
     if t.dtype == torch.float32:
@@ -185,7 +226,9 @@ def conv3x3(x, weight, cout, transposed=False, impl=0, d=None, noise=None, noise
         nbs = 0 if noise.shape[0] == 1 else oh * ow
     a = ConvArgs(_ptr(x), _ptr(weight), _ptr(y), _ptr(ys), _ptr(d), _ptr(noise), nbs, _ptr(noise_w), _ptr(bias), _ptr(s_next),
                  b, h, w, cin, cout, int(transposed), int(act), impl, _dt(x), int(out_f32))
-    check(_lib.lib().ood_conv3x3(C.byref(a), _stream()), 'conv3x3')
+    # algorithmic work: 2*B*Co*Ci*9*H*W with H, W the INPUT size for the transposed form
+    with _timed('conv3x3_tc' if impl == 0 else 'conv3x3_simt', 2.0 * b * cout * cin * 9 * h * w):
+        check(_lib.lib().ood_conv3x3(C.byref(a), _stream()), 'conv3x3')
     return y, ys
 
 
@@ -207,7 +250,11 @@ def blur_act(t, taps, d=None, noise=None, noise_w=None, bias=None, s_next=None, 
     a = BlurActArgs(_ptr(t), int(t.dtype == torch.float32 and dtype != torch.float32), _ptr(img), _ptr(y), _ptr(ys), _ptr(d),
                     _ptr(noise), _ptr(noise_w), _ptr(bias), _ptr(s_next), nbs, (C.c_float * 4)(*taps), b, ih, iw, c,
                     int(act), F32 if dtype == torch.float32 else BF16)
-    check(_lib.lib().ood_blur_act(C.byref(a), _stream()), 'blur_act')
+    nout = sum(o is not None for o in (img, y, ys))
+    work = b * c * (ih * iw * _esize(t) + nout * (ih - 1) * (iw - 1) * (4 if dtype == torch.float32 else 2)) + \
+        (0 if noise is None else noise.shape[0] * (ih - 1) * (iw - 1) * 4)
+    with _timed('blur_act', work):
+        check(_lib.lib().ood_blur_act(C.byref(a), _stream()), 'blur_act')
     return img, y, ys
 
 
@@ -218,8 +265,10 @@ def noise_act(img, noise, noise_w, bias, s_next=None, want_y=True, want_ys=False
     y = torch.empty_like(img) if want_y else None
     ys = torch.empty_like(img) if want_ys else None
     nbs = 0 if (noise is None or noise.shape[0] == 1) else h * w
-    check(_lib.lib().ood_noise_act(_ptr(img), _ptr(y), _ptr(ys), _ptr(noise), nbs, _ptr(noise_w), _ptr(bias), _ptr(s_next),
-                                   b, h * w, c, _dt(img), _stream()), 'noise_act')
+    nout = (y is not None) + (ys is not None)
+    with _timed('noise_act', b * h * w * (c * _esize(img) * (1 + nout) + 4)):
+        check(_lib.lib().ood_noise_act(_ptr(img), _ptr(y), _ptr(ys), _ptr(noise), nbs, _ptr(noise_w), _ptr(bias), _ptr(s_next),
+                                       b, h * w, c, _dt(img), _stream()), 'noise_act')
     return y, ys
 
 
@@ -230,8 +279,10 @@ def torgb(y, wrgb, bias, skip=None, taps_up=None):
     b, h, w, c = y.shape
     out = torch.empty(b, 3, h, w, device=y.device, dtype=torch.float32)
     taps = (C.c_float * 4)(*(taps_up or fir_taps(gain=2.0)))
-    check(_lib.lib().ood_torgb(_ptr(y), _ptr(wrgb), _ptr(_f32c(bias).reshape(-1)), _ptr(skip), _ptr(out), taps, b, h, w, c,
-                               _dt(y), _stream()), 'torgb')
+    work = b * h * w * (c * _esize(y) + 3 * 4 + (0 if skip is None else 3)) 
+    with _timed('torgb', work):
+        check(_lib.lib().ood_torgb(_ptr(y), _ptr(wrgb), _ptr(_f32c(bias).reshape(-1)), _ptr(skip), _ptr(out), taps, b, h, w, c,
+                                   _dt(y), _stream()), 'torgb')
     return out
 
 
@@ -254,7 +305,19 @@ def warp_mix(gen, field):
     assert gen.is_contiguous()
     b, h, w, c = gen.shape
     out = torch.empty_like(gen)
-    check(_lib.lib().ood_warp_mix(_ptr(gen), _ptr(_f32c(field)), _ptr(out), b, h, w, c, _dt(gen), _stream()), 'warp_mix')
+    with _timed('warp_mix', b * h * w * (2 * c * _esize(gen) + 3 * 4)):
+        check(_lib.lib().ood_warp_mix(_ptr(gen), _ptr(_f32c(field)), _ptr(out), b, h, w, c, _dt(gen), _stream()), 'warp_mix')
+    return out
+
+
+def bicubic_up_add(x, y):
+    """x NHWC [B,h,w,C], y NHWC [B,H,W,C] -> bicubic_up(x, align_corners=True) + y (NHWC)"""
+    _cuda(x, y)
+    assert x.is_contiguous() and y.is_contiguous() and x.dtype == y.dtype
+    b, h, w, c = x.shape
+    _, H, W, _ = y.shape
+    out = torch.empty_like(y)
+    check(_lib.lib().ood_bicubic_up_add(_ptr(x), _ptr(y), _ptr(out), b, h, w, H, W, c, _dt(x), _stream()), 'bicubic_up_add')
     return out
 
 
@@ -269,7 +332,9 @@ def mask_blend(fields, x, gen, want_alpha=True):
     n = len(fields)
     ptrs = (C.c_void_p * n)(*[f.data_ptr() for f in fields])
     sizes = (C.c_int * n)(*[f.shape[-1] for f in fields])
-    check(_lib.lib().ood_mask_blend(ptrs, sizes, n, _ptr(x), _ptr(gen), _ptr(out), _ptr(alpha), b, s, _stream()), 'mask_blend')
+    work = b * (3 * 3 * s * s * 4 + (s * s * 4 if want_alpha else 0) + sum(f.shape[-1] ** 2 * 4 for f in fields))
+    with _timed('mask_blend', work):
+        check(_lib.lib().ood_mask_blend(ptrs, sizes, n, _ptr(x), _ptr(gen), _ptr(out), _ptr(alpha), b, s, _stream()), 'mask_blend')
     return out, alpha
 
 

@@ -36,6 +36,9 @@ class bottleneck_IR(nn.Module):
                                        nn.PReLU(depth), nn.Conv2d(depth, depth, (3, 3), stride, 1, bias=bias), BN(depth, bn=bn))
 
     def forward(self, x):
+        if isinstance(self.shortcut_layer, nn.MaxPool2d):       # MaxPool2d(1, s) == strided subsampling: no kernel needed
+            s = self.shortcut_layer.stride
+            return self.res_layer(x) + (x if s == 1 else x[:, :, ::s, ::s])
         return self.res_layer(x) + self.shortcut_layer(x)
 
 

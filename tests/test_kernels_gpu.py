@@ -352,3 +352,15 @@ def test_errors_are_loud():
     with pytest.raises(RuntimeError):
         K().conv3x3(torch.zeros(1, 4, 4, 24, device=DEV, dtype=torch.bfloat16), torch.zeros(9, 32, 24, device=DEV,
                     dtype=torch.bfloat16), 32, impl=0)                                              # cin % 32
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_bicubic_up_add(dtype):
+    x, y = rnd(2, 16, 8, 8, seed=1).to(dtype).float(), rnd(2, 16, 16, 16, seed=2).to(dtype).float()
+    ref = F.interpolate(x, size=(16, 16), mode='bicubic', align_corners=True) + y
+    out = K().bicubic_up_add(nhwc(x, dtype), nhwc(y, dtype))
+    tol = dict(rtol=1e-5, atol=1e-5) if dtype == torch.float32 else dict(rtol=2e-2, atol=2e-2)
+    torch.testing.assert_close(nchw(out), ref, **tol)
+    x2, y2 = rnd(1, 8, 5, 7, seed=3).to(dtype).float(), rnd(1, 8, 9, 16, seed=4).to(dtype).float()     # non-integer ratio
+    ref2 = F.interpolate(x2, size=(9, 16), mode='bicubic', align_corners=True) + y2
+    torch.testing.assert_close(nchw(K().bicubic_up_add(nhwc(x2, dtype), nhwc(y2, dtype))), ref2, **tol)
