@@ -108,6 +108,8 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--batch', type=int, default=BATCH)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--ncu', action='store_true', help='run warm-up, then ONE step between cudaProfilerStart/Stop and exit '
+                    '(for `ncu --profile-from-start off`; never a bench value)')
     ap.add_argument('--profile', action='store_true', help='print a torch.profiler kernel table for one step (not a bench value)')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', 0))
@@ -170,6 +172,13 @@ def main():
     for _ in range(max(args.warmup, 3)):
         step_resident()
     barrier()
+
+    if args.ncu:
+        torch.cuda.profiler.start()
+        step_resident()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return 0
 
     if args.profile and rank == 0:
         from torch.profiler import ProfilerActivity, profile

@@ -1,0 +1,104 @@
+"""Host-side logic that needs no GPU: module trees / state-dict keys, pad arithmetic, conditioning schedule, loud
+CPU-tensor errors, and the N>1 sharding + max-over-ranks reduction over gloo (world_size 2)."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+from oracle import ood as oood, stylegan as ostyle
+
+
+def test_generator_state_dict_keys_match_reference_layout():
+    from ood_gan_inversion_b200.stylegan import Generator
+    for size in (16, 256, 1024):
+        sd = ostyle.synthetic_generator_state(size, seed=1)     # key names pinned against the reference by make_golden.py
+        g = Generator(size, 512, 8)
+        assert set(g.state_dict().keys()) == set(sd.keys())
+        g.load_state_dict(sd, strict=True)
+    assert len(Generator(1024, 512, 8).state_dict()) == 171
+    assert Generator(1024, 512, 8).n_latent == 18
+
+
+def test_full_arch_state_dict_and_schedule():
+    from ood_gan_inversion_b200.arch import ood_faceGAN_e4e
+    net = ood_faceGAN_e4e(out_size=1024, warp_scale=0.08, cycle_align=2, ModSize=256)
+    sd = oood.synthetic_ood_state(1024, seed=0)
+    net.load_state_dict(sd, strict=True)
+    assert len(net.state_dict()) == 882
+    feats = [torch.zeros(1, 1, r, r) for r in (256, 128, 64, 32)]
+    conds = net.feats2condition(feats)
+    assert len(conds) == 4 and [(2 * (k + 2)) + 1 for k in range(len(conds))] == [5, 7, 9, 11]
+    net.ModSize = 64
+    assert len(net.feats2condition(feats)) == 2
+    n_params = sum(p.numel() for p in net.parameters())
+    assert abs(n_params - 341.49e6) < 0.05e6
+
+
+def test_pad_arithmetic_and_kernels():
+    from ood_gan_inversion_b200.stylegan import Blur, Downsample, ModulatedConv2d, Upsample, make_kernel
+    k = make_kernel([1, 3, 3, 1])
+    assert k.shape == (4, 4) and abs(float(k.sum()) - 1) < 1e-6
+    assert Upsample([1, 3, 3, 1]).pad == (2, 1) and float(Upsample([1, 3, 3, 1]).kernel.sum()) == pytest.approx(4.0)
+    assert Downsample([1, 3, 3, 1]).pad == (1, 1)
+    assert ModulatedConv2d(8, 8, 3, 8, upsample=True).blur.pad == (1, 1)
+    assert ModulatedConv2d(8, 8, 3, 8, downsample=True).blur.pad == (2, 2)
+    assert Blur([1, 3, 3, 1], (1, 1), upsample_factor=2).taps == pytest.approx([0.25, 0.75, 0.75, 0.25])
+    assert ostyle.up_blur_pads() == (1, 1) and ostyle.skip_up_pads() == (2, 1)
+
+
+def test_cpu_tensors_raise():
+    from ood_gan_inversion_b200.op import fused_leaky_relu, upfirdn2d
+    from ood_gan_inversion_b200.stylegan import Generator
+    with pytest.raises(RuntimeError, match='CUDA-only'):
+        upfirdn2d(torch.zeros(1, 1, 4, 4), torch.ones(4, 4))
+    with pytest.raises(RuntimeError, match='CUDA-only'):
+        fused_leaky_relu(torch.zeros(2, 4), torch.zeros(4))
+    with pytest.raises(RuntimeError, match='CUDA-only'):
+        Generator(16, 512, 2)(torch.zeros(1, 6, 512), input_is_tensor=True, input_is_latent=True)
+
+
+def test_shard_bounds_cover_the_batch():
+    from ood_gan_inversion_b200.sharding import shard_bounds
+    for total, world in [(256, 8), (256, 4), (16, 3), (5, 8), (0, 2)]:
+        spans = [shard_bounds(total, world, r) for r in range(world)]
+        assert spans[0][0] == 0 and spans[-1][1] == total
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        sizes = [hi - lo for lo, hi in spans]
+        assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        shard_bounds(4, 2, 2)
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from ood_gan_inversion_b200.sharding import aggregate_throughput, max_over_ranks, shard_bounds
+    dist.init_process_group('gloo', init_method=f'tcp://127.0.0.1:{port}', rank=rank, world_size=world)
+    lo, hi = shard_bounds(33, world, rank)
+    ms = 100.0 * (rank + 1)                     # rank 1 is the slow one
+    slowest = max_over_ranks(ms)
+    thr = aggregate_throughput(hi - lo, ms)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (lo, hi))
+    dist.barrier()
+    dist.destroy_process_group()
+    q.put((rank, slowest, thr, gathered))
+
+
+def test_two_rank_gloo_sharding_and_timing():
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, slowest, thr, gathered in res:
+        assert slowest == pytest.approx(200.0)                       # max over ranks, not the local time
+        assert thr == pytest.approx(33 / 0.2)                        # all units / slowest rank
+        assert gathered == [(0, 17), (17, 33)]
