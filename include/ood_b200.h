@@ -111,10 +111,11 @@ typedef struct {
     const float *s_next;   /* [B,Co]; required iff out_ys */
     int batch, h, w, cin, cout;
     int transposed;        /* 0 | 1 */
-    int act;               /* 0 | 1 */
+    int act;               /* 0 none | 1 leaky-ReLU(0.2)*sqrt2 | 2 PReLU(prelu_slope[o]) (AlignNet, shared-weight mode) */
     int impl;              /* 0 tcgen05 | 1 simt */
     int dtype;             /* storage type of in / out */
     int out_f32;           /* 1: out_y is fp32 regardless of dtype (raw accumulators of the transposed conv) */
+    const float *prelu_slope; /* [Co], act == 2 */
 } ood_conv3x3_args;
 int ood_conv3x3(const ood_conv3x3_args *args_host, void *stream);
 
@@ -166,6 +167,24 @@ int ood_field_step(const float *z, const float *prev, const float *coarse, float
  *      x [B,h,w,C], y / out [B,H,W,C] (y may be NULL).  ATen's channels-last bicubic costs 40 ms per call at B=16. */
 int ood_bicubic_up_add(const void *x, const void *y, void *out, int batch, int h, int w, int H, int W, int channels,
                        int dtype, void *stream);
+
+/* ---- a11. AlignNet instance norms on NHWC (SAMM/helpers.py:96-101, e4e/encoders/helpers.py:93-99,426-448).
+ *      ood_in_stats: per-(b,c) moments over the pixels.  y == NULL: stats[b][c] = {mean, rstd}.
+ *      y != NULL (pair): stats[b][c] = {mean_x, rstd_x, mean_y, rstd_y, rstd_d, rstd_e2} where, with a = IN(x), e = IN(y),
+ *      rstd_d = rsqrt(var(a-e)+eps) and rstd_e2 = rsqrt(var(e)+eps): the moments of z0 = cat[a-e, e] without a pass over z0.
+ *      workspace: ood_in_stats_workspace() bytes (two-stage deterministic reduction, no float atomics).
+ *      ood_alignnet_front: out[.,0:C] = (a-e)*rstd_d*w+bias, out[.,C:2C] = e*rstd_e2*w+bias   (= INaff(z0), block-0 conv input)
+ *      ood_alignnet_res0 : out = INaff(t; st2, w, bias) + z0 (z0 re-derived from cur/enc/st6)   (block-0 output, 2C channels)
+ *      ood_in_apply      : out = (x-mean)*rstd*w + bias. */
+int64_t ood_in_stats_workspace(int batch, int64_t pixels, int channels, int pair);
+int ood_in_stats(const void *x, const void *y, float *workspace, float *stats, int batch, int64_t pixels, int channels,
+                 float eps, int dtype, void *stream);
+int ood_alignnet_front(const void *cur, const void *enc, const float *st6, const float *w, const float *bias, void *out,
+                       int batch, int64_t pixels, int channels, int dtype, void *stream);
+int ood_alignnet_res0(const void *t, const float *st2, const float *w, const float *bias, const void *cur, const void *enc,
+                      const float *st6, void *out, int batch, int64_t pixels, int channels, int dtype, void *stream);
+int ood_in_apply(const void *x, const float *st2, const float *w, const float *bias, void *out, int batch, int64_t pixels,
+                 int channels, int dtype, void *stream);
 
 /* ---- a11. warp + alpha mix (helpers.py:168-177) on NHWC features:
  *      out[b,y,x,:] = bilinear(gen[b], lin_x[x]+dx, lin_y[y]+dy)*alpha + gen[b,y,x,:]*(1-alpha)

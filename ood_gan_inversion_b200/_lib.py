@@ -17,7 +17,7 @@ class ConvArgs(C.Structure):
     _fields_ = [('inp', c_void_p), ('weight', c_void_p), ('out_y', c_void_p), ('out_ys', c_void_p), ('d', c_void_p),
                 ('noise', c_void_p), ('noise_bstride', c_i64), ('noise_w', c_void_p), ('bias', c_void_p),
                 ('s_next', c_void_p), ('batch', c_int), ('h', c_int), ('w', c_int), ('cin', c_int), ('cout', c_int),
-                ('transposed', c_int), ('act', c_int), ('impl', c_int), ('dtype', c_int), ('out_f32', c_int)]
+                ('transposed', c_int), ('act', c_int), ('impl', c_int), ('dtype', c_int), ('out_f32', c_int), ('prelu_slope', c_void_p)]
 
 
 class BlurActArgs(C.Structure):
@@ -53,6 +53,12 @@ _SIGS = {
     'ood_field_step': ([c_void_p, c_void_p, c_void_p, c_void_p, C.POINTER(c_float), c_float, c_int, c_int, c_int,
                         c_void_p], c_int),
     'ood_bicubic_up_add': ([c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p], c_int),
+    'ood_in_stats_workspace': ([c_int, c_i64, c_int, c_int], c_i64),
+    'ood_in_stats': ([c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_i64, c_int, c_float, c_int, c_void_p], c_int),
+    'ood_alignnet_front': ([c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_i64, c_int, c_int, c_void_p], c_int),
+    'ood_alignnet_res0': ([c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_i64, c_int,
+                           c_int, c_void_p], c_int),
+    'ood_in_apply': ([c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_i64, c_int, c_int, c_void_p], c_int),
     'ood_warp_mix': ([c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p], c_int),
     'ood_mask_blend': ([C.POINTER(c_void_p), C.POINTER(c_int), c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                         c_void_p], c_int),

@@ -63,8 +63,15 @@ struct ConvEpilogue {
     void *out_y, *out_ys;
     const float *d, *noise, *noise_w, *bias, *s_next;
     int64_t noise_bstride;
-    int act;
+    int act;                // 0 none | 1 leaky-ReLU(0.2)*sqrt2 | 2 PReLU(prelu[c])
     int out_f32;
+    const float *prelu;     // [Co], act == 2
 };
+
+__device__ __forceinline__ float apply_act(float v, int act, float slope) {
+    if (act == 1) return lrelu_sqrt2(v);
+    if (act == 2) return v > 0.f ? v : v * slope;
+    return v;
+}
 
 }  // namespace ood

@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const SimtParams p) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             v[j] = fmaf(acc[i][j], dd[j], nz) + bias[j];
-            if (p.ep.act) v[j] = lrelu_sqrt2(v[j]);
+            v[j] = apply_act(v[j], p.ep.act, p.ep.act == 2 ? p.ep.prelu[n + j] : 0.f);
         }
         if (p.ep.out_y) *reinterpret_cast<float4 *>((float *)p.ep.out_y + pix * cout + n) = make_float4(v[0], v[1], v[2], v[3]);
         if (p.ep.out_ys) {
@@ -123,7 +123,7 @@ int conv3x3_simt(const ood_conv3x3_args &a, cudaStream_t st) {
     p.in = (const float *)a.in;
     p.w = (const float *)a.weight;
     p.g = make_geom(a.batch, a.h, a.w, a.cin, a.cout, a.transposed);
-    p.ep = ConvEpilogue{a.out_y, a.out_ys, a.d, a.noise, a.noise_w, a.bias, a.s_next, a.noise_bstride, a.act, 1};
+    p.ep = ConvEpilogue{a.out_y, a.out_ys, a.d, a.noise, a.noise_w, a.bias, a.s_next, a.noise_bstride, a.act, 1, a.prelu_slope};
     int mmax = 0;
     for (int i = 0; i < p.g.nphases; ++i) mmax = std::max(mmax, p.g.ph[i].m_total);
     dim3 grid(ceil_div(mmax, SBM), ceil_div(a.cout, SBN), p.g.nphases);

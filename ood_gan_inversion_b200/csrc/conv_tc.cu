@@ -274,9 +274,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
                         }
                     }
-                    if (p.ep.act) {
+                    if (p.ep.act == 1) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = lrelu_sqrt2(v[j] + nz);
+                    } else if (p.ep.act == 2) {
+                        const float4 *pp = reinterpret_cast<const float4 *>(p.ep.prelu + n);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 t = __ldg(pp + j);
+                            v[4 * j] = apply_act(v[4 * j] + nz, 2, t.x); v[4 * j + 1] = apply_act(v[4 * j + 1] + nz, 2, t.y);
+                            v[4 * j + 2] = apply_act(v[4 * j + 2] + nz, 2, t.z); v[4 * j + 3] = apply_act(v[4 * j + 3] + nz, 2, t.w);
+                        }
                     } else if (p.ep.noise) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] += nz;
@@ -392,7 +400,7 @@ int conv3x3_tc(const ood_conv3x3_args &a, cudaStream_t st) {
         tiles += P.tiles_x * P.tiles_y * P.tiles_b * p.n_tiles_n;
     }
     p.total_tiles = tiles;
-    p.ep = ConvEpilogue{a.out_y, a.out_ys, a.d, a.noise, a.noise_w, a.bias, a.s_next, a.noise_bstride, a.act, a.out_f32};
+    p.ep = ConvEpilogue{a.out_y, a.out_ys, a.d, a.noise, a.noise_w, a.bias, a.s_next, a.noise_bstride, a.act, a.out_f32, a.prelu_slope};
     p.out_bf16 = 1;
 
     CUtensorMap tmA, tmB;
@@ -437,6 +445,7 @@ extern "C" int ood_conv3x3(const ood_conv3x3_args *a, void *stream) {
     OOD_REQUIRE(!a->transposed || (!a->out_ys && !a->act && !a->noise && !a->bias),
                 "conv3x3: the transposed form writes raw accumulators (the epilogue follows the blur)");
     OOD_REQUIRE(!(a->out_f32 && a->out_ys), "conv3x3: out_f32 applies to out_y only");
+    OOD_REQUIRE(a->act >= 0 && a->act <= 2 && (a->act != 2 || a->prelu_slope), "conv3x3: act must be 0, 1 or 2 (PReLU needs prelu_slope)");
     cudaStream_t st = (cudaStream_t)stream;
     if (a->impl == 1) return conv3x3_simt(*a, st);
     OOD_REQUIRE(a->impl == 0, "conv3x3: impl must be 0 (tcgen05) or 1 (simt)");

@@ -212,7 +212,7 @@ def torgb_weight(w, s, scale=None):
 
 # ----------------------------------------------------------------------------------------------- convolution
 def conv3x3(x, weight, cout, transposed=False, impl=0, d=None, noise=None, noise_w=None, bias=None, s_next=None,
-            act=False, want_y=True, want_ys=False, out_f32=False):
+            act=False, want_y=True, want_ys=False, out_f32=False, prelu=None):
     """x NHWC [B,H,W,Ci] pre-modulated; weight packed for `impl`.  Returns (y, ys) (None where not requested)."""
     _cuda(x, weight, d, noise, noise_w, bias, s_next)
     assert x.is_contiguous()
@@ -225,7 +225,7 @@ def conv3x3(x, weight, cout, transposed=False, impl=0, d=None, noise=None, noise
         assert noise.dtype == torch.float32 and noise.is_contiguous() and noise.shape[-2:] == (oh, ow)
         nbs = 0 if noise.shape[0] == 1 else oh * ow
     a = ConvArgs(_ptr(x), _ptr(weight), _ptr(y), _ptr(ys), _ptr(d), _ptr(noise), nbs, _ptr(noise_w), _ptr(bias), _ptr(s_next),
-                 b, h, w, cin, cout, int(transposed), int(act), impl, _dt(x), int(out_f32))
+                 b, h, w, cin, cout, int(transposed), 2 if prelu is not None else int(act), impl, _dt(x), int(out_f32), _ptr(prelu))
     # algorithmic work: 2*B*Co*Ci*9*H*W with H, W the INPUT size for the transposed form
     with _timed('conv3x3_tc' if impl == 0 else 'conv3x3_simt', 2.0 * b * cout * cin * 9 * h * w):
         check(_lib.lib().ood_conv3x3(C.byref(a), _stream()), 'conv3x3')
@@ -307,6 +307,47 @@ def warp_mix(gen, field):
     out = torch.empty_like(gen)
     with _timed('warp_mix', b * h * w * (2 * c * _esize(gen) + 3 * 4)):
         check(_lib.lib().ood_warp_mix(_ptr(gen), _ptr(_f32c(field)), _ptr(out), b, h, w, c, _dt(gen), _stream()), 'warp_mix')
+    return out
+
+
+def in_stats(x, y=None, eps=1e-5):
+    """x (and y) NHWC [B,H,W,C] -> stats [B,C,2] = (mean, rstd), or for a pair [B,C,6] (see ood_b200.h)."""
+    _cuda(x, y)
+    assert x.is_contiguous() and (y is None or (y.is_contiguous() and y.shape == x.shape and y.dtype == x.dtype))
+    b, h, w, c = x.shape
+    ws = torch.empty(_lib.lib().ood_in_stats_workspace(b, h * w, c, int(y is not None)) // 4, device=x.device, dtype=torch.float32)
+    st = torch.empty(b, c, 6 if y is not None else 2, device=x.device, dtype=torch.float32)
+    with _timed('in_stats', b * h * w * c * _esize(x) * (2 if y is not None else 1)):
+        check(_lib.lib().ood_in_stats(_ptr(x), _ptr(y), _ptr(ws), _ptr(st), b, h * w, c, float(eps), _dt(x), _stream()), 'in_stats')
+    return st
+
+
+def alignnet_front(cur, enc, st6, w, bias):
+    _cuda(cur, enc, st6, w, bias)
+    b, h, wd, c = cur.shape
+    out = torch.empty(b, h, wd, 2 * c, device=cur.device, dtype=cur.dtype)
+    with _timed('alignnet_ew', b * h * wd * c * _esize(cur) * 4):
+        check(_lib.lib().ood_alignnet_front(_ptr(cur), _ptr(enc), _ptr(st6), _ptr(w), _ptr(bias), _ptr(out), b, h * wd, c,
+                                            _dt(cur), _stream()), 'alignnet_front')
+    return out
+
+
+def alignnet_res0(t, st2, w, bias, cur, enc, st6):
+    _cuda(t, st2, w, bias, cur, enc, st6)
+    b, h, wd, c = cur.shape
+    out = torch.empty_like(t)
+    with _timed('alignnet_ew', b * h * wd * c * _esize(cur) * 6):
+        check(_lib.lib().ood_alignnet_res0(_ptr(t), _ptr(st2), _ptr(w), _ptr(bias), _ptr(cur), _ptr(enc), _ptr(st6), _ptr(out),
+                                           b, h * wd, c, _dt(cur), _stream()), 'alignnet_res0')
+    return out
+
+
+def in_apply(x, st2, w=None, bias=None):
+    _cuda(x, st2, w, bias)
+    b, h, wd, c = x.shape
+    out = torch.empty_like(x)
+    with _timed('alignnet_ew', b * h * wd * c * _esize(x) * 2):
+        check(_lib.lib().ood_in_apply(_ptr(x), _ptr(st2), _ptr(w), _ptr(bias), _ptr(out), b, h * wd, c, _dt(x), _stream()), 'in_apply')
     return out
 
 

@@ -77,6 +77,56 @@ class AlignNet(nn.Module):
             z = self.body(z)
         return z.float()
 
+    # ---- fused NHWC route: every 2C-channel pass runs on this package's kernels (shared-weight tcgen05 / SIMT conv with
+    # a PReLU epilogue, one-pass pair statistics, re-derived residual); only the 3-channel fp32 tail stays torch ops.
+    def fused_ok(self):
+        convs = [self.body[0].res_layer[1], self.body[0].res_layer[3], self.body[1].res_layer[1], self.body[1].res_layer[3],
+                 self.body[1].shortcut_layer[0]]
+        c2 = convs[0].weight.shape[0]
+        return self.diff_fAndg and all(c.bias is None for c in convs) and c2 % sg._granule() == 0 and \
+            isinstance(self.body[0].res_layer[0], nn.InstanceNorm2d)
+
+    def _packed(self):
+        b0, b1 = self.body[0], self.body[1]
+        params = [b0.res_layer[1].weight, b0.res_layer[3].weight, b1.res_layer[1].weight, b1.shortcut_layer[0].weight]
+        key = (sg.get_precision(), params[0].device) + tuple(p._version for p in params)
+        hit = getattr(self, '_pk', None)
+        if hit is None or hit[0] != key:
+            with torch.no_grad():
+                dt, cim = sg._act_dtype(), sg.get_precision() == 'fp32'
+                g = sg._granule()
+                wc = sg._pad_dim(b1.res_layer[1].weight.detach().float(), 0, g).contiguous()       # 2C -> 3 (zero-padded rows)
+                pk = dict(wa=K.pack_conv_weight(b0.res_layer[1].weight.detach(), dt, cim),
+                          wb=K.pack_conv_weight(b0.res_layer[3].weight.detach(), dt, cim),
+                          wc=K.pack_conv_weight(wc, dt, cim), cp=g,
+                          w1=b1.shortcut_layer[0].weight.detach().float().reshape(3, -1).contiguous())
+            self._pk = (key, pk)
+            hit = self._pk
+        return hit[1]
+
+    def raw_nhwc(self, cur, enc):
+        """cur, enc: NHWC [B,R,R,C] in the pipeline's storage type -> pre-activation field [B,3,R,R] fp32."""
+        b0, b1 = self.body[0], self.body[1]
+        pk = self._packed()
+        f = lambda p: p.detach().float().contiguous()
+        b, r, _, c = cur.shape
+        impl = sg._impl()
+        eps = self.norm.eps
+        st6 = K.in_stats(cur, enc, eps)
+        x = K.alignnet_front(cur, enc, st6, f(b0.res_layer[0].weight), f(b0.res_layer[0].bias))
+        x, _ = K.conv3x3(x, pk['wa'], 2 * c, impl=impl, prelu=f(b0.res_layer[2].weight))
+        x, _ = K.conv3x3(x, pk['wb'], 2 * c, impl=impl)
+        out0 = K.alignnet_res0(x, K.in_stats(x, None, eps), f(b0.res_layer[4].weight), f(b0.res_layer[4].bias), cur, enc, st6)
+        x = K.in_apply(out0, K.in_stats(out0, None, eps), f(b1.res_layer[0].weight), f(b1.res_layer[0].bias))
+        x, _ = K.conv3x3(x, pk['wc'], pk['cp'], impl=impl, out_f32=True)
+        res = x[..., :3].permute(0, 3, 1, 2).float()
+        zero = torch.zeros(3, device=cur.device)
+        sc = K.torgb(out0, pk['w1'].unsqueeze(0).expand(b, -1, -1).contiguous(), zero)      # 1x1 conv 2C -> 3, fp32 NCHW
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):                     # 3-channel fp32 tail
+            sc = b1.shortcut_layer[1](sc)
+            res = b1.res_layer[4](b1.res_layer[3](b1.res_layer[2](res)))
+        return res + sc
+
     def forward(self, source, target, **kwargs):
         z = self.raw(source, target)
         return torch.cat([self.tanh(z[:, 0:1]) * self.scale, self.tanh(z[:, 1:2]) * self.scale, self.sigmoid(z[:, 2:])], dim=1)
@@ -113,10 +163,16 @@ class SPM_Warp(nn.Module):
         Returns (aligned features NHWC, field fp32 [B,3,R,R])."""
         if self.blur.taps is None:
             raise NotImplementedError('ood_gan_inversion_b200: SPM_Warp needs a 4-tap blur kernel')
+        fused = self.body.fused_ok()
         src = source.to(target_nhwc.dtype)
+        if fused:
+            src = src.permute(0, 2, 3, 1).contiguous()               # encoder features -> NHWC once per level
         cur, acc = target_nhwc, None
         for k in range(self.cycle_align):
-            z = self.body.raw(cur.permute(0, 3, 1, 2), src)          # NHWC storage viewed as channels_last NCHW
+            if fused:
+                z = self.body.raw_nhwc(cur, src)
+            else:
+                z = self.body.raw(cur.permute(0, 3, 1, 2), src)      # NHWC storage viewed as channels_last NCHW
             last = k == self.cycle_align - 1
             acc = K.field_step(z, acc, aligned if last else None, self.scale, self.blur.taps)
             cur = K.warp_mix(target_nhwc, acc)

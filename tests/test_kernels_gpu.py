@@ -364,3 +364,54 @@ def test_bicubic_up_add(dtype):
     x2, y2 = rnd(1, 8, 5, 7, seed=3).to(dtype).float(), rnd(1, 8, 9, 16, seed=4).to(dtype).float()     # non-integer ratio
     ref2 = F.interpolate(x2, size=(9, 16), mode='bicubic', align_corners=True) + y2
     torch.testing.assert_close(nchw(K().bicubic_up_add(nhwc(x2, dtype), nhwc(y2, dtype))), ref2, **tol)
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_alignnet_norm_kernels(dtype):
+    b, c, h, w = 2, 32, 50, 70
+    cur, enc = (3 * rnd(b, c, h, w, seed=1) + 1).to(dtype).float(), (0.5 * rnd(b, c, h, w, seed=2) - 2).to(dtype).float()
+    tol = dict(rtol=1e-4, atol=1e-4) if dtype == torch.float32 else dict(rtol=3e-2, atol=3e-2)
+    a, e = osamm.instance_norm(cur), osamm.instance_norm(enc)
+    z0 = torch.cat([a - e, e], 1)
+    w0, b0 = 1 + 0.1 * rnd(2 * c, seed=3), 0.1 * rnd(2 * c, seed=4)
+    st6 = K().in_stats(nhwc(cur, dtype), nhwc(enc, dtype))
+    torch.testing.assert_close(st6[..., 0].cpu(), cur.mean((2, 3)), rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(st6[..., 1].cpu(), torch.rsqrt(cur.var((2, 3), unbiased=False) + 1e-5), rtol=1e-4, atol=1e-4)
+    front = K().alignnet_front(nhwc(cur, dtype), nhwc(enc, dtype), st6, w0.to(DEV), b0.to(DEV))
+    torch.testing.assert_close(nchw(front), osamm.instance_norm(z0, w0, b0), **tol)
+    t = rnd(b, 2 * c, h, w, seed=5).to(dtype).float()
+    st2 = K().in_stats(nhwc(t, dtype))
+    res = K().alignnet_res0(nhwc(t, dtype), st2, w0.to(DEV), b0.to(DEV), nhwc(cur, dtype), nhwc(enc, dtype), st6)
+    torch.testing.assert_close(nchw(res), osamm.instance_norm(t, w0, b0) + z0, **tol)
+    app = K().in_apply(nhwc(t, dtype), st2, w0.to(DEV), b0.to(DEV))
+    torch.testing.assert_close(nchw(app), osamm.instance_norm(t, w0, b0), **tol)
+
+
+@pytest.mark.parametrize('impl', [0, 1])
+def test_conv3x3_prelu_epilogue(impl):
+    b, h, ci, co = 2, 12, 64, 64
+    dt = torch.bfloat16 if impl == 0 else torch.float32
+    x, w = rnd(b, ci, h, h, seed=1).to(dt).float(), (0.1 * rnd(co, ci, 3, 3, seed=2)).to(dt).float()
+    slope = 0.25 + 0.1 * rnd(co, seed=3)
+    y, _ = K().conv3x3(nhwc(x, dt), K().pack_conv_weight(w.to(DEV), dt, impl == 1), co, impl=impl, prelu=slope.to(DEV))
+    ref = F.prelu(F.conv2d(x.double(), w.double(), padding=1).float(), slope)
+    tol = dict(rtol=2e-2, atol=2e-2) if impl == 0 else dict(rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(nchw(y), ref, **tol)
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+def test_spm_warp_fused_route_vs_reference_golden(golden, precision):
+    """Two-level SPM_Warp (AlignNet on the fused NHWC kernels, channel-padded C=8 -> granule) vs the unmodified reference."""
+    import ood_gan_inversion_b200.stylegan as sgm
+    from ood_gan_inversion_b200.samm import StyledscaleNshfitBlock
+    sgm.set_precision(precision)
+    G = golden('samm.pt')
+    blk = StyledscaleNshfitBlock(8, 8, 512, scale=0.08, btn=None, cycle_align=2, diff_fAndg=True).to(DEV)
+    blk.load_state_dict(G['sd'])
+    tol = dict(rtol=1e-3, atol=2e-4) if precision == 'fp32' else dict(rtol=5e-2, atol=2e-2)
+    a1, f1 = blk(G['enc'].to(DEV), None, image=G['gen'].to(DEV), aligned=None)
+    torch.testing.assert_close(f1.cpu(), G['field'], **tol)
+    torch.testing.assert_close(a1.cpu(), G['aligned'], **(tol if precision == 'fp32' else dict(rtol=5e-2, atol=5e-2)))
+    a2, f2 = blk(G['enc2'].to(DEV), None, image=G['gen2'].to(DEV), aligned=f1)
+    torch.testing.assert_close(f2.cpu(), G['field2'], **tol)
+    sgm.set_precision('bf16')
