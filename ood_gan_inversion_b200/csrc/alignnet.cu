@@ -9,7 +9,7 @@
 
 namespace ood {
 
-constexpr int kStatChunk = 2048;   // pixels per partial-sum block
+constexpr int kStatChunk = 512;    // pixels per partial-sum block
 
 // ---------------------------------------------------------------------------------------------- statistics
 // partial[b][chunk][c][K]: K = 2 (sum x, sum x^2) or 5 (+ sum y, sum y^2, sum xy)
@@ -29,6 +29,7 @@ __global__ void __launch_bounds__(256) in_partial_kernel(const T *__restrict__ x
 #pragma unroll
         for (int k = 0; k < K; ++k) acc[j][k] = 0.f;
     if (lane < lanes) {
+#pragma unroll 4
         for (int64_t p = p0 + lane; p < p1; p += lanes) {
             const int64_t off = ((int64_t)b * P + p) * C + vec * N;
             const Vec<T> xv = load_vec<T>(x + off);
@@ -104,6 +105,36 @@ __global__ void in_finalize_kernel(const float *__restrict__ partial, float *__r
 }
 
 // ---------------------------------------------------------------------------------------------- elementwise passes
+// Skeleton shared by the passes below: a thread owns ONE 16-byte channel vector and walks down a chunk of pixels, so the
+// per-(b,c) coefficients are folded once into registers and the loop body is pure vector load / FMA / vector store.
+struct PixSpan {
+    int c;              // first channel of this thread's vector
+    int64_t p, p_end;   // pixel range of this thread
+    int step;
+    bool active;
+};
+template <int N>
+__device__ __forceinline__ PixSpan pix_span(int C, int64_t P, int64_t chunk) {
+    const int cv = C / N;
+    const int lanes = blockDim.x / cv;
+    const int vec = threadIdx.x % cv, lane = threadIdx.x / cv;
+    PixSpan s;
+    s.c = vec * N;
+    s.active = lane < lanes;
+    const int64_t p0 = (int64_t)blockIdx.x * chunk;
+    s.p = p0 + lane;
+    s.p_end = min(p0 + chunk, P);
+    s.step = lanes;
+    return s;
+}
+static inline void pix_grid(int C, int N, int64_t P, int batch, dim3 &grid, int64_t &chunk) {
+    const int lanes = std::max(1, 256 / (C / N));
+    const int64_t want_blocks = std::max<int64_t>(1, (int64_t)kNumSMs * 8 / batch);
+    chunk = std::max<int64_t>((P + want_blocks - 1) / want_blocks, (int64_t)lanes * 4);
+    chunk = (chunk + lanes - 1) / lanes * lanes;
+    grid = dim3((unsigned)((P + chunk - 1) / chunk), batch);
+}
+
 // mode 0 (front): out[b,p,0:C]  = (IN(cur)-IN(enc)) * rstd_d * w[c]   + bias[c]
 //                 out[b,p,C:2C] =  IN(enc)          * rstd_e2 * w[C+c] + bias[C+c]          (conv input of block 0)
 // mode 1 (res0):  out = (t - mu_t) * rstd_t * w + bias + z0,  z0 = cat[IN(cur)-IN(enc), IN(enc)]   (block-0 output)
@@ -112,29 +143,48 @@ __global__ void __launch_bounds__(256) alignnet_ew_kernel(const T *__restrict__ 
                                                            const float *__restrict__ st6, const T *__restrict__ t,
                                                            const float *__restrict__ st2, const float *__restrict__ w,
                                                            const float *__restrict__ bias, T *__restrict__ out, int64_t P,
-                                                           int C) {
+                                                           int C, int64_t chunk) {
     constexpr int N = Vec<T>::N;
-    const int cv = C / N;
     const int b = blockIdx.y;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < P * cv; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t pix = i / cv;
-        const int c = (int)(i - pix * cv) * N;
-        const int64_t off1 = ((int64_t)b * P + pix) * C + c;           // C-channel tensors
-        const int64_t off2 = ((int64_t)b * P + pix) * 2 * C + c;       // 2C-channel tensors (first half)
-        const Vec<T> cu = load_vec<T>(cur + off1), en = load_vec<T>(enc + off1);
-        Vec<T> lo, hi, tl, th;
-        if constexpr (MODE == 1) { tl = load_vec<T>(t + off2); th = load_vec<T>(t + off2 + C); }
+    const PixSpan sp = pix_span<N>(C, P, chunk);
+    if (!sp.active) return;
+    // lo = tl*ct_lo + cu*a1 + en*a2 + a3 ; hi = th*ct_hi + en*b1 + b2
+    float a1[N], a2[N], a3[N], b1[N], b2[N], ctl[N], cth[N];
 #pragma unroll
-        for (int j = 0; j < N; ++j) {
-            const float *s = st6 + ((int64_t)b * C + c + j) * 6;
-            const float a = (cu.v[j] - s[0]) * s[1], e = (en.v[j] - s[2]) * s[3];
-            if constexpr (MODE == 0) {
-                lo.v[j] = (a - e) * s[4] * w[c + j] + bias[c + j];
-                hi.v[j] = e * s[5] * w[C + c + j] + bias[C + c + j];
-            } else {
-                const float *q0 = st2 + ((int64_t)b * 2 * C + c + j) * 2, *q1 = st2 + ((int64_t)b * 2 * C + C + c + j) * 2;
-                lo.v[j] = (tl.v[j] - q0[0]) * q0[1] * w[c + j] + bias[c + j] + (a - e);
-                hi.v[j] = (th.v[j] - q1[0]) * q1[1] * w[C + c + j] + bias[C + c + j] + e;
+    for (int j = 0; j < N; ++j) {
+        const int c = sp.c + j;
+        const float *s = st6 + ((int64_t)b * C + c) * 6;
+        const float mc = s[0], rc = s[1], me = s[2], re = s[3];
+        if constexpr (MODE == 0) {
+            const float gl = s[4] * w[c], gh = s[5] * w[C + c];
+            a1[j] = rc * gl; a2[j] = -re * gl; a3[j] = (me * re - mc * rc) * gl + bias[c];
+            b1[j] = re * gh; b2[j] = -me * re * gh + bias[C + c];
+            ctl[j] = cth[j] = 0.f;
+        } else {
+            const float *q0 = st2 + ((int64_t)b * 2 * C + c) * 2, *q1 = st2 + ((int64_t)b * 2 * C + C + c) * 2;
+            ctl[j] = q0[1] * w[c]; cth[j] = q1[1] * w[C + c];
+            a1[j] = rc; a2[j] = -re; a3[j] = (me * re - mc * rc) - q0[0] * ctl[j] + bias[c];
+            b1[j] = re; b2[j] = -me * re - q1[0] * cth[j] + bias[C + c];
+        }
+    }
+#pragma unroll 2
+    for (int64_t p = sp.p; p < sp.p_end; p += sp.step) {
+        const int64_t off1 = ((int64_t)b * P + p) * C + sp.c;
+        const int64_t off2 = ((int64_t)b * P + p) * 2 * C + sp.c;
+        const Vec<T> cu = load_vec<T>(cur + off1), en = load_vec<T>(enc + off1);
+        Vec<T> lo, hi;
+        if constexpr (MODE == 1) {
+            const Vec<T> tl = load_vec<T>(t + off2), th = load_vec<T>(t + off2 + C);
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+                lo.v[j] = fmaf(tl.v[j], ctl[j], fmaf(cu.v[j], a1[j], fmaf(en.v[j], a2[j], a3[j])));
+                hi.v[j] = fmaf(th.v[j], cth[j], fmaf(en.v[j], b1[j], b2[j]));
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+                lo.v[j] = fmaf(cu.v[j], a1[j], fmaf(en.v[j], a2[j], a3[j]));
+                hi.v[j] = fmaf(en.v[j], b1[j], b2[j]);
             }
         }
         store_vec<T>(out + off2, lo);
@@ -146,19 +196,24 @@ __global__ void __launch_bounds__(256) alignnet_ew_kernel(const T *__restrict__ 
 template <typename T>
 __global__ void __launch_bounds__(256) in_apply_kernel(const T *__restrict__ x, const float *__restrict__ st2,
                                                         const float *__restrict__ w, const float *__restrict__ bias,
-                                                        T *__restrict__ out, int64_t P, int C) {
+                                                        T *__restrict__ out, int64_t P, int C, int64_t chunk) {
     constexpr int N = Vec<T>::N;
-    const int cv = C / N;
     const int b = blockIdx.y;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < P * cv; i += (int64_t)gridDim.x * blockDim.x) {
-        const int c = (int)(i % cv) * N;
-        const int64_t off = (int64_t)b * P * C + i * N;
+    const PixSpan sp = pix_span<N>(C, P, chunk);
+    if (!sp.active) return;
+    float g[N], h[N];
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+        const float *q = st2 + ((int64_t)b * C + sp.c + j) * 2;
+        g[j] = q[1] * (w ? w[sp.c + j] : 1.f);
+        h[j] = (bias ? bias[sp.c + j] : 0.f) - q[0] * g[j];
+    }
+#pragma unroll 4
+    for (int64_t p = sp.p; p < sp.p_end; p += sp.step) {
+        const int64_t off = ((int64_t)b * P + p) * C + sp.c;
         Vec<T> v = load_vec<T>(x + off);
 #pragma unroll
-        for (int j = 0; j < N; ++j) {
-            const float *q = st2 + ((int64_t)b * C + c + j) * 2;
-            v.v[j] = (v.v[j] - q[0]) * q[1] * (w ? w[c + j] : 1.f) + (bias ? bias[c + j] : 0.f);
-        }
+        for (int j = 0; j < N; ++j) v.v[j] = fmaf(v.v[j], g[j], h[j]);
         store_vec<T>(out + off, v);
     }
 }
@@ -213,13 +268,14 @@ extern "C" int ood_alignnet_front(const void *cur, const void *enc, const float 
     const int N = dtype == OOD_F32 ? 4 : 8;
     OOD_REQUIRE(dtype == OOD_F32 || dtype == OOD_BF16, "alignnet_front: bad dtype");
     OOD_REQUIRE(channels % N == 0, "alignnet_front: channels (%d) must be a multiple of %d", channels, N);
-    const int64_t work = pixels * (channels / N);
-    dim3 grid((unsigned)std::min<int64_t>((work + 255) / 256, kNumSMs * 16), batch);
+    OOD_REQUIRE(channels / N <= 256, "alignnet_front: too many channels (%d)", channels);
+    dim3 grid; int64_t chunk;
+    pix_grid(channels, N, pixels, batch, grid, chunk);
     cudaStream_t s = (cudaStream_t)stream;
     if (dtype == OOD_F32)
-        alignnet_ew_kernel<float, 0><<<grid, 256, 0, s>>>((const float *)cur, (const float *)enc, st6, nullptr, nullptr, w, bias, (float *)out, pixels, channels);
+        alignnet_ew_kernel<float, 0><<<grid, 256, 0, s>>>((const float *)cur, (const float *)enc, st6, nullptr, nullptr, w, bias, (float *)out, pixels, channels, chunk);
     else
-        alignnet_ew_kernel<__nv_bfloat16, 0><<<grid, 256, 0, s>>>((const __nv_bfloat16 *)cur, (const __nv_bfloat16 *)enc, st6, nullptr, nullptr, w, bias, (__nv_bfloat16 *)out, pixels, channels);
+        alignnet_ew_kernel<__nv_bfloat16, 0><<<grid, 256, 0, s>>>((const __nv_bfloat16 *)cur, (const __nv_bfloat16 *)enc, st6, nullptr, nullptr, w, bias, (__nv_bfloat16 *)out, pixels, channels, chunk);
     return check_launch("alignnet_front");
 }
 
@@ -231,13 +287,14 @@ extern "C" int ood_alignnet_res0(const void *t, const float *st2, const float *w
     const int N = dtype == OOD_F32 ? 4 : 8;
     OOD_REQUIRE(dtype == OOD_F32 || dtype == OOD_BF16, "alignnet_res0: bad dtype");
     OOD_REQUIRE(channels % N == 0, "alignnet_res0: channels (%d) must be a multiple of %d", channels, N);
-    const int64_t work = pixels * (channels / N);
-    dim3 grid((unsigned)std::min<int64_t>((work + 255) / 256, kNumSMs * 16), batch);
+    OOD_REQUIRE(channels / N <= 256, "alignnet_res0: too many channels (%d)", channels);
+    dim3 grid; int64_t chunk;
+    pix_grid(channels, N, pixels, batch, grid, chunk);
     cudaStream_t s = (cudaStream_t)stream;
     if (dtype == OOD_F32)
-        alignnet_ew_kernel<float, 1><<<grid, 256, 0, s>>>((const float *)cur, (const float *)enc, st6, (const float *)t, st2, w, bias, (float *)out, pixels, channels);
+        alignnet_ew_kernel<float, 1><<<grid, 256, 0, s>>>((const float *)cur, (const float *)enc, st6, (const float *)t, st2, w, bias, (float *)out, pixels, channels, chunk);
     else
-        alignnet_ew_kernel<__nv_bfloat16, 1><<<grid, 256, 0, s>>>((const __nv_bfloat16 *)cur, (const __nv_bfloat16 *)enc, st6, (const __nv_bfloat16 *)t, st2, w, bias, (__nv_bfloat16 *)out, pixels, channels);
+        alignnet_ew_kernel<__nv_bfloat16, 1><<<grid, 256, 0, s>>>((const __nv_bfloat16 *)cur, (const __nv_bfloat16 *)enc, st6, (const __nv_bfloat16 *)t, st2, w, bias, (__nv_bfloat16 *)out, pixels, channels, chunk);
     return check_launch("alignnet_res0");
 }
 
@@ -248,10 +305,11 @@ extern "C" int ood_in_apply(const void *x, const float *st2, const float *w, con
     const int N = dtype == OOD_F32 ? 4 : 8;
     OOD_REQUIRE(dtype == OOD_F32 || dtype == OOD_BF16, "in_apply: bad dtype");
     OOD_REQUIRE(channels % N == 0, "in_apply: channels (%d) must be a multiple of %d", channels, N);
-    const int64_t work = pixels * (channels / N);
-    dim3 grid((unsigned)std::min<int64_t>((work + 255) / 256, kNumSMs * 16), batch);
+    OOD_REQUIRE(channels / N <= 256, "in_apply: too many channels (%d)", channels);
+    dim3 grid; int64_t chunk;
+    pix_grid(channels, N, pixels, batch, grid, chunk);
     cudaStream_t s = (cudaStream_t)stream;
-    if (dtype == OOD_F32) in_apply_kernel<float><<<grid, 256, 0, s>>>((const float *)x, st2, w, bias, (float *)out, pixels, channels);
-    else in_apply_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16 *)x, st2, w, bias, (__nv_bfloat16 *)out, pixels, channels);
+    if (dtype == OOD_F32) in_apply_kernel<float><<<grid, 256, 0, s>>>((const float *)x, st2, w, bias, (float *)out, pixels, channels, chunk);
+    else in_apply_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16 *)x, st2, w, bias, (__nv_bfloat16 *)out, pixels, channels, chunk);
     return check_launch("in_apply");
 }

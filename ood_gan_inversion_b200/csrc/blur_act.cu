@@ -131,29 +131,38 @@ __global__ void __launch_bounds__(128) blur_act_kernel(const BlurParams p) {
     }
 }
 
+// thread = one 16-byte channel vector walking down a chunk of pixels: bias / next-style live in registers
 template <typename T>
 __global__ void __launch_bounds__(256) noise_act_kernel(const T *__restrict__ img, T *__restrict__ out_y,
                                                          T *__restrict__ out_ys, const float *__restrict__ noise,
                                                          int64_t noise_bstride, const float *__restrict__ noise_w,
                                                          const float *__restrict__ bias, const float *__restrict__ s_next,
-                                                         int64_t pixels, int C) {
+                                                         int64_t pixels, int C, int64_t chunk) {
     constexpr int N = Vec<T>::N;
     const int cv = C / N;
-    const int b = blockIdx.y;
+    const int lanes = blockDim.x / cv;
+    const int vec = threadIdx.x % cv, lane = threadIdx.x / cv;
+    if (lane >= lanes) return;
+    const int b = blockIdx.y, c = vec * N;
     const float nw = (noise && noise_w) ? *noise_w : 0.f;
-    const int64_t nvec = pixels * cv;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t pix = i / cv;
-        const int c = (int)(i - pix * cv) * N;
+    float breg[N], sreg[N];
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+        breg[j] = bias ? bias[c + j] : 0.f;
+        sreg[j] = out_ys ? s_next[(int64_t)b * C + c + j] : 1.f;
+    }
+    const int64_t p0 = (int64_t)blockIdx.x * chunk, p1 = min(p0 + chunk, pixels);
+#pragma unroll 4
+    for (int64_t pix = p0 + lane; pix < p1; pix += lanes) {
         const int64_t off = ((int64_t)b * pixels + pix) * C + c;
         Vec<T> x = load_vec<T>(img + off);
         const float nz = noise ? nw * __ldg(noise + b * noise_bstride + pix) : 0.f;
 #pragma unroll
-        for (int j = 0; j < N; ++j) x.v[j] = lrelu_sqrt2(x.v[j] + nz + (bias ? __ldg(bias + c + j) : 0.f));
+        for (int j = 0; j < N; ++j) x.v[j] = lrelu_sqrt2(x.v[j] + nz + breg[j]);
         if (out_y) store_vec<T>(out_y + off, x);
         if (out_ys) {
 #pragma unroll
-            for (int j = 0; j < N; ++j) x.v[j] *= __ldg(s_next + (int64_t)b * C + c + j);
+            for (int j = 0; j < N; ++j) x.v[j] *= sreg[j];
             store_vec<T>(out_ys + off, x);
         }
     }
@@ -199,15 +208,19 @@ extern "C" int ood_noise_act(const void *img, void *out_y, void *out_ys, const f
     const int N = dtype == OOD_F32 ? 4 : 8;
     OOD_REQUIRE(dtype == OOD_F32 || dtype == OOD_BF16, "noise_act: bad dtype");
     OOD_REQUIRE(channels % N == 0, "noise_act: channels (%d) must be a multiple of %d", channels, N);
-    const int64_t nvec = pixels * (channels / N);
-    dim3 grid((unsigned)std::min<int64_t>((nvec + 255) / 256, kNumSMs * 8), batch);
+    OOD_REQUIRE(channels / N <= 256, "noise_act: too many channels (%d)", channels);
+    const int lanes = std::max(1, 256 / (channels / N));
+    const int64_t want = std::max<int64_t>(1, (int64_t)kNumSMs * 8 / batch);
+    int64_t chunk = std::max<int64_t>((pixels + want - 1) / want, (int64_t)lanes * 4);
+    chunk = (chunk + lanes - 1) / lanes * lanes;
+    dim3 grid((unsigned)((pixels + chunk - 1) / chunk), batch);
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == OOD_F32)
         noise_act_kernel<float><<<grid, 256, 0, st>>>((const float *)img, (float *)out_y, (float *)out_ys, noise, noise_bstride,
-                                                      noise_w, bias, s_next, pixels, channels);
+                                                      noise_w, bias, s_next, pixels, channels, chunk);
     else
         noise_act_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16 *)img, (__nv_bfloat16 *)out_y,
                                                               (__nv_bfloat16 *)out_ys, noise, noise_bstride, noise_w, bias,
-                                                              s_next, pixels, channels);
+                                                              s_next, pixels, channels, chunk);
     return check_launch("noise_act");
 }

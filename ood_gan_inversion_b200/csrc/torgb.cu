@@ -1,18 +1,21 @@
 // ToRGB: 1x1 modulated convolution to 3 channels (no demodulation) + bias + FIR-upsampled skip accumulate.
 // Reference: src/ops/StyleGAN/model.py:353-372 (ToRGB), :30-47 (Upsample), upfirdn2d up=2 pad (2,1).
 // HBM-bound (reads C channels per pixel to produce 3): a group of G lanes owns one pixel, each lane a 16-byte
-// channel vector, so a warp reads one contiguous 512-byte run per load; RGB partials are shuffle-reduced and the
-// group leader adds bias and the 2x2-tap upsampled skip before one fp32 store per colour plane.
+// channel vector (KCH of them when C > 32 vectors), so a warp reads contiguous 512-byte runs; the lane's slice of the
+// per-sample RGB weights lives in registers for the whole kernel; RGB partials are butterfly-reduced and lanes 0..2 of
+// the group each finish one colour plane (bias + 2x2-tap upsampled skip + one fp32 store).
 #include "common.cuh"
 
 namespace ood {
 
-template <typename T>
+// KCH > 0: channel chunks per lane, weights register-resident.  KCH == 0: generic (weights re-read through L1).
+template <typename T, int KCH>
 __global__ void __launch_bounds__(256) torgb_kernel(const T *__restrict__ y, const float *__restrict__ wrgb,
                                                      const float *__restrict__ bias, const float *__restrict__ skip,
                                                      float *__restrict__ out, int H, int W, int C, int G, float kf0,
                                                      float kf1, float kf2, float kf3) {
     constexpr int N = Vec<T>::N;
+    constexpr int KR = KCH > 0 ? KCH : 1;
     const int b = blockIdx.y;
     const int lane = threadIdx.x & 31;
     const int gl = lane % G;                       // lane within the pixel group
@@ -20,50 +23,97 @@ __global__ void __launch_bounds__(256) torgb_kernel(const T *__restrict__ y, con
     const int64_t P = (int64_t)H * W;
     const float kf[4] = {kf0, kf1, kf2, kf3};
     const float *wb = wrgb + (int64_t)b * 3 * C;
+    float wreg[KR][3][N];
+    if constexpr (KCH > 0) {
+#pragma unroll
+        for (int k = 0; k < KCH; ++k)
+#pragma unroll
+            for (int q = 0; q < 3; ++q)
+#pragma unroll
+                for (int j = 0; j < N; ++j) wreg[k][q][j] = wb[q * C + (gl + k * G) * N + j];
+    }
+    const int h2 = H >> 1, w2 = W >> 1;
     // block-uniform trip count: every lane takes part in the shuffles, out-of-range groups contribute nothing
     for (int64_t base = (int64_t)blockIdx.x * groups_per_block; base < P; base += (int64_t)gridDim.x * groups_per_block) {
         const int64_t pix = base + threadIdx.x / G;
         const bool valid = pix < P;
         const T *src = y + ((int64_t)b * P + (valid ? pix : 0)) * C;
-        float r0 = 0.f, r1 = 0.f, r2 = 0.f;
-        for (int c = gl * N; valid && c < C; c += G * N) {
-            const Vec<T> x = load_vec<T>(src + c);
+        float r[3] = {0.f, 0.f, 0.f};
+        if (valid) {
+            if constexpr (KCH > 0) {
+                Vec<T> x[KCH];
 #pragma unroll
-            for (int j = 0; j < N; ++j) {
-                r0 = fmaf(x.v[j], __ldg(wb + c + j), r0);
-                r1 = fmaf(x.v[j], __ldg(wb + C + c + j), r1);
-                r2 = fmaf(x.v[j], __ldg(wb + 2 * C + c + j), r2);
-            }
-        }
-        for (int o = G >> 1; o > 0; o >>= 1) {
-            r0 += __shfl_xor_sync(0xffffffffu, r0, o);
-            r1 += __shfl_xor_sync(0xffffffffu, r1, o);
-            r2 += __shfl_xor_sync(0xffffffffu, r2, o);
-        }
-        if (valid && gl == 0) {
-            const int Y = (int)(pix / W), X = (int)(pix - (int64_t)Y * W);
-            float rgb[3] = {r0 + bias[0], r1 + bias[1], r2 + bias[2]};
-            if (skip) {
-                const int h2 = H >> 1, w2 = W >> 1;
+                for (int k = 0; k < KCH; ++k) x[k] = load_vec<T>(src + (gl + k * G) * N);
 #pragma unroll
-                for (int ky = 0; ky < 4; ++ky) {
-                    const int u = Y + ky - 2;
-                    if (u < 0 || (u & 1) || (u >> 1) >= h2) continue;
+                for (int k = 0; k < KCH; ++k)
 #pragma unroll
-                    for (int kx = 0; kx < 4; ++kx) {
-                        const int v = X + kx - 2;
-                        if (v < 0 || (v & 1) || (v >> 1) >= w2) continue;
-                        const float wgt = kf[ky] * kf[kx];
-                        const float *sp = skip + ((int64_t)b * 3 * h2 + (u >> 1)) * w2 + (v >> 1);
+                    for (int j = 0; j < N; ++j) {
+                        r[0] = fmaf(x[k].v[j], wreg[k][0][j], r[0]);
+                        r[1] = fmaf(x[k].v[j], wreg[k][1][j], r[1]);
+                        r[2] = fmaf(x[k].v[j], wreg[k][2][j], r[2]);
+                    }
+            } else {
+                for (int c = gl * N; c < C; c += G * N) {
+                    const Vec<T> x = load_vec<T>(src + c);
 #pragma unroll
-                        for (int k = 0; k < 3; ++k) rgb[k] = fmaf(wgt, __ldg(sp + (int64_t)k * h2 * w2), rgb[k]);
+                    for (int j = 0; j < N; ++j) {
+                        r[0] = fmaf(x.v[j], __ldg(wb + c + j), r[0]);
+                        r[1] = fmaf(x.v[j], __ldg(wb + C + c + j), r[1]);
+                        r[2] = fmaf(x.v[j], __ldg(wb + 2 * C + c + j), r[2]);
                     }
                 }
             }
+        }
+        for (int o = G >> 1; o > 0; o >>= 1) {
+            r[0] += __shfl_xor_sync(0xffffffffu, r[0], o);
+            r[1] += __shfl_xor_sync(0xffffffffu, r[1], o);
+            r[2] += __shfl_xor_sync(0xffffffffu, r[2], o);
+        }
+        if (!valid) continue;
+        const int Y = (int)(pix / W), X = (int)(pix - (int64_t)Y * W);
+        // colour k is finished by lane k of the group (all three by lane 0 when the group is smaller than 4 lanes)
+        const int k_lo = G >= 4 ? gl : 0, k_hi = G >= 4 ? gl + 1 : 3;
+        if (gl < (G >= 4 ? 3 : 1)) {
+            for (int k = k_lo; k < k_hi; ++k) {
+                float v = (k == 0 ? r[0] : (k == 1 ? r[1] : r[2])) + bias[k];
+                if (skip) {
+                    const float *sp = skip + ((int64_t)b * 3 + k) * h2 * w2;
 #pragma unroll
-            for (int k = 0; k < 3; ++k) out[((int64_t)b * 3 + k) * P + pix] = rgb[k];
+                    for (int ky = 0; ky < 4; ++ky) {
+                        const int u = Y + ky - 2;
+                        if (u < 0 || (u & 1) || (u >> 1) >= h2) continue;
+#pragma unroll
+                        for (int kx = 0; kx < 4; ++kx) {
+                            const int q = X + kx - 2;
+                            if (q < 0 || (q & 1) || (q >> 1) >= w2) continue;
+                            v = fmaf(kf[ky] * kf[kx], __ldg(sp + (int64_t)(u >> 1) * w2 + (q >> 1)), v);
+                        }
+                    }
+                }
+                out[((int64_t)b * 3 + k) * P + pix] = v;
+            }
         }
     }
+}
+
+template <typename T>
+static int launch_torgb(const void *y, const float *wrgb, const float *bias, const float *skip, float *out, const float *kf,
+                        int batch, int h, int w, int C, cudaStream_t st) {
+    constexpr int N = Vec<T>::N;
+    int G = 1;
+    while (G < 32 && G * 2 * N <= C) G *= 2;        // power of two, <= 32, G*N <= C
+    OOD_REQUIRE(C % (G * N) == 0, "torgb: channels (%d) must be a multiple of %d", C, G * N);
+    const int kch = C / (G * N);
+    const int64_t P = (int64_t)h * w;
+    const int gpb = 256 / G;
+    dim3 grid((unsigned)std::min<int64_t>((P + gpb - 1) / gpb, std::max(1, kNumSMs * 8 / batch)), batch);
+#define OOD_TORGB(K) torgb_kernel<T, K><<<grid, 256, 0, st>>>((const T *)y, wrgb, bias, skip, out, h, w, C, G, kf[0], kf[1], kf[2], kf[3])
+    if (kch == 1) OOD_TORGB(1);
+    else if (kch == 2) OOD_TORGB(2);
+    else if (kch == 4 && N == 8) OOD_TORGB(4);
+    else OOD_TORGB(0);
+#undef OOD_TORGB
+    return check_launch("torgb");
 }
 
 }  // namespace ood
@@ -76,18 +126,9 @@ extern "C" int ood_torgb(const void *y, const float *wrgb, const float *bias, co
     OOD_REQUIRE(!skip || (taps_up_host && h % 2 == 0 && w % 2 == 0), "torgb: skip needs taps and even size");
     const int N = dtype == OOD_F32 ? 4 : 8;
     OOD_REQUIRE(channels % N == 0, "torgb: channels (%d) must be a multiple of %d", channels, N);
-    int G = 1;
-    while (G < 32 && G * 2 * N <= channels) G *= 2;        // power of two, <= 32, G*N <= C
-    OOD_REQUIRE(channels % (G * N) == 0, "torgb: channels (%d) must be a multiple of %d", channels, G * N);
     float kf[4] = {0, 0, 0, 0};
     if (skip) for (int i = 0; i < 4; ++i) kf[i] = taps_up_host[3 - i];
-    const int64_t P = (int64_t)h * w;
-    const int gpb = 256 / G;
-    dim3 grid((unsigned)std::min<int64_t>((P + gpb - 1) / gpb, kNumSMs * 16), batch);
     cudaStream_t st = (cudaStream_t)stream;
-    if (dtype == OOD_F32)
-        torgb_kernel<float><<<grid, 256, 0, st>>>((const float *)y, wrgb, bias, skip, out, h, w, channels, G, kf[0], kf[1], kf[2], kf[3]);
-    else
-        torgb_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16 *)y, wrgb, bias, skip, out, h, w, channels, G, kf[0], kf[1], kf[2], kf[3]);
-    return check_launch("torgb");
+    return dtype == OOD_F32 ? launch_torgb<float>(y, wrgb, bias, skip, out, kf, batch, h, w, channels, st)
+                            : launch_torgb<__nv_bfloat16>(y, wrgb, bias, skip, out, kf, batch, h, w, channels, st);
 }
