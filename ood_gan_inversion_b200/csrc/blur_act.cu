@@ -168,6 +168,8 @@ __global__ void __launch_bounds__(256) noise_act_kernel(const T *__restrict__ im
     }
 }
 
+int blur_act_tma(const ood_blur_act_args *a, cudaStream_t st, int *handled);   // blur_tma.cu
+
 }  // namespace ood
 
 extern "C" int ood_blur_act(const ood_blur_act_args *a, void *stream) {
@@ -180,6 +182,11 @@ extern "C" int ood_blur_act(const ood_blur_act_args *a, void *stream) {
     OOD_REQUIRE(!a->out_ys || a->s_next, "blur_act: out_ys needs s_next");
     const int N = a->dtype == OOD_F32 ? 4 : 8;
     OOD_REQUIRE(a->channels % N == 0, "blur_act: channels (%d) must be a multiple of %d", a->channels, N);
+    {   // TMA-staged path (channels % 32 == 0 on sm_100); otherwise the register-window kernel below
+        int handled = 0;
+        const int rc = blur_act_tma(a, (cudaStream_t)stream, &handled);
+        if (handled) return rc;
+    }
     BlurParams p;
     p.in = a->in; p.out_img = a->out_img; p.out_y = a->out_y; p.out_ys = a->out_ys;
     p.d = a->d; p.noise = a->noise; p.noise_w = a->noise_w; p.bias = a->bias; p.s_next = a->s_next;

@@ -12,22 +12,20 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
-// one warp per input channel i; loops over the batch so the weight row is read once.
+// one warp per (b, i): grid (ceil(cin/8), batch)
 __global__ void __launch_bounds__(256) style_s_kernel(const float *__restrict__ latent, int64_t lstride,
                                                        const float *__restrict__ mod_w, const float *__restrict__ mod_b,
                                                        float *__restrict__ s, int batch, int D, int cin, float lin_scale) {
     const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
+    const int b = blockIdx.y;
     if (i >= cin) return;
     const float *wrow = mod_w + (int64_t)i * D;
-    const float bias = mod_b ? mod_b[i] : 0.f;
-    for (int b = 0; b < batch; ++b) {
-        const float *l = latent + b * lstride;
-        float acc = 0.f;
-        for (int j = lane; j < D; j += 32) acc = fmaf(l[j], wrow[j], acc);
-        acc = warp_sum(acc);
-        if (lane == 0) s[(int64_t)b * cin + i] = acc * lin_scale + bias;
-    }
+    const float *l = latent + b * lstride;
+    float acc = 0.f;
+    for (int j = lane; j < D; j += 32) acc = fmaf(__ldg(l + j), __ldg(wrow + j), acc);
+    acc = warp_sum(acc);
+    if (lane == 0) s[(int64_t)b * cin + i] = acc * lin_scale + (mod_b ? mod_b[i] : 0.f);
 }
 
 // one warp per (b, o)
@@ -86,7 +84,8 @@ extern "C" int ood_modulation(const float *latent, int64_t latent_stride, const 
     using namespace ood;
     OOD_REQUIRE(latent && mod_w && s_out && batch > 0 && style_dim > 0 && cin > 0, "modulation: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
-    style_s_kernel<<<ceil_div(cin, 8), 256, 0, st>>>(latent, latent_stride, mod_w, mod_b, s_out, batch, style_dim, cin,
+    OOD_REQUIRE(batch <= 65535, "modulation: batch too large");
+    style_s_kernel<<<dim3(ceil_div(cin, 8), batch), 256, 0, st>>>(latent, latent_stride, mod_w, mod_b, s_out, batch, style_dim, cin,
                                                       1.0f / sqrtf((float)style_dim));
     if (d_out) {
         OOD_REQUIRE(cout > 0, "modulation: cout");

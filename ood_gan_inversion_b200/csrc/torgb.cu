@@ -21,7 +21,6 @@ __global__ void __launch_bounds__(256) torgb_kernel(const T *__restrict__ y, con
     const int gl = lane % G;                       // lane within the pixel group
     const int groups_per_block = blockDim.x / G;
     const int64_t P = (int64_t)H * W;
-    const float kf[4] = {kf0, kf1, kf2, kf3};
     const float *wb = wrgb + (int64_t)b * 3 * C;
     float wreg[KR][3][N];
     if constexpr (KCH > 0) {
@@ -33,60 +32,82 @@ __global__ void __launch_bounds__(256) torgb_kernel(const T *__restrict__ y, con
                 for (int j = 0; j < N; ++j) wreg[k][q][j] = wb[q * C + (gl + k * G) * N + j];
     }
     const int h2 = H >> 1, w2 = W >> 1;
+    constexpr int PPI = KCH > 0 ? (KCH == 1 ? 4 : 2) : 1;      // pixels per group per iteration (independent loads in flight)
     // block-uniform trip count: every lane takes part in the shuffles, out-of-range groups contribute nothing
-    for (int64_t base = (int64_t)blockIdx.x * groups_per_block; base < P; base += (int64_t)gridDim.x * groups_per_block) {
-        const int64_t pix = base + threadIdx.x / G;
-        const bool valid = pix < P;
-        const T *src = y + ((int64_t)b * P + (valid ? pix : 0)) * C;
-        float r[3] = {0.f, 0.f, 0.f};
-        if (valid) {
-            if constexpr (KCH > 0) {
-                Vec<T> x[KCH];
+    for (int64_t base = (int64_t)blockIdx.x * groups_per_block * PPI; base < P;
+         base += (int64_t)gridDim.x * groups_per_block * PPI) {
+        float r[PPI][3];
+        int64_t pixs[PPI];
+        if constexpr (KCH > 0) {
+            Vec<T> x[PPI][KCH];
 #pragma unroll
-                for (int k = 0; k < KCH; ++k) x[k] = load_vec<T>(src + (gl + k * G) * N);
+            for (int q = 0; q < PPI; ++q) {
+                pixs[q] = base + (int64_t)q * groups_per_block + threadIdx.x / G;
+                const T *src = y + ((int64_t)b * P + (pixs[q] < P ? pixs[q] : 0)) * C;
+#pragma unroll
+                for (int k = 0; k < KCH; ++k) x[q][k] = load_vec<T>(src + (gl + k * G) * N);
+            }
+#pragma unroll
+            for (int q = 0; q < PPI; ++q) {
+                r[q][0] = r[q][1] = r[q][2] = 0.f;
 #pragma unroll
                 for (int k = 0; k < KCH; ++k)
 #pragma unroll
                     for (int j = 0; j < N; ++j) {
-                        r[0] = fmaf(x[k].v[j], wreg[k][0][j], r[0]);
-                        r[1] = fmaf(x[k].v[j], wreg[k][1][j], r[1]);
-                        r[2] = fmaf(x[k].v[j], wreg[k][2][j], r[2]);
+                        r[q][0] = fmaf(x[q][k].v[j], wreg[k][0][j], r[q][0]);
+                        r[q][1] = fmaf(x[q][k].v[j], wreg[k][1][j], r[q][1]);
+                        r[q][2] = fmaf(x[q][k].v[j], wreg[k][2][j], r[q][2]);
                     }
-            } else {
+            }
+        } else {
+            pixs[0] = base + threadIdx.x / G;
+            r[0][0] = r[0][1] = r[0][2] = 0.f;
+            if (pixs[0] < P) {
+                const T *src = y + ((int64_t)b * P + pixs[0]) * C;
                 for (int c = gl * N; c < C; c += G * N) {
                     const Vec<T> x = load_vec<T>(src + c);
 #pragma unroll
                     for (int j = 0; j < N; ++j) {
-                        r[0] = fmaf(x.v[j], __ldg(wb + c + j), r[0]);
-                        r[1] = fmaf(x.v[j], __ldg(wb + C + c + j), r[1]);
-                        r[2] = fmaf(x.v[j], __ldg(wb + 2 * C + c + j), r[2]);
+                        r[0][0] = fmaf(x.v[j], __ldg(wb + c + j), r[0][0]);
+                        r[0][1] = fmaf(x.v[j], __ldg(wb + C + c + j), r[0][1]);
+                        r[0][2] = fmaf(x.v[j], __ldg(wb + 2 * C + c + j), r[0][2]);
                     }
                 }
             }
         }
-        for (int o = G >> 1; o > 0; o >>= 1) {
-            r[0] += __shfl_xor_sync(0xffffffffu, r[0], o);
-            r[1] += __shfl_xor_sync(0xffffffffu, r[1], o);
-            r[2] += __shfl_xor_sync(0xffffffffu, r[2], o);
+#pragma unroll
+        for (int q = 0; q < PPI; ++q) {
+            for (int o = G >> 1; o > 0; o >>= 1) {
+                r[q][0] += __shfl_xor_sync(0xffffffffu, r[q][0], o);
+                r[q][1] += __shfl_xor_sync(0xffffffffu, r[q][1], o);
+                r[q][2] += __shfl_xor_sync(0xffffffffu, r[q][2], o);
+            }
         }
-        if (!valid) continue;
-        const int Y = (int)(pix / W), X = (int)(pix - (int64_t)Y * W);
-        // colour k is finished by lane k of the group (all three by lane 0 when the group is smaller than 4 lanes)
-        const int k_lo = G >= 4 ? gl : 0, k_hi = G >= 4 ? gl + 1 : 3;
-        if (gl < (G >= 4 ? 3 : 1)) {
+#pragma unroll
+        for (int q = 0; q < PPI; ++q) {
+            const int64_t pix = pixs[q];
+            if (pix >= P) continue;
+            const int Y = (int)(pix / W), X = (int)(pix - (int64_t)Y * W);
+            // colour k is finished by lane k of the group (all three by lane 0 when the group is smaller than 4 lanes)
+            const int k_lo = G >= 4 ? gl : 0, k_hi = G >= 4 ? gl + 1 : 3;
+            if (gl >= (G >= 4 ? 3 : 1)) continue;
             for (int k = k_lo; k < k_hi; ++k) {
-                float v = (k == 0 ? r[0] : (k == 1 ? r[1] : r[2])) + bias[k];
+                float v = (k == 0 ? r[q][0] : (k == 1 ? r[q][1] : r[q][2])) + bias[k];
                 if (skip) {
+                    // up-2 polyphase: output row Y sees skip rows (Y + ky0 - 2)/2 and the next one, taps ky0, ky0+2 (ky0 = Y & 1)
                     const float *sp = skip + ((int64_t)b * 3 + k) * h2 * w2;
+                    const int ky0 = Y & 1, kx0 = X & 1;
+                    const int ra = (Y + ky0 - 2) >> 1, ca = (X + kx0 - 2) >> 1;
+                    const float wy[2] = {ky0 ? kf1 : kf0, ky0 ? kf3 : kf2}, wx[2] = {kx0 ? kf1 : kf0, kx0 ? kf3 : kf2};
 #pragma unroll
-                    for (int ky = 0; ky < 4; ++ky) {
-                        const int u = Y + ky - 2;
-                        if (u < 0 || (u & 1) || (u >> 1) >= h2) continue;
+                    for (int dy = 0; dy < 2; ++dy) {
+                        const int rr = ra + dy;
+                        if (rr < 0 || rr >= h2) continue;
 #pragma unroll
-                        for (int kx = 0; kx < 4; ++kx) {
-                            const int q = X + kx - 2;
-                            if (q < 0 || (q & 1) || (q >> 1) >= w2) continue;
-                            v = fmaf(kf[ky] * kf[kx], __ldg(sp + (int64_t)(u >> 1) * w2 + (q >> 1)), v);
+                        for (int dx = 0; dx < 2; ++dx) {
+                            const int cc = ca + dx;
+                            if (cc < 0 || cc >= w2) continue;
+                            v = fmaf(wy[dy] * wx[dx], __ldg(sp + (int64_t)rr * w2 + cc), v);
                         }
                     }
                 }
@@ -106,7 +127,7 @@ static int launch_torgb(const void *y, const float *wrgb, const float *bias, con
     const int kch = C / (G * N);
     const int64_t P = (int64_t)h * w;
     const int gpb = 256 / G;
-    dim3 grid((unsigned)std::min<int64_t>((P + gpb - 1) / gpb, std::max(1, kNumSMs * 8 / batch)), batch);
+    dim3 grid((unsigned)std::min<int64_t>((P + gpb - 1) / gpb, std::max(1, kNumSMs * 16 / batch)), batch);
 #define OOD_TORGB(K) torgb_kernel<T, K><<<grid, 256, 0, st>>>((const T *)y, wrgb, bias, skip, out, h, w, C, G, kf[0], kf[1], kf[2], kf[3])
     if (kch == 1) OOD_TORGB(1);
     else if (kch == 2) OOD_TORGB(2);

@@ -5,7 +5,7 @@
 set -e
 name=$1; regex=$2; skip=$3; count=$4
 mkdir -p gpurun_out
-ncu --profile-from-start off --set full --clock-control none --import-source on -k "regex:$regex" -s "$skip" -c "$count" \
+ncu --profile-from-start off --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:$regex" -s "$skip" -c "$count" \
     -f -o /tmp/ncu_$name python bench.py --ncu --steps 1 --warmup 3 > gpurun_out/ncu_$name.log 2>&1
 ncu -i /tmp/ncu_$name.ncu-rep --page raw --csv > gpurun_out/ncu_${name}_raw.csv
 ncu -i /tmp/ncu_$name.ncu-rep --page details --csv > gpurun_out/ncu_${name}_details.csv 2>/dev/null || true
