@@ -92,6 +92,7 @@ int ood_pack_conv_weight(const float *w, void *out, int cout, int cin, int taps,
  *      Uses (W*s*d) (*) x == d . (W (*) (s . x))  (SURVEY.md section 7 step 4): `in` already carries s.
  *      transposed == 0: stride-1, pad-1 conv, out [B,H,W,Co]           (model.py:268-272)
  *      transposed == 1: stride-2 transposed conv, out [B,2H+1,2W+1,Co]  (model.py:246-256), raw accumulators.
+ *      transposed == 2: stride-2 valid conv, in [B,2h+1,2w+1,Ci] -> out [B,h,w,Co]: the data gradient of form 1 (autograd of model.py:255).
  *      Epilogue (stride-1 only; any pointer may be NULL to skip that term):
  *          v  = acc * d[b,o] + noise_w * noise[b,y,x] + bias[o];  y = act ? lrelu(v,0.2)*sqrt2 : v
  *          out_y  = y            out_ys = y * s_next[b,o]
@@ -110,7 +111,7 @@ typedef struct {
     const float *bias;     /* [Co] or NULL */
     const float *s_next;   /* [B,Co]; required iff out_ys */
     int batch, h, w, cin, cout;
-    int transposed;        /* 0 | 1 */
+    int transposed;        /* 0 stride-1 conv | 1 stride-2 transposed conv | 2 stride-2 valid conv (data gradient of 1) */
     int act;               /* 0 none | 1 leaky-ReLU(0.2)*sqrt2 | 2 PReLU(prelu_slope[o]) (AlignNet, shared-weight mode) */
     int impl;              /* 0 tcgen05 | 1 simt */
     int dtype;             /* storage type of in / out */
@@ -136,6 +137,7 @@ typedef struct {
     int batch, ih, iw, channels;
     int act;              /* 0: stop after img (out_y/out_ys must be NULL) */
     int dtype;
+    int pad0, pad1;       /* FIR pads (same on both axes); 0,0 means (1,1).  (2,2) is the adjoint of the (1,1) blur: out = in + 1 */
 } ood_blur_act_args;
 int ood_blur_act(const ood_blur_act_args *args_host, void *stream);
 
@@ -167,6 +169,21 @@ int ood_field_step(const float *z, const float *prev, const float *coarse, float
  *      x [B,h,w,C], y / out [B,H,W,C] (y may be NULL).  ATen's channels-last bicubic costs 40 ms per call at B=16. */
 int ood_bicubic_up_add(const void *x, const void *y, void *out, int batch, int h, int w, int H, int W, int channels,
                        int dtype, void *stream);
+
+/* ---- a14. backward of the synthesis path for optimisation-based inversion (autograd through model.py:233-372; weights frozen).
+ *      ood_act_bwd : gv = gy*sqrt2*(y>0 ? 1 : 0.2) (gate on the saved OUTPUT, fused_bias_act_kernel.cu:36-47);  g = gv*d[b,c];
+ *                    gd[b,c] = sum_pix gv*acc with acc = (y/(sqrt2*gate) - noise_w*noise - bias)/d re-derived from y.
+ *      ood_dot_reduce: out[b,c] = sum_pix a*b  (style gradient sum_pix gxs*x).
+ *      ood_torgb_bwd : g_out = (g_in ? g_in : 0) + sum_k g_rgb[b,k,p]*wrgb[b,k,c]  (NHWC);  g_wrgb[b,c,k] = sum_pix g_rgb[b,k,p]*y[b,p,c].
+ *      workspace: ood_bwd_workspace(batch, pixels, channels, k) bytes, k = 1 (act_bwd, dot_reduce) or 3 (torgb_bwd). */
+int64_t ood_bwd_workspace(int batch, int64_t pixels, int channels, int k);
+int ood_act_bwd(const void *gy, const void *y, const float *d, const float *bias, const float *noise, int64_t noise_bstride,
+                const float *noise_w, void *g, float *workspace, float *gd, int batch, int64_t pixels, int channels, int dtype,
+                void *stream);
+int ood_dot_reduce(const void *a, const void *b, float *workspace, float *out, int batch, int64_t pixels, int channels,
+                   int dtype, void *stream);
+int ood_torgb_bwd(const float *g_rgb, const float *wrgb, const void *y, const void *g_in, void *g_out, float *workspace,
+                  float *g_wrgb, int batch, int64_t pixels, int channels, int dtype, void *stream);
 
 /* ---- a11. AlignNet instance norms on NHWC (SAMM/helpers.py:96-101, e4e/encoders/helpers.py:93-99,426-448).
  *      ood_in_stats: per-(b,c) moments over the pixels.  y == NULL: stats[b][c] = {mean, rstd}.

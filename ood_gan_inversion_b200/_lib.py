@@ -24,7 +24,7 @@ class BlurActArgs(C.Structure):
     _fields_ = [('inp', c_void_p), ('in_f32', c_int), ('out_img', c_void_p), ('out_y', c_void_p), ('out_ys', c_void_p),
                 ('d', c_void_p), ('noise', c_void_p), ('noise_w', c_void_p), ('bias', c_void_p), ('s_next', c_void_p),
                 ('noise_bstride', c_i64), ('taps', c_float * 4), ('batch', c_int), ('ih', c_int), ('iw', c_int),
-                ('channels', c_int), ('act', c_int), ('dtype', c_int)]
+                ('channels', c_int), ('act', c_int), ('dtype', c_int), ('pad0', c_int), ('pad1', c_int)]
 
 
 _SIGS = {
@@ -53,6 +53,12 @@ _SIGS = {
     'ood_field_step': ([c_void_p, c_void_p, c_void_p, c_void_p, C.POINTER(c_float), c_float, c_int, c_int, c_int,
                         c_void_p], c_int),
     'ood_bicubic_up_add': ([c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p], c_int),
+    'ood_bwd_workspace': ([c_int, c_i64, c_int, c_int], c_i64),
+    'ood_act_bwd': ([c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_i64,
+                     c_int, c_int, c_void_p], c_int),
+    'ood_dot_reduce': ([c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_i64, c_int, c_int, c_void_p], c_int),
+    'ood_torgb_bwd': ([c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_i64, c_int, c_int,
+                       c_void_p], c_int),
     'ood_in_stats_workspace': ([c_int, c_i64, c_int, c_int], c_i64),
     'ood_in_stats': ([c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_i64, c_int, c_float, c_int, c_void_p], c_int),
     'ood_alignnet_front': ([c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_i64, c_int, c_int, c_void_p], c_int),

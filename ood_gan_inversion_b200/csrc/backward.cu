@@ -1,0 +1,261 @@
+// Backward kernels of the synthesis path for optimisation-based inversion (W+ latents are the leaves, weights frozen).
+// Reference: autograd through src/ops/StyleGAN/model.py:233-372 (ModulatedConv2d / NoiseInjection / FusedLeakyReLU / ToRGB);
+// the lrelu gate follows src/ops/op/fused_bias_act_kernel.cu:36-47 (sign of the saved OUTPUT).
+//
+// With shared weights no weight-gradient GEMM is needed:
+//     gv = gy * sqrt2 * (y > 0 ? 1 : 0.2)                 g_acc = gv * d            (input of the data-gradient conv)
+//     gd[b,o]  = sum_pix gv * acc,   acc = (v - nw*noise - bias) / d,  v = y / (sqrt2 * gate)      (reconstructed from y)
+//     gs[b,i]  = sum_pix gxs * x  +  demod term (host, tiny)                         (ood_dot_reduce)
+// All kernels: thread = one 16-byte channel vector walking down a chunk of pixels, deterministic two-stage reductions.
+#include "common.cuh"
+
+namespace ood {
+
+constexpr int kBwdChunk = 512;
+
+template <int N>
+__device__ __forceinline__ void block_reduce_store(float (*acc)[N], int K, float *red, float *partial_row, int C, int cv,
+                                                   int lanes, int lane, int vec, bool active) {
+    // red: [lanes][C*K]
+    if (active) {
+        float *r = red + ((size_t)lane * cv + vec) * N * K;
+        for (int k = 0; k < K; ++k)
+#pragma unroll
+            for (int j = 0; j < N; ++j) r[j * K + k] = acc[k][j];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < C * K; i += blockDim.x) {
+        float s = 0.f;
+        for (int l = 0; l < lanes; ++l) s += red[(size_t)l * C * K + i];
+        partial_row[i] = s;
+    }
+}
+
+// ---- lrelu*sqrt2 / noise / bias / demod backward: g = gv*d, partial gd numerators
+template <typename T>
+__global__ void __launch_bounds__(256) act_bwd_kernel(const T *__restrict__ gy, const T *__restrict__ y, const float *__restrict__ d,
+                                                       const float *__restrict__ bias, const float *__restrict__ noise,
+                                                       int64_t noise_bstride, const float *__restrict__ noise_w,
+                                                       T *__restrict__ g, float *__restrict__ partial, int64_t P, int C,
+                                                       int nchunks) {
+    constexpr int N = Vec<T>::N;
+    extern __shared__ float red[];
+    const int cv = C / N, lanes = 256 / cv;
+    const int vec = threadIdx.x % cv, lane = threadIdx.x / cv;
+    const bool active = lane < lanes;
+    const int b = blockIdx.y, chunk = blockIdx.x, c = vec * N;
+    const float nw = (noise && noise_w) ? *noise_w : 0.f;
+    float acc[1][N];
+    float dreg[N], breg[N];
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+        acc[0][j] = 0.f;
+        dreg[j] = (active && d) ? d[(int64_t)b * C + c + j] : 1.f;
+        breg[j] = (active && bias) ? bias[c + j] : 0.f;
+    }
+    if (active) {
+        const int64_t p0 = (int64_t)chunk * kBwdChunk, p1 = min(p0 + kBwdChunk, P);
+#pragma unroll 2
+        for (int64_t p = p0 + lane; p < p1; p += lanes) {
+            const int64_t off = ((int64_t)b * P + p) * C + c;
+            const Vec<T> gv = load_vec<T>(gy + off), yv = load_vec<T>(y + off);
+            const float nz = noise ? nw * __ldg(noise + b * noise_bstride + p) : 0.f;
+            Vec<T> o;
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+                const float gate = yv.v[j] > 0.f ? kSqrt2 : 0.2f * kSqrt2;
+                const float gvv = gv.v[j] * gate;
+                const float v = yv.v[j] / gate;                       // pre-activation
+                acc[0][j] = fmaf(gvv, v - nz - breg[j], acc[0][j]);   // = gv * acc * d
+                o.v[j] = gvv * dreg[j];
+            }
+            store_vec<T>(g + off, o);
+        }
+    }
+    block_reduce_store<N>(acc, 1, red, partial + (((int64_t)b * nchunks + chunk) * C), C, cv, lanes, lane, vec, active);
+}
+
+// ---- sum_pix a*b per (b,c)
+template <typename T>
+__global__ void __launch_bounds__(256) dot_partial_kernel(const T *__restrict__ a, const T *__restrict__ bb,
+                                                           float *__restrict__ partial, int64_t P, int C, int nchunks) {
+    constexpr int N = Vec<T>::N;
+    extern __shared__ float red[];
+    const int cv = C / N, lanes = 256 / cv;
+    const int vec = threadIdx.x % cv, lane = threadIdx.x / cv;
+    const bool active = lane < lanes;
+    const int b = blockIdx.y, chunk = blockIdx.x, c = vec * N;
+    float acc[1][N];
+#pragma unroll
+    for (int j = 0; j < N; ++j) acc[0][j] = 0.f;
+    if (active) {
+        const int64_t p0 = (int64_t)chunk * kBwdChunk, p1 = min(p0 + kBwdChunk, P);
+#pragma unroll 4
+        for (int64_t p = p0 + lane; p < p1; p += lanes) {
+            const int64_t off = ((int64_t)b * P + p) * C + c;
+            const Vec<T> av = load_vec<T>(a + off), bv = load_vec<T>(bb + off);
+#pragma unroll
+            for (int j = 0; j < N; ++j) acc[0][j] = fmaf(av.v[j], bv.v[j], acc[0][j]);
+        }
+    }
+    block_reduce_store<N>(acc, 1, red, partial + (((int64_t)b * nchunks + chunk) * C), C, cv, lanes, lane, vec, active);
+}
+
+// out[b,c,k] = sum_chunks partial[b][chunk][c*K+k] * (div ? 1/div[b,c] : 1)
+__global__ void reduce_partials_kernel(const float *__restrict__ partial, const float *__restrict__ div, float *__restrict__ out,
+                                       int C, int K, int nchunks, int64_t total) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;    // b*C*K + c*K + k
+    if (i >= total) return;
+    const int64_t b = i / ((int64_t)C * K);
+    const int64_t r = i % ((int64_t)C * K);
+    double s = 0;
+    for (int k = 0; k < nchunks; ++k) s += partial[((b * nchunks + k) * C) * K + r];
+    if (div) s /= div[b * C + r / K];
+    out[i] = (float)s;
+}
+
+// ---- ToRGB backward w.r.t. the activation: gy[b,p,c] = (g_in ? g_in : 0) + sum_k g_rgb[b,k,p] * wrgb[b,k,c]
+template <typename T>
+__global__ void __launch_bounds__(256) torgb_bwd_y_kernel(const float *__restrict__ g_rgb, const float *__restrict__ wrgb,
+                                                           const T *__restrict__ g_in, T *__restrict__ out, int64_t P, int C) {
+    constexpr int N = Vec<T>::N;
+    const int cv = C / N, lanes = 256 / cv;
+    const int vec = threadIdx.x % cv, lane = threadIdx.x / cv;
+    if (lane >= lanes) return;
+    const int b = blockIdx.y, c = vec * N;
+    float w[3][N];
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+        for (int j = 0; j < N; ++j) w[k][j] = wrgb[((int64_t)b * 3 + k) * C + c + j];
+    const int64_t p0 = (int64_t)blockIdx.x * kBwdChunk, p1 = min(p0 + kBwdChunk, P);
+#pragma unroll 2
+    for (int64_t p = p0 + lane; p < p1; p += lanes) {
+        const float g0 = __ldg(g_rgb + ((int64_t)b * 3 + 0) * P + p), g1 = __ldg(g_rgb + ((int64_t)b * 3 + 1) * P + p),
+                    g2 = __ldg(g_rgb + ((int64_t)b * 3 + 2) * P + p);
+        const int64_t off = ((int64_t)b * P + p) * C + c;
+        Vec<T> o;
+        if (g_in) o = load_vec<T>(g_in + off);
+        else {
+#pragma unroll
+            for (int j = 0; j < N; ++j) o.v[j] = 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < N; ++j) o.v[j] += g0 * w[0][j] + g1 * w[1][j] + g2 * w[2][j];
+        store_vec<T>(out + off, o);
+    }
+}
+
+// ---- ToRGB backward w.r.t. the per-sample RGB weights: partial[b][chunk][c*3+k] = sum_pix g_rgb[b,k,p] * y[b,p,c]
+template <typename T>
+__global__ void __launch_bounds__(256) torgb_wgrad_kernel(const float *__restrict__ g_rgb, const T *__restrict__ y,
+                                                           float *__restrict__ partial, int64_t P, int C, int nchunks) {
+    constexpr int N = Vec<T>::N;
+    extern __shared__ float red[];
+    const int cv = C / N, lanes = 256 / cv;
+    const int vec = threadIdx.x % cv, lane = threadIdx.x / cv;
+    const bool active = lane < lanes;
+    const int b = blockIdx.y, chunk = blockIdx.x, c = vec * N;
+    float acc[3][N];
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+        for (int j = 0; j < N; ++j) acc[k][j] = 0.f;
+    if (active) {
+        const int64_t p0 = (int64_t)chunk * kBwdChunk, p1 = min(p0 + kBwdChunk, P);
+#pragma unroll 2
+        for (int64_t p = p0 + lane; p < p1; p += lanes) {
+            const float g0 = __ldg(g_rgb + ((int64_t)b * 3 + 0) * P + p), g1 = __ldg(g_rgb + ((int64_t)b * 3 + 1) * P + p),
+                        g2 = __ldg(g_rgb + ((int64_t)b * 3 + 2) * P + p);
+            const Vec<T> yv = load_vec<T>(y + ((int64_t)b * P + p) * C + c);
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+                acc[0][j] = fmaf(g0, yv.v[j], acc[0][j]);
+                acc[1][j] = fmaf(g1, yv.v[j], acc[1][j]);
+                acc[2][j] = fmaf(g2, yv.v[j], acc[2][j]);
+            }
+        }
+    }
+    block_reduce_store<N>(acc, 3, red, partial + (((int64_t)b * nchunks + chunk) * C) * 3, C, cv, lanes, lane, vec, active);
+}
+
+static inline int bwd_chunks(int64_t P) { return ceil_div(P, kBwdChunk); }
+
+template <typename T>
+static int check_vec(const char *what, int C) {
+    constexpr int N = Vec<T>::N;
+    OOD_REQUIRE(C % N == 0 && C / N <= 256, "%s: channels (%d) must be a multiple of %d and at most %d", what, C, N, 256 * N);
+    return OOD_OK;
+}
+
+}  // namespace ood
+
+extern "C" int64_t ood_bwd_workspace(int batch, int64_t pixels, int channels, int k) {
+    return (int64_t)batch * ood::bwd_chunks(pixels) * channels * k * (int64_t)sizeof(float);
+}
+
+extern "C" int ood_act_bwd(const void *gy, const void *y, const float *d, const float *bias, const float *noise,
+                           int64_t noise_bstride, const float *noise_w, void *g, float *workspace, float *gd, int batch,
+                           int64_t pixels, int channels, int dtype, void *stream) {
+    using namespace ood;
+    OOD_REQUIRE(gy && y && g && workspace && gd && batch > 0 && batch <= 65535 && pixels > 0, "act_bwd: bad arguments");
+    OOD_REQUIRE(dtype == OOD_F32 || dtype == OOD_BF16, "act_bwd: bad dtype");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int nch = bwd_chunks(pixels);
+    dim3 grid(nch, batch);
+    const int N = dtype == OOD_F32 ? 4 : 8;
+    if (int rc = (dtype == OOD_F32 ? check_vec<float>("act_bwd", channels) : check_vec<__nv_bfloat16>("act_bwd", channels))) return rc;
+    const size_t smem = (size_t)(256 / (channels / N)) * channels * sizeof(float);
+    if (dtype == OOD_F32)
+        act_bwd_kernel<float><<<grid, 256, smem, s>>>((const float *)gy, (const float *)y, d, bias, noise, noise_bstride, noise_w,
+                                                       (float *)g, workspace, pixels, channels, nch);
+    else
+        act_bwd_kernel<__nv_bfloat16><<<grid, 256, smem, s>>>((const __nv_bfloat16 *)gy, (const __nv_bfloat16 *)y, d, bias, noise,
+                                                               noise_bstride, noise_w, (__nv_bfloat16 *)g, workspace, pixels,
+                                                               channels, nch);
+    const int64_t total = (int64_t)batch * channels;
+    reduce_partials_kernel<<<ceil_div(total, 256), 256, 0, s>>>(workspace, d, gd, channels, 1, nch, total);
+    return check_launch("act_bwd", 2);
+}
+
+extern "C" int ood_dot_reduce(const void *a, const void *b, float *workspace, float *out, int batch, int64_t pixels,
+                              int channels, int dtype, void *stream) {
+    using namespace ood;
+    OOD_REQUIRE(a && b && workspace && out && batch > 0 && batch <= 65535 && pixels > 0, "dot_reduce: bad arguments");
+    OOD_REQUIRE(dtype == OOD_F32 || dtype == OOD_BF16, "dot_reduce: bad dtype");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int nch = bwd_chunks(pixels);
+    dim3 grid(nch, batch);
+    const int N = dtype == OOD_F32 ? 4 : 8;
+    if (int rc = (dtype == OOD_F32 ? check_vec<float>("dot_reduce", channels) : check_vec<__nv_bfloat16>("dot_reduce", channels))) return rc;
+    const size_t smem = (size_t)(256 / (channels / N)) * channels * sizeof(float);
+    if (dtype == OOD_F32) dot_partial_kernel<float><<<grid, 256, smem, s>>>((const float *)a, (const float *)b, workspace, pixels, channels, nch);
+    else dot_partial_kernel<__nv_bfloat16><<<grid, 256, smem, s>>>((const __nv_bfloat16 *)a, (const __nv_bfloat16 *)b, workspace, pixels, channels, nch);
+    const int64_t total = (int64_t)batch * channels;
+    reduce_partials_kernel<<<ceil_div(total, 256), 256, 0, s>>>(workspace, nullptr, out, channels, 1, nch, total);
+    return check_launch("dot_reduce", 2);
+}
+
+extern "C" int ood_torgb_bwd(const float *g_rgb, const float *wrgb, const void *y, const void *g_in, void *g_out,
+                             float *workspace, float *g_wrgb, int batch, int64_t pixels, int channels, int dtype,
+                             void *stream) {
+    using namespace ood;
+    OOD_REQUIRE(g_rgb && wrgb && y && g_out && workspace && g_wrgb && batch > 0 && batch <= 65535 && pixels > 0, "torgb_bwd: bad arguments");
+    OOD_REQUIRE(dtype == OOD_F32 || dtype == OOD_BF16, "torgb_bwd: bad dtype");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int nch = bwd_chunks(pixels);
+    dim3 grid(nch, batch);
+    const int N = dtype == OOD_F32 ? 4 : 8;
+    if (int rc = (dtype == OOD_F32 ? check_vec<float>("torgb_bwd", channels) : check_vec<__nv_bfloat16>("torgb_bwd", channels))) return rc;
+    const size_t smem = (size_t)(256 / (channels / N)) * channels * 3 * sizeof(float);
+    if (dtype == OOD_F32) {
+        torgb_bwd_y_kernel<float><<<grid, 256, 0, s>>>(g_rgb, wrgb, (const float *)g_in, (float *)g_out, pixels, channels);
+        torgb_wgrad_kernel<float><<<grid, 256, smem, s>>>(g_rgb, (const float *)y, workspace, pixels, channels, nch);
+    } else {
+        torgb_bwd_y_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(g_rgb, wrgb, (const __nv_bfloat16 *)g_in, (__nv_bfloat16 *)g_out, pixels, channels);
+        torgb_wgrad_kernel<__nv_bfloat16><<<grid, 256, smem, s>>>(g_rgb, (const __nv_bfloat16 *)y, workspace, pixels, channels, nch);
+    }
+    const int64_t total = (int64_t)batch * channels * 3;
+    reduce_partials_kernel<<<ceil_div(total, 256), 256, 0, s>>>(workspace, nullptr, g_wrgb, channels, 3, nch, total);
+    return check_launch("torgb_bwd", 3);
+}

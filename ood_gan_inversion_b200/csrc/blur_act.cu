@@ -21,6 +21,7 @@ struct BlurParams {
     float k[4];          // flipped 1-D taps
     int batch, ih, iw, oh, ow, C;
     int act;
+    int pad0;            // leading pad: input pixel = output pixel - pad0 + tap
 };
 
 template <typename TIN, int N>
@@ -92,13 +93,13 @@ __global__ void __launch_bounds__(128) blur_act_kernel(const BlurParams p) {
     float hw[4][XPT][N];   // horizontally filtered rows, slot = input-row index & 3 (compile-time after unrolling)
 #pragma unroll
     for (int i = 0; i < kStrip + 3; ++i) {
-        const int iy = oy0 - 1 + i;
+        const int iy = oy0 - p.pad0 + i;
         // ---- horizontal pass for input row iy ----
         float row[XPT + 3][N];
         const bool row_ok = iy >= 0 && iy < p.ih;
 #pragma unroll
         for (int q = 0; q < XPT + 3; ++q) {
-            const int ix = ox0 - 1 + q;
+            const int ix = ox0 - p.pad0 + q;
             if (row_ok && ix >= 0 && ix < p.iw) {
                 load_n<TIN, N>(src + ((int64_t)iy * p.iw + ix) * p.C, row[q]);
             } else {
@@ -192,7 +193,9 @@ extern "C" int ood_blur_act(const ood_blur_act_args *a, void *stream) {
     p.d = a->d; p.noise = a->noise; p.noise_w = a->noise_w; p.bias = a->bias; p.s_next = a->s_next;
     p.noise_bstride = a->noise_bstride;
     for (int i = 0; i < 4; ++i) p.k[i] = a->taps[3 - i];   // correlation with the flipped FIR (upfirdn2d.py:179)
-    p.batch = a->batch; p.ih = a->ih; p.iw = a->iw; p.oh = a->ih - 1; p.ow = a->iw - 1; p.C = a->channels;
+    p.batch = a->batch; p.ih = a->ih; p.iw = a->iw; p.pad0 = a->pad0 > 0 ? a->pad0 : 1;
+    const int pad1 = a->pad0 > 0 ? a->pad1 : 1;
+    p.oh = a->ih + p.pad0 + pad1 - 3; p.ow = a->iw + p.pad0 + pad1 - 3; p.C = a->channels;
     p.act = a->act;
     constexpr int XPT = 2;
     const int cv = p.C / N;

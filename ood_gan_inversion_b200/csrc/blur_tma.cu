@@ -19,7 +19,7 @@ struct BlurTmaParams {
     const float *d, *noise, *noise_w, *bias, *s_next;
     int64_t noise_bstride;
     float k[4];
-    int batch, oh, ow, C;
+    int batch, oh, ow, C, pad0;
     int tiles_x, tiles_y, cblocks, total_tiles;
     int act;
 };
@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(256) blur_tma_kernel(const __grid_constant__ C
         asm volatile(
             "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
             ::"r"(bt_smem_u32(smem + stage * STAGE_STRIDE)), "l"(&tm), "r"(bt_smem_u32(&bars[stage])), "r"(cb * BT_CB),
-            "r"(tx * BT_TW - 1), "r"(ty * BT_TH - 1), "r"(b)
+            "r"(tx * BT_TW - p.pad0), "r"(ty * BT_TH - p.pad0), "r"(b)
             : "memory");
     };
 
@@ -229,7 +229,9 @@ int blur_act_tma(const ood_blur_act_args *a, cudaStream_t st, int *handled) {
     p.d = a->d; p.noise = a->noise; p.noise_w = a->noise_w; p.bias = a->bias; p.s_next = a->s_next;
     p.noise_bstride = a->noise_bstride;
     for (int i = 0; i < 4; ++i) p.k[i] = a->taps[3 - i];
-    p.batch = a->batch; p.oh = a->ih - 1; p.ow = a->iw - 1; p.C = a->channels;
+    p.pad0 = a->pad0 > 0 ? a->pad0 : 1;
+    const int pad1 = a->pad0 > 0 ? a->pad1 : 1;
+    p.batch = a->batch; p.oh = a->ih + p.pad0 + pad1 - 3; p.ow = a->iw + p.pad0 + pad1 - 3; p.C = a->channels;
     p.tiles_x = ceil_div(p.ow, BT_TW); p.tiles_y = ceil_div(p.oh, BT_TH); p.cblocks = a->channels / BT_CB;
     const int64_t total = (int64_t)p.tiles_x * p.tiles_y * p.cblocks * a->batch;
     if (total >= (1LL << 31)) return OOD_OK;

@@ -21,6 +21,7 @@ struct ConvGeom {
     int batch, h, w, cin, cout;
     int OH, OW;           // full output size
     int sy, sx;           // output stride of a phase (1 or 2)
+    int isy, isx;         // input stride: input pixel = (oy*isy + dy, ox*isx + dx)   (2 for the strided data-gradient form)
     int nphases;
     ConvPhase ph[4];
 };
@@ -28,7 +29,20 @@ struct ConvGeom {
 static inline ConvGeom make_geom(int batch, int h, int w, int cin, int cout, int transposed) {
     ConvGeom g{};
     g.batch = batch; g.h = h; g.w = w; g.cin = cin; g.cout = cout;
-    if (!transposed) {
+    g.isy = g.isx = 1;
+    if (transposed == 2) {
+        // stride-2 "valid" 3x3 conv: out[y,x] = sum in[2y+ky, 2x+kx] * W[ky,kx] -- the data gradient of the stride-2
+        // transposed conv (input = gradient of the (2h+1)x(2w+1) tensor, output h x w)
+        g.OH = (h - 1) / 2; g.OW = (w - 1) / 2; g.sy = g.sx = 1; g.isy = g.isx = 2; g.nphases = 1;
+        ConvPhase &p = g.ph[0];
+        p.oh = g.OH; p.ow = g.OW; p.py = p.px = 0; p.ntaps = 9;
+        for (int ky = 0; ky < 3; ++ky)
+            for (int kx = 0; kx < 3; ++kx) {
+                const int t = ky * 3 + kx;
+                p.dy[t] = ky; p.dx[t] = kx; p.wt[t] = t;
+            }
+        p.m_total = batch * p.oh * p.ow;
+    } else if (!transposed) {
         g.OH = h; g.OW = w; g.sy = g.sx = 1; g.nphases = 1;
         ConvPhase &p = g.ph[0];
         p.oh = h; p.ow = w; p.py = p.px = 0; p.ntaps = 9;

@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const SimtParams p) {
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
     for (int t = 0; t < ph.ntaps; ++t) {
-        const int iy = aoy + ph.dy[t], ix = aox + ph.dx[t];
+        const int iy = aoy * p.g.isy + ph.dy[t], ix = aox * p.g.isx + ph.dx[t];
         const bool in_ok = a_valid && iy >= 0 && iy < p.g.h && ix >= 0 && ix < p.g.w;
         const float *arow = p.in + (((int64_t)ab * p.g.h + iy) * p.g.w + ix) * cin;
         const float *wtap = p.w + (int64_t)ph.wt[t] * cin * cout;

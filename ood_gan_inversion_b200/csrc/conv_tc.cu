@@ -27,6 +27,7 @@ struct TcPhase {
 
 struct TcParams {
     int batch, h, w, cin, cout, OH, OW, sy, sx;
+    int isy, isx;                   // input stride (2 for the strided data-gradient form; the TMA map then carries elementStrides 2)
     int TW, TH, NB;                 // pixel patch of one M tile: NB*TH*TW == 128
     int nphases, n_tiles_n, total_tiles;
     TcPhase ph[4];
@@ -193,7 +194,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     for (int kc = 0; kc < kchunks; ++kc) {
                         mbar_wait(&empty[stage], phase ^ 1);
                         mbar_expect_tx(&full[stage], Cfg::kStageBytes);
-                        tma_load_4d(sA + stage * Cfg::kABytes, &tmA, &full[stage], kc * BK, tc.x0 + P.dx[t], tc.y0 + P.dy[t], tc.b0);
+                        tma_load_4d(sA + stage * Cfg::kABytes, &tmA, &full[stage], kc * BK, tc.x0 * p.isx + P.dx[t], tc.y0 * p.isy + P.dy[t], tc.b0);
                         tma_load_3d(sB + stage * Cfg::kBBytes, &tmB, &full[stage], kc * BK, tc.n0, P.wt[t]);
                         if (++stage == S) { stage = 0; phase ^= 1; }
                     }
@@ -382,6 +383,7 @@ int conv3x3_tc(const ood_conv3x3_args &a, cudaStream_t st) {
 
     TcParams p{};
     p.batch = g.batch; p.h = g.h; p.w = g.w; p.cin = g.cin; p.cout = g.cout; p.OH = g.OH; p.OW = g.OW; p.sy = g.sy; p.sx = g.sx;
+    p.isy = g.isy; p.isx = g.isx;
     int ohm = 0, owm = 0;
     for (int i = 0; i < g.nphases; ++i) { ohm = std::max(ohm, g.ph[i].oh); owm = std::max(owm, g.ph[i].ow); }
     p.TW = std::min(pow2_ceil(owm), TBM);
@@ -407,8 +409,9 @@ int conv3x3_tc(const ood_conv3x3_args &a, cudaStream_t st) {
     {
         cuuint64_t dims[4] = {(cuuint64_t)a.cin, (cuuint64_t)a.w, (cuuint64_t)a.h, (cuuint64_t)a.batch};
         cuuint64_t strides[3] = {(cuuint64_t)a.cin * 2, (cuuint64_t)a.w * a.cin * 2, (cuuint64_t)a.h * a.w * a.cin * 2};
-        cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)p.TW, (cuuint32_t)p.TH, (cuuint32_t)p.NB};
-        cuuint32_t es[4] = {1, 1, 1, 1};
+        // with element stride s the box spans s*(n-1)+1 tensor elements and delivers n of them to shared memory
+        cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)(g.isx * (p.TW - 1) + 1), (cuuint32_t)(g.isy * (p.TH - 1) + 1), (cuuint32_t)p.NB};
+        cuuint32_t es[4] = {1, (cuuint32_t)g.isx, (cuuint32_t)g.isy, 1};
         CUresult r = encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(a.in), dims, strides, box, es,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -442,8 +445,11 @@ extern "C" int ood_conv3x3(const ood_conv3x3_args *a, void *stream) {
     OOD_REQUIRE(a->batch > 0 && a->h > 0 && a->w > 0 && a->cin > 0 && a->cout > 0, "conv3x3: bad sizes");
     OOD_REQUIRE(a->out_y || a->out_ys, "conv3x3: no output requested");
     OOD_REQUIRE(!a->out_ys || a->s_next, "conv3x3: out_ys needs s_next");
-    OOD_REQUIRE(!a->transposed || (!a->out_ys && !a->act && !a->noise && !a->bias),
+    OOD_REQUIRE(a->transposed >= 0 && a->transposed <= 2, "conv3x3: transposed must be 0, 1 or 2");
+    OOD_REQUIRE(a->transposed != 1 || (!a->out_ys && !a->act && !a->noise && !a->bias),
                 "conv3x3: the transposed form writes raw accumulators (the epilogue follows the blur)");
+    OOD_REQUIRE(a->transposed != 2 || (a->h % 2 == 1 && a->w % 2 == 1 && a->h >= 3 && a->w >= 3 && !a->noise),
+                "conv3x3: the strided data-gradient form needs an odd (2h+1)x(2w+1) input");
     OOD_REQUIRE(!(a->out_f32 && a->out_ys), "conv3x3: out_f32 applies to out_y only");
     OOD_REQUIRE(a->act >= 0 && a->act <= 2 && (a->act != 2 || a->prelu_slope), "conv3x3: act must be 0, 1 or 2 (PReLU needs prelu_slope)");
     cudaStream_t st = (cudaStream_t)stream;

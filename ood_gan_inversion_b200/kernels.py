@@ -217,7 +217,8 @@ def conv3x3(x, weight, cout, transposed=False, impl=0, d=None, noise=None, noise
     _cuda(x, weight, d, noise, noise_w, bias, s_next)
     assert x.is_contiguous()
     b, h, w, cin = x.shape
-    oh, ow = (2 * h + 1, 2 * w + 1) if transposed else (h, w)
+    transposed = int(transposed)      # 0 stride-1 | 1 stride-2 transposed | 2 stride-2 valid (data gradient of 1)
+    oh, ow = {0: (h, w), 1: (2 * h + 1, 2 * w + 1), 2: ((h - 1) // 2, (w - 1) // 2)}[transposed]
     y = torch.empty(b, oh, ow, cout, device=x.device, dtype=torch.float32 if out_f32 else x.dtype) if want_y else None
     ys = torch.empty(b, oh, ow, cout, device=x.device, dtype=x.dtype) if want_ys else None
     nbs = 0
@@ -233,26 +234,28 @@ def conv3x3(x, weight, cout, transposed=False, impl=0, d=None, noise=None, noise
 
 
 def blur_act(t, taps, d=None, noise=None, noise_w=None, bias=None, s_next=None, act=True, want_img=False, want_y=True,
-             want_ys=False, dtype=None):
-    """t NHWC [B,IH,IW,C] (fp32 or storage dtype) -> blurred [B,IH-1,IW-1,C] (+ fused StyledConv tail)."""
+             want_ys=False, dtype=None, pad=(1, 1)):
+    """t NHWC [B,IH,IW,C] (fp32 or storage dtype) -> blurred [B,IH+p0+p1-3,...,C] (+ fused StyledConv tail).
+    pad (1,1): the blur after the transposed conv; pad (2,2): its adjoint (gradient w.r.t. the transposed-conv output)."""
     _cuda(t, d, noise, noise_w, bias, s_next)
     assert t.is_contiguous()
     b, ih, iw, c = t.shape
     dtype = dtype or t.dtype
-    mk = lambda: torch.empty(b, ih - 1, iw - 1, c, device=t.device, dtype=dtype)
+    oh, ow = ih + pad[0] + pad[1] - 3, iw + pad[0] + pad[1] - 3
+    mk = lambda: torch.empty(b, oh, ow, c, device=t.device, dtype=dtype)
     img = mk() if want_img else None
     y = mk() if (act and want_y) else None
     ys = mk() if (act and want_ys) else None
     nbs = 0
     if noise is not None:
         assert noise.dtype == torch.float32 and noise.is_contiguous()
-        nbs = 0 if noise.shape[0] == 1 else (ih - 1) * (iw - 1)
+        nbs = 0 if noise.shape[0] == 1 else oh * ow
     a = BlurActArgs(_ptr(t), int(t.dtype == torch.float32 and dtype != torch.float32), _ptr(img), _ptr(y), _ptr(ys), _ptr(d),
                     _ptr(noise), _ptr(noise_w), _ptr(bias), _ptr(s_next), nbs, (C.c_float * 4)(*taps), b, ih, iw, c,
-                    int(act), F32 if dtype == torch.float32 else BF16)
+                    int(act), F32 if dtype == torch.float32 else BF16, int(pad[0]), int(pad[1]))
     nout = sum(o is not None for o in (img, y, ys))
-    work = b * c * (ih * iw * _esize(t) + nout * (ih - 1) * (iw - 1) * (4 if dtype == torch.float32 else 2)) + \
-        (0 if noise is None else noise.shape[0] * (ih - 1) * (iw - 1) * 4)
+    work = b * c * (ih * iw * _esize(t) + nout * oh * ow * (4 if dtype == torch.float32 else 2)) + \
+        (0 if noise is None else noise.shape[0] * oh * ow * 4)
     with _timed('blur_act', work):
         check(_lib.lib().ood_blur_act(C.byref(a), _stream()), 'blur_act')
     return img, y, ys
@@ -308,6 +311,50 @@ def warp_mix(gen, field):
     with _timed('warp_mix', b * h * w * (2 * c * _esize(gen) + 3 * 4)):
         check(_lib.lib().ood_warp_mix(_ptr(gen), _ptr(_f32c(field)), _ptr(out), b, h, w, c, _dt(gen), _stream()), 'warp_mix')
     return out
+
+
+def _bwd_ws(b, pixels, c, k, device):
+    return torch.empty(_lib.lib().ood_bwd_workspace(b, pixels, c, k) // 4, device=device, dtype=torch.float32)
+
+
+def act_bwd(gy, y, d, bias, noise, noise_w):
+    """Backward of lrelu*sqrt2 / bias / noise / demod.  gy, y NHWC -> (g = gv*d NHWC, gd [B,C] fp32)."""
+    _cuda(gy, y, d, bias, noise, noise_w)
+    assert gy.is_contiguous() and y.is_contiguous() and gy.dtype == y.dtype
+    b, h, w, c = y.shape
+    g = torch.empty_like(y)
+    gd = torch.empty(b, c, device=y.device, dtype=torch.float32)
+    nbs = 0 if (noise is None or noise.shape[0] == 1) else h * w
+    with _timed('act_bwd', b * h * w * c * _esize(y) * 3):
+        check(_lib.lib().ood_act_bwd(_ptr(gy), _ptr(y), _ptr(d), _ptr(bias), _ptr(noise), nbs, _ptr(noise_w), _ptr(g),
+                                     _ptr(_bwd_ws(b, h * w, c, 1, y.device)), _ptr(gd), b, h * w, c, _dt(y), _stream()), 'act_bwd')
+    return g, gd
+
+
+def dot_reduce(a, x):
+    """sum over pixels of a*x per (b, c): NHWC, NHWC -> [B,C] fp32"""
+    _cuda(a, x)
+    assert a.is_contiguous() and x.is_contiguous() and a.dtype == x.dtype and a.shape == x.shape
+    b, h, w, c = a.shape
+    out = torch.empty(b, c, device=a.device, dtype=torch.float32)
+    with _timed('dot_reduce', b * h * w * c * _esize(a) * 2):
+        check(_lib.lib().ood_dot_reduce(_ptr(a), _ptr(x), _ptr(_bwd_ws(b, h * w, c, 1, a.device)), _ptr(out), b, h * w, c, _dt(a),
+                                        _stream()), 'dot_reduce')
+    return out
+
+
+def torgb_bwd(g_rgb, wrgb, y, g_in=None):
+    """g_rgb NCHW fp32 [B,3,H,W]; wrgb [B,3,C]; y NHWC -> (g_y NHWC = g_in + expand, g_wrgb [B,3,C] fp32)"""
+    _cuda(g_rgb, wrgb, y, g_in)
+    assert y.is_contiguous() and (g_in is None or (g_in.is_contiguous() and g_in.dtype == y.dtype))
+    g_rgb = _f32c(g_rgb)
+    b, h, w, c = y.shape
+    g_out = torch.empty_like(y)
+    gw = torch.empty(b, c, 3, device=y.device, dtype=torch.float32)
+    with _timed('torgb_bwd', b * h * w * (c * _esize(y) * 3 + 12)):
+        check(_lib.lib().ood_torgb_bwd(_ptr(g_rgb), _ptr(wrgb), _ptr(y), _ptr(g_in), _ptr(g_out), _ptr(_bwd_ws(b, h * w, c, 3, y.device)),
+                                       _ptr(gw), b, h * w, c, _dt(y), _stream()), 'torgb_bwd')
+    return g_out, gw.permute(0, 2, 1).contiguous()
 
 
 def in_stats(x, y=None, eps=1e-5):

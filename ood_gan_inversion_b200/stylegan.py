@@ -484,6 +484,20 @@ class Generator(nn.Module):
     def _synthesis(self, latent, noise, conditions, cond_layers, return_features, kwargs):
         if not latent.is_cuda:
             raise RuntimeError('ood_gan_inversion_b200 is CUDA-only: move the generator and latents to a CUDA device')
+        if torch.is_grad_enabled() and latent.requires_grad:
+            # optimisation-based inversion: differentiable w.r.t. the W+ latents (weights frozen), hand-written backward
+            if (cond_layers is not None and conditions is not None) or kwargs.get('features_in', None) is not None or return_features:
+                raise NotImplementedError('ood_gan_inversion_b200: the differentiable path covers the plain synthesis '
+                                          '(no alignment callback / features_in / return_features)')
+            from .synthesis_grad import synthesis
+            b = latent.shape[0]
+            nz = []
+            for li in range(self.num_layers):
+                res = 2 ** ((li + 5) // 2)
+                n = noise[li]
+                nz.append(n.detach().float().contiguous() if n is not None else
+                          torch.empty(b, 1, res, res, device=latent.device, dtype=torch.float32).normal_())
+            return synthesis(self, latent, nz), None
         lat = latent.detach().float().contiguous()
         b = lat.shape[0]
         dev = lat.device

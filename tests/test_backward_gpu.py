@@ -1,0 +1,171 @@
+"""GPU parity of the backward path: kernels vs autograd of the oracle formulas, and the W+ latent
+gradient of the whole synthesis vs torch.autograd through the oracle generator (same device, TF32 off)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import ops as oops, stylegan as ostyle
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+
+
+@pytest.fixture(autouse=True)
+def _setup():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+
+
+def K():
+    from ood_gan_inversion_b200 import kernels
+    return kernels
+
+
+def rnd(*shape, seed=0):
+    return torch.randn(*shape, generator=torch.Generator().manual_seed(seed))
+
+
+def nhwc(x, dtype=torch.float32):
+    return x.permute(0, 2, 3, 1).contiguous().to(dtype).to(DEV)
+
+
+def nchw(x):
+    return x.float().permute(0, 3, 1, 2).contiguous().cpu()
+
+
+@pytest.mark.parametrize('impl', [0, 1])
+@pytest.mark.parametrize('case', [dict(b=2, h=9, w=13, ci=64, co=32), dict(b=1, h=17, w=17, ci=32, co=64), dict(b=3, h=5, w=5, ci=128, co=128),
+                                  dict(b=1, h=9, w=271, ci=32, co=32)])
+def test_strided_gather_conv(impl, case):
+    """transposed=2: out[y,x] = sum in[2y+ky, 2x+kx] W[ky,kx] == F.conv2d(stride=2) == data gradient of conv_transpose2d(stride=2)."""
+    b, h, w_, ci, co = case['b'], case['h'], case['w'], case['ci'], case['co']
+    dt = torch.bfloat16 if impl == 0 else torch.float32
+    x, w = rnd(b, ci, h, w_, seed=1).to(dt).float(), (0.2 * rnd(co, ci, 3, 3, seed=2)).to(dt).float()
+    y, _ = K().conv3x3(nhwc(x, dt), K().pack_conv_weight(w.to(DEV), dt, impl == 1), co, transposed=2, impl=impl, out_f32=(impl == 0))
+    ref = F.conv2d(x.double(), w.double(), stride=2).float()
+    assert y.shape[1:3] == ((h - 1) // 2, (w_ - 1) // 2)
+    torch.testing.assert_close(nchw(y), ref, rtol=1e-4, atol=2e-3)
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_blur_adjoint(dtype):
+    x = rnd(2, 32, 10, 14, seed=1).to(dtype).float()
+    k = oops.fir_kernel([1, 3, 3, 1], 4.0)
+    ref = oops.upfirdn2d(x, torch.flip(k, [0, 1]), pad=(2, 2))         # adjoint of the pad-(1,1) blur
+    out, _, _ = K().blur_act(nhwc(x, dtype), list(reversed(K().fir_taps(gain=2.0))), act=False, want_img=True, pad=(2, 2))
+    assert out.shape[1:3] == (11, 15)
+    tol = dict(rtol=1e-5, atol=1e-5) if dtype == torch.float32 else dict(rtol=2e-2, atol=2e-2)
+    torch.testing.assert_close(nchw(out), ref, **tol)
+    # <blur(t), g> == <t, blur^T(g)>
+    t, g = rnd(1, 32, 9, 9, seed=2), rnd(1, 32, 8, 8, seed=3)
+    bt, _, _ = K().blur_act(nhwc(t), K().fir_taps(gain=2.0), act=False, want_img=True)
+    bg, _, _ = K().blur_act(nhwc(g), list(reversed(K().fir_taps(gain=2.0))), act=False, want_img=True, pad=(2, 2))
+    assert abs(float((bt * nhwc(g)).sum()) - float((nhwc(t) * bg).sum())) < 1e-2
+
+
+def test_act_bwd_dot_torgb_bwd_vs_autograd():
+    b, c, h, w = 2, 32, 9, 11
+    acc = rnd(b, c, h, w, seed=1).requires_grad_(True)
+    d = (0.5 + rnd(b, c, seed=2).abs()).requires_grad_(True)
+    bias, noise, nw = rnd(c, seed=3), rnd(b, 1, h, w, seed=4), torch.tensor([0.3])
+    y = oops.fused_leaky_relu(acc * d[:, :, None, None] + nw * noise, bias)
+    gy = rnd(b, c, h, w, seed=5)
+    g_acc_ref, gd_ref = torch.autograd.grad(y, [acc, d], gy)
+    g, gd = K().act_bwd(nhwc(gy), nhwc(y.detach()), d.detach().to(DEV), bias.to(DEV), noise.to(DEV), nw.to(DEV))
+    torch.testing.assert_close(nchw(g), g_acc_ref, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(gd.cpu(), gd_ref, rtol=1e-3, atol=1e-3)
+    a_, x_ = rnd(b, c, h, w, seed=6), rnd(b, c, h, w, seed=7)
+    torch.testing.assert_close(K().dot_reduce(nhwc(a_), nhwc(x_)).cpu(), (a_ * x_).sum((2, 3)), rtol=1e-4, atol=1e-4)
+    # ToRGB
+    yv = rnd(b, c, h, w, seed=8).requires_grad_(True)
+    wrgb = rnd(b, 3, c, seed=9).requires_grad_(True)
+    rgb = torch.einsum('bchw,bkc->bkhw', yv, wrgb)
+    g_rgb, g_in = rnd(b, 3, h, w, seed=10), rnd(b, c, h, w, seed=11)
+    gy_ref, gw_ref = torch.autograd.grad(rgb, [yv, wrgb], g_rgb)
+    gy_k, gw_k = K().torgb_bwd(g_rgb.to(DEV), wrgb.detach().to(DEV), nhwc(yv.detach()), nhwc(g_in))
+    torch.testing.assert_close(nchw(gy_k), gy_ref + g_in, rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(gw_k.cpu(), gw_ref, rtol=1e-4, atol=1e-3)
+
+
+def _latent_grad_case(size, batch, precision):
+    import ood_gan_inversion_b200.stylegan as sg
+    sg.set_precision(precision)
+    sd = ostyle.synthetic_generator_state(size, seed=size)
+    gen = sg.Generator(size, 512, 8).to(DEV)
+    gen.load_state_dict(sd, strict=True)
+    for p in gen.parameters():
+        p.requires_grad_(False)
+    lat0 = torch.randn(batch, gen.n_latent, 512, generator=torch.Generator().manual_seed(1)).to(DEV)
+    target = torch.randn(batch, 3, size, size, generator=torch.Generator().manual_seed(2)).to(DEV) * 0.3
+    lat = lat0.clone().requires_grad_(True)
+    img, _ = gen(lat, input_is_tensor=True, input_is_latent=True, randomize_noise=False)
+    loss = F.mse_loss(img, target)
+    g, = torch.autograd.grad(loss, lat)
+    sdd = {k: v.to(DEV) for k, v in sd.items()}
+    lat_r = lat0.clone().requires_grad_(True)
+    img_r = ostyle.generator_forward(sdd, lat_r, size, randomize_noise=False)
+    g_r, = torch.autograd.grad(F.mse_loss(img_r, target), lat_r)
+    sg.set_precision('bf16')
+    return g, g_r, float((img.detach() - img_r.detach()).abs().max())
+
+
+@pytest.mark.parametrize('size,batch', [(16, 2), (64, 2), (256, 1)])
+def test_latent_gradient_fp32_vs_oracle_autograd(size, batch):
+    g, g_r, img_err = _latent_grad_case(size, batch, 'fp32')
+    assert img_err < 1e-3
+    rel = float((g - g_r).norm() / g_r.norm())
+    print(f'fp32 dL/dW+ size {size}: rel-L2 {rel:.3g}, max-abs {float((g - g_r).abs().max()):.3g} (|g| max {float(g_r.abs().max()):.3g})')
+    assert rel < 1e-3
+    torch.testing.assert_close(g, g_r, rtol=1e-2, atol=1e-3 * float(g_r.abs().max()))
+
+
+@pytest.mark.parametrize('size,batch', [(64, 2), (256, 1)])
+def test_latent_gradient_bf16_direction(size, batch):
+    g, g_r, img_err = _latent_grad_case(size, batch, 'bf16')
+    cos = float(F.cosine_similarity(g.flatten(), g_r.flatten(), dim=0))
+    rel = float((g - g_r).norm() / g_r.norm())
+    print(f'bf16 dL/dW+ size {size}: cosine {cos:.5f}, rel-L2 {rel:.3g}')
+    assert img_err < 2e-2 and cos > 0.99 and rel < 0.1
+
+
+def test_adam_inversion_loss_curve_matches_oracle():
+    """BASELINE config 4 protocol at small size: N Adam steps on W+ from the same start; loss curves and final latents agree."""
+    import ood_gan_inversion_b200.stylegan as sg
+    sg.set_precision('fp32')
+    size, batch, steps = 32, 2, 8
+    sd = ostyle.synthetic_generator_state(size, seed=3)
+    gen = sg.Generator(size, 512, 8).to(DEV)
+    gen.load_state_dict(sd)
+    for p in gen.parameters():
+        p.requires_grad_(False)
+    sdd = {k: v.to(DEV) for k, v in sd.items()}
+    lat0 = 0.5 * torch.randn(batch, gen.n_latent, 512, generator=torch.Generator().manual_seed(4)).to(DEV)
+    with torch.no_grad():
+        target = ostyle.generator_forward(sdd, torch.randn(batch, gen.n_latent, 512, generator=torch.Generator().manual_seed(5)).to(DEV),
+                                          size, randomize_noise=False)
+    curves = []
+    finals = []
+    for which in ('ours', 'oracle'):
+        lat = lat0.clone().requires_grad_(True)
+        opt = torch.optim.Adam([lat], lr=0.01)
+        losses = []
+        for _ in range(steps):
+            opt.zero_grad()
+            if which == 'ours':
+                img, _ = gen(lat, input_is_tensor=True, input_is_latent=True, randomize_noise=False)
+            else:
+                img = ostyle.generator_forward(sdd, lat, size, randomize_noise=False)
+            loss = F.mse_loss(img, target)
+            loss.backward()
+            opt.step()
+            losses.append(float(loss))
+        curves.append(losses)
+        finals.append(lat.detach())
+    print('loss curves', curves)
+    assert curves[0][-1] < curves[0][0]
+    torch.testing.assert_close(torch.tensor(curves[0]), torch.tensor(curves[1]), rtol=1e-3, atol=1e-6)
+    assert float((finals[0] - finals[1]).abs().max()) < 5e-3
+    sg.set_precision('bf16')
