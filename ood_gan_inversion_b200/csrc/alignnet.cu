@@ -9,20 +9,26 @@
 
 namespace ood {
 
-constexpr int kStatChunk = 512;    // pixels per partial-sum block
+// pixels per partial-sum block: small tensors get small chunks so that the grid still fills the 148 SMs
+static inline int stat_chunk(int64_t P, int batch) {
+    int c = 512;
+    while (c > 32 && (int64_t)batch * ((P + c - 1) / c) < 1024) c >>= 1;
+    return c;
+}
 
 // ---------------------------------------------------------------------------------------------- statistics
 // partial[b][chunk][c][K]: K = 2 (sum x, sum x^2) or 5 (+ sum y, sum y^2, sum xy)
 template <typename T, int K>
 __global__ void __launch_bounds__(256) in_partial_kernel(const T *__restrict__ x, const T *__restrict__ y,
-                                                          float *__restrict__ partial, int64_t P, int C, int nchunks) {
+                                                          float *__restrict__ partial, int64_t P, int C, int nchunks,
+                                                          int chunk_px) {
     constexpr int N = Vec<T>::N;
     extern __shared__ float red[];                      // [lanes][cv*N*K]
     const int cv = C / N;
     const int lanes = 256 / cv > 0 ? 256 / cv : 1;      // pixel lanes per block (cv <= 256 enforced by the host)
     const int vec = threadIdx.x % cv, lane = threadIdx.x / cv;
     const int b = blockIdx.y, chunk = blockIdx.x;
-    const int64_t p0 = (int64_t)chunk * kStatChunk, p1 = min(p0 + kStatChunk, P);
+    const int64_t p0 = (int64_t)chunk * chunk_px, p1 = min(p0 + chunk_px, P);
     float acc[N][K];
 #pragma unroll
     for (int j = 0; j < N; ++j)
@@ -223,7 +229,8 @@ static int launch_stats(const void *x, const void *y, float *partial, float *st,
                         cudaStream_t s) {
     constexpr int N = Vec<T>::N;
     OOD_REQUIRE(C % N == 0 && C / N <= 256, "in_stats: channels (%d) must be a multiple of %d and at most %d", C, N, 256 * N);
-    const int nchunks = ceil_div(P, kStatChunk);
+    const int chunk_px = stat_chunk(P, batch);
+    const int nchunks = ceil_div(P, chunk_px);
     const int cv = C / N, lanes = 256 / cv;
     const int K = y ? 5 : 2;
     const size_t smem = (size_t)lanes * C * K * sizeof(float);
@@ -232,13 +239,13 @@ static int launch_stats(const void *x, const void *y, float *partial, float *st,
     if (y) {
         auto kern = in_partial_kernel<T, 5>;
         if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        kern<<<grid, 256, smem, s>>>((const T *)x, (const T *)y, partial, P, C, nchunks);
+        kern<<<grid, 256, smem, s>>>((const T *)x, (const T *)y, partial, P, C, nchunks, chunk_px);
         const int64_t total = (int64_t)batch * C;
         in_finalize_pair_kernel<<<ceil_div(total, 256), 256, 0, s>>>(partial, st, P, C, nchunks, eps, total);
     } else {
         auto kern = in_partial_kernel<T, 2>;
         if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        kern<<<grid, 256, smem, s>>>((const T *)x, nullptr, partial, P, C, nchunks);
+        kern<<<grid, 256, smem, s>>>((const T *)x, nullptr, partial, P, C, nchunks, chunk_px);
         const int64_t total = (int64_t)batch * C;
         in_finalize_kernel<<<ceil_div(total, 256), 256, 0, s>>>(partial, st, P, C, nchunks, eps, total);
     }
@@ -248,7 +255,7 @@ static int launch_stats(const void *x, const void *y, float *partial, float *st,
 }  // namespace ood
 
 extern "C" int64_t ood_in_stats_workspace(int batch, int64_t pixels, int channels, int pair) {
-    return (int64_t)batch * ood::ceil_div(pixels, ood::kStatChunk) * channels * (pair ? 5 : 2) * (int64_t)sizeof(float);
+    return (int64_t)batch * ood::ceil_div(pixels, ood::stat_chunk(pixels, batch)) * channels * (pair ? 5 : 2) * (int64_t)sizeof(float);
 }
 
 extern "C" int ood_in_stats(const void *x, const void *y, float *workspace, float *stats, int batch, int64_t pixels,

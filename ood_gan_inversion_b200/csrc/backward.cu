@@ -11,7 +11,11 @@
 
 namespace ood {
 
-constexpr int kBwdChunk = 512;
+static inline int bwd_chunk_px(int64_t P, int batch) {
+    int c = 512;
+    while (c > 32 && (int64_t)batch * ((P + c - 1) / c) < 1024) c >>= 1;
+    return c;
+}
 
 template <int N>
 __device__ __forceinline__ void block_reduce_store(float (*acc)[N], int K, float *red, float *partial_row, int C, int cv,
@@ -37,7 +41,7 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const T *__restrict__ gy, 
                                                        const float *__restrict__ bias, const float *__restrict__ noise,
                                                        int64_t noise_bstride, const float *__restrict__ noise_w,
                                                        T *__restrict__ g, float *__restrict__ partial, int64_t P, int C,
-                                                       int nchunks) {
+                                                       int nchunks, int chunk_px) {
     constexpr int N = Vec<T>::N;
     extern __shared__ float red[];
     const int cv = C / N, lanes = 256 / cv;
@@ -54,7 +58,7 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const T *__restrict__ gy, 
         breg[j] = (active && bias) ? bias[c + j] : 0.f;
     }
     if (active) {
-        const int64_t p0 = (int64_t)chunk * kBwdChunk, p1 = min(p0 + kBwdChunk, P);
+        const int64_t p0 = (int64_t)chunk * chunk_px, p1 = min(p0 + chunk_px, P);
 #pragma unroll 2
         for (int64_t p = p0 + lane; p < p1; p += lanes) {
             const int64_t off = ((int64_t)b * P + p) * C + c;
@@ -78,7 +82,7 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const T *__restrict__ gy, 
 // ---- sum_pix a*b per (b,c)
 template <typename T>
 __global__ void __launch_bounds__(256) dot_partial_kernel(const T *__restrict__ a, const T *__restrict__ bb,
-                                                           float *__restrict__ partial, int64_t P, int C, int nchunks) {
+                                                           float *__restrict__ partial, int64_t P, int C, int nchunks, int chunk_px) {
     constexpr int N = Vec<T>::N;
     extern __shared__ float red[];
     const int cv = C / N, lanes = 256 / cv;
@@ -89,7 +93,7 @@ __global__ void __launch_bounds__(256) dot_partial_kernel(const T *__restrict__ 
 #pragma unroll
     for (int j = 0; j < N; ++j) acc[0][j] = 0.f;
     if (active) {
-        const int64_t p0 = (int64_t)chunk * kBwdChunk, p1 = min(p0 + kBwdChunk, P);
+        const int64_t p0 = (int64_t)chunk * chunk_px, p1 = min(p0 + chunk_px, P);
 #pragma unroll 4
         for (int64_t p = p0 + lane; p < p1; p += lanes) {
             const int64_t off = ((int64_t)b * P + p) * C + c;
@@ -117,7 +121,7 @@ __global__ void reduce_partials_kernel(const float *__restrict__ partial, const 
 // ---- ToRGB backward w.r.t. the activation: gy[b,p,c] = (g_in ? g_in : 0) + sum_k g_rgb[b,k,p] * wrgb[b,k,c]
 template <typename T>
 __global__ void __launch_bounds__(256) torgb_bwd_y_kernel(const float *__restrict__ g_rgb, const float *__restrict__ wrgb,
-                                                           const T *__restrict__ g_in, T *__restrict__ out, int64_t P, int C) {
+                                                           const T *__restrict__ g_in, T *__restrict__ out, int64_t P, int C, int chunk_px) {
     constexpr int N = Vec<T>::N;
     const int cv = C / N, lanes = 256 / cv;
     const int vec = threadIdx.x % cv, lane = threadIdx.x / cv;
@@ -128,7 +132,7 @@ __global__ void __launch_bounds__(256) torgb_bwd_y_kernel(const float *__restric
     for (int k = 0; k < 3; ++k)
 #pragma unroll
         for (int j = 0; j < N; ++j) w[k][j] = wrgb[((int64_t)b * 3 + k) * C + c + j];
-    const int64_t p0 = (int64_t)blockIdx.x * kBwdChunk, p1 = min(p0 + kBwdChunk, P);
+    const int64_t p0 = (int64_t)blockIdx.x * chunk_px, p1 = min(p0 + chunk_px, P);
 #pragma unroll 2
     for (int64_t p = p0 + lane; p < p1; p += lanes) {
         const float g0 = __ldg(g_rgb + ((int64_t)b * 3 + 0) * P + p), g1 = __ldg(g_rgb + ((int64_t)b * 3 + 1) * P + p),
@@ -149,7 +153,7 @@ __global__ void __launch_bounds__(256) torgb_bwd_y_kernel(const float *__restric
 // ---- ToRGB backward w.r.t. the per-sample RGB weights: partial[b][chunk][c*3+k] = sum_pix g_rgb[b,k,p] * y[b,p,c]
 template <typename T>
 __global__ void __launch_bounds__(256) torgb_wgrad_kernel(const float *__restrict__ g_rgb, const T *__restrict__ y,
-                                                           float *__restrict__ partial, int64_t P, int C, int nchunks) {
+                                                           float *__restrict__ partial, int64_t P, int C, int nchunks, int chunk_px) {
     constexpr int N = Vec<T>::N;
     extern __shared__ float red[];
     const int cv = C / N, lanes = 256 / cv;
@@ -162,7 +166,7 @@ __global__ void __launch_bounds__(256) torgb_wgrad_kernel(const float *__restric
 #pragma unroll
         for (int j = 0; j < N; ++j) acc[k][j] = 0.f;
     if (active) {
-        const int64_t p0 = (int64_t)chunk * kBwdChunk, p1 = min(p0 + kBwdChunk, P);
+        const int64_t p0 = (int64_t)chunk * chunk_px, p1 = min(p0 + chunk_px, P);
 #pragma unroll 2
         for (int64_t p = p0 + lane; p < p1; p += lanes) {
             const float g0 = __ldg(g_rgb + ((int64_t)b * 3 + 0) * P + p), g1 = __ldg(g_rgb + ((int64_t)b * 3 + 1) * P + p),
@@ -179,7 +183,7 @@ __global__ void __launch_bounds__(256) torgb_wgrad_kernel(const float *__restric
     block_reduce_store<N>(acc, 3, red, partial + (((int64_t)b * nchunks + chunk) * C) * 3, C, cv, lanes, lane, vec, active);
 }
 
-static inline int bwd_chunks(int64_t P) { return ceil_div(P, kBwdChunk); }
+static inline int bwd_chunks(int64_t P, int batch) { return ceil_div(P, bwd_chunk_px(P, batch)); }
 
 template <typename T>
 static int check_vec(const char *what, int C) {
@@ -191,7 +195,7 @@ static int check_vec(const char *what, int C) {
 }  // namespace ood
 
 extern "C" int64_t ood_bwd_workspace(int batch, int64_t pixels, int channels, int k) {
-    return (int64_t)batch * ood::bwd_chunks(pixels) * channels * k * (int64_t)sizeof(float);
+    return (int64_t)batch * ood::bwd_chunks(pixels, batch) * channels * k * (int64_t)sizeof(float);
 }
 
 extern "C" int ood_act_bwd(const void *gy, const void *y, const float *d, const float *bias, const float *noise,
@@ -201,18 +205,18 @@ extern "C" int ood_act_bwd(const void *gy, const void *y, const float *d, const 
     OOD_REQUIRE(gy && y && g && workspace && gd && batch > 0 && batch <= 65535 && pixels > 0, "act_bwd: bad arguments");
     OOD_REQUIRE(dtype == OOD_F32 || dtype == OOD_BF16, "act_bwd: bad dtype");
     cudaStream_t s = (cudaStream_t)stream;
-    const int nch = bwd_chunks(pixels);
+    const int nch = bwd_chunks(pixels, batch), cpx = bwd_chunk_px(pixels, batch);
     dim3 grid(nch, batch);
     const int N = dtype == OOD_F32 ? 4 : 8;
     if (int rc = (dtype == OOD_F32 ? check_vec<float>("act_bwd", channels) : check_vec<__nv_bfloat16>("act_bwd", channels))) return rc;
     const size_t smem = (size_t)(256 / (channels / N)) * channels * sizeof(float);
     if (dtype == OOD_F32)
         act_bwd_kernel<float><<<grid, 256, smem, s>>>((const float *)gy, (const float *)y, d, bias, noise, noise_bstride, noise_w,
-                                                       (float *)g, workspace, pixels, channels, nch);
+                                                       (float *)g, workspace, pixels, channels, nch, cpx);
     else
         act_bwd_kernel<__nv_bfloat16><<<grid, 256, smem, s>>>((const __nv_bfloat16 *)gy, (const __nv_bfloat16 *)y, d, bias, noise,
                                                                noise_bstride, noise_w, (__nv_bfloat16 *)g, workspace, pixels,
-                                                               channels, nch);
+                                                               channels, nch, cpx);
     const int64_t total = (int64_t)batch * channels;
     reduce_partials_kernel<<<ceil_div(total, 256), 256, 0, s>>>(workspace, d, gd, channels, 1, nch, total);
     return check_launch("act_bwd", 2);
@@ -224,13 +228,13 @@ extern "C" int ood_dot_reduce(const void *a, const void *b, float *workspace, fl
     OOD_REQUIRE(a && b && workspace && out && batch > 0 && batch <= 65535 && pixels > 0, "dot_reduce: bad arguments");
     OOD_REQUIRE(dtype == OOD_F32 || dtype == OOD_BF16, "dot_reduce: bad dtype");
     cudaStream_t s = (cudaStream_t)stream;
-    const int nch = bwd_chunks(pixels);
+    const int nch = bwd_chunks(pixels, batch), cpx = bwd_chunk_px(pixels, batch);
     dim3 grid(nch, batch);
     const int N = dtype == OOD_F32 ? 4 : 8;
     if (int rc = (dtype == OOD_F32 ? check_vec<float>("dot_reduce", channels) : check_vec<__nv_bfloat16>("dot_reduce", channels))) return rc;
     const size_t smem = (size_t)(256 / (channels / N)) * channels * sizeof(float);
-    if (dtype == OOD_F32) dot_partial_kernel<float><<<grid, 256, smem, s>>>((const float *)a, (const float *)b, workspace, pixels, channels, nch);
-    else dot_partial_kernel<__nv_bfloat16><<<grid, 256, smem, s>>>((const __nv_bfloat16 *)a, (const __nv_bfloat16 *)b, workspace, pixels, channels, nch);
+    if (dtype == OOD_F32) dot_partial_kernel<float><<<grid, 256, smem, s>>>((const float *)a, (const float *)b, workspace, pixels, channels, nch, cpx);
+    else dot_partial_kernel<__nv_bfloat16><<<grid, 256, smem, s>>>((const __nv_bfloat16 *)a, (const __nv_bfloat16 *)b, workspace, pixels, channels, nch, cpx);
     const int64_t total = (int64_t)batch * channels;
     reduce_partials_kernel<<<ceil_div(total, 256), 256, 0, s>>>(workspace, nullptr, out, channels, 1, nch, total);
     return check_launch("dot_reduce", 2);
@@ -243,17 +247,17 @@ extern "C" int ood_torgb_bwd(const float *g_rgb, const float *wrgb, const void *
     OOD_REQUIRE(g_rgb && wrgb && y && g_out && workspace && g_wrgb && batch > 0 && batch <= 65535 && pixels > 0, "torgb_bwd: bad arguments");
     OOD_REQUIRE(dtype == OOD_F32 || dtype == OOD_BF16, "torgb_bwd: bad dtype");
     cudaStream_t s = (cudaStream_t)stream;
-    const int nch = bwd_chunks(pixels);
+    const int nch = bwd_chunks(pixels, batch), cpx = bwd_chunk_px(pixels, batch);
     dim3 grid(nch, batch);
     const int N = dtype == OOD_F32 ? 4 : 8;
     if (int rc = (dtype == OOD_F32 ? check_vec<float>("torgb_bwd", channels) : check_vec<__nv_bfloat16>("torgb_bwd", channels))) return rc;
     const size_t smem = (size_t)(256 / (channels / N)) * channels * 3 * sizeof(float);
     if (dtype == OOD_F32) {
-        torgb_bwd_y_kernel<float><<<grid, 256, 0, s>>>(g_rgb, wrgb, (const float *)g_in, (float *)g_out, pixels, channels);
-        torgb_wgrad_kernel<float><<<grid, 256, smem, s>>>(g_rgb, (const float *)y, workspace, pixels, channels, nch);
+        torgb_bwd_y_kernel<float><<<grid, 256, 0, s>>>(g_rgb, wrgb, (const float *)g_in, (float *)g_out, pixels, channels, cpx);
+        torgb_wgrad_kernel<float><<<grid, 256, smem, s>>>(g_rgb, (const float *)y, workspace, pixels, channels, nch, cpx);
     } else {
-        torgb_bwd_y_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(g_rgb, wrgb, (const __nv_bfloat16 *)g_in, (__nv_bfloat16 *)g_out, pixels, channels);
-        torgb_wgrad_kernel<__nv_bfloat16><<<grid, 256, smem, s>>>(g_rgb, (const __nv_bfloat16 *)y, workspace, pixels, channels, nch);
+        torgb_bwd_y_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(g_rgb, wrgb, (const __nv_bfloat16 *)g_in, (__nv_bfloat16 *)g_out, pixels, channels, cpx);
+        torgb_wgrad_kernel<__nv_bfloat16><<<grid, 256, smem, s>>>(g_rgb, (const __nv_bfloat16 *)y, workspace, pixels, channels, nch, cpx);
     }
     const int64_t total = (int64_t)batch * channels * 3;
     reduce_partials_kernel<<<ceil_div(total, 256), 256, 0, s>>>(workspace, nullptr, g_wrgb, channels, 3, nch, total);
