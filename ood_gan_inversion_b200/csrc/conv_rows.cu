@@ -1,0 +1,373 @@
+// Row-sliding variant of the tcgen05 3x3 convolution for the high-resolution, small-channel layers (Ci, Co in {32, 64},
+// width a multiple of 128: the 512 px and 1024 px StyleGAN2 layers, src/ops/StyleGAN/model.py:268-272).
+//
+// Why: in the generic kernel (conv_tc.cu) every tap re-reads its 128-pixel A tile through TMA, i.e. 9 x the activation
+// bytes cross L2->SM; with N = Co <= 64 that traffic, not the tensor pipe, bounds the layer (ncu: conv<32,32> at 1024 px
+// took 2.6 ms for 0.31 TFLOP).  Here a persistent CTA owns a strip of output rows of one 128-pixel column block:
+//   * the nine weight tiles [Co x Ci] are loaded ONCE per CTA and stay in shared memory;
+//   * each input row segment [130 px x Ci] is loaded ONCE into a ring of row buffers; the three vertical taps are three
+//     ring slots, the three horizontal taps are the SAME buffer addressed with the descriptor start shifted by one pixel
+//     row (the swizzle is a function of the absolute shared-memory address, verified by scripts/probe_umma_shift.py);
+//   * accumulators: 4 TMEM buffers of Co columns, so the epilogue of row y overlaps the MMAs of rows y+1..y+3.
+// Activation traffic drops from 9x to (1 + 2/32)x; the layer becomes HBM-bound as it should be.
+#include <cuda.h>
+
+#include "conv_common.cuh"
+
+namespace ood {
+namespace rows {
+
+constexpr int kThreads = 192;
+constexpr int kStripRows = 32;
+constexpr int kNAcc = 4;
+constexpr int kRowPx = 130;
+
+struct RowParams {
+    int batch, h, w, tiles_x, strips_y, total_strips;
+    ConvEpilogue ep;
+    int cout;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n.reg .pred p;\nRW_LOOP:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra RW_DONE;\nbra RW_LOOP;\nRW_DONE:\n}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t *r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+template <int ROWB>   // bytes per pixel row of the K-major tile (64 or 128) == swizzle span
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)((8 * ROWB) >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)(ROWB == 128 ? 2 : 4) << 61;
+    return d;
+}
+
+template <int CI, int CO>
+struct Cfg {
+    static constexpr int ROWB = CI * 2;
+    static constexpr int kRowBytes = kRowPx * ROWB;                           // bytes one TMA row load delivers
+    static constexpr int kRowStride = (kRowBytes + 1023) & ~1023;
+    static constexpr int kWTile = CO * ROWB;                                  // one tap's [Co x Ci] tile
+    static constexpr int kWStride = (kWTile + 1023) & ~1023;
+    static constexpr int kRing = CI == 64 ? 6 : 8;
+    static constexpr int kTmemCols = kNAcc * CO < 32 ? 32 : kNAcc * CO;
+    static constexpr int kSmem = 9 * kWStride + kRing * kRowStride + 1024 + 512;
+    static constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(CO >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+};
+
+struct Ring {
+    int slot;
+    uint32_t phase;
+    int n;
+    __device__ __forceinline__ void advance() { if (++slot == n) { slot = 0; phase ^= 1; } }
+    __device__ __forceinline__ Ring next() const { Ring r = *this; r.advance(); return r; }
+};
+
+template <int CI, int CO>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const RowParams p) {
+    using C = Cfg<CI, CO>;
+    extern __shared__ uint8_t rows_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(rows_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t *sW = smem;
+    uint8_t *sR = smem + 9 * C::kWStride;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sR + C::kRing * C::kRowStride);
+    uint64_t *full = bars, *empty = bars + C::kRing, *tfull = bars + 2 * C::kRing, *tempty = tfull + kNAcc, *wbar = tempty + kNAcc;
+    uint32_t *tmem_holder = reinterpret_cast<uint32_t *>(wbar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        for (int i = 0; i < C::kRing; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < kNAcc; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+        mbar_init(wbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_holder)), "r"(C::kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+
+    auto strip_coords = [&](int strip, int &b, int &ya, int &x0, int &nrows) {
+        const int tx = strip % p.tiles_x;
+        int r = strip / p.tiles_x;
+        const int sy = r % p.strips_y;
+        b = r / p.strips_y;
+        ya = sy * kStripRows;
+        x0 = tx * 128;
+        nrows = min(kStripRows, p.h - ya);
+    };
+
+    if (warp == 0) {
+        // ===================================================== TMA producer
+        if (lane == 0) {
+            mbar_expect_tx(wbar, 9 * C::kWTile);
+            for (int t = 0; t < 9; ++t) tma_load_3d(sW + t * C::kWStride, &tmB, wbar, 0, 0, t);
+            Ring ring{0, 0, C::kRing};
+            for (int strip = blockIdx.x; strip < p.total_strips; strip += gridDim.x) {
+                int b, ya, x0, nrows;
+                strip_coords(strip, b, ya, x0, nrows);
+                for (int i = 0; i < nrows + 2; ++i) {
+                    mbar_wait(&empty[ring.slot], ring.phase ^ 1);
+                    mbar_expect_tx(&full[ring.slot], C::kRowBytes);
+                    tma_load_4d(sR + ring.slot * C::kRowStride, &tmA, &full[ring.slot], 0, x0 - 1, ya - 1 + i, b);
+                    ring.advance();
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================================== MMA issuer
+        if (lane == 0) {
+            mbar_wait(wbar, 0);
+            tc_fence_after();
+            Ring base{0, 0, C::kRing};
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int strip = blockIdx.x; strip < p.total_strips; strip += gridDim.x) {
+                int b, ya, x0, nrows;
+                strip_coords(strip, b, ya, x0, nrows);
+                for (int j = 0; j < nrows; ++j) {
+                    const Ring r0 = base, r1 = r0.next(), r2 = r1.next();
+                    if (j == 0) { mbar_wait(&full[r0.slot], r0.phase); mbar_wait(&full[r1.slot], r1.phase); }
+                    mbar_wait(&full[r2.slot], r2.phase);
+                    mbar_wait(&tempty[acc], acc_phase ^ 1);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + acc * CO;
+                    const int slots[3] = {r0.slot, r1.slot, r2.slot};
+#pragma unroll
+                    for (int dy = 0; dy < 3; ++dy) {
+                        const uint32_t rowbase = smem_u32(sR + slots[dy] * C::kRowStride);
+#pragma unroll
+                        for (int dx = 0; dx < 3; ++dx) {
+                            const uint64_t da = make_desc<C::ROWB>(rowbase + dx * C::ROWB);
+                            const uint64_t db = make_desc<C::ROWB>(smem_u32(sW + (dy * 3 + dx) * C::kWStride));
+#pragma unroll
+                            for (int k = 0; k < CI / 16; ++k)
+                                umma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), C::kIdesc, (dy | dx | k) != 0);
+                        }
+                    }
+                    umma_commit(&empty[r0.slot]);                 // input row (y-1) has no later consumer
+                    if (j == nrows - 1) { umma_commit(&empty[r1.slot]); umma_commit(&empty[r2.slot]); }
+                    umma_commit(&tfull[acc]);
+                    if (++acc == kNAcc) { acc = 0; acc_phase ^= 1; }
+                    base.advance();
+                }
+                base.advance();
+                base.advance();
+            }
+        }
+    } else {
+        // ===================================================== epilogue warps (TMEM lane quadrant = warp % 4)
+        const int quad = warp & 3;
+        const int m = quad * 32 + lane;
+        const float nw = (p.ep.noise && p.ep.noise_w) ? *p.ep.noise_w : 0.f;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int strip = blockIdx.x; strip < p.total_strips; strip += gridDim.x) {
+            int b, ya, x0, nrows;
+            strip_coords(strip, b, ya, x0, nrows);
+            const int X = x0 + m;
+            for (int j = 0; j < nrows; ++j) {
+                const int Y = ya + j;
+                const int64_t pix = ((int64_t)b * p.h + Y) * p.w + X;
+                float nz = 0.f;
+                if (p.ep.noise) nz = nw * __ldg(p.ep.noise + b * p.ep.noise_bstride + (int64_t)Y * p.w + X);
+                mbar_wait(&tfull[acc], acc_phase);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * CO;
+#pragma unroll
+                for (int ch = 0; ch < CO / 32; ++ch) {
+                    uint32_t r[32];
+                    tmem_ld32(taddr + ch * 32, r);
+                    tmem_ld_wait();
+                    const int n = ch * 32;
+                    float v[32];
+#pragma unroll
+                    for (int q = 0; q < 32; ++q) v[q] = __uint_as_float(r[q]);
+                    if (p.ep.d) {
+                        const float4 *dp = reinterpret_cast<const float4 *>(p.ep.d + (int64_t)b * CO + n);
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const float4 t = __ldg(dp + q);
+                            v[4 * q] *= t.x; v[4 * q + 1] *= t.y; v[4 * q + 2] *= t.z; v[4 * q + 3] *= t.w;
+                        }
+                    }
+                    if (p.ep.bias) {
+                        const float4 *bp = reinterpret_cast<const float4 *>(p.ep.bias + n);
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const float4 t = __ldg(bp + q);
+                            v[4 * q] += t.x; v[4 * q + 1] += t.y; v[4 * q + 2] += t.z; v[4 * q + 3] += t.w;
+                        }
+                    }
+                    if (p.ep.act == 1) {
+#pragma unroll
+                        for (int q = 0; q < 32; ++q) v[q] = lrelu_sqrt2(v[q] + nz);
+                    } else if (p.ep.noise) {
+#pragma unroll
+                        for (int q = 0; q < 32; ++q) v[q] += nz;
+                    }
+                    if (p.ep.out_y) {
+                        uint4 *o = reinterpret_cast<uint4 *>((__nv_bfloat16 *)p.ep.out_y + pix * CO + n);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            o[q] = make_uint4(pack_bf16x2(v[8 * q], v[8 * q + 1]), pack_bf16x2(v[8 * q + 2], v[8 * q + 3]),
+                                              pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), pack_bf16x2(v[8 * q + 6], v[8 * q + 7]));
+                    }
+                    if (p.ep.out_ys) {
+                        const float4 *sp = reinterpret_cast<const float4 *>(p.ep.s_next + (int64_t)b * CO + n);
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const float4 t = __ldg(sp + q);
+                            v[4 * q] *= t.x; v[4 * q + 1] *= t.y; v[4 * q + 2] *= t.z; v[4 * q + 3] *= t.w;
+                        }
+                        uint4 *o = reinterpret_cast<uint4 *>((__nv_bfloat16 *)p.ep.out_ys + pix * CO + n);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            o[q] = make_uint4(pack_bf16x2(v[8 * q], v[8 * q + 1]), pack_bf16x2(v[8 * q + 2], v[8 * q + 3]),
+                                              pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), pack_bf16x2(v[8 * q + 6], v[8 * q + 7]));
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[acc]);
+                if (++acc == kNAcc) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::kTmemCols) : "memory");
+    }
+}
+
+typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                             const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+template <int CI, int CO>
+static int launch(const CUtensorMap &tmA, const CUtensorMap &tmB, const RowParams &p, cudaStream_t st) {
+    using C = Cfg<CI, CO>;
+    auto kern = conv_rows_kernel<CI, CO>;
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem);
+        if (e != cudaSuccess) { set_error("conv3x3 rows: smem attribute: %s", cudaGetErrorString(e)); return OOD_ERR_CUDA; }
+        attr = true;
+    }
+    int dev = 0, sms = kNumSMs;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    kern<<<std::min(p.total_strips, sms), kThreads, C::kSmem, st>>>(tmA, tmB, p);
+    return check_launch("conv3x3 rows");
+}
+
+}  // namespace rows
+
+// Returns OOD_OK with *handled = 0 when the configuration is outside this kernel's envelope.
+int conv3x3_rows(const ood_conv3x3_args &a, cudaStream_t st, int *handled) {
+    using namespace rows;
+    *handled = 0;
+    if (a.transposed || a.dtype != OOD_BF16 || a.out_f32 || a.act == 2) return OOD_OK;
+    if (!((a.cin == 32 || a.cin == 64) && (a.cout == 32 || a.cout == 64) && a.cin >= a.cout)) return OOD_OK;
+    if (a.w % 128 != 0 || a.h < 3) return OOD_OK;
+    static EncodeFn encode = nullptr;
+    if (!encode) {
+        void *ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) != cudaSuccess || !ptr) return OOD_OK;
+        encode = (EncodeFn)ptr;
+    }
+    const CUtensorMapSwizzle sw = a.cin == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+    CUtensorMap tmA, tmB;
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)a.cin, (cuuint64_t)a.w, (cuuint64_t)a.h, (cuuint64_t)a.batch};
+        cuuint64_t strides[3] = {(cuuint64_t)a.cin * 2, (cuuint64_t)a.w * a.cin * 2, (cuuint64_t)a.h * a.w * a.cin * 2};
+        cuuint32_t box[4] = {(cuuint32_t)a.cin, (cuuint32_t)kRowPx, 1, 1};
+        cuuint32_t es[4] = {1, 1, 1, 1};
+        if (encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(a.in), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return OOD_OK;
+    }
+    {
+        cuuint64_t dims[3] = {(cuuint64_t)a.cin, (cuuint64_t)a.cout, 9};
+        cuuint64_t strides[2] = {(cuuint64_t)a.cin * 2, (cuuint64_t)a.cout * a.cin * 2};
+        cuuint32_t box[3] = {(cuuint32_t)a.cin, (cuuint32_t)a.cout, 1};
+        cuuint32_t es[3] = {1, 1, 1};
+        if (encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void *>(a.weight), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return OOD_OK;
+    }
+    RowParams p{};
+    p.batch = a.batch; p.h = a.h; p.w = a.w; p.cout = a.cout;
+    p.tiles_x = a.w / 128;
+    p.strips_y = ceil_div(a.h, kStripRows);
+    const int64_t total = (int64_t)p.tiles_x * p.strips_y * a.batch;
+    if (total >= (1LL << 31)) return OOD_OK;
+    p.total_strips = (int)total;
+    p.ep = ConvEpilogue{a.out_y, a.out_ys, a.d, a.noise, a.noise_w, a.bias, a.s_next, a.noise_bstride, a.act, 0, nullptr};
+    *handled = 1;
+    if (a.cin == 64 && a.cout == 64) return launch<64, 64>(tmA, tmB, p, st);
+    if (a.cin == 64 && a.cout == 32) return launch<64, 32>(tmA, tmB, p, st);
+    return launch<32, 32>(tmA, tmB, p, st);
+}
+
+}  // namespace ood

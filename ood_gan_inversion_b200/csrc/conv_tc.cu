@@ -437,7 +437,10 @@ int conv3x3_tc(const ood_conv3x3_args &a, cudaStream_t st) {
 
 }  // namespace ood
 
-namespace ood { int conv3x3_simt(const ood_conv3x3_args &a, cudaStream_t st); }
+namespace ood {
+int conv3x3_simt(const ood_conv3x3_args &a, cudaStream_t st);
+int conv3x3_rows(const ood_conv3x3_args &a, cudaStream_t st, int *handled);
+}
 
 extern "C" int ood_conv3x3(const ood_conv3x3_args *a, void *stream) {
     using namespace ood;
@@ -456,5 +459,10 @@ extern "C" int ood_conv3x3(const ood_conv3x3_args *a, void *stream) {
     if (a->impl == 1) return conv3x3_simt(*a, st);
     OOD_REQUIRE(a->impl == 0, "conv3x3: impl must be 0 (tcgen05) or 1 (simt)");
     if (!ood_device_is_sm100()) { set_error("conv3x3: the tcgen05 path needs an sm_100 device"); return OOD_ERR_DEVICE; }
+    {   // high-resolution small-channel layers: row-sliding kernel (conv_rows.cu); anything else: the generic tiles below
+        int handled = 0;
+        const int rc = conv3x3_rows(*a, st, &handled);
+        if (handled) return rc;
+    }
     return conv3x3_tc(*a, st);
 }

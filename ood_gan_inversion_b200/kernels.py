@@ -325,9 +325,10 @@ def act_bwd(gy, y, d, bias, noise, noise_w):
     g = torch.empty_like(y)
     gd = torch.empty(b, c, device=y.device, dtype=torch.float32)
     nbs = 0 if (noise is None or noise.shape[0] == 1) else h * w
+    ws = _bwd_ws(b, h * w, c, 1, y.device)          # kept alive until the launch has been queued
     with _timed('act_bwd', b * h * w * c * _esize(y) * 3):
         check(_lib.lib().ood_act_bwd(_ptr(gy), _ptr(y), _ptr(d), _ptr(bias), _ptr(noise), nbs, _ptr(noise_w), _ptr(g),
-                                     _ptr(_bwd_ws(b, h * w, c, 1, y.device)), _ptr(gd), b, h * w, c, _dt(y), _stream()), 'act_bwd')
+                                     _ptr(ws), _ptr(gd), b, h * w, c, _dt(y), _stream()), 'act_bwd')
     return g, gd
 
 
@@ -337,9 +338,9 @@ def dot_reduce(a, x):
     assert a.is_contiguous() and x.is_contiguous() and a.dtype == x.dtype and a.shape == x.shape
     b, h, w, c = a.shape
     out = torch.empty(b, c, device=a.device, dtype=torch.float32)
+    ws = _bwd_ws(b, h * w, c, 1, a.device)
     with _timed('dot_reduce', b * h * w * c * _esize(a) * 2):
-        check(_lib.lib().ood_dot_reduce(_ptr(a), _ptr(x), _ptr(_bwd_ws(b, h * w, c, 1, a.device)), _ptr(out), b, h * w, c, _dt(a),
-                                        _stream()), 'dot_reduce')
+        check(_lib.lib().ood_dot_reduce(_ptr(a), _ptr(x), _ptr(ws), _ptr(out), b, h * w, c, _dt(a), _stream()), 'dot_reduce')
     return out
 
 
@@ -351,9 +352,10 @@ def torgb_bwd(g_rgb, wrgb, y, g_in=None):
     b, h, w, c = y.shape
     g_out = torch.empty_like(y)
     gw = torch.empty(b, c, 3, device=y.device, dtype=torch.float32)
+    ws = _bwd_ws(b, h * w, c, 3, y.device)
     with _timed('torgb_bwd', b * h * w * (c * _esize(y) * 3 + 12)):
-        check(_lib.lib().ood_torgb_bwd(_ptr(g_rgb), _ptr(wrgb), _ptr(y), _ptr(g_in), _ptr(g_out), _ptr(_bwd_ws(b, h * w, c, 3, y.device)),
-                                       _ptr(gw), b, h * w, c, _dt(y), _stream()), 'torgb_bwd')
+        check(_lib.lib().ood_torgb_bwd(_ptr(g_rgb), _ptr(wrgb), _ptr(y), _ptr(g_in), _ptr(g_out), _ptr(ws), _ptr(gw), b, h * w, c,
+                                       _dt(y), _stream()), 'torgb_bwd')
     return g_out, gw.permute(0, 2, 1).contiguous()
 
 

@@ -415,3 +415,22 @@ def test_spm_warp_fused_route_vs_reference_golden(golden, precision):
     a2, f2 = blk(G['enc2'].to(DEV), None, image=G['gen2'].to(DEV), aligned=f1)
     torch.testing.assert_close(f2.cpu(), G['field2'], **tol)
     sgm.set_precision('bf16')
+
+
+@pytest.mark.parametrize('case', [dict(b=2, h=40, w=128, ci=64, co=64), dict(b=1, h=33, w=256, ci=32, co=32),
+                                  dict(b=3, h=5, w=384, ci=64, co=32), dict(b=1, h=70, w=128, ci=32, co=32)])
+def test_conv3x3_row_sliding_kernel(case):
+    """Row-sliding tcgen05 kernel (W % 128 == 0, Ci, Co in {32, 64}): strips of 32 rows, remainders, several column blocks."""
+    b, h, w_, ci, co = case['b'], case['h'], case['w'], case['ci'], case['co']
+    x, w = rnd(b, ci, h, w_, seed=1).bfloat16().float(), rnd(co, ci, 3, 3, seed=2).bfloat16().float()
+    d, bias, s_next = 0.05 * (1 + rnd(b, co, seed=3).abs()), rnd(co, seed=4), 1 + 0.3 * rnd(b, co, seed=5)
+    noise, nw = rnd(b, 1, h, w_, seed=6), torch.tensor([0.37])
+    wp = K().pack_conv_weight(w.to(DEV), torch.bfloat16, False)
+    raw, _ = K().conv3x3(nhwc(x, torch.bfloat16), wp, co, impl=0)
+    ref_raw = F.conv2d(x.double(), w.double(), padding=1).float()
+    torch.testing.assert_close(nchw(raw), ref_raw, rtol=1e-2, atol=0.15)
+    y, ys = K().conv3x3(nhwc(x, torch.bfloat16), wp, co, impl=0, d=d.to(DEV), noise=noise.to(DEV), noise_w=nw.to(DEV),
+                        bias=bias.to(DEV), s_next=s_next.to(DEV), act=True, want_y=True, want_ys=True)
+    ref = oops.fused_leaky_relu(ref_raw * d[:, :, None, None] + nw * noise, bias)
+    torch.testing.assert_close(nchw(y), ref, rtol=2e-2, atol=3e-2)
+    torch.testing.assert_close(nchw(ys), ref * s_next[:, :, None, None], rtol=2e-2, atol=3e-2)
