@@ -17,7 +17,7 @@
 namespace ood {
 namespace rows {
 
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;          // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two groups: low / high half of the channels)
 constexpr int kStripRows = 32;
 constexpr int kNAcc = 4;
 constexpr int kRowPx = 130;
@@ -64,6 +64,17 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
         "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// same instruction, descriptors passed as (lo, hi) halves: only `lo` (the start address) changes between taps / k-steps,
+// so the single issuing thread spends one 32-bit add per MMA instead of rebuilding 64-bit descriptors (measured: ~100
+// cycles per tcgen05.mma with the naive form, which made the N = 32 / 64 layers issue-bound).
+__device__ __forceinline__ void umma_bf16_split(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                                uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n.reg .b64 da, db;\n.reg .pred p;\nmov.b64 da, {%1, %2};\nmov.b64 db, {%3, %4};\nsetp.ne.b32 p, %6, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n}\n" ::"r"(tmem_d),
+        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -76,6 +87,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t *r) {
           "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
           "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
           "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t *r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr)
         : "memory");
 }
@@ -99,9 +119,10 @@ struct Cfg {
     static constexpr int kRowStride = (kRowBytes + 1023) & ~1023;
     static constexpr int kWTile = CO * ROWB;                                  // one tap's [Co x Ci] tile
     static constexpr int kWStride = (kWTile + 1023) & ~1023;
-    static constexpr int kRing = CI == 64 ? 6 : 8;
+    static constexpr int kRing = CI == 64 ? 5 : 8;
     static constexpr int kTmemCols = kNAcc * CO < 32 ? 32 : kNAcc * CO;
-    static constexpr int kSmem = 9 * kWStride + kRing * kRowStride + 1024 + 512;
+    static constexpr int kOutTile = 128 * CO * 2;                             // one staged output row tile (bf16)
+    static constexpr int kSmem = 9 * kWStride + kRing * kRowStride + 4 * kOutTile + 1024 + 512;   // staging: 2 buffers x (y, ys)
     static constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(CO >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 };
 
@@ -115,20 +136,22 @@ struct Ring {
 
 template <int CI, int CO>
 __global__ void __launch_bounds__(kThreads, 1)
-conv_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const RowParams p) {
+conv_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmYS, const RowParams p) {
     using C = Cfg<CI, CO>;
     extern __shared__ uint8_t rows_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(rows_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t *sW = smem;
     uint8_t *sR = smem + 9 * C::kWStride;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sR + C::kRing * C::kRowStride);
+    uint8_t *sO = sR + C::kRing * C::kRowStride;                  // staging: [2][128 px][CO] bf16, TMA-store swizzle
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sO + 4 * C::kOutTile);
     uint64_t *full = bars, *empty = bars + C::kRing, *tfull = bars + 2 * C::kRing, *tempty = tfull + kNAcc, *wbar = tempty + kNAcc;
     uint32_t *tmem_holder = reinterpret_cast<uint32_t *>(wbar + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == 0 && lane == 0) {
         for (int i = 0; i < C::kRing; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-        for (int i = 0; i < kNAcc; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+        for (int i = 0; i < kNAcc; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
         mbar_init(wbar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -178,6 +201,11 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             Ring base{0, 0, C::kRing};
             int acc = 0;
             uint32_t acc_phase = 0;
+            // descriptor halves: hi = {SBO, version, swizzle} is common to A and B (same row pitch); lo = start address >> 4
+            const uint64_t dproto = make_desc<C::ROWB>(0);
+            const uint32_t desc_hi = (uint32_t)(dproto >> 32);
+            const uint32_t ring_lo = (uint32_t)dproto | ((smem_u32(sR) >> 4) & 0x3FFF);
+            const uint32_t w_lo = (uint32_t)dproto | ((smem_u32(sW) >> 4) & 0x3FFF);
             for (int strip = blockIdx.x; strip < p.total_strips; strip += gridDim.x) {
                 int b, ya, x0, nrows;
                 strip_coords(strip, b, ya, x0, nrows);
@@ -188,19 +216,17 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     mbar_wait(&tempty[acc], acc_phase ^ 1);
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + acc * CO;
-                    const int slots[3] = {r0.slot, r1.slot, r2.slot};
+                    const uint32_t a_lo[3] = {ring_lo + (uint32_t)r0.slot * (C::kRowStride >> 4), ring_lo + (uint32_t)r1.slot * (C::kRowStride >> 4),
+                                              ring_lo + (uint32_t)r2.slot * (C::kRowStride >> 4)};
 #pragma unroll
-                    for (int dy = 0; dy < 3; ++dy) {
-                        const uint32_t rowbase = smem_u32(sR + slots[dy] * C::kRowStride);
+                    for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
-                        for (int dx = 0; dx < 3; ++dx) {
-                            const uint64_t da = make_desc<C::ROWB>(rowbase + dx * C::ROWB);
-                            const uint64_t db = make_desc<C::ROWB>(smem_u32(sW + (dy * 3 + dx) * C::kWStride));
+                        for (int dx = 0; dx < 3; ++dx)
 #pragma unroll
                             for (int k = 0; k < CI / 16; ++k)
-                                umma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), C::kIdesc, (dy | dx | k) != 0);
-                        }
-                    }
+                                umma_bf16_split(d_tmem, a_lo[dy] + (uint32_t)((dx * C::ROWB + k * 32) >> 4), desc_hi,
+                                                w_lo + (uint32_t)(((dy * 3 + dx) * C::kWStride + k * 32) >> 4), desc_hi, C::kIdesc,
+                                                (dy | dx | k) != 0 ? 1u : 0u);
                     umma_commit(&empty[r0.slot]);                 // input row (y-1) has no later consumer
                     if (j == nrows - 1) { umma_commit(&empty[r1.slot]); umma_commit(&empty[r2.slot]); }
                     umma_commit(&tfull[acc]);
@@ -212,85 +238,105 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
         }
     } else {
-        // ===================================================== epilogue warps (TMEM lane quadrant = warp % 4)
+        // ===================================================== epilogue: 8 warps.  TMEM lane quadrant = warp % 4; group g = low / high
+        // half of the output channels, so a thread owns ONE pixel x CH channels and the per-(b, channel) coefficients of
+        // a whole strip live in registers (the single-group version was latency-bound: one warp per scheduler, 425
+        // dependent instructions per row tile).
+        constexpr int CH = CO / 2;
         const int quad = warp & 3;
+        const int grp = (warp - 2) >> 2;
         const int m = quad * 32 + lane;
+        const int n0 = grp * CH;
+        const bool issuer = (m == 0 && grp == 0);
         const float nw = (p.ep.noise && p.ep.noise_w) ? *p.ep.noise_w : 0.f;
         int acc = 0;
         uint32_t acc_phase = 0;
+        int sbuf = 0;                                   // staging buffer of this tile (double buffered)
+        // swizzled staging row of this pixel (matches the SWIZZLE_128B / SWIZZLE_64B mode of the store maps)
+        const uint32_t row_off = (uint32_t)m * (CO * 2);
+        const uint32_t swz = CO == 64 ? (uint32_t)(m & 7) : (uint32_t)((m >> 1) & 3);
         for (int strip = blockIdx.x; strip < p.total_strips; strip += gridDim.x) {
             int b, ya, x0, nrows;
             strip_coords(strip, b, ya, x0, nrows);
             const int X = x0 + m;
+            float dreg[CH], breg[CH], sreg[CH];
+#pragma unroll
+            for (int q = 0; q < CH; ++q) {
+                dreg[q] = p.ep.d ? __ldg(p.ep.d + (int64_t)b * CO + n0 + q) : 1.f;
+                breg[q] = p.ep.bias ? __ldg(p.ep.bias + n0 + q) : 0.f;
+                sreg[q] = p.ep.out_ys ? __ldg(p.ep.s_next + (int64_t)b * CO + n0 + q) : 1.f;
+            }
+            // noise is streamed from HBM (4 B per pixel): prefetch it two row tiles ahead, or its ~1 us latency lands on the
+            // critical path of every tile (ncu: 28 % of all stall samples sat on the first use of this load)
+            const float *nzp = p.ep.noise ? p.ep.noise + b * p.ep.noise_bstride + (int64_t)ya * p.w + X : nullptr;
+            float nz0 = (nzp && 0 < nrows) ? __ldg(nzp) : 0.f;
+            float nz1 = (nzp && 1 < nrows) ? __ldg(nzp + p.w) : 0.f;
             for (int j = 0; j < nrows; ++j) {
                 const int Y = ya + j;
                 const int64_t pix = ((int64_t)b * p.h + Y) * p.w + X;
-                float nz = 0.f;
-                if (p.ep.noise) nz = nw * __ldg(p.ep.noise + b * p.ep.noise_bstride + (int64_t)Y * p.w + X);
+                const float nz_raw = nz0;
+                nz0 = nz1;
+                nz1 = (nzp && j + 2 < nrows) ? __ldg(nzp + (int64_t)(j + 2) * p.w) : 0.f;
+                // the stores issued two tiles ago (same staging buffer) must have finished READING it
+                if (issuer) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                uint8_t *sY = sO + sbuf * 2 * C::kOutTile, *sYS = sY + C::kOutTile;
+                asm volatile("bar.sync 1, 256;" ::: "memory");
                 mbar_wait(&tfull[acc], acc_phase);
                 tc_fence_after();
-                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * CO;
-#pragma unroll
-                for (int ch = 0; ch < CO / 32; ++ch) {
-                    uint32_t r[32];
-                    tmem_ld32(taddr + ch * 32, r);
-                    tmem_ld_wait();
-                    const int n = ch * 32;
-                    float v[32];
-#pragma unroll
-                    for (int q = 0; q < 32; ++q) v[q] = __uint_as_float(r[q]);
-                    if (p.ep.d) {
-                        const float4 *dp = reinterpret_cast<const float4 *>(p.ep.d + (int64_t)b * CO + n);
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            const float4 t = __ldg(dp + q);
-                            v[4 * q] *= t.x; v[4 * q + 1] *= t.y; v[4 * q + 2] *= t.z; v[4 * q + 3] *= t.w;
-                        }
-                    }
-                    if (p.ep.bias) {
-                        const float4 *bp = reinterpret_cast<const float4 *>(p.ep.bias + n);
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            const float4 t = __ldg(bp + q);
-                            v[4 * q] += t.x; v[4 * q + 1] += t.y; v[4 * q + 2] += t.z; v[4 * q + 3] += t.w;
-                        }
-                    }
-                    if (p.ep.act == 1) {
-#pragma unroll
-                        for (int q = 0; q < 32; ++q) v[q] = lrelu_sqrt2(v[q] + nz);
-                    } else if (p.ep.noise) {
-#pragma unroll
-                        for (int q = 0; q < 32; ++q) v[q] += nz;
-                    }
-                    if (p.ep.out_y) {
-                        uint4 *o = reinterpret_cast<uint4 *>((__nv_bfloat16 *)p.ep.out_y + pix * CO + n);
-#pragma unroll
-                        for (int q = 0; q < 4; ++q)
-                            o[q] = make_uint4(pack_bf16x2(v[8 * q], v[8 * q + 1]), pack_bf16x2(v[8 * q + 2], v[8 * q + 3]),
-                                              pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), pack_bf16x2(v[8 * q + 6], v[8 * q + 7]));
-                    }
-                    if (p.ep.out_ys) {
-                        const float4 *sp = reinterpret_cast<const float4 *>(p.ep.s_next + (int64_t)b * CO + n);
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            const float4 t = __ldg(sp + q);
-                            v[4 * q] *= t.x; v[4 * q + 1] *= t.y; v[4 * q + 2] *= t.z; v[4 * q + 3] *= t.w;
-                        }
-                        uint4 *o = reinterpret_cast<uint4 *>((__nv_bfloat16 *)p.ep.out_ys + pix * CO + n);
-#pragma unroll
-                        for (int q = 0; q < 4; ++q)
-                            o[q] = make_uint4(pack_bf16x2(v[8 * q], v[8 * q + 1]), pack_bf16x2(v[8 * q + 2], v[8 * q + 3]),
-                                              pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), pack_bf16x2(v[8 * q + 6], v[8 * q + 7]));
-                    }
-                }
+                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * CO + n0;
+                uint32_t r[CH];
+                if constexpr (CH == 32) tmem_ld32(taddr, r); else tmem_ld16(taddr, r);
+                tmem_ld_wait();
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&tempty[acc]);
+                if (lane == 0) mbar_arrive(&tempty[acc]);           // TMEM buffer free: the MMA warp may start row y+4
+                float v[CH];
+                const float nz = nw * nz_raw;
+#pragma unroll
+                for (int q = 0; q < CH; ++q) {
+                    v[q] = fmaf(__uint_as_float(r[q]), dreg[q], breg[q] + nz);
+
+                    if (p.ep.act == 1) v[q] = lrelu_sqrt2(v[q]);
+                }
+                if (p.ep.out_y) {
+#pragma unroll
+                    for (int q = 0; q < CH / 8; ++q) {
+                        const uint32_t chunk = ((uint32_t)(grp * (CH / 8) + q)) ^ swz;
+                        *reinterpret_cast<uint4 *>(sY + row_off + chunk * 16) =
+                            make_uint4(pack_bf16x2(v[8 * q], v[8 * q + 1]), pack_bf16x2(v[8 * q + 2], v[8 * q + 3]),
+                                       pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), pack_bf16x2(v[8 * q + 6], v[8 * q + 7]));
+                    }
+                }
+                if (p.ep.out_ys) {
+#pragma unroll
+                    for (int q = 0; q < CH; ++q) v[q] *= sreg[q];
+#pragma unroll
+                    for (int q = 0; q < CH / 8; ++q) {
+                        const uint32_t chunk = ((uint32_t)(grp * (CH / 8) + q)) ^ swz;
+                        *reinterpret_cast<uint4 *>(sYS + row_off + chunk * 16) =
+                            make_uint4(pack_bf16x2(v[8 * q], v[8 * q + 1]), pack_bf16x2(v[8 * q + 2], v[8 * q + 3]),
+                                       pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), pack_bf16x2(v[8 * q + 6], v[8 * q + 7]));
+                    }
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy STS -> visible to the TMA store
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (issuer) {                                        // 128 px x CO channels are CONTIGUOUS in NHWC: one bulk store each
+                    const int pix0 = (int)(pix - m);
+                    if (p.ep.out_y)
+                        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                                     ::"l"(&tmY), "r"(smem_u32(sY)), "r"(0), "r"(pix0) : "memory");
+                    if (p.ep.out_ys)
+                        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                                     ::"l"(&tmYS), "r"(smem_u32(sYS)), "r"(0), "r"(pix0) : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+                sbuf ^= 1;
                 if (++acc == kNAcc) { acc = 0; acc_phase ^= 1; }
             }
         }
     }
 
+    if (warp == 4 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // the thread (group 0, m == 0) that issued the stores
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
@@ -304,7 +350,8 @@ typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, voi
                              CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 template <int CI, int CO>
-static int launch(const CUtensorMap &tmA, const CUtensorMap &tmB, const RowParams &p, cudaStream_t st) {
+static int launch(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmY, const CUtensorMap &tmYS, const RowParams &p,
+                  cudaStream_t st) {
     using C = Cfg<CI, CO>;
     auto kern = conv_rows_kernel<CI, CO>;
     static bool attr = false;
@@ -316,7 +363,7 @@ static int launch(const CUtensorMap &tmA, const CUtensorMap &tmB, const RowParam
     int dev = 0, sms = kNumSMs;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    kern<<<std::min(p.total_strips, sms), kThreads, C::kSmem, st>>>(tmA, tmB, p);
+    kern<<<std::min(p.total_strips, sms), kThreads, C::kSmem, st>>>(tmA, tmB, tmY, tmYS, p);
     return check_launch("conv3x3 rows");
 }
 
@@ -328,7 +375,7 @@ int conv3x3_rows(const ood_conv3x3_args &a, cudaStream_t st, int *handled) {
     *handled = 0;
     if (a.transposed || a.dtype != OOD_BF16 || a.out_f32 || a.act == 2) return OOD_OK;
     if (!((a.cin == 32 || a.cin == 64) && (a.cout == 32 || a.cout == 64) && a.cin >= a.cout)) return OOD_OK;
-    if (a.w % 128 != 0 || a.h < 3) return OOD_OK;
+    if (a.w % 128 != 0 || a.h < 3 || (int64_t)a.batch * a.h * a.w >= (1LL << 31)) return OOD_OK;
     static EncodeFn encode = nullptr;
     if (!encode) {
         void *ptr = nullptr;
@@ -356,6 +403,20 @@ int conv3x3_rows(const ood_conv3x3_args &a, cudaStream_t st, int *handled) {
                    CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
             return OOD_OK;
     }
+    // output maps: the NHWC tensor as [total pixels][Co]; box = one 128-pixel row tile; swizzle = the staging layout
+    CUtensorMap tmY, tmYS;
+    {
+        const CUtensorMapSwizzle swo = a.cout == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+        cuuint64_t dims[2] = {(cuuint64_t)a.cout, (cuuint64_t)a.batch * a.h * a.w};
+        cuuint64_t strides[1] = {(cuuint64_t)a.cout * 2};
+        cuuint32_t box[2] = {(cuuint32_t)a.cout, 128};
+        cuuint32_t es[2] = {1, 1};
+        void *py = a.out_y ? a.out_y : a.out_ys, *pys = a.out_ys ? a.out_ys : a.out_y;
+        if (encode(&tmY, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, py, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swo,
+                   CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return OOD_OK;
+        if (encode(&tmYS, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, pys, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swo,
+                   CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return OOD_OK;
+    }
     RowParams p{};
     p.batch = a.batch; p.h = a.h; p.w = a.w; p.cout = a.cout;
     p.tiles_x = a.w / 128;
@@ -365,9 +426,9 @@ int conv3x3_rows(const ood_conv3x3_args &a, cudaStream_t st, int *handled) {
     p.total_strips = (int)total;
     p.ep = ConvEpilogue{a.out_y, a.out_ys, a.d, a.noise, a.noise_w, a.bias, a.s_next, a.noise_bstride, a.act, 0, nullptr};
     *handled = 1;
-    if (a.cin == 64 && a.cout == 64) return launch<64, 64>(tmA, tmB, p, st);
-    if (a.cin == 64 && a.cout == 32) return launch<64, 32>(tmA, tmB, p, st);
-    return launch<32, 32>(tmA, tmB, p, st);
+    if (a.cin == 64 && a.cout == 64) return launch<64, 64>(tmA, tmB, tmY, tmYS, p, st);
+    if (a.cin == 64 && a.cout == 32) return launch<64, 32>(tmA, tmB, tmY, tmYS, p, st);
+    return launch<32, 32>(tmA, tmB, tmY, tmYS, p, st);
 }
 
 }  // namespace ood
