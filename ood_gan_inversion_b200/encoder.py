@@ -108,7 +108,7 @@ class GradualStyleBlock(nn.Module):
     def forward(self, x):
         x = self.convs(x).reshape(-1, self.out_c)
         with torch.autocast('cuda', enabled=False):        # the W+ latents are always produced in fp32
-            return F.linear(x.float(), self.linear.weight * self.linear.scale, self.linear.bias * self.linear.lr_mul)
+            return F.linear(x.float(), self.linear.weight.float() * self.linear.scale, self.linear.bias.float() * self.linear.lr_mul)
 
 
 def _upsample_add(x, y):

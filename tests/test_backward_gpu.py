@@ -16,7 +16,8 @@ DEV = 'cuda'
 def _setup():
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
-    yield
+    with torch.enable_grad():
+        yield
 
 
 def K():

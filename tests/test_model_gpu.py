@@ -215,3 +215,25 @@ def test_generic_callback_protocol():
     assert seen == [(0, (2, 512, 32, 32))]
     assert (img - ref).abs().max() < 1e-3
     m.set_precision('bf16')
+
+
+def test_encoder_inference_copy_matches_module():
+    """BN-folded inference copy of the E4E encoder (fp32 arithmetic here) == the module tree it was built from."""
+    from ood_gan_inversion_b200 import encoder_infer
+    from ood_gan_inversion_b200.encoder import Encoder4Editing
+    torch.manual_seed(0)
+    enc = Encoder4Editing(50, 'ir_se', {'stylegan_size': 1024}).to(DEV).eval()
+    for m in enc.modules():                                   # non-trivial running statistics
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.normal_(0, 0.1)
+            m.running_var.uniform_(0.8, 1.2)
+            m.weight.data.normal_(1, 0.1)
+            m.bias.data.normal_(0, 0.1)
+    folded = encoder_infer.build(enc, dtype=torch.float32)
+    assert sum(isinstance(m, torch.nn.BatchNorm2d) for m in folded.modules()) < sum(isinstance(m, torch.nn.BatchNorm2d) for m in enc.modules())
+    x = torch.randn(2, 3, 256, 256, device=DEV)
+    w0, f0 = enc(x, return_feats=True)
+    w1, f1 = folded(x.contiguous(memory_format=torch.channels_last), return_feats=True)
+    torch.testing.assert_close(w1, w0, rtol=1e-3, atol=1e-3)
+    for a, b in zip(f0, f1):
+        torch.testing.assert_close(b, a, rtol=1e-3, atol=1e-3)

@@ -8,7 +8,13 @@ import torch.nn.functional as F
 
 from oracle import ops, stylegan, samm, ood
 
-torch.set_grad_enabled(False)
+
+
+@pytest.fixture(autouse=True)
+def _no_grad():
+    # function-scoped: a module-level torch.set_grad_enabled(False) would leak into every other test module at collection
+    with torch.no_grad():
+        yield
 
 
 def test_upfirdn2d_golden(golden):
