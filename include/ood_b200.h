@@ -117,6 +117,11 @@ typedef struct {
     int dtype;             /* storage type of in / out */
     int out_f32;           /* 1: out_y is fp32 regardless of dtype (raw accumulators of the transposed conv) */
     const float *prelu_slope; /* [Co], act == 2 */
+    /* fused ToRGB (tcgen05 path, stride-1, Co <= 256): rgb_out[B,3,H,W] fp32 = sum_o y[o]*rgb_w[b,k,o] + rgb_bias[k] + up2fir(rgb_skip);
+     * rgb_w from ood_torgb_weight, rgb_skip [B,3,H/2,W/2] fp32 or NULL, rgb_taps = 1-D up-FIR.  out_y / out_ys may then be NULL. */
+    const float *rgb_w, *rgb_bias, *rgb_skip;
+    float *rgb_out;
+    float rgb_taps[4];
 } ood_conv3x3_args;
 int ood_conv3x3(const ood_conv3x3_args *args_host, void *stream);
 

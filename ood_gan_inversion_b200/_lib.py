@@ -17,7 +17,8 @@ class ConvArgs(C.Structure):
     _fields_ = [('inp', c_void_p), ('weight', c_void_p), ('out_y', c_void_p), ('out_ys', c_void_p), ('d', c_void_p),
                 ('noise', c_void_p), ('noise_bstride', c_i64), ('noise_w', c_void_p), ('bias', c_void_p),
                 ('s_next', c_void_p), ('batch', c_int), ('h', c_int), ('w', c_int), ('cin', c_int), ('cout', c_int),
-                ('transposed', c_int), ('act', c_int), ('impl', c_int), ('dtype', c_int), ('out_f32', c_int), ('prelu_slope', c_void_p)]
+                ('transposed', c_int), ('act', c_int), ('impl', c_int), ('dtype', c_int), ('out_f32', c_int), ('prelu_slope', c_void_p),
+                ('rgb_w', c_void_p), ('rgb_bias', c_void_p), ('rgb_skip', c_void_p), ('rgb_out', c_void_p), ('rgb_taps', c_float * 4)]
 
 
 class BlurActArgs(C.Structure):

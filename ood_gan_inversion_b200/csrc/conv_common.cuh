@@ -80,7 +80,45 @@ struct ConvEpilogue {
     int act;                // 0 none | 1 leaky-ReLU(0.2)*sqrt2 | 2 PReLU(prelu[c])
     int out_f32;
     const float *prelu;     // [Co], act == 2
+    // fused ToRGB (model.py:363-372): rgb_out[b,k,Y,X] = sum_o y[o]*rgb_w[b,k,o] + rgb_bias[k] + up2fir(rgb_skip)[b,k,Y,X]
+    const float *rgb_w, *rgb_bias, *rgb_skip;
+    float *rgb_out;
+    float rgb_k[4];         // flipped 1-D up-FIR taps
 };
+
+static inline ConvEpilogue make_epilogue(const ood_conv3x3_args &a, int out_f32) {
+    ConvEpilogue e{};
+    e.out_y = a.out_y; e.out_ys = a.out_ys; e.d = a.d; e.noise = a.noise; e.noise_w = a.noise_w; e.bias = a.bias;
+    e.s_next = a.s_next; e.noise_bstride = a.noise_bstride; e.act = a.act; e.out_f32 = out_f32; e.prelu = a.prelu_slope;
+    e.rgb_w = a.rgb_w; e.rgb_bias = a.rgb_bias; e.rgb_skip = a.rgb_skip; e.rgb_out = a.rgb_out;
+    for (int i = 0; i < 4; ++i) e.rgb_k[i] = a.rgb_taps[3 - i];
+    return e;
+}
+
+// bias + 2x2-tap polyphase up-FIR of the previous level's RGB (upfirdn2d up=2, pad (2,1)) for colour plane k of pixel (Y, X)
+__device__ __forceinline__ float rgb_finish(const ConvEpilogue &e, float partial, int b, int k, int Y, int X, int H, int W) {
+    float v = partial + __ldg(e.rgb_bias + k);
+    if (e.rgb_skip) {
+        const int h2 = H >> 1, w2 = W >> 1;
+        const float *sp = e.rgb_skip + ((int64_t)b * 3 + k) * h2 * w2;
+        const int ky0 = Y & 1, kx0 = X & 1;
+        const int ra = (Y + ky0 - 2) >> 1, ca = (X + kx0 - 2) >> 1;
+        const float wy[2] = {ky0 ? e.rgb_k[1] : e.rgb_k[0], ky0 ? e.rgb_k[3] : e.rgb_k[2]};
+        const float wx[2] = {kx0 ? e.rgb_k[1] : e.rgb_k[0], kx0 ? e.rgb_k[3] : e.rgb_k[2]};
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy) {
+            const int rr = ra + dy;
+            if (rr < 0 || rr >= h2) continue;
+#pragma unroll
+            for (int dx = 0; dx < 2; ++dx) {
+                const int cc = ca + dx;
+                if (cc < 0 || cc >= w2) continue;
+                v = fmaf(wy[dy] * wx[dx], __ldg(sp + (int64_t)rr * w2 + cc), v);
+            }
+        }
+    }
+    return v;
+}
 
 __device__ __forceinline__ float apply_act(float v, int act, float slope) {
     if (act == 1) return lrelu_sqrt2(v);

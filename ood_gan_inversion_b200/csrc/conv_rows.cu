@@ -122,7 +122,7 @@ struct Cfg {
     static constexpr int kRing = CI == 64 ? 5 : 8;
     static constexpr int kTmemCols = kNAcc * CO < 32 ? 32 : kNAcc * CO;
     static constexpr int kOutTile = 128 * CO * 2;                             // one staged output row tile (bf16)
-    static constexpr int kSmem = 9 * kWStride + kRing * kRowStride + 4 * kOutTile + 1024 + 512;   // staging: 2 buffers x (y, ys)
+    static constexpr int kSmem = 9 * kWStride + kRing * kRowStride + 4 * kOutTile + 1024 + 512 + 2048;   // staging: 2 buffers x (y, ys); + RGB partials
     static constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(CO >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 };
 
@@ -147,6 +147,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint64_t *bars = reinterpret_cast<uint64_t *>(sO + 4 * C::kOutTile);
     uint64_t *full = bars, *empty = bars + C::kRing, *tfull = bars + 2 * C::kRing, *tempty = tfull + kNAcc, *wbar = tempty + kNAcc;
     uint32_t *tmem_holder = reinterpret_cast<uint32_t *>(wbar + 1);
+    float *sRGB = reinterpret_cast<float *>(bars) + 128;          // [128 px][3]: fused-ToRGB partial sums of the upper channel half
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == 0 && lane == 0) {
@@ -277,6 +278,12 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const float nz_raw = nz0;
                 nz0 = nz1;
                 nz1 = (nzp && j + 2 < nrows) ? __ldg(nzp + (int64_t)(j + 2) * p.w) : 0.f;
+                // fused ToRGB: bias + upsampled-skip term does not depend on this tile's MMAs -> issue its loads now
+                float rgb_tail[3] = {0.f, 0.f, 0.f};
+                if (p.ep.rgb_out && grp == 0) {
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) rgb_tail[k] = rgb_finish(p.ep, 0.f, b, k, Y, X, p.h, p.w);
+                }
                 // the stores issued two tiles ago (same staging buffer) must have finished READING it
                 if (issuer) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
                 uint8_t *sY = sO + sbuf * 2 * C::kOutTile, *sYS = sY + C::kOutTile;
@@ -297,6 +304,19 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     v[q] = fmaf(__uint_as_float(r[q]), dreg[q], breg[q] + nz);
 
                     if (p.ep.act == 1) v[q] = lrelu_sqrt2(v[q]);
+                }
+                float rgbp[3] = {0.f, 0.f, 0.f};
+                if (p.ep.rgb_out) {          // fused ToRGB: this thread's CH channels of the unscaled activation
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        const float4 *wp = reinterpret_cast<const float4 *>(p.ep.rgb_w + ((int64_t)b * 3 + k) * CO + n0);
+#pragma unroll
+                        for (int q = 0; q < CH / 4; ++q) {
+                            const float4 t = __ldg(wp + q);
+                            rgbp[k] = fmaf(v[4 * q], t.x, fmaf(v[4 * q + 1], t.y, fmaf(v[4 * q + 2], t.z, fmaf(v[4 * q + 3], t.w, rgbp[k]))));
+                        }
+                    }
+                    if (grp == 1) { sRGB[m * 3 + 0] = rgbp[0]; sRGB[m * 3 + 1] = rgbp[1]; sRGB[m * 3 + 2] = rgbp[2]; }
                 }
                 if (p.ep.out_y) {
 #pragma unroll
@@ -329,6 +349,11 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                                      ::"l"(&tmYS), "r"(smem_u32(sYS)), "r"(0), "r"(pix0) : "memory");
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+                if (p.ep.rgb_out && grp == 0) {                      // lower half + upper half (smem) + bias + upsampled skip
+#pragma unroll
+                    for (int k = 0; k < 3; ++k)
+                        p.ep.rgb_out[((int64_t)b * 3 + k) * p.h * p.w + (int64_t)Y * p.w + X] = rgbp[k] + sRGB[m * 3 + k] + rgb_tail[k];
                 }
                 sbuf ^= 1;
                 if (++acc == kNAcc) { acc = 0; acc_phase ^= 1; }
@@ -411,7 +436,7 @@ int conv3x3_rows(const ood_conv3x3_args &a, cudaStream_t st, int *handled) {
         cuuint64_t strides[1] = {(cuuint64_t)a.cout * 2};
         cuuint32_t box[2] = {(cuuint32_t)a.cout, 128};
         cuuint32_t es[2] = {1, 1};
-        void *py = a.out_y ? a.out_y : a.out_ys, *pys = a.out_ys ? a.out_ys : a.out_y;
+        void *py = a.out_y ? a.out_y : (a.out_ys ? a.out_ys : (void *)a.rgb_out), *pys = a.out_ys ? a.out_ys : py;
         if (encode(&tmY, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, py, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swo,
                    CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return OOD_OK;
         if (encode(&tmYS, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, pys, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swo,
@@ -424,7 +449,7 @@ int conv3x3_rows(const ood_conv3x3_args &a, cudaStream_t st, int *handled) {
     const int64_t total = (int64_t)p.tiles_x * p.strips_y * a.batch;
     if (total >= (1LL << 31)) return OOD_OK;
     p.total_strips = (int)total;
-    p.ep = ConvEpilogue{a.out_y, a.out_ys, a.d, a.noise, a.noise_w, a.bias, a.s_next, a.noise_bstride, a.act, 0, nullptr};
+    p.ep = make_epilogue(a, 0);
     *handled = 1;
     if (a.cin == 64 && a.cout == 64) return launch<64, 64>(tmA, tmB, tmY, tmYS, p, st);
     if (a.cin == 64 && a.cout == 32) return launch<64, 32>(tmA, tmB, tmY, tmYS, p, st);

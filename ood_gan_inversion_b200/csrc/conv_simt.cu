@@ -123,7 +123,8 @@ int conv3x3_simt(const ood_conv3x3_args &a, cudaStream_t st) {
     p.in = (const float *)a.in;
     p.w = (const float *)a.weight;
     p.g = make_geom(a.batch, a.h, a.w, a.cin, a.cout, a.transposed);
-    p.ep = ConvEpilogue{a.out_y, a.out_ys, a.d, a.noise, a.noise_w, a.bias, a.s_next, a.noise_bstride, a.act, 1, a.prelu_slope};
+    OOD_REQUIRE(!a.rgb_out, "conv3x3 simt: the fused ToRGB epilogue exists on the tcgen05 path only");
+    p.ep = make_epilogue(a, 1);
     int mmax = 0;
     for (int i = 0; i < p.g.nphases; ++i) mmax = std::max(mmax, p.g.ph[i].m_total);
     dim3 grid(ceil_div(mmax, SBM), ceil_div(a.cout, SBN), p.g.nphases);

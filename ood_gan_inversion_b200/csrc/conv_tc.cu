@@ -246,9 +246,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int64_t pix = ((int64_t)b * p.OH + Y) * p.OW + X;
             float nz = 0.f;
             if (valid && p.ep.noise) nz = nw * __ldg(p.ep.noise + b * p.ep.noise_bstride + (int64_t)Y * p.OW + X);
+            float rgb_tail[3] = {0.f, 0.f, 0.f};      // fused ToRGB: bias + upsampled skip, independent of the accumulator
+            if (p.ep.rgb_out && valid) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) rgb_tail[k] = rgb_finish(p.ep, 0.f, b, k, Y, X, p.OH, p.OW);
+            }
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN;
+            float rgbp[3] = {0.f, 0.f, 0.f};
 #pragma unroll 1
             for (int ch = 0; ch < BN / 32; ++ch) {
                 uint32_t r[32];
@@ -290,6 +296,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] += nz;
                     }
+                    if (p.ep.rgb_out) {      // fused ToRGB: 3 dot products over this chunk's 32 channels of the unscaled activation
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) {
+                            const float4 *wp = reinterpret_cast<const float4 *>(p.ep.rgb_w + ((int64_t)b * 3 + k) * p.cout + n);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const float4 t = __ldg(wp + j);
+                                rgbp[k] = fmaf(v[4 * j], t.x, fmaf(v[4 * j + 1], t.y, fmaf(v[4 * j + 2], t.z, fmaf(v[4 * j + 3], t.w, rgbp[k]))));
+                            }
+                        }
+                    }
                     if (p.ep.out_y) {
                         if (p.ep.out_f32) {
                             float4 *o = reinterpret_cast<float4 *>((float *)p.ep.out_y + pix * p.cout + n);
@@ -317,6 +334,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                               pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
                     }
                 }
+            }
+            if (p.ep.rgb_out && valid) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k)
+                    p.ep.rgb_out[((int64_t)b * 3 + k) * p.OH * p.OW + (int64_t)Y * p.OW + X] = rgbp[k] + rgb_tail[k];
             }
             tc_fence_before();
             __syncwarp();
@@ -402,7 +424,8 @@ int conv3x3_tc(const ood_conv3x3_args &a, cudaStream_t st) {
         tiles += P.tiles_x * P.tiles_y * P.tiles_b * p.n_tiles_n;
     }
     p.total_tiles = tiles;
-    p.ep = ConvEpilogue{a.out_y, a.out_ys, a.d, a.noise, a.noise_w, a.bias, a.s_next, a.noise_bstride, a.act, a.out_f32, a.prelu_slope};
+    OOD_REQUIRE(!a.rgb_out || (p.n_tiles_n == 1 && !a.transposed), "conv3x3 tc: the fused ToRGB epilogue needs Co == tile N (Co <= 256) and the stride-1 form");
+    p.ep = make_epilogue(a, a.out_f32);
     p.out_bf16 = 1;
 
     CUtensorMap tmA, tmB;
@@ -446,7 +469,8 @@ extern "C" int ood_conv3x3(const ood_conv3x3_args *a, void *stream) {
     using namespace ood;
     OOD_REQUIRE(a && a->in && a->weight, "conv3x3: null pointer");
     OOD_REQUIRE(a->batch > 0 && a->h > 0 && a->w > 0 && a->cin > 0 && a->cout > 0, "conv3x3: bad sizes");
-    OOD_REQUIRE(a->out_y || a->out_ys, "conv3x3: no output requested");
+    OOD_REQUIRE(a->out_y || a->out_ys || a->rgb_out, "conv3x3: no output requested");
+    OOD_REQUIRE(!a->rgb_out || (a->rgb_w && a->rgb_bias && a->act == 1 && a->h % 2 == 0 && a->w % 2 == 0), "conv3x3: fused ToRGB needs rgb_w, rgb_bias, act=1 and even sizes");
     OOD_REQUIRE(!a->out_ys || a->s_next, "conv3x3: out_ys needs s_next");
     OOD_REQUIRE(a->transposed >= 0 && a->transposed <= 2, "conv3x3: transposed must be 0, 1 or 2");
     OOD_REQUIRE(a->transposed != 1 || (!a->out_ys && !a->act && !a->noise && !a->bias),

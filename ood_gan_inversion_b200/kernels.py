@@ -212,8 +212,9 @@ def torgb_weight(w, s, scale=None):
 
 # ----------------------------------------------------------------------------------------------- convolution
 def conv3x3(x, weight, cout, transposed=False, impl=0, d=None, noise=None, noise_w=None, bias=None, s_next=None,
-            act=False, want_y=True, want_ys=False, out_f32=False, prelu=None):
-    """x NHWC [B,H,W,Ci] pre-modulated; weight packed for `impl`.  Returns (y, ys) (None where not requested)."""
+            act=False, want_y=True, want_ys=False, out_f32=False, prelu=None, rgb=None):
+    """x NHWC [B,H,W,Ci] pre-modulated; weight packed for `impl`.  Returns (y, ys) (None where not requested).
+    rgb=(wrgb [B,3,Co], bias [3], skip NCHW fp32 or None, up taps): fused ToRGB, returns (y, ys, rgb_out NCHW fp32)."""
     _cuda(x, weight, d, noise, noise_w, bias, s_next)
     assert x.is_contiguous()
     b, h, w, cin = x.shape
@@ -227,9 +228,18 @@ def conv3x3(x, weight, cout, transposed=False, impl=0, d=None, noise=None, noise
         nbs = 0 if noise.shape[0] == 1 else oh * ow
     a = ConvArgs(_ptr(x), _ptr(weight), _ptr(y), _ptr(ys), _ptr(d), _ptr(noise), nbs, _ptr(noise_w), _ptr(bias), _ptr(s_next),
                  b, h, w, cin, cout, int(transposed), 2 if prelu is not None else int(act), impl, _dt(x), int(out_f32), _ptr(prelu))
+    rgb_out = None
+    if rgb is not None:
+        wrgb, rbias, rskip, rtaps = rgb
+        _cuda(wrgb, rbias, rskip)
+        rgb_out = torch.empty(b, 3, oh, ow, device=x.device, dtype=torch.float32)
+        a.rgb_w, a.rgb_bias, a.rgb_skip, a.rgb_out = _ptr(wrgb), _ptr(rbias), _ptr(rskip), _ptr(rgb_out)
+        a.rgb_taps = (C.c_float * 4)(*rtaps)
     # algorithmic work: 2*B*Co*Ci*9*H*W with H, W the INPUT size for the transposed form
     with _timed('conv3x3_tc' if impl == 0 else 'conv3x3_simt', 2.0 * b * cout * cin * 9 * h * w):
         check(_lib.lib().ood_conv3x3(C.byref(a), _stream()), 'conv3x3')
+    if rgb is not None:
+        return y, ys, rgb_out
     return y, ys
 
 

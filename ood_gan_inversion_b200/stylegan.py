@@ -298,7 +298,7 @@ class StyledConv(nn.Module):
         self.activate = FusedLeakyReLU(out_channel) if kwargs.get('activation', True) else (lambda x: x)
 
     # ---- NHWC pipeline stage (used by Generator and by forward) --------------------------------------------
-    def run_nhwc(self, xs, style, noise, s_next=None, want_y=True, want_ys=False, hook=None, d=None):
+    def run_nhwc(self, xs, style, noise, s_next=None, want_y=True, want_ys=False, hook=None, d=None, rgb=None):
         """xs: NHWC activations already carrying this conv's style scale.  noise: fp32 [B|1,1,H,W] (required).
         hook(image_nhwc) -> replacement image (NHWC), applied between the convolution and the noise injection.
         d: demodulation coefficients if the caller already has them (else computed from `style`)."""
@@ -325,7 +325,7 @@ class StyledConv(nn.Module):
             return K.noise_act(img, noise, nw, bias, s_next, want_y, want_ys)
         if hook is None:
             return K.conv3x3(xs, wp, conv.cout_p, impl=_impl(), d=d, noise=noise, noise_w=nw, bias=bias, s_next=s_next,
-                             act=True, want_y=want_y, want_ys=want_ys)
+                             act=True, want_y=want_y, want_ys=want_ys, rgb=rgb)
         img, _ = K.conv3x3(xs, wp, conv.cout_p, impl=_impl(), d=d)
         img = hook(img)
         return K.noise_act(img, noise, nw, bias, s_next, want_y, want_ys)
@@ -382,6 +382,13 @@ class ToRGB(nn.Module):
         self.bias = nn.Parameter(torch.zeros(1, 3, 1, 1))
         k1 = [float(v) for v in blur_kernel]
         self.taps_up = [v / sum(k1) * 2 for v in k1]
+
+    def fused_args(self, style, skip):
+        """(wrgb, bias, skip, taps) for the conv epilogue that computes this ToRGB in place (ood_conv3x3 rgb_* fields)."""
+        wp, _, _, _ = self.conv.packed()
+        s, _ = self.conv.coeffs(style)
+        return (K.torgb_weight(wp, s, self.conv.scale), self.bias.detach().float().reshape(3).contiguous(),
+                None if skip is None else skip.float().contiguous(), self.taps_up)
 
     def run_nhwc(self, y, style, skip=None):
         """y: UNscaled NHWC activations; skip: NCHW fp32 [B,3,H/2,W/2] or None -> NCHW fp32 [B,3,H,W]."""
@@ -553,9 +560,20 @@ class Generator(nn.Module):
                 y1s = insert_feature(y1, s2, i + 1)
             last = blk == n_blocks - 1
             s_next = None if last else sd[3 + 2 * blk][0]
-            y, ys = conv2.run_nhwc(y1s, lat[:, i + 1], draw(noise[2 + 2 * blk], res), s_next=s_next, want_y=True,
-                                   want_ys=not last, d=d2)
-            skip = to_rgb.run_nhwc(y, lat[:, i + 2], skip)
+            # ToRGB fused into conv2's epilogue when one N tile holds all channels (tcgen05 path, Co <= 256): the unscaled
+            # activation is then neither written nor re-read (it is only kept when someone else needs it)
+            co = conv2.conv.cout_p
+            need_y = return_features and last or (features_in is not None and not last and features_in[i + 2] is not None)
+            # (the row-sliding kernel of the 32/64-channel layers is epilogue-bound: fusing there costs more than the separate
+            # ToRGB pass, measured 0.9 -> 1.8 ms at 1024 px, so only the 128/256-channel layers fuse)
+            fuse = _PRECISION == 'bf16' and 128 <= co <= 256 and co == conv2.conv.out_channel and len(to_rgb.taps_up) == 4 and res % 2 == 0
+            if fuse:
+                y, ys, skip = conv2.run_nhwc(y1s, lat[:, i + 1], draw(noise[2 + 2 * blk], res), s_next=s_next, want_y=need_y,
+                                             want_ys=not last, d=d2, rgb=to_rgb.fused_args(lat[:, i + 2], skip))
+            else:
+                y, ys = conv2.run_nhwc(y1s, lat[:, i + 1], draw(noise[2 + 2 * blk], res), s_next=s_next, want_y=True,
+                                       want_ys=not last, d=d2)
+                skip = to_rgb.run_nhwc(y, lat[:, i + 2], skip)
             i += 2
         feat = _to_nchw(y, self.convs[-1].conv.out_channel if n_blocks else self.conv1.conv.out_channel) if return_features else None
         return skip, feat

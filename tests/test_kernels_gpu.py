@@ -434,3 +434,30 @@ def test_conv3x3_row_sliding_kernel(case):
     ref = oops.fused_leaky_relu(ref_raw * d[:, :, None, None] + nw * noise, bias)
     torch.testing.assert_close(nchw(y), ref, rtol=2e-2, atol=3e-2)
     torch.testing.assert_close(nchw(ys), ref * s_next[:, :, None, None], rtol=2e-2, atol=3e-2)
+
+
+@pytest.mark.parametrize('case', [dict(b=2, h=16, w=16, ci=64, co=128), dict(b=1, h=32, w=32, ci=128, co=256),   # generic tiles, BN == Co
+                                  dict(b=2, h=34, w=128, ci=64, co=64), dict(b=1, h=6, w=256, ci=32, co=32)])   # row-sliding kernel
+def test_conv3x3_fused_torgb_epilogue(case):
+    """ToRGB (1x1 modconv + bias + up-FIR skip) computed in the conv epilogue == separate torgb kernel == oracle formula."""
+    b, h, w_, ci, co = case['b'], case['h'], case['w'], case['ci'], case['co']
+    x, w = rnd(b, ci, h, w_, seed=1).bfloat16().float(), (0.2 * rnd(co, ci, 3, 3, seed=2)).bfloat16().float()
+    d, bias, s_next = 0.3 * (1 + rnd(b, co, seed=3).abs()), rnd(co, seed=4), 1 + 0.3 * rnd(b, co, seed=5)
+    noise, nw = rnd(b, 1, h, w_, seed=6), torch.tensor([0.37])
+    wr, sr, rb, skip = rnd(3, co, seed=7), 1 + 0.3 * rnd(b, co, seed=8), rnd(3, seed=9), rnd(b, 3, h // 2, w_ // 2, seed=10)
+    wrgb = K().torgb_weight(wr.to(DEV), sr.to(DEV))
+    wp = K().pack_conv_weight(w.to(DEV), torch.bfloat16, False)
+    args = dict(impl=0, d=d.to(DEV), noise=noise.to(DEV), noise_w=nw.to(DEV), bias=bias.to(DEV), s_next=s_next.to(DEV), act=True)
+    y, ys, rgb = K().conv3x3(nhwc(x, torch.bfloat16), wp, co, want_y=True, want_ys=True,
+                             rgb=(wrgb, rb.to(DEV), skip.to(DEV), K().fir_taps(gain=2.0)), **args)
+    yref = oops.fused_leaky_relu(F.conv2d(x.double(), w.double(), padding=1).float() * d[:, :, None, None] + nw * noise, bias)
+    rgb_ref = torch.einsum('bchw,bkc->bkhw', yref, wr[None] * sr[:, None, :] / math.sqrt(co)) + rb.reshape(1, 3, 1, 1) + \
+        oops.upfirdn2d(skip, oops.fir_kernel([1, 3, 3, 1], 4.0), up=2, pad=(2, 1))
+    torch.testing.assert_close(nchw(y), yref, rtol=2e-2, atol=3e-2)
+    torch.testing.assert_close(rgb.cpu(), rgb_ref, rtol=1e-2, atol=3e-2)
+    # rgb only (no activation written), no skip
+    y2, ys2, rgb2 = K().conv3x3(nhwc(x, torch.bfloat16), wp, co, want_y=False, want_ys=False,
+                                rgb=(wrgb, rb.to(DEV), None, K().fir_taps(gain=2.0)), **args)
+    assert y2 is None and ys2 is None
+    torch.testing.assert_close(rgb2.cpu(), rgb_ref - oops.upfirdn2d(skip, oops.fir_kernel([1, 3, 3, 1], 4.0), up=2, pad=(2, 1)),
+                               rtol=1e-2, atol=3e-2)
