@@ -237,3 +237,36 @@ def test_encoder_inference_copy_matches_module():
     torch.testing.assert_close(w1, w0, rtol=1e-3, atol=1e-3)
     for a, b in zip(f0, f1):
         torch.testing.assert_close(b, a, rtol=1e-3, atol=1e-3)
+
+
+def test_generator_z_space_truncation_and_mixing_vs_oracle():
+    """Generator.forward's latent handling (model.py:501-538): mapping network, truncation, style mixing, return_latents."""
+    m = sg()
+    m.set_precision('fp32')
+    size = 32
+    sd = ostyle.synthetic_generator_state(size, seed=11)
+    sdd = to_dev(sd)
+    gen = m.Generator(size, 512, 8).to(DEV)
+    gen.load_state_dict(sd)
+    z1 = torch.randn(2, 512, generator=torch.Generator().manual_seed(1)).to(DEV)
+    z2 = torch.randn(2, 512, generator=torch.Generator().manual_seed(2)).to(DEV)
+    w1, w2 = ostyle.mapping_network(sdd, '', z1), ostyle.mapping_network(sdd, '', z2)
+    mean_w = w1.mean(0, keepdim=True)
+    # single style + truncation
+    img, lat = gen([z1], truncation=0.7, truncation_latent=mean_w, randomize_noise=False, return_latents=True)
+    wt = mean_w + 0.7 * (w1 - mean_w)
+    ref_lat = wt.unsqueeze(1).repeat(1, gen.n_latent, 1)
+    torch.testing.assert_close(lat, ref_lat, rtol=1e-4, atol=1e-4)
+    ref = ostyle.generator_forward(sdd, ref_lat, size, randomize_noise=False)
+    assert (img - ref).abs().max() < 1e-3
+    # style mixing at a fixed index
+    img2, lat2 = gen([z1, z2], inject_index=3, randomize_noise=False, return_latents=True)
+    ref_lat2 = torch.cat([w1.unsqueeze(1).repeat(1, 3, 1), w2.unsqueeze(1).repeat(1, gen.n_latent - 3, 1)], 1)
+    torch.testing.assert_close(lat2, ref_lat2, rtol=1e-4, atol=1e-4)
+    assert (img2 - ostyle.generator_forward(sdd, ref_lat2, size, randomize_noise=False)).abs().max() < 1e-3
+    # explicit per-layer noise list
+    noises = [torch.randn(2, 1, 2 ** ((i + 5) // 2), 2 ** ((i + 5) // 2), generator=torch.Generator().manual_seed(20 + i)).to(DEV)
+              for i in range(gen.num_layers)]
+    img3, _ = gen(ref_lat, input_is_tensor=True, input_is_latent=True, noise=noises)
+    assert (img3 - ostyle.generator_forward(sdd, ref_lat, size, noise=noises)).abs().max() < 1e-3
+    m.set_precision('bf16')
