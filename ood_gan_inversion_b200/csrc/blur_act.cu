@@ -169,7 +169,8 @@ __global__ void __launch_bounds__(256) noise_act_kernel(const T *__restrict__ im
     }
 }
 
-int blur_act_tma(const ood_blur_act_args *a, cudaStream_t st, int *handled);   // blur_tma.cu
+int blur_act_tma(const ood_blur_act_args *a, cudaStream_t st, int *handled);    // blur_tma.cu
+int blur_act_rows(const ood_blur_act_args *a, cudaStream_t st, int *handled);   // blur_rows.cu
 
 }  // namespace ood
 
@@ -183,9 +184,12 @@ extern "C" int ood_blur_act(const ood_blur_act_args *a, void *stream) {
     OOD_REQUIRE(!a->out_ys || a->s_next, "blur_act: out_ys needs s_next");
     const int N = a->dtype == OOD_F32 ? 4 : 8;
     OOD_REQUIRE(a->channels % N == 0, "blur_act: channels (%d) must be a multiple of %d", a->channels, N);
-    {   // TMA-staged path (channels % 32 == 0 on sm_100); otherwise the register-window kernel below
+    {   // TMA-staged paths (channels % 32 == 0 on sm_100): row-streaming strips for images >= one strip wide, [16 x 32]
+        // tiles below that; otherwise the register-window kernel below
         int handled = 0;
-        const int rc = blur_act_tma(a, (cudaStream_t)stream, &handled);
+        int rc = blur_act_rows(a, (cudaStream_t)stream, &handled);
+        if (handled) return rc;
+        rc = blur_act_tma(a, (cudaStream_t)stream, &handled);
         if (handled) return rc;
     }
     BlurParams p;

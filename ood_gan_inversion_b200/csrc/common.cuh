@@ -45,6 +45,19 @@ template <typename T> __device__ __forceinline__ T from_f32(float x);
 template <> __device__ __forceinline__ float from_f32<float>(float x) { return x; }
 template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float x) { return __float2bfloat16_rn(x); }
 
+// ---- packed fp32x2 arithmetic (FFMA2 / FMUL2 / FADD2, sm_100): two lanes per issue slot.  The bandwidth kernels are
+// issue-bound long before they are FMA-pipe-bound (ncu: blur 27 instructions per element at 69 % issue utilisation), so
+// halving the arithmetic instruction count is what moves them towards the HBM roofline. ----
+__device__ __forceinline__ float2 f2(float a) { return make_float2(a, a); }
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 max2(float2 a, float2 b) { return make_float2(fmaxf(a.x, b.x), fmaxf(a.y, b.y)); }
+// bf16x2 word -> (low element, high element)
+__device__ __forceinline__ float2 unpack_bf16x2(uint32_t w) {
+    return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+}
+
 // 16-byte global load of T, unpacked to fp32 lanes.
 template <typename T> __device__ __forceinline__ Vec<T> load_vec(const T *p);
 template <> __device__ __forceinline__ Vec<float> load_vec<float>(const float *p) {

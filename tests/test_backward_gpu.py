@@ -52,12 +52,13 @@ def test_strided_gather_conv(impl, case):
 
 
 @pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
-def test_blur_adjoint(dtype):
-    x = rnd(2, 32, 10, 14, seed=1).to(dtype).float()
+@pytest.mark.parametrize('hw', [(10, 14), (70, 90)])        # tile kernel / row-streaming kernel
+def test_blur_adjoint(dtype, hw):
+    x = rnd(2, 32, hw[0], hw[1], seed=1).to(dtype).float()
     k = oops.fir_kernel([1, 3, 3, 1], 4.0)
     ref = oops.upfirdn2d(x, torch.flip(k, [0, 1]), pad=(2, 2))         # adjoint of the pad-(1,1) blur
     out, _, _ = K().blur_act(nhwc(x, dtype), list(reversed(K().fir_taps(gain=2.0))), act=False, want_img=True, pad=(2, 2))
-    assert out.shape[1:3] == (11, 15)
+    assert out.shape[1:3] == (hw[0] + 1, hw[1] + 1)
     tol = dict(rtol=1e-5, atol=1e-5) if dtype == torch.float32 else dict(rtol=2e-2, atol=2e-2)
     torch.testing.assert_close(nchw(out), ref, **tol)
     # <blur(t), g> == <t, blur^T(g)>

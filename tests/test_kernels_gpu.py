@@ -249,7 +249,7 @@ def test_modulated_conv_identity_vs_oracle():
 
 # ----------------------------------------------------------------------------------------------- blur + epilogue, torgb
 @pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
-@pytest.mark.parametrize('shape', [(2, 32, 9, 9), (1, 64, 33, 17), (2, 8, 65, 65)])
+@pytest.mark.parametrize('shape', [(2, 32, 9, 9), (1, 64, 33, 17), (2, 8, 65, 65), (2, 32, 67, 65), (1, 64, 150, 131)])
 def test_blur_act(dtype, shape):
     b, c, ih, iw = shape
     if dtype == torch.float32 and c % 4 or dtype == torch.bfloat16 and c % 8:
