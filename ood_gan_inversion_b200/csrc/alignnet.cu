@@ -9,54 +9,103 @@
 
 namespace ood {
 
-// pixels per partial-sum block: small tensors get small chunks so that the grid still fills the 148 SMs
+// pixels per partial-sum block: ONE resident wave (two CTAs per SM) of long streaming blocks.  The earlier 512-pixel
+// chunks ran ~7 short waves whose start-up (first-load latency) and tail (shared-memory reduction, partial store) cost
+// as much as the streaming itself (0.44 of HBM peak on a pure read).
 static inline int stat_chunk(int64_t P, int batch) {
-    int c = 512;
-    while (c > 32 && (int64_t)batch * ((P + c - 1) / c) < 1024) c >>= 1;
-    return c;
+    const int64_t per_image = std::max<int64_t>(1, (int64_t)kNumSMs * 2 / batch);
+    return (int)std::max<int64_t>((P + per_image - 1) / per_image, 32);
+}
+
+// 16 bytes of T -> N/2 fp32 pairs
+template <typename T> __device__ __forceinline__ void load_pairs(const T *p, float2 *dst);
+template <> __device__ __forceinline__ void load_pairs<float>(const float *p, float2 *dst) {
+    const float4 r = __ldg(reinterpret_cast<const float4 *>(p));
+    dst[0] = make_float2(r.x, r.y); dst[1] = make_float2(r.z, r.w);
+}
+template <> __device__ __forceinline__ void load_pairs<__nv_bfloat16>(const __nv_bfloat16 *p, float2 *dst) {
+    const uint4 r = __ldg(reinterpret_cast<const uint4 *>(p));
+    dst[0] = unpack_bf16x2(r.x); dst[1] = unpack_bf16x2(r.y); dst[2] = unpack_bf16x2(r.z); dst[3] = unpack_bf16x2(r.w);
+}
+template <typename T> __device__ __forceinline__ void store_pairs(T *p, const float2 *v);
+template <> __device__ __forceinline__ void store_pairs<float>(float *p, const float2 *v) {
+    *reinterpret_cast<float4 *>(p) = make_float4(v[0].x, v[0].y, v[1].x, v[1].y);
+}
+template <> __device__ __forceinline__ void store_pairs<__nv_bfloat16>(__nv_bfloat16 *p, const float2 *v) {
+    uint4 r;
+    r.x = pack_bf16x2(v[0].x, v[0].y); r.y = pack_bf16x2(v[1].x, v[1].y);
+    r.z = pack_bf16x2(v[2].x, v[2].y); r.w = pack_bf16x2(v[3].x, v[3].y);
+    *reinterpret_cast<uint4 *>(p) = r;
 }
 
 // ---------------------------------------------------------------------------------------------- statistics
-// partial[b][chunk][c][K]: K = 2 (sum x, sum x^2) or 5 (+ sum y, sum y^2, sum xy)
+// partial[b][chunk][c][K]: K = 2 (sum x, sum x^2) or 5 (+ sum y, sum y^2, sum xy); packed fp32x2 accumulation
 template <typename T, int K>
-__global__ void __launch_bounds__(256) in_partial_kernel(const T *__restrict__ x, const T *__restrict__ y,
-                                                          float *__restrict__ partial, int64_t P, int C, int nchunks,
-                                                          int chunk_px) {
-    constexpr int N = Vec<T>::N;
+__global__ void __launch_bounds__(256, 2) in_partial_kernel(const T *__restrict__ x, const T *__restrict__ y,
+                                                             float *__restrict__ partial, int64_t P, int C, int nchunks,
+                                                             int chunk_px) {
+    constexpr int N = Vec<T>::N, N2 = N / 2;
+    constexpr int UNROLL = K == 5 ? 4 : 8;
     extern __shared__ float red[];                      // [lanes][cv*N*K]
     const int cv = C / N;
     const int lanes = 256 / cv > 0 ? 256 / cv : 1;      // pixel lanes per block (cv <= 256 enforced by the host)
     const int vec = threadIdx.x % cv, lane = threadIdx.x / cv;
     const int b = blockIdx.y, chunk = blockIdx.x;
     const int64_t p0 = (int64_t)chunk * chunk_px, p1 = min(p0 + chunk_px, P);
-    float acc[N][K];
+    float2 acc[N2][K];
 #pragma unroll
-    for (int j = 0; j < N; ++j)
+    for (int j = 0; j < N2; ++j)
 #pragma unroll
-        for (int k = 0; k < K; ++k) acc[j][k] = 0.f;
+        for (int k = 0; k < K; ++k) acc[j][k] = f2(0.f);
     if (lane < lanes) {
-#pragma unroll 4
-        for (int64_t p = p0 + lane; p < p1; p += lanes) {
-            const int64_t off = ((int64_t)b * P + p) * C + vec * N;
-            const Vec<T> xv = load_vec<T>(x + off);
-            if constexpr (K == 5) {
-                const Vec<T> yv = load_vec<T>(y + off);
+        const int64_t stride = (int64_t)lanes * C;
+        const T *xp = x + ((int64_t)b * P + p0 + lane) * C + vec * N;
+        const T *yp = K == 5 ? y + ((int64_t)b * P + p0 + lane) * C + vec * N : nullptr;
+        int64_t n = p0 + lane < p1 ? (p1 - p0 - lane + lanes - 1) / lanes : 0;      // pixels of this thread
+        for (; n >= UNROLL; n -= UNROLL) {
+            float2 xv[UNROLL][N2], yv[K == 5 ? UNROLL : 1][N2];
 #pragma unroll
-                for (int j = 0; j < N; ++j) {
-                    acc[j][0] += xv.v[j]; acc[j][1] = fmaf(xv.v[j], xv.v[j], acc[j][1]);
-                    acc[j][2] += yv.v[j]; acc[j][3] = fmaf(yv.v[j], yv.v[j], acc[j][3]);
-                    acc[j][4] = fmaf(xv.v[j], yv.v[j], acc[j][4]);
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < N; ++j) { acc[j][0] += xv.v[j]; acc[j][1] = fmaf(xv.v[j], xv.v[j], acc[j][1]); }
+            for (int u = 0; u < UNROLL; ++u) {
+                load_pairs<T>(xp + u * stride, xv[u]);
+                if constexpr (K == 5) load_pairs<T>(yp + u * stride, yv[u]);
             }
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u)
+#pragma unroll
+                for (int j = 0; j < N2; ++j) {
+                    acc[j][0] = add2(acc[j][0], xv[u][j]);
+                    acc[j][1] = fma2(xv[u][j], xv[u][j], acc[j][1]);
+                    if constexpr (K == 5) {
+                        acc[j][2] = add2(acc[j][2], yv[u][j]);
+                        acc[j][3] = fma2(yv[u][j], yv[u][j], acc[j][3]);
+                        acc[j][4] = fma2(xv[u][j], yv[u][j], acc[j][4]);
+                    }
+                }
+            xp += UNROLL * stride;
+            if constexpr (K == 5) yp += UNROLL * stride;
+        }
+        for (; n > 0; --n) {
+            float2 xv[N2], yv[N2];
+            load_pairs<T>(xp, xv);
+            if constexpr (K == 5) load_pairs<T>(yp, yv);
+#pragma unroll
+            for (int j = 0; j < N2; ++j) {
+                acc[j][0] = add2(acc[j][0], xv[j]);
+                acc[j][1] = fma2(xv[j], xv[j], acc[j][1]);
+                if constexpr (K == 5) {
+                    acc[j][2] = add2(acc[j][2], yv[j]);
+                    acc[j][3] = fma2(yv[j], yv[j], acc[j][3]);
+                    acc[j][4] = fma2(xv[j], yv[j], acc[j][4]);
+                }
+            }
+            xp += stride;
+            if constexpr (K == 5) yp += stride;
         }
         float *r = red + ((size_t)lane * cv + vec) * N * K;
 #pragma unroll
-        for (int j = 0; j < N; ++j)
+        for (int j = 0; j < N2; ++j)
 #pragma unroll
-            for (int k = 0; k < K; ++k) r[j * K + k] = acc[j][k];
+            for (int k = 0; k < K; ++k) { r[(2 * j) * K + k] = acc[j][k].x; r[(2 * j + 1) * K + k] = acc[j][k].y; }
     }
     __syncthreads();
     // fixed-order reduction over the pixel lanes
@@ -154,47 +203,57 @@ __global__ void __launch_bounds__(256) alignnet_ew_kernel(const T *__restrict__ 
     const int b = blockIdx.y;
     const PixSpan sp = pix_span<N>(C, P, chunk);
     if (!sp.active) return;
-    // lo = tl*ct_lo + cu*a1 + en*a2 + a3 ; hi = th*ct_hi + en*b1 + b2
-    float a1[N], a2[N], a3[N], b1[N], b2[N], ctl[N], cth[N];
+    // lo = tl*ct_lo + cu*a1 + en*a2 + a3 ; hi = th*ct_hi + en*b1 + b2      (channel pairs: FFMA2)
+    constexpr int N2 = N / 2;
+    float2 a1[N2], a2[N2], a3[N2], b1[N2], b2[N2], ctl[N2], cth[N2];
 #pragma unroll
     for (int j = 0; j < N; ++j) {
         const int c = sp.c + j;
         const float *s = st6 + ((int64_t)b * C + c) * 6;
         const float mc = s[0], rc = s[1], me = s[2], re = s[3];
+        float va1, va2, va3, vb1, vb2, vctl = 0.f, vcth = 0.f;
         if constexpr (MODE == 0) {
             const float gl = s[4] * w[c], gh = s[5] * w[C + c];
-            a1[j] = rc * gl; a2[j] = -re * gl; a3[j] = (me * re - mc * rc) * gl + bias[c];
-            b1[j] = re * gh; b2[j] = -me * re * gh + bias[C + c];
-            ctl[j] = cth[j] = 0.f;
+            va1 = rc * gl; va2 = -re * gl; va3 = (me * re - mc * rc) * gl + bias[c];
+            vb1 = re * gh; vb2 = -me * re * gh + bias[C + c];
         } else {
             const float *q0 = st2 + ((int64_t)b * 2 * C + c) * 2, *q1 = st2 + ((int64_t)b * 2 * C + C + c) * 2;
-            ctl[j] = q0[1] * w[c]; cth[j] = q1[1] * w[C + c];
-            a1[j] = rc; a2[j] = -re; a3[j] = (me * re - mc * rc) - q0[0] * ctl[j] + bias[c];
-            b1[j] = re; b2[j] = -me * re - q1[0] * cth[j] + bias[C + c];
+            vctl = q0[1] * w[c]; vcth = q1[1] * w[C + c];
+            va1 = rc; va2 = -re; va3 = (me * re - mc * rc) - q0[0] * vctl + bias[c];
+            vb1 = re; vb2 = -me * re - q1[0] * vcth + bias[C + c];
         }
+        if (j & 1) { a1[j / 2].y = va1; a2[j / 2].y = va2; a3[j / 2].y = va3; b1[j / 2].y = vb1; b2[j / 2].y = vb2; ctl[j / 2].y = vctl; cth[j / 2].y = vcth; }
+        else       { a1[j / 2].x = va1; a2[j / 2].x = va2; a3[j / 2].x = va3; b1[j / 2].x = vb1; b2[j / 2].x = vb2; ctl[j / 2].x = vctl; cth[j / 2].x = vcth; }
     }
+    const int64_t s1 = (int64_t)sp.step * C, s2 = 2 * s1;
+    const T *cup = cur + ((int64_t)b * P + sp.p) * C + sp.c, *enp = enc + ((int64_t)b * P + sp.p) * C + sp.c;
+    const T *tp = MODE == 1 ? t + ((int64_t)b * P + sp.p) * 2 * C + sp.c : nullptr;
+    T *op = out + ((int64_t)b * P + sp.p) * 2 * C + sp.c;
 #pragma unroll 2
     for (int64_t p = sp.p; p < sp.p_end; p += sp.step) {
-        const int64_t off1 = ((int64_t)b * P + p) * C + sp.c;
-        const int64_t off2 = ((int64_t)b * P + p) * 2 * C + sp.c;
-        const Vec<T> cu = load_vec<T>(cur + off1), en = load_vec<T>(enc + off1);
-        Vec<T> lo, hi;
+        float2 cu[N2], en[N2], lo[N2], hi[N2];
+        load_pairs<T>(cup, cu);
+        load_pairs<T>(enp, en);
         if constexpr (MODE == 1) {
-            const Vec<T> tl = load_vec<T>(t + off2), th = load_vec<T>(t + off2 + C);
+            float2 tl[N2], th[N2];
+            load_pairs<T>(tp, tl);
+            load_pairs<T>(tp + C, th);
 #pragma unroll
-            for (int j = 0; j < N; ++j) {
-                lo.v[j] = fmaf(tl.v[j], ctl[j], fmaf(cu.v[j], a1[j], fmaf(en.v[j], a2[j], a3[j])));
-                hi.v[j] = fmaf(th.v[j], cth[j], fmaf(en.v[j], b1[j], b2[j]));
+            for (int j = 0; j < N2; ++j) {
+                lo[j] = fma2(tl[j], ctl[j], fma2(cu[j], a1[j], fma2(en[j], a2[j], a3[j])));
+                hi[j] = fma2(th[j], cth[j], fma2(en[j], b1[j], b2[j]));
             }
+            tp += s2;
         } else {
 #pragma unroll
-            for (int j = 0; j < N; ++j) {
-                lo.v[j] = fmaf(cu.v[j], a1[j], fmaf(en.v[j], a2[j], a3[j]));
-                hi.v[j] = fmaf(en.v[j], b1[j], b2[j]);
+            for (int j = 0; j < N2; ++j) {
+                lo[j] = fma2(cu[j], a1[j], fma2(en[j], a2[j], a3[j]));
+                hi[j] = fma2(en[j], b1[j], b2[j]);
             }
         }
-        store_vec<T>(out + off2, lo);
-        store_vec<T>(out + off2 + C, hi);
+        store_pairs<T>(op, lo);
+        store_pairs<T>(op + C, hi);
+        cup += s1; enp += s1; op += s2;
     }
 }
 
@@ -207,20 +266,26 @@ __global__ void __launch_bounds__(256) in_apply_kernel(const T *__restrict__ x, 
     const int b = blockIdx.y;
     const PixSpan sp = pix_span<N>(C, P, chunk);
     if (!sp.active) return;
-    float g[N], h[N];
+    constexpr int N2 = N / 2;
+    float2 g[N2], h[N2];
 #pragma unroll
     for (int j = 0; j < N; ++j) {
         const float *q = st2 + ((int64_t)b * C + sp.c + j) * 2;
-        g[j] = q[1] * (w ? w[sp.c + j] : 1.f);
-        h[j] = (bias ? bias[sp.c + j] : 0.f) - q[0] * g[j];
+        const float gj = q[1] * (w ? w[sp.c + j] : 1.f);
+        const float hj = (bias ? bias[sp.c + j] : 0.f) - q[0] * gj;
+        if (j & 1) { g[j / 2].y = gj; h[j / 2].y = hj; } else { g[j / 2].x = gj; h[j / 2].x = hj; }
     }
+    const int64_t s1 = (int64_t)sp.step * C;
+    const T *xp = x + ((int64_t)b * P + sp.p) * C + sp.c;
+    T *op = out + ((int64_t)b * P + sp.p) * C + sp.c;
 #pragma unroll 4
     for (int64_t p = sp.p; p < sp.p_end; p += sp.step) {
-        const int64_t off = ((int64_t)b * P + p) * C + sp.c;
-        Vec<T> v = load_vec<T>(x + off);
+        float2 v[N2];
+        load_pairs<T>(xp, v);
 #pragma unroll
-        for (int j = 0; j < N; ++j) v.v[j] = fmaf(v.v[j], g[j], h[j]);
-        store_vec<T>(out + off, v);
+        for (int j = 0; j < N2; ++j) v[j] = fma2(v[j], g[j], h[j]);
+        store_pairs<T>(op, v);
+        xp += s1; op += s1;
     }
 }
 
