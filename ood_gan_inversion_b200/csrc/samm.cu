@@ -91,58 +91,111 @@ __global__ void __launch_bounds__(FT * FT) field_step_kernel(const float *__rest
     acc[o + 2 * pl] = f[2];
 }
 
+// 16 bytes of T <-> N/2 fp32 pairs
+template <typename T> __device__ __forceinline__ void wm_load(const T *p, float2 *dst);
+template <> __device__ __forceinline__ void wm_load<float>(const float *p, float2 *dst) {
+    const float4 r = __ldg(reinterpret_cast<const float4 *>(p));
+    dst[0] = make_float2(r.x, r.y); dst[1] = make_float2(r.z, r.w);
+}
+template <> __device__ __forceinline__ void wm_load<__nv_bfloat16>(const __nv_bfloat16 *p, float2 *dst) {
+    const uint4 r = __ldg(reinterpret_cast<const uint4 *>(p));
+    dst[0] = unpack_bf16x2(r.x); dst[1] = unpack_bf16x2(r.y); dst[2] = unpack_bf16x2(r.z); dst[3] = unpack_bf16x2(r.w);
+}
+template <typename T> __device__ __forceinline__ void wm_store(T *p, const float2 *v);
+template <> __device__ __forceinline__ void wm_store<float>(float *p, const float2 *v) {
+    *reinterpret_cast<float4 *>(p) = make_float4(v[0].x, v[0].y, v[1].x, v[1].y);
+}
+template <> __device__ __forceinline__ void wm_store<__nv_bfloat16>(__nv_bfloat16 *p, const float2 *v) {
+    uint4 r;
+    r.x = pack_bf16x2(v[0].x, v[0].y); r.y = pack_bf16x2(v[1].x, v[1].y);
+    r.z = pack_bf16x2(v[2].x, v[2].y); r.w = pack_bf16x2(v[3].x, v[3].y);
+    *reinterpret_cast<uint4 *>(p) = r;
+}
+
 // ------------------------------------------------------------------ warp + alpha mix
 // A thread owns VPT channel vectors of one pixel (slab-interleaved so a warp still reads contiguous runs): the grid /
 // bilinear-weight arithmetic of the pixel is done once per VPT vectors instead of once per vector (ncu: the one-vector
-// version was issue-bound at 70 % with 25 % of DRAM peak).
+// version was issue-bound at 70 % with 25 % of DRAM peak).  A block owns a 2-D tile of pixels -- `segw` columns by
+// `rows_conc` rows in flight, walked down `WM_ITER` times -- so the four bilinear taps of neighbouring pixels (2x overlap
+// in x, 2x in y) hit in L1 instead of being fetched from L2 four times: with the earlier 1-D pixel order the kernel sat
+// at the L2 throughput limit (5 sector reads per algorithmic read) at 0.51 of HBM peak.
+
 template <typename T, int VPT>
-__global__ void __launch_bounds__(256) warp_mix_kernel(const T *__restrict__ gen, const float *__restrict__ field,
-                                                        T *__restrict__ out, int H, int W, int C) {
-    constexpr int N = Vec<T>::N;
+__global__ void __launch_bounds__(256, 4) warp_mix_kernel(const T *__restrict__ gen, const float *__restrict__ field,
+                                                        T *__restrict__ out, int H, int W, int C, int segw, int tiles_x,
+                                                        int tiles, int WM_ITER) {
+    constexpr int N = Vec<T>::N, N2 = N / 2;
     const int cv = C / N;
-    const int cvg = cv / VPT;                 // thread groups per pixel
+    const int cvg = cv / VPT;                 // threads per pixel
+    const int lanes_px = blockDim.x / cvg;    // pixels in flight per block
+    const int rows_conc = lanes_px / segw;
+    const int tile_h = rows_conc * WM_ITER;
     const int b = blockIdx.y;
     const int64_t P = (int64_t)H * W;
     const float *fb = field + (int64_t)b * 3 * P;
     const T *gb = gen + (int64_t)b * P * C;
     T *ob = out + (int64_t)b * P * C;
     const float stepx = W > 1 ? 2.f / (float)(W - 1) : 0.f, stepy = H > 1 ? 2.f / (float)(H - 1) : 0.f;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < P * cvg; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t pix = i / cvg;
-        const int g = (int)(i - pix * cvg);
-        const int y = (int)(pix / W), x = (int)(pix - (int64_t)y * W);
-        // torch.linspace(-1, 1, n): start + i*step in the first half, end - (n-1-i)*step in the second
-        const float lx = (x < W / 2) ? (-1.f + stepx * x) : (1.f - stepx * (W - 1 - x));
-        const float ly = (y < H / 2) ? (-1.f + stepy * y) : (1.f - stepy * (H - 1 - y));
-        const float gx = lx + __ldg(fb + pix), gy = ly + __ldg(fb + P + pix);
-        const float alpha = __ldg(fb + 2 * P + pix);
-        const float ix = ((gx + 1.f) * W - 1.f) * 0.5f, iy = ((gy + 1.f) * H - 1.f) * 0.5f;   // align_corners=False
-        const float fx0 = floorf(ix), fy0 = floorf(iy);
-        const int x0i = (int)fx0, y0i = (int)fy0;
-        const float wx1 = ix - fx0, wy1 = iy - fy0, wx0 = 1.f - wx1, wy0 = 1.f - wy1;
-        float wq[4];
-        int64_t oq[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int xx = x0i + (q & 1), yy = y0i + (q >> 1);
-            const bool ok = xx >= 0 && xx < W && yy >= 0 && yy < H;                            // zeros padding
-            wq[q] = ok ? ((q & 1) ? wx1 : wx0) * ((q >> 1) ? wy1 : wy0) : 0.f;
-            oq[q] = ok ? ((int64_t)yy * W + xx) * C : 0;
-        }
-#pragma unroll
-        for (int v = 0; v < VPT; ++v) {
-            const int c = (v * cvg + g) * N;
-            Vec<T> t[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) t[q] = load_vec<T>(gb + oq[q] + c);
-            const Vec<T> gv = load_vec<T>(gb + pix * C + c);
-            Vec<T> o;
-#pragma unroll
-            for (int j = 0; j < N; ++j) {
-                const float smp = wq[0] * t[0].v[j] + wq[1] * t[1].v[j] + wq[2] * t[2].v[j] + wq[3] * t[3].v[j];
-                o.v[j] = smp * alpha + gv.v[j] * (1.f - alpha);
+    const int pl = threadIdx.x / cvg, g = threadIdx.x - pl * cvg;
+    const int px = pl % segw, py = pl / segw;
+    if (pl >= lanes_px) return;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+        const int x = tx * segw + px;
+        if (x >= W) continue;
+        // the field of the NEXT row of the walk is fetched before this row's gathers are issued: one memory latency per
+        // row instead of two dependent ones
+        float fn[3] = {0.f, 0.f, 0.f};
+        {
+            const int y = ty * tile_h + py;
+            if (y < H) {
+                const int64_t pix = (int64_t)y * W + x;
+                fn[0] = __ldg(fb + pix); fn[1] = __ldg(fb + P + pix); fn[2] = __ldg(fb + 2 * P + pix);
             }
-            store_vec<T>(ob + pix * C + c, o);
+        }
+#pragma unroll 1
+        for (int it = 0; it < WM_ITER; ++it) {
+            const int y = ty * tile_h + it * rows_conc + py;
+            if (y >= H) break;
+            const int64_t pix = (int64_t)y * W + x;
+            const float f0 = fn[0], f1 = fn[1], alpha = fn[2];
+            if (it + 1 < WM_ITER && y + rows_conc < H) {
+                const int64_t pn = pix + (int64_t)rows_conc * W;
+                fn[0] = __ldg(fb + pn); fn[1] = __ldg(fb + P + pn); fn[2] = __ldg(fb + 2 * P + pn);
+            }
+            // torch.linspace(-1, 1, n): start + i*step in the first half, end - (n-1-i)*step in the second
+            const float lx = (x < W / 2) ? (-1.f + stepx * x) : (1.f - stepx * (W - 1 - x));
+            const float ly = (y < H / 2) ? (-1.f + stepy * y) : (1.f - stepy * (H - 1 - y));
+            const float gx = lx + f0, gy = ly + f1;
+            const float ix = ((gx + 1.f) * W - 1.f) * 0.5f, iy = ((gy + 1.f) * H - 1.f) * 0.5f;   // align_corners=False
+            const float fx0 = floorf(ix), fy0 = floorf(iy);
+            const int x0i = (int)fx0, y0i = (int)fy0;
+            const float wx1 = ix - fx0, wy1 = iy - fy0, wx0 = 1.f - wx1, wy0 = 1.f - wy1;
+            float2 wq[4];
+            int64_t oq[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int xx = x0i + (q & 1), yy = y0i + (q >> 1);
+                const bool ok = xx >= 0 && xx < W && yy >= 0 && yy < H;                            // zeros padding
+                wq[q] = f2(ok ? ((q & 1) ? wx1 : wx0) * ((q >> 1) ? wy1 : wy0) : 0.f);
+                oq[q] = ok ? ((int64_t)yy * W + xx) * C : 0;
+            }
+            const float2 al = f2(alpha), al1 = f2(1.f - alpha);
+#pragma unroll
+            for (int v = 0; v < VPT; ++v) {
+                const int c = (v * cvg + g) * N;
+                float2 t[4][N2], gv[N2], o[N2];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) wm_load<T>(gb + oq[q] + c, t[q]);
+                wm_load<T>(gb + pix * C + c, gv);
+#pragma unroll
+                for (int j = 0; j < N2; ++j) {
+                    // same association as the scalar form: ((w0 t0 + w1 t1) + w2 t2) + w3 t3, then smp*alpha + g*(1-alpha)
+                    const float2 smp = fma2(wq[3], t[3][j], fma2(wq[2], t[2][j], fma2(wq[1], t[1][j], mul2(wq[0], t[0][j]))));
+                    o[j] = fma2(smp, al, mul2(gv[j], al1));
+                }
+                wm_store<T>(ob + pix * C + c, o);
+            }
         }
     }
 }
@@ -164,6 +217,11 @@ __device__ __forceinline__ float bilinear_up(const float *__restrict__ a, int r,
            ly1 * (lx0 * __ldg(a + (int64_t)y1 * r + x0) + lx1 * __ldg(a + (int64_t)y1 * r + x1));
 }
 
+// Four consecutive pixels of one row per thread.  The six streaming 16-byte loads (x, gen: 3 planes each) are issued
+// first so that they are in flight while the masks are composed; when the image is at least 4x a mask level (always, in
+// the reference configuration) the four pixels touch at most three mask columns and share the two mask rows, so a level
+// costs 6 loads instead of 16.  Arithmetic per tap is unchanged (ATen's upsample_bilinear2d order).
+template <bool FAST>
 __global__ void __launch_bounds__(256) mask_blend_kernel(const MaskParams mp, const float *__restrict__ xin,
                                                           const float *__restrict__ gen, float *__restrict__ out,
                                                           float *__restrict__ alpha_out, int S) {
@@ -173,28 +231,64 @@ __global__ void __launch_bounds__(256) mask_blend_kernel(const MaskParams mp, co
     for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < nq; q += (int64_t)gridDim.x * blockDim.x) {
         const int64_t pix = q * 4;
         const int y = (int)(pix / S), x = (int)(pix - (int64_t)y * S);
-        float A[4];
+        float4 xv[3], gv[3];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            float a = 0.f;
-            for (int k = 0; k < mp.n; ++k) {
-                const int r = mp.r[k];
-                const float u = bilinear_up(mp.f[k] + ((int64_t)b * 3 + 2) * r * r, r, (float)r / (float)S, y, x + j);
-                a = (k == 0) ? u : (u * a + a * (1.f - a));
-            }
-            A[j] = fminf(fmaxf(a, 0.f), 1.f);
+        for (int k = 0; k < 3; ++k) {
+            const int64_t o = ((int64_t)b * 3 + k) * P + pix;
+            xv[k] = __ldg(reinterpret_cast<const float4 *>(xin + o));
+            gv[k] = __ldg(reinterpret_cast<const float4 *>(gen + o));
         }
+        float A[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int k = 0; k < mp.n; ++k) {
+            const int r = mp.r[k];
+            const float *a = mp.f[k] + ((int64_t)b * 3 + 2) * r * r;
+            float u[4];
+            if (FAST) {
+                const float scale = (float)r / (float)S;
+                const float sy = fmaxf(((float)y + 0.5f) * scale - 0.5f, 0.f);
+                const int y0 = (int)sy, y1 = y0 + (y0 < r - 1);
+                const float ly1 = sy - y0, ly0 = 1.f - ly1;
+                float sx[4];
+                int x0[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    sx[j] = fmaxf(((float)(x + j) + 0.5f) * scale - 0.5f, 0.f);
+                    x0[j] = (int)sx[j];
+                }
+                const int base = x0[0];
+                float top[3], bot[3];
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    const int cx = min(base + i, r - 1);
+                    top[i] = __ldg(a + (int64_t)y0 * r + cx);
+                    bot[i] = __ldg(a + (int64_t)y1 * r + cx);
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int i0 = x0[j] - base, i1 = i0 + (x0[j] < r - 1);      // 0..1, 0..2
+                    const float lx1 = sx[j] - x0[j], lx0 = 1.f - lx1;
+                    const float t0 = i0 ? top[1] : top[0], t1 = i1 == 0 ? top[0] : (i1 == 1 ? top[1] : top[2]);
+                    const float b0 = i0 ? bot[1] : bot[0], b1 = i1 == 0 ? bot[0] : (i1 == 1 ? bot[1] : bot[2]);
+                    u[j] = ly0 * (lx0 * t0 + lx1 * t1) + ly1 * (lx0 * b0 + lx1 * b1);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) u[j] = bilinear_up(a, r, (float)r / (float)S, y, x + j);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) A[j] = (k == 0) ? u[j] : (u[j] * A[j] + A[j] * (1.f - A[j]));
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) A[j] = fminf(fmaxf(A[j], 0.f), 1.f);
         if (alpha_out) *reinterpret_cast<float4 *>(alpha_out + (int64_t)b * P + pix) = make_float4(A[0], A[1], A[2], A[3]);
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
             const int64_t o = ((int64_t)b * 3 + k) * P + pix;
-            const float4 xv = __ldg(reinterpret_cast<const float4 *>(xin + o));
-            const float4 gv = __ldg(reinterpret_cast<const float4 *>(gen + o));
             float4 r;
-            r.x = A[0] * xv.x + gv.x * (1.f - A[0]);
-            r.y = A[1] * xv.y + gv.y * (1.f - A[1]);
-            r.z = A[2] * xv.z + gv.z * (1.f - A[2]);
-            r.w = A[3] * xv.w + gv.w * (1.f - A[3]);
+            r.x = A[0] * xv[k].x + gv[k].x * (1.f - A[0]);
+            r.y = A[1] * xv[k].y + gv[k].y * (1.f - A[1]);
+            r.z = A[2] * xv[k].z + gv[k].z * (1.f - A[2]);
+            r.w = A[3] * xv[k].w + gv[k].w * (1.f - A[3]);
             *reinterpret_cast<float4 *>(out + o) = r;
         }
     }
@@ -291,10 +385,23 @@ extern "C" int ood_warp_mix(const void *gen, const float *field, void *out, int 
     OOD_REQUIRE(channels % N == 0, "warp_mix: channels (%d) must be a multiple of %d", channels, N);
     const int cv = channels / N;
     const int vpt = cv % 4 == 0 ? 4 : (cv % 2 == 0 ? 2 : 1);
-    const int64_t work = (int64_t)h * w * (cv / vpt);
-    dim3 grid((unsigned)std::min<int64_t>((work + 255) / 256, kNumSMs * 16), batch);
+    const int cvg = cv / vpt;
+    OOD_REQUIRE(cvg <= 256, "warp_mix: too many channels (%d)", channels);
+    const int lanes_px = 256 / cvg;
+    static int WM_ITER = -1, seg_max = 16;
+    if (WM_ITER < 0) {
+        const char *e = getenv("OOD_WARP_ITER"), *e2 = getenv("OOD_WARP_SEG");
+        WM_ITER = e ? atoi(e) : 4;
+        if (e2) seg_max = atoi(e2);
+    }
+    int segw = 1;
+    while (segw * 2 <= lanes_px && segw < seg_max) segw *= 2;      // columns in flight (power of two); the rest are rows
+    const int rows_conc = std::max(1, lanes_px / segw);
+    const int tiles_x = ceil_div(w, segw), tiles_y = ceil_div(h, rows_conc * WM_ITER);
+    const int64_t tiles = (int64_t)tiles_x * tiles_y;
+    dim3 grid((unsigned)std::min<int64_t>(tiles, kNumSMs * 16), batch);
     cudaStream_t st = (cudaStream_t)stream;
-#define OOD_WARP(T, V) warp_mix_kernel<T, V><<<grid, 256, 0, st>>>((const T *)gen, field, (T *)out, h, w, channels)
+#define OOD_WARP(T, V) warp_mix_kernel<T, V><<<grid, 256, 0, st>>>((const T *)gen, field, (T *)out, h, w, channels, segw, tiles_x, (int)tiles, WM_ITER)
     if (dtype == OOD_F32) { if (vpt == 4) OOD_WARP(float, 4); else if (vpt == 2) OOD_WARP(float, 2); else OOD_WARP(float, 1); }
     else { if (vpt == 4) OOD_WARP(__nv_bfloat16, 4); else if (vpt == 2) OOD_WARP(__nv_bfloat16, 2); else OOD_WARP(__nv_bfloat16, 1); }
 #undef OOD_WARP
@@ -315,6 +422,9 @@ extern "C" int ood_mask_blend(const float *const *fields_host, const int *field_
     }
     const int64_t nq = (int64_t)size * size / 4;
     dim3 grid((unsigned)std::min<int64_t>((nq + 255) / 256, kNumSMs * 16), batch);
-    mask_blend_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(mp, x, gen, out, alpha_out, size);
+    bool fast = true;                    // every level at most a quarter of the image: 4 pixels span <= 3 mask columns
+    for (int i = 0; i < n_fields; ++i) fast = fast && (int64_t)mp.r[i] * 4 <= size;
+    if (fast) mask_blend_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(mp, x, gen, out, alpha_out, size);
+    else mask_blend_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(mp, x, gen, out, alpha_out, size);
     return check_launch("mask_blend");
 }

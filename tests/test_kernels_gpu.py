@@ -328,8 +328,9 @@ def test_warp_mix(dtype, shape):
     torch.testing.assert_close(nchw(out), ref, **tol)
 
 
-def test_mask_blend():
-    b, size = 2, 64
+@pytest.mark.parametrize('size', [64, 128])      # 64: generic taps; 128: every level <= size/4 (shared-tap fast path)
+def test_mask_blend(size):
+    b = 2
     fields = [torch.rand(b, 3, r, r, generator=g(r)) for r in (4, 8, 16, 32)]
     x, gen = rnd(b, 3, size, size, seed=1), rnd(b, 3, size, size, seed=2)
     alpha = osamm.compose_masks(fields, size)
