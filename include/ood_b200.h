@@ -93,6 +93,8 @@ int ood_pack_conv_weight(const float *w, void *out, int cout, int cin, int taps,
  *      transposed == 0: stride-1, pad-1 conv, out [B,H,W,Co]           (model.py:268-272)
  *      transposed == 1: stride-2 transposed conv, out [B,2H+1,2W+1,Co]  (model.py:246-256), raw accumulators.
  *      transposed == 2: stride-2 valid conv, in [B,2h+1,2w+1,Ci] -> out [B,h,w,Co]: the data gradient of form 1 (autograd of model.py:255).
+ *      transposed == 3: stride-2, pad-1 conv, out [B,(H-1)/2+1,(W-1)/2+1,Co]: the encoder's down-sampling convolutions
+ *                       (src/ops/e4e/encoders/psp_encoders.py:41-48, helpers.py:488-491).
  *      Epilogue (stride-1 only; any pointer may be NULL to skip that term):
  *          v  = acc * d[b,o] + noise_w * noise[b,y,x] + bias[o];  y = act ? lrelu(v,0.2)*sqrt2 : v
  *          out_y  = y            out_ys = y * s_next[b,o]
@@ -111,7 +113,7 @@ typedef struct {
     const float *bias;     /* [Co] or NULL */
     const float *s_next;   /* [B,Co]; required iff out_ys */
     int batch, h, w, cin, cout;
-    int transposed;        /* 0 stride-1 conv | 1 stride-2 transposed conv | 2 stride-2 valid conv (data gradient of 1) */
+    int transposed;        /* 0 stride-1 conv | 1 stride-2 transposed conv | 2 stride-2 valid conv (data gradient of 1) | 3 stride-2 pad-1 conv */
     int act;               /* 0 none | 1 leaky-ReLU(0.2)*sqrt2 | 2 PReLU(prelu_slope[o]) (AlignNet, shared-weight mode) */
     int impl;              /* 0 tcgen05 | 1 simt */
     int dtype;             /* storage type of in / out */
@@ -122,6 +124,12 @@ typedef struct {
     const float *rgb_w, *rgb_bias, *rgb_skip;
     float *rgb_out;
     float rgb_taps[4];
+    /* grouped form (tcgen05 path; the 18 style heads of the E4E encoder, psp_encoders.py:34-56,207-214): `batch` = groups * images;
+     * output image g*images + i is the convolution of input image g*images + i (or of image i of a [images,...] input shared by
+     * all groups when in_shared = 1) with weights [g] of a [groups][9][Co][Ci] pack; bias / prelu_slope are [groups][Co].
+     * Epilogue: bias + activation only.  groups <= 1: the plain form. */
+    int groups;
+    int in_shared;
 } ood_conv3x3_args;
 int ood_conv3x3(const ood_conv3x3_args *args_host, void *stream);
 
@@ -174,6 +182,18 @@ int ood_field_step(const float *z, const float *prev, const float *coarse, float
  *      x [B,h,w,C], y / out [B,H,W,C] (y may be NULL).  ATen's channels-last bicubic costs 40 ms per call at B=16. */
 int ood_bicubic_up_add(const void *x, const void *y, void *out, int batch, int h, int w, int H, int W, int channels,
                        int dtype, void *stream);
+
+/* ---- a13 (encoder trunk, e4e/encoders/helpers.py:59-76 SEModule, :476-501 bottleneck_IR_SE) on NHWC activations.
+ *      ood_se_gate:     stats [B,C,2] from ood_in_stats (channel means) -> gate[b,c] = sigmoid(w2 . relu(w1 . mean[b,:]));
+ *                       w1 [C/r, C], w2 [C, C/r] fp32 (the two bias-free 1x1 convolutions).
+ *      ood_se_residual: out = v * gate[b,c] + shortcut   (shortcut [B, h*s, w*s, C] read at stride s = 1 | 2 -- MaxPool2d(1, s) --
+ *                       or NULL; gate NULL = 1), and, when t_next is given, t_next = out * bn_g[c] + bn_h[c]: the next
+ *                       block's eval-mode BatchNorm.  Either output may be NULL. */
+int ood_se_gate(const float *stats, const float *w1, const float *w2, float *gate, int batch, int channels, int reduced,
+                void *stream);
+int ood_se_residual(const void *v, const float *gate, const void *shortcut, int sc_stride, const float *bn_g,
+                    const float *bn_h, void *out, void *t_next, int batch, int h, int w, int channels, int dtype,
+                    void *stream);
 
 /* ---- a14. backward of the synthesis path for optimisation-based inversion (autograd through model.py:233-372; weights frozen).
  *      ood_act_bwd : gv = gy*sqrt2*(y>0 ? 1 : 0.2) (gate on the saved OUTPUT, fused_bias_act_kernel.cu:36-47);  g = gv*d[b,c];

@@ -18,7 +18,8 @@ class ConvArgs(C.Structure):
                 ('noise', c_void_p), ('noise_bstride', c_i64), ('noise_w', c_void_p), ('bias', c_void_p),
                 ('s_next', c_void_p), ('batch', c_int), ('h', c_int), ('w', c_int), ('cin', c_int), ('cout', c_int),
                 ('transposed', c_int), ('act', c_int), ('impl', c_int), ('dtype', c_int), ('out_f32', c_int), ('prelu_slope', c_void_p),
-                ('rgb_w', c_void_p), ('rgb_bias', c_void_p), ('rgb_skip', c_void_p), ('rgb_out', c_void_p), ('rgb_taps', c_float * 4)]
+                ('rgb_w', c_void_p), ('rgb_bias', c_void_p), ('rgb_skip', c_void_p), ('rgb_out', c_void_p), ('rgb_taps', c_float * 4),
+                ('groups', c_int), ('in_shared', c_int)]
 
 
 class BlurActArgs(C.Structure):
@@ -53,6 +54,9 @@ _SIGS = {
                    c_void_p], c_int),
     'ood_field_step': ([c_void_p, c_void_p, c_void_p, c_void_p, C.POINTER(c_float), c_float, c_int, c_int, c_int,
                         c_void_p], c_int),
+    'ood_se_gate': ([c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p], c_int),
+    'ood_se_residual': ([c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                        c_int, c_void_p], c_int),
     'ood_bicubic_up_add': ([c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p], c_int),
     'ood_bwd_workspace': ([c_int, c_i64, c_int, c_int], c_i64),
     'ood_act_bwd': ([c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_i64,

@@ -173,20 +173,20 @@ class ood_faceGAN_e4e(nn.Module):
     # ---- forward -------------------------------------------------------------------------------------------------
     def encode(self, x):
         """E4E encoder on the bilinear 256x256 thumbnail -> (w [B,18,512] fp32, feats).  e4e_arch.py:256-258.
-        bf16 mode runs a cached inference copy (BN folded into the preceding convs, weights stored once in bf16)."""
+        bf16 mode runs a cached inference copy on this library's kernels (encoder_fast.FastEncoder)."""
         bf16 = sg.get_precision() == 'bf16'
         with torch.no_grad():
             self.encoder.eval()
             small = F.interpolate(x, (256, 256), mode='bilinear')
             with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
                 if bf16:
-                    from . import encoder_infer
+                    from . import encoder_fast, encoder_infer
                     key = (x.device, encoder_infer.state_key(self.encoder))
                     if getattr(self, '_enc_infer', None) is None or self._enc_infer[0] != key:
-                        object.__setattr__(self, '_enc_infer', (key, encoder_infer.build(self.encoder)))
+                        object.__setattr__(self, '_enc_infer', (key, encoder_fast.FastEncoder(self.encoder)))
                     enc = self._enc_infer[1]
                     enc.progressive_stage = self.encoder.progressive_stage
-                    w, feats = enc(small.to(torch.bfloat16).contiguous(memory_format=torch.channels_last), return_feats=True)
+                    w, feats = enc(small, return_feats=True)
                 else:
                     w, feats = self.encoder(small, return_feats=True)
         return w.float(), feats

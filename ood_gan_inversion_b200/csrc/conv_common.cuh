@@ -42,6 +42,18 @@ static inline ConvGeom make_geom(int batch, int h, int w, int cin, int cout, int
                 p.dy[t] = ky; p.dx[t] = kx; p.wt[t] = t;
             }
         p.m_total = batch * p.oh * p.ow;
+    } else if (transposed == 3) {
+        // stride-2 pad-1 3x3 conv: out[y,x] = sum in[2y+ky-1, 2x+kx-1] * W[ky,kx] -- the down-sampling convolutions of the
+        // E4E encoder (GradualStyleBlock psp_encoders.py:41-48, bottleneck_IR_SE helpers.py:488-491)
+        g.OH = (h - 1) / 2 + 1; g.OW = (w - 1) / 2 + 1; g.sy = g.sx = 1; g.isy = g.isx = 2; g.nphases = 1;
+        ConvPhase &p = g.ph[0];
+        p.oh = g.OH; p.ow = g.OW; p.py = p.px = 0; p.ntaps = 9;
+        for (int ky = 0; ky < 3; ++ky)
+            for (int kx = 0; kx < 3; ++kx) {
+                const int t = ky * 3 + kx;
+                p.dy[t] = ky - 1; p.dx[t] = kx - 1; p.wt[t] = t;
+            }
+        p.m_total = batch * p.oh * p.ow;
     } else if (!transposed) {
         g.OH = h; g.OW = w; g.sy = g.sx = 1; g.nphases = 1;
         ConvPhase &p = g.ph[0];

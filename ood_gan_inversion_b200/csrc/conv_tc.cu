@@ -30,6 +30,7 @@ struct TcParams {
     int isy, isx;                   // input stride (2 for the strided data-gradient form; the TMA map then carries elementStrides 2)
     int TW, TH, NB;                 // pixel patch of one M tile: NB*TH*TW == 128
     int nphases, n_tiles_n, total_tiles;
+    int groups, gbatch, in_shared;  // grouped form: output image g*gbatch + i uses weights [g*9 + tap] and input image i (shared) or g*gbatch + i
     TcPhase ph[4];
     ConvEpilogue ep;
     int out_bf16;                   // storage type of out_y / out_ys
@@ -137,6 +138,7 @@ struct TcCfg {
 
 struct TileCoord {
     int phase, b0, y0, x0, n0;
+    int group, bl0;                 // group of this tile and its first image inside the group (b0 = group*gbatch + bl0)
 };
 
 __device__ __forceinline__ TileCoord decode_tile(const TcParams &p, int tile, int BN) {
@@ -149,7 +151,9 @@ __device__ __forceinline__ TileCoord decode_tile(const TcParams &p, int tile, in
     const int local = tile - P.tile_begin;
     const int nt = local % p.n_tiles_n, mt = local / p.n_tiles_n;
     const int tx = mt % P.tiles_x, ty = (mt / P.tiles_x) % P.tiles_y, tb = mt / (P.tiles_x * P.tiles_y);
-    tc.phase = ph; tc.b0 = tb * p.NB; tc.y0 = ty * p.TH; tc.x0 = tx * p.TW; tc.n0 = nt * BN;
+    const int tiles_bg = P.tiles_b / p.groups;          // M tiles never straddle a group
+    tc.group = tb / tiles_bg; tc.bl0 = (tb - tc.group * tiles_bg) * p.NB;
+    tc.phase = ph; tc.b0 = tc.group * p.gbatch + tc.bl0; tc.y0 = ty * p.TH; tc.x0 = tx * p.TW; tc.n0 = nt * BN;
     return tc;
 }
 
@@ -194,8 +198,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     for (int kc = 0; kc < kchunks; ++kc) {
                         mbar_wait(&empty[stage], phase ^ 1);
                         mbar_expect_tx(&full[stage], Cfg::kStageBytes);
-                        tma_load_4d(sA + stage * Cfg::kABytes, &tmA, &full[stage], kc * BK, tc.x0 * p.isx + P.dx[t], tc.y0 * p.isy + P.dy[t], tc.b0);
-                        tma_load_3d(sB + stage * Cfg::kBBytes, &tmB, &full[stage], kc * BK, tc.n0, P.wt[t]);
+                        tma_load_4d(sA + stage * Cfg::kABytes, &tmA, &full[stage], kc * BK, tc.x0 * p.isx + P.dx[t], tc.y0 * p.isy + P.dy[t],
+                                    p.in_shared ? tc.bl0 : tc.b0);
+                        tma_load_3d(sB + stage * Cfg::kBBytes, &tmB, &full[stage], kc * BK, tc.n0, P.wt[t] + tc.group * 9);
                         if (++stage == S) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -241,7 +246,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const TileCoord tc = decode_tile(p, tile, BN);
             const TcPhase &P = p.ph[tc.phase];
             const int b = tc.b0 + nb, oy = tc.y0 + ty, ox = tc.x0 + tx;
-            const bool valid = b < p.batch && oy < P.oh && ox < P.ow;
+            const bool valid = tc.bl0 + nb < p.gbatch && oy < P.oh && ox < P.ow;
+            const int gofs = tc.group * p.cout;           // per-group bias / PReLU slopes: [groups][Co]
             const int Y = oy * p.sy + P.py, X = ox * p.sx + P.px;
             const int64_t pix = ((int64_t)b * p.OH + Y) * p.OW + X;
             float nz = 0.f;
@@ -274,7 +280,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         }
                     }
                     if (p.ep.bias) {
-                        const float4 *bp = reinterpret_cast<const float4 *>(p.ep.bias + n);
+                        const float4 *bp = reinterpret_cast<const float4 *>(p.ep.bias + gofs + n);
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
                             const float4 t = __ldg(bp + j);
@@ -285,7 +291,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = lrelu_sqrt2(v[j] + nz);
                     } else if (p.ep.act == 2) {
-                        const float4 *pp = reinterpret_cast<const float4 *>(p.ep.prelu + n);
+                        const float4 *pp = reinterpret_cast<const float4 *>(p.ep.prelu + gofs + n);
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
                             const float4 t = __ldg(pp + j);
@@ -399,9 +405,12 @@ int conv3x3_tc(const ood_conv3x3_args &a, cudaStream_t st) {
     EncodeTiledFn encode = get_encode_fn();
     if (!encode) { set_error("conv3x3 tc: cuTensorMapEncodeTiled is unavailable"); return OOD_ERR_CUDA; }
 
+    const int groups = a.groups > 1 ? a.groups : 1;
+    OOD_REQUIRE(a.batch % groups == 0, "conv3x3 tc: batch (%d) must be a multiple of groups (%d)", a.batch, groups);
+    OOD_REQUIRE(groups == 1 || (!a.d && !a.noise && !a.out_ys && !a.rgb_out), "conv3x3 tc: the grouped form supports bias / activation epilogues only");
     const ConvGeom g = make_geom(a.batch, a.h, a.w, a.cin, a.cout, a.transposed);
     const int BK = (a.cin % 64 == 0) ? 64 : 32;
-    const int BN = a.cout % 256 == 0 ? 256 : (a.cout % 128 == 0 ? 128 : (a.cout % 64 == 0 ? 64 : 32));
+    int BN = a.cout % 256 == 0 ? 256 : (a.cout % 128 == 0 ? 128 : (a.cout % 64 == 0 ? 64 : 32));
 
     TcParams p{};
     p.batch = g.batch; p.h = g.h; p.w = g.w; p.cin = g.cin; p.cout = g.cout; p.OH = g.OH; p.OW = g.OW; p.sy = g.sy; p.sx = g.sx;
@@ -412,16 +421,24 @@ int conv3x3_tc(const ood_conv3x3_args &a, cudaStream_t st) {
     p.TH = std::min(pow2_ceil(ohm), TBM / p.TW);
     p.NB = TBM / (p.TW * p.TH);
     p.nphases = g.nphases;
-    p.n_tiles_n = a.cout / BN;
+    p.groups = groups; p.gbatch = a.batch / groups; p.in_shared = a.in_shared ? 1 : 0;
     int tiles = 0;
-    for (int i = 0; i < g.nphases; ++i) {
-        TcPhase &P = p.ph[i];
-        const ConvPhase &G = g.ph[i];
-        P.oh = G.oh; P.ow = G.ow; P.py = G.py; P.px = G.px; P.ntaps = G.ntaps;
-        for (int t = 0; t < 9; ++t) { P.dy[t] = G.dy[t]; P.dx[t] = G.dx[t]; P.wt[t] = G.wt[t]; }
-        P.tiles_x = ceil_div(G.ow, p.TW); P.tiles_y = ceil_div(G.oh, p.TH); P.tiles_b = ceil_div(g.batch, p.NB);
-        P.tile_begin = tiles;
-        tiles += P.tiles_x * P.tiles_y * P.tiles_b * p.n_tiles_n;
+    for (;;) {
+        p.n_tiles_n = a.cout / BN;
+        tiles = 0;
+        for (int i = 0; i < g.nphases; ++i) {
+            TcPhase &P = p.ph[i];
+            const ConvPhase &G = g.ph[i];
+            P.oh = G.oh; P.ow = G.ow; P.py = G.py; P.px = G.px; P.ntaps = G.ntaps;
+            for (int t = 0; t < 9; ++t) { P.dy[t] = G.dy[t]; P.dx[t] = G.dx[t]; P.wt[t] = G.wt[t]; }
+            P.tiles_x = ceil_div(G.ow, p.TW); P.tiles_y = ceil_div(G.oh, p.TH); P.tiles_b = groups * ceil_div(p.gbatch, p.NB);
+            P.tile_begin = tiles;
+            tiles += P.tiles_x * P.tiles_y * P.tiles_b * p.n_tiles_n;
+        }
+        // few-pixel problems (the tails of the encoder's style heads) are bound by streaming the weights: narrower N
+        // tiles put more SMs on that stream
+        if (tiles >= kNumSMs || BN <= 64 || a.rgb_out) break;
+        BN >>= 1;
     }
     p.total_tiles = tiles;
     OOD_REQUIRE(!a.rgb_out || (p.n_tiles_n == 1 && !a.transposed), "conv3x3 tc: the fused ToRGB epilogue needs Co == tile N (Co <= 256) and the stride-1 form");
@@ -430,7 +447,7 @@ int conv3x3_tc(const ood_conv3x3_args &a, cudaStream_t st) {
 
     CUtensorMap tmA, tmB;
     {
-        cuuint64_t dims[4] = {(cuuint64_t)a.cin, (cuuint64_t)a.w, (cuuint64_t)a.h, (cuuint64_t)a.batch};
+        cuuint64_t dims[4] = {(cuuint64_t)a.cin, (cuuint64_t)a.w, (cuuint64_t)a.h, (cuuint64_t)(p.in_shared ? p.gbatch : a.batch)};
         cuuint64_t strides[3] = {(cuuint64_t)a.cin * 2, (cuuint64_t)a.w * a.cin * 2, (cuuint64_t)a.h * a.w * a.cin * 2};
         // with element stride s the box spans s*(n-1)+1 tensor elements and delivers n of them to shared memory
         cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)(g.isx * (p.TW - 1) + 1), (cuuint32_t)(g.isy * (p.TH - 1) + 1), (cuuint32_t)p.NB};
@@ -441,7 +458,7 @@ int conv3x3_tc(const ood_conv3x3_args &a, cudaStream_t st) {
         if (r != CUDA_SUCCESS) { set_error("conv3x3 tc: activation tensor map encode failed (%d)", (int)r); return OOD_ERR_CUDA; }
     }
     {
-        cuuint64_t dims[3] = {(cuuint64_t)a.cin, (cuuint64_t)a.cout, 9};
+        cuuint64_t dims[3] = {(cuuint64_t)a.cin, (cuuint64_t)a.cout, (cuuint64_t)(9 * groups)};
         cuuint64_t strides[2] = {(cuuint64_t)a.cin * 2, (cuuint64_t)a.cout * a.cin * 2};
         cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)BN, 1};
         cuuint32_t es[3] = {1, 1, 1};
@@ -472,7 +489,7 @@ extern "C" int ood_conv3x3(const ood_conv3x3_args *a, void *stream) {
     OOD_REQUIRE(a->out_y || a->out_ys || a->rgb_out, "conv3x3: no output requested");
     OOD_REQUIRE(!a->rgb_out || (a->rgb_w && a->rgb_bias && a->act == 1 && a->h % 2 == 0 && a->w % 2 == 0), "conv3x3: fused ToRGB needs rgb_w, rgb_bias, act=1 and even sizes");
     OOD_REQUIRE(!a->out_ys || a->s_next, "conv3x3: out_ys needs s_next");
-    OOD_REQUIRE(a->transposed >= 0 && a->transposed <= 2, "conv3x3: transposed must be 0, 1 or 2");
+    OOD_REQUIRE(a->transposed >= 0 && a->transposed <= 3, "conv3x3: transposed must be 0, 1, 2 or 3");
     OOD_REQUIRE(a->transposed != 1 || (!a->out_ys && !a->act && !a->noise && !a->bias),
                 "conv3x3: the transposed form writes raw accumulators (the epilogue follows the blur)");
     OOD_REQUIRE(a->transposed != 2 || (a->h % 2 == 1 && a->w % 2 == 1 && a->h >= 3 && a->w >= 3 && !a->noise),

@@ -1,0 +1,142 @@
+// Glue kernels of the IR-SE bottleneck of the E4E encoder on NHWC activations.
+// Reference: src/ops/e4e/encoders/helpers.py:59-76 (SEModule), :476-501 (bottleneck_IR_SE):
+//     out = SE(BN2(conv2(PReLU(conv1(BN1(x)))))) + shortcut(x),   SE(v) = v * sigmoid(fc2(relu(fc1(mean_hw(v)))))
+// The convolutions run on the tcgen05 kernel (conv_tc.cu) with PReLU / folded-BN2 bias epilogues; what is left is
+//   se_gate:     per-image channel means (from ood_in_stats) -> the two tiny fully-connected layers -> gate[b,c]
+//   se_residual: out = v * gate + shortcut(x) in one pass, which also emits the NEXT block's BN1(out) so that the
+//                normalised copy never costs a pass of its own.
+// PyTorch runs this tail as ~8 elementwise / reduction kernels per block (24 blocks).
+#include "common.cuh"
+
+namespace ood {
+
+__global__ void __launch_bounds__(256) se_gate_kernel(const float *__restrict__ stats, const float *__restrict__ w1,
+                                                       const float *__restrict__ w2, float *__restrict__ gate, int C, int Cr) {
+    extern __shared__ float sg[];            // mean[C], hid[Cr]
+    float *mean = sg, *hid = sg + C;
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int c = tid; c < C; c += blockDim.x) mean[c] = stats[((int64_t)b * C + c) * 2];
+    __syncthreads();
+    for (int j = warp; j < Cr; j += blockDim.x / 32) {
+        const float *wr = w1 + (int64_t)j * C;
+        float s = 0.f;
+        for (int c = lane; c < C; c += 32) s = fmaf(wr[c], mean[c], s);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) hid[j] = fmaxf(s, 0.f);
+    }
+    __syncthreads();
+    for (int c = tid; c < C; c += blockDim.x) {
+        const float *wr = w2 + (int64_t)c * Cr;
+        float s = 0.f;
+        for (int j = 0; j < Cr; ++j) s = fmaf(wr[j], hid[j], s);
+        gate[(int64_t)b * C + c] = 1.f / (1.f + __expf(-s));
+    }
+}
+
+template <typename T> __device__ __forceinline__ void enc_load(const T *p, float2 *dst);
+template <> __device__ __forceinline__ void enc_load<float>(const float *p, float2 *dst) {
+    const float4 r = __ldg(reinterpret_cast<const float4 *>(p));
+    dst[0] = make_float2(r.x, r.y); dst[1] = make_float2(r.z, r.w);
+}
+template <> __device__ __forceinline__ void enc_load<__nv_bfloat16>(const __nv_bfloat16 *p, float2 *dst) {
+    const uint4 r = __ldg(reinterpret_cast<const uint4 *>(p));
+    dst[0] = unpack_bf16x2(r.x); dst[1] = unpack_bf16x2(r.y); dst[2] = unpack_bf16x2(r.z); dst[3] = unpack_bf16x2(r.w);
+}
+template <typename T> __device__ __forceinline__ void enc_store(T *p, const float2 *v);
+template <> __device__ __forceinline__ void enc_store<float>(float *p, const float2 *v) {
+    *reinterpret_cast<float4 *>(p) = make_float4(v[0].x, v[0].y, v[1].x, v[1].y);
+}
+template <> __device__ __forceinline__ void enc_store<__nv_bfloat16>(__nv_bfloat16 *p, const float2 *v) {
+    uint4 r;
+    r.x = pack_bf16x2(v[0].x, v[0].y); r.y = pack_bf16x2(v[1].x, v[1].y);
+    r.z = pack_bf16x2(v[2].x, v[2].y); r.w = pack_bf16x2(v[3].x, v[3].y);
+    *reinterpret_cast<uint4 *>(p) = r;
+}
+
+// A thread owns one 16-byte channel vector and walks down a chunk of pixels (coefficients in registers).
+template <typename T>
+__global__ void __launch_bounds__(256) se_residual_kernel(const T *__restrict__ v, const float *__restrict__ gate,
+                                                           const T *__restrict__ sc, int ss, const float *__restrict__ bn_g,
+                                                           const float *__restrict__ bn_h, T *__restrict__ out,
+                                                           T *__restrict__ tn, int H, int W, int C, int64_t chunk) {
+    constexpr int N = Vec<T>::N, N2 = N / 2;
+    const int b = blockIdx.y;
+    const int cv = C / N;
+    const int lanes = blockDim.x / cv;
+    const int vec = threadIdx.x % cv, lane = threadIdx.x / cv;
+    if (lane >= lanes) return;
+    const int c = vec * N;
+    const int64_t P = (int64_t)H * W;
+    float2 g[N2], bg[N2], bh[N2];
+#pragma unroll
+    for (int j = 0; j < N2; ++j) {
+        g[j] = gate ? make_float2(gate[(int64_t)b * C + c + 2 * j], gate[(int64_t)b * C + c + 2 * j + 1]) : f2(1.f);
+        bg[j] = tn ? make_float2(bn_g[c + 2 * j], bn_g[c + 2 * j + 1]) : f2(1.f);
+        bh[j] = tn ? make_float2(bn_h[c + 2 * j], bn_h[c + 2 * j + 1]) : f2(0.f);
+    }
+    const int64_t p0 = (int64_t)blockIdx.x * chunk, p1 = min(p0 + chunk, P);
+    const int Ws = W * ss;
+#pragma unroll 2
+    for (int64_t p = p0 + lane; p < p1; p += lanes) {
+        const int64_t off = ((int64_t)b * P + p) * C + c;
+        float2 x[N2];
+        enc_load<T>(v + off, x);
+        if (sc) {
+            int64_t soff = off;
+            if (ss != 1) {
+                const int y = (int)(p / W), xx = (int)(p - (int64_t)y * W);
+                soff = (((int64_t)b * H * ss + (int64_t)y * ss) * Ws + (int64_t)xx * ss) * C + c;
+            }
+            float2 s[N2];
+            enc_load<T>(sc + soff, s);
+#pragma unroll
+            for (int j = 0; j < N2; ++j) x[j] = fma2(x[j], g[j], s[j]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < N2; ++j) x[j] = mul2(x[j], g[j]);
+        }
+        if (out) enc_store<T>(out + off, x);
+        if (tn) {
+#pragma unroll
+            for (int j = 0; j < N2; ++j) x[j] = fma2(x[j], bg[j], bh[j]);
+            enc_store<T>(tn + off, x);
+        }
+    }
+}
+
+}  // namespace ood
+
+extern "C" int ood_se_gate(const float *stats, const float *w1, const float *w2, float *gate, int batch, int channels,
+                           int reduced, void *stream) {
+    using namespace ood;
+    OOD_REQUIRE(stats && w1 && w2 && gate && batch > 0 && channels > 0 && reduced > 0, "se_gate: bad arguments");
+    const size_t smem = (size_t)(channels + reduced) * sizeof(float);
+    OOD_REQUIRE(smem <= 48 * 1024, "se_gate: too many channels (%d)", channels);
+    se_gate_kernel<<<batch, 256, smem, (cudaStream_t)stream>>>(stats, w1, w2, gate, channels, reduced);
+    return check_launch("se_gate");
+}
+
+extern "C" int ood_se_residual(const void *v, const float *gate, const void *shortcut, int sc_stride, const float *bn_g,
+                               const float *bn_h, void *out, void *t_next, int batch, int h, int w, int channels, int dtype,
+                               void *stream) {
+    using namespace ood;
+    OOD_REQUIRE(v && (out || t_next) && batch > 0 && batch <= 65535 && h > 0 && w > 0, "se_residual: bad arguments");
+    OOD_REQUIRE(dtype == OOD_F32 || dtype == OOD_BF16, "se_residual: bad dtype");
+    OOD_REQUIRE(sc_stride == 1 || sc_stride == 2, "se_residual: shortcut stride must be 1 or 2");
+    OOD_REQUIRE(!t_next || (bn_g && bn_h), "se_residual: t_next needs the affine coefficients");
+    const int N = dtype == OOD_F32 ? 4 : 8;
+    OOD_REQUIRE(channels % N == 0 && channels / N <= 256, "se_residual: channels (%d) must be a multiple of %d and at most %d", channels, N, 256 * N);
+    const int64_t P = (int64_t)h * w;
+    const int lanes = std::max(1, 256 / (channels / N));
+    const int64_t want_blocks = std::max<int64_t>(1, (int64_t)kNumSMs * 8 / batch);
+    int64_t chunk = std::max<int64_t>((P + want_blocks - 1) / want_blocks, (int64_t)lanes * 4);
+    chunk = (chunk + lanes - 1) / lanes * lanes;
+    dim3 grid((unsigned)((P + chunk - 1) / chunk), batch);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == OOD_F32)
+        se_residual_kernel<float><<<grid, 256, 0, st>>>((const float *)v, gate, (const float *)shortcut, sc_stride, bn_g, bn_h, (float *)out, (float *)t_next, h, w, channels, chunk);
+    else
+        se_residual_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16 *)v, gate, (const __nv_bfloat16 *)shortcut, sc_stride, bn_g, bn_h, (__nv_bfloat16 *)out, (__nv_bfloat16 *)t_next, h, w, channels, chunk);
+    return check_launch("se_residual");
+}

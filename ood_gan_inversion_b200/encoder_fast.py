@@ -1,0 +1,157 @@
+"""bf16 inference path of the E4E encoder on this library's kernels (NHWC activations).
+
+Reference module: src/ops/e4e/encoders/psp_encoders.py:34-56,125-216 and helpers.py:59-76,476-501 (eval mode,
+e4e_arch.py:256-258).  The trunk's 48 stride-1 / stride-2 3x3 convolutions and the 98 stride-2 convolutions of the 18
+GradualStyleBlocks run on the tcgen05 implicit-GEMM kernel (`ood_conv3x3`, forms 0 and 3) with their PReLU / folded
+BatchNorm bias / LeakyReLU fused into the epilogue; the squeeze-excite gate and the residual sum (which also emits the
+next block's BatchNorm) are `ood_se_gate` / `ood_se_residual`.  What stays cuDNN: the 3->64 input convolution, the three
+1x1 stride-2 shortcut convolutions and the two 1x1 lateral convolutions.
+
+Built from (and numerically checked against) `encoder.Encoder4Editing`; eval-mode BatchNorms are folded in fp32.
+"""
+import torch
+from torch import nn
+from torch.nn import functional as F
+
+from . import kernels as K
+
+
+def _bn_affine(bn):
+    g = bn.weight.detach().float() * torch.rsqrt(bn.running_var.detach().float() + bn.eps)
+    return g.contiguous(), (bn.bias.detach().float() - bn.running_mean.detach().float() * g).contiguous()
+
+
+def _pack(w):
+    return K.pack_conv_weight(w.float().contiguous(), torch.bfloat16, False)
+
+
+def _nhwc(t):
+    """NCHW channels_last tensor -> NHWC contiguous view (no copy when already channels_last)."""
+    return t.permute(0, 2, 3, 1).contiguous()
+
+
+def _nchw(t):
+    """NHWC contiguous -> NCHW view in channels_last memory format (no copy)."""
+    return t.permute(0, 3, 1, 2)
+
+
+class _Block:
+    def __init__(self, blk):
+        bn1, conv1, prelu, conv2, bn2, se = list(blk.res_layer.children())
+        self.stride = conv2.stride[0]
+        self.depth = conv1.out_channels
+        self.bn1 = _bn_affine(bn1)
+        self.w1 = _pack(conv1.weight.detach())
+        self.slope = prelu.weight.detach().float().contiguous()
+        g2, h2 = _bn_affine(bn2)
+        self.w2 = _pack(conv2.weight.detach().float() * g2.reshape(-1, 1, 1, 1))
+        self.b2 = h2
+        self.se1 = se.fc1.weight.detach().float().reshape(se.fc1.out_channels, -1).contiguous()
+        self.se2 = se.fc2.weight.detach().float().reshape(se.fc2.out_channels, -1).contiguous()
+        self.shortcut = None
+        if isinstance(blk.shortcut_layer, nn.Sequential):
+            conv, bn = list(blk.shortcut_layer.children())
+            g, h = _bn_affine(bn)
+            sc = nn.Conv2d(conv.in_channels, conv.out_channels, 1, conv.stride, bias=True).to(conv.weight.device)
+            sc.weight = nn.Parameter(conv.weight.detach().float() * g.reshape(-1, 1, 1, 1), requires_grad=False)
+            sc.bias = nn.Parameter(h, requires_grad=False)
+            self.shortcut = sc.to(torch.bfloat16).to(memory_format=torch.channels_last)
+
+
+class _HeadGroup:
+    """All GradualStyleBlocks that read the same feature map (3 coarse / 4 middle / 11 fine heads): their convolution
+    chains have identical shapes, so every depth is ONE grouped launch (`groups` = heads) instead of one tiny launch per
+    head -- at 16 px and below a single head's convolution is a few CTAs streaming 4.7 MB of weights."""
+
+    def __init__(self, heads):
+        self.n = len(heads)
+        chains = [[m for m in h.convs.children() if isinstance(m, nn.Conv2d)] for h in heads]
+        self.depth = len(chains[0])
+        self.out_c = heads[0].out_c
+        self.layers = []
+        for d in range(self.depth):
+            w = torch.cat([_pack(c[d].weight.detach()) for c in chains], 0)                       # [n*9, Co, Ci]
+            b = torch.stack([c[d].bias.detach().float() for c in chains]).contiguous()           # [n, Co]
+            slope = torch.full_like(b, 0.01)                                                     # nn.LeakyReLU()
+            self.layers.append((w, b, slope, chains[0][d].out_channels))
+        self.lw = torch.stack([h.linear.weight.detach().float() * h.linear.scale for h in heads]).contiguous()       # [n, out, in]
+        self.lb = torch.stack([h.linear.bias.detach().float() * h.linear.lr_mul for h in heads]).contiguous()        # [n, out]
+
+    def __call__(self, x):
+        """x NHWC [B,S,S,512] -> [n, B, 512] fp32 latents"""
+        b = x.shape[0]
+        for d, (w, bias, slope, co) in enumerate(self.layers):
+            x, _ = K.conv3x3(x, w, co, transposed=3, bias=bias, prelu=slope, tag='encoder_conv', groups=self.n, in_shared=(d == 0))
+        x = x.reshape(self.n, b, self.out_c).float()
+        return torch.baddbmm(self.lb[:, None, :], x, self.lw.transpose(1, 2))
+
+
+class FastEncoder:
+    """Callable with the signature of Encoder4Editing.forward(x, return_feats=...) for bf16 channels_last inputs."""
+
+    @torch.no_grad()
+    def __init__(self, enc):
+        conv, bn, prelu = list(enc.input_layer.children())
+        g, h = _bn_affine(bn)
+        first = nn.Conv2d(3, conv.out_channels, 3, 1, 1, bias=True).to(conv.weight.device)
+        first.weight = nn.Parameter(conv.weight.detach().float() * g.reshape(-1, 1, 1, 1), requires_grad=False)
+        first.bias = nn.Parameter(h, requires_grad=False)
+        self.first = first.to(torch.bfloat16).to(memory_format=torch.channels_last)
+        self.first_slope = prelu.weight.detach().to(torch.bfloat16)
+        self.blocks = [_Block(b) for b in enc.body]
+        self.style_count, self.coarse_ind, self.middle_ind = enc.style_count, enc.coarse_ind, enc.middle_ind
+        styles = list(enc.styles)
+        self.head_groups = [_HeadGroup(styles[:self.coarse_ind]), _HeadGroup(styles[self.coarse_ind:self.middle_ind]),
+                            _HeadGroup(styles[self.middle_ind:])]
+        self.lat1 = nn.Conv2d(256, 512, 1).to(conv.weight.device)
+        self.lat1.load_state_dict(enc.latlayer1.state_dict())
+        self.lat2 = nn.Conv2d(128, 512, 1).to(conv.weight.device)
+        self.lat2.load_state_dict(enc.latlayer2.state_dict())
+        self.lat1 = self.lat1.to(torch.bfloat16).to(memory_format=torch.channels_last).requires_grad_(False)
+        self.lat2 = self.lat2.to(torch.bfloat16).to(memory_format=torch.channels_last).requires_grad_(False)
+        self.progressive_stage = enc.progressive_stage
+
+    @torch.no_grad()
+    def __call__(self, x, return_feats=False, **kwargs):
+        if not x.is_cuda:
+            raise RuntimeError('ood_gan_inversion_b200 is CUDA-only')
+        x = x.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        x0 = F.prelu(self.first(x), self.first_slope)                      # cuDNN: 3 input channels
+        cur = _nhwc(x0)
+        feats = [x0]
+        # t = BN1(cur) of the first block; afterwards every residual pass emits the next block's BN1 itself
+        _, t = K.se_residual(cur, bn_g=self.blocks[0].bn1[0], bn_h=self.blocks[0].bn1[1], want_out=False)
+        taps = {}
+        for i, blk in enumerate(self.blocks):
+            u, _ = K.conv3x3(t, blk.w1, blk.depth, prelu=blk.slope, tag='encoder_conv')
+            v, _ = K.conv3x3(u, blk.w2, blk.depth, transposed=3 if blk.stride == 2 else 0, bias=blk.b2, tag='encoder_conv')
+            gate = K.se_gate(K.in_stats(v), blk.se1, blk.se2)
+            if blk.shortcut is not None:
+                sc, ss = _nhwc(blk.shortcut(_nchw(cur))), 1
+            else:
+                sc, ss = cur, blk.stride                                   # MaxPool2d(1, s): strided read
+            nxt = self.blocks[i + 1].bn1 if i + 1 < len(self.blocks) else (None, None)
+            cur, t = K.se_residual(v, gate, sc, ss, nxt[0], nxt[1])
+            if i in (2, 6, 20, 23):
+                taps[i] = cur
+                feats.append(_nchw(cur))
+        c1, c2, c3 = taps[6], taps[20], taps[23]
+        # psp_encoders.py:199-214: w_i = w_0 + head_i(features); heads beyond the progressive stage repeat w_0
+        stage = self.progressive_stage.value
+        coarse = self.head_groups[0](c3)                                   # [3, B, 512]
+        w0 = coarse[0]
+        w = [w0] * self.style_count
+        for i in range(1, min(stage + 1, self.coarse_ind)):
+            w[i] = w0 + coarse[i]
+        if stage >= self.coarse_ind:
+            p2 = K.bicubic_up_add(c3, _nhwc(self.lat1(_nchw(c2))))
+            mid = self.head_groups[1](p2)
+            for i in range(self.coarse_ind, min(stage + 1, self.middle_ind)):
+                w[i] = w0 + mid[i - self.coarse_ind]
+        if stage >= self.middle_ind:
+            p1 = K.bicubic_up_add(p2, _nhwc(self.lat2(_nchw(c1))))
+            fine = self.head_groups[2](p1)
+            for i in range(self.middle_ind, min(stage + 1, self.style_count)):
+                w[i] = w0 + fine[i - self.middle_ind]
+        w = torch.stack(w, dim=1)
+        return (w, feats) if return_feats else w

@@ -212,14 +212,17 @@ def torgb_weight(w, s, scale=None):
 
 # ----------------------------------------------------------------------------------------------- convolution
 def conv3x3(x, weight, cout, transposed=False, impl=0, d=None, noise=None, noise_w=None, bias=None, s_next=None,
-            act=False, want_y=True, want_ys=False, out_f32=False, prelu=None, rgb=None):
+            act=False, want_y=True, want_ys=False, out_f32=False, prelu=None, rgb=None, tag=None, groups=1, in_shared=False):
     """x NHWC [B,H,W,Ci] pre-modulated; weight packed for `impl`.  Returns (y, ys) (None where not requested).
     rgb=(wrgb [B,3,Co], bias [3], skip NCHW fp32 or None, up taps): fused ToRGB, returns (y, ys, rgb_out NCHW fp32)."""
     _cuda(x, weight, d, noise, noise_w, bias, s_next)
     assert x.is_contiguous()
     b, h, w, cin = x.shape
-    transposed = int(transposed)      # 0 stride-1 | 1 stride-2 transposed | 2 stride-2 valid (data gradient of 1)
-    oh, ow = {0: (h, w), 1: (2 * h + 1, 2 * w + 1), 2: ((h - 1) // 2, (w - 1) // 2)}[transposed]
+    if in_shared:            # grouped form on a shared input: every group convolves the same [images, ...] tensor
+        b = b * groups
+    transposed = int(transposed)      # 0 stride-1 | 1 stride-2 transposed | 2 stride-2 valid (data gradient of 1) | 3 stride-2 pad-1
+    oh, ow = {0: (h, w), 1: (2 * h + 1, 2 * w + 1), 2: ((h - 1) // 2, (w - 1) // 2),
+              3: ((h - 1) // 2 + 1, (w - 1) // 2 + 1)}[transposed]
     y = torch.empty(b, oh, ow, cout, device=x.device, dtype=torch.float32 if out_f32 else x.dtype) if want_y else None
     ys = torch.empty(b, oh, ow, cout, device=x.device, dtype=x.dtype) if want_ys else None
     nbs = 0
@@ -228,6 +231,7 @@ def conv3x3(x, weight, cout, transposed=False, impl=0, d=None, noise=None, noise
         nbs = 0 if noise.shape[0] == 1 else oh * ow
     a = ConvArgs(_ptr(x), _ptr(weight), _ptr(y), _ptr(ys), _ptr(d), _ptr(noise), nbs, _ptr(noise_w), _ptr(bias), _ptr(s_next),
                  b, h, w, cin, cout, int(transposed), 2 if prelu is not None else int(act), impl, _dt(x), int(out_f32), _ptr(prelu))
+    a.groups, a.in_shared = int(groups), int(bool(in_shared))
     rgb_out = None
     if rgb is not None:
         wrgb, rbias, rskip, rtaps = rgb
@@ -236,7 +240,8 @@ def conv3x3(x, weight, cout, transposed=False, impl=0, d=None, noise=None, noise
         a.rgb_w, a.rgb_bias, a.rgb_skip, a.rgb_out = _ptr(wrgb), _ptr(rbias), _ptr(rskip), _ptr(rgb_out)
         a.rgb_taps = (C.c_float * 4)(*rtaps)
     # algorithmic work: 2*B*Co*Ci*9*H*W with H, W the INPUT size for the transposed form
-    with _timed('conv3x3_tc' if impl == 0 else 'conv3x3_simt', 2.0 * b * cout * cin * 9 * h * w):
+    px = h * w if transposed in (0, 1) else oh * ow
+    with _timed(tag or ('conv3x3_tc' if impl == 0 else 'conv3x3_simt'), 2.0 * b * cout * cin * 9 * px):
         check(_lib.lib().ood_conv3x3(C.byref(a), _stream()), 'conv3x3')
     if rgb is not None:
         return y, ys, rgb_out
@@ -419,6 +424,32 @@ def bicubic_up_add(x, y):
     out = torch.empty_like(y)
     check(_lib.lib().ood_bicubic_up_add(_ptr(x), _ptr(y), _ptr(out), b, h, w, H, W, c, _dt(x), _stream()), 'bicubic_up_add')
     return out
+
+
+def se_gate(stats, w1, w2):
+    """stats [B,C,2] (in_stats) -> gate [B,C] = sigmoid(w2 . relu(w1 . mean))   (SEModule, helpers.py:59-76)"""
+    _cuda(stats, w1, w2)
+    b, c, _ = stats.shape
+    gate = torch.empty(b, c, device=stats.device, dtype=torch.float32)
+    check(_lib.lib().ood_se_gate(_ptr(stats), _ptr(w1), _ptr(w2), _ptr(gate), b, c, w1.shape[0], _stream()), 'se_gate')
+    return gate
+
+
+def se_residual(v, gate=None, shortcut=None, sc_stride=1, bn_g=None, bn_h=None, want_out=True):
+    """v NHWC; out = v*gate + shortcut[:, ::s, ::s]; optionally t_next = out*bn_g + bn_h.  Returns (out, t_next)."""
+    _cuda(v, gate, shortcut, bn_g, bn_h)
+    assert v.is_contiguous() and (shortcut is None or (shortcut.is_contiguous() and shortcut.dtype == v.dtype))
+    b, h, w, c = v.shape
+    if shortcut is not None:
+        assert shortcut.shape[0] == b and shortcut.shape[3] == c and shortcut.shape[1] >= (h - 1) * sc_stride + 1, 'shortcut shape'
+        assert shortcut.shape[1] == h * sc_stride and shortcut.shape[2] == w * sc_stride, 'shortcut must be exactly stride x the output size'
+    out = torch.empty_like(v) if want_out else None
+    tn = torch.empty_like(v) if bn_g is not None else None
+    nbytes = b * h * w * c * _esize(v) * (1 + (shortcut is not None) + want_out + (tn is not None))
+    with _timed('se_residual', nbytes):
+        check(_lib.lib().ood_se_residual(_ptr(v), _ptr(gate), _ptr(shortcut), int(sc_stride), _ptr(bn_g), _ptr(bn_h), _ptr(out),
+                                         _ptr(tn), b, h, w, c, _dt(v), _stream()), 'se_residual')
+    return out, tn
 
 
 def mask_blend(fields, x, gen, want_alpha=True):

@@ -230,6 +230,43 @@ def test_conv3x3_tc_matches_simt_large():
     torch.testing.assert_close(t_tc, t_si, rtol=1e-3, atol=2e-2)
 
 
+@pytest.mark.parametrize('impl', [0, 1])
+@pytest.mark.parametrize('case', [dict(b=2, h=16, w=16, ci=64, co=64), dict(b=3, h=2, w=2, ci=128, co=128), dict(b=16, h=4, w=4, ci=64, co=256),
+                                  dict(b=1, h=9, w=13, ci=32, co=32), dict(b=2, h=64, w=64, ci=64, co=32)])
+def test_stride2_pad1_conv(impl, case):
+    """transposed=3: the encoder's stride-2 pad-1 3x3 conv (psp_encoders.py:41-48) with fused bias + LeakyReLU(0.01) (as PReLU)."""
+    b, h, w_, ci, co = case['b'], case['h'], case['w'], case['ci'], case['co']
+    dt = torch.bfloat16 if impl == 0 else torch.float32
+    x, w = rnd(b, ci, h, w_, seed=1).to(dt).float(), (0.2 * rnd(co, ci, 3, 3, seed=2)).to(dt).float()
+    bias, slope = rnd(co, seed=3), torch.full((co,), 0.01)
+    y, _ = K().conv3x3(nhwc(x, dt), K().pack_conv_weight(w.to(DEV), dt, impl == 1), co, transposed=3, impl=impl, bias=bias.to(DEV),
+                       prelu=slope.to(DEV))
+    ref = torch.nn.functional.leaky_relu(torch.nn.functional.conv2d(x.double(), w.double(), bias.double(), stride=2, padding=1), 0.01).float()
+    assert y.shape[1:3] == ((h - 1) // 2 + 1, (w_ - 1) // 2 + 1)
+    tol = dict(rtol=1e-4, atol=2e-3) if impl == 1 else dict(rtol=2e-2, atol=3e-2)
+    torch.testing.assert_close(nchw(y), ref, **tol)
+
+
+@pytest.mark.parametrize('case', [dict(g=3, b=2, h=8, ci=64, co=128, shared=True), dict(g=4, b=16, h=2, ci=128, co=256, shared=False),
+                                  dict(g=2, b=3, h=32, ci=64, co=64, shared=True), dict(g=5, b=2, h=4, ci=64, co=64, shared=False)])
+def test_grouped_stride2_conv(case):
+    """Grouped form of ood_conv3x3 (the encoder's style heads, one launch per depth): per-group weights / bias / slopes,
+    optionally one input shared by every group."""
+    g_, b, h, ci, co = case['g'], case['b'], case['h'], case['ci'], case['co']
+    dt = torch.bfloat16
+    xin = rnd(b if case['shared'] else g_ * b, ci, h, h, seed=1).to(dt).float()
+    ws = [(0.2 * rnd(co, ci, 3, 3, seed=10 + i)).to(dt).float() for i in range(g_)]
+    bias, slope = rnd(g_, co, seed=3), 0.05 + 0.2 * torch.rand(g_, co, generator=g(4))
+    wp = torch.cat([K().pack_conv_weight(w.to(DEV), dt, False) for w in ws], 0)
+    y, _ = K().conv3x3(nhwc(xin, dt), wp, co, transposed=3, bias=bias.to(DEV), prelu=slope.to(DEV), groups=g_, in_shared=case['shared'])
+    assert y.shape == (g_ * b, (h - 1) // 2 + 1, (h - 1) // 2 + 1, co)
+    for i in range(g_):
+        xi = xin if case['shared'] else xin[i * b:(i + 1) * b]
+        r = torch.nn.functional.conv2d(xi.double(), ws[i].double(), bias[i].double(), stride=2, padding=1)
+        ref = torch.where(r > 0, r, r * slope[i].double().reshape(1, -1, 1, 1)).float()
+        torch.testing.assert_close(nchw(y[i * b:(i + 1) * b]), ref, rtol=2e-2, atol=3e-2)
+
+
 def test_modulated_conv_identity_vs_oracle():
     # (W*s*d) (*) x == d . (W (*) (s . x)): the kernels' formulation against the reference's (oracle) formulation
     b, ci, co, h = 2, 64, 32, 12

@@ -239,6 +239,33 @@ def test_encoder_inference_copy_matches_module():
         torch.testing.assert_close(b, a, rtol=1e-3, atol=1e-3)
 
 
+def test_fast_encoder_matches_module():
+    """Encoder on this library's kernels (tcgen05 convs with fused PReLU / bias / LeakyReLU, SE gate, fused residual +
+    next-block BatchNorm) against the fp32 module tree it was built from; bf16 storage -> relative-L2 tolerance."""
+    from ood_gan_inversion_b200 import encoder_fast
+    from ood_gan_inversion_b200.encoder import Encoder4Editing
+    torch.manual_seed(0)
+    enc = Encoder4Editing(50, 'ir_se', {'stylegan_size': 1024}).to(DEV).eval()
+    for m in enc.modules():                                   # non-trivial running statistics
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.normal_(0, 0.1)
+            m.running_var.uniform_(0.8, 1.2)
+            m.weight.data.normal_(1, 0.1)
+            m.bias.data.normal_(0, 0.1)
+    fast = encoder_fast.FastEncoder(enc)
+    x = torch.randn(3, 3, 256, 256, device=DEV).clamp(-1, 1)
+    with torch.no_grad():
+        w0, f0 = enc(x, return_feats=True)
+    w1, f1 = fast(x, return_feats=True)
+    rel = lambda a, b: float((a.float() - b.float()).norm() / b.float().norm())
+    assert w1.shape == w0.shape and w1.dtype == torch.float32
+    assert rel(w1, w0) < 3e-2, rel(w1, w0)
+    assert len(f1) == len(f0)
+    for a, b in zip(f1, f0):
+        assert a.shape == b.shape
+        assert rel(a, b) < 3e-2, rel(a, b)
+
+
 def test_generator_z_space_truncation_and_mixing_vs_oracle():
     """Generator.forward's latent handling (model.py:501-538): mapping network, truncation, style mixing, return_latents."""
     m = sg()
