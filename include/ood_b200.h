@@ -95,6 +95,8 @@ int ood_pack_conv_weight(const float *w, void *out, int cout, int cin, int taps,
  *      transposed == 2: stride-2 valid conv, in [B,2h+1,2w+1,Ci] -> out [B,h,w,Co]: the data gradient of form 1 (autograd of model.py:255).
  *      transposed == 3: stride-2, pad-1 conv, out [B,(H-1)/2+1,(W-1)/2+1,Co]: the encoder's down-sampling convolutions
  *                       (src/ops/e4e/encoders/psp_encoders.py:41-48, helpers.py:488-491).
+ *      transposed == 4: 1x1 convolution, weight pack [1][Co][Ci] (bf16, K-major): lateral / feature convolutions
+ *                       (psp_encoders.py:153-154, e4e_arch.py feats_conv) and the per-tap projection consumed by ood_tap_sum.
  *      Epilogue (stride-1 only; any pointer may be NULL to skip that term):
  *          v  = acc * d[b,o] + noise_w * noise[b,y,x] + bias[o];  y = act ? lrelu(v,0.2)*sqrt2 : v
  *          out_y  = y            out_ys = y * s_next[b,o]
@@ -113,7 +115,7 @@ typedef struct {
     const float *bias;     /* [Co] or NULL */
     const float *s_next;   /* [B,Co]; required iff out_ys */
     int batch, h, w, cin, cout;
-    int transposed;        /* 0 stride-1 conv | 1 stride-2 transposed conv | 2 stride-2 valid conv (data gradient of 1) | 3 stride-2 pad-1 conv */
+    int transposed;        /* 0 stride-1 conv | 1 stride-2 transposed conv | 2 stride-2 valid conv (data gradient of 1) | 3 stride-2 pad-1 conv | 4 1x1 conv */
     int act;               /* 0 none | 1 leaky-ReLU(0.2)*sqrt2 | 2 PReLU(prelu_slope[o]) (AlignNet, shared-weight mode) */
     int impl;              /* 0 tcgen05 | 1 simt */
     int dtype;             /* storage type of in / out */
@@ -182,6 +184,13 @@ int ood_field_step(const float *z, const float *prev, const float *coarse, float
  *      x [B,h,w,C], y / out [B,H,W,C] (y may be NULL).  ATen's channels-last bicubic costs 40 ms per call at B=16. */
 int ood_bicubic_up_add(const void *x, const void *y, void *out, int batch, int h, int w, int H, int W, int channels,
                        int dtype, void *stream);
+
+/* ---- a11 (AlignNet head, SAMM/helpers.py:85-109 via bottleneck_IR e4e/encoders/helpers.py:426-448): a 3x3 convolution
+ *      2C -> 3 reads its 2C-channel input nine times for three outputs.  Instead ood_conv3x3(transposed = 4) projects every
+ *      pixel once onto the 27 (tap, colour) weights, proj [B,H,W,Cp] fp32 with channel 3*t + k (Cp >= 27), and
+ *          out[b,k,y,x] = sum_t proj[b, y + t/3 - 1, x + t%3 - 1, 3*t + k]        (zero outside the image)
+ *      gathers the nine shifted partial sums.  out fp32 NCHW [B,3,H,W]. */
+int ood_tap_sum(const float *proj, float *out, int batch, int h, int w, int cp, void *stream);
 
 /* ---- a13 (encoder trunk, e4e/encoders/helpers.py:59-76 SEModule, :476-501 bottleneck_IR_SE) on NHWC activations.
  *      ood_se_gate:     stats [B,C,2] from ood_in_stats (channel means) -> gate[b,c] = sigmoid(w2 . relu(w1 . mean[b,:]));

@@ -54,6 +54,7 @@ _SIGS = {
                    c_void_p], c_int),
     'ood_field_step': ([c_void_p, c_void_p, c_void_p, c_void_p, C.POINTER(c_float), c_float, c_int, c_int, c_int,
                         c_void_p], c_int),
+    'ood_tap_sum': ([c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p], c_int),
     'ood_se_gate': ([c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p], c_int),
     'ood_se_residual': ([c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                         c_int, c_void_p], c_int),

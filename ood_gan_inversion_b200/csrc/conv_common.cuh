@@ -42,6 +42,14 @@ static inline ConvGeom make_geom(int batch, int h, int w, int cin, int cout, int
                 p.dy[t] = ky; p.dx[t] = kx; p.wt[t] = t;
             }
         p.m_total = batch * p.oh * p.ow;
+    } else if (transposed == 4) {
+        // 1x1 convolution (one tap, no padding): the encoder's lateral / feature convolutions and the per-tap projection
+        // of the AlignNet's 2C -> 3 head (see ood_tap_sum)
+        g.OH = h; g.OW = w; g.sy = g.sx = 1; g.nphases = 1;
+        ConvPhase &p = g.ph[0];
+        p.oh = h; p.ow = w; p.py = p.px = 0; p.ntaps = 1;
+        p.dy[0] = p.dx[0] = 0; p.wt[0] = 0;
+        p.m_total = batch * h * w;
     } else if (transposed == 3) {
         // stride-2 pad-1 3x3 conv: out[y,x] = sum in[2y+ky-1, 2x+kx-1] * W[ky,kx] -- the down-sampling convolutions of the
         // E4E encoder (GradualStyleBlock psp_encoders.py:41-48, bottleneck_IR_SE helpers.py:488-491)

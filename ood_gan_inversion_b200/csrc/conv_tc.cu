@@ -30,6 +30,7 @@ struct TcParams {
     int isy, isx;                   // input stride (2 for the strided data-gradient form; the TMA map then carries elementStrides 2)
     int TW, TH, NB;                 // pixel patch of one M tile: NB*TH*TW == 128
     int nphases, n_tiles_n, total_tiles;
+    int wtaps;                      // taps per group in the weight pack (9, or 1 for the 1x1 form)
     int groups, gbatch, in_shared;  // grouped form: output image g*gbatch + i uses weights [g*9 + tap] and input image i (shared) or g*gbatch + i
     TcPhase ph[4];
     ConvEpilogue ep;
@@ -200,7 +201,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         mbar_expect_tx(&full[stage], Cfg::kStageBytes);
                         tma_load_4d(sA + stage * Cfg::kABytes, &tmA, &full[stage], kc * BK, tc.x0 * p.isx + P.dx[t], tc.y0 * p.isy + P.dy[t],
                                     p.in_shared ? tc.bl0 : tc.b0);
-                        tma_load_3d(sB + stage * Cfg::kBBytes, &tmB, &full[stage], kc * BK, tc.n0, P.wt[t] + tc.group * 9);
+                        tma_load_3d(sB + stage * Cfg::kBBytes, &tmB, &full[stage], kc * BK, tc.n0, P.wt[t] + tc.group * p.wtaps);
                         if (++stage == S) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -422,6 +423,7 @@ int conv3x3_tc(const ood_conv3x3_args &a, cudaStream_t st) {
     p.NB = TBM / (p.TW * p.TH);
     p.nphases = g.nphases;
     p.groups = groups; p.gbatch = a.batch / groups; p.in_shared = a.in_shared ? 1 : 0;
+    p.wtaps = a.transposed == 4 ? 1 : 9;
     int tiles = 0;
     for (;;) {
         p.n_tiles_n = a.cout / BN;
@@ -458,7 +460,7 @@ int conv3x3_tc(const ood_conv3x3_args &a, cudaStream_t st) {
         if (r != CUDA_SUCCESS) { set_error("conv3x3 tc: activation tensor map encode failed (%d)", (int)r); return OOD_ERR_CUDA; }
     }
     {
-        cuuint64_t dims[3] = {(cuuint64_t)a.cin, (cuuint64_t)a.cout, (cuuint64_t)(9 * groups)};
+        cuuint64_t dims[3] = {(cuuint64_t)a.cin, (cuuint64_t)a.cout, (cuuint64_t)(p.wtaps * groups)};
         cuuint64_t strides[2] = {(cuuint64_t)a.cin * 2, (cuuint64_t)a.cout * a.cin * 2};
         cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)BN, 1};
         cuuint32_t es[3] = {1, 1, 1};
@@ -489,7 +491,7 @@ extern "C" int ood_conv3x3(const ood_conv3x3_args *a, void *stream) {
     OOD_REQUIRE(a->out_y || a->out_ys || a->rgb_out, "conv3x3: no output requested");
     OOD_REQUIRE(!a->rgb_out || (a->rgb_w && a->rgb_bias && a->act == 1 && a->h % 2 == 0 && a->w % 2 == 0), "conv3x3: fused ToRGB needs rgb_w, rgb_bias, act=1 and even sizes");
     OOD_REQUIRE(!a->out_ys || a->s_next, "conv3x3: out_ys needs s_next");
-    OOD_REQUIRE(a->transposed >= 0 && a->transposed <= 3, "conv3x3: transposed must be 0, 1, 2 or 3");
+    OOD_REQUIRE(a->transposed >= 0 && a->transposed <= 4, "conv3x3: transposed must be 0..4");
     OOD_REQUIRE(a->transposed != 1 || (!a->out_ys && !a->act && !a->noise && !a->bias),
                 "conv3x3: the transposed form writes raw accumulators (the epilogue follows the blur)");
     OOD_REQUIRE(a->transposed != 2 || (a->h % 2 == 1 && a->w % 2 == 1 && a->h >= 3 && a->w >= 3 && !a->noise),

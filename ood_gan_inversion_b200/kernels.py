@@ -14,11 +14,14 @@ FIR_1331 = (1.0, 3.0, 3.0, 1.0)
 
 # ---- optional per-launch timing (bench.py roofline): CUDA events on the launching stream ------------------------
 _prof = None
+_prof_only = None
 
 
-def profile_begin():
-    global _prof
+def profile_begin(only=None):
+    """Start recording per-launch CUDA events; `only` restricts it to the named kernels (cheap enough for a timed region)."""
+    global _prof, _prof_only
     _prof = []
+    _prof_only = set(only) if only else None
 
 
 def profile_end():
@@ -39,12 +42,13 @@ class _timed:
         self.name, self.work = name, work
 
     def __enter__(self):
-        if _prof is not None:
+        self.on = _prof is not None and (_prof_only is None or self.name in _prof_only)
+        if self.on:
             self.e0, self.e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             self.e0.record()
 
     def __exit__(self, *exc):
-        if _prof is not None:
+        if self.on and _prof is not None:
             self.e1.record()
             _prof.append((self.name, self.e0, self.e1, self.work))
         return False
@@ -222,7 +226,7 @@ def conv3x3(x, weight, cout, transposed=False, impl=0, d=None, noise=None, noise
         b = b * groups
     transposed = int(transposed)      # 0 stride-1 | 1 stride-2 transposed | 2 stride-2 valid (data gradient of 1) | 3 stride-2 pad-1
     oh, ow = {0: (h, w), 1: (2 * h + 1, 2 * w + 1), 2: ((h - 1) // 2, (w - 1) // 2),
-              3: ((h - 1) // 2 + 1, (w - 1) // 2 + 1)}[transposed]
+              3: ((h - 1) // 2 + 1, (w - 1) // 2 + 1), 4: (h, w)}[transposed]
     y = torch.empty(b, oh, ow, cout, device=x.device, dtype=torch.float32 if out_f32 else x.dtype) if want_y else None
     ys = torch.empty(b, oh, ow, cout, device=x.device, dtype=x.dtype) if want_ys else None
     nbs = 0
@@ -241,7 +245,7 @@ def conv3x3(x, weight, cout, transposed=False, impl=0, d=None, noise=None, noise
         a.rgb_taps = (C.c_float * 4)(*rtaps)
     # algorithmic work: 2*B*Co*Ci*9*H*W with H, W the INPUT size for the transposed form
     px = h * w if transposed in (0, 1) else oh * ow
-    with _timed(tag or ('conv3x3_tc' if impl == 0 else 'conv3x3_simt'), 2.0 * b * cout * cin * 9 * px):
+    with _timed(tag or ('conv3x3_tc' if impl == 0 else 'conv3x3_simt'), 2.0 * b * cout * cin * (1 if transposed == 4 else 9) * px):
         check(_lib.lib().ood_conv3x3(C.byref(a), _stream()), 'conv3x3')
     if rgb is not None:
         return y, ys, rgb_out
@@ -423,6 +427,23 @@ def bicubic_up_add(x, y):
     _, H, W, _ = y.shape
     out = torch.empty_like(y)
     check(_lib.lib().ood_bicubic_up_add(_ptr(x), _ptr(y), _ptr(out), b, h, w, H, W, c, _dt(x), _stream()), 'bicubic_up_add')
+    return out
+
+
+def pack_conv1x1_weight(w, dtype, ci_major):
+    """w [Co,Ci] (or [Co,Ci,1,1]) -> the one-tap pack of ood_conv3x3(transposed=4): [1][Co][Ci] (tcgen05) / [1][Ci][Co] (simt)."""
+    w = w.reshape(w.shape[0], -1).float()
+    return (w.t() if ci_major else w).contiguous().to(dtype).unsqueeze(0)
+
+
+def tap_sum(proj):
+    """proj fp32 NHWC [B,H,W,Cp>=27] (channel 3*tap + colour) -> fp32 NCHW [B,3,H,W]: the nine shifted partial sums of a 3x3 conv."""
+    _cuda(proj)
+    assert proj.is_contiguous() and proj.dtype == torch.float32
+    b, h, w, cp = proj.shape
+    out = torch.empty(b, 3, h, w, device=proj.device, dtype=torch.float32)
+    with _timed('tap_sum', b * h * w * (27 + 3) * 4):
+        check(_lib.lib().ood_tap_sum(_ptr(proj), _ptr(out), b, h, w, cp, _stream()), 'tap_sum')
     return out
 
 

@@ -95,10 +95,13 @@ class AlignNet(nn.Module):
             with torch.no_grad():
                 dt, cim = sg._act_dtype(), sg.get_precision() == 'fp32'
                 g = sg._granule()
-                wc = sg._pad_dim(b1.res_layer[1].weight.detach().float(), 0, g).contiguous()       # 2C -> 3 (zero-padded rows)
+                # 2C -> 3 head as a per-pixel projection onto the 27 (tap, colour) weights (ood_tap_sum): row 3*t + k
+                wc = b1.res_layer[1].weight.detach().float()                                        # [3, 2C, 3, 3]
+                w27 = torch.zeros(32, wc.shape[1], device=wc.device)
+                w27[:27] = wc.permute(2, 3, 0, 1).reshape(27, -1)
                 pk = dict(wa=K.pack_conv_weight(b0.res_layer[1].weight.detach(), dt, cim),
                           wb=K.pack_conv_weight(b0.res_layer[3].weight.detach(), dt, cim),
-                          wc=K.pack_conv_weight(wc, dt, cim), cp=g,
+                          wc=K.pack_conv1x1_weight(w27, dt, cim), cp=32,
                           w1=b1.shortcut_layer[0].weight.detach().float().reshape(3, -1).contiguous())
             self._pk = (key, pk)
             hit = self._pk
@@ -118,8 +121,8 @@ class AlignNet(nn.Module):
         x, _ = K.conv3x3(x, pk['wb'], 2 * c, impl=impl)
         out0 = K.alignnet_res0(x, K.in_stats(x, None, eps), f(b0.res_layer[4].weight), f(b0.res_layer[4].bias), cur, enc, st6)
         x = K.in_apply(out0, K.in_stats(out0, None, eps), f(b1.res_layer[0].weight), f(b1.res_layer[0].bias))
-        x, _ = K.conv3x3(x, pk['wc'], pk['cp'], impl=impl, out_f32=True)
-        res = x[..., :3].permute(0, 3, 1, 2).float()
+        x, _ = K.conv3x3(x, pk['wc'], pk['cp'], transposed=4, impl=impl, out_f32=True)
+        res = K.tap_sum(x)
         zero = torch.zeros(3, device=cur.device)
         sc = K.torgb(out0, pk['w1'].unsqueeze(0).expand(b, -1, -1).contiguous(), zero)      # 1x1 conv 2C -> 3, fp32 NCHW
         with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):                     # 3-channel fp32 tail

@@ -267,6 +267,30 @@ def test_grouped_stride2_conv(case):
         torch.testing.assert_close(nchw(y[i * b:(i + 1) * b]), ref, rtol=2e-2, atol=3e-2)
 
 
+@pytest.mark.parametrize('impl', [0, 1])
+def test_conv1x1_and_tap_sum(impl):
+    """transposed=4 (1x1 form) + ood_tap_sum == a 3x3 pad-1 convolution to 3 channels (the AlignNet 2C -> 3 head)."""
+    b, ci, h, w_ = 2, 64, 11, 9
+    dt = torch.bfloat16 if impl == 0 else torch.float32
+    x, w = rnd(b, ci, h, w_, seed=1).to(dt).float(), (0.2 * rnd(3, ci, 3, 3, seed=2)).to(dt).float()
+    w27 = torch.zeros(32, ci)
+    w27[:27] = w.permute(2, 3, 0, 1).reshape(27, ci)
+    proj, _ = K().conv3x3(nhwc(x, dt), K().pack_conv1x1_weight(w27.to(DEV), dt, impl == 1), 32, transposed=4, impl=impl, out_f32=True)
+    assert proj.shape == (b, h, w_, 32) and proj.dtype == torch.float32
+    ref1 = torch.einsum('bchw,nc->bhwn', x.double(), w27.double()).float()
+    torch.testing.assert_close(proj.cpu(), ref1, rtol=1e-4, atol=2e-3)
+    out = K().tap_sum(proj)
+    ref = torch.nn.functional.conv2d(x.double(), w.double(), padding=1).float()
+    torch.testing.assert_close(out.cpu(), ref, rtol=1e-4, atol=5e-3)
+    # 1x1 conv with bias + PReLU epilogue, 256 output channels
+    w2, bias, slope = (0.2 * rnd(256, ci, seed=5)).to(dt).float(), rnd(256, seed=6), 0.1 + 0.1 * torch.rand(256, generator=g(7))
+    if impl == 0:
+        y, _ = K().conv3x3(nhwc(x, dt), K().pack_conv1x1_weight(w2.to(DEV), dt, False), 256, transposed=4, bias=bias.to(DEV), prelu=slope.to(DEV))
+        r = torch.einsum('bchw,nc->bnhw', x.double(), w2.double()) + bias.double().reshape(1, -1, 1, 1)
+        ref2 = torch.where(r > 0, r, r * slope.double().reshape(1, -1, 1, 1)).float()
+        torch.testing.assert_close(nchw(y), ref2, rtol=2e-2, atol=3e-2)
+
+
 def test_modulated_conv_identity_vs_oracle():
     # (W*s*d) (*) x == d . (W (*) (s . x)): the kernels' formulation against the reference's (oracle) formulation
     b, ci, co, h = 2, 64, 32, 12

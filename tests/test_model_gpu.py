@@ -297,3 +297,24 @@ def test_generator_z_space_truncation_and_mixing_vs_oracle():
     img3, _ = gen(ref_lat, input_is_tensor=True, input_is_latent=True, noise=noises)
     assert (img3 - ostyle.generator_forward(sdd, ref_lat, size, noise=noises)).abs().max() < 1e-3
     m.set_precision('bf16')
+
+
+def test_graphed_forward_replays_the_eager_result():
+    """ood_gan_inversion_b200.graphs.GraphedForward: a captured synthesis step replays bit-identically (fixed noise)."""
+    from ood_gan_inversion_b200.graphs import GraphedForward
+    m = sg()
+    m.set_precision('bf16')
+    size = 64
+    gen = m.Generator(size, 512, 8).to(DEV).eval()
+    gen.load_state_dict(ostyle.synthetic_generator_state(size, seed=5))
+    fn = lambda lat: gen(lat, input_is_tensor=True, input_is_latent=True, randomize_noise=False)[0]
+    lat1 = torch.randn(2, gen.n_latent, 512, generator=torch.Generator().manual_seed(1)).to(DEV)
+    lat2 = torch.randn(2, gen.n_latent, 512, generator=torch.Generator().manual_seed(2)).to(DEV)
+    with torch.no_grad():
+        ref1, ref2 = fn(lat1).clone(), fn(lat2).clone()
+    graphed = GraphedForward(fn, lat1)
+    out1 = graphed(lat1).clone()
+    out2 = graphed(lat2).clone()
+    assert torch.equal(out1, ref1) and torch.equal(out2, ref2)
+    with pytest.raises(ValueError):
+        graphed(lat1[:1])
