@@ -3,19 +3,11 @@
 // for the minor==1 form the Python wrapper issues; semantics follow upfirdn2d_native
 // (src/ops/op/upfirdn2d.py:160-193).  HBM-bound: every input element is staged once per tile in shared
 // memory (halo included), only taps that hit a real sample are visited, every parameter is generic.
-#include "common.cuh"
+#include "upfirdn_common.cuh"
 
 namespace ood {
 
-struct UpfirdnParams {
-    const void *in;
-    void *out;
-    const float *kernel;
-    int64_t planes;
-    int in_h, in_w, out_h, out_w;
-    int kh, kw, up_x, up_y, down_x, down_y, pad_x0, pad_y0;
-    int tiles_x, tiles_y, sih, siw;
-};
+int plane_fir(const UpfirdnParams &p, int pad_x1, int pad_y1, cudaStream_t st, int *handled);   // plane_fir.cu
 
 constexpr int kTOH = 32, kTOW = 64, kThreads = 256;
 
@@ -260,5 +252,10 @@ extern "C" int ood_upfirdn2d(const void *in, void *out, const float *kernel, int
     p.sih = ((kTOH - 1) * down_y + kh - 1) / up_y + 2;
     p.siw = ((kTOW - 1) * down_x + kw - 1) / up_x + 2;
     cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == OOD_F32) {      // wide fp32 planes: row-streaming cp.async kernel (plane_fir.cu)
+        int handled = 0;
+        const int rc = plane_fir(p, pad_x1, pad_y1, st, &handled);
+        if (handled) return rc;
+    }
     return dtype == OOD_F32 ? launch_upfirdn<float>(p, st) : launch_upfirdn<__nv_bfloat16>(p, st);
 }

@@ -54,6 +54,10 @@ def test_upfirdn2d_golden_cases(golden):
     dict(shape=(1, 2, 100, 130), up=1, down=1, pad=(2, 1), gain=1.0),     # multi-tile, ragged
     dict(shape=(1, 2, 19, 23), up=3, down=2, pad=(4, 3), gain=9.0),       # generic path
     dict(shape=(1, 1, 1, 1), up=2, down=1, pad=(2, 1), gain=4.0),         # smallest input
+    dict(shape=(2, 2, 131, 1025), up=1, down=1, pad=(1, 1), gain=4.0),    # wide planes: row-streaming kernel, odd width, 2+ strips
+    dict(shape=(1, 3, 300, 260), up=1, down=1, pad=(2, 1), gain=1.0),     # row-streaming blur, pad (2,1), one ragged strip
+    dict(shape=(1, 2, 140, 1100), up=1, down=2, pad=(1, 1), gain=1.0),    # row-streaming down2, ragged second strip
+    dict(shape=(2, 1, 70, 600), up=2, down=1, pad=(2, 1), gain=4.0),      # row-streaming up2 (polyphase), two strips
 ])
 @pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
 def test_upfirdn2d_vs_oracle(cfg, dtype):
