@@ -11,10 +11,32 @@
 
 namespace ood {
 
+// pixels per partial-sum block: ~two resident waves of long streaming blocks (see stat_chunk in alignnet.cu: the earlier
+// 512-pixel chunks paid the start-up / shared-memory-reduction tail once per 512 pixels)
 static inline int bwd_chunk_px(int64_t P, int batch) {
-    int c = 512;
-    while (c > 32 && (int64_t)batch * ((P + c - 1) / c) < 1024) c >>= 1;
-    return c;
+    const int64_t per_image = std::max<int64_t>(1, (int64_t)kNumSMs * 4 / batch);
+    return (int)std::max<int64_t>((P + per_image - 1) / per_image, 32);
+}
+
+// 16 bytes of T <-> N/2 fp32 pairs
+template <typename T> __device__ __forceinline__ void bw_load(const T *p, float2 *dst);
+template <> __device__ __forceinline__ void bw_load<float>(const float *p, float2 *dst) {
+    const float4 r = __ldg(reinterpret_cast<const float4 *>(p));
+    dst[0] = make_float2(r.x, r.y); dst[1] = make_float2(r.z, r.w);
+}
+template <> __device__ __forceinline__ void bw_load<__nv_bfloat16>(const __nv_bfloat16 *p, float2 *dst) {
+    const uint4 r = __ldg(reinterpret_cast<const uint4 *>(p));
+    dst[0] = unpack_bf16x2(r.x); dst[1] = unpack_bf16x2(r.y); dst[2] = unpack_bf16x2(r.z); dst[3] = unpack_bf16x2(r.w);
+}
+template <typename T> __device__ __forceinline__ void bw_store(T *p, const float2 *v);
+template <> __device__ __forceinline__ void bw_store<float>(float *p, const float2 *v) {
+    *reinterpret_cast<float4 *>(p) = make_float4(v[0].x, v[0].y, v[1].x, v[1].y);
+}
+template <> __device__ __forceinline__ void bw_store<__nv_bfloat16>(__nv_bfloat16 *p, const float2 *v) {
+    uint4 r;
+    r.x = pack_bf16x2(v[0].x, v[0].y); r.y = pack_bf16x2(v[1].x, v[1].y);
+    r.z = pack_bf16x2(v[2].x, v[2].y); r.w = pack_bf16x2(v[3].x, v[3].y);
+    *reinterpret_cast<uint4 *>(p) = r;
 }
 
 template <int N>
@@ -49,33 +71,45 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const T *__restrict__ gy, 
     const bool active = lane < lanes;
     const int b = blockIdx.y, chunk = blockIdx.x, c = vec * N;
     const float nw = (noise && noise_w) ? *noise_w : 0.f;
+    constexpr int N2 = N / 2;
     float acc[1][N];
-    float dreg[N], breg[N];
+    float2 acc2[N2], d2[N2], nb2[N2];              // nb2 = -bias
 #pragma unroll
-    for (int j = 0; j < N; ++j) {
-        acc[0][j] = 0.f;
-        dreg[j] = (active && d) ? d[(int64_t)b * C + c + j] : 1.f;
-        breg[j] = (active && bias) ? bias[c + j] : 0.f;
+    for (int j = 0; j < N2; ++j) {
+        acc2[j] = f2(0.f);
+        d2[j] = (active && d) ? make_float2(d[(int64_t)b * C + c + 2 * j], d[(int64_t)b * C + c + 2 * j + 1]) : f2(1.f);
+        nb2[j] = (active && bias) ? make_float2(-bias[c + 2 * j], -bias[c + 2 * j + 1]) : f2(0.f);
     }
     if (active) {
         const int64_t p0 = (int64_t)chunk * chunk_px, p1 = min(p0 + chunk_px, P);
+        const int64_t stride = (int64_t)lanes * C;
+        const T *gp = gy + ((int64_t)b * P + p0 + lane) * C + c, *yp = y + ((int64_t)b * P + p0 + lane) * C + c;
+        T *op = g + ((int64_t)b * P + p0 + lane) * C + c;
+        const float *np = noise ? noise + b * noise_bstride + p0 + lane : nullptr;
+        constexpr float kGp = kSqrt2, kGn = 0.2f * kSqrt2, kIp = 1.f / kSqrt2, kIn = 1.f / (0.2f * kSqrt2);
 #pragma unroll 2
         for (int64_t p = p0 + lane; p < p1; p += lanes) {
-            const int64_t off = ((int64_t)b * P + p) * C + c;
-            const Vec<T> gv = load_vec<T>(gy + off), yv = load_vec<T>(y + off);
-            const float nz = noise ? nw * __ldg(noise + b * noise_bstride + p) : 0.f;
-            Vec<T> o;
+            float2 gv[N2], yv[N2], o[N2];
+            bw_load<T>(gp, gv);
+            bw_load<T>(yp, yv);
+            const float2 nz = f2(np ? -nw * __ldg(np) : 0.f);
 #pragma unroll
-            for (int j = 0; j < N; ++j) {
-                const float gate = yv.v[j] > 0.f ? kSqrt2 : 0.2f * kSqrt2;
-                const float gvv = gv.v[j] * gate;
-                const float v = yv.v[j] / gate;                       // pre-activation
-                acc[0][j] = fmaf(gvv, v - nz - breg[j], acc[0][j]);   // = gv * acc * d
-                o.v[j] = gvv * dreg[j];
+            for (int j = 0; j < N2; ++j) {
+                // gate on the sign of the saved output; the pre-activation is y / gate (a multiply by the reciprocal)
+                const bool px = yv[j].x > 0.f, py = yv[j].y > 0.f;
+                const float2 gate = make_float2(px ? kGp : kGn, py ? kGp : kGn), inv = make_float2(px ? kIp : kIn, py ? kIp : kIn);
+                const float2 gvv = mul2(gv[j], gate);
+                const float2 v = fma2(yv[j], inv, add2(nz, nb2[j]));       // v - nz*nw - bias = acc * d
+                acc2[j] = fma2(gvv, v, acc2[j]);
+                o[j] = mul2(gvv, d2[j]);
             }
-            store_vec<T>(g + off, o);
+            bw_store<T>(op, o);
+            gp += stride; yp += stride; op += stride;
+            if (np) np += lanes;
         }
     }
+#pragma unroll
+    for (int j = 0; j < N2; ++j) { acc[0][2 * j] = acc2[j].x; acc[0][2 * j + 1] = acc2[j].y; }
     block_reduce_store<N>(acc, 1, red, partial + (((int64_t)b * nchunks + chunk) * C), C, cv, lanes, lane, vec, active);
 }
 
@@ -89,19 +123,27 @@ __global__ void __launch_bounds__(256) dot_partial_kernel(const T *__restrict__ 
     const int vec = threadIdx.x % cv, lane = threadIdx.x / cv;
     const bool active = lane < lanes;
     const int b = blockIdx.y, chunk = blockIdx.x, c = vec * N;
+    constexpr int N2 = N / 2;
     float acc[1][N];
+    float2 acc2[N2];
 #pragma unroll
-    for (int j = 0; j < N; ++j) acc[0][j] = 0.f;
+    for (int j = 0; j < N2; ++j) acc2[j] = f2(0.f);
     if (active) {
         const int64_t p0 = (int64_t)chunk * chunk_px, p1 = min(p0 + chunk_px, P);
+        const int64_t stride = (int64_t)lanes * C;
+        const T *ap = a + ((int64_t)b * P + p0 + lane) * C + c, *bp = bb + ((int64_t)b * P + p0 + lane) * C + c;
 #pragma unroll 4
         for (int64_t p = p0 + lane; p < p1; p += lanes) {
-            const int64_t off = ((int64_t)b * P + p) * C + c;
-            const Vec<T> av = load_vec<T>(a + off), bv = load_vec<T>(bb + off);
+            float2 av[N2], bv[N2];
+            bw_load<T>(ap, av);
+            bw_load<T>(bp, bv);
 #pragma unroll
-            for (int j = 0; j < N; ++j) acc[0][j] = fmaf(av.v[j], bv.v[j], acc[0][j]);
+            for (int j = 0; j < N2; ++j) acc2[j] = fma2(av[j], bv[j], acc2[j]);
+            ap += stride; bp += stride;
         }
     }
+#pragma unroll
+    for (int j = 0; j < N2; ++j) { acc[0][2 * j] = acc2[j].x; acc[0][2 * j + 1] = acc2[j].y; }
     block_reduce_store<N>(acc, 1, red, partial + (((int64_t)b * nchunks + chunk) * C), C, cv, lanes, lane, vec, active);
 }
 
