@@ -197,12 +197,13 @@ int ood_tap_sum(const float *proj, float *out, int batch, int h, int w, int cp, 
  *                       w1 [C/r, C], w2 [C, C/r] fp32 (the two bias-free 1x1 convolutions).
  *      ood_se_residual: out = v * gate[b,c] + shortcut   (shortcut [B, h*s, w*s, C] read at stride s = 1 | 2 -- MaxPool2d(1, s) --
  *                       or NULL; gate NULL = 1), and, when t_next is given, t_next = out * bn_g[c] + bn_h[c]: the next
- *                       block's eval-mode BatchNorm.  Either output may be NULL. */
+ *                       block's eval-mode BatchNorm.  Either output may be NULL.  With dtype OOD_BF16, shortcut_f32 / out_f32 = 1
+ *                       read the shortcut / write `out` as fp32: the bf16 path keeps the residual stream itself in fp32. */
 int ood_se_gate(const float *stats, const float *w1, const float *w2, float *gate, int batch, int channels, int reduced,
                 void *stream);
 int ood_se_residual(const void *v, const float *gate, const void *shortcut, int sc_stride, const float *bn_g,
                     const float *bn_h, void *out, void *t_next, int batch, int h, int w, int channels, int dtype,
-                    void *stream);
+                    int shortcut_f32, int out_f32, void *stream);
 
 /* ---- a14. backward of the synthesis path for optimisation-based inversion (autograd through model.py:233-372; weights frozen).
  *      ood_act_bwd : gv = gy*sqrt2*(y>0 ? 1 : 0.2) (gate on the saved OUTPUT, fused_bias_act_kernel.cu:36-47);  g = gv*d[b,c];

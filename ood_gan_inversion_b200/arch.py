@@ -191,6 +191,20 @@ class ood_faceGAN_e4e(nn.Module):
                     w, feats = self.encoder(small, return_feats=True)
         return w.float(), feats
 
+    def _feats_conv_nhwc(self, i, feat):
+        """feats_conv[i] (1x1 convolution + bias, e4e_arch.py:109-113) on the tcgen05 1x1 form; NCHW view of an NHWC result."""
+        conv = self.feats_conv[i]
+        key = (conv.weight.device, conv.weight._version, conv.bias._version)
+        cache = self.__dict__.setdefault('_fc_cache', {})
+        if cache.get(i, (None,))[0] != key:
+            with torch.no_grad():
+                cache[i] = (key, K.pack_conv1x1_weight(conv.weight.detach(), torch.bfloat16, False), conv.bias.detach().float().contiguous())
+        _, w, b = cache[i]
+        with torch.no_grad():
+            x = feat.to(torch.bfloat16).permute(0, 2, 3, 1).contiguous()
+            y, _ = K.conv3x3(x, w, conv.out_channels, transposed=4, bias=b, tag='encoder_conv')
+        return y.permute(0, 3, 1, 2)
+
     def forward(self, x, **kwargs):
         if kwargs.get('random_gen', False):
             return self.random_gen(batch_size=kwargs.get('batch_size', 1), gen=kwargs.get('gen', True))
@@ -207,9 +221,11 @@ class ood_faceGAN_e4e(nn.Module):
         if self.modulation is None:
             out, _ = self.generator(lats, input_is_tensor=True, input_is_latent=True)
             return out, lats
-        with torch.no_grad(), torch.backends.cudnn.flags(enabled=True, allow_tf32=False), \
-                torch.autocast('cuda', dtype=torch.bfloat16, enabled=bf16):
-            self.feats = [self.feats_conv[i](feats[i]) for i in range(4)]
+        if bf16:
+            self.feats = [self._feats_conv_nhwc(i, feats[i]) for i in range(4)]
+        else:
+            with torch.no_grad(), torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+                self.feats = [self.feats_conv[i](feats[i]) for i in range(4)]
         self.lats = lats
         self.aligns = {}
         conditions = self.feats2condition(self.feats)

@@ -55,10 +55,13 @@ template <> __device__ __forceinline__ void enc_store<__nv_bfloat16>(__nv_bfloat
 }
 
 // A thread owns one 16-byte channel vector and walks down a chunk of pixels (coefficients in registers).
-template <typename T>
+// SF / OF: the shortcut / `out` are fp32 although the activations are T -- the bf16 path keeps the RESIDUAL STREAM in
+// fp32 (24 blocks of "round the sum to bf16" cost the pipeline 6 dB of PSNR and half of its max-abs budget), while the
+// convolution inputs (t_next) and the residual branch (v) stay bf16.
+template <typename T, bool SF, bool OF>
 __global__ void __launch_bounds__(256) se_residual_kernel(const T *__restrict__ v, const float *__restrict__ gate,
-                                                           const T *__restrict__ sc, int ss, const float *__restrict__ bn_g,
-                                                           const float *__restrict__ bn_h, T *__restrict__ out,
+                                                           const void *__restrict__ sc_, int ss, const float *__restrict__ bn_g,
+                                                           const float *__restrict__ bn_h, void *__restrict__ out_,
                                                            T *__restrict__ tn, int H, int W, int C, int64_t chunk) {
     constexpr int N = Vec<T>::N, N2 = N / 2;
     const int b = blockIdx.y;
@@ -82,21 +85,33 @@ __global__ void __launch_bounds__(256) se_residual_kernel(const T *__restrict__ 
         const int64_t off = ((int64_t)b * P + p) * C + c;
         float2 x[N2];
         enc_load<T>(v + off, x);
-        if (sc) {
+        if (sc_) {
             int64_t soff = off;
             if (ss != 1) {
                 const int y = (int)(p / W), xx = (int)(p - (int64_t)y * W);
                 soff = (((int64_t)b * H * ss + (int64_t)y * ss) * Ws + (int64_t)xx * ss) * C + c;
             }
             float2 s[N2];
-            enc_load<T>(sc + soff, s);
+            if (SF) {
+#pragma unroll
+                for (int q = 0; q < N / 4; ++q) enc_load<float>((const float *)sc_ + soff + 4 * q, s + 2 * q);
+            } else {
+                enc_load<T>((const T *)sc_ + soff, s);
+            }
 #pragma unroll
             for (int j = 0; j < N2; ++j) x[j] = fma2(x[j], g[j], s[j]);
         } else {
 #pragma unroll
             for (int j = 0; j < N2; ++j) x[j] = mul2(x[j], g[j]);
         }
-        if (out) enc_store<T>(out + off, x);
+        if (out_) {
+            if (OF) {
+#pragma unroll
+                for (int q = 0; q < N / 4; ++q) enc_store<float>((float *)out_ + off + 4 * q, x + 2 * q);
+            } else {
+                enc_store<T>((T *)out_ + off, x);
+            }
+        }
         if (tn) {
 #pragma unroll
             for (int j = 0; j < N2; ++j) x[j] = fma2(x[j], bg[j], bh[j]);
@@ -148,7 +163,7 @@ extern "C" int ood_se_gate(const float *stats, const float *w1, const float *w2,
 
 extern "C" int ood_se_residual(const void *v, const float *gate, const void *shortcut, int sc_stride, const float *bn_g,
                                const float *bn_h, void *out, void *t_next, int batch, int h, int w, int channels, int dtype,
-                               void *stream) {
+                               int shortcut_f32, int out_f32, void *stream) {
     using namespace ood;
     OOD_REQUIRE(v && (out || t_next) && batch > 0 && batch <= 65535 && h > 0 && w > 0, "se_residual: bad arguments");
     OOD_REQUIRE(dtype == OOD_F32 || dtype == OOD_BF16, "se_residual: bad dtype");
@@ -163,9 +178,17 @@ extern "C" int ood_se_residual(const void *v, const float *gate, const void *sho
     chunk = (chunk + lanes - 1) / lanes * lanes;
     dim3 grid((unsigned)((P + chunk - 1) / chunk), batch);
     cudaStream_t st = (cudaStream_t)stream;
-    if (dtype == OOD_F32)
-        se_residual_kernel<float><<<grid, 256, 0, st>>>((const float *)v, gate, (const float *)shortcut, sc_stride, bn_g, bn_h, (float *)out, (float *)t_next, h, w, channels, chunk);
-    else
-        se_residual_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16 *)v, gate, (const __nv_bfloat16 *)shortcut, sc_stride, bn_g, bn_h, (__nv_bfloat16 *)out, (__nv_bfloat16 *)t_next, h, w, channels, chunk);
+    if (dtype == OOD_F32) {
+        se_residual_kernel<float, false, false><<<grid, 256, 0, st>>>((const float *)v, gate, shortcut, sc_stride, bn_g, bn_h, out, (float *)t_next, h, w, channels, chunk);
+    } else {
+        const __nv_bfloat16 *vv = (const __nv_bfloat16 *)v;
+        __nv_bfloat16 *tn = (__nv_bfloat16 *)t_next;
+#define OOD_SE(SF, OF) se_residual_kernel<__nv_bfloat16, SF, OF><<<grid, 256, 0, st>>>(vv, gate, shortcut, sc_stride, bn_g, bn_h, out, tn, h, w, channels, chunk)
+        if (shortcut_f32 && out_f32) OOD_SE(true, true);
+        else if (shortcut_f32) OOD_SE(true, false);
+        else if (out_f32) OOD_SE(false, true);
+        else OOD_SE(false, false);
+#undef OOD_SE
+    }
     return check_launch("se_residual");
 }

@@ -4,8 +4,9 @@ Reference module: src/ops/e4e/encoders/psp_encoders.py:34-56,125-216 and helpers
 e4e_arch.py:256-258).  The trunk's 48 stride-1 / stride-2 3x3 convolutions and the 98 stride-2 convolutions of the 18
 GradualStyleBlocks run on the tcgen05 implicit-GEMM kernel (`ood_conv3x3`, forms 0 and 3) with their PReLU / folded
 BatchNorm bias / LeakyReLU fused into the epilogue; the squeeze-excite gate and the residual sum (which also emits the
-next block's BatchNorm) are `ood_se_gate` / `ood_se_residual`.  What stays cuDNN: the 3->64 input convolution, the three
-1x1 stride-2 shortcut convolutions and the two 1x1 lateral convolutions.
+next block's BatchNorm) are `ood_se_gate` / `ood_se_residual`; the 3->64 input convolution runs with its input channels
+zero-padded to 32, the lateral 1x1 convolutions on the 1x1 form; the residual stream is kept in fp32.  What stays cuDNN: the
+three 1x1 stride-2 shortcut convolutions.
 
 Built from (and numerically checked against) `encoder.Encoder4Editing`; eval-mode BatchNorms are folded in fp32.
 """
@@ -93,33 +94,38 @@ class FastEncoder:
     def __init__(self, enc):
         conv, bn, prelu = list(enc.input_layer.children())
         g, h = _bn_affine(bn)
-        first = nn.Conv2d(3, conv.out_channels, 3, 1, 1, bias=True).to(conv.weight.device)
-        first.weight = nn.Parameter(conv.weight.detach().float() * g.reshape(-1, 1, 1, 1), requires_grad=False)
-        first.bias = nn.Parameter(h, requires_grad=False)
-        self.first = first.to(torch.bfloat16).to(memory_format=torch.channels_last)
-        self.first_slope = prelu.weight.detach().to(torch.bfloat16)
+        # input layer (3 -> 64, BatchNorm folded, PReLU in the epilogue) on the tcgen05 kernel: input channels zero-padded to 32
+        w0 = torch.zeros(conv.out_channels, 32, 3, 3, device=conv.weight.device)
+        w0[:, :3] = conv.weight.detach().float() * g.reshape(-1, 1, 1, 1)
+        self.first_w, self.first_b, self.first_c = _pack(w0), h, conv.out_channels
+        self.first_slope = prelu.weight.detach().float().contiguous()
         self.blocks = [_Block(b) for b in enc.body]
         self.style_count, self.coarse_ind, self.middle_ind = enc.style_count, enc.coarse_ind, enc.middle_ind
         styles = list(enc.styles)
         self.head_groups = [_HeadGroup(styles[:self.coarse_ind]), _HeadGroup(styles[self.coarse_ind:self.middle_ind]),
                             _HeadGroup(styles[self.middle_ind:])]
-        self.lat1 = nn.Conv2d(256, 512, 1).to(conv.weight.device)
-        self.lat1.load_state_dict(enc.latlayer1.state_dict())
-        self.lat2 = nn.Conv2d(128, 512, 1).to(conv.weight.device)
-        self.lat2.load_state_dict(enc.latlayer2.state_dict())
-        self.lat1 = self.lat1.to(torch.bfloat16).to(memory_format=torch.channels_last).requires_grad_(False)
-        self.lat2 = self.lat2.to(torch.bfloat16).to(memory_format=torch.channels_last).requires_grad_(False)
+        self.lat = []                                        # lateral 1x1 convolutions (bias in the epilogue)
+        for lat in (enc.latlayer1, enc.latlayer2):
+            self.lat.append((K.pack_conv1x1_weight(lat.weight.detach(), torch.bfloat16, False), lat.bias.detach().float().contiguous(),
+                             lat.out_channels))
         self.progressive_stage = enc.progressive_stage
+
+    def _lateral(self, i, x):
+        w, b, co = self.lat[i]
+        return K.conv3x3(x, w, co, transposed=4, bias=b, tag='encoder_conv')[0]
 
     @torch.no_grad()
     def __call__(self, x, return_feats=False, **kwargs):
         if not x.is_cuda:
             raise RuntimeError('ood_gan_inversion_b200 is CUDA-only')
-        x = x.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
-        x0 = F.prelu(self.first(x), self.first_slope)                      # cuDNN: 3 input channels
-        cur = _nhwc(x0)
-        feats = [x0]
-        # t = BN1(cur) of the first block; afterwards every residual pass emits the next block's BN1 itself
+        xp = torch.zeros(x.shape[0], x.shape[2], x.shape[3], 32, device=x.device, dtype=torch.bfloat16)
+        xp[..., :3] = x.permute(0, 2, 3, 1)
+        x0, _ = K.conv3x3(xp, self.first_w, self.first_c, bias=self.first_b, prelu=self.first_slope, tag='encoder_conv')
+        feats = [_nchw(x0)]
+        # The residual stream `cur` is fp32 from the first block on (out_f32): rounding the running sum to bf16 after each of
+        # the 24 blocks was the largest single error source of the bf16 pipeline (alpha error 1.2e-2 -> 0.5e-2 without it).
+        # t = BN1(cur) of the first block; afterwards every residual pass emits the next block's BN1 itself.
+        cur = x0
         _, t = K.se_residual(cur, bn_g=self.blocks[0].bn1[0], bn_h=self.blocks[0].bn1[1], want_out=False)
         taps = {}
         for i, blk in enumerate(self.blocks):
@@ -127,14 +133,14 @@ class FastEncoder:
             v, _ = K.conv3x3(u, blk.w2, blk.depth, transposed=3 if blk.stride == 2 else 0, bias=blk.b2, tag='encoder_conv')
             gate = K.se_gate(K.in_stats(v), blk.se1, blk.se2)
             if blk.shortcut is not None:
-                sc, ss = _nhwc(blk.shortcut(_nchw(cur))), 1
+                sc, ss = _nhwc(blk.shortcut(_nchw(cur.to(torch.bfloat16)))), 1
             else:
                 sc, ss = cur, blk.stride                                   # MaxPool2d(1, s): strided read
             nxt = self.blocks[i + 1].bn1 if i + 1 < len(self.blocks) else (None, None)
-            cur, t = K.se_residual(v, gate, sc, ss, nxt[0], nxt[1])
+            cur, t = K.se_residual(v, gate, sc, ss, nxt[0], nxt[1], out_f32=True)
             if i in (2, 6, 20, 23):
-                taps[i] = cur
-                feats.append(_nchw(cur))
+                taps[i] = cur.to(torch.bfloat16)
+                feats.append(_nchw(taps[i]))
         c1, c2, c3 = taps[6], taps[20], taps[23]
         # psp_encoders.py:199-214: w_i = w_0 + head_i(features); heads beyond the progressive stage repeat w_0
         stage = self.progressive_stage.value
@@ -144,12 +150,12 @@ class FastEncoder:
         for i in range(1, min(stage + 1, self.coarse_ind)):
             w[i] = w0 + coarse[i]
         if stage >= self.coarse_ind:
-            p2 = K.bicubic_up_add(c3, _nhwc(self.lat1(_nchw(c2))))
+            p2 = K.bicubic_up_add(c3, self._lateral(0, c2))
             mid = self.head_groups[1](p2)
             for i in range(self.coarse_ind, min(stage + 1, self.middle_ind)):
                 w[i] = w0 + mid[i - self.coarse_ind]
         if stage >= self.middle_ind:
-            p1 = K.bicubic_up_add(p2, _nhwc(self.lat2(_nchw(c1))))
+            p1 = K.bicubic_up_add(p2, self._lateral(1, c1))
             fine = self.head_groups[2](p1)
             for i in range(self.middle_ind, min(stage + 1, self.style_count)):
                 w[i] = w0 + fine[i - self.middle_ind]

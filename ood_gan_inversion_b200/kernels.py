@@ -456,20 +456,25 @@ def se_gate(stats, w1, w2):
     return gate
 
 
-def se_residual(v, gate=None, shortcut=None, sc_stride=1, bn_g=None, bn_h=None, want_out=True):
-    """v NHWC; out = v*gate + shortcut[:, ::s, ::s]; optionally t_next = out*bn_g + bn_h.  Returns (out, t_next)."""
+def se_residual(v, gate=None, shortcut=None, sc_stride=1, bn_g=None, bn_h=None, want_out=True, out_f32=False):
+    """v NHWC; out = v*gate + shortcut[:, ::s, ::s]; optionally t_next = out*bn_g + bn_h.  Returns (out, t_next).
+    With bf16 activations the shortcut may be fp32 and `out` can be requested in fp32 (fp32 residual stream)."""
     _cuda(v, gate, shortcut, bn_g, bn_h)
-    assert v.is_contiguous() and (shortcut is None or (shortcut.is_contiguous() and shortcut.dtype == v.dtype))
+    assert v.is_contiguous() and (shortcut is None or shortcut.is_contiguous())
     b, h, w, c = v.shape
+    sc_f32 = shortcut is not None and shortcut.dtype == torch.float32 and v.dtype != torch.float32
     if shortcut is not None:
-        assert shortcut.shape[0] == b and shortcut.shape[3] == c and shortcut.shape[1] >= (h - 1) * sc_stride + 1, 'shortcut shape'
-        assert shortcut.shape[1] == h * sc_stride and shortcut.shape[2] == w * sc_stride, 'shortcut must be exactly stride x the output size'
-    out = torch.empty_like(v) if want_out else None
+        assert shortcut.dtype in (v.dtype, torch.float32)
+        assert shortcut.shape == (b, h * sc_stride, w * sc_stride, c), 'shortcut must be exactly stride x the output size'
+    out_f32 = bool(out_f32) and v.dtype != torch.float32
+    out = torch.empty(v.shape, device=v.device, dtype=torch.float32 if out_f32 else v.dtype) if want_out else None
     tn = torch.empty_like(v) if bn_g is not None else None
-    nbytes = b * h * w * c * _esize(v) * (1 + (shortcut is not None) + want_out + (tn is not None))
+    es = _esize(v)
+    nbytes = b * h * w * c * (es + (0 if shortcut is None else (4 if sc_f32 else es)) + (0 if out is None else (4 if out_f32 else es)) +
+                              (0 if tn is None else es))
     with _timed('se_residual', nbytes):
         check(_lib.lib().ood_se_residual(_ptr(v), _ptr(gate), _ptr(shortcut), int(sc_stride), _ptr(bn_g), _ptr(bn_h), _ptr(out),
-                                         _ptr(tn), b, h, w, c, _dt(v), _stream()), 'se_residual')
+                                         _ptr(tn), b, h, w, c, _dt(v), int(sc_f32), int(out_f32), _stream()), 'se_residual')
     return out, tn
 
 
