@@ -178,7 +178,17 @@ int ood_torgb(const void *y, const float *wrgb, const float *bias, const float *
  *      coarse != NULL (last cycle of a finer level): acc2 = clip(PRM(bicubic_up(coarse2), acc2),0,1)
  *      PRM(x,y) = y*x + x*(1-x).  coarse is [B,3,Rc,Rc]; bicubic align_corners=True (helpers.py:69-70). */
 int ood_field_step(const float *z, const float *prev, const float *coarse, float *acc, const float *taps_host,
-                   float scale, int batch, int r, int rc, void *stream);
+                   float scale, int batch, int r, int rc, const float *z2, const float *coef, void *stream);
+/*      z2 / coef [B,3,3] (both or neither): the pre-activation field is z*coef[b,ch,0] + z2*coef[b,ch,1] + coef[b,ch,2].
+ *
+ *      ood_alignnet_tail (bottleneck_IR(2C -> 3) tail, e4e/encoders/helpers.py:426-448 inside SAMM/helpers.py:97-101):
+ *      r2 = conv3x3(PReLU(res; slope[3]); conv_w [3,3,3,3], pad 1), and coef such that
+ *          InstanceNorm(r2; in_res_w, in_res_b) + InstanceNorm(shortcut; in_sc_w, in_sc_b) = r2*coef[..0] + shortcut*coef[..1] + coef[..2]
+ *      (biased variance, eps) -- feed (z = r2, z2 = shortcut, coef) to ood_field_step.  res / shortcut / r2 fp32 [B,3,R,R]. */
+int64_t ood_alignnet_tail_workspace(int batch, int r);
+int ood_alignnet_tail(const float *res, const float *shortcut, const float *prelu_slope, const float *conv_w,
+                      const float *in_res_w, const float *in_res_b, const float *in_sc_w, const float *in_sc_b, float eps,
+                      float *r2, float *workspace, float *coef, int batch, int r, void *stream);
 
 /* ---- a13 (encoder FPN merge, e4e/encoders/helpers.py:504-521): out = bicubic_up(x, align_corners=True) + y on NHWC.
  *      x [B,h,w,C], y / out [B,H,W,C] (y may be NULL).  ATen's channels-last bicubic costs 40 ms per call at B=16. */

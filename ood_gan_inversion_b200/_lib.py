@@ -52,8 +52,10 @@ _SIGS = {
     'ood_torgb_weight': ([c_void_p, c_void_p, c_void_p, c_float, c_int, c_int, c_void_p], c_int),
     'ood_torgb': ([c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, C.POINTER(c_float), c_int, c_int, c_int, c_int, c_int,
                    c_void_p], c_int),
-    'ood_field_step': ([c_void_p, c_void_p, c_void_p, c_void_p, C.POINTER(c_float), c_float, c_int, c_int, c_int,
-                        c_void_p], c_int),
+    'ood_field_step': ([c_void_p, c_void_p, c_void_p, c_void_p, C.POINTER(c_float), c_float, c_int, c_int, c_int, c_void_p, c_void_p,
+                       c_void_p], c_int),
+    'ood_alignnet_tail_workspace': ([c_int, c_int], c_i64),
+    'ood_alignnet_tail': ([c_void_p] * 8 + [c_float, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p], c_int),
     'ood_tap_sum': ([c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p], c_int),
     'ood_se_gate': ([c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p], c_int),
     'ood_se_residual': ([c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,

@@ -36,14 +36,17 @@ __device__ float bicubic_ac(const float *__restrict__ src, int rc, int r, int y,
     return acc;
 }
 
+// z2 / coef (optional): the field is z*coef[b][ch][0] + z2*coef[b][ch][1] + coef[b][ch][2] -- the two instance norms and the
+// residual sum that end the AlignNet (ood_alignnet_tail) folded into this kernel's load.
 __global__ void __launch_bounds__(FT * FT) field_step_kernel(const float *__restrict__ z, const float *__restrict__ prev,
                                                               const float *__restrict__ coarse, float *__restrict__ acc,
                                                               float k0, float k1, float k2, float k3, float scale, int R,
-                                                              int Rc) {
+                                                              int Rc, const float *__restrict__ z2, const float *__restrict__ coef) {
     __shared__ float sa[3][FT + 3][FT + 4];
     const int b = blockIdx.z;
     const int y0 = blockIdx.y * FT, x0 = blockIdx.x * FT;
     const float *zb = z + (int64_t)b * 3 * R * R;
+    const float *z2b = z2 ? z2 + (int64_t)b * 3 * R * R : nullptr;
     for (int i = threadIdx.x; i < 3 * (FT + 3) * (FT + 3); i += FT * FT) {
         const int ch = i / ((FT + 3) * (FT + 3));
         const int r = i % ((FT + 3) * (FT + 3));
@@ -51,7 +54,11 @@ __global__ void __launch_bounds__(FT * FT) field_step_kernel(const float *__rest
         const int y = y0 + ty - 2, x = x0 + tx - 2;
         float v = 0.f;
         if (y >= 0 && y < R && x >= 0 && x < R) {
-            const float t = zb[((int64_t)ch * R + y) * R + x];
+            float t = zb[((int64_t)ch * R + y) * R + x];
+            if (z2b) {
+                const float *cf = coef + ((int64_t)b * 3 + ch) * 3;
+                t = fmaf(t, cf[0], fmaf(z2b[((int64_t)ch * R + y) * R + x], cf[1], cf[2]));
+            }
             v = (ch < 2) ? tanhf(t) * scale : 1.f / (1.f + expf(-t));
         }
         sa[ch][ty][tx] = v;
@@ -110,6 +117,94 @@ template <> __device__ __forceinline__ void wm_store<__nv_bfloat16>(__nv_bfloat1
     r.x = pack_bf16x2(v[0].x, v[0].y); r.y = pack_bf16x2(v[1].x, v[1].y);
     r.z = pack_bf16x2(v[2].x, v[2].y); r.w = pack_bf16x2(v[3].x, v[3].y);
     *reinterpret_cast<uint4 *>(p) = r;
+}
+
+// ------------------------------------------------------------------ AlignNet tail (3-channel fp32)
+// bottleneck_IR(2C -> 3) ends with  PReLU(3) -> conv3x3(3 -> 3) -> InstanceNorm(3)  on the residual branch and
+// InstanceNorm(3) on the 1x1 shortcut (e4e/encoders/helpers.py:426-448 inside SAMM/helpers.py:97-101).  One pass computes
+// r2 = conv(PReLU(res)) and the per-block partial moments of r2 and of the shortcut; the finalize kernel turns them into
+// the affine coefficients that ood_field_step applies on load, so the two norms and the sum cost no pass of their own.
+constexpr int TT = 16;
+__global__ void __launch_bounds__(TT * TT) alignnet_tail_kernel(const float *__restrict__ res, const float *__restrict__ sc,
+                                                                 const float *__restrict__ slope, const float *__restrict__ w,
+                                                                 float *__restrict__ r2, float *__restrict__ partial, int R) {
+    __shared__ float sa[3][TT + 2][TT + 3];
+    __shared__ float sw[81];
+    __shared__ float red[TT * TT / 32][12];
+    const int b = blockIdx.z;
+    const int y0 = blockIdx.y * TT, x0 = blockIdx.x * TT;
+    const int64_t pl = (int64_t)R * R;
+    const float *rb = res + (int64_t)b * 3 * pl;
+    if (threadIdx.x < 81) sw[threadIdx.x] = w[threadIdx.x];                    // [o][i][ky][kx]
+    for (int i = threadIdx.x; i < 3 * (TT + 2) * (TT + 2); i += TT * TT) {
+        const int ch = i / ((TT + 2) * (TT + 2)), r = i % ((TT + 2) * (TT + 2));
+        const int ty = r / (TT + 2), tx = r % (TT + 2);
+        const int y = y0 + ty - 1, x = x0 + tx - 1;
+        float v = 0.f;
+        if (y >= 0 && y < R && x >= 0 && x < R) {
+            v = rb[ch * pl + (int64_t)y * R + x];
+            v = v > 0.f ? v : v * slope[ch];
+        }
+        sa[ch][ty][tx] = v;
+    }
+    __syncthreads();
+    const int ty = threadIdx.x / TT, tx = threadIdx.x % TT;
+    const int y = y0 + ty, x = x0 + tx;
+    const bool ok = y < R && x < R;
+    float m[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) m[i] = 0.f;
+    if (ok) {
+        const int64_t o = (int64_t)b * 3 * pl + (int64_t)y * R + x;
+#pragma unroll
+        for (int oc = 0; oc < 3; ++oc) {
+            float a = 0.f;
+#pragma unroll
+            for (int ic = 0; ic < 3; ++ic)
+#pragma unroll
+                for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx) a = fmaf(sw[((oc * 3 + ic) * 3 + ky) * 3 + kx], sa[ic][ty + ky][tx + kx], a);
+            r2[o + oc * pl] = a;
+            const float s = sc[o + oc * pl];
+            m[oc * 4 + 0] = a; m[oc * 4 + 1] = a * a; m[oc * 4 + 2] = s; m[oc * 4 + 3] = s * s;
+        }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+        float v = m[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) red[warp][i] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 12) {
+        float v = 0.f;
+        for (int wv = 0; wv < TT * TT / 32; ++wv) v += red[wv][threadIdx.x];
+        const int blk = blockIdx.y * gridDim.x + blockIdx.x;
+        partial[((int64_t)b * gridDim.x * gridDim.y + blk) * 12 + threadIdx.x] = v;
+    }
+}
+
+// coef[b][ch] = {rstd_r*w_r, rstd_s*w_s, b_r + b_s - mu_r*rstd_r*w_r - mu_s*rstd_s*w_s}
+__global__ void alignnet_tail_finalize_kernel(const float *__restrict__ partial, int nblocks, double n, float eps,
+                                              const float *__restrict__ wr, const float *__restrict__ br,
+                                              const float *__restrict__ ws, const float *__restrict__ bs, float *__restrict__ coef,
+                                              int total) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;        // b*3 + ch
+    if (i >= total) return;
+    const int b = i / 3, ch = i % 3;
+    double s[4] = {0, 0, 0, 0};
+    for (int k = 0; k < nblocks; ++k) {
+        const float *p = partial + ((int64_t)b * nblocks + k) * 12 + ch * 4;
+        for (int j = 0; j < 4; ++j) s[j] += p[j];
+    }
+    const double mr = s[0] / n, vr = fmax(s[1] / n - mr * mr, 0.0), ms = s[2] / n, vs = fmax(s[3] / n - ms * ms, 0.0);
+    const double gr = wr[ch] / sqrt(vr + eps), gs = ws[ch] / sqrt(vs + eps);
+    coef[i * 3 + 0] = (float)gr;
+    coef[i * 3 + 1] = (float)gs;
+    coef[i * 3 + 2] = (float)(br[ch] + bs[ch] - mr * gr - ms * gs);
 }
 
 // ------------------------------------------------------------------ warp + alpha mix
@@ -364,15 +459,37 @@ extern "C" int ood_bicubic_up_add(const void *x, const void *y, void *out, int b
     return check_launch("bicubic_up_add");
 }
 
+extern "C" int64_t ood_alignnet_tail_workspace(int batch, int r) {
+    const int nb = ood::ceil_div(r, ood::TT);
+    return (int64_t)batch * nb * nb * 12 * (int64_t)sizeof(float);
+}
+
+extern "C" int ood_alignnet_tail(const float *res, const float *shortcut, const float *prelu_slope, const float *conv_w,
+                                 const float *in_res_w, const float *in_res_b, const float *in_sc_w, const float *in_sc_b,
+                                 float eps, float *r2, float *workspace, float *coef, int batch, int r, void *stream) {
+    using namespace ood;
+    OOD_REQUIRE(res && shortcut && prelu_slope && conv_w && in_res_w && in_res_b && in_sc_w && in_sc_b && r2 && workspace && coef,
+                "alignnet_tail: null pointer");
+    OOD_REQUIRE(batch > 0 && batch <= 65535 && r > 0, "alignnet_tail: bad sizes");
+    const int nb = ceil_div(r, TT);
+    dim3 grid(nb, nb, batch);
+    cudaStream_t st = (cudaStream_t)stream;
+    alignnet_tail_kernel<<<grid, TT * TT, 0, st>>>(res, shortcut, prelu_slope, conv_w, r2, workspace, r);
+    alignnet_tail_finalize_kernel<<<ceil_div(batch * 3, 64), 64, 0, st>>>(workspace, nb * nb, (double)r * r, eps, in_res_w, in_res_b,
+                                                                           in_sc_w, in_sc_b, coef, batch * 3);
+    return check_launch("alignnet_tail", 2);
+}
+
 extern "C" int ood_field_step(const float *z, const float *prev, const float *coarse, float *acc, const float *taps_host,
-                              float scale, int batch, int r, int rc, void *stream) {
+                              float scale, int batch, int r, int rc, const float *z2, const float *coef, void *stream) {
     using namespace ood;
     OOD_REQUIRE(z && acc && taps_host && batch > 0 && batch <= 65535 && r > 0, "field_step: bad arguments");
+    OOD_REQUIRE(!z2 == !coef, "field_step: z2 and coef come together");
     OOD_REQUIRE(!coarse || rc > 0, "field_step: coarse needs its size");
     dim3 grid(ceil_div(r, FT), ceil_div(r, FT), batch);
     // correlation with the flipped taps (upfirdn2d.py:179)
     field_step_kernel<<<grid, FT * FT, 0, (cudaStream_t)stream>>>(z, prev, coarse, acc, taps_host[3], taps_host[2],
-                                                                   taps_host[1], taps_host[0], scale, r, rc);
+                                                                   taps_host[1], taps_host[0], scale, r, rc, z2, coef);
     return check_launch("field_step");
 }
 

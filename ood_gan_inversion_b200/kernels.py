@@ -309,16 +309,32 @@ def torgb(y, wrgb, bias, skip=None, taps_up=None):
 
 
 # ----------------------------------------------------------------------------------------------- SAMM
-def field_step(z, prev, coarse, scale, taps=None):
-    _cuda(z, prev, coarse)
+def field_step(z, prev, coarse, scale, taps=None, z2=None, coef=None):
+    """z fp32 [B,3,R,R] pre-activation (or z*coef0 + z2*coef1 + coef2 with coef [B,3,3] from alignnet_tail)."""
+    _cuda(z, prev, coarse, z2, coef)
     z = _f32c(z)
     b, _, r, _ = z.shape
     acc = torch.empty_like(z)
     rc = coarse.shape[-1] if coarse is not None else 0
     t = (C.c_float * 4)(*(taps or fir_taps()))
     check(_lib.lib().ood_field_step(_ptr(z), _ptr(_f32c(prev)), _ptr(_f32c(coarse)), _ptr(acc), t, float(scale), b, r, rc,
-                                    _stream()), 'field_step')
+                                    _ptr(_f32c(z2)), _ptr(_f32c(coef)), _stream()), 'field_step')
     return acc
+
+
+def alignnet_tail(res, shortcut, slope, conv_w, in_res_w, in_res_b, in_sc_w, in_sc_b, eps=1e-5):
+    """-> (r2, coef): InstanceNorm(conv3x3(PReLU(res))) + InstanceNorm(shortcut) == r2*coef[...,0] + shortcut*coef[...,1] + coef[...,2]"""
+    _cuda(res, shortcut, slope, conv_w, in_res_w, in_res_b, in_sc_w, in_sc_b)
+    assert res.dtype == torch.float32 and shortcut.dtype == torch.float32 and res.is_contiguous() and shortcut.is_contiguous()
+    b, _, r, _ = res.shape
+    r2 = torch.empty_like(res)
+    ws = torch.empty(_lib.lib().ood_alignnet_tail_workspace(b, r) // 4, device=res.device, dtype=torch.float32)
+    coef = torch.empty(b, 3, 3, device=res.device, dtype=torch.float32)
+    with _timed('alignnet_tail', b * 3 * r * r * 4 * 3):
+        check(_lib.lib().ood_alignnet_tail(_ptr(res), _ptr(shortcut), _ptr(slope), _ptr(conv_w), _ptr(in_res_w), _ptr(in_res_b),
+                                           _ptr(in_sc_w), _ptr(in_sc_b), float(eps), _ptr(r2), _ptr(ws), _ptr(coef), b, r, _stream()),
+              'alignnet_tail')
+    return r2, coef
 
 
 def warp_mix(gen, field):

@@ -84,7 +84,8 @@ class AlignNet(nn.Module):
                  self.body[1].shortcut_layer[0]]
         c2 = convs[0].weight.shape[0]
         return self.diff_fAndg and all(c.bias is None for c in convs) and c2 % sg._granule() == 0 and \
-            isinstance(self.body[0].res_layer[0], nn.InstanceNorm2d)
+            isinstance(self.body[0].res_layer[0], nn.InstanceNorm2d) and isinstance(self.body[1].res_layer[4], nn.InstanceNorm2d) and \
+            isinstance(self.body[1].shortcut_layer[1], nn.InstanceNorm2d)
 
     def _packed(self):
         b0, b1 = self.body[0], self.body[1]
@@ -107,8 +108,10 @@ class AlignNet(nn.Module):
             hit = self._pk
         return hit[1]
 
-    def raw_nhwc(self, cur, enc):
-        """cur, enc: NHWC [B,R,R,C] in the pipeline's storage type -> pre-activation field [B,3,R,R] fp32."""
+    def raw_nhwc(self, cur, enc, fold=False):
+        """cur, enc: NHWC [B,R,R,C] in the pipeline's storage type -> pre-activation field [B,3,R,R] fp32.
+        fold=True returns (r2, shortcut, coef) instead: the field is r2*coef[...,0] + shortcut*coef[...,1] + coef[...,2], which
+        ood_field_step applies on load (the two closing InstanceNorms and the residual sum never take a pass of their own)."""
         b0, b1 = self.body[0], self.body[1]
         pk = self._packed()
         f = lambda p: p.detach().float().contiguous()
@@ -125,10 +128,12 @@ class AlignNet(nn.Module):
         res = K.tap_sum(x)
         zero = torch.zeros(3, device=cur.device)
         sc = K.torgb(out0, pk['w1'].unsqueeze(0).expand(b, -1, -1).contiguous(), zero)      # 1x1 conv 2C -> 3, fp32 NCHW
-        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):                     # 3-channel fp32 tail
-            sc = b1.shortcut_layer[1](sc)
-            res = b1.res_layer[4](b1.res_layer[3](b1.res_layer[2](res)))
-        return res + sc
+        n_res, n_sc = b1.res_layer[4], b1.shortcut_layer[1]
+        r2, coef = K.alignnet_tail(res, sc, f(b1.res_layer[2].weight), f(b1.res_layer[3].weight), f(n_res.weight), f(n_res.bias),
+                                   f(n_sc.weight), f(n_sc.bias), n_res.eps)
+        if fold:
+            return r2, sc, coef
+        return r2 * coef[:, :, 0, None, None] + sc * coef[:, :, 1, None, None] + coef[:, :, 2, None, None]
 
     def forward(self, source, target, **kwargs):
         z = self.raw(source, target)
@@ -173,11 +178,11 @@ class SPM_Warp(nn.Module):
         cur, acc = target_nhwc, None
         for k in range(self.cycle_align):
             if fused:
-                z = self.body.raw_nhwc(cur, src)
+                z, z2, coef = self.body.raw_nhwc(cur, src, fold=True)
             else:
-                z = self.body.raw(cur.permute(0, 3, 1, 2), src)      # NHWC storage viewed as channels_last NCHW
+                z, z2, coef = self.body.raw(cur.permute(0, 3, 1, 2), src), None, None      # NHWC storage viewed as channels_last NCHW
             last = k == self.cycle_align - 1
-            acc = K.field_step(z, acc, aligned if last else None, self.scale, self.blur.taps)
+            acc = K.field_step(z, acc, aligned if last else None, self.scale, self.blur.taps, z2=z2, coef=coef)
             cur = K.warp_mix(target_nhwc, acc)
         return cur, acc
 

@@ -357,6 +357,27 @@ def test_torgb(dtype, c, h):
 
 
 # ----------------------------------------------------------------------------------------------- SAMM kernels
+@pytest.mark.parametrize('r', [9, 32, 70])
+def test_alignnet_tail_and_folded_field_step(r):
+    """ood_alignnet_tail: PReLU -> conv3x3(3->3) -> InstanceNorm plus InstanceNorm(shortcut), returned as an affine form that
+    ood_field_step applies on load (bottleneck_IR tail, e4e/encoders/helpers.py:426-448)."""
+    b = 2
+    res, sc = rnd(b, 3, r, r, seed=1), 0.5 + 2 * rnd(b, 3, r, r, seed=2)
+    slope, w = 0.25 + 0.1 * rnd(3, seed=3), 0.3 * rnd(3, 3, 3, 3, seed=4)
+    wr, br, ws, bs = 1 + 0.2 * rnd(3, seed=5), rnd(3, seed=6), 1 + 0.2 * rnd(3, seed=7), rnd(3, seed=8)
+    F_ = torch.nn.functional
+    ref = F_.instance_norm(F_.conv2d(F_.prelu(res, slope), w, padding=1), weight=wr, bias=br, eps=1e-5) + \
+        F_.instance_norm(sc, weight=ws, bias=bs, eps=1e-5)
+    d = lambda t: t.to(DEV)
+    r2, coef = K().alignnet_tail(d(res), d(sc), d(slope), d(w), d(wr), d(br), d(ws), d(bs), 1e-5)
+    z = r2 * coef[:, :, 0, None, None] + d(sc) * coef[:, :, 1, None, None] + coef[:, :, 2, None, None]
+    torch.testing.assert_close(z.cpu(), ref, rtol=1e-4, atol=1e-4)
+    k = oops.fir_kernel([1, 3, 3, 1])
+    direct = K().field_step(z, None, None, 0.08)
+    folded = K().field_step(r2, None, None, 0.08, z2=d(sc), coef=coef)
+    torch.testing.assert_close(folded, direct, rtol=1e-5, atol=1e-6)
+
+
 @pytest.mark.parametrize('r', [12, 32, 50])
 def test_field_step(r):
     b, scale = 2, 0.08
