@@ -3,14 +3,15 @@ up2 / down2 / blur at every resolution 4..1024, against the measured tensor and 
 
     python scripts/kernel_sweep.py [--out profiles/sweep_rNN.json]
 
-CUDA events on the launching stream, 3 warm-up + best-of-5 timed launches per case (inputs of successive cases differ,
-and every case above 64 px exceeds L2).  Algorithmic work per SURVEY.md section 8(d).
+CUDA events on the launching stream, 0.5 s idle + 3 warm-up + best-of-5 timed launches per case (inputs of successive cases
+differ, and every case above 64 px exceeds L2).  Algorithmic work per SURVEY.md section 8(d).
 """
 import argparse
 import json
 import math
 import os
 import sys
+import time
 
 import torch
 
@@ -19,6 +20,8 @@ from ood_gan_inversion_b200 import kernels as K  # noqa: E402
 
 
 def timeit(fn, warm=3, rep=5):
+    torch.cuda.synchronize()
+    time.sleep(0.5)            # every case starts from an idle GPU: the peaks it is compared with are burst figures (kernel timed alone)
     for _ in range(warm):
         fn()
     best = 1e9
@@ -84,6 +87,18 @@ def main():
                 rows.append(dict(op=f'upfirdn2d_{name}', dtype=str(dt).split('.')[-1], res=res, planes=b * c, ms=ms, gbs=gb / (ms * 1e-3),
                                  frac_of_hbm_peak=gb / (ms * 1e-3) / pk['hbm_gbs']))
             del cases
+    # --- the bf16 pipeline's own FIR path: NHWC fused blur + demod + noise + bias + lrelu + next style at the generator's sizes
+    taps = K.fir_taps(gain=2.0)
+    for res, c in [(64, 512), (128, 256), (256, 128), (512, 64), (1024, 32)]:
+        b = 16
+        t = torch.randn(b, res + 1, res + 1, c, device=dev).bfloat16()
+        dd, ss = torch.rand(b, c, device=dev) + 0.5, torch.rand(b, c, device=dev) + 0.5
+        nz, nw, bias = torch.randn(b, 1, res, res, device=dev), torch.tensor([0.1], device=dev), torch.randn(c, device=dev)
+        ms = timeit(lambda: K.blur_act(t, taps, d=dd, noise=nz, noise_w=nw, bias=bias, s_next=ss, act=True, want_y=False, want_ys=True))
+        gb = (b * c * ((res + 1) ** 2 + res * res) * 2 + b * res * res * 4) / 1e9
+        rows.append(dict(op='blur_act_nhwc', dtype='bfloat16', res=res, channels=c, batch=b, ms=ms, gbs=gb / (ms * 1e-3),
+                         frac_of_hbm_peak=gb / (ms * 1e-3) / pk['hbm_gbs']))
+        del t
     for r in rows:
         print(json.dumps(r))
     if args.out:

@@ -21,7 +21,7 @@ def timeit(fn, warm=3, rep=8):
 
 k4 = torch.tensor([1., 3., 3., 1.], device='cuda')
 k2d = torch.outer(k4, k4) / 64
-for res, planes in [(256, 2048), (512, 1024), (1024, 256)]:
+for res, planes in [(256, 2048), (512, 1024), (1024, 256), (1024, 1024), (2048, 256)]:
     for name, shape, args in [('blur', (planes, res + 1, res + 1), (1, 1, 1, 1, 1, 1, 1, 1)),
                               ('up2', (planes, res // 2, res // 2), (2, 2, 1, 1, 2, 1, 2, 1)),
                               ('down2', (planes, res, res), (1, 1, 2, 2, 1, 1, 1, 1))]:
