@@ -102,7 +102,7 @@ class AlignNet(nn.Module):
                 w27[:27] = wc.permute(2, 3, 0, 1).reshape(27, -1)
                 pk = dict(wa=K.pack_conv_weight(b0.res_layer[1].weight.detach(), dt, cim),
                           wb=K.pack_conv_weight(b0.res_layer[3].weight.detach(), dt, cim),
-                          wc=K.pack_conv1x1_weight(w27, dt, cim), cp=32,
+                          wc=K.pack_conv1x1_weight(w27, dt, cim), cp=32, w27=w27.contiguous(),
                           w1=b1.shortcut_layer[0].weight.detach().float().reshape(3, -1).contiguous())
             self._pk = (key, pk)
             hit = self._pk
@@ -123,8 +123,17 @@ class AlignNet(nn.Module):
         x, _ = K.conv3x3(x, pk['wa'], 2 * c, impl=impl, prelu=f(b0.res_layer[2].weight))
         x, _ = K.conv3x3(x, pk['wb'], 2 * c, impl=impl)
         out0 = K.alignnet_res0(x, K.in_stats(x, None, eps), f(b0.res_layer[4].weight), f(b0.res_layer[4].bias), cur, enc, st6)
-        x = K.in_apply(out0, K.in_stats(out0, None, eps), f(b1.res_layer[0].weight), f(b1.res_layer[0].bias))
-        x, _ = K.conv3x3(x, pk['wc'], pk['cp'], transposed=4, impl=impl, out_f32=True)
+        st = K.in_stats(out0, None, eps)
+        if impl == 0:
+            # InstanceNorm(out0) folded into the projection: W27 . (g*out0 + h) = (W27 diag(g_b)) . out0 + W27 . h_b -- one weight
+            # set per sample (grouped form, groups = batch) and a per-sample bias, so the normalised copy is never written
+            g = st[..., 1] * f(b1.res_layer[0].weight)                                   # [B, 2C]
+            h = f(b1.res_layer[0].bias) - st[..., 0] * g
+            wps = (pk['w27'].unsqueeze(0) * g.unsqueeze(1)).to(torch.bfloat16)           # [B, 32, 2C] = [groups][1 tap][Co][Ci]
+            x, _ = K.conv3x3(out0, wps, pk['cp'], transposed=4, impl=0, out_f32=True, groups=b, bias=(h @ pk['w27'].t()).contiguous())
+        else:
+            x = K.in_apply(out0, st, f(b1.res_layer[0].weight), f(b1.res_layer[0].bias))
+            x, _ = K.conv3x3(x, pk['wc'], pk['cp'], transposed=4, impl=impl, out_f32=True)
         res = K.tap_sum(x)
         zero = torch.zeros(3, device=cur.device)
         sc = K.torgb(out0, pk['w1'].unsqueeze(0).expand(b, -1, -1).contiguous(), zero)      # 1x1 conv 2C -> 3, fp32 NCHW
