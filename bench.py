@@ -41,24 +41,60 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region: NVML every 10 ms (nvidia_ml_py), else nvidia-smi."""
     Q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+    NAMES = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
 
     def __init__(self, index):
-        self.index, self.rows, self.stop = index, [], False
+        self.index, self.rows, self.stop = index, [], False      # rows: (sm_mhz, max_mhz, [reason flags])
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index(index))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
         self.t = threading.Thread(target=self.run, daemon=True)
+
+    @staticmethod
+    def _physical_index(index):
+        vis = os.environ.get('CUDA_VISIBLE_DEVICES', '')
+        ids = [v for v in vis.split(',') if v.strip() != '']
+        try:
+            return int(ids[index]) if ids else index
+        except (ValueError, IndexError):
+            return index
+
+    def sample_nvml(self):
+        n = self.nvml
+        sm = n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)
+        mx = n.nvmlDeviceGetMaxClockInfo(self.h, n.NVML_CLOCK_SM)
+        r = n.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(n, 'nvmlDeviceGetCurrentClocksEventReasons') \
+            else n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        bits = [getattr(n, 'nvmlClocksThrottleReasonHwSlowdown', 0x8), getattr(n, 'nvmlClocksThrottleReasonHwThermalSlowdown', 0x40),
+                getattr(n, 'nvmlClocksThrottleReasonSwThermalSlowdown', 0x20), getattr(n, 'nvmlClocksThrottleReasonSwPowerCap', 0x4)]
+        self.rows.append((float(sm), float(mx), [bool(r & b) for b in bits]))
+
+    def sample_smi(self):
+        o = subprocess.run(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.Q}', '--format=csv,noheader,nounits'],
+                           capture_output=True, text=True, timeout=5).stdout.strip()
+        c = [v.strip() for v in o.split(',')]
+        if len(c) >= 7 and c[0].replace('.', '').isdigit():
+            self.rows.append((float(c[0]), float(c[1]), [v.lower() == 'active' for v in c[3:7]]))
 
     def run(self):
         while not self.stop:
             try:
-                o = subprocess.run(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.Q}', '--format=csv,noheader,nounits'],
-                                   capture_output=True, text=True, timeout=5).stdout.strip()
-                if o:
-                    self.rows.append([c.strip() for c in o.split(',')])
+                if self.nvml is not None:
+                    self.sample_nvml()
+                else:
+                    self.sample_smi()
             except Exception:
-                pass
-            time.sleep(0.2)
+                if self.nvml is not None:
+                    self.nvml = None                     # fall back to nvidia-smi
+            time.sleep(0.01 if self.nvml is not None else 0.2)
 
     def __enter__(self):
         self.t.start()
@@ -69,12 +105,12 @@ class ClockSampler:
         self.t.join(timeout=6)
 
     def summary(self):
-        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace('.', '').isdigit())
-        if not sm:
+        if not self.rows:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=['unavailable'])
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower() == 'active' for r in self.rows)]
-        return dict(sm_mhz=sm[len(sm) // 2], sm_max_mhz=float(self.rows[0][1]), samples=len(sm), reasons=reasons)
+        sm = sorted(r[0] for r in self.rows)
+        reasons = [n for i, n in enumerate(self.NAMES) if any(r[2][i] for r in self.rows)]
+        return dict(sm_mhz=sm[len(sm) // 2], sm_max_mhz=self.rows[0][1], samples=len(sm), reasons=reasons,
+                    source='nvml' if self.nvml is not None else 'nvidia-smi')
 
 
 def cpu_reference(steps, warmup, images_per_step=1, state=None):
@@ -137,9 +173,12 @@ def main():
         raise RuntimeError('bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm')
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
+    # stdout carries exactly one JSON line: libraries that print there (NCCL's version banner) are sent to stderr, and the
+    # line is written to the saved descriptor at the end
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
-        if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION'):
-            os.environ['NCCL_DEBUG'] = 'WARN'       # keep stdout to the one JSON line (NCCL prints its version banner there)
         dist.init_process_group('nccl', device_id=dev)
     torch.backends.cudnn.benchmark = True
     torch.set_grad_enabled(False)
@@ -324,7 +363,8 @@ def main():
         sd = {k: v.detach().float().cpu() for k, v in net.state_dict().items()}
         r = cpu_reference(2, 1, 1, state=sd)
         line['cpu_baseline'] = dict(value=r['value'], unit=UNIT, cores=r['cores'], kind='port', sample=r['sample'])
-    print(json.dumps(line))
+    sys.stdout.flush()
+    os.write(json_fd, (json.dumps(line) + '\n').encode())
     if world > 1:
         dist.destroy_process_group()
     return 0
