@@ -125,14 +125,14 @@ __global__ void __launch_bounds__(256) tap_sum_kernel(const float *__restrict__ 
     const int b = blockIdx.y;
     const int64_t P = (int64_t)H * W;
     const float *pb = proj + (int64_t)b * P * Cp;
-    for (int64_t pix = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; pix < P; pix += (int64_t)gridDim.x * blockDim.x) {
-        const int y = (int)(pix / W), x = (int)(pix - (int64_t)y * W);
+    for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < (int)P; pix += gridDim.x * blockDim.x) {     // P < 2^31 (host check)
+        const int y = pix / W, x = pix - y * W;
         float acc[3] = {0.f, 0.f, 0.f};
 #pragma unroll
         for (int t = 0; t < 9; ++t) {
             const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
             if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
-            const float *q = pb + ((int64_t)yy * W + xx) * Cp + 3 * t;
+            const float *q = pb + (int64_t)(yy * W + xx) * Cp + 3 * t;
             acc[0] += __ldg(q); acc[1] += __ldg(q + 1); acc[2] += __ldg(q + 2);
         }
 #pragma unroll
@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(256) tap_sum_kernel(const float *__restrict__ 
 
 extern "C" int ood_tap_sum(const float *proj, float *out, int batch, int h, int w, int cp, void *stream) {
     using namespace ood;
-    OOD_REQUIRE(proj && out && batch > 0 && batch <= 65535 && h > 0 && w > 0 && cp >= 27, "tap_sum: bad arguments");
+    OOD_REQUIRE(proj && out && batch > 0 && batch <= 65535 && h > 0 && w > 0 && cp >= 27 && (int64_t)h * w < (1LL << 30), "tap_sum: bad arguments");
     const int64_t P = (int64_t)h * w;
     dim3 grid((unsigned)std::min<int64_t>((P + 255) / 256, kNumSMs * 16), batch);
     tap_sum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(proj, out, h, w, cp);

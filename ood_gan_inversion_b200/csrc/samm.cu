@@ -322,10 +322,11 @@ __global__ void __launch_bounds__(256) mask_blend_kernel(const MaskParams mp, co
                                                           float *__restrict__ alpha_out, int S) {
     const int b = blockIdx.y;
     const int64_t P = (int64_t)S * S;
-    const int64_t nq = P / 4;    // S % 4 == 0
-    for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < nq; q += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t pix = q * 4;
-        const int y = (int)(pix / S), x = (int)(pix - (int64_t)y * S);
+    const int nq = (int)(P / 4);    // S % 4 == 0; 32-bit pixel arithmetic (S <= 16384 is checked by the host)
+    const int qrow = S / 4;
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += gridDim.x * blockDim.x) {
+        const int y = q / qrow, x = (q - y * qrow) * 4;
+        const int64_t pix = (int64_t)q * 4;
         float4 xv[3], gv[3];
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
@@ -334,7 +335,9 @@ __global__ void __launch_bounds__(256) mask_blend_kernel(const MaskParams mp, co
             gv[k] = __ldg(reinterpret_cast<const float4 *>(gen + o));
         }
         float A[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int k = 0; k < mp.n; ++k) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (k >= mp.n) break;
             const int r = mp.r[k];
             const float *a = mp.f[k] + ((int64_t)b * 3 + 2) * r * r;
             float u[4];
@@ -529,7 +532,7 @@ extern "C" int ood_mask_blend(const float *const *fields_host, const int *field_
                               const float *gen, float *out, float *alpha_out, int batch, int size, void *stream) {
     using namespace ood;
     OOD_REQUIRE(fields_host && field_sizes_host && n_fields >= 1 && n_fields <= 4, "mask_blend: 1..4 fields supported");
-    OOD_REQUIRE(x && gen && out && batch > 0 && batch <= 65535 && size > 0 && size % 4 == 0, "mask_blend: bad arguments");
+    OOD_REQUIRE(x && gen && out && batch > 0 && batch <= 65535 && size > 0 && size % 4 == 0 && size <= 16384, "mask_blend: bad arguments");
     MaskParams mp{};
     mp.n = n_fields;
     for (int i = 0; i < n_fields; ++i) {

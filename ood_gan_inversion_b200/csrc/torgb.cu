@@ -252,35 +252,41 @@ __global__ void __launch_bounds__(256) torgb_mma_kernel(const __nv_bfloat16 *__r
         if (pix >= P) continue;
         rgb[0] += bias_r; rgb[1] += bias_g; rgb[2] += bias_b;
         if (skip) {
-            // up-2 polyphase: output row Y sees skip rows (Y + ky0 - 2)/2 and the next one, taps ky0, ky0+2 (ky0 = Y & 1)
-            const int Y = (int)(pix / W), X = (int)(pix - (int64_t)Y * W);
+            // up-2 polyphase: output row Y sees skip rows (Y + ky0 - 2)/2 and the next one, taps ky0, ky0+2 (ky0 = Y & 1).
+            // 32-bit pixel arithmetic (P < 2^31 is checked by the host): the 64-bit division of the first version was a
+            // third of the kernel's instructions (ncu: 381 warp-instructions per 32-pixel chunk, issue-bound).
+            const int pi = (int)pix;
+            const int Y = pi / W, X = pi - Y * W;
             const int ky0 = Y & 1, kx0 = X & 1;
             const int ra = (Y + ky0 - 2) >> 1, ca = (X + kx0 - 2) >> 1;
             const float wy[2] = {ky0 ? kf1 : kf0, ky0 ? kf3 : kf2}, wx[2] = {kx0 ? kf1 : kf0, kx0 ? kf3 : kf2};
-            const float *sp = skip + (int64_t)b * 3 * h2 * w2;
+            const int plane = h2 * w2;
+            const float *sp = skip + (int64_t)b * 3 * plane;
+            const bool cok[2] = {ca >= 0, ca + 1 < w2};
 #pragma unroll
             for (int dy = 0; dy < 2; ++dy) {
                 const int rr = ra + dy;
                 if (rr < 0 || rr >= h2) continue;
+                const float *srow = sp + rr * w2 + ca;
 #pragma unroll
                 for (int dx = 0; dx < 2; ++dx) {
-                    const int cc = ca + dx;
-                    if (cc < 0 || cc >= w2) continue;
+                    if (!cok[dx]) continue;
                     const float wgt = wy[dy] * wx[dx];
-                    const float *s0 = sp + (int64_t)rr * w2 + cc;
 #pragma unroll
-                    for (int k = 0; k < 3; ++k) rgb[k] = fmaf(wgt, __ldg(s0 + (int64_t)k * h2 * w2), rgb[k]);
+                    for (int k = 0; k < 3; ++k) rgb[k] = fmaf(wgt, __ldg(srow + dx + k * plane), rgb[k]);
                 }
             }
         }
+        float *op = out + (int64_t)b * 3 * P + pix;
 #pragma unroll
-        for (int k = 0; k < 3; ++k) out[((int64_t)b * 3 + k) * P + pix] = rgb[k];
+        for (int k = 0; k < 3; ++k) op[(int64_t)k * P] = rgb[k];
     }
 }
 
 static int launch_torgb_mma(const void *y, const float *wrgb, const float *bias, const float *skip, float *out, const float *kf,
                             int batch, int h, int w, int C, cudaStream_t st) {
     const int64_t P = (int64_t)h * w;
+    OOD_REQUIRE(P < (1LL << 31) / 4, "torgb: image too large");
     const int64_t chunks = (P + 255) / 256;              // 8 warps x 32 pixels per block iteration
     dim3 grid((unsigned)std::min<int64_t>(chunks, std::max(1, kNumSMs * 8 / batch)), batch);
     const __nv_bfloat16 *yy = (const __nv_bfloat16 *)y;
