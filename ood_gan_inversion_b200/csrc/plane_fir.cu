@@ -3,7 +3,7 @@
 // configurations the reference actually instantiates (model.py:30-88: Upsample pad (2,1), Downsample pad (1,1), Blur).
 //
 // The tile kernels in upfirdn2d.cu stage a [32 x 64] output tile per CTA with scalar loads that wait in registers, and
-// sat at 0.14-0.45 of HBM peak (sweep_r01.json).  Here a CTA owns a 128 / 256 / 512-column strip of one plane and streams its input
+// sat at 0.14-0.45 of HBM peak (sweep_r01.json).  Here a CTA owns a 64 / 128 / 256 / 512-column strip of one plane and streams its input
 // rows ONCE through a shared-memory ring with cp.async (4-byte copies: plane rows of odd width, e.g. the 1025-wide
 // transposed-conv output, are only 4-byte aligned, which rules out TMA and 16-byte vectors), so 12-16 KB per CTA are in
 // flight without holding registers.  A thread owns the output columns t and t + SW/2 as one fp32x2 pair: the vertical
@@ -217,12 +217,12 @@ int plane_fir(const UpfirdnParams &u, int pad_x1, int pad_y1, cudaStream_t st, i
     p.chunk_rows = 0;
     int rc;
     const bool pads_ok = u.pad_x0 >= 0 && u.pad_y0 >= 0;
-    // strip width: the widest of 512 / 256 / 128 that the plane fills (a thread owns columns t and t + SW/2)
+    // strip width: the widest of 512 / 256 / 128 / 64 that the plane fills (a thread owns columns t and t + SW/2)
 #define OOD_PF(MODE, W) ((W) >= 384 ? launch_plane_fir<MODE, 512>(p, u.planes, st) : (W) >= 192 ? launch_plane_fir<MODE, 256>(p, u.planes, st) \
-                                                                                   : launch_plane_fir<MODE, 128>(p, u.planes, st))
-    if (u.up_x == 1 && u.down_x == 1 && u.out_w >= 96 && pads_ok) rc = OOD_PF(0, u.out_w);
-    else if (u.up_x == 1 && u.down_x == 2 && u.out_w >= 96 && pads_ok) rc = OOD_PF(1, u.out_w);
-    else if (u.up_x == 2 && u.down_x == 1 && u.in_w >= 96 && u.pad_x0 == 2 && u.pad_y0 == 2 && pad_x1 == 1 && pad_y1 == 1 &&
+                        : (W) >= 96 ? launch_plane_fir<MODE, 128>(p, u.planes, st) : launch_plane_fir<MODE, 64>(p, u.planes, st))
+    if (u.up_x == 1 && u.down_x == 1 && u.out_w >= 48 && pads_ok) rc = OOD_PF(0, u.out_w);
+    else if (u.up_x == 1 && u.down_x == 2 && u.out_w >= 48 && pads_ok) rc = OOD_PF(1, u.out_w);
+    else if (u.up_x == 2 && u.down_x == 1 && u.in_w >= 48 && u.pad_x0 == 2 && u.pad_y0 == 2 && pad_x1 == 1 && pad_y1 == 1 &&
              u.out_w % 2 == 0) rc = OOD_PF(2, u.in_w);
     else return OOD_OK;
 #undef OOD_PF

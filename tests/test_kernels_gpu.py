@@ -58,6 +58,8 @@ def test_upfirdn2d_golden_cases(golden):
     dict(shape=(1, 3, 300, 260), up=1, down=1, pad=(2, 1), gain=1.0),     # row-streaming blur, pad (2,1), one ragged strip
     dict(shape=(1, 2, 140, 1100), up=1, down=2, pad=(1, 1), gain=1.0),    # row-streaming down2, ragged second strip
     dict(shape=(2, 1, 70, 600), up=2, down=1, pad=(2, 1), gain=4.0),      # row-streaming up2 (polyphase), two strips
+    dict(shape=(3, 2, 64, 64), up=2, down=1, pad=(2, 1), gain=4.0),       # narrowest strip (64 columns)
+    dict(shape=(2, 2, 128, 120), up=1, down=2, pad=(1, 1), gain=1.0),     # down2 on a 60-wide output
 ])
 @pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
 def test_upfirdn2d_vs_oracle(cfg, dtype):
