@@ -331,6 +331,19 @@ def main():
             dist.destroy_process_group()
         return 0
 
+    def ncu_traffic(name):
+        """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the kernel family from the committed ncu --set full capture."""
+        try:
+            d = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'profiles', 'ncu_r01_summary.json')))[name]
+            unit = dict(byte=1.0, Kbyte=1e3, Mbyte=1e6, Gbyte=1e9)
+            tot = 0.0
+            for k in ('dram_read', 'dram_write'):
+                v, u = d[k].split()
+                tot += float(v) * unit[u]
+            return tot
+        except Exception:
+            return None
+
     pk = peaks()
     conv = prof.get('conv3x3_tc', dict(ms=0.0, work=0.0, launches=0))
     blur = prof.get('blur_act', dict(ms=0.0, work=0.0, launches=0))
@@ -351,12 +364,14 @@ def main():
                          d2h_bytes_per_step=out_host.numel() * 4, ms_per_step=ms_e2e / args.steps),
                 gpu_launches=int(launches),
                 roofline=dict(kernel='conv_tc_kernel (tcgen05 implicit-GEMM 3x3 modulated conv)', bound='tensor', achieved=conv_tf,
-                              peak=pk['tf_sus'], unit='TFLOP/s', frac=conv_tf / pk['tf_sus'], traffic=None,
+                              peak=pk['tf_sus'], unit='TFLOP/s', frac=conv_tf / pk['tf_sus'], traffic=ncu_traffic('conv256'),
+                              traffic_note='DRAM bytes of one conv_tc_kernel<256,64> launch (AlignNet 1024->1024 ch at 64 px: 1.24 TFLOP, 0.29 GB of activations + weights; L2 hit 97 %), profiles/ncu_r01_conv256_raw.csv',
                               peak_source=pk['src'] + ', sustained figure (kernel timed inside a long step)',
                               share_of_step=conv['ms'] / prof_steps / max(step_ms, 1e-9), launches_per_step=conv['launches'] / prof_steps,
                               timing='CUDA events around every launch in an eager pass of the same step, same process'),
                 roofline_hbm=dict(kernel='blur_rows_kernel / blur_tma_kernel (FIR blur + demod + noise + bias + lrelu + next style)', bound='hbm',
-                                  achieved=blur_gbs, peak=pk['hbm'], unit='GB/s', frac=blur_gbs / pk['hbm'], traffic=None,
+                                  achieved=blur_gbs, peak=pk['hbm'], unit='GB/s', frac=blur_gbs / pk['hbm'], traffic=ncu_traffic('blurrows'),
+                                  traffic_note='DRAM bytes of the 1024 px blur_rows_kernel launch (2.15 GB algorithmic), profiles/ncu_r01_blurrows_raw.csv',
                                   share_of_step=blur['ms'] / prof_steps / max(step_ms, 1e-9)),
                 kernels=kern)
     if world == 1 and not args.no_cpu_baseline:
