@@ -550,3 +550,34 @@ def test_conv3x3_fused_torgb_epilogue(case):
     assert y2 is None and ys2 is None
     torch.testing.assert_close(rgb2.cpu(), rgb_ref - oops.upfirdn2d(skip, oops.fir_kernel([1, 3, 3, 1], 4.0), up=2, pad=(2, 1)),
                                rtol=1e-2, atol=3e-2)
+
+
+# ----------------------------------------------------------------------------------------------- encoder glue kernels
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('case', [dict(c=64, h=6, w=10, stride=1, f32=False), dict(c=128, h=5, w=7, stride=2, f32=True),
+                                  dict(c=512, h=4, w=4, stride=1, f32=True)])
+def test_se_gate_and_residual(dtype, case):
+    """ood_se_gate / ood_se_residual vs SEModule + residual sum + next BatchNorm (e4e/encoders/helpers.py:59-76,476-501)."""
+    b, c, h, w_, st = 2, case['c'], case['h'], case['w'], case['stride']
+    stream_f32 = case['f32'] and dtype == torch.bfloat16
+    v = rnd(b, c, h, w_, seed=1).to(dtype).float()
+    sc_full = rnd(b, c, h * st, w_ * st, seed=2)
+    sc_full = sc_full if stream_f32 else sc_full.to(dtype).float()
+    w1, w2 = 0.2 * rnd(c // 16, c, seed=3), 0.2 * rnd(c, c // 16, seed=4)
+    g2, h2 = 1 + 0.1 * rnd(c, seed=5), 0.1 * rnd(c, seed=6)
+    gate_ref = torch.sigmoid(torch.relu(v.mean((2, 3)) @ w1.t()) @ w2.t())
+    out_ref = v * gate_ref[:, :, None, None] + sc_full[:, :, ::st, ::st]
+    tn_ref = out_ref * g2[None, :, None, None] + h2[None, :, None, None]
+    vd = nhwc(v, dtype)
+    gate = K().se_gate(K().in_stats(vd), w1.to(DEV), w2.to(DEV))
+    torch.testing.assert_close(gate.cpu(), gate_ref, rtol=1e-4, atol=1e-4)
+    scd = nhwc(sc_full, torch.float32 if stream_f32 else dtype)
+    out, tn = K().se_residual(vd, gate, scd, st, g2.to(DEV), h2.to(DEV), out_f32=stream_f32)
+    assert out.dtype == (torch.float32 if (stream_f32 or dtype == torch.float32) else torch.bfloat16) and tn.dtype == dtype
+    tol = dict(rtol=1e-5, atol=1e-5) if dtype == torch.float32 else dict(rtol=2e-2, atol=2e-2)
+    torch.testing.assert_close(nchw(out), out_ref, **(dict(rtol=1e-4, atol=1e-4) if stream_f32 else tol))
+    torch.testing.assert_close(nchw(tn), tn_ref, **tol)
+    # affine-only form (first block's BatchNorm): no gate, no shortcut, no `out`
+    o2, t2 = K().se_residual(vd, bn_g=g2.to(DEV), bn_h=h2.to(DEV), want_out=False)
+    assert o2 is None
+    torch.testing.assert_close(nchw(t2), v * g2[None, :, None, None] + h2[None, :, None, None], **tol)
