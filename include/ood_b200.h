@@ -132,6 +132,11 @@ typedef struct {
      * Epilogue: bias + activation only.  groups <= 1: the plain form. */
     int groups;
     int in_shared;
+    /* accumulator seed (tcgen05 path, every form except transposed == 1): fp32 NHWC [B,OH,OW,Co] added to the accumulator
+     * before d / bias / noise / activation.  A convolution whose input channels split into a part that changes between calls
+     * and a part that does not (AlignNet: cat[IN(cur)-IN(enc), IN(enc)], SAMM/helpers.py:96-101, over the alignment cycles
+     * :154-166) runs the constant part once (out_f32 = 1, no epilogue terms) and seeds every later call with it. */
+    const float *acc_in;
 } ood_conv3x3_args;
 int ood_conv3x3(const ood_conv3x3_args *args_host, void *stream);
 
@@ -247,6 +252,18 @@ int ood_alignnet_res0(const void *t, const float *st2, const float *w, const flo
                       const float *st6, void *out, int batch, int64_t pixels, int channels, int dtype, void *stream);
 int ood_in_apply(const void *x, const float *st2, const float *w, const float *bias, void *out, int batch, int64_t pixels,
                  int channels, int dtype, void *stream);
+/*      ood_alignnet_front_split: the two halves of ood_alignnet_front as separate [B,P,C] tensors; out_hi == NULL skips the
+ *      IN(enc) half, which does not depend on `cur` (the second alignment cycle, SAMM/helpers.py:154-166, reuses it -- and the
+ *      part of the first convolution computed from it, see ood_conv3x3_args.acc_in).
+ *      ood_alignnet_res0_stats: ood_alignnet_res0 that also returns stats_out [B,2C,2] = {mean, rstd} of its OUTPUT as stored
+ *      (the statistics of the next InstanceNorm, e4e/encoders/helpers.py:426-448 res_layer[0] of the second block) without a
+ *      pass over it; channels / (16 / sizeof(T)) must divide 256.  workspace: ood_alignnet_res0_workspace() bytes. */
+int ood_alignnet_front_split(const void *cur, const void *enc, const float *st6, const float *w, const float *bias,
+                             void *out_lo, void *out_hi, int batch, int64_t pixels, int channels, int dtype, void *stream);
+int64_t ood_alignnet_res0_workspace(int batch, int64_t pixels, int channels, int dtype);
+int ood_alignnet_res0_stats(const void *t, const float *st2, const float *w, const float *bias, const void *cur,
+                            const void *enc, const float *st6, void *out, float *workspace, float *stats_out, float eps,
+                            int batch, int64_t pixels, int channels, int dtype, void *stream);
 
 /* ---- a11. warp + alpha mix (helpers.py:168-177) on NHWC features:
  *      out[b,y,x,:] = bilinear(gen[b], lin_x[x]+dx, lin_y[y]+dy)*alpha + gen[b,y,x,:]*(1-alpha)

@@ -19,7 +19,7 @@ class ConvArgs(C.Structure):
                 ('s_next', c_void_p), ('batch', c_int), ('h', c_int), ('w', c_int), ('cin', c_int), ('cout', c_int),
                 ('transposed', c_int), ('act', c_int), ('impl', c_int), ('dtype', c_int), ('out_f32', c_int), ('prelu_slope', c_void_p),
                 ('rgb_w', c_void_p), ('rgb_bias', c_void_p), ('rgb_skip', c_void_p), ('rgb_out', c_void_p), ('rgb_taps', c_float * 4),
-                ('groups', c_int), ('in_shared', c_int)]
+                ('groups', c_int), ('in_shared', c_int), ('acc_in', c_void_p)]
 
 
 class BlurActArgs(C.Structure):
@@ -72,6 +72,9 @@ _SIGS = {
     'ood_alignnet_front': ([c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_i64, c_int, c_int, c_void_p], c_int),
     'ood_alignnet_res0': ([c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_i64, c_int,
                            c_int, c_void_p], c_int),
+    'ood_alignnet_front_split': ([c_void_p] * 7 + [c_int, c_i64, c_int, c_int, c_void_p], c_int),
+    'ood_alignnet_res0_workspace': ([c_int, c_i64, c_int, c_int], c_i64),
+    'ood_alignnet_res0_stats': ([c_void_p] * 10 + [c_float, c_int, c_i64, c_int, c_int, c_void_p], c_int),
     'ood_in_apply': ([c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_i64, c_int, c_int, c_void_p], c_int),
     'ood_warp_mix': ([c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p], c_int),
     'ood_mask_blend': ([C.POINTER(c_void_p), C.POINTER(c_int), c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,

@@ -38,6 +38,14 @@ template <> __device__ __forceinline__ void store_pairs<__nv_bfloat16>(__nv_bflo
     *reinterpret_cast<uint4 *>(p) = r;
 }
 
+// values as they will read back from storage type T
+template <typename T> __device__ __forceinline__ void round_pairs(float2 *v);
+template <> __device__ __forceinline__ void round_pairs<float>(float2 *) {}
+template <> __device__ __forceinline__ void round_pairs<__nv_bfloat16>(float2 *v) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = unpack_bf16x2(pack_bf16x2(v[j].x, v[j].y));
+}
+
 // ---------------------------------------------------------------------------------------------- statistics
 // partial[b][chunk][c][K]: K = 2 (sum x, sum x^2) or 5 (+ sum y, sum y^2, sum xy); packed fp32x2 accumulation
 template <typename T, int K>
@@ -190,19 +198,28 @@ static inline void pix_grid(int C, int N, int64_t P, int batch, dim3 &grid, int6
     grid = dim3((unsigned)((P + chunk - 1) / chunk), batch);
 }
 
-// mode 0 (front): out[b,p,0:C]  = (IN(cur)-IN(enc)) * rstd_d * w[c]   + bias[c]
-//                 out[b,p,C:2C] =  IN(enc)          * rstd_e2 * w[C+c] + bias[C+c]          (conv input of block 0)
+// mode 0 (front): lo[b,p,0:C] = (IN(cur)-IN(enc)) * rstd_d * w[c]   + bias[c]
+//                 hi[b,p,0:C] =  IN(enc)          * rstd_e2 * w[C+c] + bias[C+c]            (conv input of block 0)
+//                 lo = out, hi = out_hi, both with a pixel pitch of `pitch` channels: one [.,2C] tensor (out_hi = out + C,
+//                 pitch 2C) or two [.,C] tensors; out_hi == nullptr skips the hi half (it does not depend on `cur`, so the
+//                 second alignment cycle does not rebuild it)
 // mode 1 (res0):  out = (t - mu_t) * rstd_t * w + bias + z0,  z0 = cat[IN(cur)-IN(enc), IN(enc)]   (block-0 output)
+// mode 2:         mode 1 + per-block partial moments (sum, sum of squares) of `out` AS STORED (after the rounding to T):
+//                 partial[b][block][2C][2], finished by in_finalize_kernel -- the next InstanceNorm's statistics without a
+//                 pass over `out`
 template <typename T, int MODE>
 __global__ void __launch_bounds__(256) alignnet_ew_kernel(const T *__restrict__ cur, const T *__restrict__ enc,
                                                            const float *__restrict__ st6, const T *__restrict__ t,
                                                            const float *__restrict__ st2, const float *__restrict__ w,
-                                                           const float *__restrict__ bias, T *__restrict__ out, int64_t P,
-                                                           int C, int64_t chunk) {
+                                                           const float *__restrict__ bias, T *__restrict__ out,
+                                                           T *__restrict__ out_hi, int pitch, float *__restrict__ partial,
+                                                           int64_t P, int C, int64_t chunk) {
     constexpr int N = Vec<T>::N;
+    constexpr bool RES = MODE != 0;
     const int b = blockIdx.y;
     const PixSpan sp = pix_span<N>(C, P, chunk);
-    if (!sp.active) return;
+    if (MODE != 2 && !sp.active) return;
+    if (MODE == 2 && !sp.active) { __syncthreads(); return; }       // cv divides 256 on this path (host check): never taken
     // lo = tl*ct_lo + cu*a1 + en*a2 + a3 ; hi = th*ct_hi + en*b1 + b2      (channel pairs: FFMA2)
     constexpr int N2 = N / 2;
     float2 a1[N2], a2[N2], a3[N2], b1[N2], b2[N2], ctl[N2], cth[N2];
@@ -225,16 +242,22 @@ __global__ void __launch_bounds__(256) alignnet_ew_kernel(const T *__restrict__ 
         if (j & 1) { a1[j / 2].y = va1; a2[j / 2].y = va2; a3[j / 2].y = va3; b1[j / 2].y = vb1; b2[j / 2].y = vb2; ctl[j / 2].y = vctl; cth[j / 2].y = vcth; }
         else       { a1[j / 2].x = va1; a2[j / 2].x = va2; a3[j / 2].x = va3; b1[j / 2].x = vb1; b2[j / 2].x = vb2; ctl[j / 2].x = vctl; cth[j / 2].x = vcth; }
     }
-    const int64_t s1 = (int64_t)sp.step * C, s2 = 2 * s1;
+    const int64_t s1 = (int64_t)sp.step * C, s2 = 2 * s1, so = (int64_t)sp.step * pitch;
     const T *cup = cur + ((int64_t)b * P + sp.p) * C + sp.c, *enp = enc + ((int64_t)b * P + sp.p) * C + sp.c;
-    const T *tp = MODE == 1 ? t + ((int64_t)b * P + sp.p) * 2 * C + sp.c : nullptr;
-    T *op = out + ((int64_t)b * P + sp.p) * 2 * C + sp.c;
+    const T *tp = RES ? t + ((int64_t)b * P + sp.p) * 2 * C + sp.c : nullptr;
+    T *op = out + ((int64_t)b * P + sp.p) * pitch + sp.c;
+    T *oph = out_hi ? out_hi + ((int64_t)b * P + sp.p) * pitch + sp.c : nullptr;
+    float2 m_lo[MODE == 2 ? N2 : 1][2], m_hi[MODE == 2 ? N2 : 1][2];
+    if constexpr (MODE == 2) {
+#pragma unroll
+        for (int j = 0; j < N2; ++j) { m_lo[j][0] = m_lo[j][1] = m_hi[j][0] = m_hi[j][1] = f2(0.f); }
+    }
 #pragma unroll 2
     for (int64_t p = sp.p; p < sp.p_end; p += sp.step) {
         float2 cu[N2], en[N2], lo[N2], hi[N2];
         load_pairs<T>(cup, cu);
         load_pairs<T>(enp, en);
-        if constexpr (MODE == 1) {
+        if constexpr (RES) {
             float2 tl[N2], th[N2];
             load_pairs<T>(tp, tl);
             load_pairs<T>(tp + C, th);
@@ -251,9 +274,39 @@ __global__ void __launch_bounds__(256) alignnet_ew_kernel(const T *__restrict__ 
                 hi[j] = fma2(en[j], b1[j], b2[j]);
             }
         }
+        if constexpr (MODE == 2) {
+            round_pairs<T>(lo);
+            round_pairs<T>(hi);
+#pragma unroll
+            for (int j = 0; j < N2; ++j) {
+                m_lo[j][0] = add2(m_lo[j][0], lo[j]); m_lo[j][1] = fma2(lo[j], lo[j], m_lo[j][1]);
+                m_hi[j][0] = add2(m_hi[j][0], hi[j]); m_hi[j][1] = fma2(hi[j], hi[j], m_hi[j][1]);
+            }
+        }
         store_pairs<T>(op, lo);
-        store_pairs<T>(op + C, hi);
-        cup += s1; enp += s1; op += s2;
+        if (MODE != 0 || oph) store_pairs<T>(oph, hi);
+        cup += s1; enp += s1; op += so;
+        if (MODE != 0 || oph) oph += so;
+    }
+    if constexpr (MODE == 2) {
+        // fixed-order reduction over the block's pixel lanes: red[lane][channel of 2C][2]
+        __shared__ float red[256 * N * 4];
+        const int lane = threadIdx.x / (C / N);
+        float *r = red + (size_t)lane * 2 * C * 2;
+#pragma unroll
+        for (int j = 0; j < N2; ++j) {
+            float *q = r + (sp.c + 2 * j) * 2;
+            q[0] = m_lo[j][0].x; q[1] = m_lo[j][1].x; q[2] = m_lo[j][0].y; q[3] = m_lo[j][1].y;
+            q += 2 * C;
+            q[0] = m_hi[j][0].x; q[1] = m_hi[j][1].x; q[2] = m_hi[j][0].y; q[3] = m_hi[j][1].y;
+        }
+        __syncthreads();
+        const int lanes = 256 / (C / N);
+        for (int i = threadIdx.x; i < 4 * C; i += 256) {
+            float sum = 0.f;
+            for (int l = 0; l < lanes; ++l) sum += red[(size_t)l * 4 * C + i];
+            partial[((int64_t)b * gridDim.x + blockIdx.x) * 4 * C + i] = sum;
+        }
     }
 }
 
@@ -345,9 +398,9 @@ extern "C" int ood_alignnet_front(const void *cur, const void *enc, const float 
     pix_grid(channels, N, pixels, batch, grid, chunk);
     cudaStream_t s = (cudaStream_t)stream;
     if (dtype == OOD_F32)
-        alignnet_ew_kernel<float, 0><<<grid, 256, 0, s>>>((const float *)cur, (const float *)enc, st6, nullptr, nullptr, w, bias, (float *)out, pixels, channels, chunk);
+        alignnet_ew_kernel<float, 0><<<grid, 256, 0, s>>>((const float *)cur, (const float *)enc, st6, nullptr, nullptr, w, bias, (float *)out, (float *)out + channels, 2 * channels, nullptr, pixels, channels, chunk);
     else
-        alignnet_ew_kernel<__nv_bfloat16, 0><<<grid, 256, 0, s>>>((const __nv_bfloat16 *)cur, (const __nv_bfloat16 *)enc, st6, nullptr, nullptr, w, bias, (__nv_bfloat16 *)out, pixels, channels, chunk);
+        alignnet_ew_kernel<__nv_bfloat16, 0><<<grid, 256, 0, s>>>((const __nv_bfloat16 *)cur, (const __nv_bfloat16 *)enc, st6, nullptr, nullptr, w, bias, (__nv_bfloat16 *)out, (__nv_bfloat16 *)out + channels, 2 * channels, nullptr, pixels, channels, chunk);
     return check_launch("alignnet_front");
 }
 
@@ -364,10 +417,58 @@ extern "C" int ood_alignnet_res0(const void *t, const float *st2, const float *w
     pix_grid(channels, N, pixels, batch, grid, chunk);
     cudaStream_t s = (cudaStream_t)stream;
     if (dtype == OOD_F32)
-        alignnet_ew_kernel<float, 1><<<grid, 256, 0, s>>>((const float *)cur, (const float *)enc, st6, (const float *)t, st2, w, bias, (float *)out, pixels, channels, chunk);
+        alignnet_ew_kernel<float, 1><<<grid, 256, 0, s>>>((const float *)cur, (const float *)enc, st6, (const float *)t, st2, w, bias, (float *)out, (float *)out + channels, 2 * channels, nullptr, pixels, channels, chunk);
     else
-        alignnet_ew_kernel<__nv_bfloat16, 1><<<grid, 256, 0, s>>>((const __nv_bfloat16 *)cur, (const __nv_bfloat16 *)enc, st6, (const __nv_bfloat16 *)t, st2, w, bias, (__nv_bfloat16 *)out, pixels, channels, chunk);
+        alignnet_ew_kernel<__nv_bfloat16, 1><<<grid, 256, 0, s>>>((const __nv_bfloat16 *)cur, (const __nv_bfloat16 *)enc, st6, (const __nv_bfloat16 *)t, st2, w, bias, (__nv_bfloat16 *)out, (__nv_bfloat16 *)out + channels, 2 * channels, nullptr, pixels, channels, chunk);
     return check_launch("alignnet_res0");
+}
+
+extern "C" int ood_alignnet_front_split(const void *cur, const void *enc, const float *st6, const float *w, const float *bias,
+                                        void *out_lo, void *out_hi, int batch, int64_t pixels, int channels, int dtype,
+                                        void *stream) {
+    using namespace ood;
+    OOD_REQUIRE(cur && enc && st6 && w && bias && out_lo && batch > 0 && batch <= 65535 && pixels > 0, "alignnet_front_split: bad arguments");
+    const int N = dtype == OOD_F32 ? 4 : 8;
+    OOD_REQUIRE(dtype == OOD_F32 || dtype == OOD_BF16, "alignnet_front_split: bad dtype");
+    OOD_REQUIRE(channels % N == 0, "alignnet_front_split: channels (%d) must be a multiple of %d", channels, N);
+    OOD_REQUIRE(channels / N <= 256, "alignnet_front_split: too many channels (%d)", channels);
+    dim3 grid; int64_t chunk;
+    pix_grid(channels, N, pixels, batch, grid, chunk);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (dtype == OOD_F32)
+        alignnet_ew_kernel<float, 0><<<grid, 256, 0, s>>>((const float *)cur, (const float *)enc, st6, nullptr, nullptr, w, bias, (float *)out_lo, (float *)out_hi, channels, nullptr, pixels, channels, chunk);
+    else
+        alignnet_ew_kernel<__nv_bfloat16, 0><<<grid, 256, 0, s>>>((const __nv_bfloat16 *)cur, (const __nv_bfloat16 *)enc, st6, nullptr, nullptr, w, bias, (__nv_bfloat16 *)out_lo, (__nv_bfloat16 *)out_hi, channels, nullptr, pixels, channels, chunk);
+    return check_launch("alignnet_front_split");
+}
+
+extern "C" int64_t ood_alignnet_res0_workspace(int batch, int64_t pixels, int channels, int dtype) {
+    using namespace ood;
+    dim3 grid; int64_t chunk;
+    pix_grid(channels, dtype == OOD_F32 ? 4 : 8, pixels, batch > 0 ? batch : 1, grid, chunk);
+    return (int64_t)batch * grid.x * 4 * channels * (int64_t)sizeof(float);
+}
+
+extern "C" int ood_alignnet_res0_stats(const void *t, const float *st2, const float *w, const float *bias, const void *cur,
+                                       const void *enc, const float *st6, void *out, float *workspace, float *stats_out,
+                                       float eps, int batch, int64_t pixels, int channels, int dtype, void *stream) {
+    using namespace ood;
+    OOD_REQUIRE(t && st2 && w && bias && cur && enc && st6 && out && workspace && stats_out && batch > 0 && batch <= 65535 && pixels > 0,
+                "alignnet_res0_stats: bad arguments");
+    const int N = dtype == OOD_F32 ? 4 : 8;
+    OOD_REQUIRE(dtype == OOD_F32 || dtype == OOD_BF16, "alignnet_res0_stats: bad dtype");
+    OOD_REQUIRE(channels % N == 0 && channels / N <= 256 && 256 % (channels / N) == 0,
+                "alignnet_res0_stats: channels / %d (%d) must divide 256", N, channels / N);
+    dim3 grid; int64_t chunk;
+    pix_grid(channels, N, pixels, batch, grid, chunk);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (dtype == OOD_F32)
+        alignnet_ew_kernel<float, 2><<<grid, 256, 0, s>>>((const float *)cur, (const float *)enc, st6, (const float *)t, st2, w, bias, (float *)out, (float *)out + channels, 2 * channels, workspace, pixels, channels, chunk);
+    else
+        alignnet_ew_kernel<__nv_bfloat16, 2><<<grid, 256, 0, s>>>((const __nv_bfloat16 *)cur, (const __nv_bfloat16 *)enc, st6, (const __nv_bfloat16 *)t, st2, w, bias, (__nv_bfloat16 *)out, (__nv_bfloat16 *)out + channels, 2 * channels, workspace, pixels, channels, chunk);
+    const int64_t total = (int64_t)batch * 2 * channels;
+    in_finalize_kernel<<<ceil_div(total, 256), 256, 0, s>>>(workspace, stats_out, pixels, 2 * channels, (int)grid.x, eps, total);
+    return check_launch("alignnet_res0_stats", 2);
 }
 
 extern "C" int ood_in_apply(const void *x, const float *st2, const float *w, const float *bias, void *out, int batch,

@@ -100,6 +100,7 @@ struct ConvEpilogue {
     int act;                // 0 none | 1 leaky-ReLU(0.2)*sqrt2 | 2 PReLU(prelu[c])
     int out_f32;
     const float *prelu;     // [Co], act == 2
+    const float *acc_in;    // fp32 NHWC [B,OH,OW,Co] added to the accumulator first (tcgen05 path), or null
     // fused ToRGB (model.py:363-372): rgb_out[b,k,Y,X] = sum_o y[o]*rgb_w[b,k,o] + rgb_bias[k] + up2fir(rgb_skip)[b,k,Y,X]
     const float *rgb_w, *rgb_bias, *rgb_skip;
     float *rgb_out;
@@ -109,7 +110,7 @@ struct ConvEpilogue {
 static inline ConvEpilogue make_epilogue(const ood_conv3x3_args &a, int out_f32) {
     ConvEpilogue e{};
     e.out_y = a.out_y; e.out_ys = a.out_ys; e.d = a.d; e.noise = a.noise; e.noise_w = a.noise_w; e.bias = a.bias;
-    e.s_next = a.s_next; e.noise_bstride = a.noise_bstride; e.act = a.act; e.out_f32 = out_f32; e.prelu = a.prelu_slope;
+    e.s_next = a.s_next; e.noise_bstride = a.noise_bstride; e.act = a.act; e.out_f32 = out_f32; e.prelu = a.prelu_slope; e.acc_in = a.acc_in;
     e.rgb_w = a.rgb_w; e.rgb_bias = a.rgb_bias; e.rgb_skip = a.rgb_skip; e.rgb_out = a.rgb_out;
     for (int i = 0; i < 4; ++i) e.rgb_k[i] = a.rgb_taps[3 - i];
     return e;

@@ -158,7 +158,7 @@ __device__ __forceinline__ TileCoord decode_tile(const TcParams &p, int tile, in
     return tc;
 }
 
-template <int BN, int BK>
+template <int BN, int BK, bool SEED = false>
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
     using Cfg = TcCfg<BN, BK>;
@@ -258,6 +258,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                 for (int k = 0; k < 3; ++k) rgb_tail[k] = rgb_finish(p.ep, 0.f, b, k, Y, X, p.OH, p.OW);
             }
+            // accumulator seed: this pixel's 32-channel run of the fp32 partial, fetched one chunk ahead of the TMEM read so
+            // that its latency hides behind the previous chunk's stores (and, for chunk 0, behind the wait for the MMAs)
+            const float4 *seed = (SEED && p.ep.acc_in && valid) ? reinterpret_cast<const float4 *>(p.ep.acc_in + pix * p.cout + tc.n0) : nullptr;
+            float4 sd[8], sdn[8] = {};
+            if (SEED && seed) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) sd[j] = __ldg(seed + j);
+            }
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN;
@@ -265,6 +273,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll 1
             for (int ch = 0; ch < BN / 32; ++ch) {
                 uint32_t r[32];
+                if (SEED && seed && ch + 1 < BN / 32) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) sdn[j] = __ldg(seed + (ch + 1) * 8 + j);
+                }
                 tmem_ld32(taddr + ch * 32, r);
                 tmem_ld_wait();
                 if (valid) {
@@ -272,6 +284,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     float v[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                    if (SEED && seed) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            v[4 * j] += sd[j].x; v[4 * j + 1] += sd[j].y; v[4 * j + 2] += sd[j].z; v[4 * j + 3] += sd[j].w;
+                            sd[j] = sdn[j];
+                        }
+                    }
                     if (p.ep.d) {
                         const float4 *dp = reinterpret_cast<const float4 *>(p.ep.d + (int64_t)b * p.cout + n);
 #pragma unroll
@@ -381,10 +400,10 @@ static EncodeTiledFn get_encode_fn() {
 
 static int pow2_ceil(int v) { int r = 1; while (r < v) r <<= 1; return r; }
 
-template <int BN, int BK>
+template <int BN, int BK, bool SEED = false>
 static int launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, const TcParams &p, cudaStream_t st) {
     using Cfg = TcCfg<BN, BK>;
-    auto kern = conv_tc_kernel<BN, BK>;
+    auto kern = conv_tc_kernel<BN, BK, SEED>;
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
@@ -439,13 +458,14 @@ int conv3x3_tc(const ood_conv3x3_args &a, cudaStream_t st) {
         }
         // few-pixel problems (the tails of the encoder's style heads) are bound by streaming the weights: narrower N
         // tiles put more SMs on that stream
-        if (tiles >= kNumSMs || BN <= 64 || a.rgb_out) break;
+        if (tiles >= kNumSMs || BN <= (a.acc_in ? 128 : 64) || a.rgb_out) break;     // seeded accumulators: 128 / 256-wide tiles only
         BN >>= 1;
     }
     p.total_tiles = tiles;
     OOD_REQUIRE(!a.rgb_out || (p.n_tiles_n == 1 && !a.transposed), "conv3x3 tc: the fused ToRGB epilogue needs Co == tile N (Co <= 256) and the stride-1 form");
     p.ep = make_epilogue(a, a.out_f32);
     p.out_bf16 = 1;
+    OOD_REQUIRE(!a.acc_in || (a.transposed != 1 && (uintptr_t)a.acc_in % 16 == 0), "conv3x3 tc: acc_in needs a single-phase form and 16-byte alignment");
 
     CUtensorMap tmA, tmB;
     {
@@ -468,6 +488,12 @@ int conv3x3_tc(const ood_conv3x3_args &a, cudaStream_t st) {
                             CU_TENSOR_MAP_INTERLEAVE_NONE, BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { set_error("conv3x3 tc: weight tensor map encode failed (%d)", (int)r); return OOD_ERR_CUDA; }
+    }
+    if (a.acc_in) {     // seeded accumulators: built for the wide tiles only (the AlignNet convolutions)
+        if (BN == 256 && BK == 64) return launch_tc<256, 64, true>(tmA, tmB, p, st);
+        if (BN == 128 && BK == 64) return launch_tc<128, 64, true>(tmA, tmB, p, st);
+        set_error("conv3x3 tc: acc_in needs cin %% 64 == 0 and a 128- or 256-wide N tile (cout %% 128 == 0), got cin %d cout %d", a.cin, a.cout);
+        return OOD_ERR_ARG;
     }
 #define OOD_TC_CASE(bn, bk) if (BN == bn && BK == bk) return launch_tc<bn, bk>(tmA, tmB, p, st)
     OOD_TC_CASE(256, 64); OOD_TC_CASE(128, 64); OOD_TC_CASE(64, 64); OOD_TC_CASE(32, 64);

@@ -216,10 +216,12 @@ def torgb_weight(w, s, scale=None):
 
 # ----------------------------------------------------------------------------------------------- convolution
 def conv3x3(x, weight, cout, transposed=False, impl=0, d=None, noise=None, noise_w=None, bias=None, s_next=None,
-            act=False, want_y=True, want_ys=False, out_f32=False, prelu=None, rgb=None, tag=None, groups=1, in_shared=False):
+            act=False, want_y=True, want_ys=False, out_f32=False, prelu=None, rgb=None, tag=None, groups=1, in_shared=False,
+            acc_in=None):
     """x NHWC [B,H,W,Ci] pre-modulated; weight packed for `impl`.  Returns (y, ys) (None where not requested).
-    rgb=(wrgb [B,3,Co], bias [3], skip NCHW fp32 or None, up taps): fused ToRGB, returns (y, ys, rgb_out NCHW fp32)."""
-    _cuda(x, weight, d, noise, noise_w, bias, s_next)
+    rgb=(wrgb [B,3,Co], bias [3], skip NCHW fp32 or None, up taps): fused ToRGB, returns (y, ys, rgb_out NCHW fp32).
+    acc_in: fp32 NHWC [B,OH,OW,Co] seed added to the accumulator before the epilogue (tcgen05 path)."""
+    _cuda(x, weight, d, noise, noise_w, bias, s_next, acc_in)
     assert x.is_contiguous()
     b, h, w, cin = x.shape
     if in_shared:            # grouped form on a shared input: every group convolves the same [images, ...] tensor
@@ -236,6 +238,9 @@ def conv3x3(x, weight, cout, transposed=False, impl=0, d=None, noise=None, noise
     a = ConvArgs(_ptr(x), _ptr(weight), _ptr(y), _ptr(ys), _ptr(d), _ptr(noise), nbs, _ptr(noise_w), _ptr(bias), _ptr(s_next),
                  b, h, w, cin, cout, int(transposed), 2 if prelu is not None else int(act), impl, _dt(x), int(out_f32), _ptr(prelu))
     a.groups, a.in_shared = int(groups), int(bool(in_shared))
+    if acc_in is not None:
+        assert acc_in.dtype == torch.float32 and acc_in.is_contiguous() and tuple(acc_in.shape) == (b, oh, ow, cout)
+        a.acc_in = _ptr(acc_in)
     rgb_out = None
     if rgb is not None:
         wrgb, rbias, rskip, rtaps = rgb
@@ -414,6 +419,32 @@ def alignnet_front(cur, enc, st6, w, bias):
         check(_lib.lib().ood_alignnet_front(_ptr(cur), _ptr(enc), _ptr(st6), _ptr(w), _ptr(bias), _ptr(out), b, h * wd, c,
                                             _dt(cur), _stream()), 'alignnet_front')
     return out
+
+
+def alignnet_front_split(cur, enc, st6, w, bias, want_hi=True):
+    """The two halves of alignnet_front as separate [B,H,W,C] tensors: (lo, hi); hi (the IN(enc) half, independent of `cur`)
+    is skipped with want_hi=False."""
+    _cuda(cur, enc, st6, w, bias)
+    b, h, wd, c = cur.shape
+    lo = torch.empty_like(cur)
+    hi = torch.empty_like(cur) if want_hi else None
+    with _timed('alignnet_ew', b * h * wd * c * _esize(cur) * (4 if want_hi else 3)):
+        check(_lib.lib().ood_alignnet_front_split(_ptr(cur), _ptr(enc), _ptr(st6), _ptr(w), _ptr(bias), _ptr(lo), _ptr(hi), b, h * wd, c,
+                                                  _dt(cur), _stream()), 'alignnet_front_split')
+    return lo, hi
+
+
+def alignnet_res0_stats(t, st2, w, bias, cur, enc, st6, eps=1e-5):
+    """alignnet_res0 + the (mean, rstd) [B,2C,2] of its output as stored, from the same pass."""
+    _cuda(t, st2, w, bias, cur, enc, st6)
+    b, h, wd, c = cur.shape
+    out = torch.empty_like(t)
+    ws = torch.empty(_lib.lib().ood_alignnet_res0_workspace(b, h * wd, c, _dt(cur)) // 4, device=cur.device, dtype=torch.float32)
+    st = torch.empty(b, 2 * c, 2, device=cur.device, dtype=torch.float32)
+    with _timed('alignnet_ew', b * h * wd * c * _esize(cur) * 6):
+        check(_lib.lib().ood_alignnet_res0_stats(_ptr(t), _ptr(st2), _ptr(w), _ptr(bias), _ptr(cur), _ptr(enc), _ptr(st6), _ptr(out),
+                                                 _ptr(ws), _ptr(st), float(eps), b, h * wd, c, _dt(cur), _stream()), 'alignnet_res0_stats')
+    return out, st
 
 
 def alignnet_res0(t, st2, w, bias, cur, enc, st6):

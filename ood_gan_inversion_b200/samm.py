@@ -3,7 +3,8 @@
 Same module tree and state-dict keys (`alignment.body.body.{0,1}.{res_layer,shortcut_layer}.*`, `alignment.blur.kernel`,
 `weight`, `noiseInj.weight`).  The field head (tanh/sigmoid + FIR blur + accumulate/PRM/clip + coarse-level bicubic PRM),
 the flow warp + alpha mix and (in arch.py) the mask compose + blend are single fused sm_100a kernels; the AlignNet
-convolution stacks stay cuDNN library calls in this round ("next").
+convolution stacks run on the package's tcgen05 convolution in shared-weight mode (AlignNet.raw_nhwc; SURVEY.md section
+8(f) rank 1), with the `enc`-only half of the first convolution computed once per level and reused by every cycle.
 """
 import torch
 from torch import nn
@@ -100,7 +101,12 @@ class AlignNet(nn.Module):
                 wc = b1.res_layer[1].weight.detach().float()                                        # [3, 2C, 3, 3]
                 w27 = torch.zeros(32, wc.shape[1], device=wc.device)
                 w27[:27] = wc.permute(2, 3, 0, 1).reshape(27, -1)
-                pk = dict(wa=K.pack_conv_weight(b0.res_layer[1].weight.detach(), dt, cim),
+                wa = b0.res_layer[1].weight.detach()
+                half = wa.shape[1] // 2
+                # first convolution split along its input channels: [IN(cur)-IN(enc)] half | [IN(enc)] half (see raw_nhwc)
+                split = dict(wa_lo=K.pack_conv_weight(wa[:, :half].contiguous(), dt, cim),
+                             wa_hi=K.pack_conv_weight(wa[:, half:].contiguous(), dt, cim)) if not cim else {}
+                pk = dict(wa=K.pack_conv_weight(wa, dt, cim), **split,
                           wb=K.pack_conv_weight(b0.res_layer[3].weight.detach(), dt, cim),
                           wc=K.pack_conv1x1_weight(w27, dt, cim), cp=32, w27=w27.contiguous(),
                           w1=b1.shortcut_layer[0].weight.detach().float().reshape(3, -1).contiguous())
@@ -108,10 +114,14 @@ class AlignNet(nn.Module):
             hit = self._pk
         return hit[1]
 
-    def raw_nhwc(self, cur, enc, fold=False):
+    def raw_nhwc(self, cur, enc, fold=False, carry=None):
         """cur, enc: NHWC [B,R,R,C] in the pipeline's storage type -> pre-activation field [B,3,R,R] fp32.
         fold=True returns (r2, shortcut, coef) instead: the field is r2*coef[...,0] + shortcut*coef[...,1] + coef[...,2], which
-        ood_field_step applies on load (the two closing InstanceNorms and the residual sum never take a pass of their own)."""
+        ood_field_step applies on load (the two closing InstanceNorms and the residual sum never take a pass of their own).
+        carry: a dict the caller keeps across the alignment cycles of ONE `enc` (SPM_Warp.forward_nhwc).  The first
+        convolution is linear in its input cat[INaff(IN(cur)-IN(enc)), INaff(IN(enc))]; its second half depends on `enc`
+        alone, so that half of the contraction (fp32 accumulators) is computed in the first cycle and seeds the accumulators
+        of the [IN(cur)-IN(enc)] half in every cycle: 3.5 instead of 4 wide convolutions per two-cycle level."""
         b0, b1 = self.body[0], self.body[1]
         pk = self._packed()
         f = lambda p: p.detach().float().contiguous()
@@ -119,11 +129,24 @@ class AlignNet(nn.Module):
         impl = sg._impl()
         eps = self.norm.eps
         st6 = K.in_stats(cur, enc, eps)
-        x = K.alignnet_front(cur, enc, st6, f(b0.res_layer[0].weight), f(b0.res_layer[0].bias))
-        x, _ = K.conv3x3(x, pk['wa'], 2 * c, impl=impl, prelu=f(b0.res_layer[2].weight))
+        split = impl == 0 and carry is not None and c % 64 == 0
+        if split:
+            seed = carry.get('seed')
+            lo, hi = K.alignnet_front_split(cur, enc, st6, f(b0.res_layer[0].weight), f(b0.res_layer[0].bias), want_hi=seed is None)
+            if seed is None:
+                seed, _ = K.conv3x3(hi, pk['wa_hi'], 2 * c, impl=0, out_f32=True)
+                carry['seed'] = seed
+            x, _ = K.conv3x3(lo, pk['wa_lo'], 2 * c, impl=0, prelu=f(b0.res_layer[2].weight), acc_in=seed)
+        else:
+            x = K.alignnet_front(cur, enc, st6, f(b0.res_layer[0].weight), f(b0.res_layer[0].bias))
+            x, _ = K.conv3x3(x, pk['wa'], 2 * c, impl=impl, prelu=f(b0.res_layer[2].weight))
         x, _ = K.conv3x3(x, pk['wb'], 2 * c, impl=impl)
-        out0 = K.alignnet_res0(x, K.in_stats(x, None, eps), f(b0.res_layer[4].weight), f(b0.res_layer[4].bias), cur, enc, st6)
-        st = K.in_stats(out0, None, eps)
+        nvec = c // (8 if cur.dtype == torch.bfloat16 else 4)
+        if nvec <= 256 and 256 % nvec == 0:
+            out0, st = K.alignnet_res0_stats(x, K.in_stats(x, None, eps), f(b0.res_layer[4].weight), f(b0.res_layer[4].bias), cur, enc, st6, eps)
+        else:
+            out0 = K.alignnet_res0(x, K.in_stats(x, None, eps), f(b0.res_layer[4].weight), f(b0.res_layer[4].bias), cur, enc, st6)
+            st = K.in_stats(out0, None, eps)
         if impl == 0:
             # InstanceNorm(out0) folded into the projection: W27 . (g*out0 + h) = (W27 diag(g_b)) . out0 + W27 . h_b -- one weight
             # set per sample (grouped form, groups = batch) and a per-sample bias, so the normalised copy is never written
@@ -185,9 +208,10 @@ class SPM_Warp(nn.Module):
         if fused:
             src = src.permute(0, 2, 3, 1).contiguous()               # encoder features -> NHWC once per level
         cur, acc = target_nhwc, None
+        carry = {}                      # per-call state shared by the cycles (the enc-only part of the first convolution)
         for k in range(self.cycle_align):
             if fused:
-                z, z2, coef = self.body.raw_nhwc(cur, src, fold=True)
+                z, z2, coef = self.body.raw_nhwc(cur, src, fold=True, carry=carry if self.cycle_align > 1 else None)
             else:
                 z, z2, coef = self.body.raw(cur.permute(0, 3, 1, 2), src), None, None      # NHWC storage viewed as channels_last NCHW
             last = k == self.cycle_align - 1

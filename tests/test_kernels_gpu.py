@@ -581,3 +581,84 @@ def test_se_gate_and_residual(dtype, case):
     o2, t2 = K().se_residual(vd, bn_g=g2.to(DEV), bn_h=h2.to(DEV), want_out=False)
     assert o2 is None
     torch.testing.assert_close(nchw(t2), v * g2[None, :, None, None] + h2[None, :, None, None], **tol)
+
+
+@pytest.mark.parametrize('case', [dict(b=2, h=24, w=20, ci=64, co=128), dict(b=3, h=16, w=16, ci=128, co=256),
+                                  dict(b=1, h=9, w=37, ci=64, co=512)])
+def test_conv3x3_seeded_accumulator(case):
+    """ood_conv3x3_args.acc_in: a convolution over cat[xa, xb] as conv(xa; W[:, :C]) seeded with the fp32 accumulators of
+    conv(xb; W[:, C:]) -- the split AlignNet.raw_nhwc uses across alignment cycles (SAMM/helpers.py:96-101,154-166)."""
+    b, h, w, ci, co = (case[k] for k in ('b', 'h', 'w', 'ci', 'co'))
+    dt = torch.bfloat16
+    xa, xb = rnd(b, ci, h, w, seed=1).to(dt).float(), rnd(b, ci, h, w, seed=2).to(dt).float()
+    wt = (0.05 * rnd(co, 2 * ci, 3, 3, seed=3)).to(dt).float()
+    slope = 0.25 + 0.1 * rnd(co, seed=4)
+    pack = lambda t: K().pack_conv_weight(t.contiguous().to(DEV), dt, False)
+    seed, _ = K().conv3x3(nhwc(xb, dt), pack(wt[:, ci:]), co, impl=0, out_f32=True)
+    assert seed.dtype == torch.float32
+    torch.testing.assert_close(nchw(seed), F.conv2d(xb.double(), wt[:, ci:].double(), padding=1).float(), rtol=1e-4, atol=1e-4)
+    y, _ = K().conv3x3(nhwc(xa, dt), pack(wt[:, :ci]), co, impl=0, prelu=slope.to(DEV), acc_in=seed)
+    ref = F.prelu(F.conv2d(torch.cat([xa, xb], 1).double(), wt.double(), padding=1).float(), slope)
+    torch.testing.assert_close(nchw(y), ref, rtol=1e-2, atol=1e-2)
+    # against the unsplit kernel: same fp32 sum in another order, then one bf16 rounding
+    full, _ = K().conv3x3(nhwc(torch.cat([xa, xb], 1), dt), pack(wt), co, impl=0, prelu=slope.to(DEV))
+    diff = (y.float() - full.float()).abs()
+    assert float((diff > 2 ** -7 * full.float().abs().clamp_min(2 ** -6)).float().mean()) == 0.0
+    # no activation, bias and d on top of the seed
+    d, bias = 0.5 + torch.rand(b, co, generator=g(5)), 0.1 * rnd(co, seed=6)
+    y2, _ = K().conv3x3(nhwc(xa, dt), pack(wt[:, :ci]), co, impl=0, d=d.to(DEV), bias=bias.to(DEV), acc_in=seed)
+    ref2 = F.conv2d(torch.cat([xa, xb], 1).double(), wt.double(), padding=1).float() * d[:, :, None, None] + bias[None, :, None, None]
+    torch.testing.assert_close(nchw(y2), ref2, rtol=1e-2, atol=1e-2)
+    with pytest.raises(RuntimeError):          # the seed is a tcgen05-path feature
+        K().conv3x3(nhwc(xa, torch.float32), K().pack_conv_weight(wt[:, :ci].contiguous().to(DEV), torch.float32, True), co, impl=1,
+                    acc_in=seed)
+
+
+@pytest.mark.parametrize('dtype,c', [(torch.float32, 32), (torch.bfloat16, 64), (torch.bfloat16, 128)])
+def test_alignnet_split_front_and_fused_statistics(dtype, c):
+    b, h, w = 2, 37, 53
+    cur, enc = (2 * rnd(b, c, h, w, seed=1) + 1).to(dtype).float(), (0.5 * rnd(b, c, h, w, seed=2) - 1).to(dtype).float()
+    w0, b0 = (1 + 0.1 * rnd(2 * c, seed=3)).to(DEV), (0.1 * rnd(2 * c, seed=4)).to(DEV)
+    cu, en = nhwc(cur, dtype), nhwc(enc, dtype)
+    st6 = K().in_stats(cu, en)
+    front = K().alignnet_front(cu, en, st6, w0, b0)
+    lo, hi = K().alignnet_front_split(cu, en, st6, w0, b0)
+    assert torch.equal(lo, front[..., :c]) and torch.equal(hi, front[..., c:])
+    lo2, none = K().alignnet_front_split(cu, en, st6, w0, b0, want_hi=False)
+    assert none is None and torch.equal(lo2, lo)
+    t = nhwc(rnd(b, 2 * c, h, w, seed=5), dtype)
+    st2 = K().in_stats(t)
+    res = K().alignnet_res0(t, st2, w0, b0, cu, en, st6)
+    res_s, st = K().alignnet_res0_stats(t, st2, w0, b0, cu, en, st6)
+    assert torch.equal(res_s, res)
+    ref = K().in_stats(res)
+    torch.testing.assert_close(st[..., 0], ref[..., 0], rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(st[..., 1], ref[..., 1], rtol=1e-4, atol=1e-5)
+    x = res.float()
+    torch.testing.assert_close(st[..., 0], x.mean((1, 2)), rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(st[..., 1], torch.rsqrt(x.var((1, 2), unbiased=False) + 1e-5), rtol=1e-4, atol=1e-4)
+
+
+def test_alignnet_cycle_carry_matches_unsplit_route():
+    """AlignNet.raw_nhwc with the per-level carry (enc-only half of the first convolution computed once, both cycles seeded
+    with it) against the route that runs the whole convolution every cycle, and against the torch module (raw)."""
+    import ood_gan_inversion_b200.stylegan as sgm
+    from ood_gan_inversion_b200.samm import AlignNet
+    sgm.set_precision('bf16')
+    torch.manual_seed(0)
+    c, r, b = 64, 24, 2
+    net = AlignNet(c, 3, scale=0.08).to(DEV)
+    for m in net.modules():
+        if isinstance(m, torch.nn.Conv2d):
+            torch.nn.init.xavier_normal_(m.weight)
+    enc, cur1, cur2 = (nhwc(rnd(b, c, r, r, seed=s), torch.bfloat16) for s in (1, 2, 3))
+    carry = {}
+    with torch.no_grad():
+        a1 = net.raw_nhwc(cur1, enc, carry=carry)
+        assert 'seed' in carry and carry['seed'].dtype == torch.float32
+        a2 = net.raw_nhwc(cur2, enc, carry=carry)
+        p1, p2 = net.raw_nhwc(cur1, enc), net.raw_nhwc(cur2, enc)
+        t2 = net.raw(cur2.permute(0, 3, 1, 2), enc.permute(0, 3, 1, 2))
+    torch.testing.assert_close(a1, p1, rtol=2e-2, atol=2e-2)
+    torch.testing.assert_close(a2, p2, rtol=2e-2, atol=2e-2)
+    torch.testing.assert_close(a2, t2, rtol=5e-2, atol=5e-2)
