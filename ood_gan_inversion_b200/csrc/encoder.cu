@@ -140,12 +140,50 @@ __global__ void __launch_bounds__(256) tap_sum_kernel(const float *__restrict__ 
     }
 }
 
+// Tiled form (Cp % 4 == 0): a block stages the (8+2) x (32+2) pixel neighbourhood of its 8 x 32 outputs in shared memory
+// with coalesced 16-byte loads -- every projection line is fetched once per block instead of by nine different threads, three
+// scalars at a time (that version was bound by L1 sector requests at 1.0 TB/s) -- and each thread then sums its 27 values from
+// shared memory (row pitch 33 words: conflict-free).
+constexpr int TSX = 32, TSY = 8, TSV = 7;          // TSV float4 = 28 >= 27 channels per pixel
+__global__ void __launch_bounds__(TSX * TSY) tap_sum_tile_kernel(const float *__restrict__ proj, float *__restrict__ out, int H, int W, int Cp) {
+    __shared__ float sp[(TSY + 2) * (TSX + 2)][33];
+    const int b = blockIdx.z, x0 = blockIdx.x * TSX, y0 = blockIdx.y * TSY;
+    const int64_t P = (int64_t)H * W;
+    const float *pb = proj + (int64_t)b * P * Cp;
+    for (int i = threadIdx.x; i < (TSY + 2) * (TSX + 2) * TSV; i += TSX * TSY) {
+        const int pixel = i / TSV, v = i - pixel * TSV;
+        const int ty = pixel / (TSX + 2), tx = pixel - ty * (TSX + 2);
+        const int y = y0 + ty - 1, x = x0 + tx - 1;
+        float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (y >= 0 && y < H && x >= 0 && x < W) val = __ldg(reinterpret_cast<const float4 *>(pb + ((int64_t)y * W + x) * Cp) + v);
+        float *d = &sp[pixel][4 * v];
+        d[0] = val.x; d[1] = val.y; d[2] = val.z; d[3] = val.w;
+    }
+    __syncthreads();
+    const int ty = threadIdx.x / TSX, tx = threadIdx.x - ty * TSX;
+    const int y = y0 + ty, x = x0 + tx;
+    if (y >= H || x >= W) return;
+    float acc[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {                  // same summation order as the scalar kernel (out-of-image taps add zero)
+        const float *q = sp[(ty + t / 3) * (TSX + 2) + tx + t % 3] + 3 * t;
+        acc[0] += q[0]; acc[1] += q[1]; acc[2] += q[2];
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) out[((int64_t)b * 3 + k) * P + (int64_t)y * W + x] = acc[k];
+}
+
 }  // namespace ood
 
 extern "C" int ood_tap_sum(const float *proj, float *out, int batch, int h, int w, int cp, void *stream) {
     using namespace ood;
     OOD_REQUIRE(proj && out && batch > 0 && batch <= 65535 && h > 0 && w > 0 && cp >= 27 && (int64_t)h * w < (1LL << 30), "tap_sum: bad arguments");
     const int64_t P = (int64_t)h * w;
+    if (cp % 4 == 0 && ((uintptr_t)proj % 16) == 0 && ceil_div(h, TSY) <= 65535) {
+        dim3 tg(ceil_div(w, TSX), ceil_div(h, TSY), batch);
+        tap_sum_tile_kernel<<<tg, TSX * TSY, 0, (cudaStream_t)stream>>>(proj, out, h, w, cp);
+        return check_launch("tap_sum");
+    }
     dim3 grid((unsigned)std::min<int64_t>((P + 255) / 256, kNumSMs * 16), batch);
     tap_sum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(proj, out, h, w, cp);
     return check_launch("tap_sum");

@@ -188,18 +188,26 @@ __global__ void __launch_bounds__(TT * TT) alignnet_tail_kernel(const float *__r
 }
 
 // coef[b][ch] = {rstd_r*w_r, rstd_s*w_s, b_r + b_s - mu_r*rstd_r*w_r - mu_s*rstd_s*w_s}
-__global__ void alignnet_tail_finalize_kernel(const float *__restrict__ partial, int nblocks, double n, float eps,
-                                              const float *__restrict__ wr, const float *__restrict__ br,
-                                              const float *__restrict__ ws, const float *__restrict__ bs, float *__restrict__ coef,
-                                              int total) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;        // b*3 + ch
+// One warp per (b, ch): the lanes stride over the block partials (up to 256 of them at 256 px) and combine in a fixed
+// shuffle order, so the result is deterministic; a single thread walking all partials took 21 us per launch.
+__global__ void __launch_bounds__(128) alignnet_tail_finalize_kernel(const float *__restrict__ partial, int nblocks, double n, float eps,
+                                                                      const float *__restrict__ wr, const float *__restrict__ br,
+                                                                      const float *__restrict__ ws, const float *__restrict__ bs,
+                                                                      float *__restrict__ coef, int total) {
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;        // b*3 + ch (warp-uniform)
+    const int lane = threadIdx.x & 31;
     if (i >= total) return;
     const int b = i / 3, ch = i % 3;
     double s[4] = {0, 0, 0, 0};
-    for (int k = 0; k < nblocks; ++k) {
-        const float *p = partial + ((int64_t)b * nblocks + k) * 12 + ch * 4;
-        for (int j = 0; j < 4; ++j) s[j] += p[j];
+    for (int k = lane; k < nblocks; k += 32) {
+        const float4 p = __ldg(reinterpret_cast<const float4 *>(partial + ((int64_t)b * nblocks + k) * 12 + ch * 4));
+        s[0] += p.x; s[1] += p.y; s[2] += p.z; s[3] += p.w;
     }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s[j] += __shfl_xor_sync(0xffffffffu, s[j], o);
+    if (lane) return;
     const double mr = s[0] / n, vr = fmax(s[1] / n - mr * mr, 0.0), ms = s[2] / n, vs = fmax(s[3] / n - ms * ms, 0.0);
     const double gr = wr[ch] / sqrt(vr + eps), gs = ws[ch] / sqrt(vs + eps);
     coef[i * 3 + 0] = (float)gr;
@@ -478,7 +486,7 @@ extern "C" int ood_alignnet_tail(const float *res, const float *shortcut, const 
     dim3 grid(nb, nb, batch);
     cudaStream_t st = (cudaStream_t)stream;
     alignnet_tail_kernel<<<grid, TT * TT, 0, st>>>(res, shortcut, prelu_slope, conv_w, r2, workspace, r);
-    alignnet_tail_finalize_kernel<<<ceil_div(batch * 3, 64), 64, 0, st>>>(workspace, nb * nb, (double)r * r, eps, in_res_w, in_res_b,
+    alignnet_tail_finalize_kernel<<<ceil_div(batch * 3, 4), 128, 0, st>>>(workspace, nb * nb, (double)r * r, eps, in_res_w, in_res_b,
                                                                            in_sc_w, in_sc_b, coef, batch * 3);
     return check_launch("alignnet_tail", 2);
 }

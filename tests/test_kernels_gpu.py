@@ -662,3 +662,16 @@ def test_alignnet_cycle_carry_matches_unsplit_route():
     torch.testing.assert_close(a1, p1, rtol=2e-2, atol=2e-2)
     torch.testing.assert_close(a2, p2, rtol=2e-2, atol=2e-2)
     torch.testing.assert_close(a2, t2, rtol=5e-2, atol=5e-2)
+
+
+@pytest.mark.parametrize('h,w,cp', [(70, 45, 32), (8, 32, 28), (33, 65, 27), (1, 1, 32), (256, 256, 32)])
+def test_tap_sum_tiled_and_scalar_forms(h, w, cp):
+    """ood_tap_sum (tiled shared-memory form when Cp % 4 == 0, scalar form otherwise) vs nine shifted slices."""
+    b = 2
+    proj = rnd(b, h, w, cp, seed=h + w).to(DEV)
+    out = K().tap_sum(proj)
+    pad = F.pad(proj, (0, 0, 1, 1, 1, 1))
+    ref = torch.zeros(b, 3, h, w, device=DEV)
+    for t in range(9):
+        ref += pad[:, t // 3:t // 3 + h, t % 3:t % 3 + w, 3 * t:3 * t + 3].permute(0, 3, 1, 2)
+    torch.testing.assert_close(out, ref, rtol=1e-5, atol=1e-5)
