@@ -137,8 +137,16 @@ typedef struct {
      * and a part that does not (AlignNet: cat[IN(cur)-IN(enc), IN(enc)], SAMM/helpers.py:96-101, over the alignment cycles
      * :154-166) runs the constant part once (out_f32 = 1, no epilogue terms) and seeds every later call with it. */
     const float *acc_in;
+    /* tiled = 1: the fp32 tensors of this call -- acc_in, and out_y when out_f32 = 1 -- are not NHWC but in the kernel's own
+     * tile order (ood_conv3x3_tiled_bytes() bytes; opaque, valid between calls with the same batch, h, w, cout and form).  An
+     * epilogue thread owns one pixel and 32 consecutive channels of it, so NHWC fp32 costs 32 separate 16-byte transactions
+     * per warp instruction; the tile order makes the same access one contiguous 512-byte run (measured on the 256 px
+     * AlignNet level: seeded half convolution 898 us with an NHWC seed against 505 us without any seed). */
+    int tiled;
 } ood_conv3x3_args;
 int ood_conv3x3(const ood_conv3x3_args *args_host, void *stream);
+/* bytes of a tile-order fp32 tensor for the tcgen05 path (0 when the arguments are outside that path) */
+int64_t ood_conv3x3_tiled_bytes(int batch, int h, int w, int cin, int cout, int transposed);
 
 /* ---- a1+a2+a6 fused: FIR blur (4x4 separable taps, pad (1,1)) of the transposed-conv output
  *      [B,2h+1,2w+1,C] -> [B,2h,2w,C], then the StyledConv epilogue (model.py:257, 283-292, fused_act.py:96):

@@ -101,6 +101,7 @@ struct ConvEpilogue {
     int out_f32;
     const float *prelu;     // [Co], act == 2
     const float *acc_in;    // fp32 NHWC [B,OH,OW,Co] added to the accumulator first (tcgen05 path), or null
+    int tiled;              // acc_in / fp32 out_y in tile order: float4 index ((tile*(BN/32) + chunk)*8 + j)*128 + row
     // fused ToRGB (model.py:363-372): rgb_out[b,k,Y,X] = sum_o y[o]*rgb_w[b,k,o] + rgb_bias[k] + up2fir(rgb_skip)[b,k,Y,X]
     const float *rgb_w, *rgb_bias, *rgb_skip;
     float *rgb_out;
@@ -110,7 +111,7 @@ struct ConvEpilogue {
 static inline ConvEpilogue make_epilogue(const ood_conv3x3_args &a, int out_f32) {
     ConvEpilogue e{};
     e.out_y = a.out_y; e.out_ys = a.out_ys; e.d = a.d; e.noise = a.noise; e.noise_w = a.noise_w; e.bias = a.bias;
-    e.s_next = a.s_next; e.noise_bstride = a.noise_bstride; e.act = a.act; e.out_f32 = out_f32; e.prelu = a.prelu_slope; e.acc_in = a.acc_in;
+    e.s_next = a.s_next; e.noise_bstride = a.noise_bstride; e.act = a.act; e.out_f32 = out_f32; e.prelu = a.prelu_slope; e.acc_in = a.acc_in; e.tiled = a.tiled;
     e.rgb_w = a.rgb_w; e.rgb_bias = a.rgb_bias; e.rgb_skip = a.rgb_skip; e.rgb_out = a.rgb_out;
     for (int i = 0; i < 4; ++i) e.rgb_k[i] = a.rgb_taps[3 - i];
     return e;

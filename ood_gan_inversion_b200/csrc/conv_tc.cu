@@ -133,7 +133,9 @@ struct TcCfg {
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kStages = (200 * 1024 / kStageBytes) > 8 ? 8 : (200 * 1024 / kStageBytes);
     static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
-    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int kEpiVecs = 7;                       // bias, prelu, d, s_next, rgb_w[3]: BN floats each, double buffered
+    static constexpr int kEpiBytes = 2 * kEpiVecs * BN * 4;
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kEpiBytes;
     static constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
 };
 
@@ -170,6 +172,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + S * Cfg::kStageBytes);
     uint64_t *full = bars, *empty = bars + S, *tfull = bars + 2 * S, *tempty = bars + 2 * S + 2;
     uint32_t *tmem_holder = reinterpret_cast<uint32_t *>(bars + 2 * S + 4);
+    float *epi_vecs = reinterpret_cast<float *>(smem + S * Cfg::kStageBytes + 256);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kchunks = p.cin / BK;
@@ -253,6 +256,32 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int64_t pix = ((int64_t)b * p.OH + Y) * p.OW + X;
             float nz = 0.f;
             if (valid && p.ep.noise) nz = nw * __ldg(p.ep.noise + b * p.ep.noise_bstride + (int64_t)Y * p.OW + X);
+            // Per-channel epilogue vectors of this tile staged in shared memory while the MMAs of the tile are still running:
+            // read from global memory inside the chunk loop they sat behind the TMEM load (an asm barrier for the compiler)
+            // and exposed an L2 round trip per vector per chunk (ncu: the top stall of the epilogue warps).  The per-sample
+            // vectors (d, s_next, rgb_w) are tile-uniform only when a tile holds one image (NB == 1); otherwise they stay global.
+            float *sv = epi_vecs + acc * (Cfg::kEpiVecs * BN);
+            const bool stg = p.NB == 1;
+            {
+                const int et = threadIdx.x - 64;
+                for (int i = et; i < BN; i += 128) {
+                    const int n = tc.n0 + i;
+                    if (p.ep.bias) sv[i] = __ldg(p.ep.bias + gofs + n);
+                    if (p.ep.act == 2) sv[BN + i] = __ldg(p.ep.prelu + gofs + n);
+                    if (stg) {
+                        if (p.ep.d) sv[2 * BN + i] = __ldg(p.ep.d + (int64_t)tc.b0 * p.cout + n);
+                        if (p.ep.out_ys) sv[3 * BN + i] = __ldg(p.ep.s_next + (int64_t)tc.b0 * p.cout + n);
+                        if (p.ep.rgb_out) {
+#pragma unroll
+                            for (int k = 0; k < 3; ++k) sv[(4 + k) * BN + i] = __ldg(p.ep.rgb_w + ((int64_t)tc.b0 * 3 + k) * p.cout + n);
+                        }
+                    }
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");      // the four epilogue warps only
+            }
+            auto vec4 = [&](int kind, const float *gvec, int ch, int j) -> float4 {      // float4 j of chunk ch of a per-sample vector
+                return stg ? *reinterpret_cast<const float4 *>(sv + kind * BN + ch * 32 + 4 * j) : __ldg(reinterpret_cast<const float4 *>(gvec) + j);
+            };
             float rgb_tail[3] = {0.f, 0.f, 0.f};      // fused ToRGB: bias + upsampled skip, independent of the accumulator
             if (p.ep.rgb_out && valid) {
 #pragma unroll
@@ -260,22 +289,39 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             // accumulator seed: this pixel's 32-channel run of the fp32 partial, fetched one chunk ahead of the TMEM read so
             // that its latency hides behind the previous chunk's stores (and, for chunk 0, behind the wait for the MMAs)
-            const float4 *seed = (SEED && p.ep.acc_in && valid) ? reinterpret_cast<const float4 *>(p.ep.acc_in + pix * p.cout + tc.n0) : nullptr;
+            // NHWC: this pixel's channel run, float4 j of chunk c at seed[c*8 + j]; tile order: at seed[(c*8 + j)*128] (lanes contiguous)
+            const int sstep = p.ep.tiled ? TBM : 1;
+            const float4 *seed = nullptr;
+            if (SEED && p.ep.acc_in && valid)
+                seed = p.ep.tiled ? reinterpret_cast<const float4 *>(p.ep.acc_in) + (int64_t)tile * (BN / 32) * 8 * TBM + row
+                                  : reinterpret_cast<const float4 *>(p.ep.acc_in + pix * p.cout + tc.n0);
+            if (SEED && p.ep.acc_in && p.ep.tiled && threadIdx.x == 64) {
+                // tile order: the seed of a tile is one contiguous block -- ask L2 for the NEXT tile's block now (a tile period
+                // ahead), and for this CTA's first tile at its start; the register prefetch below then only covers an L2 hit
+                const int64_t blk = (int64_t)BN * TBM * sizeof(float);
+                const char *base = reinterpret_cast<const char *>(p.ep.acc_in);
+                if (tile == (int)blockIdx.x)
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(base + (int64_t)tile * blk), "r"((uint32_t)blk) : "memory");
+                if (tile + (int)gridDim.x < p.total_tiles)
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(base + (int64_t)(tile + gridDim.x) * blk), "r"((uint32_t)blk) : "memory");
+            }
             float4 sd[8], sdn[8] = {};
             if (SEED && seed) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) sd[j] = __ldg(seed + j);
+                for (int j = 0; j < 8; ++j) sd[j] = __ldg(seed + j * sstep);
             }
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN;
             float rgbp[3] = {0.f, 0.f, 0.f};
-#pragma unroll 1
-            for (int ch = 0; ch < BN / 32; ++ch) {
+            // one 32-channel chunk; `cur` holds this chunk's seed values, the next chunk's are requested into `nxt` first so that
+            // their latency spans the whole chunk (the two arrays swap roles from chunk to chunk: no register copies, which
+            // would wait for the loads)
+            auto do_chunk = [&](const int ch, float4 (&cur)[8], float4 (&nxt)[8]) {
                 uint32_t r[32];
                 if (SEED && seed && ch + 1 < BN / 32) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) sdn[j] = __ldg(seed + (ch + 1) * 8 + j);
+                    for (int j = 0; j < 8; ++j) nxt[j] = __ldg(seed + ((ch + 1) * 8 + j) * sstep);
                 }
                 tmem_ld32(taddr + ch * 32, r);
                 tmem_ld_wait();
@@ -287,23 +333,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     if (SEED && seed) {
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
-                            v[4 * j] += sd[j].x; v[4 * j + 1] += sd[j].y; v[4 * j + 2] += sd[j].z; v[4 * j + 3] += sd[j].w;
-                            sd[j] = sdn[j];
+                            v[4 * j] += cur[j].x; v[4 * j + 1] += cur[j].y; v[4 * j + 2] += cur[j].z; v[4 * j + 3] += cur[j].w;
                         }
                     }
                     if (p.ep.d) {
-                        const float4 *dp = reinterpret_cast<const float4 *>(p.ep.d + (int64_t)b * p.cout + n);
+                        const float *dp = p.ep.d + (int64_t)b * p.cout + n;
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
-                            const float4 t = __ldg(dp + j);
+                            const float4 t = vec4(2, dp, ch, j);
                             v[4 * j] *= t.x; v[4 * j + 1] *= t.y; v[4 * j + 2] *= t.z; v[4 * j + 3] *= t.w;
                         }
                     }
                     if (p.ep.bias) {
-                        const float4 *bp = reinterpret_cast<const float4 *>(p.ep.bias + gofs + n);
+                        const float4 *bp = reinterpret_cast<const float4 *>(sv + ch * 32);
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
-                            const float4 t = __ldg(bp + j);
+                            const float4 t = bp[j];
                             v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
                         }
                     }
@@ -311,10 +356,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = lrelu_sqrt2(v[j] + nz);
                     } else if (p.ep.act == 2) {
-                        const float4 *pp = reinterpret_cast<const float4 *>(p.ep.prelu + gofs + n);
+                        const float4 *pp = reinterpret_cast<const float4 *>(sv + BN + ch * 32);
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
-                            const float4 t = __ldg(pp + j);
+                            const float4 t = pp[j];
                             v[4 * j] = apply_act(v[4 * j] + nz, 2, t.x); v[4 * j + 1] = apply_act(v[4 * j + 1] + nz, 2, t.y);
                             v[4 * j + 2] = apply_act(v[4 * j + 2] + nz, 2, t.z); v[4 * j + 3] = apply_act(v[4 * j + 3] + nz, 2, t.w);
                         }
@@ -325,19 +370,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     if (p.ep.rgb_out) {      // fused ToRGB: 3 dot products over this chunk's 32 channels of the unscaled activation
 #pragma unroll
                         for (int k = 0; k < 3; ++k) {
-                            const float4 *wp = reinterpret_cast<const float4 *>(p.ep.rgb_w + ((int64_t)b * 3 + k) * p.cout + n);
+                            const float *wp = p.ep.rgb_w + ((int64_t)b * 3 + k) * p.cout + n;
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
-                                const float4 t = __ldg(wp + j);
+                                const float4 t = vec4(4 + k, wp, ch, j);
                                 rgbp[k] = fmaf(v[4 * j], t.x, fmaf(v[4 * j + 1], t.y, fmaf(v[4 * j + 2], t.z, fmaf(v[4 * j + 3], t.w, rgbp[k]))));
                             }
                         }
                     }
                     if (p.ep.out_y) {
                         if (p.ep.out_f32) {
-                            float4 *o = reinterpret_cast<float4 *>((float *)p.ep.out_y + pix * p.cout + n);
+                            const int ostep = p.ep.tiled ? TBM : 1;
+                            float4 *o = p.ep.tiled ? reinterpret_cast<float4 *>(p.ep.out_y) + ((int64_t)tile * (BN / 32) + ch) * 8 * TBM + row
+                                                   : reinterpret_cast<float4 *>((float *)p.ep.out_y + pix * p.cout + n);
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                            for (int j = 0; j < 8; ++j) o[j * ostep] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                         } else {
                             uint4 *o = reinterpret_cast<uint4 *>((__nv_bfloat16 *)p.ep.out_y + pix * p.cout + n);
 #pragma unroll
@@ -347,10 +394,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         }
                     }
                     if (p.ep.out_ys) {
-                        const float4 *sp = reinterpret_cast<const float4 *>(p.ep.s_next + (int64_t)b * p.cout + n);
+                        const float *sp = p.ep.s_next + (int64_t)b * p.cout + n;
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
-                            const float4 t = __ldg(sp + j);
+                            const float4 t = vec4(3, sp, ch, j);
                             v[4 * j] *= t.x; v[4 * j + 1] *= t.y; v[4 * j + 2] *= t.z; v[4 * j + 3] *= t.w;
                         }
                         uint4 *o = reinterpret_cast<uint4 *>((__nv_bfloat16 *)p.ep.out_ys + pix * p.cout + n);
@@ -360,6 +407,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                               pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
                     }
                 }
+            };
+            if constexpr (SEED) {
+#pragma unroll 1
+                for (int ch = 0; ch < BN / 32; ch += 2) { do_chunk(ch, sd, sdn); do_chunk(ch + 1, sdn, sd); }
+            } else {
+#pragma unroll 1
+                for (int ch = 0; ch < BN / 32; ++ch) do_chunk(ch, sd, sdn);
             }
             if (p.ep.rgb_out && valid) {
 #pragma unroll
@@ -418,21 +472,12 @@ static int launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, const TcPar
     return check_launch("conv3x3 tc");
 }
 
-int conv3x3_tc(const ood_conv3x3_args &a, cudaStream_t st) {
-    OOD_REQUIRE(a.dtype == OOD_BF16, "conv3x3 tc: storage type must be bf16");
-    OOD_REQUIRE(a.cin % 32 == 0 && a.cout % 32 == 0, "conv3x3 tc: cin and cout must be multiples of 32 (got %d, %d)", a.cin, a.cout);
-    OOD_REQUIRE(((uintptr_t)a.in % 16 == 0) && ((uintptr_t)a.weight % 16 == 0), "conv3x3 tc: operands must be 16-byte aligned");
-    EncodeTiledFn encode = get_encode_fn();
-    if (!encode) { set_error("conv3x3 tc: cuTensorMapEncodeTiled is unavailable"); return OOD_ERR_CUDA; }
-
+// Tile plan of a launch: patch shape, N tile, tile enumeration.  A function of (batch, h, w, cout, form, groups) and of whether
+// the call uses seeded / tile-order tensors (those keep the 128- or 256-wide N tiles) -- never of the data or of cin, so two
+// launches with the same arguments enumerate the same tiles (what the tile-order fp32 tensors rely on).
+static void plan_tiles(const ood_conv3x3_args &a, const ConvGeom &g, TcParams &p, int &BN) {
     const int groups = a.groups > 1 ? a.groups : 1;
-    OOD_REQUIRE(a.batch % groups == 0, "conv3x3 tc: batch (%d) must be a multiple of groups (%d)", a.batch, groups);
-    OOD_REQUIRE(groups == 1 || (!a.d && !a.noise && !a.out_ys && !a.rgb_out), "conv3x3 tc: the grouped form supports bias / activation epilogues only");
-    const ConvGeom g = make_geom(a.batch, a.h, a.w, a.cin, a.cout, a.transposed);
-    const int BK = (a.cin % 64 == 0) ? 64 : 32;
-    int BN = a.cout % 256 == 0 ? 256 : (a.cout % 128 == 0 ? 128 : (a.cout % 64 == 0 ? 64 : 32));
-
-    TcParams p{};
+    BN = a.cout % 256 == 0 ? 256 : (a.cout % 128 == 0 ? 128 : (a.cout % 64 == 0 ? 64 : 32));
     p.batch = g.batch; p.h = g.h; p.w = g.w; p.cin = g.cin; p.cout = g.cout; p.OH = g.OH; p.OW = g.OW; p.sy = g.sy; p.sx = g.sx;
     p.isy = g.isy; p.isx = g.isx;
     int ohm = 0, owm = 0;
@@ -443,6 +488,7 @@ int conv3x3_tc(const ood_conv3x3_args &a, cudaStream_t st) {
     p.nphases = g.nphases;
     p.groups = groups; p.gbatch = a.batch / groups; p.in_shared = a.in_shared ? 1 : 0;
     p.wtaps = a.transposed == 4 ? 1 : 9;
+    const int bn_min = (a.acc_in || a.tiled) ? 128 : 64;
     int tiles = 0;
     for (;;) {
         p.n_tiles_n = a.cout / BN;
@@ -458,14 +504,35 @@ int conv3x3_tc(const ood_conv3x3_args &a, cudaStream_t st) {
         }
         // few-pixel problems (the tails of the encoder's style heads) are bound by streaming the weights: narrower N
         // tiles put more SMs on that stream
-        if (tiles >= kNumSMs || BN <= (a.acc_in ? 128 : 64) || a.rgb_out) break;     // seeded accumulators: 128 / 256-wide tiles only
+        if (tiles >= kNumSMs || BN <= bn_min || a.rgb_out) break;
         BN >>= 1;
     }
     p.total_tiles = tiles;
+}
+
+int conv3x3_tc(const ood_conv3x3_args &a, cudaStream_t st) {
+    OOD_REQUIRE(a.dtype == OOD_BF16, "conv3x3 tc: storage type must be bf16");
+    OOD_REQUIRE(a.cin % 32 == 0 && a.cout % 32 == 0, "conv3x3 tc: cin and cout must be multiples of 32 (got %d, %d)", a.cin, a.cout);
+    OOD_REQUIRE(((uintptr_t)a.in % 16 == 0) && ((uintptr_t)a.weight % 16 == 0), "conv3x3 tc: operands must be 16-byte aligned");
+    EncodeTiledFn encode = get_encode_fn();
+    if (!encode) { set_error("conv3x3 tc: cuTensorMapEncodeTiled is unavailable"); return OOD_ERR_CUDA; }
+
+    const int groups = a.groups > 1 ? a.groups : 1;
+    OOD_REQUIRE(a.batch % groups == 0, "conv3x3 tc: batch (%d) must be a multiple of groups (%d)", a.batch, groups);
+    OOD_REQUIRE(groups == 1 || (!a.d && !a.noise && !a.out_ys && !a.rgb_out), "conv3x3 tc: the grouped form supports bias / activation epilogues only");
+    OOD_REQUIRE(!(a.acc_in || a.tiled) || (a.cout % 128 == 0 && a.transposed != 1),
+                "conv3x3 tc: acc_in / tiled need cout %% 128 == 0 (got %d) and a single-phase form", a.cout);
+    OOD_REQUIRE(!a.tiled || a.acc_in || (a.out_f32 && a.out_y), "conv3x3 tc: tiled = 1 without a tile-order tensor (acc_in, or out_y with out_f32)");
+    const ConvGeom g = make_geom(a.batch, a.h, a.w, a.cin, a.cout, a.transposed);
+    const int BK = (a.cin % 64 == 0) ? 64 : 32;
+    int BN = 0;
+
+    TcParams p{};
+    plan_tiles(a, g, p, BN);
     OOD_REQUIRE(!a.rgb_out || (p.n_tiles_n == 1 && !a.transposed), "conv3x3 tc: the fused ToRGB epilogue needs Co == tile N (Co <= 256) and the stride-1 form");
     p.ep = make_epilogue(a, a.out_f32);
     p.out_bf16 = 1;
-    OOD_REQUIRE(!a.acc_in || (a.transposed != 1 && (uintptr_t)a.acc_in % 16 == 0), "conv3x3 tc: acc_in needs a single-phase form and 16-byte alignment");
+    OOD_REQUIRE(!a.acc_in || (uintptr_t)a.acc_in % 16 == 0, "conv3x3 tc: acc_in must be 16-byte aligned");
 
     CUtensorMap tmA, tmB;
     {
@@ -504,6 +571,18 @@ int conv3x3_tc(const ood_conv3x3_args &a, cudaStream_t st) {
 }
 
 }  // namespace ood
+
+extern "C" int64_t ood_conv3x3_tiled_bytes(int batch, int h, int w, int cin, int cout, int transposed) {
+    using namespace ood;
+    if (batch <= 0 || h <= 0 || w <= 0 || cin <= 0 || cout <= 0 || cout % 128 != 0 || transposed == 1 || transposed < 0 || transposed > 4) return 0;
+    ood_conv3x3_args a{};
+    a.batch = batch; a.h = h; a.w = w; a.cin = cin; a.cout = cout; a.transposed = transposed; a.tiled = 1;
+    const ConvGeom g = make_geom(batch, h, w, cin, cout, transposed);
+    TcParams p{};
+    int BN = 0;
+    plan_tiles(a, g, p, BN);
+    return (int64_t)p.total_tiles * TBM * BN * (int64_t)sizeof(float);
+}
 
 namespace ood {
 int conv3x3_simt(const ood_conv3x3_args &a, cudaStream_t st);

@@ -217,10 +217,12 @@ def torgb_weight(w, s, scale=None):
 # ----------------------------------------------------------------------------------------------- convolution
 def conv3x3(x, weight, cout, transposed=False, impl=0, d=None, noise=None, noise_w=None, bias=None, s_next=None,
             act=False, want_y=True, want_ys=False, out_f32=False, prelu=None, rgb=None, tag=None, groups=1, in_shared=False,
-            acc_in=None):
+            acc_in=None, tiled=False):
     """x NHWC [B,H,W,Ci] pre-modulated; weight packed for `impl`.  Returns (y, ys) (None where not requested).
     rgb=(wrgb [B,3,Co], bias [3], skip NCHW fp32 or None, up taps): fused ToRGB, returns (y, ys, rgb_out NCHW fp32).
-    acc_in: fp32 NHWC [B,OH,OW,Co] seed added to the accumulator before the epilogue (tcgen05 path)."""
+    acc_in: fp32 NHWC [B,OH,OW,Co] seed added to the accumulator before the epilogue (tcgen05 path).
+    tiled: acc_in, and y when out_f32, are flat fp32 tensors in the kernel's tile order (ood_conv3x3_tiled_bytes): the fast form
+    of a seed that only ever travels between two launches with the same geometry."""
     _cuda(x, weight, d, noise, noise_w, bias, s_next, acc_in)
     assert x.is_contiguous()
     b, h, w, cin = x.shape
@@ -229,7 +231,15 @@ def conv3x3(x, weight, cout, transposed=False, impl=0, d=None, noise=None, noise
     transposed = int(transposed)      # 0 stride-1 | 1 stride-2 transposed | 2 stride-2 valid (data gradient of 1) | 3 stride-2 pad-1
     oh, ow = {0: (h, w), 1: (2 * h + 1, 2 * w + 1), 2: ((h - 1) // 2, (w - 1) // 2),
               3: ((h - 1) // 2 + 1, (w - 1) // 2 + 1), 4: (h, w)}[transposed]
-    y = torch.empty(b, oh, ow, cout, device=x.device, dtype=torch.float32 if out_f32 else x.dtype) if want_y else None
+    nt = 0
+    if tiled:
+        nt = _lib.lib().ood_conv3x3_tiled_bytes(b, h, w, cin, cout, transposed) // 4
+        if nt <= 0:
+            raise RuntimeError('ood_gan_inversion_b200: conv3x3 tiled=True needs cout % 128 == 0 and a single-phase form')
+    if tiled and out_f32 and want_y:
+        y = torch.empty(nt, device=x.device, dtype=torch.float32)
+    else:
+        y = torch.empty(b, oh, ow, cout, device=x.device, dtype=torch.float32 if out_f32 else x.dtype) if want_y else None
     ys = torch.empty(b, oh, ow, cout, device=x.device, dtype=x.dtype) if want_ys else None
     nbs = 0
     if noise is not None:
@@ -239,8 +249,10 @@ def conv3x3(x, weight, cout, transposed=False, impl=0, d=None, noise=None, noise
                  b, h, w, cin, cout, int(transposed), 2 if prelu is not None else int(act), impl, _dt(x), int(out_f32), _ptr(prelu))
     a.groups, a.in_shared = int(groups), int(bool(in_shared))
     if acc_in is not None:
-        assert acc_in.dtype == torch.float32 and acc_in.is_contiguous() and tuple(acc_in.shape) == (b, oh, ow, cout)
+        assert acc_in.dtype == torch.float32 and acc_in.is_contiguous()
+        assert tuple(acc_in.shape) == ((nt,) if tiled else (b, oh, ow, cout))
         a.acc_in = _ptr(acc_in)
+    a.tiled = int(bool(tiled))
     rgb_out = None
     if rgb is not None:
         wrgb, rbias, rskip, rtaps = rgb

@@ -6,6 +6,8 @@ the flow warp + alpha mix and (in arch.py) the mask compose + blend are single f
 convolution stacks run on the package's tcgen05 convolution in shared-weight mode (AlignNet.raw_nhwc; SURVEY.md section
 8(f) rank 1), with the `enc`-only half of the first convolution computed once per level and reused by every cycle.
 """
+import os
+
 import torch
 from torch import nn
 from torch.nn import functional as F
@@ -13,6 +15,13 @@ from torch.nn import functional as F
 from . import kernels as K
 from . import stylegan as sg
 from .stylegan import Blur, NoiseInjection
+
+
+# Levels whose first AlignNet convolution is split across the alignment cycles (AlignNet.raw_nhwc): below this channel count
+# the half-K convolutions are bound by their epilogue and operand feed rather than by the tensor pipe, and the seed's extra
+# traffic costs more than the saved MACs (scripts/seed_bench.py on B200: C=128 at 256 px, whole 1.83 ms vs split 2.0 ms per
+# two cycles; C=256 at 128 px 1.66 vs 1.42; C=512 at 64 px 1.58 vs 1.24).
+_SPLIT_MIN_C = int(os.environ.get('OOD_SPLIT_MIN_C', 256))
 
 
 def BN(depth, bn=True):
@@ -129,14 +138,14 @@ class AlignNet(nn.Module):
         impl = sg._impl()
         eps = self.norm.eps
         st6 = K.in_stats(cur, enc, eps)
-        split = impl == 0 and carry is not None and c % 64 == 0
+        split = impl == 0 and carry is not None and c % 64 == 0 and c >= _SPLIT_MIN_C
         if split:
             seed = carry.get('seed')
             lo, hi = K.alignnet_front_split(cur, enc, st6, f(b0.res_layer[0].weight), f(b0.res_layer[0].bias), want_hi=seed is None)
             if seed is None:
-                seed, _ = K.conv3x3(hi, pk['wa_hi'], 2 * c, impl=0, out_f32=True)
+                seed, _ = K.conv3x3(hi, pk['wa_hi'], 2 * c, impl=0, out_f32=True, tiled=True)
                 carry['seed'] = seed
-            x, _ = K.conv3x3(lo, pk['wa_lo'], 2 * c, impl=0, prelu=f(b0.res_layer[2].weight), acc_in=seed)
+            x, _ = K.conv3x3(lo, pk['wa_lo'], 2 * c, impl=0, prelu=f(b0.res_layer[2].weight), acc_in=seed, tiled=True)
         else:
             x = K.alignnet_front(cur, enc, st6, f(b0.res_layer[0].weight), f(b0.res_layer[0].bias))
             x, _ = K.conv3x3(x, pk['wa'], 2 * c, impl=impl, prelu=f(b0.res_layer[2].weight))

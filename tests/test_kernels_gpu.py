@@ -604,6 +604,11 @@ def test_conv3x3_seeded_accumulator(case):
     full, _ = K().conv3x3(nhwc(torch.cat([xa, xb], 1), dt), pack(wt), co, impl=0, prelu=slope.to(DEV))
     diff = (y.float() - full.float()).abs()
     assert float((diff > 2 ** -7 * full.float().abs().clamp_min(2 ** -6)).float().mean()) == 0.0
+    # the same seed in the kernel's tile order (what AlignNet.raw_nhwc uses): identical arithmetic, coalesced fp32 access
+    seed_t, _ = K().conv3x3(nhwc(xb, dt), pack(wt[:, ci:]), co, impl=0, out_f32=True, tiled=True)
+    assert seed_t.dim() == 1 and seed_t.numel() >= seed.numel()
+    y_t, _ = K().conv3x3(nhwc(xa, dt), pack(wt[:, :ci]), co, impl=0, prelu=slope.to(DEV), acc_in=seed_t, tiled=True)
+    assert torch.equal(y_t, y)
     # no activation, bias and d on top of the seed
     d, bias = 0.5 + torch.rand(b, co, generator=g(5)), 0.1 * rnd(co, seed=6)
     y2, _ = K().conv3x3(nhwc(xa, dt), pack(wt[:, :ci]), co, impl=0, d=d.to(DEV), bias=bias.to(DEV), acc_in=seed)
