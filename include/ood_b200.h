@@ -143,10 +143,19 @@ typedef struct {
      * per warp instruction; the tile order makes the same access one contiguous 512-byte run (measured on the 256 px
      * AlignNet level: seeded half convolution 898 us with an NHWC seed against 505 us without any seed). */
     int tiled;
+    /* fused output statistics (tcgen05 path; stride-1 / 1x1 form, bf16 out_y only, cin % 64 == 0, cout % 128 == 0, h*w >= 128):
+     * stats_out [B,Co,2] = {mean, rsqrt(biased variance + stats_eps)} over the pixels of every output channel of out_y AS
+     * STORED -- the statistics of the InstanceNorm2d that follows the convolution (bottleneck_IR res_layer[4],
+     * e4e/encoders/helpers.py:436-441) from the epilogue instead of a pass over out_y.  Deterministic (fixed-order sums).
+     * stats_ws: ood_conv3x3_stats_workspace() bytes. */
+    float *stats_out, *stats_ws;
+    float stats_eps;
 } ood_conv3x3_args;
 int ood_conv3x3(const ood_conv3x3_args *args_host, void *stream);
 /* bytes of a tile-order fp32 tensor for the tcgen05 path (0 when the arguments are outside that path) */
 int64_t ood_conv3x3_tiled_bytes(int batch, int h, int w, int cin, int cout, int transposed);
+/* bytes of stats_ws (0 when the arguments are outside the fused-statistics envelope) */
+int64_t ood_conv3x3_stats_workspace(int batch, int h, int w, int cin, int cout, int transposed);
 
 /* ---- a1+a2+a6 fused: FIR blur (4x4 separable taps, pad (1,1)) of the transposed-conv output
  *      [B,2h+1,2w+1,C] -> [B,2h,2w,C], then the StyledConv epilogue (model.py:257, 283-292, fused_act.py:96):
@@ -214,6 +223,10 @@ int ood_bicubic_up_add(const void *x, const void *y, void *out, int batch, int h
  *          out[b,k,y,x] = sum_t proj[b, y + t/3 - 1, x + t%3 - 1, 3*t + k]        (zero outside the image)
  *      gathers the nine shifted partial sums.  out fp32 NCHW [B,3,H,W]. */
 int ood_tap_sum(const float *proj, float *out, int batch, int h, int w, int cp, void *stream);
+/*      ood_tap_sum_shortcut: the same, plus shortcut[b,k,y,x] = proj[b,y,x,27+k] (Cp >= 30): the bottleneck's 1x1 shortcut
+ *      convolution 2C -> 3 (e4e/encoders/helpers.py:430-433) computed by the projection in three of its spare output channels,
+ *      so its 2C-channel input is not read a second time. */
+int ood_tap_sum_shortcut(const float *proj, float *out, float *shortcut, int batch, int h, int w, int cp, void *stream);
 
 /* ---- a13 (encoder trunk, e4e/encoders/helpers.py:59-76 SEModule, :476-501 bottleneck_IR_SE) on NHWC activations.
  *      ood_se_gate:     stats [B,C,2] from ood_in_stats (channel means) -> gate[b,c] = sigmoid(w2 . relu(w1 . mean[b,:]));

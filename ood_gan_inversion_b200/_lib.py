@@ -19,7 +19,7 @@ class ConvArgs(C.Structure):
                 ('s_next', c_void_p), ('batch', c_int), ('h', c_int), ('w', c_int), ('cin', c_int), ('cout', c_int),
                 ('transposed', c_int), ('act', c_int), ('impl', c_int), ('dtype', c_int), ('out_f32', c_int), ('prelu_slope', c_void_p),
                 ('rgb_w', c_void_p), ('rgb_bias', c_void_p), ('rgb_skip', c_void_p), ('rgb_out', c_void_p), ('rgb_taps', c_float * 4),
-                ('groups', c_int), ('in_shared', c_int), ('acc_in', c_void_p), ('tiled', c_int)]
+                ('groups', c_int), ('in_shared', c_int), ('acc_in', c_void_p), ('tiled', c_int), ('stats_out', c_void_p), ('stats_ws', c_void_p), ('stats_eps', c_float)]
 
 
 class BlurActArgs(C.Structure):
@@ -47,6 +47,7 @@ _SIGS = {
     'ood_pack_conv_weight': ([c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p], c_int),
     'ood_conv3x3': ([C.POINTER(ConvArgs), c_void_p], c_int),
     'ood_conv3x3_tiled_bytes': ([c_int] * 6, c_i64),
+    'ood_conv3x3_stats_workspace': ([c_int] * 6, c_i64),
     'ood_blur_act': ([C.POINTER(BlurActArgs), c_void_p], c_int),
     'ood_noise_act': ([c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_void_p, c_void_p, c_int, c_i64, c_int,
                        c_int, c_void_p], c_int),
@@ -58,6 +59,7 @@ _SIGS = {
     'ood_alignnet_tail_workspace': ([c_int, c_int], c_i64),
     'ood_alignnet_tail': ([c_void_p] * 8 + [c_float, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p], c_int),
     'ood_tap_sum': ([c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p], c_int),
+    'ood_tap_sum_shortcut': ([c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p], c_int),
     'ood_se_gate': ([c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p], c_int),
     'ood_se_residual': ([c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                         c_int, c_int, c_int, c_void_p], c_int),

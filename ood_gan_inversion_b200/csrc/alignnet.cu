@@ -342,6 +342,12 @@ __global__ void __launch_bounds__(256) in_apply_kernel(const T *__restrict__ x, 
     }
 }
 
+// finalize [B][nchunks][C][2] partial moments (shared with the convolution's fused statistics, conv_tc.cu)
+void in_finalize_launch(const float *partial, float *st2, int64_t P, int C, int nchunks, float eps, int batch, cudaStream_t s) {
+    const int64_t total = (int64_t)batch * C;
+    in_finalize_kernel<<<ceil_div(total, 256), 256, 0, s>>>(partial, st2, P, C, nchunks, eps, total);
+}
+
 template <typename T>
 static int launch_stats(const void *x, const void *y, float *partial, float *st, int batch, int64_t P, int C, float eps,
                         cudaStream_t s) {

@@ -398,7 +398,7 @@ static int launch(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensor
 int conv3x3_rows(const ood_conv3x3_args &a, cudaStream_t st, int *handled) {
     using namespace rows;
     *handled = 0;
-    if (a.transposed || a.dtype != OOD_BF16 || a.out_f32 || a.act == 2 || a.groups > 1 || a.acc_in || a.tiled) return OOD_OK;
+    if (a.transposed || a.dtype != OOD_BF16 || a.out_f32 || a.act == 2 || a.groups > 1 || a.acc_in || a.tiled || a.stats_out) return OOD_OK;
     if (!((a.cin == 32 || a.cin == 64) && (a.cout == 32 || a.cout == 64) && a.cin >= a.cout)) return OOD_OK;
     if (a.w % 128 != 0 || a.h < 3 || (int64_t)a.batch * a.h * a.w >= (1LL << 31)) return OOD_OK;
     static EncodeFn encode = nullptr;

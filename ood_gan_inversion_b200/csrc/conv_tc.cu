@@ -135,6 +135,7 @@ struct TcCfg {
     static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
     static constexpr int kEpiVecs = 7;                       // bias, prelu, d, s_next, rgb_w[3]: BN floats each, double buffered
     static constexpr int kEpiBytes = 2 * kEpiVecs * BN * 4;
+    static constexpr int kStatBytes = 4 * BN * 2 * 4;        // STATS kernels: [epilogue warp][channel][sum, sum of squares]
     static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kEpiBytes;
     static constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
 };
@@ -160,7 +161,9 @@ __device__ __forceinline__ TileCoord decode_tile(const TcParams &p, int tile, in
     return tc;
 }
 
-template <int BN, int BK, bool SEED = false>
+// SEED: fp32 accumulator seed (ConvEpilogue::acc_in).  STATS: per-tile channel moments of the stored output
+// (ConvEpilogue::stat_partial) -- the statistics of the InstanceNorm that follows the convolution, without a pass over it.
+template <int BN, int BK, bool SEED = false, bool STATS = false>
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
     using Cfg = TcCfg<BN, BK>;
@@ -173,6 +176,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint64_t *full = bars, *empty = bars + S, *tfull = bars + 2 * S, *tempty = bars + 2 * S + 2;
     uint32_t *tmem_holder = reinterpret_cast<uint32_t *>(bars + 2 * S + 4);
     float *epi_vecs = reinterpret_cast<float *>(smem + S * Cfg::kStageBytes + 256);
+    float *stat_red = epi_vecs + 2 * Cfg::kEpiVecs * BN;     // STATS kernels only (the launch adds kStatBytes)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kchunks = p.cin / BK;
@@ -325,9 +329,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
                 tmem_ld32(taddr + ch * 32, r);
                 tmem_ld_wait();
+                float v[32];
                 if (valid) {
                     const int n = tc.n0 + ch * 32;
-                    float v[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
                     if (SEED && seed) {
@@ -407,6 +411,28 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                               pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
                     }
                 }
+                if constexpr (STATS) {
+                    // moments of this warp's 32 pixels for the chunk's 32 channels, of the values as stored (bf16): a
+                    // transpose-reduce over the lanes (31 shuffles per moment) leaves channel `lane` in element 0
+                    float q[32], q2[32];
+#pragma unroll
+                    for (int j = 0; j < 32; j += 2) {
+                        const float2 t = valid ? unpack_bf16x2(pack_bf16x2(v[j], v[j + 1])) : make_float2(0.f, 0.f);
+                        q[j] = t.x; q[j + 1] = t.y; q2[j] = t.x * t.x; q2[j + 1] = t.y * t.y;
+                    }
+#pragma unroll
+                    for (int o = 16; o >= 1; o >>= 1) {
+                        const bool up = lane & o;
+#pragma unroll
+                        for (int i = 0; i < o; ++i) {
+                            const float s1 = up ? q[i] : q[i + o], k1 = up ? q[i + o] : q[i];
+                            const float s2 = up ? q2[i] : q2[i + o], k2 = up ? q2[i + o] : q2[i];
+                            q[i] = k1 + __shfl_xor_sync(0xffffffffu, s1, o);
+                            q2[i] = k2 + __shfl_xor_sync(0xffffffffu, s2, o);
+                        }
+                    }
+                    *reinterpret_cast<float2 *>(stat_red + ((quad * BN) + ch * 32 + lane) * 2) = make_float2(q[0], q2[0]);
+                }
             };
             if constexpr (SEED) {
 #pragma unroll 1
@@ -414,6 +440,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             } else {
 #pragma unroll 1
                 for (int ch = 0; ch < BN / 32; ++ch) do_chunk(ch, sd, sdn);
+            }
+            if constexpr (STATS) {
+                // combine the four warps in a fixed order: partial[image][m tile of the image][channel] = {sum, sum of squares}
+                asm volatile("bar.sync 2, 128;" ::: "memory");
+                const int mt = (tile - P.tile_begin) / p.n_tiles_n, mpi = P.tiles_x * P.tiles_y;
+                float2 *dst = reinterpret_cast<float2 *>(p.ep.stat_partial) + ((int64_t)tc.b0 * mpi + mt % mpi) * p.cout + tc.n0;
+                for (int i = threadIdx.x - 64; i < BN; i += 128) {
+                    float2 a = *reinterpret_cast<const float2 *>(stat_red + i * 2);
+#pragma unroll
+                    for (int w4 = 1; w4 < 4; ++w4) {
+                        const float2 t = *reinterpret_cast<const float2 *>(stat_red + (w4 * BN + i) * 2);
+                        a.x += t.x; a.y += t.y;
+                    }
+                    dst[i] = a;
+                }
             }
             if (p.ep.rgb_out && valid) {
 #pragma unroll
@@ -454,13 +495,15 @@ static EncodeTiledFn get_encode_fn() {
 
 static int pow2_ceil(int v) { int r = 1; while (r < v) r <<= 1; return r; }
 
-template <int BN, int BK, bool SEED = false>
+template <int BN, int BK, bool SEED = false, bool STATS = false>
 static int launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, const TcParams &p, cudaStream_t st) {
     using Cfg = TcCfg<BN, BK>;
-    auto kern = conv_tc_kernel<BN, BK, SEED>;
+    auto kern = conv_tc_kernel<BN, BK, SEED, STATS>;
+    constexpr int kSmem = Cfg::kSmemBytes + (STATS ? Cfg::kStatBytes : 0);
+    static_assert(kSmem <= 227 * 1024, "shared memory budget");
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
         if (e != cudaSuccess) { set_error("conv3x3 tc: smem attribute: %s", cudaGetErrorString(e)); return OOD_ERR_CUDA; }
         attr_set = true;
     }
@@ -468,9 +511,11 @@ static int launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, const TcPar
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int grid = std::min(p.total_tiles, sms);
-    kern<<<grid, kTcThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, p);
+    kern<<<grid, kTcThreads, kSmem, st>>>(tmA, tmB, p);
     return check_launch("conv3x3 tc");
 }
+
+void in_finalize_launch(const float *partial, float *st2, int64_t P, int C, int nchunks, float eps, int batch, cudaStream_t s);   // alignnet.cu
 
 // Tile plan of a launch: patch shape, N tile, tile enumeration.  A function of (batch, h, w, cout, form, groups) and of whether
 // the call uses seeded / tile-order tensors (those keep the 128- or 256-wide N tiles) -- never of the data or of cin, so two
@@ -488,7 +533,7 @@ static void plan_tiles(const ood_conv3x3_args &a, const ConvGeom &g, TcParams &p
     p.nphases = g.nphases;
     p.groups = groups; p.gbatch = a.batch / groups; p.in_shared = a.in_shared ? 1 : 0;
     p.wtaps = a.transposed == 4 ? 1 : 9;
-    const int bn_min = (a.acc_in || a.tiled) ? 128 : 64;
+    const int bn_min = (a.acc_in || a.tiled || a.stats_out) ? 128 : 64;
     int tiles = 0;
     for (;;) {
         p.n_tiles_n = a.cout / BN;
@@ -556,6 +601,16 @@ int conv3x3_tc(const ood_conv3x3_args &a, cudaStream_t st) {
                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { set_error("conv3x3 tc: weight tensor map encode failed (%d)", (int)r); return OOD_ERR_CUDA; }
     }
+    if (a.stats_out) {  // fused output statistics: wide tiles, one image per tile, single phase
+        OOD_REQUIRE(a.stats_ws && !a.acc_in && !a.out_ys && !a.out_f32 && a.out_y && groups == 1 && (a.transposed == 0 || a.transposed == 4) &&
+                    p.NB == 1 && BK == 64 && (BN == 256 || BN == 128),
+                    "conv3x3 tc: stats_out needs the stride-1 / 1x1 form, bf16 out_y only, cin %% 64 == 0, cout %% 128 == 0 and h*w >= 128");
+        p.ep.stat_partial = a.stats_ws;
+        const int rc = BN == 256 ? launch_tc<256, 64, false, true>(tmA, tmB, p, st) : launch_tc<128, 64, false, true>(tmA, tmB, p, st);
+        if (rc != OOD_OK) return rc;
+        in_finalize_launch(a.stats_ws, a.stats_out, (int64_t)a.h * a.w, a.cout, p.ph[0].tiles_x * p.ph[0].tiles_y, a.stats_eps, a.batch, st);
+        return check_launch("conv3x3 tc stats", 1);
+    }
     if (a.acc_in) {     // seeded accumulators: built for the wide tiles only (the AlignNet convolutions)
         if (BN == 256 && BK == 64) return launch_tc<256, 64, true>(tmA, tmB, p, st);
         if (BN == 128 && BK == 64) return launch_tc<128, 64, true>(tmA, tmB, p, st);
@@ -571,6 +626,21 @@ int conv3x3_tc(const ood_conv3x3_args &a, cudaStream_t st) {
 }
 
 }  // namespace ood
+
+extern "C" int64_t ood_conv3x3_stats_workspace(int batch, int h, int w, int cin, int cout, int transposed) {
+    using namespace ood;
+    if (batch <= 0 || h <= 0 || w <= 0 || cin <= 0 || cout <= 0 || cout % 128 != 0 || (transposed != 0 && transposed != 4)) return 0;
+    ood_conv3x3_args a{};
+    a.batch = batch; a.h = h; a.w = w; a.cin = cin; a.cout = cout; a.transposed = transposed;
+    float dummy = 0.f;
+    a.stats_out = &dummy;
+    const ConvGeom g = make_geom(batch, h, w, cin, cout, transposed);
+    TcParams p{};
+    int BN = 0;
+    plan_tiles(a, g, p, BN);
+    if (p.NB != 1) return 0;
+    return (int64_t)batch * p.ph[0].tiles_x * p.ph[0].tiles_y * cout * 2 * (int64_t)sizeof(float);
+}
 
 extern "C" int64_t ood_conv3x3_tiled_bytes(int batch, int h, int w, int cin, int cout, int transposed) {
     using namespace ood;

@@ -120,8 +120,10 @@ __global__ void __launch_bounds__(256) se_residual_kernel(const T *__restrict__ 
     }
 }
 
-// out[b,k,y,x] = sum over the nine taps of the per-pixel projections (see ood_b200.h: ood_tap_sum)
-__global__ void __launch_bounds__(256) tap_sum_kernel(const float *__restrict__ proj, float *__restrict__ out, int H, int W, int Cp) {
+// out[b,k,y,x] = sum over the nine taps of the per-pixel projections (see ood_b200.h: ood_tap_sum); sc (optional) = channels
+// 27..29 of the pixel itself: a 1x1 shortcut convolution that rode along in the projection's spare output channels
+__global__ void __launch_bounds__(256) tap_sum_kernel(const float *__restrict__ proj, float *__restrict__ out, float *__restrict__ sc,
+                                                       int H, int W, int Cp) {
     const int b = blockIdx.y;
     const int64_t P = (int64_t)H * W;
     const float *pb = proj + (int64_t)b * P * Cp;
@@ -137,6 +139,10 @@ __global__ void __launch_bounds__(256) tap_sum_kernel(const float *__restrict__ 
         }
 #pragma unroll
         for (int k = 0; k < 3; ++k) out[((int64_t)b * 3 + k) * P + pix] = acc[k];
+        if (sc) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) sc[((int64_t)b * 3 + k) * P + pix] = __ldg(pb + (int64_t)pix * Cp + 27 + k);
+        }
     }
 }
 
@@ -144,8 +150,10 @@ __global__ void __launch_bounds__(256) tap_sum_kernel(const float *__restrict__ 
 // with coalesced 16-byte loads -- every projection line is fetched once per block instead of by nine different threads, three
 // scalars at a time (that version was bound by L1 sector requests at 1.0 TB/s) -- and each thread then sums its 27 values from
 // shared memory (row pitch 33 words: conflict-free).
-constexpr int TSX = 32, TSY = 8, TSV = 7;          // TSV float4 = 28 >= 27 channels per pixel
-__global__ void __launch_bounds__(TSX * TSY) tap_sum_tile_kernel(const float *__restrict__ proj, float *__restrict__ out, int H, int W, int Cp) {
+constexpr int TSX = 32, TSY = 8;
+template <int TSV>                                  // float4 per pixel: 7 (27 channels used) or 8 (+ the shortcut's 27..29)
+__global__ void __launch_bounds__(TSX * TSY) tap_sum_tile_kernel(const float *__restrict__ proj, float *__restrict__ out,
+                                                                  float *__restrict__ sc, int H, int W, int Cp) {
     __shared__ float sp[(TSY + 2) * (TSX + 2)][33];
     const int b = blockIdx.z, x0 = blockIdx.x * TSX, y0 = blockIdx.y * TSY;
     const int64_t P = (int64_t)H * W;
@@ -171,22 +179,38 @@ __global__ void __launch_bounds__(TSX * TSY) tap_sum_tile_kernel(const float *__
     }
 #pragma unroll
     for (int k = 0; k < 3; ++k) out[((int64_t)b * 3 + k) * P + (int64_t)y * W + x] = acc[k];
+    if (TSV == 8 && sc) {
+        const float *q = sp[(ty + 1) * (TSX + 2) + tx + 1] + 27;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) sc[((int64_t)b * 3 + k) * P + (int64_t)y * W + x] = q[k];
+    }
+}
+
+static int launch_tap_sum(const float *proj, float *out, float *sc, int batch, int h, int w, int cp, cudaStream_t st) {
+    OOD_REQUIRE(proj && out && batch > 0 && batch <= 65535 && h > 0 && w > 0 && cp >= (sc ? 30 : 27) && (int64_t)h * w < (1LL << 30),
+                "tap_sum: bad arguments");
+    const int64_t P = (int64_t)h * w;
+    if (cp % 4 == 0 && ((uintptr_t)proj % 16) == 0 && ceil_div(h, TSY) <= 65535) {
+        dim3 tg(ceil_div(w, TSX), ceil_div(h, TSY), batch);
+        if (sc) tap_sum_tile_kernel<8><<<tg, TSX * TSY, 0, st>>>(proj, out, sc, h, w, cp);
+        else tap_sum_tile_kernel<7><<<tg, TSX * TSY, 0, st>>>(proj, out, nullptr, h, w, cp);
+        return check_launch("tap_sum");
+    }
+    dim3 grid((unsigned)std::min<int64_t>((P + 255) / 256, kNumSMs * 16), batch);
+    tap_sum_kernel<<<grid, 256, 0, st>>>(proj, out, sc, h, w, cp);
+    return check_launch("tap_sum");
 }
 
 }  // namespace ood
 
 extern "C" int ood_tap_sum(const float *proj, float *out, int batch, int h, int w, int cp, void *stream) {
+    return ood::launch_tap_sum(proj, out, nullptr, batch, h, w, cp, (cudaStream_t)stream);
+}
+
+extern "C" int ood_tap_sum_shortcut(const float *proj, float *out, float *shortcut, int batch, int h, int w, int cp, void *stream) {
     using namespace ood;
-    OOD_REQUIRE(proj && out && batch > 0 && batch <= 65535 && h > 0 && w > 0 && cp >= 27 && (int64_t)h * w < (1LL << 30), "tap_sum: bad arguments");
-    const int64_t P = (int64_t)h * w;
-    if (cp % 4 == 0 && ((uintptr_t)proj % 16) == 0 && ceil_div(h, TSY) <= 65535) {
-        dim3 tg(ceil_div(w, TSX), ceil_div(h, TSY), batch);
-        tap_sum_tile_kernel<<<tg, TSX * TSY, 0, (cudaStream_t)stream>>>(proj, out, h, w, cp);
-        return check_launch("tap_sum");
-    }
-    dim3 grid((unsigned)std::min<int64_t>((P + 255) / 256, kNumSMs * 16), batch);
-    tap_sum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(proj, out, h, w, cp);
-    return check_launch("tap_sum");
+    OOD_REQUIRE(shortcut, "tap_sum_shortcut: null pointer");
+    return launch_tap_sum(proj, out, shortcut, batch, h, w, cp, (cudaStream_t)stream);
 }
 
 extern "C" int ood_se_gate(const float *stats, const float *w1, const float *w2, float *gate, int batch, int channels,

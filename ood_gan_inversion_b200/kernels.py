@@ -217,12 +217,14 @@ def torgb_weight(w, s, scale=None):
 # ----------------------------------------------------------------------------------------------- convolution
 def conv3x3(x, weight, cout, transposed=False, impl=0, d=None, noise=None, noise_w=None, bias=None, s_next=None,
             act=False, want_y=True, want_ys=False, out_f32=False, prelu=None, rgb=None, tag=None, groups=1, in_shared=False,
-            acc_in=None, tiled=False):
+            acc_in=None, tiled=False, stats_eps=None):
     """x NHWC [B,H,W,Ci] pre-modulated; weight packed for `impl`.  Returns (y, ys) (None where not requested).
     rgb=(wrgb [B,3,Co], bias [3], skip NCHW fp32 or None, up taps): fused ToRGB, returns (y, ys, rgb_out NCHW fp32).
     acc_in: fp32 NHWC [B,OH,OW,Co] seed added to the accumulator before the epilogue (tcgen05 path).
     tiled: acc_in, and y when out_f32, are flat fp32 tensors in the kernel's tile order (ood_conv3x3_tiled_bytes): the fast form
-    of a seed that only ever travels between two launches with the same geometry."""
+    of a seed that only ever travels between two launches with the same geometry.
+    stats_eps: also return [B,Co,2] = (mean, rstd) of y as stored, computed in the epilogue -> (y, ys, stats); use
+    conv3x3_stats_ok() for the envelope."""
     _cuda(x, weight, d, noise, noise_w, bias, s_next, acc_in)
     assert x.is_contiguous()
     b, h, w, cin = x.shape
@@ -253,6 +255,14 @@ def conv3x3(x, weight, cout, transposed=False, impl=0, d=None, noise=None, noise
         assert tuple(acc_in.shape) == ((nt,) if tiled else (b, oh, ow, cout))
         a.acc_in = _ptr(acc_in)
     a.tiled = int(bool(tiled))
+    st = None
+    if stats_eps is not None:
+        nws = _lib.lib().ood_conv3x3_stats_workspace(b, h, w, cin, cout, transposed) // 4
+        if nws <= 0:
+            raise RuntimeError('ood_gan_inversion_b200: conv3x3 fused statistics are outside their envelope (see ood_b200.h)')
+        ws = torch.empty(nws, device=x.device, dtype=torch.float32)
+        st = torch.empty(b, cout, 2, device=x.device, dtype=torch.float32)
+        a.stats_ws, a.stats_out, a.stats_eps = _ptr(ws), _ptr(st), float(stats_eps)
     rgb_out = None
     if rgb is not None:
         wrgb, rbias, rskip, rtaps = rgb
@@ -266,7 +276,16 @@ def conv3x3(x, weight, cout, transposed=False, impl=0, d=None, noise=None, noise
         check(_lib.lib().ood_conv3x3(C.byref(a), _stream()), 'conv3x3')
     if rgb is not None:
         return y, ys, rgb_out
+    if stats_eps is not None:
+        return y, ys, st
     return y, ys
+
+
+def conv3x3_stats_ok(x, cout, transposed=0):
+    """True when conv3x3(..., stats_eps=...) is available for this input (tcgen05 path, bf16, wide tiles, one image per tile)."""
+    b, h, w, cin = x.shape
+    return x.dtype == torch.bfloat16 and cin % 64 == 0 and \
+        _lib.lib().ood_conv3x3_stats_workspace(b, h, w, cin, cout, int(transposed)) > 0
 
 
 def blur_act(t, taps, d=None, noise=None, noise_w=None, bias=None, s_next=None, act=True, want_img=False, want_y=True,
@@ -495,12 +514,18 @@ def pack_conv1x1_weight(w, dtype, ci_major):
     return (w.t() if ci_major else w).contiguous().to(dtype).unsqueeze(0)
 
 
-def tap_sum(proj):
-    """proj fp32 NHWC [B,H,W,Cp>=27] (channel 3*tap + colour) -> fp32 NCHW [B,3,H,W]: the nine shifted partial sums of a 3x3 conv."""
+def tap_sum(proj, shortcut=False):
+    """proj fp32 NHWC [B,H,W,Cp>=27] (channel 3*tap + colour) -> fp32 NCHW [B,3,H,W]: the nine shifted partial sums of a 3x3 conv.
+    shortcut=True also returns channels 27..29 of every pixel as a second [B,3,H,W] tensor (a 1x1 convolution that rode along)."""
     _cuda(proj)
     assert proj.is_contiguous() and proj.dtype == torch.float32
     b, h, w, cp = proj.shape
     out = torch.empty(b, 3, h, w, device=proj.device, dtype=torch.float32)
+    if shortcut:
+        sc = torch.empty_like(out)
+        with _timed('tap_sum', b * h * w * (30 + 6) * 4):
+            check(_lib.lib().ood_tap_sum_shortcut(_ptr(proj), _ptr(out), _ptr(sc), b, h, w, cp, _stream()), 'tap_sum_shortcut')
+        return out, sc
     with _timed('tap_sum', b * h * w * (27 + 3) * 4):
         check(_lib.lib().ood_tap_sum(_ptr(proj), _ptr(out), b, h, w, cp, _stream()), 'tap_sum')
     return out

@@ -22,6 +22,9 @@ from .stylegan import Blur, NoiseInjection
 # traffic costs more than the saved MACs (scripts/seed_bench.py on B200: C=128 at 256 px, whole 1.83 ms vs split 2.0 ms per
 # two cycles; C=256 at 128 px 1.66 vs 1.42; C=512 at 64 px 1.58 vs 1.24).
 _SPLIT_MIN_C = int(os.environ.get('OOD_SPLIT_MIN_C', 256))
+# A/B switches for the measurements in profiles/README.md (defaults = the fast route)
+_CONV_STATS = os.environ.get('OOD_CONV_STATS', '1') != '0'      # InstanceNorm statistics from the convolution's epilogue
+_FOLD_SHORTCUT = os.environ.get('OOD_FOLD_SHORTCUT', '1') != '0'  # 1x1 shortcut in the projection's spare output channels
 
 
 def BN(depth, bn=True):
@@ -149,26 +152,40 @@ class AlignNet(nn.Module):
         else:
             x = K.alignnet_front(cur, enc, st6, f(b0.res_layer[0].weight), f(b0.res_layer[0].bias))
             x, _ = K.conv3x3(x, pk['wa'], 2 * c, impl=impl, prelu=f(b0.res_layer[2].weight))
-        x, _ = K.conv3x3(x, pk['wb'], 2 * c, impl=impl)
+        if impl == 0 and _CONV_STATS and K.conv3x3_stats_ok(x, 2 * c):      # InstanceNorm statistics of the output from the convolution's epilogue
+            x, _, st_x = K.conv3x3(x, pk['wb'], 2 * c, impl=0, stats_eps=b0.res_layer[4].eps)
+        else:
+            x, _ = K.conv3x3(x, pk['wb'], 2 * c, impl=impl)
+            st_x = K.in_stats(x, None, b0.res_layer[4].eps)
         nvec = c // (8 if cur.dtype == torch.bfloat16 else 4)
         if nvec <= 256 and 256 % nvec == 0:
-            out0, st = K.alignnet_res0_stats(x, K.in_stats(x, None, eps), f(b0.res_layer[4].weight), f(b0.res_layer[4].bias), cur, enc, st6, eps)
+            out0, st = K.alignnet_res0_stats(x, st_x, f(b0.res_layer[4].weight), f(b0.res_layer[4].bias), cur, enc, st6, eps)
         else:
-            out0 = K.alignnet_res0(x, K.in_stats(x, None, eps), f(b0.res_layer[4].weight), f(b0.res_layer[4].bias), cur, enc, st6)
+            out0 = K.alignnet_res0(x, st_x, f(b0.res_layer[4].weight), f(b0.res_layer[4].bias), cur, enc, st6)
             st = K.in_stats(out0, None, eps)
         if impl == 0:
             # InstanceNorm(out0) folded into the projection: W27 . (g*out0 + h) = (W27 diag(g_b)) . out0 + W27 . h_b -- one weight
             # set per sample (grouped form, groups = batch) and a per-sample bias, so the normalised copy is never written
             g = st[..., 1] * f(b1.res_layer[0].weight)                                   # [B, 2C]
             h = f(b1.res_layer[0].bias) - st[..., 0] * g
-            wps = (pk['w27'].unsqueeze(0) * g.unsqueeze(1)).to(torch.bfloat16)           # [B, 32, 2C] = [groups][1 tap][Co][Ci]
-            x, _ = K.conv3x3(out0, wps, pk['cp'], transposed=4, impl=0, out_f32=True, groups=b, bias=(h @ pk['w27'].t()).contiguous())
+            # rows 27..29 of the projection: the bottleneck's 1x1 shortcut convolution on the UN-normalised out0 (no g, no bias),
+            # so out0 is read once for both branches; ood_tap_sum_shortcut hands those channels back as planes
+            wps = pk['w27'].unsqueeze(0) * g.unsqueeze(1)                                 # [B, 32, 2C] = [groups][1 tap][Co][Ci]
+            if _FOLD_SHORTCUT:
+                wps[:, 27:30] = pk['w1']
+            x, _ = K.conv3x3(out0, wps.to(torch.bfloat16), pk['cp'], transposed=4, impl=0, out_f32=True, groups=b,
+                             bias=(h @ pk['w27'].t()).contiguous())
+            if _FOLD_SHORTCUT:
+                res, sc = K.tap_sum(x, shortcut=True)
+            else:
+                res = K.tap_sum(x)
+                sc = K.torgb(out0, pk['w1'].unsqueeze(0).expand(b, -1, -1).contiguous(), torch.zeros(3, device=cur.device))
         else:
             x = K.in_apply(out0, st, f(b1.res_layer[0].weight), f(b1.res_layer[0].bias))
             x, _ = K.conv3x3(x, pk['wc'], pk['cp'], transposed=4, impl=impl, out_f32=True)
-        res = K.tap_sum(x)
-        zero = torch.zeros(3, device=cur.device)
-        sc = K.torgb(out0, pk['w1'].unsqueeze(0).expand(b, -1, -1).contiguous(), zero)      # 1x1 conv 2C -> 3, fp32 NCHW
+            res = K.tap_sum(x)
+            zero = torch.zeros(3, device=cur.device)
+            sc = K.torgb(out0, pk['w1'].unsqueeze(0).expand(b, -1, -1).contiguous(), zero)      # 1x1 conv 2C -> 3, fp32 NCHW
         n_res, n_sc = b1.res_layer[4], b1.shortcut_layer[1]
         r2, coef = K.alignnet_tail(res, sc, f(b1.res_layer[2].weight), f(b1.res_layer[3].weight), f(n_res.weight), f(n_res.bias),
                                    f(n_sc.weight), f(n_sc.bias), n_res.eps)

@@ -644,11 +644,13 @@ def test_alignnet_split_front_and_fused_statistics(dtype, c):
     torch.testing.assert_close(st[..., 1], torch.rsqrt(x.var((1, 2), unbiased=False) + 1e-5), rtol=1e-4, atol=1e-4)
 
 
-def test_alignnet_cycle_carry_matches_unsplit_route():
+def test_alignnet_cycle_carry_matches_unsplit_route(monkeypatch):
     """AlignNet.raw_nhwc with the per-level carry (enc-only half of the first convolution computed once, both cycles seeded
     with it) against the route that runs the whole convolution every cycle, and against the torch module (raw)."""
     import ood_gan_inversion_b200.stylegan as sgm
+    from ood_gan_inversion_b200 import samm
     from ood_gan_inversion_b200.samm import AlignNet
+    monkeypatch.setattr(samm, '_SPLIT_MIN_C', 64)          # the pipeline splits from C = 256 up; exercise it on a small level
     sgm.set_precision('bf16')
     torch.manual_seed(0)
     c, r, b = 64, 24, 2
@@ -680,3 +682,38 @@ def test_tap_sum_tiled_and_scalar_forms(h, w, cp):
     for t in range(9):
         ref += pad[:, t // 3:t // 3 + h, t % 3:t % 3 + w, 3 * t:3 * t + 3].permute(0, 3, 1, 2)
     torch.testing.assert_close(out, ref, rtol=1e-5, atol=1e-5)
+    if cp >= 30:
+        out2, sc = K().tap_sum(proj, shortcut=True)
+        assert torch.equal(out2, out)
+        assert torch.equal(sc, proj[..., 27:30].permute(0, 3, 1, 2).contiguous())
+
+
+@pytest.mark.parametrize('case', [dict(b=2, h=24, w=20, ci=64, co=128), dict(b=3, h=32, w=32, ci=128, co=256),
+                                  dict(b=2, h=16, w=8, ci=64, co=512), dict(b=1, h=40, w=72, ci=64, co=256, one=True)])
+def test_conv3x3_fused_output_statistics(case):
+    """ood_conv3x3_args.stats_out: (mean, rstd) per (image, output channel) of the stored bf16 output, from the epilogue,
+    against ood_in_stats over the same tensor and against torch moments; the output itself is unchanged."""
+    b, h, w, ci, co = (case[k] for k in ('b', 'h', 'w', 'ci', 'co'))
+    dt = torch.bfloat16
+    x = nhwc(rnd(b, ci, h, w, seed=1) + 0.3, dt)
+    form = 4 if case.get('one') else 0
+    wt = (0.05 * rnd(co, ci, 1, 1, seed=3) if form == 4 else 0.05 * rnd(co, ci, 3, 3, seed=3))
+    pk = K().pack_conv1x1_weight(wt.reshape(co, ci).to(DEV), dt, False) if form == 4 else K().pack_conv_weight(wt.to(DEV), dt, False)
+    assert K().conv3x3_stats_ok(x, co, form)
+    y0, _ = K().conv3x3(x, pk, co, transposed=form, impl=0)
+    y, _, st = K().conv3x3(x, pk, co, transposed=form, impl=0, stats_eps=1e-5)
+    assert torch.equal(y, y0)
+    ref = K().in_stats(y)
+    torch.testing.assert_close(st[..., 0], ref[..., 0], rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(st[..., 1], ref[..., 1], rtol=1e-4, atol=1e-5)
+    yf = y.float()
+    torch.testing.assert_close(st[..., 0], yf.mean((1, 2)), rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(st[..., 1], torch.rsqrt(yf.var((1, 2), unbiased=False) + 1e-5), rtol=1e-3, atol=1e-4)
+    # with an activation and a bias in front of the store
+    slope, bias = (0.25 + 0.1 * rnd(co, seed=4)).to(DEV), (0.1 * rnd(co, seed=5)).to(DEV)
+    y2, _, st2 = K().conv3x3(x, pk, co, transposed=form, impl=0, prelu=slope, bias=bias, stats_eps=1e-5)
+    ref2 = K().in_stats(y2)
+    torch.testing.assert_close(st2, ref2, rtol=1e-4, atol=1e-5)
+    assert not K().conv3x3_stats_ok(nhwc(rnd(1, 64, 8, 8), dt), 128)        # 64 pixels: several images per tile
+
+
