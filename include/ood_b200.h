@@ -97,6 +97,12 @@ int ood_pack_conv_weight(const float *w, void *out, int cout, int cin, int taps,
  *                       (src/ops/e4e/encoders/psp_encoders.py:41-48, helpers.py:488-491).
  *      transposed == 4: 1x1 convolution, weight pack [1][Co][Ci] (bf16, K-major): lateral / feature convolutions
  *                       (psp_encoders.py:153-154, e4e_arch.py feats_conv) and the per-tap projection consumed by ood_tap_sum.
+ *      transposed == 5: form 1 with the four output-parity phases fused into one GEMM (tcgen05 path; raw accumulators like
+ *                       form 1).  Weight pack [4 shifts][4*Co][Ci] bf16, shift t = (dy, dx) = (-(t>>1), -(t&1)), row
+ *                       (2*py + px)*Co + o holds W[o][:][ky][kx] of the tap of output parity (py, px) that reads input
+ *                       (oy+dy, ox+dx) -- ky = py if dy == 0, ky = 2 if dy == -1 and py == 0, else the row is zero; kx alike.
+ *                       For the 512 / 1024 px layers (Co <= 64): one read of the input patch per shift instead of per tap,
+ *                       2x2 output pixel blocks per position, a quarter of the tiles.
  *      Epilogue (stride-1 only; any pointer may be NULL to skip that term):
  *          v  = acc * d[b,o] + noise_w * noise[b,y,x] + bias[o];  y = act ? lrelu(v,0.2)*sqrt2 : v
  *          out_y  = y            out_ys = y * s_next[b,o]
@@ -115,7 +121,7 @@ typedef struct {
     const float *bias;     /* [Co] or NULL */
     const float *s_next;   /* [B,Co]; required iff out_ys */
     int batch, h, w, cin, cout;
-    int transposed;        /* 0 stride-1 conv | 1 stride-2 transposed conv | 2 stride-2 valid conv (data gradient of 1) | 3 stride-2 pad-1 conv | 4 1x1 conv */
+    int transposed;        /* 0 stride-1 conv | 1 stride-2 transposed conv | 2 stride-2 valid conv (data gradient of 1) | 3 stride-2 pad-1 conv | 4 1x1 conv | 5 = 1 with fused phases */
     int act;               /* 0 none | 1 leaky-ReLU(0.2)*sqrt2 | 2 PReLU(prelu_slope[o]) (AlignNet, shared-weight mode) */
     int impl;              /* 0 tcgen05 | 1 simt */
     int dtype;             /* storage type of in / out */

@@ -42,6 +42,17 @@ static inline ConvGeom make_geom(int batch, int h, int w, int cin, int cout, int
                 p.dy[t] = ky; p.dx[t] = kx; p.wt[t] = t;
             }
         p.m_total = batch * p.oh * p.ow;
+    } else if (transposed == 5) {
+        // the stride-2 transposed conv with its four output-parity phases fused into ONE implicit GEMM: a tile is 128 input
+        // positions (oy, ox) of the (h+1) x (w+1) grid, N = 4*Co (phase-major columns), K = 4 input shifts x Ci.  Shift
+        // (dy, dx) in {0,-1}^2 feeds every phase that has a tap there (weights zero-padded elsewhere: ood_b200.h), so the
+        // input patch is read 4 times instead of 9 and a tile's outputs are 2x2 pixel blocks (full 128-byte runs).  Built for
+        // the small-channel 512 / 1024 px layers, which are bound by per-tile overheads and HBM, not by the tensor pipe.
+        g.OH = 2 * h + 1; g.OW = 2 * w + 1; g.sy = g.sx = 2; g.nphases = 1;
+        ConvPhase &p = g.ph[0];
+        p.oh = h + 1; p.ow = w + 1; p.py = p.px = 0; p.ntaps = 4;
+        for (int t = 0; t < 4; ++t) { p.dy[t] = -(t >> 1); p.dx[t] = -(t & 1); p.wt[t] = t; }
+        p.m_total = batch * p.oh * p.ow;
     } else if (transposed == 4) {
         // 1x1 convolution (one tap, no padding): the encoder's lateral / feature convolutions and the per-tap projection
         // of the AlignNet's 2C -> 3 head (see ood_tap_sum)

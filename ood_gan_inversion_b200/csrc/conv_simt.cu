@@ -125,6 +125,7 @@ int conv3x3_simt(const ood_conv3x3_args &a, cudaStream_t st) {
     p.g = make_geom(a.batch, a.h, a.w, a.cin, a.cout, a.transposed);
     OOD_REQUIRE(!a.rgb_out, "conv3x3 simt: the fused ToRGB epilogue exists on the tcgen05 path only");
     OOD_REQUIRE(a.groups <= 1, "conv3x3 simt: the grouped form exists on the tcgen05 path only");
+    OOD_REQUIRE(a.transposed != 5, "conv3x3 simt: the fused-phase transposed form (5) exists on the tcgen05 path only; use form 1");
     OOD_REQUIRE(!a.acc_in && !a.tiled && !a.stats_out, "conv3x3 simt: the accumulator seed (acc_in), the tile-order tensors and the fused statistics exist on the tcgen05 path only");
     p.ep = make_epilogue(a, 1);
     int mmax = 0;

@@ -16,7 +16,7 @@
 namespace ood {
 
 constexpr int TBM = 128;            // UMMA M
-constexpr int kTcThreads = 192;     // warp0 TMA, warp1 MMA (+TMEM alloc), warps 2..5 epilogue
+// threads: warp0 TMA, warp1 MMA (+TMEM alloc), then EPW epilogue warps (template parameter of the kernel)
 
 struct TcPhase {
     int oh, ow, py, px, ntaps;
@@ -31,6 +31,7 @@ struct TcParams {
     int TW, TH, NB;                 // pixel patch of one M tile: NB*TH*TW == 128
     int nphases, n_tiles_n, total_tiles;
     int wtaps;                      // taps per group in the weight pack (9, or 1 for the 1x1 form)
+    int fused;                      // transposed == 5: N = 4*cout phase-major columns, outputs scattered to 2x2 pixel blocks
     int groups, gbatch, in_shared;  // grouped form: output image g*gbatch + i uses weights [g*9 + tap] and input image i (shared) or g*gbatch + i
     TcPhase ph[4];
     ConvEpilogue ep;
@@ -163,8 +164,11 @@ __device__ __forceinline__ TileCoord decode_tile(const TcParams &p, int tile, in
 
 // SEED: fp32 accumulator seed (ConvEpilogue::acc_in).  STATS: per-tile channel moments of the stored output
 // (ConvEpilogue::stat_partial) -- the statistics of the InstanceNorm that follows the convolution, without a pass over it.
-template <int BN, int BK, bool SEED = false, bool STATS = false>
-__global__ void __launch_bounds__(kTcThreads, 1)
+// EPW: epilogue warps, 4 or 8.  A warp reads the TMEM lane quadrant warp % 4; with 8 warps two warps share a quadrant and
+// take alternate 32-column chunks -- for tiles whose K is short (the fused-phase transposed form, K = 4 shifts) the epilogue,
+// not the MMA, sets the tile period.
+template <int BN, int BK, bool SEED = false, bool STATS = false, int EPW = 4>
+__global__ void __launch_bounds__(64 + 32 * EPW, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
     using Cfg = TcCfg<BN, BK>;
     constexpr int S = Cfg::kStages;
@@ -183,7 +187,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     if (warp == 0 && lane == 0) {
         for (int i = 0; i < S; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], EPW); }
         fence_barrier_init();
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
@@ -245,6 +249,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     } else {
         // ===================================================== epilogue warps (TMEM lane quadrant = warp % 4)
         const int quad = warp & 3;
+        const int chalf = (warp - 2) >> 2;      // EPW == 8: which of the two warps of this quadrant (chunk parity it owns)
         const int row = quad * 32 + lane;
         const int nb = row / (p.TH * p.TW), ty = (row / p.TW) % p.TH, tx = row % p.TW;
         const float nw = (p.ep.noise && p.ep.noise_w) ? *p.ep.noise_w : 0.f;
@@ -268,7 +273,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const bool stg = p.NB == 1;
             {
                 const int et = threadIdx.x - 64;
-                for (int i = et; i < BN; i += 128) {
+                for (int i = et; i < BN; i += 32 * EPW) {
                     const int n = tc.n0 + i;
                     if (p.ep.bias) sv[i] = __ldg(p.ep.bias + gofs + n);
                     if (p.ep.act == 2) sv[BN + i] = __ldg(p.ep.prelu + gofs + n);
@@ -281,7 +286,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         }
                     }
                 }
-                asm volatile("bar.sync 1, 128;" ::: "memory");      // the four epilogue warps only
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * EPW) : "memory");      // the epilogue warps only
             }
             auto vec4 = [&](int kind, const float *gvec, int ch, int j) -> float4 {      // float4 j of chunk ch of a per-sample vector
                 return stg ? *reinterpret_cast<const float4 *>(sv + kind * BN + ch * 32 + 4 * j) : __ldg(reinterpret_cast<const float4 *>(gvec) + j);
@@ -330,8 +335,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 tmem_ld32(taddr + ch * 32, r);
                 tmem_ld_wait();
                 float v[32];
-                if (valid) {
-                    const int n = tc.n0 + ch * 32;
+                int n = tc.n0 + ch * 32;
+                bool cvalid = valid;
+                int64_t cpix = pix;
+                if (p.fused) {          // column block -> (output parity phase, channel); position (oy, ox) -> pixel (2oy+fy, 2ox+fx)
+                    const int phs = n / p.cout, fy = phs >> 1, fx = phs & 1;
+                    n -= phs * p.cout;
+                    cvalid = valid && oy < p.h + 1 - fy && ox < p.w + 1 - fx;
+                    cpix = ((int64_t)b * p.OH + 2 * oy + fy) * p.OW + 2 * ox + fx;
+                }
+                if (cvalid) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
                     if (SEED && seed) {
@@ -386,11 +399,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         if (p.ep.out_f32) {
                             const int ostep = p.ep.tiled ? TBM : 1;
                             float4 *o = p.ep.tiled ? reinterpret_cast<float4 *>(p.ep.out_y) + ((int64_t)tile * (BN / 32) + ch) * 8 * TBM + row
-                                                   : reinterpret_cast<float4 *>((float *)p.ep.out_y + pix * p.cout + n);
+                                                   : reinterpret_cast<float4 *>((float *)p.ep.out_y + cpix * p.cout + n);
 #pragma unroll
                             for (int j = 0; j < 8; ++j) o[j * ostep] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                         } else {
-                            uint4 *o = reinterpret_cast<uint4 *>((__nv_bfloat16 *)p.ep.out_y + pix * p.cout + n);
+                            uint4 *o = reinterpret_cast<uint4 *>((__nv_bfloat16 *)p.ep.out_y + cpix * p.cout + n);
 #pragma unroll
                             for (int j = 0; j < 4; ++j)
                                 o[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
@@ -404,7 +417,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             const float4 t = vec4(3, sp, ch, j);
                             v[4 * j] *= t.x; v[4 * j + 1] *= t.y; v[4 * j + 2] *= t.z; v[4 * j + 3] *= t.w;
                         }
-                        uint4 *o = reinterpret_cast<uint4 *>((__nv_bfloat16 *)p.ep.out_ys + pix * p.cout + n);
+                        uint4 *o = reinterpret_cast<uint4 *>((__nv_bfloat16 *)p.ep.out_ys + cpix * p.cout + n);
 #pragma unroll
                         for (int j = 0; j < 4; ++j)
                             o[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
@@ -437,6 +450,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if constexpr (SEED) {
 #pragma unroll 1
                 for (int ch = 0; ch < BN / 32; ch += 2) { do_chunk(ch, sd, sdn); do_chunk(ch + 1, sdn, sd); }
+            } else if constexpr (EPW == 8) {
+#pragma unroll 1
+                for (int ch = chalf; ch < BN / 32; ch += 2) do_chunk(ch, sd, sdn);
             } else {
 #pragma unroll 1
                 for (int ch = 0; ch < BN / 32; ++ch) do_chunk(ch, sd, sdn);
@@ -495,10 +511,11 @@ static EncodeTiledFn get_encode_fn() {
 
 static int pow2_ceil(int v) { int r = 1; while (r < v) r <<= 1; return r; }
 
-template <int BN, int BK, bool SEED = false, bool STATS = false>
+template <int BN, int BK, bool SEED = false, bool STATS = false, int EPW = 4>
 static int launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, const TcParams &p, cudaStream_t st) {
     using Cfg = TcCfg<BN, BK>;
-    auto kern = conv_tc_kernel<BN, BK, SEED, STATS>;
+    static_assert(EPW == 4 || (EPW == 8 && !SEED && !STATS), "8 epilogue warps: plain kernels only");
+    auto kern = conv_tc_kernel<BN, BK, SEED, STATS, EPW>;
     constexpr int kSmem = Cfg::kSmemBytes + (STATS ? Cfg::kStatBytes : 0);
     static_assert(kSmem <= 227 * 1024, "shared memory budget");
     static bool attr_set = false;
@@ -511,18 +528,26 @@ static int launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, const TcPar
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int grid = std::min(p.total_tiles, sms);
-    kern<<<grid, kTcThreads, kSmem, st>>>(tmA, tmB, p);
+    kern<<<grid, 64 + 32 * EPW, kSmem, st>>>(tmA, tmB, p);
     return check_launch("conv3x3 tc");
 }
 
 void in_finalize_launch(const float *partial, float *st2, int64_t P, int C, int nchunks, float eps, int batch, cudaStream_t s);   // alignnet.cu
+
+static bool epw8() {        // experiment switch: OOD_EPW8=0 falls back to four epilogue warps
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("OOD_EPW8"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v == 1;
+}
 
 // Tile plan of a launch: patch shape, N tile, tile enumeration.  A function of (batch, h, w, cout, form, groups) and of whether
 // the call uses seeded / tile-order tensors (those keep the 128- or 256-wide N tiles) -- never of the data or of cin, so two
 // launches with the same arguments enumerate the same tiles (what the tile-order fp32 tensors rely on).
 static void plan_tiles(const ood_conv3x3_args &a, const ConvGeom &g, TcParams &p, int &BN) {
     const int groups = a.groups > 1 ? a.groups : 1;
-    BN = a.cout % 256 == 0 ? 256 : (a.cout % 128 == 0 ? 128 : (a.cout % 64 == 0 ? 64 : 32));
+    const int ncols = a.transposed == 5 ? 4 * a.cout : a.cout;      // GEMM N
+    BN = ncols % 256 == 0 ? 256 : (ncols % 128 == 0 ? 128 : (ncols % 64 == 0 ? 64 : 32));
+    p.fused = a.transposed == 5;
     p.batch = g.batch; p.h = g.h; p.w = g.w; p.cin = g.cin; p.cout = g.cout; p.OH = g.OH; p.OW = g.OW; p.sy = g.sy; p.sx = g.sx;
     p.isy = g.isy; p.isx = g.isx;
     int ohm = 0, owm = 0;
@@ -532,11 +557,11 @@ static void plan_tiles(const ood_conv3x3_args &a, const ConvGeom &g, TcParams &p
     p.NB = TBM / (p.TW * p.TH);
     p.nphases = g.nphases;
     p.groups = groups; p.gbatch = a.batch / groups; p.in_shared = a.in_shared ? 1 : 0;
-    p.wtaps = a.transposed == 4 ? 1 : 9;
+    p.wtaps = a.transposed == 4 ? 1 : (a.transposed == 5 ? 4 : 9);
     const int bn_min = (a.acc_in || a.tiled || a.stats_out) ? 128 : 64;
     int tiles = 0;
     for (;;) {
-        p.n_tiles_n = a.cout / BN;
+        p.n_tiles_n = ncols / BN;
         tiles = 0;
         for (int i = 0; i < g.nphases; ++i) {
             TcPhase &P = p.ph[i];
@@ -565,6 +590,8 @@ int conv3x3_tc(const ood_conv3x3_args &a, cudaStream_t st) {
     const int groups = a.groups > 1 ? a.groups : 1;
     OOD_REQUIRE(a.batch % groups == 0, "conv3x3 tc: batch (%d) must be a multiple of groups (%d)", a.batch, groups);
     OOD_REQUIRE(groups == 1 || (!a.d && !a.noise && !a.out_ys && !a.rgb_out), "conv3x3 tc: the grouped form supports bias / activation epilogues only");
+    OOD_REQUIRE(a.transposed != 5 || (groups == 1 && !a.acc_in && !a.tiled && !a.stats_out && !a.rgb_out),
+                "conv3x3 tc: the fused-phase transposed form takes no seed / tile-order / statistics / ToRGB options");
     OOD_REQUIRE(!(a.acc_in || a.tiled) || (a.cout % 128 == 0 && a.transposed != 1),
                 "conv3x3 tc: acc_in / tiled need cout %% 128 == 0 (got %d) and a single-phase form", a.cout);
     OOD_REQUIRE(!a.tiled || a.acc_in || (a.out_f32 && a.out_y), "conv3x3 tc: tiled = 1 without a tile-order tensor (acc_in, or out_y with out_f32)");
@@ -592,8 +619,9 @@ int conv3x3_tc(const ood_conv3x3_args &a, cudaStream_t st) {
         if (r != CUDA_SUCCESS) { set_error("conv3x3 tc: activation tensor map encode failed (%d)", (int)r); return OOD_ERR_CUDA; }
     }
     {
-        cuuint64_t dims[3] = {(cuuint64_t)a.cin, (cuuint64_t)a.cout, (cuuint64_t)(p.wtaps * groups)};
-        cuuint64_t strides[2] = {(cuuint64_t)a.cin * 2, (cuuint64_t)a.cout * a.cin * 2};
+        const cuuint64_t ncols = (cuuint64_t)(p.fused ? 4 * a.cout : a.cout);
+        cuuint64_t dims[3] = {(cuuint64_t)a.cin, ncols, (cuuint64_t)(p.wtaps * groups)};
+        cuuint64_t strides[2] = {(cuuint64_t)a.cin * 2, ncols * a.cin * 2};
         cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)BN, 1};
         cuuint32_t es[3] = {1, 1, 1};
         CUresult r = encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void *>(a.weight), dims, strides, box, es,
@@ -616,6 +644,14 @@ int conv3x3_tc(const ood_conv3x3_args &a, cudaStream_t st) {
         if (BN == 128 && BK == 64) return launch_tc<128, 64, true>(tmA, tmB, p, st);
         set_error("conv3x3 tc: acc_in needs cin %% 64 == 0 and a 128- or 256-wide N tile (cout %% 128 == 0), got cin %d cout %d", a.cin, a.cout);
         return OOD_ERR_ARG;
+    }
+    if (p.fused && epw8()) {
+        // eight epilogue warps for the fused-phase transposed form (4 k-iterations per tile: 742 -> 709 us on the 1024 px
+        // layer).  Measured and NOT adopted elsewhere: the stride-1 convolutions, including the half-K AlignNet ones, did not
+        // move with 8 warps (A/B in profiles/README.md) -- their tile period is not set by epilogue issue rate.
+#define OOD_TC_CASE8(bn, bk) if (BN == bn && BK == bk) return launch_tc<bn, bk, false, false, 8>(tmA, tmB, p, st)
+        OOD_TC_CASE8(256, 64); OOD_TC_CASE8(128, 64); OOD_TC_CASE8(256, 32); OOD_TC_CASE8(128, 32);
+#undef OOD_TC_CASE8
     }
 #define OOD_TC_CASE(bn, bk) if (BN == bn && BK == bk) return launch_tc<bn, bk>(tmA, tmB, p, st)
     OOD_TC_CASE(256, 64); OOD_TC_CASE(128, 64); OOD_TC_CASE(64, 64); OOD_TC_CASE(32, 64);
@@ -666,8 +702,8 @@ extern "C" int ood_conv3x3(const ood_conv3x3_args *a, void *stream) {
     OOD_REQUIRE(a->out_y || a->out_ys || a->rgb_out, "conv3x3: no output requested");
     OOD_REQUIRE(!a->rgb_out || (a->rgb_w && a->rgb_bias && a->act == 1 && a->h % 2 == 0 && a->w % 2 == 0), "conv3x3: fused ToRGB needs rgb_w, rgb_bias, act=1 and even sizes");
     OOD_REQUIRE(!a->out_ys || a->s_next, "conv3x3: out_ys needs s_next");
-    OOD_REQUIRE(a->transposed >= 0 && a->transposed <= 4, "conv3x3: transposed must be 0..4");
-    OOD_REQUIRE(a->transposed != 1 || (!a->out_ys && !a->act && !a->noise && !a->bias),
+    OOD_REQUIRE(a->transposed >= 0 && a->transposed <= 5, "conv3x3: transposed must be 0..5");
+    OOD_REQUIRE((a->transposed != 1 && a->transposed != 5) || (!a->out_ys && !a->act && !a->noise && !a->bias && !a->d),
                 "conv3x3: the transposed form writes raw accumulators (the epilogue follows the blur)");
     OOD_REQUIRE(a->transposed != 2 || (a->h % 2 == 1 && a->w % 2 == 1 && a->h >= 3 && a->w >= 3 && !a->noise),
                 "conv3x3: the strided data-gradient form needs an odd (2h+1)x(2w+1) input");

@@ -191,6 +191,24 @@ def pack_conv_weight(w, dtype, ci_major):
     return out
 
 
+def pack_convt_fused(w9):
+    """[9][Co][Ci] bf16 pack (pack_conv_weight) -> [4 shifts][4*Co][Ci] pack of the fused-phase transposed form (conv3x3
+    transposed=5, see ood_b200.h): shift t reads input (oy - (t>>1), ox - (t&1)); row block 2*py + px is output parity (py, px)."""
+    _, co, ci = w9.shape
+    out = torch.zeros(4, 4 * co, ci, device=w9.device, dtype=w9.dtype)
+    for t in range(4):
+        sy, sx = t >> 1, t & 1                      # 1 = the shift by -1
+        for py in range(2):
+            for px in range(2):
+                ky = py if sy == 0 else (2 if py == 0 else None)
+                kx = px if sx == 0 else (2 if px == 0 else None)
+                if ky is None or kx is None:
+                    continue
+                ph = 2 * py + px
+                out[t, ph * co:(ph + 1) * co] = w9[ky * 3 + kx]
+    return out.contiguous()
+
+
 def modulation(latent, mod_w, mod_b, wsq, conv_scale, cout, want_d=True):
     """latent [B,D] fp32 (row stride may exceed D) -> s [B,Ci], d [B,Co] (or None)."""
     _cuda(latent, mod_w, mod_b, wsq)
@@ -232,7 +250,7 @@ def conv3x3(x, weight, cout, transposed=False, impl=0, d=None, noise=None, noise
         b = b * groups
     transposed = int(transposed)      # 0 stride-1 | 1 stride-2 transposed | 2 stride-2 valid (data gradient of 1) | 3 stride-2 pad-1
     oh, ow = {0: (h, w), 1: (2 * h + 1, 2 * w + 1), 2: ((h - 1) // 2, (w - 1) // 2),
-              3: ((h - 1) // 2 + 1, (w - 1) // 2 + 1), 4: (h, w)}[transposed]
+              3: ((h - 1) // 2 + 1, (w - 1) // 2 + 1), 4: (h, w), 5: (2 * h + 1, 2 * w + 1)}[transposed]
     nt = 0
     if tiled:
         nt = _lib.lib().ood_conv3x3_tiled_bytes(b, h, w, cin, cout, transposed) // 4
@@ -271,7 +289,7 @@ def conv3x3(x, weight, cout, transposed=False, impl=0, d=None, noise=None, noise
         a.rgb_w, a.rgb_bias, a.rgb_skip, a.rgb_out = _ptr(wrgb), _ptr(rbias), _ptr(rskip), _ptr(rgb_out)
         a.rgb_taps = (C.c_float * 4)(*rtaps)
     # algorithmic work: 2*B*Co*Ci*9*H*W with H, W the INPUT size for the transposed form
-    px = h * w if transposed in (0, 1) else oh * ow
+    px = h * w if transposed in (0, 1, 5) else oh * ow
     with _timed(tag or ('conv3x3_tc' if impl == 0 else 'conv3x3_simt'), 2.0 * b * cout * cin * (1 if transposed == 4 else 9) * px):
         check(_lib.lib().ood_conv3x3(C.byref(a), _stream()), 'conv3x3')
     if rgb is not None:

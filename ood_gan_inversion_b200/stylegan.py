@@ -26,6 +26,9 @@ from . import kernels as K
 from .op import FusedLeakyReLU, fused_leaky_relu, upfirdn2d
 
 _PRECISION = os.environ.get('OOD_B200_PRECISION', 'bf16')
+# up-sampling layers with at most this many output channels use the fused-phase transposed convolution (conv3x3 form 5): the
+# zero-padded weight blocks cost 1.8x the MACs, which only the HBM / per-tile-overhead bound small-channel layers can afford
+_FUSED_T_MAX_CO = int(os.environ.get('OOD_FUSED_T_MAX_CO', 64))
 
 
 def set_precision(p):
@@ -218,9 +221,20 @@ class ModulatedConv2d(nn.Module):
                 wsq = K.weight_sumsq(w) if self.demodulate else None
                 mw = _pad_dim(self.modulation.weight.detach().float(), 0, cin_p).contiguous()
                 mb = _pad_dim(self.modulation.bias.detach().float() * self.modulation.lr_mul, 0, cin_p).contiguous()
+                # small-channel up-sampling layers (512 / 1024 px): fused-phase transposed form (conv3x3 transposed=5)
+                self._cache['fused_t'] = K.pack_convt_fused(wp) if (self.upsample and self.kernel_size == 3 and _PRECISION == 'bf16'
+                                                                      and cout_p <= _FUSED_T_MAX_CO and cin_p % 32 == 0) else None
             self._cache['k'] = (key, (wp, wsq, mw, mb))
             hit = self._cache['k']
         return hit[1]
+
+    def conv_transposed(self, xs):
+        """Raw accumulators [B,2h+1,2w+1,Co] of the stride-2 transposed convolution (model.py:246-256) of pre-modulated xs."""
+        wp, _, _, _ = self.packed()
+        wf = self._cache.get('fused_t')
+        if wf is not None and _impl() == 0:
+            return K.conv3x3(xs, wf, self.cout_p, transposed=5, impl=0)[0]
+        return K.conv3x3(xs, wp, self.cout_p, transposed=True, impl=_impl())[0]
 
     def coeffs(self, style):
         """style [B,style_dim] fp32 (may be a strided row view of the W+ tensor) -> (s [B,Ci], d [B,Co])."""
@@ -251,7 +265,7 @@ class ModulatedConv2d(nn.Module):
             return _to_nchw(y, self.out_channel)[:, :, 1::2, 1::2][:, :, :oh, :ow].contiguous()
         xs = _to_nhwc(input, s, self.cin_p)
         if self.upsample:
-            t, _ = K.conv3x3(xs, wp, self.cout_p, transposed=True, impl=_impl())
+            t = self.conv_transposed(xs)
             img, _, _ = K.blur_act(t, self.blur.taps, d=d, act=False, want_img=True)
             return _to_nchw(img, self.out_channel)
         y, _ = K.conv3x3(xs, wp, self.cout_p, impl=_impl(), d=d)
@@ -315,7 +329,7 @@ class StyledConv(nn.Module):
         if not has_act:
             raise NotImplementedError('ood_gan_inversion_b200: StyledConv(activation=False) is not on the hot path')
         if conv.upsample:
-            t, _ = K.conv3x3(xs, wp, conv.cout_p, transposed=True, impl=_impl())
+            t = conv.conv_transposed(xs)
             if hook is None:
                 _, y, ys = K.blur_act(t, conv.blur.taps, d=d, noise=noise, noise_w=nw, bias=bias, s_next=s_next, act=True,
                                       want_y=want_y, want_ys=want_ys)

@@ -28,3 +28,6 @@ for ci, co, r in [(64, 32, 512), (128, 64, 256), (256, 128, 128), (512, 256, 64)
     byt = b * (r * r * ci + (2 * r + 1) ** 2 * co) * 2
     fl = 2.0 * b * co * ci * 9 * r * r
     print(f'convT {ci}->{co} {r}->{2 * r + 1}: {ms * 1e3:.1f} us  {byt / ms / 1e6:.0f} GB/s ({byt / ms / 1e6 / 6534.8:.3f} of HBM)  {fl / ms / 1e9:.0f} TFLOP/s')
+    wf = K.pack_convt_fused(wp)
+    ms = timeit(lambda: K.conv3x3(x, wf, co, transposed=5))
+    print(f'   fused phases (form 5):        {ms * 1e3:.1f} us  {byt / ms / 1e6:.0f} GB/s ({byt / ms / 1e6 / 6534.8:.3f} of HBM)  {fl / ms / 1e9:.0f} TFLOP/s')

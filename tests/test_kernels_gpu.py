@@ -717,3 +717,24 @@ def test_conv3x3_fused_output_statistics(case):
     assert not K().conv3x3_stats_ok(nhwc(rnd(1, 64, 8, 8), dt), 128)        # 64 pixels: several images per tile
 
 
+
+@pytest.mark.parametrize('case', [dict(b=2, h=8, w=8, ci=64, co=32), dict(b=1, h=13, w=21, ci=64, co=32), dict(b=2, h=16, w=16, ci=128, co=64),
+                                  dict(b=1, h=5, w=40, ci=32, co=32), dict(b=3, h=32, w=32, ci=64, co=128), dict(b=1, h=1, w=1, ci=32, co=32)])
+def test_conv_transposed_fused_phases(case):
+    """conv3x3 form 5 (four output-parity phases in one GEMM, zero-padded shift weights) == form 1 == conv_transpose2d
+    (model.py:246-256), including odd sizes and the last output row / column that only the even phases own."""
+    b, h, w, ci, co = (case[k] for k in ('b', 'h', 'w', 'ci', 'co'))
+    dt = torch.bfloat16
+    x = rnd(b, ci, h, w, seed=1).to(dt).float()
+    wt = (0.1 * rnd(co, ci, 3, 3, seed=2)).to(dt).float()
+    w9 = K().pack_conv_weight(wt.to(DEV), dt, False)
+    wf = K().pack_convt_fused(w9)
+    assert wf.shape == (4, 4 * co, ci)
+    t5, _ = K().conv3x3(nhwc(x, dt), wf, co, transposed=5, impl=0)
+    t1, _ = K().conv3x3(nhwc(x, dt), w9, co, transposed=1, impl=0)
+    assert t5.shape == (b, 2 * h + 1, 2 * w + 1, co)
+    ref = F.conv_transpose2d(x.double(), wt.double().transpose(0, 1), stride=2).float()
+    torch.testing.assert_close(nchw(t5), ref, rtol=2e-2, atol=2e-2)
+    torch.testing.assert_close(t5.float(), t1.float(), rtol=1e-2, atol=1e-2)
+    f5, _ = K().conv3x3(nhwc(x, dt), wf, co, transposed=5, impl=0, out_f32=True)
+    torch.testing.assert_close(nchw(f5), ref, rtol=1e-3, atol=1e-3)
