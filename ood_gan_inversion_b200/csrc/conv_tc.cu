@@ -400,14 +400,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             const int ostep = p.ep.tiled ? TBM : 1;
                             float4 *o = p.ep.tiled ? reinterpret_cast<float4 *>(p.ep.out_y) + ((int64_t)tile * (BN / 32) + ch) * 8 * TBM + row
                                                    : reinterpret_cast<float4 *>((float *)p.ep.out_y + cpix * p.cout + n);
+                            if (p.ep.tiled) {
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) o[j * ostep] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                                for (int j = 0; j < 8; ++j) o[j * ostep] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                            } else {        // NHWC: a 128-byte run per thread as four 32-byte stores
+#pragma unroll
+                                for (int j = 0; j < 4; ++j)
+                                    st_global_256(o + 2 * j, __float_as_uint(v[8 * j]), __float_as_uint(v[8 * j + 1]), __float_as_uint(v[8 * j + 2]),
+                                                  __float_as_uint(v[8 * j + 3]), __float_as_uint(v[8 * j + 4]), __float_as_uint(v[8 * j + 5]),
+                                                  __float_as_uint(v[8 * j + 6]), __float_as_uint(v[8 * j + 7]));
+                            }
                         } else {
-                            uint4 *o = reinterpret_cast<uint4 *>((__nv_bfloat16 *)p.ep.out_y + cpix * p.cout + n);
+                            __nv_bfloat16 *o = (__nv_bfloat16 *)p.ep.out_y + cpix * p.cout + n;      // 64-byte aligned (cout, n % 32 == 0)
 #pragma unroll
-                            for (int j = 0; j < 4; ++j)
-                                o[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
-                                                  pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+                            for (int j = 0; j < 2; ++j)
+                                st_global_256(o + 16 * j, pack_bf16x2(v[16 * j], v[16 * j + 1]), pack_bf16x2(v[16 * j + 2], v[16 * j + 3]),
+                                              pack_bf16x2(v[16 * j + 4], v[16 * j + 5]), pack_bf16x2(v[16 * j + 6], v[16 * j + 7]),
+                                              pack_bf16x2(v[16 * j + 8], v[16 * j + 9]), pack_bf16x2(v[16 * j + 10], v[16 * j + 11]),
+                                              pack_bf16x2(v[16 * j + 12], v[16 * j + 13]), pack_bf16x2(v[16 * j + 14], v[16 * j + 15]));
                         }
                     }
                     if (p.ep.out_ys) {
@@ -417,11 +427,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             const float4 t = vec4(3, sp, ch, j);
                             v[4 * j] *= t.x; v[4 * j + 1] *= t.y; v[4 * j + 2] *= t.z; v[4 * j + 3] *= t.w;
                         }
-                        uint4 *o = reinterpret_cast<uint4 *>((__nv_bfloat16 *)p.ep.out_ys + cpix * p.cout + n);
+                        __nv_bfloat16 *o = (__nv_bfloat16 *)p.ep.out_ys + cpix * p.cout + n;
 #pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            o[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
-                                              pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+                        for (int j = 0; j < 2; ++j)
+                            st_global_256(o + 16 * j, pack_bf16x2(v[16 * j], v[16 * j + 1]), pack_bf16x2(v[16 * j + 2], v[16 * j + 3]),
+                                          pack_bf16x2(v[16 * j + 4], v[16 * j + 5]), pack_bf16x2(v[16 * j + 6], v[16 * j + 7]),
+                                          pack_bf16x2(v[16 * j + 8], v[16 * j + 9]), pack_bf16x2(v[16 * j + 10], v[16 * j + 11]),
+                                          pack_bf16x2(v[16 * j + 12], v[16 * j + 13]), pack_bf16x2(v[16 * j + 14], v[16 * j + 15]));
                     }
                 }
                 if constexpr (STATS) {
@@ -605,6 +617,7 @@ int conv3x3_tc(const ood_conv3x3_args &a, cudaStream_t st) {
     p.ep = make_epilogue(a, a.out_f32);
     p.out_bf16 = 1;
     OOD_REQUIRE(!a.acc_in || (uintptr_t)a.acc_in % 16 == 0, "conv3x3 tc: acc_in must be 16-byte aligned");
+    OOD_REQUIRE((uintptr_t)a.out_y % 32 == 0 && (uintptr_t)a.out_ys % 32 == 0, "conv3x3 tc: outputs must be 32-byte aligned (256-bit stores)");
 
     CUtensorMap tmA, tmB;
     {
