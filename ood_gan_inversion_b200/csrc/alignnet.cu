@@ -342,8 +342,37 @@ __global__ void __launch_bounds__(256) in_apply_kernel(const T *__restrict__ x, 
     }
 }
 
+// The same for C % 32 == 0 with the chunk loop spread over eight thread rows: a block owns (image, 32 channels), row r sums
+// chunks r, r+8, ..., and the eight row sums are combined in a fixed order.  With the convolution's fused statistics there
+// are up to 512 partials per channel (one per 128-pixel tile of a 256 px image); one thread walking them took ~35 us.
+__global__ void __launch_bounds__(256) in_finalize_wide_kernel(const float *__restrict__ partial, float *__restrict__ st2, int64_t P,
+                                                                int C, int nchunks, float eps) {
+    __shared__ double s0[8][32], s1[8][32];
+    const int cg = C / 32;
+    const int b = blockIdx.x / cg, c = (blockIdx.x - b * cg) * 32 + (threadIdx.x & 31), r = threadIdx.x >> 5;
+    const float2 *p = reinterpret_cast<const float2 *>(partial) + ((int64_t)b * nchunks + r) * C + c;
+    double a0 = 0, a1 = 0;
+#pragma unroll 4
+    for (int k = r; k < nchunks; k += 8, p += (int64_t)8 * C) {
+        const float2 v = __ldg(p);
+        a0 += v.x; a1 += v.y;
+    }
+    s0[r][threadIdx.x & 31] = a0; s1[r][threadIdx.x & 31] = a1;
+    __syncthreads();
+    if (r == 0) {
+#pragma unroll
+        for (int k = 1; k < 8; ++k) { a0 += s0[k][threadIdx.x]; a1 += s1[k][threadIdx.x]; }
+        const double m = a0 / (double)P, v = fmax(a1 / (double)P - m * m, 0.0);
+        *reinterpret_cast<float2 *>(st2 + ((int64_t)b * C + c) * 2) = make_float2((float)m, (float)(1.0 / sqrt(v + eps)));
+    }
+}
+
 // finalize [B][nchunks][C][2] partial moments (shared with the convolution's fused statistics, conv_tc.cu)
 void in_finalize_launch(const float *partial, float *st2, int64_t P, int C, int nchunks, float eps, int batch, cudaStream_t s) {
+    if (C % 32 == 0 && nchunks > 8) {
+        in_finalize_wide_kernel<<<batch * (C / 32), 256, 0, s>>>(partial, st2, P, C, nchunks, eps);
+        return;
+    }
     const int64_t total = (int64_t)batch * C;
     in_finalize_kernel<<<ceil_div(total, 256), 256, 0, s>>>(partial, st2, P, C, nchunks, eps, total);
 }
@@ -370,8 +399,7 @@ static int launch_stats(const void *x, const void *y, float *partial, float *st,
         auto kern = in_partial_kernel<T, 2>;
         if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         kern<<<grid, 256, smem, s>>>((const T *)x, nullptr, partial, P, C, nchunks, chunk_px);
-        const int64_t total = (int64_t)batch * C;
-        in_finalize_kernel<<<ceil_div(total, 256), 256, 0, s>>>(partial, st, P, C, nchunks, eps, total);
+        in_finalize_launch(partial, st, P, C, nchunks, eps, batch, s);
     }
     return check_launch("in_stats", 2);
 }
@@ -472,8 +500,7 @@ extern "C" int ood_alignnet_res0_stats(const void *t, const float *st2, const fl
         alignnet_ew_kernel<float, 2><<<grid, 256, 0, s>>>((const float *)cur, (const float *)enc, st6, (const float *)t, st2, w, bias, (float *)out, (float *)out + channels, 2 * channels, workspace, pixels, channels, chunk);
     else
         alignnet_ew_kernel<__nv_bfloat16, 2><<<grid, 256, 0, s>>>((const __nv_bfloat16 *)cur, (const __nv_bfloat16 *)enc, st6, (const __nv_bfloat16 *)t, st2, w, bias, (__nv_bfloat16 *)out, (__nv_bfloat16 *)out + channels, 2 * channels, workspace, pixels, channels, chunk);
-    const int64_t total = (int64_t)batch * 2 * channels;
-    in_finalize_kernel<<<ceil_div(total, 256), 256, 0, s>>>(workspace, stats_out, pixels, 2 * channels, (int)grid.x, eps, total);
+    in_finalize_launch(workspace, stats_out, pixels, 2 * channels, (int)grid.x, eps, batch, s);
     return check_launch("alignnet_res0_stats", 2);
 }
 
