@@ -365,7 +365,7 @@ def main():
                 gpu_launches=int(launches),
                 roofline=dict(kernel='conv_tc_kernel (tcgen05 implicit-GEMM 3x3 modulated conv)', bound='tensor', achieved=conv_tf,
                               peak=pk['tf_sus'], unit='TFLOP/s', frac=conv_tf / pk['tf_sus'], traffic=ncu_traffic('conv256'),
-                              traffic_note='DRAM bytes of one conv_tc_kernel<256,64> launch (AlignNet 1024->1024 ch at 64 px: 1.24 TFLOP, 0.29 GB of activations + weights; L2 hit 97 %), profiles/ncu_r01_conv256_raw.csv',
+                              traffic_note='DRAM bytes of one conv_tc_kernel<256,64,STATS> launch (AlignNet 1024->1024 ch at 64 px: 1.24 TFLOP, 0.29 GB of activations + weights algorithmic; L2 hit 96 %), profiles/ncu_r01_conv256_raw.csv',
                               peak_source=pk['src'] + ', sustained figure (kernel timed inside a long step)',
                               share_of_step=conv['ms'] / prof_steps / max(step_ms, 1e-9), launches_per_step=conv['launches'] / prof_steps,
                               timing='CUDA events around every launch in an eager pass of the same step, same process'),

@@ -19,8 +19,8 @@ cap() {   # name regex skip command...
 B="python bench.py --ncu --steps 1 --warmup 3 --no-cpu-baseline"
 # AlignNet second convolution, 1024 -> 1024 channels at 64 px, full K, fused output statistics (STATS variant, 3rd launch)
 cap conv256 'conv_tc_kernel<.int.256, .int.64, .bool.0, .bool.1' 2 $B
-# fused-phase transposed convolution of the 1024 px layer (8 epilogue warps; 2nd launch = 64 -> 32 at 512 -> 1025)
-cap convt 'conv_tc_kernel<.int.128, .int.64, .bool.0, .bool.0, .int.8' 1 $B
+# fused-phase transposed convolution of the 1024 px layer (8 epilogue warps, N = 128: 64 -> 32 channels at 512 -> 1025 px)
+cap convt 'conv_tc_kernel<.int.128, .int.64, .bool.0, .bool.0, .int.8' 0 $B
 python scripts/kernel_sweep.py > gpurun_out/sweep.log 2>&1
 python scripts/bench_extra.py > gpurun_out/bench_extra.log 2>&1
 python scripts/seed_bench.py > gpurun_out/seed_bench.log 2>&1
