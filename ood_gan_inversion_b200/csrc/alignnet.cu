@@ -191,9 +191,15 @@ __device__ __forceinline__ PixSpan pix_span(int C, int64_t P, int64_t chunk) {
     return s;
 }
 static inline void pix_grid(int C, int N, int64_t P, int batch, dim3 &grid, int64_t &chunk) {
+    // ONE resident wave (two 256-thread blocks per SM at 82-128 registers), like the statistics pass: a thread folds ~100 scalar
+    // coefficients (statistics, affine weights) before its first pixel, so blocks should be few and long, and a second,
+    // partial wave costs a whole block time.  The earlier fixed 8 blocks per SM ran 4-14 pixels per thread at 32 / 64 px:
+    // 75 / 130 us for passes whose HBM time is 15 / 60 us (scripts/seed_bench.py; OOD_EW_WAVES overrides the wave count).
+    static int waves = -1;
+    if (waves < 0) { const char *e = getenv("OOD_EW_WAVES"); waves = e ? atoi(e) : 1; if (waves <= 0) waves = 1; }
     const int lanes = std::max(1, 256 / (C / N));
-    const int64_t want_blocks = std::max<int64_t>(1, (int64_t)kNumSMs * 8 / batch);
-    chunk = std::max<int64_t>((P + want_blocks - 1) / want_blocks, (int64_t)lanes * 4);
+    const int64_t per_image = std::max<int64_t>(1, (int64_t)kNumSMs * 2 * waves / batch);
+    chunk = std::max<int64_t>((P + per_image - 1) / per_image, (int64_t)lanes * 4);
     chunk = (chunk + lanes - 1) / lanes * lanes;
     grid = dim3((unsigned)((P + chunk - 1) / chunk), batch);
 }

@@ -546,6 +546,15 @@ static int launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, const TcPar
 
 void in_finalize_launch(const float *partial, float *st2, int64_t P, int C, int nchunks, float eps, int batch, cudaStream_t s);   // alignnet.cu
 
+// Narrower N tiles are tried while a launch has fewer tiles than this.  100, not one per SM: at 100..147 tiles one wave of wide
+// tiles on part of the SMs beats two waves of half-width tiles, which also need 1.33x the L2 -> SM operand traffic per FLOP
+// (encoder 256 -> 256 at 32 px, 128 tiles: 0.83 -> 0.74 ms per 26 launches; OOD_MIN_TILES overrides).
+static int min_tiles() {
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("OOD_MIN_TILES"); v = e ? atoi(e) : 100; if (v <= 0) v = 100; }
+    return v;
+}
+
 static bool epw8() {        // experiment switch: OOD_EPW8=0 falls back to four epilogue warps
     static int v = -1;
     if (v < 0) { const char *e = getenv("OOD_EPW8"); v = (e && e[0] == '0') ? 0 : 1; }
@@ -586,7 +595,7 @@ static void plan_tiles(const ood_conv3x3_args &a, const ConvGeom &g, TcParams &p
         }
         // few-pixel problems (the tails of the encoder's style heads) are bound by streaming the weights: narrower N
         // tiles put more SMs on that stream
-        if (tiles >= kNumSMs || BN <= bn_min || a.rgb_out) break;
+        if (tiles >= min_tiles() || BN <= bn_min || a.rgb_out) break;
         BN >>= 1;
     }
     p.total_tiles = tiles;

@@ -318,3 +318,28 @@ def test_graphed_forward_replays_the_eager_result():
     assert torch.equal(out1, ref1) and torch.equal(out2, ref2)
     with pytest.raises(ValueError):
         graphed(lat1[:1])
+
+
+def test_pipelined_forward_serving_loop():
+    """graphs.PipelinedForward: host -> device -> replay -> host over two round-robin graphs returns, for every request, what
+    the eager call returns (fixed noise), in order, including when the same pinned buffers are reused by later requests."""
+    from ood_gan_inversion_b200.graphs import PipelinedForward
+    m = sg()
+    m.set_precision('bf16')
+    size = 64
+    gen = m.Generator(size, 512, 8).to(DEV).eval()
+    gen.load_state_dict(ostyle.synthetic_generator_state(size, seed=5))
+    fn = lambda lat: gen(lat, input_is_tensor=True, input_is_latent=True, randomize_noise=False)[0]
+    lats = [torch.randn(2, gen.n_latent, 512, generator=torch.Generator().manual_seed(s)).pin_memory() for s in range(5)]
+    with torch.no_grad():
+        refs = [fn(l.to(DEV)).cpu() for l in lats]
+    pipe = PipelinedForward(fn, lats[0].to(DEV), depth=2)
+    outs = [torch.empty_like(refs[0]).pin_memory() for _ in lats]
+    events = [pipe.submit(l, o) for l, o in zip(lats, outs)]
+    events[0].synchronize()
+    assert torch.equal(outs[0], refs[0])
+    pipe.synchronize()
+    for o, r in zip(outs, refs):
+        assert torch.equal(o, r)
+    with pytest.raises(ValueError):
+        pipe.submit(lats[0][:1], outs[0])
