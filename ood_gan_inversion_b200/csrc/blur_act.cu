@@ -224,7 +224,7 @@ extern "C" int ood_noise_act(const void *img, void *out_y, void *out_ys, const f
     OOD_REQUIRE(channels % N == 0, "noise_act: channels (%d) must be a multiple of %d", channels, N);
     OOD_REQUIRE(channels / N <= 256, "noise_act: too many channels (%d)", channels);
     const int lanes = std::max(1, 256 / (channels / N));
-    const int64_t want = std::max<int64_t>(1, (int64_t)kNumSMs * 8 / batch);
+    const int64_t want = std::max<int64_t>(1, (int64_t)kNumSMs * pixwalk_blocks_per_sm(8) / batch);
     int64_t chunk = std::max<int64_t>((pixels + want - 1) / want, (int64_t)lanes * 4);
     chunk = (chunk + lanes - 1) / lanes * lanes;
     dim3 grid((unsigned)((pixels + chunk - 1) / chunk), batch);

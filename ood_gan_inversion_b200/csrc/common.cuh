@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstdio>
 
 #include "../../include/ood_b200.h"
@@ -14,6 +15,14 @@ namespace ood {
 
 void set_error(const char *fmt, ...);
 int check_launch(const char *what, int kernels = 1);
+// blocks per SM for the pixel-walk elementwise kernels (a thread owns a channel vector and walks a chunk of pixels): few long
+// blocks -- one resident wave -- beat many short ones, whose per-thread coefficient set-up and partial last wave dominate on
+// small tensors (alignnet.cu: pix_grid).  OOD_PW_BPS overrides for experiments.
+static inline int pixwalk_blocks_per_sm(int dflt) {
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("OOD_PW_BPS"); v = e ? atoi(e) : 0; if (v < 0) v = 0; }
+    return v > 0 ? v : dflt;
+}
 
 #define OOD_REQUIRE(cond, ...)              \
     do {                                    \

@@ -235,7 +235,7 @@ extern "C" int ood_se_residual(const void *v, const float *gate, const void *sho
     OOD_REQUIRE(channels % N == 0 && channels / N <= 256, "se_residual: channels (%d) must be a multiple of %d and at most %d", channels, N, 256 * N);
     const int64_t P = (int64_t)h * w;
     const int lanes = std::max(1, 256 / (channels / N));
-    const int64_t want_blocks = std::max<int64_t>(1, (int64_t)kNumSMs * 8 / batch);
+    const int64_t want_blocks = std::max<int64_t>(1, (int64_t)kNumSMs * pixwalk_blocks_per_sm(8) / batch);
     int64_t chunk = std::max<int64_t>((P + want_blocks - 1) / want_blocks, (int64_t)lanes * 4);
     chunk = (chunk + lanes - 1) / lanes * lanes;
     dim3 grid((unsigned)((P + chunk - 1) / chunk), batch);
