@@ -738,3 +738,21 @@ def test_conv_transposed_fused_phases(case):
     torch.testing.assert_close(t5.float(), t1.float(), rtol=1e-2, atol=1e-2)
     f5, _ = K().conv3x3(nhwc(x, dt), wf, co, transposed=5, impl=0, out_f32=True)
     torch.testing.assert_close(nchw(f5), ref, rtol=1e-3, atol=1e-3)
+
+
+@pytest.mark.parametrize('case', [dict(b=2, h=20, w=128, ci=64, co=64), dict(b=1, h=9, w=256, ci=64, co=32), dict(b=2, h=7, w=128, ci=32, co=32)])
+def test_conv3x3_encoder_epilogues_on_wide_images(case):
+    """The encoder's epilogues (bottleneck_IR_SE, e4e/encoders/helpers.py:476-501) at small channel counts on 128 / 256 px wide
+    images: PReLU(conv) and PReLU(conv + bias) on the generic tiles, conv + folded-BatchNorm bias on the row-sliding kernel."""
+    b, h, w_, ci, co = case['b'], case['h'], case['w'], case['ci'], case['co']
+    dt = torch.bfloat16
+    x, w = rnd(b, ci, h, w_, seed=1).to(dt).float(), (0.1 * rnd(co, ci, 3, 3, seed=2)).to(dt).float()
+    slope, bias = 0.25 + 0.1 * rnd(co, seed=3), 0.2 * rnd(co, seed=4)
+    wp = K().pack_conv_weight(w.to(DEV), dt, False)
+    raw = F.conv2d(x.double(), w.double(), padding=1).float()
+    y1, _ = K().conv3x3(nhwc(x, dt), wp, co, impl=0, prelu=slope.to(DEV))
+    torch.testing.assert_close(nchw(y1), F.prelu(raw, slope), rtol=2e-2, atol=2e-2)
+    y2, _ = K().conv3x3(nhwc(x, dt), wp, co, impl=0, prelu=slope.to(DEV), bias=bias.to(DEV))
+    torch.testing.assert_close(nchw(y2), F.prelu(raw + bias[None, :, None, None], slope), rtol=2e-2, atol=2e-2)
+    y3, _ = K().conv3x3(nhwc(x, dt), wp, co, impl=0, bias=bias.to(DEV))
+    torch.testing.assert_close(nchw(y3), raw + bias[None, :, None, None], rtol=2e-2, atol=2e-2)
