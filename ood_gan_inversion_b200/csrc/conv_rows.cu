@@ -453,6 +453,12 @@ int conv3x3_rows(const ood_conv3x3_args &a, cudaStream_t st, int *handled) {
     p.strips_y = ceil_div(a.h, kStripRows);
     const int64_t total = (int64_t)p.tiles_x * p.strips_y * a.batch;
     if (total >= (1LL << 31)) return OOD_OK;
+    {   // fewer strips than SMs (e.g. 64 at 128 px, batch 16): the generic tiles fill the GPU.  OOD_ROWS_MIN_STRIPS overrides
+        // (the parity tests run this kernel on small problems with it).
+        const char *e = getenv("OOD_ROWS_MIN_STRIPS");
+        const int64_t min_strips = e ? atoll(e) : kNumSMs;
+        if (total < min_strips) return OOD_OK;
+    }
     p.total_strips = (int)total;
     p.ep = make_epilogue(a, 0);
     *handled = 1;
