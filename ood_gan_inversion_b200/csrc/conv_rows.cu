@@ -265,8 +265,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (int q = 0; q < CH; ++q) {
                 dreg[q] = p.ep.d ? __ldg(p.ep.d + (int64_t)b * CO + n0 + q) : 1.f;
                 breg[q] = p.ep.bias ? __ldg(p.ep.bias + n0 + q) : 0.f;
-                // out_ys: the next layer's style; PReLU form (act == 2, no out_ys -- host check): the channel's negative slope
-                sreg[q] = p.ep.out_ys ? __ldg(p.ep.s_next + (int64_t)b * CO + n0 + q) : (p.ep.act == 2 ? __ldg(p.ep.prelu + n0 + q) : 1.f);
+                sreg[q] = p.ep.out_ys ? __ldg(p.ep.s_next + (int64_t)b * CO + n0 + q) : 1.f;
             }
             // noise is streamed from HBM (4 B per pixel): prefetch it two row tiles ahead, or its ~1 us latency lands on the
             // critical path of every tile (ncu: 28 % of all stall samples sat on the first use of this load)
@@ -305,7 +304,6 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     v[q] = fmaf(__uint_as_float(r[q]), dreg[q], breg[q] + nz);
 
                     if (p.ep.act == 1) v[q] = lrelu_sqrt2(v[q]);
-                    else if (p.ep.act == 2) v[q] = v[q] > 0.f ? v[q] : v[q] * sreg[q];
                 }
                 float rgbp[3] = {0.f, 0.f, 0.f};
                 if (p.ep.rgb_out) {          // fused ToRGB: this thread's CH channels of the unscaled activation
@@ -400,9 +398,9 @@ static int launch(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensor
 int conv3x3_rows(const ood_conv3x3_args &a, cudaStream_t st, int *handled) {
     using namespace rows;
     *handled = 0;
-    // PReLU convolutions (the encoder's 64-channel layers at 128 / 256 px) are NOT routed here although the epilogue has the
-    // form: measured 0.22 -> 0.37 ms (4 launches at 128 px: 64 strips for 148 SMs) and 0.19 -> 0.22 ms (256 px) against the
-    // generic tiles -- the strips are sized for the 512 / 1024 px generator layers.
+    // PReLU convolutions (the encoder's 64-channel layers at 128 / 256 px) stay on the generic tiles.  A PReLU form of this
+    // epilogue was built and measured: 0.22 -> 0.37 ms (4 launches at 128 px: 64 strips for 148 SMs), 0.19 -> 0.22 ms at
+    // 256 px, and its extra live registers made the <64,64> instance spill (512 px generator layer 0.48 -> 0.82 ms) -- removed.
     if (a.transposed || a.dtype != OOD_BF16 || a.out_f32 || a.act == 2 || a.groups > 1 || a.acc_in || a.tiled || a.stats_out) return OOD_OK;
     if (!((a.cin == 32 || a.cin == 64) && (a.cout == 32 || a.cout == 64) && a.cin >= a.cout)) return OOD_OK;
     if (a.w % 128 != 0 || a.h < 3 || (int64_t)a.batch * a.h * a.w >= (1LL << 31)) return OOD_OK;
