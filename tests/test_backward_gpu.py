@@ -171,3 +171,38 @@ def test_adam_inversion_loss_curve_matches_oracle():
     torch.testing.assert_close(torch.tensor(curves[0]), torch.tensor(curves[1]), rtol=1e-3, atol=1e-6)
     assert float((finals[0] - finals[1]).abs().max()) < 5e-3
     sg.set_precision('bf16')
+
+
+def test_inversion_api_per_image_and_shared_delta():
+    """ood_gan_inversion_b200.inversion.invert (BASELINE config 4 in one call): per-image W+ codes reproduce the hand-written Adam
+    loop above, and the shared-offset mode (arch delta_latent, OOD_faceGAN_e4e_arch.py:126-129) moves ONE [1,n,512] offset for
+    every image and matches torch.autograd through the oracle."""
+    import ood_gan_inversion_b200.stylegan as sg
+    from ood_gan_inversion_b200.inversion import LatentInverter, generator_synthesizer, invert
+    sg.set_precision('fp32')
+    size, batch, steps = 32, 2, 6
+    sd = ostyle.synthetic_generator_state(size, seed=3)
+    gen = sg.Generator(size, 512, 8).to(DEV)
+    gen.load_state_dict(sd)
+    sdd = {k: v.to(DEV) for k, v in sd.items()}
+    lat0 = 0.5 * torch.randn(batch, gen.n_latent, 512, generator=torch.Generator().manual_seed(4)).to(DEV)
+    with torch.no_grad():
+        target = ostyle.generator_forward(sdd, torch.randn(batch, gen.n_latent, 512, generator=torch.Generator().manual_seed(5)).to(DEV),
+                                          size, randomize_noise=False)
+    lat, losses = invert(gen, target, lat0, steps=steps, lr=0.01)
+    assert lat.shape == lat0.shape and losses[-1] < losses[0]
+    oracle = LatentInverter(lambda l: ostyle.generator_forward(sdd, l, size, randomize_noise=False), lr=0.01)
+    lat_o, losses_o = oracle.run(target, lat0, steps)
+    torch.testing.assert_close(torch.tensor(losses), torch.tensor(losses_o), rtol=1e-3, atol=1e-6)
+    assert float((lat - lat_o).abs().max()) < 5e-3
+    inv = LatentInverter(generator_synthesizer(gen), lr=0.01, shared_delta=True)
+    lat_d, losses_d = inv.run(target, lat0, steps)
+    oracle_d = LatentInverter(lambda l: ostyle.generator_forward(sdd, l, size, randomize_noise=False), lr=0.01, shared_delta=True)
+    _, losses_od = oracle_d.run(target, lat0, steps)
+    assert inv.delta.shape == (1, gen.n_latent, 512) and losses_d[-1] < losses_d[0]
+    torch.testing.assert_close(torch.tensor(losses_d), torch.tensor(losses_od), rtol=1e-3, atol=1e-6)
+    # Adam normalises every element's step, so elements whose gradient sits at the rounding noise can walk apart by a few lr:
+    # the offsets agree on average and never by more than half of the distance walked (6 steps x lr 0.01)
+    diff = (inv.delta - oracle_d.delta).abs()
+    assert float(diff.mean()) < 5e-4 and float(diff.max()) < 3e-2
+    sg.set_precision('bf16')

@@ -102,3 +102,82 @@ def test_two_rank_gloo_sharding_and_timing():
         assert slowest == pytest.approx(200.0)                       # max over ranks, not the local time
         assert thr == pytest.approx(33 / 0.2)                        # all units / slowest rank
         assert gathered == [(0, 17), (17, 33)]
+
+
+# ----------------------------------------------------------------------------------------------- inversion (config 4) host logic
+def _toy_problem(n, seed=0):
+    """A differentiable stand-in for the synthesis (the real one is CUDA-only): image = tanh(latent . A)."""
+    g = torch.Generator().manual_seed(seed)
+    a = torch.randn(4 * 8, 3 * 6 * 6, generator=g) * 0.3
+    base = torch.randn(n, 4, 8, generator=g) * 0.1
+    target = torch.tanh((torch.randn(n, 4, 8, generator=g)).reshape(n, -1) @ a).reshape(n, 3, 6, 6)
+    synth = lambda lat: torch.tanh(lat.reshape(lat.shape[0], -1) @ a).reshape(-1, 3, 6, 6)
+    return synth, base, target
+
+
+def test_latent_inverter_single_process_modes():
+    from ood_gan_inversion_b200.inversion import LatentInverter
+    synth, base, target = _toy_problem(6)
+    lat, losses = LatentInverter(synth, lr=0.05).run(target, base, 40)
+    assert lat.shape == base.shape and losses[-1] < 0.5 * losses[0]
+    lat_d, losses_d = LatentInverter(synth, lr=0.05, shared_delta=True).run(target, base, 40)
+    delta = lat_d - base
+    assert torch.allclose(delta[0], delta[-1], atol=1e-6) and losses_d[-1] < losses_d[0]     # ONE offset for every image
+    with pytest.raises(ValueError):
+        LatentInverter(synth).run(target, base[:2], 1)
+
+
+def _inversion_worker(rank, world, port, q, uneven):
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from ood_gan_inversion_b200.inversion import LatentInverter
+    from ood_gan_inversion_b200.sharding import shard_bounds
+    dist.init_process_group('gloo', init_method=f'tcp://127.0.0.1:{port}', rank=rank, world_size=world)
+    synth, base, target = _toy_problem(8)
+    lo, hi = shard_bounds(8, world, rank)
+    if uneven and rank == 1:
+        hi -= 1
+    try:
+        inv = LatentInverter(synth, lr=0.05, shared_delta=True)
+        lat, losses = inv.run(target[lo:hi], base[lo:hi], 12)
+        res = ('ok', inv.delta[0].tolist(), losses)      # plain lists: the worker exits right after the put
+    except ValueError as e:
+        res = ('error', str(e), None)
+    dist.barrier()
+    dist.destroy_process_group()
+    q.put((rank,) + res)
+
+
+def _run_two_ranks(uneven):
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000 + (1 if uneven else 0)
+    procs = [ctx.Process(target=_inversion_worker, args=(r, 2, port, q, uneven)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    return res
+
+
+def test_shared_delta_inversion_allreduce_matches_single_process():
+    """the shared delta_latent is the one exchange step of the path -- two gloo ranks on half the images each
+    must walk the same Adam trajectory as one process on all of them, and stay identical to each other."""
+    from ood_gan_inversion_b200.inversion import LatentInverter
+    res = _run_two_ranks(uneven=False)
+    assert [r[1] for r in res] == ['ok', 'ok']
+    d0, d1 = torch.tensor(res[0][2]), torch.tensor(res[1][2])
+    assert torch.equal(d0, d1)
+    synth, base, target = _toy_problem(8)
+    inv = LatentInverter(synth, lr=0.05, shared_delta=True)
+    lat, losses = inv.run(target, base, 12)
+    assert torch.allclose(inv.delta[0], d0, atol=1e-6)
+    # the global loss is the mean of the two local ones (equal shard sizes)
+    assert losses[-1] == pytest.approx(0.5 * (res[0][3][-1] + res[1][3][-1]), rel=1e-5)
+
+
+def test_shared_delta_inversion_rejects_uneven_shards():
+    res = _run_two_ranks(uneven=True)
+    assert [r[1] for r in res] == ['error', 'error'] and 'same number of images' in res[0][2]
