@@ -326,6 +326,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // one 32-channel chunk; `cur` holds this chunk's seed values, the next chunk's are requested into `nxt` first so that
             // their latency spans the whole chunk (the two arrays swap roles from chunk to chunk: no register copies, which
             // would wait for the loads)
+            // (Measured and not kept: requesting the next chunk's TMEM load before processing the current one -- a second 32-register
+            // buffer in the plain kernels -- left the half-K convolutions at 384 / 406 us and made the C=128 ones 5-9 % slower.)
             auto do_chunk = [&](const int ch, float4 (&cur)[8], float4 (&nxt)[8]) {
                 uint32_t r[32];
                 if (SEED && seed && ch + 1 < BN / 32) {
