@@ -654,13 +654,13 @@ int conv3x3_tc(const ood_conv3x3_args &a, cudaStream_t st) {
         if (r != CUDA_SUCCESS) { set_error("conv3x3 tc: weight tensor map encode failed (%d)", (int)r); return OOD_ERR_CUDA; }
     }
     if (a.stats_out) {  // fused output statistics: wide tiles, one image per tile, single phase
-        OOD_REQUIRE(a.stats_ws && !a.acc_in && !a.out_ys && !a.out_f32 && a.out_y && groups == 1 && (a.transposed == 0 || a.transposed == 4) &&
+        OOD_REQUIRE(a.stats_ws && !a.acc_in && !a.out_ys && !a.out_f32 && a.out_y && groups == 1 && (a.transposed == 0 || a.transposed == 3 || a.transposed == 4) &&
                     p.NB == 1 && BK == 64 && (BN == 256 || BN == 128),
-                    "conv3x3 tc: stats_out needs the stride-1 / 1x1 form, bf16 out_y only, cin %% 64 == 0, cout %% 128 == 0 and h*w >= 128");
+                    "conv3x3 tc: stats_out needs the stride-1 / stride-2 pad-1 / 1x1 form, bf16 out_y only, cin %% 64 == 0, cout %% 128 == 0 and >= 128 output pixels");
         p.ep.stat_partial = a.stats_ws;
         const int rc = BN == 256 ? launch_tc<256, 64, false, true>(tmA, tmB, p, st) : launch_tc<128, 64, false, true>(tmA, tmB, p, st);
         if (rc != OOD_OK) return rc;
-        in_finalize_launch(a.stats_ws, a.stats_out, (int64_t)a.h * a.w, a.cout, p.ph[0].tiles_x * p.ph[0].tiles_y, a.stats_eps, a.batch, st);
+        in_finalize_launch(a.stats_ws, a.stats_out, (int64_t)g.OH * g.OW, a.cout, p.ph[0].tiles_x * p.ph[0].tiles_y, a.stats_eps, a.batch, st);
         return check_launch("conv3x3 tc stats", 1);
     }
     if (a.acc_in) {     // seeded accumulators: built for the wide tiles only (the AlignNet convolutions)
@@ -689,7 +689,7 @@ int conv3x3_tc(const ood_conv3x3_args &a, cudaStream_t st) {
 
 extern "C" int64_t ood_conv3x3_stats_workspace(int batch, int h, int w, int cin, int cout, int transposed) {
     using namespace ood;
-    if (batch <= 0 || h <= 0 || w <= 0 || cin <= 0 || cout <= 0 || cout % 128 != 0 || (transposed != 0 && transposed != 4)) return 0;
+    if (batch <= 0 || h <= 0 || w <= 0 || cin <= 0 || cout <= 0 || cout % 128 != 0 || (transposed != 0 && transposed != 3 && transposed != 4)) return 0;
     ood_conv3x3_args a{};
     a.batch = batch; a.h = h; a.w = w; a.cin = cin; a.cout = cout; a.transposed = transposed;
     float dummy = 0.f;

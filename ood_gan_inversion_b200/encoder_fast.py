@@ -10,11 +10,15 @@ three 1x1 stride-2 shortcut convolutions.
 
 Built from (and numerically checked against) `encoder.Encoder4Editing`; eval-mode BatchNorms are folded in fp32.
 """
+import os
+
 import torch
 from torch import nn
 from torch.nn import functional as F
 
 from . import kernels as K
+
+_SE_MEAN_FROM_CONV = os.environ.get('OOD_SE_MEAN_FROM_CONV', '0') != '0'       # A/B switch (profiles/microbench_r01b.txt)
 
 
 def _bn_affine(bn):
@@ -130,8 +134,14 @@ class FastEncoder:
         taps = {}
         for i, blk in enumerate(self.blocks):
             u, _ = K.conv3x3(t, blk.w1, blk.depth, prelu=blk.slope, tag='encoder_conv')
-            v, _ = K.conv3x3(u, blk.w2, blk.depth, transposed=3 if blk.stride == 2 else 0, bias=blk.b2, tag='encoder_conv')
-            gate = K.se_gate(K.in_stats(v), blk.se1, blk.se2)
+            form = 3 if blk.stride == 2 else 0
+            if _SE_MEAN_FROM_CONV and K.conv3x3_stats_ok(u, blk.depth, form):
+                # SEModule's global average pool (helpers.py:59-76) = the channel means the convolution's epilogue can emit
+                v, _, st = K.conv3x3(u, blk.w2, blk.depth, transposed=form, bias=blk.b2, tag='encoder_conv', stats_eps=1e-5)
+            else:
+                v, _ = K.conv3x3(u, blk.w2, blk.depth, transposed=form, bias=blk.b2, tag='encoder_conv')
+                st = K.in_stats(v)
+            gate = K.se_gate(st, blk.se1, blk.se2)
             if blk.shortcut is not None:
                 sc, ss = _nhwc(blk.shortcut(_nchw(cur.to(torch.bfloat16)))), 1
             else:

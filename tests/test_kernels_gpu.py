@@ -721,6 +721,10 @@ def test_conv3x3_fused_output_statistics(case):
     ref2 = K().in_stats(y2)
     torch.testing.assert_close(st2, ref2, rtol=1e-4, atol=1e-5)
     assert not K().conv3x3_stats_ok(nhwc(rnd(1, 64, 8, 8), dt), 128)        # 64 pixels: several images per tile
+    if form == 0 and h % 2 == 0 and w % 2 == 0 and (h // 2) * (w // 2) >= 128:   # the encoder's stride-2 pad-1 form
+        assert K().conv3x3_stats_ok(x, co, 3)
+        y3, _, st3 = K().conv3x3(x, pk, co, transposed=3, impl=0, bias=bias, stats_eps=1e-5)
+        torch.testing.assert_close(st3, K().in_stats(y3), rtol=1e-4, atol=1e-5)
 
 
 
