@@ -512,16 +512,24 @@ extern "C" int ood_warp_mix(const void *gen, const float *field, void *out, int 
     const int N = dtype == OOD_F32 ? 4 : 8;
     OOD_REQUIRE(channels % N == 0, "warp_mix: channels (%d) must be a multiple of %d", channels, N);
     const int cv = channels / N;
-    const int vpt = cv % 4 == 0 ? 4 : (cv % 2 == 0 ? 2 : 1);
+    // measurement knobs, read per call (three getenv per launch; the step's launches are replayed from a CUDA graph)
+    const char *e = getenv("OOD_WARP_ITER"), *e2 = getenv("OOD_WARP_SEG"), *e3 = getenv("OOD_WARP_VPT");
+    int vpt = cv % 4 == 0 ? 4 : (cv % 2 == 0 ? 2 : 1);
+    int WM_ITER = 4;
+    // small levels: keep at least ~two blocks per SM in flight (a 32 px level with 4 vectors x 4 rows per thread is 256 blocks
+    // of dependent gathers on 148 SMs)
+    {
+        const int64_t px = (int64_t)batch * h * w;
+        auto blocks = [&](int v, int it) { return px * (cv / v) / (256 * (int64_t)it); };
+        while (WM_ITER > 1 && blocks(vpt, WM_ITER) < kNumSMs * 4) WM_ITER >>= 1;
+        while (vpt > 1 && blocks(vpt, WM_ITER) < kNumSMs * 4) vpt >>= 1;
+    }
+    if (e) WM_ITER = std::max(1, atoi(e));
+    if (e3) { const int v = atoi(e3); if ((v == 1 || v == 2 || v == 4) && cv % v == 0) vpt = v; }
+    const int seg_max = e2 ? std::max(1, atoi(e2)) : 16;
     const int cvg = cv / vpt;
     OOD_REQUIRE(cvg <= 256, "warp_mix: too many channels (%d)", channels);
     const int lanes_px = 256 / cvg;
-    static int WM_ITER = -1, seg_max = 16;
-    if (WM_ITER < 0) {
-        const char *e = getenv("OOD_WARP_ITER"), *e2 = getenv("OOD_WARP_SEG");
-        WM_ITER = e ? atoi(e) : 4;
-        if (e2) seg_max = atoi(e2);
-    }
     int segw = 1;
     while (segw * 2 <= lanes_px && segw < seg_max) segw *= 2;      // columns in flight (power of two); the rest are rows
     const int rows_conc = std::max(1, lanes_px / segw);
