@@ -136,6 +136,80 @@ def cpu_reference(steps, warmup, images_per_step=1, state=None):
                 sample=f'{len(times)} step(s) x {images_per_step} image(s) of the 1024px pipeline, fp32, after {warmup} warm-up')
 
 
+def cpu_op_baselines(device=None):
+    """SURVEY section 8(d) "CPU baseline timing": the reference's native branch (`upfirdn2d_native`, native
+    `fused_leaky_relu`: oracle/ops.py restates src/ops/op/upfirdn2d.py:160-193 and fused_act.py:92-96) and BASELINE
+    configs[0] (Generator(256) forward, batch 1, fixed noise) on the host cores -- median of 3 calls after one warm-up,
+    one image per call (bounded sample: ~10 s of CPU work).  With `device`, the same op through this library on the
+    same shape at batch 4 (CUDA events, best of 10; every tensor is larger than L2 or the case is marked latency).
+    Reported baselines only."""
+    import torch
+    from oracle import ops as oops, stylegan as ostyle
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_grad_enabled(False)
+
+    def cpu_ms(fn):
+        fn()
+        ts = []
+        for _ in range(3):
+            t0 = time.perf_counter(); fn(); ts.append(time.perf_counter() - t0)
+        return 1e3 * sorted(ts)[1]
+
+    def gpu_ms(fn):
+        for _ in range(3):
+            fn()
+        best = 1e9
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record(); torch.cuda.synchronize(device)
+            best = min(best, e0.elapsed_time(e1))
+        return best
+
+    k = oops.fir_kernel([1, 3, 3, 1])
+    cases = [('upfirdn2d blur up1 pad(1,1)', (32, 1025, 1025), dict(up=1, down=1, pad=(1, 1)), 4.0),
+             ('upfirdn2d up2 pad(2,1)', (3, 512, 512), dict(up=2, down=1, pad=(2, 1)), 4.0),
+             ('upfirdn2d down2 pad(1,1)', (32, 1024, 1024), dict(up=1, down=2, pad=(1, 1)), 1.0)]
+    rows = []
+    for name, chw, kw, gain in cases:
+        x = torch.randn(1, *chw)
+        y = oops.upfirdn2d(x, k * gain, **kw)
+        byt = (x.numel() + y.numel()) * 4                                   # section 8(d): in + out bytes per image
+        ms = cpu_ms(lambda: oops.upfirdn2d(x, k * gain, **kw))
+        row = dict(op=name, shape=[1, *chw], cpu_ms=ms, cpu_gbs=byt / ms / 1e6)
+        if device is not None:
+            from ood_gan_inversion_b200 import op as pop
+            xg, kg = torch.randn(4, *chw, device=device), (k * gain).to(device)
+            g = gpu_ms(lambda: pop.upfirdn2d(xg, kg, **kw))
+            row.update(gpu_shape=[4, *chw], gpu_us=1e3 * g, gpu_gbs=4 * byt / g / 1e6)
+            del xg
+        rows.append(row)
+    x, bias = torch.randn(1, 32, 1024, 1024), torch.randn(32)
+    ms = cpu_ms(lambda: oops.fused_leaky_relu(x, bias))
+    row = dict(op='fused_leaky_relu', shape=[1, 32, 1024, 1024], cpu_ms=ms, cpu_gbs=2 * x.numel() * 4 / ms / 1e6)
+    if device is not None:
+        from ood_gan_inversion_b200 import op as pop
+        xg, bg = torch.randn(4, 32, 1024, 1024, device=device), bias.to(device)
+        g = gpu_ms(lambda: pop.fused_leaky_relu(xg, bg))
+        row.update(gpu_shape=[4, 32, 1024, 1024], gpu_us=1e3 * g, gpu_gbs=4 * 2 * x.numel() * 4 / g / 1e6)
+        del xg
+    rows.append(row)
+    # BASELINE configs[0]: StyleGAN2 256px synthesis forward, batch 1, W+ latents (seed 1), registered noise buffers
+    sd = ostyle.synthetic_generator_state(256, seed=0)
+    lat = torch.randn(1, 14, 512, generator=torch.Generator().manual_seed(1))
+    ms = cpu_ms(lambda: ostyle.generator_forward(sd, lat, 256, randomize_noise=False))
+    row = dict(op='Generator(256) forward, batch 1 (BASELINE configs[0])', shape=[1, 14, 512], cpu_ms=ms, cpu_images_per_s=1e3 / ms)
+    if device is not None:
+        from ood_gan_inversion_b200 import stylegan as sgm
+        gen = sgm.Generator(256, 512, 8).to(device)
+        gen.load_state_dict(sd, strict=True)
+        gen.eval()
+        lg = lat.to(device)
+        g = gpu_ms(lambda: gen(lg, input_is_tensor=True, input_is_latent=True, randomize_noise=False))
+        row.update(gpu_us=1e3 * g, gpu_images_per_s=1e3 / g, gpu_note='eager launches, batch 1: launch-latency bound')
+    rows.append(row)
+    return dict(cores=torch.get_num_threads(), kind='port', ops=rows)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -164,6 +238,7 @@ def main():
                                 'fused_act branch, oracle port) on the host cores, 1 image per step'),
                     cpu_baseline=dict(value=r['value'], unit=UNIT, cores=r['cores'], kind='port', sample=r['sample']),
                     e2e=dict(value=r['value'], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+        line['cpu_baseline']['ops'] = cpu_op_baselines()['ops']
         print(json.dumps(line))
         return 0
 
@@ -395,6 +470,10 @@ def main():
         sd = {k: v.detach().float().cpu() for k, v in net.state_dict().items()}
         r = cpu_reference(2, 1, 1, state=sd)
         line['cpu_baseline'] = dict(value=r['value'], unit=UNIT, cores=r['cores'], kind='port', sample=r['sample'])
+        try:
+            line['cpu_baseline']['ops'] = cpu_op_baselines(dev)['ops']
+        except Exception as exc:                                 # a reported baseline must not cost the bench line
+            line['cpu_baseline']['ops_error'] = f'{type(exc).__name__}: {exc}'[:300]
     sys.stdout.flush()
     os.write(json_fd, (json.dumps(line) + '\n').encode())
     if world > 1:
