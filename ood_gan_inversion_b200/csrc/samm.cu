@@ -307,6 +307,7 @@ __global__ void __launch_bounds__(256, 4) warp_mix_kernel(const T *__restrict__ 
 struct MaskParams {
     const float *f[4];
     int r[4];
+    float scale[4];     // ATen's area_pixel_compute_scale (align_corners=False): float(r) / float(S)
     int n;
 };
 
@@ -320,83 +321,80 @@ __device__ __forceinline__ float bilinear_up(const float *__restrict__ a, int r,
            ly1 * (lx0 * __ldg(a + (int64_t)y1 * r + x0) + lx1 * __ldg(a + (int64_t)y1 * r + x1));
 }
 
-// Four consecutive pixels of one row per thread.  The six streaming 16-byte loads (x, gen: 3 planes each) are issued
-// first so that they are in flight while the masks are composed; when the image is at least 4x a mask level (always, in
-// the reference configuration) the four pixels touch at most three mask columns and share the two mask rows, so a level
-// costs 6 loads instead of 16.  Arithmetic per tap is unchanged (ATen's upsample_bilinear2d order).
+// Four consecutive pixels of one row per thread, 2-D grid (no integer division per thread).  The six streaming 16-byte
+// loads (x, gen: 3 planes each) are issued first so that they are in flight while the masks are composed.  When the image
+// is at least 4x a mask level (always, in the reference configuration) the four pixels touch at most three mask columns and
+// share the two mask rows, so a level costs 6 loads instead of 16.  The first form of this path was issue-bound (ncu: issue
+// active 77 %, math-pipe throttle, DRAM at 0.66 of peak): ~15 int<->float conversions (quarter-rate pipe) and a float
+// division per level per thread.  Now: the host passes the ATen scale (float(r) / float(S)), one F2I + I2F per axis per
+// level (the other pixels' column offset is the exact float difference to the first column), clamped column loads make the
+// right tap `column + 1` without a special case, and the three columns are interpolated vertically first
+// (14 instead of 24 multiply-adds per level; differs from ATen's horizontal-first order by rounding only).
 template <bool FAST>
 __global__ void __launch_bounds__(256) mask_blend_kernel(const MaskParams mp, const float *__restrict__ xin,
                                                           const float *__restrict__ gen, float *__restrict__ out,
                                                           float *__restrict__ alpha_out, int S) {
-    const int b = blockIdx.y;
+    const int b = blockIdx.z;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (x >= S || y >= S) return;
     const int64_t P = (int64_t)S * S;
-    const int nq = (int)(P / 4);    // S % 4 == 0; 32-bit pixel arithmetic (S <= 16384 is checked by the host)
-    const int qrow = S / 4;
-    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += gridDim.x * blockDim.x) {
-        const int y = q / qrow, x = (q - y * qrow) * 4;
-        const int64_t pix = (int64_t)q * 4;
-        float4 xv[3], gv[3];
+    const int64_t pix = (int64_t)y * S + x;
+    float4 xv[3], gv[3];
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            const int64_t o = ((int64_t)b * 3 + k) * P + pix;
-            xv[k] = __ldg(reinterpret_cast<const float4 *>(xin + o));
-            gv[k] = __ldg(reinterpret_cast<const float4 *>(gen + o));
-        }
-        float A[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int k = 0; k < 3; ++k) {
+        const int64_t o = ((int64_t)b * 3 + k) * P + pix;
+        xv[k] = __ldg(reinterpret_cast<const float4 *>(xin + o));
+        gv[k] = __ldg(reinterpret_cast<const float4 *>(gen + o));
+    }
+    float A[4] = {0.f, 0.f, 0.f, 0.f};
+    const float xf05 = (float)x + 0.5f, yf05 = (float)y + 0.5f;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if (k >= mp.n) break;
-            const int r = mp.r[k];
-            const float *a = mp.f[k] + ((int64_t)b * 3 + 2) * r * r;
-            float u[4];
-            if (FAST) {
-                const float scale = (float)r / (float)S;
-                const float sy = fmaxf(((float)y + 0.5f) * scale - 0.5f, 0.f);
-                const int y0 = (int)sy, y1 = y0 + (y0 < r - 1);
-                const float ly1 = sy - y0, ly0 = 1.f - ly1;
-                float sx[4];
-                int x0[4];
+    for (int k = 0; k < 4; ++k) {
+        if (k >= mp.n) break;
+        const int r = mp.r[k];
+        const float scale = mp.scale[k];
+        const float *a = mp.f[k] + ((int64_t)b * 3 + 2) * r * r;
+        float u[4];
+        if (FAST) {
+            const float sy = fmaxf(yf05 * scale - 0.5f, 0.f);
+            const int y0 = (int)sy, y1 = min(y0 + 1, r - 1);
+            const float ly1 = sy - (float)y0, ly0 = 1.f - ly1;
+            const float sx0 = fmaxf(xf05 * scale - 0.5f, 0.f);
+            const int base = (int)sx0;
+            const float fbase = (float)base;
+            const int c1 = min(base + 1, r - 1), c2 = min(base + 2, r - 1);
+            const float *r0 = a + y0 * r, *r1 = a + y1 * r;
+            const float t0 = __ldg(r0 + base), t1 = __ldg(r0 + c1), t2 = __ldg(r0 + c2);
+            const float b0 = __ldg(r1 + base), b1 = __ldg(r1 + c1), b2 = __ldg(r1 + c2);
+            const float v0 = ly0 * t0 + ly1 * b0, v1 = ly0 * t1 + ly1 * b1, v2 = ly0 * t2 + ly1 * b2;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    sx[j] = fmaxf(((float)(x + j) + 0.5f) * scale - 0.5f, 0.f);
-                    x0[j] = (int)sx[j];
-                }
-                const int base = x0[0];
-                float top[3], bot[3];
-#pragma unroll
-                for (int i = 0; i < 3; ++i) {
-                    const int cx = min(base + i, r - 1);
-                    top[i] = __ldg(a + (int64_t)y0 * r + cx);
-                    bot[i] = __ldg(a + (int64_t)y1 * r + cx);
-                }
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int i0 = x0[j] - base, i1 = i0 + (x0[j] < r - 1);      // 0..1, 0..2
-                    const float lx1 = sx[j] - x0[j], lx0 = 1.f - lx1;
-                    const float t0 = i0 ? top[1] : top[0], t1 = i1 == 0 ? top[0] : (i1 == 1 ? top[1] : top[2]);
-                    const float b0 = i0 ? bot[1] : bot[0], b1 = i1 == 0 ? bot[0] : (i1 == 1 ? bot[1] : bot[2]);
-                    u[j] = ly0 * (lx0 * t0 + lx1 * t1) + ly1 * (lx0 * b0 + lx1 * b1);
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) u[j] = bilinear_up(a, r, (float)r / (float)S, y, x + j);
+            for (int j = 0; j < 4; ++j) {
+                const float sxj = j == 0 ? sx0 : fmaxf((xf05 + (float)j) * scale - 0.5f, 0.f);
+                const float f = sxj - fbase;                       // exact; in [0, 2): the pixel's column is base or base + 1
+                const bool ge = f >= 1.f;
+                const float lx1 = ge ? f - 1.f : f, lx0 = 1.f - lx1;
+                u[j] = lx0 * (ge ? v1 : v0) + lx1 * (ge ? v2 : v1);
             }
+        } else {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) A[j] = (k == 0) ? u[j] : (u[j] * A[j] + A[j] * (1.f - A[j]));
+            for (int j = 0; j < 4; ++j) u[j] = bilinear_up(a, r, scale, y, x + j);
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) A[j] = fminf(fmaxf(A[j], 0.f), 1.f);
-        if (alpha_out) *reinterpret_cast<float4 *>(alpha_out + (int64_t)b * P + pix) = make_float4(A[0], A[1], A[2], A[3]);
+        for (int j = 0; j < 4; ++j) A[j] = (k == 0) ? u[j] : (u[j] * A[j] + A[j] * (1.f - A[j]));
+    }
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            const int64_t o = ((int64_t)b * 3 + k) * P + pix;
-            float4 r;
-            r.x = A[0] * xv[k].x + gv[k].x * (1.f - A[0]);
-            r.y = A[1] * xv[k].y + gv[k].y * (1.f - A[1]);
-            r.z = A[2] * xv[k].z + gv[k].z * (1.f - A[2]);
-            r.w = A[3] * xv[k].w + gv[k].w * (1.f - A[3]);
-            *reinterpret_cast<float4 *>(out + o) = r;
-        }
+    for (int j = 0; j < 4; ++j) A[j] = fminf(fmaxf(A[j], 0.f), 1.f);
+    if (alpha_out) *reinterpret_cast<float4 *>(alpha_out + (int64_t)b * P + pix) = make_float4(A[0], A[1], A[2], A[3]);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const int64_t o = ((int64_t)b * 3 + k) * P + pix;
+        float4 r;
+        r.x = A[0] * xv[k].x + gv[k].x * (1.f - A[0]);
+        r.y = A[1] * xv[k].y + gv[k].y * (1.f - A[1]);
+        r.z = A[2] * xv[k].z + gv[k].z * (1.f - A[2]);
+        r.w = A[3] * xv[k].w + gv[k].w * (1.f - A[3]);
+        *reinterpret_cast<float4 *>(out + o) = r;
     }
 }
 
@@ -555,12 +553,15 @@ extern "C" int ood_mask_blend(const float *const *fields_host, const int *field_
         OOD_REQUIRE(fields_host[i] && field_sizes_host[i] > 0, "mask_blend: bad field %d", i);
         mp.f[i] = fields_host[i];
         mp.r[i] = field_sizes_host[i];
+        mp.scale[i] = (float)field_sizes_host[i] / (float)size;
     }
-    const int64_t nq = (int64_t)size * size / 4;
-    dim3 grid((unsigned)std::min<int64_t>((nq + 255) / 256, kNumSMs * 16), batch);
+    int tx = 1;
+    while (tx < 256 && tx * 4 < size) tx *= 2;            // threads along a row (4 pixels each); the rest of the block are rows
+    const dim3 block(tx, 256 / tx);
+    const dim3 grid(ceil_div(size / 4, tx), ceil_div(size, (int)block.y), batch);
     bool fast = true;                    // every level at most a quarter of the image: 4 pixels span <= 3 mask columns
     for (int i = 0; i < n_fields; ++i) fast = fast && (int64_t)mp.r[i] * 4 <= size;
-    if (fast) mask_blend_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(mp, x, gen, out, alpha_out, size);
-    else mask_blend_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(mp, x, gen, out, alpha_out, size);
+    if (fast) mask_blend_kernel<true><<<grid, block, 0, (cudaStream_t)stream>>>(mp, x, gen, out, alpha_out, size);
+    else mask_blend_kernel<false><<<grid, block, 0, (cudaStream_t)stream>>>(mp, x, gen, out, alpha_out, size);
     return check_launch("mask_blend");
 }
