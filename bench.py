@@ -220,6 +220,8 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--ncu', action='store_true', help='run warm-up, then ONE step between cudaProfilerStart/Stop and exit '
                     '(for `ncu --profile-from-start off`; never a bench value)')
+    ap.add_argument('--u8-io', action='store_true', help='also time the byte-format serving loop (imgio.ByteServing: uint8 BGR frames '
+                    'across PCIe both ways, 3 instead of 12 bytes per pixel) and report it as "e2e_u8"; N=1 only')
     ap.add_argument('--no-graph', action='store_true', help='time eager launches instead of a CUDA-graph replay of the step')
     ap.add_argument('--profile', action='store_true', help='print a torch.profiler kernel table for one step (not a bench value)')
     args = ap.parse_args()
@@ -418,6 +420,35 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_e2e = float(t.item())
 
+    # ---------------- optional timed region 3: the same serving loop on the reference script's byte formats -----------------
+    e2e_u8 = None
+    if args.u8_io and world == 1 and pipe is not None:
+        try:
+            from ood_gan_inversion_b200 import imgio
+            from ood_gan_inversion_b200.graphs import PipelinedForward
+            frames_dev = imgio.tensor2img(x_dev, min_max=(-1, 1))                      # uint8 BGR [B,1024,1024,3]
+            frames_host = frames_dev.cpu().pin_memory()
+            out8_host = torch.empty_like(frames_host).pin_memory()
+            torch.manual_seed(1000 + rank)
+            pipe8 = PipelinedForward(imgio.ByteServing(net), frames_dev, depth=2, warmup=1)
+            for _ in range(2):
+                pipe8.submit(frames_host, out8_host)
+            pipe8.synchronize()
+            barrier()
+            e0.record()
+            for _ in range(args.steps):
+                pipe8.submit(frames_host, out8_host)
+            pipe8.synchronize()
+            e1.record()
+            barrier()
+            ms8 = e0.elapsed_time(e1)
+            e2e_u8 = dict(value=args.steps * B / (ms8 * 1e-3), unit=UNIT, ms_per_step=ms8 / args.steps,
+                          h2d_bytes_per_step=frames_host.numel(), d2h_bytes_per_step=out8_host.numel(),
+                          note='uint8 BGR frames in and out (run_ood_faceGAN_inversion.py:158-174 formats), converters inside the captured step')
+        except Exception as exc:
+            e2e_u8 = dict(error=f'{type(exc).__name__}: {exc}'[:300])
+            torch.cuda.synchronize()
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -466,6 +497,8 @@ def main():
                                   traffic_note='DRAM bytes of the 1024 px blur_rows_kernel launch (2.15 GB algorithmic), profiles/ncu_r01_blurrows_raw.csv',
                                   share_of_step=blur['ms'] / prof_steps / max(step_ms, 1e-9)),
                 kernels=kern)
+    if e2e_u8 is not None:
+        line['e2e_u8'] = e2e_u8
     if world == 1 and not args.no_cpu_baseline:
         sd = {k: v.detach().float().cpu() for k, v in net.state_dict().items()}
         r = cpu_reference(2, 1, 1, state=sd)

@@ -223,6 +223,18 @@ int ood_alignnet_tail(const float *res, const float *shortcut, const float *prel
 int ood_bicubic_up_add(const void *x, const void *y, void *out, int batch, int h, int w, int H, int W, int channels,
                        int dtype, void *stream);
 
+/* ---- section 8f rank 4 (host I/O either side of the path): the byte formats of the reference's inference script, on the
+ *      device, so that a batch crosses PCIe as 3 bytes per pixel.  Bit-exact against the reference's arithmetic.
+ *      ood_img2tensor_u8: replaces `cv2.imread(f) / 255.0 -> img2tensor(bgr2rgb) -> (t - 0.5) * 2`
+ *          (run_ood_faceGAN_inversion.py:158-159, BasicSR/basicsr/utils/img_util.py:10-36):
+ *          in uint8 [B][H][W][3] (interleaved, cv2 layout) -> out fp32 planes [B][3][H][W],
+ *          out = (float32(double(v) / 255.0) - sub) * mul, channel order reversed if swap_rb.
+ *      ood_tensor2img_u8: replaces `tensor2img(t, rgb2bgr, np.uint8, min_max)` (img_util.py:38-94,
+ *          run_ood_faceGAN_inversion.py:64-72): in fp32 planes [B][3][H][W] -> out uint8 [B][H][W][3],
+ *          out = uint8(rint(((clamp(x, lo, hi) - lo) / (hi - lo)) * 255.0f)) (round half to even), reversed if swap_rb. */
+int ood_img2tensor_u8(const uint8_t *in, float *out, int batch, int h, int w, int swap_rb, float sub, float mul, void *stream);
+int ood_tensor2img_u8(const float *in, uint8_t *out, int batch, int h, int w, int swap_rb, float lo, float hi, void *stream);
+
 /* ---- a11 (AlignNet head, SAMM/helpers.py:85-109 via bottleneck_IR e4e/encoders/helpers.py:426-448): a 3x3 convolution
  *      2C -> 3 reads its 2C-channel input nine times for three outputs.  Instead ood_conv3x3(transposed = 4) projects every
  *      pixel once onto the 27 (tap, colour) weights, proj [B,H,W,Cp] fp32 with channel 3*t + k (Cp >= 27), and

@@ -526,6 +526,32 @@ def bicubic_up_add(x, y):
     return out
 
 
+def img2tensor_u8(frames, swap_rb=True, sub=0.5, mul=2.0):
+    """frames uint8 [B,H,W,3] (cv2 layout) -> fp32 [B,3,H,W] = (float32(v / 255.0) - sub) * mul, channels reversed if swap_rb."""
+    _cuda(frames)
+    if frames.dtype != torch.uint8 or frames.dim() != 4 or frames.shape[-1] != 3 or not frames.is_contiguous():
+        raise RuntimeError('img2tensor_u8: expected a contiguous uint8 [B,H,W,3] tensor')
+    b, h, w, _ = frames.shape
+    out = torch.empty(b, 3, h, w, device=frames.device, dtype=torch.float32)
+    with _timed('img2tensor_u8', b * h * w * 15):
+        check(_lib.lib().ood_img2tensor_u8(_ptr(frames), _ptr(out), b, h, w, int(bool(swap_rb)), float(sub), float(mul), _stream()),
+              'img2tensor_u8')
+    return out
+
+
+def tensor2img_u8(t, swap_rb=True, lo=0.0, hi=1.0):
+    """t fp32 [B,3,H,W] -> uint8 [B,H,W,3] = rint(((clamp(t, lo, hi) - lo) / (hi - lo)) * 255), channels reversed if swap_rb."""
+    _cuda(t)
+    if t.dtype != torch.float32 or t.dim() != 4 or t.shape[1] != 3 or not t.is_contiguous():
+        raise RuntimeError('tensor2img_u8: expected a contiguous fp32 [B,3,H,W] tensor')
+    b, _, h, w = t.shape
+    out = torch.empty(b, h, w, 3, device=t.device, dtype=torch.uint8)
+    with _timed('tensor2img_u8', b * h * w * 15):
+        check(_lib.lib().ood_tensor2img_u8(_ptr(t), _ptr(out), b, h, w, int(bool(swap_rb)), float(lo), float(hi), _stream()),
+              'tensor2img_u8')
+    return out
+
+
 def pack_conv1x1_weight(w, dtype, ci_major):
     """w [Co,Ci] (or [Co,Ci,1,1]) -> the one-tap pack of ood_conv3x3(transposed=4): [1][Co][Ci] (tcgen05) / [1][Ci][Co] (simt)."""
     w = w.reshape(w.shape[0], -1).float()

@@ -136,6 +136,29 @@ def golden_samm():
                          enc2=enc2, gen2=gen2, aligned2=a2, field2=f2))
 
 
+def golden_imgio():
+    """The byte formats either side of the path: the reference's own functions (basicsr.utils.img_util, loaded from its file:
+    the package __init__ pulls in optional dependencies this container lacks) on seeded frames / tensors, incl. every byte
+    value, out-of-range values and exact rounding ties."""
+    import importlib.util
+    import numpy as np
+    spec = importlib.util.spec_from_file_location('ref_img_util', '/root/reference/BasicSR/basicsr/utils/img_util.py')
+    iu = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(iu)
+    rng = np.random.default_rng(5)
+    frames = [np.arange(256, dtype=np.uint8).repeat(3).reshape(16, 16, 3)[..., ::-1].copy() % np.uint8(251),
+              rng.integers(0, 256, (8, 12, 3), dtype=np.uint8), rng.integers(0, 256, (5, 7, 3), dtype=np.uint8)]
+    to_t = [((torch.stack(iu.img2tensor([f / 255.0], bgr2rgb=True), dim=0) - 0.5) * 2)[0] for f in frames]   # run_ood_faceGAN_inversion.py:158-159
+    g = torch.Generator().manual_seed(6)
+    ties = (torch.arange(0, 3 * 8 * 12, dtype=torch.float32).reshape(3, 8, 12) % 256 + 0.5) / 255.0 * 2 - 1  # k + 0.5 before rounding
+    tensors = [torch.randn(3, 8, 12, generator=g) * 0.8, torch.randn(3, 5, 7, generator=g) * 2.0, ties]
+    # tensor2img clamps a CPU fp32 input IN PLACE (img_util.py:66: .float().detach().cpu() of such a tensor is the tensor itself): pass copies
+    to_f = [torch.from_numpy(iu.tensor2img(t.clone(), rgb2bgr=True, min_max=(-1, 1))) for t in tensors]     # :68
+    to_f01 = [torch.from_numpy(iu.tensor2img(t.clone(), rgb2bgr=False, min_max=(0, 1))) for t in tensors]
+    save('imgio.pt', dict(frames=[torch.from_numpy(f) for f in frames], frame_tensors=to_t, tensors=tensors,
+                          tensor_frames=to_f, tensor_frames_rgb01=to_f01))
+
+
 def golden_ood():
     from src.archs.OOD_faceGAN_e4e_arch import ood_faceGAN_e4e
     sd = synthetic_ood_state(1024, seed=0)
@@ -157,6 +180,6 @@ def golden_ood():
 
 
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['ops', 'modconv', 'generator', 'samm', 'ood']
+    which = sys.argv[1:] or ['ops', 'modconv', 'generator', 'samm', 'imgio', 'ood']
     for w in which:
         globals()[f'golden_{w}']()

@@ -439,6 +439,76 @@ def test_mask_blend(size):
     torch.testing.assert_close(same.cpu(), x, rtol=1e-6, atol=1e-6)
 
 
+# ----------------------------------------------------------------------------------------------- image byte formats
+def _frames(b, h, w, seed):
+    return torch.randint(0, 256, (b, h, w, 3), generator=g(seed), dtype=torch.uint8)
+
+
+def test_imgio_golden_cases(golden):
+    """ood_img2tensor_u8 / ood_tensor2img_u8 against the outputs of the reference's own img2tensor / tensor2img: bit-exact."""
+    from ood_gan_inversion_b200 import imgio
+    G = golden('imgio.pt')
+    for f, t in zip(G['frames'], G['frame_tensors']):
+        assert torch.equal(imgio.img2tensor(f.to(DEV))[0].cpu(), t)
+    for t, f, f01 in zip(G['tensors'], G['tensor_frames'], G['tensor_frames_rgb01']):
+        assert torch.equal(imgio.tensor2img(t.to(DEV), min_max=(-1, 1))[0].cpu(), f)
+        assert torch.equal(imgio.tensor2img(t.to(DEV), rgb2bgr=False, min_max=(0, 1))[0].cpu(), f01)
+
+
+@pytest.mark.parametrize('shape', [(2, 16, 24), (3, 5, 7), (1, 33, 31), (2, 64, 64)])     # vector path and the odd-size scalar path
+def test_imgio_vs_oracle(shape):
+    from oracle import imgio as oimg
+    b, h, w = shape
+    fr = _frames(b, h, w, seed=h)
+    out = K().img2tensor_u8(fr.to(DEV))
+    ref = torch.stack([oimg.frame_to_tensor(f.numpy()) for f in fr])
+    assert torch.equal(out.cpu(), ref)
+    keep = K().img2tensor_u8(fr.to(DEV), swap_rb=False)
+    assert torch.equal(keep.cpu(), ref.flip(1))
+    t = rnd(b, 3, h, w, seed=w) * 1.5
+    q = K().tensor2img_u8(t.to(DEV), lo=-1.0, hi=1.0)
+    refq = torch.stack([torch.from_numpy(oimg.tensor_to_frame(x)) for x in t])
+    assert torch.equal(q.cpu(), refq)
+    # an unaligned view forces the scalar path: same bytes
+    big = torch.zeros(b * h * w * 3 + 1, dtype=torch.uint8, device=DEV)
+    big[1:] = fr.to(DEV).reshape(-1)
+    assert torch.equal(K().img2tensor_u8(big[1:].view(b, h, w, 3)).cpu(), ref)
+
+
+def test_imgio_round_trip_full_size():
+    """Size-independent property at the bench size: frame -> tensor -> frame is the identity for every byte value."""
+    fr = _frames(2, 1024, 1024, seed=3).to(DEV)
+    fr[0, 0, :256, 0] = torch.arange(256, dtype=torch.uint8, device=DEV)
+    back = K().tensor2img_u8(K().img2tensor_u8(fr), lo=-1.0, hi=1.0)
+    assert torch.equal(back, fr)
+
+
+def test_imgio_byte_serving_loop():
+    """imgio.ByteServing under graphs.PipelinedForward (uint8 frames across PCIe both ways): captured, replayed, bit-exact."""
+    from oracle import imgio as oimg
+    from ood_gan_inversion_b200 import imgio
+    from ood_gan_inversion_b200.graphs import PipelinedForward
+    net = imgio.ByteServing(lambda x: (x * 0.75 + 0.1, None))
+    reqs = [_frames(2, 32, 48, seed=s).pin_memory() for s in range(3)]
+    outs = [torch.empty(2, 32, 48, 3, dtype=torch.uint8).pin_memory() for _ in reqs]
+    pipe = PipelinedForward(net, reqs[0].to(DEV), depth=2)
+    for x, o in zip(reqs, outs):
+        pipe.submit(x, o)
+    pipe.synchronize()
+    for x, o in zip(reqs, outs):
+        ref = torch.stack([torch.from_numpy(oimg.tensor_to_frame(oimg.frame_to_tensor(f.numpy()) * 0.75 + 0.1)) for f in x])
+        assert torch.equal(o, ref)
+
+
+def test_imgio_errors_are_loud():
+    with pytest.raises(RuntimeError):
+        K().img2tensor_u8(torch.zeros(1, 4, 4, 3, dtype=torch.uint8))                       # CPU tensor
+    with pytest.raises(RuntimeError):
+        K().img2tensor_u8(torch.zeros(1, 4, 4, 3, device=DEV))                              # not uint8
+    with pytest.raises(RuntimeError):
+        K().tensor2img_u8(torch.zeros(1, 3, 4, 4, device=DEV), lo=1.0, hi=1.0)              # empty range
+
+
 def test_errors_are_loud():
     with pytest.raises(RuntimeError):
         K().upfirdn2d_nchw(torch.zeros(1, 1, 4, 4), torch.ones(2, 2), 1, 1, 1, 1, 0, 0, 0, 0)      # CPU tensor

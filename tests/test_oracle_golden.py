@@ -135,3 +135,17 @@ def test_ood_full_pipeline_golden(golden):
     torch.testing.assert_close(aligns[1024][:, :1, ::16, ::16], G['aligns'][1024], rtol=1e-3, atol=2e-4)
     assert (out[:, :, ::16, ::16] - G['out']).abs().max() < 1e-3      # north-star fp32 tolerance
     assert abs(float(out.double().sum()) - G['out_sum']) < 1e-4 * G['out_abssum']
+
+
+def test_imgio_golden(golden):
+    """Byte formats either side of the path (oracle/imgio.py) against the reference's own img2tensor / tensor2img: bit-exact."""
+    from oracle import imgio
+    G = golden('imgio.pt')
+    for f, t in zip(G['frames'], G['frame_tensors']):
+        assert torch.equal(imgio.frame_to_tensor(f.numpy()), t)
+    for t, f, f01 in zip(G['tensors'], G['tensor_frames'], G['tensor_frames_rgb01']):
+        assert torch.equal(torch.from_numpy(imgio.tensor_to_frame(t)), f)
+        assert torch.equal(torch.from_numpy(imgio.tensor_to_frame(t, rgb2bgr=False, min_max=(0, 1))), f01)
+    # every byte value survives frame -> tensor -> frame
+    allv = torch.arange(256, dtype=torch.uint8).repeat_interleave(3).reshape(16, 16, 3).numpy()
+    assert (imgio.tensor_to_frame(imgio.frame_to_tensor(allv)) == allv).all()
