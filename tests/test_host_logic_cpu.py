@@ -181,3 +181,40 @@ def test_shared_delta_inversion_allreduce_matches_single_process():
 def test_shared_delta_inversion_rejects_uneven_shards():
     res = _run_two_ranks(uneven=True)
     assert [r[1] for r in res] == ['error', 'error'] and 'same number of images' in res[0][2]
+
+
+def _run_bench(*args, env=None):
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    e = dict(os.environ)
+    e.update(env or {})
+    return subprocess.run([sys.executable, os.path.join(root, 'bench.py'), *args], capture_output=True, text=True, env=e, timeout=600)
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference`: one JSON line on rank 0 with the contract's keys (CPU arithmetic of the path, bounded sample,
+    per-op baselines of SURVEY 8(d)); every other rank exits 0 without work or output."""
+    import json
+    r = _run_bench('--impl', 'reference', '--steps', '1', '--warmup', '0')
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith('{')]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d['impl'] == 'reference' and d['metric'] == '1024px inversion images/sec' and d['unit'] == 'images/s'
+    assert d['higher_is_better'] is True and d['vs_baseline'] is None and d['gpu_launches'] == 0
+    assert d['value'] > 0 and d['e2e'] == dict(value=d['value'], unit='images/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0)
+    cb = d['cpu_baseline']
+    assert cb['kind'] == 'port' and cb['cores'] >= 1 and cb['value'] == d['value'] and 'image' in cb['sample']
+    ops = {o['op']: o for o in cb['ops']}
+    assert len(ops) == 5 and all(o['cpu_ms'] > 0 for o in ops.values())
+    assert any('Generator(256)' in k for k in ops) and 'fused_leaky_relu' in ops
+    other = _run_bench('--impl', 'reference', '--gpus', '2', '--steps', '1', '--warmup', '0', env=dict(RANK='1', LOCAL_RANK='1', WORLD_SIZE='2'))
+    assert other.returncode == 0 and other.stdout.strip() == ''
+
+
+def test_bench_product_arm_has_no_cpu_fallback():
+    if torch.cuda.is_available():
+        pytest.skip('CPU-only check')
+    r = _run_bench('--steps', '1', '--warmup', '0', '--no-cpu-baseline')
+    assert r.returncode != 0 and 'no CPU fallback' in r.stderr and '{' not in r.stdout
