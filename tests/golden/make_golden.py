@@ -121,6 +121,40 @@ def golden_generator():
     save('generator.pt', res)
 
 
+def golden_inversion():
+    """BASELINE config 4 protocol at small size through the UNMODIFIED reference generator and torch.autograd (which runs the
+    reference's own dgrad + grouped wgrad through the materialised per-sample weights): 8 Adam steps on W+ (lr 0.01, MSE), frozen
+    weights, registered noise buffers.  Pins the oracle's backward (tests/test_oracle_golden.py::test_inversion_golden), which
+    is what the GPU gradient tests compare the hand-written backward with."""
+    size, batch, steps = 32, 2, 8
+    sd = synthetic_generator_state(size, seed=3)
+    gnet = rm.Generator(size, 512, 8)
+    gnet.load_state_dict(sd, strict=True)
+    gnet.eval()
+    for p in gnet.parameters():
+        p.requires_grad_(False)
+    lat0 = 0.5 * torch.randn(batch, gnet.n_latent, 512, generator=torch.Generator().manual_seed(4))
+    with torch.no_grad():
+        target, _ = gnet(torch.randn(batch, gnet.n_latent, 512, generator=torch.Generator().manual_seed(5)),
+                         input_is_tensor=True, input_is_latent=True, randomize_noise=False)
+    with torch.enable_grad():
+        lat = lat0.clone().requires_grad_(True)
+        opt = torch.optim.Adam([lat], lr=0.01)
+        losses, grad0 = [], None
+        for _ in range(steps):
+            opt.zero_grad()
+            img, _ = gnet(lat, input_is_tensor=True, input_is_latent=True, randomize_noise=False)
+            loss = torch.nn.functional.mse_loss(img, target)
+            loss.backward()
+            if grad0 is None:
+                grad0 = lat.grad.detach().clone()
+            opt.step()
+            losses.append(float(loss.detach()))
+    print('inversion losses', losses)
+    save('inversion.pt', dict(size=size, batch=batch, steps=steps, n_latent=gnet.n_latent, losses=losses, grad0=grad0,
+                              final=lat.detach().clone(), target_sum=float(target.double().sum())))
+
+
 def golden_samm():
     torch.manual_seed(3)
     blk = StyledscaleNshfitBlock(8, 8, 512, scale=0.08, btn=None, cycle_align=2, diff_fAndg=True)
@@ -180,6 +214,6 @@ def golden_ood():
 
 
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['ops', 'modconv', 'generator', 'samm', 'imgio', 'ood']
+    which = sys.argv[1:] or ['ops', 'modconv', 'generator', 'inversion', 'samm', 'imgio', 'ood']
     for w in which:
         globals()[f'golden_{w}']()

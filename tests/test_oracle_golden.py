@@ -149,3 +149,31 @@ def test_imgio_golden(golden):
     # every byte value survives frame -> tensor -> frame
     allv = torch.arange(256, dtype=torch.uint8).repeat_interleave(3).reshape(16, 16, 3).numpy()
     assert (imgio.tensor_to_frame(imgio.frame_to_tensor(allv)) == allv).all()
+
+
+def test_inversion_golden(golden):
+    """BASELINE config 4 protocol (Adam on W+, MSE, frozen weights) through the oracle + torch.autograd against the trajectory of
+    the unmodified reference generator: first gradient, loss curve and final latents."""
+    G = golden('inversion.pt')
+    size, batch, steps = G['size'], G['batch'], G['steps']
+    sd = stylegan.synthetic_generator_state(size, seed=3)
+    lat0 = 0.5 * torch.randn(batch, G['n_latent'], 512, generator=torch.Generator().manual_seed(4))
+    target = stylegan.generator_forward(sd, torch.randn(batch, G['n_latent'], 512, generator=torch.Generator().manual_seed(5)),
+                                        size, randomize_noise=False)
+    assert float(target.double().sum()) == pytest.approx(G['target_sum'], rel=1e-5, abs=1e-3)
+    with torch.enable_grad():
+        lat = lat0.clone().requires_grad_(True)
+        opt = torch.optim.Adam([lat], lr=0.01)
+        losses, grad0 = [], None
+        for _ in range(steps):
+            opt.zero_grad()
+            loss = F.mse_loss(stylegan.generator_forward(sd, lat, size, randomize_noise=False), target)
+            loss.backward()
+            if grad0 is None:
+                grad0 = lat.grad.detach().clone()
+            opt.step()
+            losses.append(float(loss.detach()))
+    rel = float((grad0 - G['grad0']).norm() / G['grad0'].norm())
+    assert rel < 1e-4, rel
+    torch.testing.assert_close(torch.tensor(losses), torch.tensor(G['losses']), rtol=1e-4, atol=1e-7)
+    assert float((lat.detach() - G['final']).abs().max()) < 2e-3
