@@ -223,6 +223,18 @@ int ood_alignnet_tail(const float *res, const float *shortcut, const float *prel
 int ood_bicubic_up_add(const void *x, const void *y, void *out, int batch, int h, int w, int H, int W, int channels,
                        int dtype, void *stream);
 
+/* ---- a14 ("grid_sample grads"; section 8b warp_alpha_bwd / mask_blend_bwd): backward of ood_warp_mix and ood_mask_blend, i.e. of
+ *      F.grid_sample(bilinear, zeros, align_corners=False) + alpha mix (SAMM/helpers.py:168-177) and of the mask pyramid
+ *      composition + clip + blend (OOD_faceGAN_e4e_arch.py:315-347), as torch.autograd computes them for the reference.
+ *      First correct path (atomics).  ZERO-INITIALISE ggen / gfield / gfields before the call: they are accumulated into.
+ *      ood_warp_mix_bwd: gen, gout NHWC [B,H,W,C] (dtype), field fp32 [B,3,H,W] -> ggen fp32 NHWC [B,H,W,C], gfield fp32 [B,3,H,W].
+ *      ood_mask_blend_bwd: fields / gfields: n host arrays of device pointers to fp32 [B,3,r_i,r_i] (only channel 2 receives a
+ *      gradient); x, gen, gout fp32 [B,3,S,S] -> gx, ggen fp32 [B,3,S,S] (written; either may be NULL). */
+int ood_warp_mix_bwd(const void *gen, const float *field, const void *gout, float *ggen, float *gfield, int batch, int h, int w,
+                     int channels, int dtype, void *stream);
+int ood_mask_blend_bwd(const float *const *fields_host, float *const *gfields_host, const int *field_sizes_host, int n_fields,
+                       const float *x, const float *gen, const float *gout, float *gx, float *ggen, int batch, int size, void *stream);
+
 /* ---- section 8f rank 4 (host I/O either side of the path): the byte formats of the reference's inference script, on the
  *      device, so that a batch crosses PCIe as 3 bytes per pixel.  Bit-exact against the reference's arithmetic.
  *      ood_img2tensor_u8: replaces `cv2.imread(f) / 255.0 -> img2tensor(bgr2rgb) -> (t - 0.5) * 2`

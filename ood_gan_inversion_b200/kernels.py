@@ -623,5 +623,35 @@ def mask_blend(fields, x, gen, want_alpha=True):
     return out, alpha
 
 
+def warp_mix_bwd(gen, field, gout):
+    """Backward of warp_mix: gen, gout NHWC [B,H,W,C]; field fp32 [B,3,H,W] -> (ggen fp32 NHWC, gfield fp32 [B,3,H,W])."""
+    _cuda(gen, field, gout)
+    assert gen.is_contiguous() and gout.is_contiguous() and gen.shape == gout.shape and gen.dtype == gout.dtype
+    b, h, w, c = gen.shape
+    ggen = torch.zeros(b, h, w, c, device=gen.device, dtype=torch.float32)
+    gfield = torch.zeros(b, 3, h, w, device=gen.device, dtype=torch.float32)
+    check(_lib.lib().ood_warp_mix_bwd(_ptr(gen), _ptr(_f32c(field)), _ptr(gout), _ptr(ggen), _ptr(gfield), b, h, w, c, _dt(gen),
+                                      _stream()), 'warp_mix_bwd')
+    return ggen, gfield
+
+
+def mask_blend_bwd(fields, x, gen, gout, want_gx=True, want_ggen=True):
+    """Backward of mask_blend: fields list of fp32 [B,3,r,r]; x, gen, gout fp32 [B,3,S,S] -> (gx, ggen, [gfields])."""
+    _cuda(x, gen, gout, *fields)
+    fields = [_f32c(f) for f in fields]
+    x, gen, gout = _f32c(x), _f32c(gen), _f32c(gout)
+    b, _, s, _ = x.shape
+    gx = torch.empty_like(x) if want_gx else None
+    ggen = torch.empty_like(x) if want_ggen else None
+    gfields = [torch.zeros_like(f) for f in fields]
+    n = len(fields)
+    ptrs = (C.c_void_p * n)(*[f.data_ptr() for f in fields])
+    gptrs = (C.c_void_p * n)(*[g.data_ptr() for g in gfields])
+    sizes = (C.c_int * n)(*[f.shape[-1] for f in fields])
+    check(_lib.lib().ood_mask_blend_bwd(ptrs, gptrs, sizes, n, _ptr(x), _ptr(gen), _ptr(gout), _ptr(gx), _ptr(ggen), b, s, _stream()),
+          'mask_blend_bwd')
+    return gx, ggen, gfields
+
+
 def conv_scale(cin, k):
     return 1.0 / math.sqrt(cin * k * k)
