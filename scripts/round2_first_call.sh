@@ -1,7 +1,7 @@
 #!/bin/bash
 # First GPU call of the next round: what the third session of round 1 could not measure (its GPU budget ended).
 #   /usr/local/graft/bin/gpurun --timeout 900 -- 'bash scripts/round2_first_call.sh'
-# 1. the whole GPU suite (the third session re-ran only the cases its changes touched);
+# 1. the whole GPU suite (the third session re-ran only the cases its changes touched; tests/test_zz_samm_bwd_gpu.py has never run);
 # 2. default bench + the byte-format serving loop (imgio.ByteServing: uint8 frames across PCIe, `e2e_u8`);
 # 3. ncu --set full of the rewritten mask_blend and of the two image-format kernels; refreshed launch list;
 # 4. the SAMM micro-benchmarks (mask_blend 0.77 / warp_mix) on this box.
