@@ -235,6 +235,13 @@ int ood_warp_mix_bwd(const void *gen, const float *field, const void *gout, floa
 int ood_mask_blend_bwd(const float *const *fields_host, float *const *gfields_host, const int *field_sizes_host, int n_fields,
                        const float *x, const float *gen, const float *gout, float *gx, float *ggen, int batch, int size, void *stream);
 
+/*      ood_field_step_bwd (section 8b prm_bwd): backward of ood_field_step in its plain form (z only, no folded norms): heads
+ *      (tanh * scale, tanh * scale, sigmoid) + 4x4 FIR + accumulate / clip / PRM + bicubic coarse PRM (SAMM/helpers.py:62-77,
+ *      149-166).  z, gacc, gz, gf_workspace fp32 [B,3,R,R]; prev / gprev [B,3,R,R] or NULL; coarse / gcoarse [B,3,Rc,Rc] or NULL
+ *      (gcoarse ZERO-INITIALISED by the caller: the bicubic gradient is accumulated into its alpha channel). */
+int ood_field_step_bwd(const float *z, const float *prev, const float *coarse, const float *gacc, const float *taps_host, float scale,
+                       int batch, int r, int rc, float *gf_workspace, float *gz, float *gprev, float *gcoarse, void *stream);
+
 /* ---- section 8f rank 4 (host I/O either side of the path): the byte formats of the reference's inference script, on the
  *      device, so that a batch crosses PCIe as 3 bytes per pixel.  Bit-exact against the reference's arithmetic.
  *      ood_img2tensor_u8: replaces `cv2.imread(f) / 255.0 -> img2tensor(bgr2rgb) -> (t - 0.5) * 2`

@@ -66,6 +66,8 @@ _SIGS = {
     'ood_bicubic_up_add': ([c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p], c_int),
     'ood_warp_mix_bwd': ([c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p], c_int),
     'ood_mask_blend_bwd': ([c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p], c_int),
+    'ood_field_step_bwd': ([c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                           c_void_p, c_void_p], c_int),
     'ood_img2tensor_u8': ([c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_float, c_void_p], c_int),
     'ood_tensor2img_u8': ([c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_float, c_void_p], c_int),
     'ood_bwd_workspace': ([c_int, c_i64, c_int, c_int], c_i64),

@@ -33,6 +33,21 @@ __global__ void __launch_bounds__(256) mask_blend_bwd_kernel(const ood_bwd::Mask
     ood_bwd::mask_blend_bwd_item(mp, xin, gen, gout, gx, ggen, b, y, x, S, ood_bwd::DeviceAdd());
 }
 
+__global__ void __launch_bounds__(256) field_step_bwd_pass1_kernel(const ood_bwd::FieldBwdArgs a, const float *__restrict__ gacc,
+                                                                    float *__restrict__ gf, float *__restrict__ gprev,
+                                                                    float *__restrict__ gcoarse) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= a.R || y >= a.R) return;
+    ood_bwd::field_step_bwd_pass1_item(a, gacc, gf, gprev, gcoarse, blockIdx.z, y, x, ood_bwd::DeviceAdd());
+}
+
+__global__ void __launch_bounds__(256) field_step_bwd_pass2_kernel(const ood_bwd::FieldBwdArgs a, const float *__restrict__ gf,
+                                                                    float *__restrict__ gz) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= a.R || y >= a.R) return;
+    ood_bwd::field_step_bwd_pass2_item(a, gf, gz, blockIdx.z, y, x);
+}
+
 }  // namespace ood
 
 extern "C" int ood_warp_mix_bwd(const void *gen, const float *field, const void *gout, float *ggen, float *gfield, int batch,
@@ -74,4 +89,23 @@ extern "C" int ood_mask_blend_bwd(const float *const *fields_host, float *const 
     const dim3 grid(ceil_div(size, 32), ceil_div(size, 8), batch);
     mask_blend_bwd_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(mp, x, gen, gout, gx, ggen, size);
     return check_launch("mask_blend_bwd");
+}
+
+extern "C" int ood_field_step_bwd(const float *z, const float *prev, const float *coarse, const float *gacc, const float *taps_host,
+                                  float scale, int batch, int r, int rc, float *gf_workspace, float *gz, float *gprev, float *gcoarse,
+                                  void *stream) {
+    using namespace ood;
+    OOD_REQUIRE(z && gacc && taps_host && gf_workspace && gz && batch > 0 && batch <= 65535 && r > 0 && r <= 32768,
+                "field_step_bwd: bad arguments");
+    OOD_REQUIRE(!coarse || rc > 0, "field_step_bwd: coarse needs its size");
+    OOD_REQUIRE(!gprev || prev, "field_step_bwd: gprev without prev");
+    OOD_REQUIRE(!gcoarse || coarse, "field_step_bwd: gcoarse without coarse");
+    // the taps as the forward applies them: correlation with the flipped kernel (upfirdn2d.py:179)
+    const ood_bwd::FieldBwdArgs a{z, prev, coarse, {taps_host[3], taps_host[2], taps_host[1], taps_host[0]}, scale, r, rc};
+    const dim3 block(32, 8);
+    const dim3 grid(ceil_div(r, 32), ceil_div(r, 8), batch);
+    cudaStream_t st = (cudaStream_t)stream;
+    field_step_bwd_pass1_kernel<<<grid, block, 0, st>>>(a, gacc, gf_workspace, gprev, gcoarse);
+    field_step_bwd_pass2_kernel<<<grid, block, 0, st>>>(a, gf_workspace, gz);
+    return check_launch("field_step_bwd", 2);
 }

@@ -167,4 +167,135 @@ OOD_HD void mask_blend_bwd_item(const MaskBwdParams &mp, const float *xin, const
     }
 }
 
+// ---------------------------------------------------------------------------------------------- field step (heads + FIR + PRM), backward
+// forward (field_step_kernel, SAMM/helpers.py:62-77,149-166):
+//   h = [tanh(z0) * scale, tanh(z1) * scale, sigmoid(z2)];   f = FIR(h)   (4x4 separable correlation, pad (2, 1), zeros outside)
+//   prev:    acc01 = clip(prev01 + f01, -scale, scale);   a1 = f2 * p2 + p2 * (1 - p2);   acc2 = clip(a1, 0, 1)      (else acc = f)
+//   coarse:  u = bicubic_up(coarse alpha, align_corners=True);   a2 = acc2 * u + u * (1 - u);   acc2 = clip(a2, 0, 1)
+// Two passes, no atomics except the bicubic scatter:
+//   pass 1 (item = output pixel): recompute f, push gacc through the clips / PRMs -> gf (gradient at the FIR output, workspace),
+//                                 gprev (written), gcoarse[:, 2] (+=, ZERO-INITIALISED by the caller)
+//   pass 2 (item = input pixel):  gz = head'(z) * FIR^T(gf)  (gather over the 4x4 outputs whose window holds the pixel)
+struct FieldBwdArgs {
+    const float *z, *prev, *coarse;      // [B,3,R,R], [B,3,R,R] or NULL, [B,3,Rc,Rc] or NULL
+    float kf[4];                         // the FIR taps as the forward applies them (flipped, upfirdn2d.py:179)
+    float scale;
+    int R, Rc;
+};
+
+OOD_HD float fs_head(const FieldBwdArgs &a, int b, int ch, int y, int x) {
+    if (y < 0 || y >= a.R || x < 0 || x >= a.R) return 0.f;
+    const float t = a.z[(((int64_t)b * 3 + ch) * a.R + y) * a.R + x];
+    return ch < 2 ? tanhf(t) * a.scale : 1.f / (1.f + expf(-t));
+}
+
+OOD_HD float fs_cubic1(float x, float A) { return ((A + 2.f) * x - (A + 3.f)) * x * x + 1.f; }
+OOD_HD float fs_cubic2(float x, float A) { return ((A * x - 5.f * A) * x + 8.f * A) * x - 4.f * A; }
+
+template <typename Add>
+OOD_HD void field_step_bwd_pass1_item(const FieldBwdArgs &a, const float *gacc, float *gf, float *gprev, float *gcoarse, int b, int y,
+                                      int x, Add add) {
+    const int R = a.R;
+    const int64_t pl = (int64_t)R * R, o = (int64_t)b * 3 * pl + (int64_t)y * R + x;
+    float f[3];
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+        float s = 0.f;
+#pragma unroll
+        for (int ky = 0; ky < 4; ++ky) {
+            float row = 0.f;
+#pragma unroll
+            for (int kx = 0; kx < 4; ++kx) row += a.kf[kx] * fs_head(a, b, ch, y + ky - 2, x + kx - 2);
+            s += a.kf[ky] * row;
+        }
+        f[ch] = s;
+    }
+    float g0 = gacc[o], g1 = gacc[o + pl], g2 = gacc[o + 2 * pl];
+    float acc2 = f[2], p2 = 0.f, a1 = 0.f;
+    if (a.prev) {
+        const float s0 = a.prev[o] + f[0], s1 = a.prev[o + pl] + f[1];
+        if (!(s0 >= -a.scale && s0 <= a.scale)) g0 = 0.f;
+        if (!(s1 >= -a.scale && s1 <= a.scale)) g1 = 0.f;
+        p2 = a.prev[o + 2 * pl];
+        a1 = f[2] * p2 + p2 * (1.f - p2);
+        acc2 = fminf(fmaxf(a1, 0.f), 1.f);
+    }
+    if (a.coarse) {
+        // bicubic, align_corners=True, clamped taps (ATen UpSampleBicubic2d): value and scatter of its gradient
+        const int Rc = a.Rc;
+        const float A = -0.75f;
+        const float sc = (R > 1) ? (float)(Rc - 1) / (float)(R - 1) : 0.f;
+        const float ry = sc * y, rx = sc * x;
+        const int iy = (int)floorf(ry), ix = (int)floorf(rx);
+        const float ty = ry - iy, tx = rx - ix;
+        const float cx[4] = {fs_cubic2(tx + 1.f, A), fs_cubic1(tx, A), fs_cubic1(1.f - tx, A), fs_cubic2(2.f - tx, A)};
+        const float cy[4] = {fs_cubic2(ty + 1.f, A), fs_cubic1(ty, A), fs_cubic1(1.f - ty, A), fs_cubic2(2.f - ty, A)};
+        const float *src = a.coarse + ((int64_t)b * 3 + 2) * Rc * Rc;
+        float u = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int yy = iy - 1 + j < 0 ? 0 : (iy - 1 + j > Rc - 1 ? Rc - 1 : iy - 1 + j);
+            float row = 0.f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int xx = ix - 1 + i < 0 ? 0 : (ix - 1 + i > Rc - 1 ? Rc - 1 : ix - 1 + i);
+                row += cx[i] * src[(int64_t)yy * Rc + xx];
+            }
+            u += cy[j] * row;
+        }
+        const float a2 = acc2 * u + u * (1.f - u);
+        if (!(a2 >= 0.f && a2 <= 1.f)) g2 = 0.f;
+        const float gu = g2 * (acc2 + 1.f - 2.f * u);
+        g2 = g2 * u;                                             // gradient at acc2 (before the coarse PRM)
+        if (gcoarse) {
+            float *dst = gcoarse + ((int64_t)b * 3 + 2) * Rc * Rc;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int yy = iy - 1 + j < 0 ? 0 : (iy - 1 + j > Rc - 1 ? Rc - 1 : iy - 1 + j);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int xx = ix - 1 + i < 0 ? 0 : (ix - 1 + i > Rc - 1 ? Rc - 1 : ix - 1 + i);
+                    add(dst + (int64_t)yy * Rc + xx, gu * cy[j] * cx[i]);
+                }
+            }
+        }
+    }
+    float gp2 = 0.f;
+    if (a.prev) {
+        if (!(a1 >= 0.f && a1 <= 1.f)) g2 = 0.f;
+        gp2 = g2 * (f[2] + 1.f - 2.f * p2);
+        g2 = g2 * p2;
+    }
+    gf[o] = g0; gf[o + pl] = g1; gf[o + 2 * pl] = g2;
+    if (gprev && a.prev) { gprev[o] = g0; gprev[o + pl] = g1; gprev[o + 2 * pl] = gp2; }
+}
+
+OOD_HD void field_step_bwd_pass2_item(const FieldBwdArgs &a, const float *gf, float *gz, int b, int y, int x) {
+    const int R = a.R;
+    const int64_t pl = (int64_t)R * R;
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+        const float *g = gf + ((int64_t)b * 3 + ch) * pl;
+        float s = 0.f;
+#pragma unroll
+        for (int ky = 0; ky < 4; ++ky) {
+            const int yy = y - ky + 2;
+            if (yy < 0 || yy >= R) continue;
+            float row = 0.f;
+#pragma unroll
+            for (int kx = 0; kx < 4; ++kx) {
+                const int xx = x - kx + 2;
+                if (xx >= 0 && xx < R) row += a.kf[kx] * g[(int64_t)yy * R + xx];
+            }
+            s += a.kf[ky] * row;
+        }
+        const int64_t o = ((int64_t)b * 3 + ch) * pl + (int64_t)y * R + x;
+        const float t = a.z[o];
+        float d;
+        if (ch < 2) { const float th = tanhf(t); d = a.scale * (1.f - th * th); }
+        else { const float sg = 1.f / (1.f + expf(-t)); d = sg * (1.f - sg); }
+        gz[o] = s * d;
+    }
+}
+
 }  // namespace ood_bwd

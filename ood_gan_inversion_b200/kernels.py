@@ -623,6 +623,21 @@ def mask_blend(fields, x, gen, want_alpha=True):
     return out, alpha
 
 
+def field_step_bwd(z, prev, coarse, gacc, scale, taps=None):
+    """Backward of field_step (plain form): -> (gz, gprev or None, gcoarse or None), all fp32."""
+    _cuda(z, prev, coarse, gacc)
+    z, prev, coarse, gacc = _f32c(z), _f32c(prev), _f32c(coarse), _f32c(gacc)
+    b, _, r, _ = z.shape
+    rc = coarse.shape[-1] if coarse is not None else 0
+    ws, gz = torch.empty_like(z), torch.empty_like(z)
+    gprev = torch.empty_like(z) if prev is not None else None
+    gcoarse = torch.zeros_like(coarse) if coarse is not None else None
+    t = (C.c_float * 4)(*(taps or fir_taps()))
+    check(_lib.lib().ood_field_step_bwd(_ptr(z), _ptr(prev), _ptr(coarse), _ptr(gacc), t, float(scale), b, r, rc, _ptr(ws), _ptr(gz),
+                                        _ptr(gprev), _ptr(gcoarse), _stream()), 'field_step_bwd')
+    return gz, gprev, gcoarse
+
+
 def warp_mix_bwd(gen, field, gout):
     """Backward of warp_mix: gen, gout NHWC [B,H,W,C]; field fp32 [B,3,H,W] -> (ggen fp32 NHWC, gfield fp32 [B,3,H,W])."""
     _cuda(gen, field, gout)

@@ -1,9 +1,11 @@
 """Differentiable forms of the SAMM gather / blend kernels ("grid_sample grads").
 
+    field = field_step(z, prev, coarse, scale)          # SAMM/helpers.py:62-77,149-166: heads + FIR + accumulate / clip / PRM
     aligned = warp_mix(gen_nhwc, field)                 # SAMM/helpers.py:168-177: grid_sample + alpha mix
     out, alpha = mask_blend(fields, x, gen)             # OOD_faceGAN_e4e_arch.py:315-347: mask pyramid, clip, blend
 
-Forward = the kernels of the inference path (ood_warp_mix, ood_mask_blend); backward = ood_warp_mix_bwd / ood_mask_blend_bwd,
+Forward = the kernels of the inference path (ood_field_step, ood_warp_mix, ood_mask_blend); backward = ood_field_step_bwd /
+ood_warp_mix_bwd / ood_mask_blend_bwd,
 whose per-item bodies are checked against torch.autograd of the reference arithmetic on the CPU (tests/test_samm_bwd_cpu.py)
 and through the C ABI on the GPU (tests/test_zz_samm_bwd_gpu.py).  The inference modules (samm.py, arch.py) keep calling the plain kernels.
 """
@@ -50,3 +52,23 @@ def mask_blend(fields, x, gen):
     """fields: fp32 [B,3,r,r] ascending; x, gen fp32 [B,3,S,S] -> (out, alpha [B,1,S,S]); differentiable in x, gen and the
     alpha channel of every field (alpha itself is returned for the arch's `aligns[1024]` and carries no gradient)."""
     return _MaskBlend.apply(x, gen, *fields)
+
+
+class _FieldStep(Function):
+    @staticmethod
+    def forward(ctx, z, prev, coarse, scale):
+        ctx.save_for_backward(z, prev, coarse)
+        ctx.scale = scale
+        return K.field_step(z, prev, coarse, scale)
+
+    @staticmethod
+    def backward(ctx, gacc):
+        z, prev, coarse = ctx.saved_tensors
+        gz, gprev, gcoarse = K.field_step_bwd(z, prev, coarse, gacc, ctx.scale)
+        return gz, gprev, gcoarse, None
+
+
+def field_step(z, prev=None, coarse=None, scale=0.08):
+    """z fp32 [B,3,R,R] (AlignNet output before its heads), prev: the field accumulated so far or None, coarse: the coarser
+    level's field or None -> accumulated field [B,3,R,R]; differentiable in z, prev and coarse's alpha channel."""
+    return _FieldStep.apply(z, prev, coarse, scale)

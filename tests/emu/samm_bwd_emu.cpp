@@ -25,3 +25,14 @@ extern "C" void emu_mask_blend_bwd(const float *const *fields, float *const *gfi
         for (int y = 0; y < size; ++y)
             for (int x_ = 0; x_ < size; ++x_) ood_bwd::mask_blend_bwd_item(mp, x, gen, gout, gx, ggen, b, y, x_, size, ood_bwd::HostAdd());
 }
+
+extern "C" void emu_field_step_bwd(const float *z, const float *prev, const float *coarse, const float *gacc, const float *taps,
+                                   float scale, int batch, int r, int rc, float *gf, float *gz, float *gprev, float *gcoarse) {
+    ood_bwd::FieldBwdArgs a{z, prev, coarse, {taps[3], taps[2], taps[1], taps[0]}, scale, r, rc};
+    for (int b = 0; b < batch; ++b)
+        for (int y = 0; y < r; ++y)
+            for (int x = 0; x < r; ++x) ood_bwd::field_step_bwd_pass1_item(a, gacc, gf, gprev, gcoarse, b, y, x, ood_bwd::HostAdd());
+    for (int b = 0; b < batch; ++b)
+        for (int y = 0; y < r; ++y)
+            for (int x = 0; x < r; ++x) ood_bwd::field_step_bwd_pass2_item(a, gf, gz, b, y, x);
+}

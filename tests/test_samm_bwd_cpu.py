@@ -8,7 +8,7 @@ import subprocess
 import pytest
 import torch
 
-from oracle import samm as osamm
+from oracle import ops as oops, samm as osamm
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -68,3 +68,41 @@ def test_mask_blend_bwd_vs_autograd(emu, size, levels):
     for g, f in zip(gf, fields):
         assert float(g[:, :2].abs().max()) == 0.0                        # only the alpha channel takes part
         torch.testing.assert_close(g, f.grad, rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize('r,with_prev,with_coarse', [(12, False, False), (12, True, False), (17, True, True), (9, False, True)])
+def test_field_step_bwd_vs_autograd(emu, r, with_prev, with_coarse):
+    """heads + FIR + accumulate / clip / PRM + coarse PRM (SAMM/helpers.py:62-77,149-166), as oracle/samm.py:spm_warp composes them."""
+    b, scale = 2, 0.08
+    k1 = torch.tensor([1., 3., 3., 1.])
+    k1 = k1 / k1.sum()
+    k = oops.fir_kernel([1, 3, 3, 1])
+    z = rnd(b, 3, r, r, seed=1).requires_grad_(True)
+    U = lambda *shape, seed: torch.rand(*shape, generator=torch.Generator().manual_seed(seed))
+    prev = coarse = None
+    if with_prev:      # beyond the valid ranges on purpose: the clips gate the gradient
+        prev = torch.cat([scale * (2 * U(b, 2, r, r, seed=2) - 1), 1.4 * U(b, 1, r, r, seed=3) - 0.2], 1).requires_grad_(True)
+    if with_coarse:
+        coarse = (1.4 * U(b, 3, max(r // 2, 2), max(r // 2, 2), seed=4) - 0.2).requires_grad_(True)
+    h = torch.cat([torch.tanh(z[:, 0:1]) * scale, torch.tanh(z[:, 1:2]) * scale, torch.sigmoid(z[:, 2:])], 1)
+    acc = oops.upfirdn2d(h, k, pad=(2, 1))
+    if prev is not None:
+        acc = torch.cat([torch.clip(prev[:, 0:1] + acc[:, 0:1], -scale, scale), torch.clip(prev[:, 1:2] + acc[:, 1:2], -scale, scale),
+                         torch.clip(osamm.prm(prev[:, 2:], acc[:, 2:]), 0.0, 1.0)], 1)
+    if coarse is not None:
+        acc = torch.cat([acc[:, 0:2], torch.clip(osamm.prm(coarse[:, 2:], acc[:, 2:]), 0.0, 1.0)], 1)
+    gacc = rnd(b, 3, r, r, seed=5)
+    (acc * gacc).sum().backward()
+    rc = coarse.shape[-1] if coarse is not None else 0
+    gf, gz = torch.zeros(b, 3, r, r), torch.zeros(b, 3, r, r)
+    gprev = torch.zeros(b, 3, r, r) if prev is not None else None
+    gcoarse = torch.zeros_like(coarse) if coarse is not None else None
+    opt = lambda t: _p(t.detach().contiguous()) if t is not None else None
+    emu.emu_field_step_bwd(_p(z.detach()), opt(prev), opt(coarse), _p(gacc), _p(k1), C.c_float(scale), b, r, rc, _p(gf), _p(gz),
+                           opt(gprev), opt(gcoarse))
+    torch.testing.assert_close(gz, z.grad, rtol=1e-4, atol=1e-6)
+    if prev is not None:
+        torch.testing.assert_close(gprev, prev.grad, rtol=1e-4, atol=1e-6)
+    if coarse is not None:
+        assert float(gcoarse[:, :2].abs().max()) == 0.0
+        torch.testing.assert_close(gcoarse, coarse.grad, rtol=1e-4, atol=1e-5)

@@ -4,7 +4,7 @@ per-item bodies are verified on the CPU by tests/test_samm_bwd_cpu.py), so their
 import pytest
 import torch
 
-from oracle import samm as osamm
+from oracle import ops as oops, samm as osamm
 
 pytestmark = pytest.mark.gpu
 DEV = 'cuda'
@@ -47,3 +47,34 @@ def test_mask_blend_bwd(size, levels):
     out.backward(gout)
     for a, r in zip(ours, ref_in):
         torch.testing.assert_close(a.grad, r.grad, rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize('r,with_prev,with_coarse', [(12, False, False), (32, True, False), (50, True, True), (9, False, True)])
+def test_field_step_bwd(r, with_prev, with_coarse):
+    from ood_gan_inversion_b200 import samm_grad
+    b, scale = 2, 0.08
+    k = oops.fir_kernel([1, 3, 3, 1]).to(DEV)
+    U = lambda *shape, seed: torch.rand(*shape, generator=torch.Generator().manual_seed(seed))
+    z0 = rnd(b, 3, r, r, seed=1)
+    prev0 = torch.cat([scale * (2 * U(b, 2, r, r, seed=2) - 1), 1.4 * U(b, 1, r, r, seed=3) - 0.2], 1) if with_prev else None
+    coarse0 = 1.4 * U(b, 3, max(r // 2, 2), max(r // 2, 2), seed=4) - 0.2 if with_coarse else None
+    gacc = rnd(b, 3, r, r, seed=5).to(DEV)
+    leaf = lambda t: t.to(DEV).requires_grad_(True) if t is not None else None
+    z, prev, coarse = leaf(z0), leaf(prev0), leaf(coarse0)
+    h = torch.cat([torch.tanh(z[:, 0:1]) * scale, torch.tanh(z[:, 1:2]) * scale, torch.sigmoid(z[:, 2:])], 1)
+    acc = oops.upfirdn2d(h, k, pad=(2, 1))
+    if prev is not None:
+        acc = torch.cat([torch.clip(prev[:, 0:1] + acc[:, 0:1], -scale, scale), torch.clip(prev[:, 1:2] + acc[:, 1:2], -scale, scale),
+                         torch.clip(osamm.prm(prev[:, 2:], acc[:, 2:]), 0.0, 1.0)], 1)
+    if coarse is not None:
+        acc = torch.cat([acc[:, 0:2], torch.clip(osamm.prm(coarse[:, 2:], acc[:, 2:]), 0.0, 1.0)], 1)
+    (acc * gacc).sum().backward()
+    z_, prev_, coarse_ = leaf(z0), leaf(prev0), leaf(coarse0)
+    out = samm_grad.field_step(z_, prev_, coarse_, scale)
+    torch.testing.assert_close(out, acc.detach(), rtol=1e-4, atol=1e-5)
+    out.backward(gacc)
+    torch.testing.assert_close(z_.grad, z.grad, rtol=1e-3, atol=1e-5)
+    if prev is not None:
+        torch.testing.assert_close(prev_.grad, prev.grad, rtol=1e-3, atol=1e-5)
+    if coarse is not None:
+        torch.testing.assert_close(coarse_.grad, coarse.grad, rtol=1e-3, atol=1e-4)
