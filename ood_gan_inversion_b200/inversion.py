@@ -31,6 +31,21 @@ def generator_synthesizer(gen, noise=None):
     return synthesize
 
 
+def blended_synthesizer(gen, fields, x, noise=None):
+    """BASELINE config 4 with the blend in the loop ("generator (+ blend optional)"): latent -> A * x + gen(latent) * (1 - A) with the
+    invertibility masks `fields` (the arch's `aligns[1..4]`, fp32 [B,3,r,r], held fixed) and the input batch `x`
+    (OOD_faceGAN_e4e_arch.py:315-347).  The blend runs the inference kernel forward and ood_mask_blend_bwd backward
+    (samm_grad.mask_blend), so the OOD region of the target does not pull on the latent."""
+    from . import samm_grad
+    fields = [f.detach() for f in fields]
+    x = x.detach()
+
+    def synthesize(latent):
+        image = gen(latent, input_is_tensor=True, input_is_latent=True, randomize_noise=False, noise=noise)[0]
+        return samm_grad.mask_blend(fields, x, image)[0]
+    return synthesize
+
+
 def mse_loss(image, target):
     """`pix_opt` of the reference (L2, reduction mean; E4E_Face.yml:152-154)."""
     return torch.nn.functional.mse_loss(image, target)

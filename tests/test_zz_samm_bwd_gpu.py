@@ -78,3 +78,34 @@ def test_field_step_bwd(r, with_prev, with_coarse):
         torch.testing.assert_close(prev_.grad, prev.grad, rtol=1e-3, atol=1e-5)
     if coarse is not None:
         torch.testing.assert_close(coarse_.grad, coarse.grad, rtol=1e-3, atol=1e-4)
+
+
+def test_inversion_with_the_blend_in_the_loop():
+    """inversion.blended_synthesizer: Adam on W+ through generator + mask blend; the trajectory matches torch.autograd of the oracle."""
+    import ood_gan_inversion_b200.stylegan as sg
+    from oracle import stylegan as ostyle
+    from ood_gan_inversion_b200.inversion import LatentInverter, blended_synthesizer
+    sg.set_precision('fp32')
+    try:
+        size, batch, steps = 32, 2, 6
+        sd = ostyle.synthetic_generator_state(size, seed=3)
+        gen = sg.Generator(size, 512, 8).to(DEV)
+        gen.load_state_dict(sd)
+        for p in gen.parameters():
+            p.requires_grad_(False)
+        sdd = {k: v.to(DEV) for k, v in sd.items()}
+        lat0 = 0.5 * torch.randn(batch, gen.n_latent, 512, generator=torch.Generator().manual_seed(4)).to(DEV)
+        x = rnd(batch, 3, size, size, seed=6).to(DEV)
+        target = rnd(batch, 3, size, size, seed=7).to(DEV)
+        fields = [torch.rand(batch, 3, r, r, generator=torch.Generator().manual_seed(20 + r)).to(DEV) for r in (4, 8)]
+        lat, losses = LatentInverter(blended_synthesizer(gen, fields, x), lr=0.01).run(target, lat0, steps)
+
+        def oracle_synth(latent):
+            img = ostyle.generator_forward(sdd, latent, size, randomize_noise=False)
+            return osamm.blend(osamm.compose_masks(fields, size), x, img)
+        lat_o, losses_o = LatentInverter(oracle_synth, lr=0.01).run(target, lat0, steps)
+        assert losses[-1] < losses[0]
+        torch.testing.assert_close(torch.tensor(losses), torch.tensor(losses_o), rtol=1e-3, atol=1e-6)
+        assert float((lat - lat_o).abs().max()) < 5e-3
+    finally:
+        sg.set_precision('bf16')
