@@ -10,6 +10,14 @@ pytestmark = pytest.mark.gpu
 DEV = 'cuda'
 
 
+@pytest.fixture(autouse=True)
+def _setup():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    with torch.enable_grad():
+        yield
+
+
 def rnd(*shape, seed=0):
     return torch.randn(*shape, generator=torch.Generator().manual_seed(seed))
 
@@ -80,32 +88,90 @@ def test_field_step_bwd(r, with_prev, with_coarse):
         torch.testing.assert_close(coarse_.grad, coarse.grad, rtol=1e-3, atol=1e-4)
 
 
-def test_inversion_with_the_blend_in_the_loop():
-    """inversion.blended_synthesizer: Adam on W+ through generator + mask blend; the trajectory matches torch.autograd of the oracle."""
+def _blend_case(size=32, batch=2):
     import ood_gan_inversion_b200.stylegan as sg
     from oracle import stylegan as ostyle
-    from ood_gan_inversion_b200.inversion import LatentInverter, blended_synthesizer
+    from ood_gan_inversion_b200.inversion import blended_synthesizer
+    sd = ostyle.synthetic_generator_state(size, seed=3)
+    gen = sg.Generator(size, 512, 8).to(DEV)
+    gen.load_state_dict(sd)
+    for p in gen.parameters():
+        p.requires_grad_(False)
+    sdd = {k: v.to(DEV) for k, v in sd.items()}
+    lat0 = 0.5 * torch.randn(batch, gen.n_latent, 512, generator=torch.Generator().manual_seed(4)).to(DEV)
+    x = rnd(batch, 3, size, size, seed=6).to(DEV)
+    target = rnd(batch, 3, size, size, seed=7).to(DEV)
+    fields = [torch.rand(batch, 3, r, r, generator=torch.Generator().manual_seed(20 + r)).to(DEV) for r in (4, 8)]
+
+    def oracle_synth(latent):
+        img = ostyle.generator_forward(sdd, latent, size, randomize_noise=False)
+        return osamm.blend(osamm.compose_masks(fields, size), x, img)
+    return gen, blended_synthesizer(gen, fields, x), oracle_synth, lat0, target
+
+
+def test_blend_in_the_loop_first_step_gradient():
+    """dL/dW+ of the FIRST step through generator + mask blend against torch.autograd of the oracle, the criterion of
+    test_backward_gpu.test_latent_gradient_fp32_vs_oracle_autograd (rel-L2 < 1e-3).  Measured on B200: 5.9e-4 (the plain
+    generator: 2.7e-4), forward 2.3e-6 (profiles/r02_diag_blend.txt)."""
+    import torch.nn.functional as F
+    import ood_gan_inversion_b200.stylegan as sg
     sg.set_precision('fp32')
     try:
-        size, batch, steps = 32, 2, 6
-        sd = ostyle.synthetic_generator_state(size, seed=3)
-        gen = sg.Generator(size, 512, 8).to(DEV)
-        gen.load_state_dict(sd)
-        for p in gen.parameters():
-            p.requires_grad_(False)
-        sdd = {k: v.to(DEV) for k, v in sd.items()}
-        lat0 = 0.5 * torch.randn(batch, gen.n_latent, 512, generator=torch.Generator().manual_seed(4)).to(DEV)
-        x = rnd(batch, 3, size, size, seed=6).to(DEV)
-        target = rnd(batch, 3, size, size, seed=7).to(DEV)
-        fields = [torch.rand(batch, 3, r, r, generator=torch.Generator().manual_seed(20 + r)).to(DEV) for r in (4, 8)]
-        lat, losses = LatentInverter(blended_synthesizer(gen, fields, x), lr=0.01).run(target, lat0, steps)
+        _, ours, oracle_synth, lat0, target = _blend_case()
+        la, lb = lat0.clone().requires_grad_(True), lat0.clone().requires_grad_(True)
+        oa, ob = ours(la), oracle_synth(lb)
+        assert float((oa.detach() - ob.detach()).abs().max()) < 1e-4
+        g, = torch.autograd.grad(F.mse_loss(oa, target), la)
+        g_r, = torch.autograd.grad(F.mse_loss(ob, target), lb)
+        rel = float((g - g_r).norm() / g_r.norm())
+        print(f'gen+blend dL/dW+: rel-L2 {rel:.3g}, max-abs {float((g - g_r).abs().max()):.3g} of {float(g_r.abs().max()):.3g}')
+        assert rel < 1e-3
+        torch.testing.assert_close(g, g_r, rtol=1e-2, atol=2e-3 * float(g_r.abs().max()))
+    finally:
+        sg.set_precision('bf16')
 
-        def oracle_synth(latent):
-            img = ostyle.generator_forward(sdd, latent, size, randomize_noise=False)
-            return osamm.blend(osamm.compose_masks(fields, size), x, img)
+
+def test_synthesis_backward_takes_a_non_contiguous_grad_output():
+    """The blend's backward hands SynthesisFn.backward whatever layout autograd produced: an NHWC-strided view of the image
+    gradient must give the gradient of its contiguous copy bit for bit."""
+    import ood_gan_inversion_b200.stylegan as sg
+    sg.set_precision('fp32')
+    try:
+        gen, _, _, lat0, _ = _blend_case()
+        go = rnd(2, 32, 32, 3, seed=9).to(DEV).permute(0, 3, 1, 2)
+        assert not go.is_contiguous()
+        grads = []
+        for g_out in (go, go.contiguous()):
+            lat = lat0.clone().requires_grad_(True)
+            img = gen(lat, input_is_tensor=True, input_is_latent=True, randomize_noise=False)[0]
+            grads.append(torch.autograd.grad(img, lat, g_out)[0])
+        assert torch.equal(grads[0], grads[1])
+    finally:
+        sg.set_precision('bf16')
+
+
+def test_inversion_with_the_blend_in_the_loop():
+    """inversion.blended_synthesizer: Adam on W+ through generator + mask blend; the trajectory matches torch.autograd of the oracle.
+
+    Criterion (round-1 failure diagnosed, scripts/diag_blend_grad.py -> profiles/r02_diag_blend.txt): the first-step gradient
+    agrees to 5.9e-4 rel-L2 (test above) and the loss curves to 1e-3, but Adam divides every element's step by the root of its
+    own squared-gradient average, so the ~1e-7 rounding noise on elements whose gradient is itself ~1e-7 (the mask keeps the
+    generator out of most of the target) becomes a +-lr step in either direction.  The oracle's OWN fp32 and fp64 runs end
+    2.2e-2 apart in max-abs (2.1e-4 mean) over these 6 steps; ours ends 1.7e-2 (1.7e-4 mean) from the fp32 oracle.  Hence the
+    Adam-aware bound already used for the shared offset in test_backward_gpu.py: mean < 5e-4, and no element further than
+    half of the distance it can walk (6 steps x lr 0.01)."""
+    import ood_gan_inversion_b200.stylegan as sg
+    from ood_gan_inversion_b200.inversion import LatentInverter
+    sg.set_precision('fp32')
+    try:
+        steps = 6
+        _, ours, oracle_synth, lat0, target = _blend_case()
+        lat, losses = LatentInverter(ours, lr=0.01).run(target, lat0, steps)
         lat_o, losses_o = LatentInverter(oracle_synth, lr=0.01).run(target, lat0, steps)
         assert losses[-1] < losses[0]
         torch.testing.assert_close(torch.tensor(losses), torch.tensor(losses_o), rtol=1e-3, atol=1e-6)
-        assert float((lat - lat_o).abs().max()) < 5e-3
+        diff = (lat - lat_o).abs()
+        print(f'final W+ after {steps} Adam steps: mean diff {float(diff.mean()):.3g}, max {float(diff.max()):.3g}')
+        assert float(diff.mean()) < 5e-4 and float(diff.max()) < 3e-2
     finally:
         sg.set_precision('bf16')
