@@ -113,27 +113,55 @@ class ClockSampler:
                     source='nvml' if self.nvml is not None else 'nvidia-smi')
 
 
-def cpu_reference(steps, warmup, images_per_step=1, state=None):
-    """The reference's arithmetic for the path (oracle port: plain PyTorch fp32, native upfirdn2d / fused_act branch) on
-    the host cores.  A step = `images_per_step` images of the same 1024px pipeline (bounded sample)."""
+REF_STAGE = os.path.join(ROOT, 'baseline', '_ref')
+
+
+def reference_available():
+    return os.path.isfile(os.path.join(REF_STAGE, 'src', 'archs', 'OOD_faceGAN_e4e_arch.py'))
+
+
+def cpu_reference(steps, warmup, images_per_step=1, state=None, prefer_reference=True):
+    """The reference's own CPU implementation of the path on the host cores, one bounded sample (`images_per_step` images of
+    the same 1024px pipeline) per step.
+
+    kind "reference": the UNMODIFIED reference modules staged under baseline/_ref by __graft_entry__.build() -- its
+    `ood_faceGAN_e4e(...)(x)` through its own API with the default device='cpu' branch of its ops (upfirdn2d_native, native
+    fused_leaky_relu).  Needs a process that sees no CUDA device (the reference JIT-builds its legacy extensions at import time
+    when one is visible, src/ops/op/upfirdn2d.py:10-18): --impl reference hides the GPUs before torch is imported.
+    kind "port": oracle/ (plain-PyTorch restatement of the same arithmetic), when the staged copy is absent."""
     import torch
-    from oracle import ood as oood
     torch.set_num_threads(os.cpu_count() or 1)
     torch.set_grad_enabled(False)
-    sd = state if state is not None else oood.synthetic_ood_state(SIZE, seed=0)
-    from ood_gan_inversion_b200.synth import synthetic_faces
+    from ood_gan_inversion_b200.synth import synthetic_faces, synthetic_init
     x = synthetic_faces(images_per_step, SIZE)
+    kind = 'port'
+    if prefer_reference and reference_available() and not torch.cuda.is_available():
+        for pth in (REF_STAGE,):
+            if pth not in sys.path:
+                sys.path.insert(0, pth)
+        from src.archs.OOD_faceGAN_e4e_arch import ood_faceGAN_e4e as ref_arch
+        torch.manual_seed(0)
+        net = synthetic_init(ref_arch(**ARCH_KW), seed=0).eval()
+        if state is not None:
+            net.load_state_dict(state, strict=True)
+        run = lambda: net(x)
+        kind = 'reference'
+    else:
+        from oracle import ood as oood
+        sd = state if state is not None else oood.synthetic_ood_state(SIZE, seed=0)
+        run = lambda: oood.ood_forward(sd, x, size=SIZE, strict_rng=False)
     times = []
     for i in range(warmup + steps):
         torch.manual_seed(123)
         t0 = time.perf_counter()
-        oood.ood_forward(sd, x, size=SIZE, strict_rng=False)
+        run()
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
     total = sum(times)
-    return dict(value=images_per_step * len(times) / total, ms_per_step=1e3 * total / len(times), cores=torch.get_num_threads(),
-                sample=f'{len(times)} step(s) x {images_per_step} image(s) of the 1024px pipeline, fp32, after {warmup} warm-up')
+    what = 'unmodified reference modules (baseline/_ref), ood_faceGAN_e4e.forward' if kind == 'reference' else 'oracle port'
+    return dict(value=images_per_step * len(times) / total, ms_per_step=1e3 * total / len(times), cores=torch.get_num_threads(), kind=kind,
+                sample=f'{len(times)} step(s) x {images_per_step} image(s) of the 1024px pipeline ({what}), fp32, after {warmup} warm-up')
 
 
 def cpu_op_baselines(device=None):
@@ -210,6 +238,170 @@ def cpu_op_baselines(device=None):
     return dict(cores=torch.get_num_threads(), kind='port', ops=rows)
 
 
+def sharded_batch_leg(net, global_batch, chunk, steps, rank, world, dev, barrier, reduce_max, want_e2e=True):
+    """BASELINE configs[2] (SURVEY.md section 8d "Config 3"): `global_batch` images split evenly over the ranks
+    (sharding.shard_bounds: contiguous slices, no data-path collective), each rank running its slice in micro-batches of
+    <= `chunk` images, per-rank seed = base + rank.  images/s = global_batch x passes / max-rank time (CUDA events).
+    Returns dict(value=device-resident, e2e=pinned host in/out with the copies inside the timed region)."""
+    import torch
+    from ood_gan_inversion_b200.graphs import GraphedForward, PipelinedForward
+    from ood_gan_inversion_b200.sharding import shard_bounds
+    from ood_gan_inversion_b200.synth import synthetic_faces
+    lo, hi = shard_bounds(global_batch, world, rank)
+    n = hi - lo
+    nch = max(1, -(-n // chunk))
+    sizes = [n // nch + (1 if i < n % nch else 0) for i in range(nch)] if n > 0 else []
+    bounds, a = [], 0
+    for sz in sizes:
+        bounds.append((a, a + sz))
+        a += sz
+    x_host = synthetic_faces(max(n, 1), SIZE, seed=100 + rank, pin=True)[:n]
+    x_dev = x_host.to(dev)
+    out_dev = torch.empty_like(x_dev)
+    fn = lambda t: net(t)[0]
+    graphs = {}
+    for sz in sorted(set(sizes)):
+        torch.manual_seed(3000 + rank)
+        graphs[sz] = GraphedForward(fn, x_dev[:sz], warmup=2)
+
+    def one_pass():
+        for a, b in bounds:
+            out_dev[a:b].copy_(graphs[b - a](x_dev[a:b]), non_blocking=True)
+    for _ in range(3):
+        one_pass()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        one_pass()
+    e1.record()
+    barrier()
+    ms = reduce_max(e0.elapsed_time(e1))
+    res = dict(global_batch=global_batch, images_per_rank=n, chunk=max(sizes) if sizes else 0, chunks_per_rank=len(sizes), passes=steps,
+               value=global_batch * steps / (ms * 1e-3), unit=UNIT, ms_per_pass=ms / steps, scaling='strong',
+               note='BASELINE configs[2]: images split by sharding.shard_bounds, no collective; value = global_batch x passes / max-rank time')
+    if want_e2e and len(set(sizes)) == 1:
+        out_host = torch.empty(n, 3, SIZE, SIZE, dtype=torch.float32).pin_memory()
+        torch.manual_seed(3000 + rank)
+        pipe = PipelinedForward(fn, x_dev[:sizes[0]], depth=2, warmup=1)
+
+        def host_pass():
+            for a, b in bounds:
+                pipe.submit(x_host[a:b], out_host[a:b])
+            pipe.synchronize()
+        host_pass()
+        barrier()
+        e0.record()
+        for _ in range(steps):
+            host_pass()
+        e1.record()
+        barrier()
+        ms2 = reduce_max(e0.elapsed_time(e1))
+        res['e2e'] = dict(value=global_batch * steps / (ms2 * 1e-3), unit=UNIT, ms_per_pass=ms2 / steps,
+                          h2d_bytes_per_pass_per_rank=x_host.numel() * 4, d2h_bytes_per_pass_per_rank=out_host.numel() * 4)
+        del pipe, out_host
+    del graphs, x_dev, out_dev
+    torch.cuda.empty_cache()
+    return res
+
+
+def inversion_leg(dev, batch=32, steps=5):
+    """BASELINE configs[3] ("Config 4"): Adam on W+ at 1024 px through this package's forward + hand-written backward
+    (inversion.LatentInverter, bf16 storage), `steps` timed steps after a 2-step warm-up run."""
+    import torch
+    from ood_gan_inversion_b200 import stylegan as sg
+    from ood_gan_inversion_b200.inversion import LatentInverter, generator_synthesizer
+    from ood_gan_inversion_b200.synth import synthetic_faces, synthetic_init
+    with torch.enable_grad():
+        torch.manual_seed(0)
+        gen = synthetic_init(sg.Generator(SIZE, 512, 8), seed=0).to(dev)
+        for p in gen.parameters():
+            p.requires_grad_(False)
+        target = synthetic_faces(batch, SIZE, seed=3, device=dev)
+        lat0 = torch.zeros(batch, 18, 512, device=dev)
+        inv = LatentInverter(generator_synthesizer(gen), lr=0.01)
+        inv.run(target, lat0, 2)
+        torch.cuda.synchronize(dev)
+        torch.cuda.reset_peak_memory_stats(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _, losses = inv.run(target, lat0, steps)
+        e1.record()
+        torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / steps
+    res = dict(workload=f'W+ latent inversion, 1024 px, Adam lr 0.01, pixel MSE, batch {batch}, bf16 (BASELINE configs[3])', batch=batch,
+               steps=steps, ms_per_step=ms, steps_per_s=1e3 / ms, image_steps_per_s=batch * 1e3 / ms, loss_first=losses[0],
+               loss_last=losses[-1], peak_mem_gib=torch.cuda.max_memory_allocated(dev) / 2 ** 30)
+    del gen, inv, target
+    torch.cuda.empty_cache()
+    return res
+
+
+def gpu_reference_leg(state, dev, batch=4, steps=3):
+    """The reference's arithmetic for the same pipeline ON THE SAME B200: the oracle port (plain PyTorch ops: ATen / cuDNN grouped
+    convolutions, upfirdn2d_native, unfused elementwise passes -- what the reference's default branch executes, SURVEY finding 2),
+    fp32, TF32 off, batch 4.  The like-for-like bar for this library's kernels; the oracle is only the thing timed here."""
+    import torch
+    from oracle import ood as oood
+    from ood_gan_inversion_b200.synth import synthetic_faces
+    tf = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        x = synthetic_faces(batch, SIZE, seed=2, device=dev)
+        for _ in range(2):
+            oood.ood_forward(state, x, size=SIZE, strict_rng=False)
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            oood.ood_forward(state, x, size=SIZE, strict_rng=False)
+        e1.record()
+        torch.cuda.synchronize(dev)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf
+    ms = e0.elapsed_time(e1) / steps
+    return dict(value=batch * 1e3 / ms, unit=UNIT, ms_per_step=ms, batch=batch, steps=steps, dtype='f32', tf32=False,
+                kind='oracle port on the same GPU (ATen/cuDNN), eager launches')
+
+
+def parity_leg(net, state, x, dev, seed=123):
+    """The benched batch against the fp32 oracle on the same device (TF32 off, same seed and RNG call order => identical noise),
+    outside every timed region: north_star's bf16 tolerances are max-abs < 2e-2 and PSNR >= 40 dB on the image."""
+    import math
+    import torch
+    from oracle import ood as oood
+    tf = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    strict = net.strict_rng
+    try:
+        net.strict_rng = True
+        torch.manual_seed(seed)
+        out, lats = net(x)
+        aligns = {k: v for k, v in net.aligns.items()}
+        torch.manual_seed(seed)
+        ref, rlats, raligns = oood.ood_forward(state, x, size=SIZE, strict_rng=True)
+        mse = float(((out - ref) ** 2).mean())
+        res = dict(batch=int(x.shape[0]), max_abs=float((out - ref).abs().max()), psnr=10 * math.log10(4.0 / max(mse, 1e-30)),
+                   lats_max_abs=float((lats - rlats).abs().max()), mask_max_abs=float((aligns[1024] - raligns[1024]).abs().max()),
+                   fields_max_abs={str(k): float((aligns[k] - raligns[k]).abs().max()) for k in (1, 2, 3, 4)},
+                   tolerance=dict(max_abs=2e-2, psnr=40.0), against='oracle port, fp32, TF32 off, same device, same seed (strict RNG order)')
+        res['ok'] = bool(res['max_abs'] < 2e-2 and res['psnr'] >= 40.0)
+    finally:
+        net.strict_rng = strict
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf
+    return res
+
+
+def main_config(world, batch, launch):
+    """`config` of the JSON line (both arms print the same one): BASELINE configs[1]."""
+    return dict(workload=WORKLOAD, batch_per_gpu=batch, global_batch=batch * world, size=SIZE, cycle_align=2, mod_size=256,
+                l2='inputs (201 MB/step) exceed the 126 MB L2', launch=launch,
+                parallelism=f'independent image shards x{world}, no collective',
+                weights='random-init (reference init + non-zero noise weights), synthetic smooth faces')
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -220,8 +412,15 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--ncu', action='store_true', help='run warm-up, then ONE step between cudaProfilerStart/Stop and exit '
                     '(for `ncu --profile-from-start off`; never a bench value)')
-    ap.add_argument('--u8-io', action='store_true', help='also time the byte-format serving loop (imgio.ByteServing: uint8 BGR frames '
-                    'across PCIe both ways, 3 instead of 12 bytes per pixel) and report it as "e2e_u8"; N=1 only')
+    ap.add_argument('--u8-io', action='store_true', help='(default on; kept for compatibility) time the byte-format serving loop')
+    ap.add_argument('--no-u8-io', action='store_true', help='skip the byte-format serving loop (imgio.ByteServing: uint8 BGR frames '
+                    'across PCIe both ways, 3 instead of 12 bytes per pixel), reported as "e2e_u8"')
+    ap.add_argument('--global-batch', type=int, default=0, help='BASELINE configs[2]: this many images per step split over the ranks '
+                    '(sharding.shard_bounds) and run in chunks of <= --chunk; value = images / max-rank time (strong scaling). '
+                    'Without it the main line is configs[1] (16 images per GPU, weak scaling) and a short configs[2] leg is '
+                    'reported under "config3"')
+    ap.add_argument('--chunk', type=int, default=32, help='largest per-GPU micro-batch of the sharded batch (SURVEY 8d: <= 32)')
+    ap.add_argument('--no-extra-legs', action='store_true', help='skip the config3 / config4 / gpu_reference / parity legs')
     ap.add_argument('--no-graph', action='store_true', help='time eager launches instead of a CUDA-graph replay of the step')
     ap.add_argument('--profile', action='store_true', help='print a torch.profiler kernel table for one step (not a bench value)')
     args = ap.parse_args()
@@ -232,18 +431,21 @@ def main():
     if args.impl == 'reference':
         if rank != 0:
             return 0
-        r = cpu_reference(max(1, args.steps), max(0, min(args.warmup, 1)))
+        os.environ['CUDA_VISIBLE_DEVICES'] = ''                  # the reference's CPU branch; also keeps its import from JIT-building
+        r = cpu_reference(max(1, args.steps), max(0, args.warmup))
         line = dict(metric=METRIC, value=r['value'], unit=UNIT, impl='reference', n_gpus=args.gpus, steps=args.steps,
-                    warmup=min(args.warmup, 1), ms_per_step=r['ms_per_step'], higher_is_better=True, scaling='weak',
+                    warmup=args.warmup, ms_per_step=r['ms_per_step'], higher_is_better=True, scaling='weak',
                     vs_baseline=None, dtype='f32', data='synthetic',
-                    config=dict(workload=WORKLOAD, note='reference arm: the reference\'s own CPU arithmetic (native upfirdn2d / '
-                                'fused_act branch, oracle port) on the host cores, 1 image per step'),
-                    cpu_baseline=dict(value=r['value'], unit=UNIT, cores=r['cores'], kind='port', sample=r['sample']),
+                    config=main_config(args.gpus, BATCH, 'host CPU, all cores'),
+                    cpu_baseline=dict(value=r['value'], unit=UNIT, cores=r['cores'], kind=r['kind'], sample=r['sample'],
+                                      note='each step is a bounded sample of the workload: 1 image of the same 1024px pipeline '
+                                           '(a 16-image step takes ~25 s on these cores); images/s is per image either way'),
                     e2e=dict(value=r['value'], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
-        try:
-            line['cpu_baseline']['ops'] = cpu_op_baselines()['ops']
-        except Exception as exc:                                 # a reported baseline must not cost the line
-            line['cpu_baseline']['ops_error'] = f'{type(exc).__name__}: {exc}'[:300]
+        if not args.no_cpu_baseline:
+            try:
+                line['cpu_baseline']['ops'] = cpu_op_baselines()['ops']
+            except Exception as exc:                                 # a reported baseline must not cost the line
+                line['cpu_baseline']['ops_error'] = f'{type(exc).__name__}: {exc}'[:300]
         print(json.dumps(line))
         return 0
 
@@ -279,6 +481,38 @@ def main():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def reduce_max(ms_local):
+        t = torch.tensor([ms_local], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    if args.global_batch > 0:
+        # BASELINE configs[2] as the main line: strong scaling of one sharded batch (no per-kernel legs, no CPU baseline)
+        for _ in range(max(args.warmup, 3)):
+            torch.manual_seed(1000 + rank)
+            net(x_dev)
+        with ClockSampler(local_rank) as clk:
+            r = sharded_batch_leg(net, args.global_batch, args.chunk, args.steps, rank, world, dev, barrier, reduce_max)
+        if rank == 0:
+            line = dict(metric=METRIC, value=r['value'], unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
+                        ms_per_step=r['ms_per_pass'], higher_is_better=True, scaling='strong', vs_baseline=None, dtype='bf16',
+                        data='synthetic', clocks=clk.summary(),
+                        config=dict(workload=f'Full OOD inversion inference 1024px, batch {args.global_batch} sharded over {world} B200 '
+                                    f'in chunks of <= {args.chunk} (BASELINE configs[2])', global_batch=args.global_batch,
+                                    images_per_rank=r['images_per_rank'], chunk=r['chunk'], size=SIZE, cycle_align=2, mod_size=256,
+                                    l2='every chunk (>= 100 MB of input, GBs of activations) exceeds the 126 MB L2',
+                                    launch='CUDA-graph replay per chunk', parallelism=f'independent image shards x{world}, no collective'),
+                        e2e=dict(value=r['e2e']['value'], unit=UNIT, ms_per_step=r['e2e']['ms_per_pass'],
+                                 h2d_bytes_per_step=r['e2e']['h2d_bytes_per_pass_per_rank'] * world,
+                                 d2h_bytes_per_step=r['e2e']['d2h_bytes_per_pass_per_rank'] * world) if 'e2e' in r else None,
+                        gpu_launches=int(_lib.lib().ood_launch_count()))
+            sys.stdout.flush()
+            os.write(json_fd, (json.dumps(line) + '\n').encode())
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
 
     def step_resident():
         torch.manual_seed(1000 + rank)
@@ -425,7 +659,7 @@ def main():
 
     # ---------------- optional timed region 3: the same serving loop on the reference script's byte formats -----------------
     e2e_u8 = None
-    if args.u8_io and world == 1 and pipe is not None:
+    if not args.no_u8_io and pipe is not None:
         try:
             from ood_gan_inversion_b200 import imgio
             from ood_gan_inversion_b200.graphs import PipelinedForward
@@ -444,13 +678,23 @@ def main():
             pipe8.synchronize()
             e1.record()
             barrier()
-            ms8 = e0.elapsed_time(e1)
-            e2e_u8 = dict(value=args.steps * B / (ms8 * 1e-3), unit=UNIT, ms_per_step=ms8 / args.steps,
+            ms8 = reduce_max(e0.elapsed_time(e1))
+            del pipe8
+            e2e_u8 = dict(value=world * args.steps * B / (ms8 * 1e-3), unit=UNIT, ms_per_step=ms8 / args.steps,
                           h2d_bytes_per_step=frames_host.numel(), d2h_bytes_per_step=out8_host.numel(),
                           note='uint8 BGR frames in and out (run_ood_faceGAN_inversion.py:158-174 formats), converters inside the captured step')
         except Exception as exc:
+            if world > 1:
+                raise                                   # a rank that drops out of the collectives would hang the others
             e2e_u8 = dict(error=f'{type(exc).__name__}: {exc}'[:300])
             torch.cuda.synchronize()
+
+    # ---------------- BASELINE configs[2]: one 256-image batch sharded over the ranks in chunks of <= 32 (every N) -------------
+    config3 = None
+    if not args.no_extra_legs:
+        pipe = graphed = None                       # frees the three captured configs[1] graphs and their pools
+        torch.cuda.empty_cache()
+        config3 = sharded_batch_leg(net, 256, args.chunk, min(args.steps, 10), rank, world, dev, barrier, reduce_max)
 
     if rank != 0:
         if world > 1:
@@ -482,9 +726,7 @@ def main():
     line = dict(metric=METRIC, value=world * args.steps * B / (ms_max * 1e-3), unit=UNIT, n_gpus=world, steps=args.steps,
                 warmup=max(args.warmup, 3), ms_per_step=step_ms, higher_is_better=True, scaling='weak', vs_baseline=None,
                 dtype='bf16', data='synthetic',
-                config=dict(workload=WORKLOAD, batch_per_gpu=B, global_batch=B * world, size=SIZE, cycle_align=2, mod_size=256,
-                            l2='inputs (201 MB/step) exceed the 126 MB L2', launch=graph_note, parallelism=f'independent image shards x{world}, no collective',
-                            weights='random-init (reference init + non-zero noise weights), synthetic smooth faces'),
+                config=main_config(world, B, graph_note),
                 clocks=clk.summary(),
                 e2e=dict(value=world * args.steps * B / (ms_e2e * 1e-3), unit=UNIT, h2d_bytes_per_step=x_host.numel() * 4,
                          d2h_bytes_per_step=out_host.numel() * 4, ms_per_step=ms_e2e / args.steps),
@@ -502,10 +744,35 @@ def main():
                 kernels=kern)
     if e2e_u8 is not None:
         line['e2e_u8'] = e2e_u8
+    if config3 is not None:
+        line['config3'] = config3
+    if world == 1 and not args.no_extra_legs:
+        # single-GPU context legs (rank 0 only; each guarded: a reported extra must not cost the line)
+        state_dev = {k: v.detach() for k, v in net.state_dict().items()}
+        for key, leg in (('parity', lambda: parity_leg(net, state_dev, x_dev, dev)),
+                         ('gpu_reference', lambda: gpu_reference_leg(state_dev, dev)),
+                         ('config4', lambda: inversion_leg(dev))):
+            try:
+                torch.cuda.empty_cache()
+                line[key] = leg()
+            except Exception as exc:
+                line[key] = dict(error=f'{type(exc).__name__}: {exc}'[:300])
+                torch.cuda.synchronize()
+        sg.set_precision('bf16')
+        del state_dev
     if world == 1 and not args.no_cpu_baseline:
-        sd = {k: v.detach().float().cpu() for k, v in net.state_dict().items()}
-        r = cpu_reference(2, 1, 1, state=sd)
-        line['cpu_baseline'] = dict(value=r['value'], unit=UNIT, cores=r['cores'], kind='port', sample=r['sample'])
+        # the reference's CPU path, timed on this box's host cores by a child process that sees no GPU (--impl reference)
+        try:
+            env = dict(os.environ, CUDA_VISIBLE_DEVICES='')
+            o = subprocess.run([sys.executable, os.path.abspath(__file__), '--impl', 'reference', '--steps', '2', '--warmup', '1',
+                                '--no-cpu-baseline'], capture_output=True, text=True, timeout=600, env=env)
+            rl = json.loads([l for l in o.stdout.splitlines() if l.startswith('{')][-1])
+            line['cpu_baseline'] = {k: rl['cpu_baseline'][k] for k in ('value', 'unit', 'cores', 'kind', 'sample')}
+        except Exception as exc:
+            sd = {k: v.detach().float().cpu() for k, v in net.state_dict().items()}
+            r = cpu_reference(2, 1, 1, state=sd, prefer_reference=False)
+            line['cpu_baseline'] = dict(value=r['value'], unit=UNIT, cores=r['cores'], kind=r['kind'], sample=r['sample'],
+                                        note=f'child process failed ({type(exc).__name__}); oracle port in-process')
         try:
             line['cpu_baseline']['ops'] = cpu_op_baselines(dev)['ops']
         except Exception as exc:                                 # a reported baseline must not cost the bench line

@@ -234,11 +234,10 @@ static int launch_blur_rows(const CUtensorMap &tm, BlurRowsParams &p, cudaStream
     using Cfg = BrCfg<T>;
     constexpr int SMEM = NG * Cfg::SLOT_BYTES + 2 * NG * 8 + 128;
     auto kern = blur_rows_kernel<T, NG, OUT>;
-    static bool attr = false;
-    if (!attr) {
+    static DeviceOnce attr;
+    if (attr.first()) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
         if (e != cudaSuccess) { set_error("blur_act rows: smem attribute: %s", cudaGetErrorString(e)); return OOD_ERR_CUDA; }
-        attr = true;
     }
     int dev = 0, sms = kNumSMs;
     cudaGetDevice(&dev);

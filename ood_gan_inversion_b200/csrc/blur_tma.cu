@@ -185,11 +185,10 @@ static int launch_blur_tma(const CUtensorMap &tm, const BlurTmaParams &p, cudaSt
     constexpr int STAGE_STRIDE = (STAGE_BYTES + 1023) & ~1023;
     constexpr int SMEM = 2 * STAGE_STRIDE + 1024 + 64;
     auto kern = blur_tma_kernel<T, TIN>;
-    static bool attr = false;
-    if (!attr) {
+    static DeviceOnce attr;
+    if (attr.first()) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
         if (e != cudaSuccess) { set_error("blur_act tma: smem attribute: %s", cudaGetErrorString(e)); return OOD_ERR_CUDA; }
-        attr = true;
     }
     int dev = 0, sms = kNumSMs;
     cudaGetDevice(&dev);

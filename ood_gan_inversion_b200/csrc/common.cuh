@@ -24,6 +24,21 @@ static inline int pixwalk_blocks_per_sm(int dflt) {
     return v > 0 ? v : dflt;
 }
 
+// One-time per-DEVICE set-up (cudaFuncSetAttribute is per context): `static DeviceOnce once; if (once.first()) {...}`.
+// A process that drives several GPUs (the reference's ops take the current device per call, upfirdn2d_kernel.cu:143-145)
+// gets the dynamic-shared-memory opt-in on each of them.
+struct DeviceOnce {
+    bool done[64] = {};
+    bool first() {
+        int d = 0;
+        cudaGetDevice(&d);
+        d &= 63;
+        if (done[d]) return false;
+        done[d] = true;
+        return true;
+    }
+};
+
 #define OOD_REQUIRE(cond, ...)              \
     do {                                    \
         if (!(cond)) {                      \

@@ -379,11 +379,10 @@ static int launch(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensor
                   cudaStream_t st) {
     using C = Cfg<CI, CO>;
     auto kern = conv_rows_kernel<CI, CO>;
-    static bool attr = false;
-    if (!attr) {
+    static DeviceOnce attr;
+    if (attr.first()) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem);
         if (e != cudaSuccess) { set_error("conv3x3 rows: smem attribute: %s", cudaGetErrorString(e)); return OOD_ERR_CUDA; }
-        attr = true;
     }
     int dev = 0, sms = kNumSMs;
     cudaGetDevice(&dev);

@@ -532,11 +532,10 @@ static int launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, const TcPar
     auto kern = conv_tc_kernel<BN, BK, SEED, STATS, EPW>;
     constexpr int kSmem = Cfg::kSmemBytes + (STATS ? Cfg::kStatBytes : 0);
     static_assert(kSmem <= 227 * 1024, "shared memory budget");
-    static bool attr_set = false;
-    if (!attr_set) {
+    static DeviceOnce attr_set;
+    if (attr_set.first()) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
         if (e != cudaSuccess) { set_error("conv3x3 tc: smem attribute: %s", cudaGetErrorString(e)); return OOD_ERR_CUDA; }
-        attr_set = true;
     }
     int dev = 0, sms = kNumSMs;
     cudaGetDevice(&dev);

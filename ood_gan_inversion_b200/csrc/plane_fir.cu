@@ -188,11 +188,10 @@ static int launch_plane_fir(const PlaneFirParams &p0, int64_t planes, cudaStream
     constexpr int PF_T = SW / 2, PF_SW = SW;
     PlaneFirParams p = p0;
     auto kern = plane_fir_kernel<MODE, SW>;
-    static bool attr = false;
-    if (!attr) {
+    static DeviceOnce attr;
+    if (attr.first()) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
         if (e != cudaSuccess) { set_error("upfirdn2d plane: smem attribute: %s", cudaGetErrorString(e)); return OOD_ERR_CUDA; }
-        attr = true;
     }
     const int unit_h = MODE == 2 ? p.in_h : p.out_h, unit_w = MODE == 2 ? p.in_w : p.out_w;
     const int strips = ceil_div(unit_w, PF_SW);

@@ -71,13 +71,66 @@ def _ptr(t):
 
 
 def _stream():
+    """The current torch stream of the CURRENT device: every public wrapper runs under _device_guard, which makes the
+    device of its tensor arguments current first (the reference's ops do the same: cudaGetDevice + getCurrentCUDAStream,
+    upfirdn2d_kernel.cu:143-145)."""
     return torch.cuda.current_stream().cuda_stream
 
 
 def _cuda(*ts):
+    """Every tensor argument is a CUDA tensor, all on ONE device, and that device is current (see _device_guard)."""
+    dev = None
     for t in ts:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise RuntimeError('ood_gan_inversion_b200 is CUDA-only: got a CPU tensor (there is no CPU fallback)')
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise RuntimeError(f'ood_gan_inversion_b200: tensor arguments on different devices ({dev} and {t.device})')
+    if dev is not None and dev.index != torch.cuda.current_device():
+        raise RuntimeError(f'ood_gan_inversion_b200: tensors on {dev} but the current device is cuda:{torch.cuda.current_device()} '
+                           '(internal: a wrapper ran outside _device_guard)')
+
+
+def _first_cuda_device(args, kwargs):
+    for a in list(args) + list(kwargs.values()):
+        if isinstance(a, torch.Tensor):
+            if a.is_cuda:
+                return a.device
+        elif isinstance(a, (list, tuple)):
+            for e in a:
+                if isinstance(e, torch.Tensor) and e.is_cuda:
+                    return e.device
+    return None
+
+
+def _device_guard(fn):
+    """Run `fn` with the device of its first CUDA tensor argument current, so that launches, the stream handed to the C ABI
+    and the tensors' memory agree when a process drives several GPUs (a model on cuda:1 while cuda:0 is current)."""
+    import functools
+
+    @functools.wraps(fn)
+    def guarded(*args, **kwargs):
+        dev = _first_cuda_device(args, kwargs)
+        if dev is None or dev.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+    return guarded
+
+
+def _noise_bstride(noise, b, oh, ow):
+    """Batch stride of an injected-noise plane [B|1, 1, oh, ow] fp32 (model.py:277-283 broadcasts a single plane)."""
+    if noise is None:
+        return 0
+    if noise.dtype != torch.float32 or not noise.is_contiguous():
+        raise RuntimeError('ood_gan_inversion_b200: noise must be a contiguous float32 tensor')
+    if noise.shape[0] not in (1, b) or tuple(noise.shape[-2:]) != (oh, ow) or noise.numel() != noise.shape[0] * oh * ow:
+        raise RuntimeError(f'ood_gan_inversion_b200: noise of shape {tuple(noise.shape)} does not fit a batch of {b} planes of {oh}x{ow} '
+                           '(expected [B,1,H,W] or [1,1,H,W])')
+    return 0 if noise.shape[0] == 1 else oh * ow
 
 
 def _f32c(t):
@@ -261,10 +314,7 @@ def conv3x3(x, weight, cout, transposed=False, impl=0, d=None, noise=None, noise
     else:
         y = torch.empty(b, oh, ow, cout, device=x.device, dtype=torch.float32 if out_f32 else x.dtype) if want_y else None
     ys = torch.empty(b, oh, ow, cout, device=x.device, dtype=x.dtype) if want_ys else None
-    nbs = 0
-    if noise is not None:
-        assert noise.dtype == torch.float32 and noise.is_contiguous() and noise.shape[-2:] == (oh, ow)
-        nbs = 0 if noise.shape[0] == 1 else oh * ow
+    nbs = _noise_bstride(noise, b, oh, ow)
     a = ConvArgs(_ptr(x), _ptr(weight), _ptr(y), _ptr(ys), _ptr(d), _ptr(noise), nbs, _ptr(noise_w), _ptr(bias), _ptr(s_next),
                  b, h, w, cin, cout, int(transposed), 2 if prelu is not None else int(act), impl, _dt(x), int(out_f32), _ptr(prelu))
     a.groups, a.in_shared = int(groups), int(bool(in_shared))
@@ -319,10 +369,7 @@ def blur_act(t, taps, d=None, noise=None, noise_w=None, bias=None, s_next=None, 
     img = mk() if want_img else None
     y = mk() if (act and want_y) else None
     ys = mk() if (act and want_ys) else None
-    nbs = 0
-    if noise is not None:
-        assert noise.dtype == torch.float32 and noise.is_contiguous()
-        nbs = 0 if noise.shape[0] == 1 else oh * ow
+    nbs = _noise_bstride(noise, b, oh, ow)
     a = BlurActArgs(_ptr(t), int(t.dtype == torch.float32 and dtype != torch.float32), _ptr(img), _ptr(y), _ptr(ys), _ptr(d),
                     _ptr(noise), _ptr(noise_w), _ptr(bias), _ptr(s_next), nbs, (C.c_float * 4)(*taps), b, ih, iw, c,
                     int(act), F32 if dtype == torch.float32 else BF16, int(pad[0]), int(pad[1]))
@@ -340,7 +387,7 @@ def noise_act(img, noise, noise_w, bias, s_next=None, want_y=True, want_ys=False
     b, h, w, c = img.shape
     y = torch.empty_like(img) if want_y else None
     ys = torch.empty_like(img) if want_ys else None
-    nbs = 0 if (noise is None or noise.shape[0] == 1) else h * w
+    nbs = _noise_bstride(noise, b, h, w)
     nout = (y is not None) + (ys is not None)
     with _timed('noise_act', b * h * w * (c * _esize(img) * (1 + nout) + 4)):
         check(_lib.lib().ood_noise_act(_ptr(img), _ptr(y), _ptr(ys), _ptr(noise), nbs, _ptr(noise_w), _ptr(bias), _ptr(s_next),
@@ -413,7 +460,7 @@ def act_bwd(gy, y, d, bias, noise, noise_w):
     b, h, w, c = y.shape
     g = torch.empty_like(y)
     gd = torch.empty(b, c, device=y.device, dtype=torch.float32)
-    nbs = 0 if (noise is None or noise.shape[0] == 1) else h * w
+    nbs = _noise_bstride(noise, b, h, w)
     ws = _bwd_ws(b, h * w, c, 1, y.device)          # kept alive until the launch has been queued
     with _timed('act_bwd', b * h * w * c * _esize(y) * 3):
         check(_lib.lib().ood_act_bwd(_ptr(gy), _ptr(y), _ptr(d), _ptr(bias), _ptr(noise), nbs, _ptr(noise_w), _ptr(g),
@@ -670,3 +717,16 @@ def mask_blend_bwd(fields, x, gen, gout, want_gx=True, want_ggen=True):
 
 def conv_scale(cin, k):
     return 1.0 / math.sqrt(cin * k * k)
+
+
+# ---- device guard over every public wrapper (a model on cuda:1 in a process whose current device is cuda:0) ----
+def _install_device_guard():
+    import types
+    g = globals()
+    skip = {'profile_begin', 'profile_end', 'fir_taps'}
+    for name, obj in list(g.items()):
+        if isinstance(obj, types.FunctionType) and obj.__module__ == __name__ and not name.startswith('_') and name not in skip:
+            g[name] = _device_guard(obj)
+
+
+_install_device_guard()

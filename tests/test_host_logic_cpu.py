@@ -205,7 +205,11 @@ def test_bench_reference_arm_contract():
     assert d['higher_is_better'] is True and d['vs_baseline'] is None and d['gpu_launches'] == 0
     assert d['value'] > 0 and d['e2e'] == dict(value=d['value'], unit='images/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0)
     cb = d['cpu_baseline']
-    assert cb['kind'] == 'port' and cb['cores'] >= 1 and cb['value'] == d['value'] and 'image' in cb['sample']
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    staged = os.path.isfile(os.path.join(root, 'baseline', '_ref', 'src', 'archs', 'OOD_faceGAN_e4e_arch.py'))
+    # the unmodified reference when __graft_entry__.build() staged it (baseline/_ref, git-ignored), else the oracle port
+    assert cb['kind'] == ('reference' if staged else 'port') and cb['cores'] >= 1 and cb['value'] == d['value'] and 'image' in cb['sample']
+    assert d['config']['workload'].startswith('E4E encoder + StyleGAN2 1024px') and d['config']['global_batch'] == 16
     ops = {o['op']: o for o in cb['ops']}
     assert len(ops) == 5 and all(o['cpu_ms'] > 0 for o in ops.values())
     assert any('Generator(256)' in k for k in ops) and 'fused_leaky_relu' in ops
