@@ -462,7 +462,6 @@ def main():
     os.dup2(2, 1)
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
-    torch.backends.cudnn.benchmark = True
     torch.set_grad_enabled(False)
 
     from ood_gan_inversion_b200 import _lib, kernels as K, stylegan as sg

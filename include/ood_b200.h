@@ -32,6 +32,7 @@ extern "C" {
 
 #define OOD_F32 0
 #define OOD_BF16 1
+#define OOD_F16 2   /* IEEE half storage: the encoder path (normalised activations); conv3x3 impl 0, in_stats, se_residual, bicubic_up_add, thumbnail_nhwc, pack_conv_weight */
 
 #define OOD_OK 0
 #define OOD_ERR_ARG (-1)      /* bad argument / unsupported configuration (never a silent no-op) */
@@ -63,6 +64,13 @@ int ood_fused_bias_act(const void *in, const void *bias, const void *refer, void
 /* grad_bias[c] = sum over batch and inner of g[b][c][inner]; fp32 output.  (fused_act.py:38-43) */
 int ood_bias_grad(const void *g, float *grad_bias, int64_t batch, int channels, int64_t inner, int dtype,
                   void *stream);
+
+/* ---- a13: the encoder's input thumbnail.  OOD_faceGAN_e4e_arch.py:256 `F.interpolate(x, (256, 256), mode='bilinear')`
+ *      (align_corners=False) fused with the layout change, cast and channel padding of the encoder's first convolution operand:
+ *      in fp32 NCHW [B,3,H,W] -> out `dtype` NHWC [B,oh,ow,cp] with channels 3..cp-1 zero (cp = 32).  ATen's arithmetic
+ *      (upsample_bilinear2d): src = scale*(dst+0.5)-0.5 clamped at 0; at 1024 -> 256 the mean of the 2x2 centre pixels of a 4x4 block. */
+int ood_thumbnail_nhwc(const float *in, void *out, int batch, int channels, int h, int w, int oh, int ow, int cp, int dtype,
+                       void *stream);
 
 /* ---- layout: NCHW fp32 <-> NHWC storage type, optional per-(b,c) scale (the style modulation of the NEXT conv).
  *      in_batch_stride 0 broadcasts one sample (ConstantInput, model.py:295-305). */
@@ -97,6 +105,8 @@ int ood_pack_conv_weight(const float *w, void *out, int cout, int cin, int taps,
  *                       (src/ops/e4e/encoders/psp_encoders.py:41-48, helpers.py:488-491).
  *      transposed == 4: 1x1 convolution, weight pack [1][Co][Ci] (bf16, K-major): lateral / feature convolutions
  *                       (psp_encoders.py:153-154, e4e_arch.py feats_conv) and the per-tap projection consumed by ood_tap_sum.
+ *      transposed == 6: 1x1 stride-2 convolution, out [B,(H-1)/2+1,(W-1)/2+1,Co], weight pack [1][Co][Ci]: the shortcut
+ *                       convolutions of the encoder's down-sampling bottlenecks (e4e helpers.py:483-486).
  *      transposed == 5: form 1 with the four output-parity phases fused into one GEMM (tcgen05 path; raw accumulators like
  *                       form 1).  Weight pack [4 shifts][4*Co][Ci] bf16, shift t = (dy, dx) = (-(t>>1), -(t&1)), row
  *                       (2*py + px)*Co + o holds W[o][:][ky][kx] of the tap of output parity (py, px) that reads input
@@ -106,7 +116,7 @@ int ood_pack_conv_weight(const float *w, void *out, int cout, int cin, int taps,
  *      Epilogue (stride-1 only; any pointer may be NULL to skip that term):
  *          v  = acc * d[b,o] + noise_w * noise[b,y,x] + bias[o];  y = act ? lrelu(v,0.2)*sqrt2 : v
  *          out_y  = y            out_ys = y * s_next[b,o]
- *      impl 0: tcgen05/TMEM/TMA implicit GEMM (dtype must be OOD_BF16, weights from ood_pack_conv_weight bf16)
+ *      impl 0: tcgen05/TMEM/TMA implicit GEMM (dtype OOD_BF16 or OOD_F16, weights from ood_pack_conv_weight in the same type)
  *      impl 1: fp32 SIMT implicit GEMM (dtype OOD_F32, weights packed ci_major_out=1).
  *      noise: fp32 [B or 1][H][W] with batch stride noise_bstride (0 = shared).  noise_w: device scalar. */
 typedef struct {
@@ -121,7 +131,7 @@ typedef struct {
     const float *bias;     /* [Co] or NULL */
     const float *s_next;   /* [B,Co]; required iff out_ys */
     int batch, h, w, cin, cout;
-    int transposed;        /* 0 stride-1 conv | 1 stride-2 transposed conv | 2 stride-2 valid conv (data gradient of 1) | 3 stride-2 pad-1 conv | 4 1x1 conv | 5 = 1 with fused phases */
+    int transposed;        /* 0 stride-1 conv | 1 stride-2 transposed conv | 2 stride-2 valid conv (data gradient of 1) | 3 stride-2 pad-1 conv | 4 1x1 conv | 5 = 1 with fused phases | 6 1x1 stride-2 conv */
     int act;               /* 0 none | 1 leaky-ReLU(0.2)*sqrt2 | 2 PReLU(prelu_slope[o]) (AlignNet, shared-weight mode) */
     int impl;              /* 0 tcgen05 | 1 simt */
     int dtype;             /* storage type of in / out */
@@ -156,6 +166,9 @@ typedef struct {
      * stats_ws: ood_conv3x3_stats_workspace() bytes. */
     float *stats_out, *stats_ws;
     float stats_eps;
+    /* storage type of out_y / out_ys when it differs from `dtype` (tcgen05 path): 0 = same as dtype, OOD_BF16 or OOD_F16.  The
+     * encoder's features are half precision, the pipeline that consumes feats_conv's output is bf16 (e4e_arch.py:109-113). */
+    int out_dtype;
 } ood_conv3x3_args;
 int ood_conv3x3(const ood_conv3x3_args *args_host, void *stream);
 /* bytes of a tile-order fp32 tensor for the tcgen05 path (0 when the arguments are outside that path) */

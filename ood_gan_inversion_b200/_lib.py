@@ -8,7 +8,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'libood_b200.so')
 
-F32, BF16 = 0, 1
+F32, BF16, F16 = 0, 1, 2
 
 c_void_p, c_int, c_i64, c_float = C.c_void_p, C.c_int, C.c_int64, C.c_float
 
@@ -19,7 +19,7 @@ class ConvArgs(C.Structure):
                 ('s_next', c_void_p), ('batch', c_int), ('h', c_int), ('w', c_int), ('cin', c_int), ('cout', c_int),
                 ('transposed', c_int), ('act', c_int), ('impl', c_int), ('dtype', c_int), ('out_f32', c_int), ('prelu_slope', c_void_p),
                 ('rgb_w', c_void_p), ('rgb_bias', c_void_p), ('rgb_skip', c_void_p), ('rgb_out', c_void_p), ('rgb_taps', c_float * 4),
-                ('groups', c_int), ('in_shared', c_int), ('acc_in', c_void_p), ('tiled', c_int), ('stats_out', c_void_p), ('stats_ws', c_void_p), ('stats_eps', c_float)]
+                ('groups', c_int), ('in_shared', c_int), ('acc_in', c_void_p), ('tiled', c_int), ('stats_out', c_void_p), ('stats_ws', c_void_p), ('stats_eps', c_float), ('out_dtype', c_int)]
 
 
 class BlurActArgs(C.Structure):
@@ -39,6 +39,7 @@ _SIGS = {
                             c_int, c_void_p], c_int),
     'ood_bias_grad': ([c_void_p, c_void_p, c_i64, c_int, c_i64, c_int, c_void_p], c_int),
     'ood_nchw_to_nhwc': ([c_void_p, c_i64, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p], c_int),
+    'ood_thumbnail_nhwc': ([c_void_p, c_void_p] + [c_int] * 8 + [c_void_p], c_int),
     'ood_nhwc_to_nchw': ([c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p], c_int),
     'ood_nhwc_scale': ([c_void_p, c_void_p, c_void_p, c_int, c_int, c_i64, c_int, c_void_p], c_int),
     'ood_modulation': ([c_void_p, c_i64, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_int, c_int, c_int,

@@ -177,32 +177,34 @@ class ood_faceGAN_e4e(nn.Module):
         bf16 = sg.get_precision() == 'bf16'
         with torch.no_grad():
             self.encoder.eval()
-            small = F.interpolate(x, (256, 256), mode='bilinear')
-            with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
-                if bf16:
-                    from . import encoder_fast, encoder_infer
-                    key = (x.device, encoder_infer.state_key(self.encoder))
-                    if getattr(self, '_enc_infer', None) is None or self._enc_infer[0] != key:
-                        object.__setattr__(self, '_enc_infer', (key, encoder_fast.FastEncoder(self.encoder)))
-                    enc = self._enc_infer[1]
-                    enc.progressive_stage = self.encoder.progressive_stage
-                    w, feats = enc(small, return_feats=True)
-                else:
+            if bf16:
+                from . import encoder_fast, encoder_infer
+                key = (x.device, encoder_infer.state_key(self.encoder))
+                if getattr(self, '_enc_infer', None) is None or self._enc_infer[0] != key:
+                    object.__setattr__(self, '_enc_infer', (key, encoder_fast.FastEncoder(self.encoder)))
+                enc = self._enc_infer[1]
+                enc.progressive_stage = self.encoder.progressive_stage
+                # bilinear 1024 -> 256 thumbnail, NHWC, bf16, channels padded to the first convolution's K granule: one kernel
+                w, feats = enc(None, return_feats=True, thumb=K.thumbnail_nhwc(x.detach(), dtype=encoder_fast.ENC_DT))
+            else:
+                small = F.interpolate(x, (256, 256), mode='bilinear')
+                with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
                     w, feats = self.encoder(small, return_feats=True)
         return w.float(), feats
 
     def _feats_conv_nhwc(self, i, feat):
         """feats_conv[i] (1x1 convolution + bias, e4e_arch.py:109-113) on the tcgen05 1x1 form; NCHW view of an NHWC result."""
         conv = self.feats_conv[i]
-        key = (conv.weight.device, conv.weight._version, conv.bias._version)
+        dt = feat.dtype if feat.dtype in (torch.bfloat16, torch.float16) else torch.bfloat16      # the encoder's storage type
+        key = (conv.weight.device, conv.weight._version, conv.bias._version, dt)
         cache = self.__dict__.setdefault('_fc_cache', {})
         if cache.get(i, (None,))[0] != key:
             with torch.no_grad():
-                cache[i] = (key, K.pack_conv1x1_weight(conv.weight.detach(), torch.bfloat16, False), conv.bias.detach().float().contiguous())
+                cache[i] = (key, K.pack_conv1x1_weight(conv.weight.detach(), dt, False), conv.bias.detach().float().contiguous())
         _, w, b = cache[i]
         with torch.no_grad():
-            x = feat.to(torch.bfloat16).permute(0, 2, 3, 1).contiguous()
-            y, _ = K.conv3x3(x, w, conv.out_channels, transposed=4, bias=b, tag='encoder_conv')
+            x = feat.to(dt).permute(0, 2, 3, 1).contiguous()          # NCHW view of the encoder's NHWC tensor: no copy
+            y, _ = K.conv3x3(x, w, conv.out_channels, transposed=4, bias=b, tag='encoder_conv', out_dtype=torch.bfloat16)
         return y.permute(0, 3, 1, 2)
 
     def forward(self, x, **kwargs):

@@ -27,7 +27,17 @@ template <> __device__ __forceinline__ void load_pairs<__nv_bfloat16>(const __nv
     const uint4 r = __ldg(reinterpret_cast<const uint4 *>(p));
     dst[0] = unpack_bf16x2(r.x); dst[1] = unpack_bf16x2(r.y); dst[2] = unpack_bf16x2(r.z); dst[3] = unpack_bf16x2(r.w);
 }
+template <> __device__ __forceinline__ void load_pairs<__half>(const __half *p, float2 *dst) {
+    const uint4 r = __ldg(reinterpret_cast<const uint4 *>(p));
+    dst[0] = unpack_f16x2(r.x); dst[1] = unpack_f16x2(r.y); dst[2] = unpack_f16x2(r.z); dst[3] = unpack_f16x2(r.w);
+}
 template <typename T> __device__ __forceinline__ void store_pairs(T *p, const float2 *v);
+template <> __device__ __forceinline__ void store_pairs<__half>(__half *p, const float2 *v) {
+    uint4 r;
+    r.x = pack_f16x2(v[0].x, v[0].y); r.y = pack_f16x2(v[1].x, v[1].y);
+    r.z = pack_f16x2(v[2].x, v[2].y); r.w = pack_f16x2(v[3].x, v[3].y);
+    *reinterpret_cast<uint4 *>(p) = r;
+}
 template <> __device__ __forceinline__ void store_pairs<float>(float *p, const float2 *v) {
     *reinterpret_cast<float4 *>(p) = make_float4(v[0].x, v[0].y, v[1].x, v[1].y);
 }
@@ -44,6 +54,11 @@ template <> __device__ __forceinline__ void round_pairs<float>(float2 *) {}
 template <> __device__ __forceinline__ void round_pairs<__nv_bfloat16>(float2 *v) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) v[j] = unpack_bf16x2(pack_bf16x2(v[j].x, v[j].y));
+}
+
+template <> __device__ __forceinline__ void round_pairs<__half>(float2 *v) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = unpack_f16x2(pack_f16x2(v[j].x, v[j].y));
 }
 
 // ---------------------------------------------------------------------------------------------- statistics
@@ -423,6 +438,7 @@ extern "C" int ood_in_stats(const void *x, const void *y, float *workspace, floa
     cudaStream_t s = (cudaStream_t)stream;
     if (dtype == OOD_F32) return launch_stats<float>(x, y, workspace, stats, batch, pixels, channels, eps, s);
     if (dtype == OOD_BF16) return launch_stats<__nv_bfloat16>(x, y, workspace, stats, batch, pixels, channels, eps, s);
+    if (dtype == OOD_F16) return launch_stats<__half>(x, y, workspace, stats, batch, pixels, channels, eps, s);
     OOD_REQUIRE(false, "in_stats: bad dtype");
 }
 

@@ -1,6 +1,7 @@
 // Shared helpers for libood_b200 kernels (sm_100a only).
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -63,11 +64,29 @@ template <> struct Vec<__nv_bfloat16> {
     float v[8];
 };
 
+template <> struct Vec<__half> {
+    static constexpr int N = 8;
+    float v[8];
+};
+
 __device__ __forceinline__ float to_f32(float x) { return x; }
+__device__ __forceinline__ float to_f32(__half x) { return __half2float(x); }
 __device__ __forceinline__ float to_f32(__nv_bfloat16 x) { return __bfloat162float(x); }
 template <typename T> __device__ __forceinline__ T from_f32(float x);
 template <> __device__ __forceinline__ float from_f32<float>(float x) { return x; }
 template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float x) { return __float2bfloat16_rn(x); }
+// fp16 storage (OOD_F16: the encoder, whose activations are normalised and O(1); 11 significant bits instead of bf16's 8).
+// Conversions saturate to the largest finite half instead of producing inf.
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ float2 unpack_f16x2(uint32_t w) { return __half22float2(*reinterpret_cast<const __half2 *>(&w)); }
+template <> __device__ __forceinline__ __half from_f32<__half>(float x) {
+    const uint32_t r = pack_f16x2(x, 0.f);
+    return __ushort_as_half((unsigned short)(r & 0xffffu));
+}
 
 // ---- packed fp32x2 arithmetic (FFMA2 / FMUL2 / FADD2, sm_100): two lanes per issue slot.  The bandwidth kernels are
 // issue-bound long before they are FMA-pipe-bound (ncu: blur 27 instructions per element at 69 % issue utilisation), so
@@ -101,6 +120,18 @@ template <> __device__ __forceinline__ Vec<__nv_bfloat16> load_vec<__nv_bfloat16
     }
     return o;
 }
+template <> __device__ __forceinline__ Vec<__half> load_vec<__half>(const __half *p) {
+    uint4 r = __ldg(reinterpret_cast<const uint4 *>(p));
+    Vec<__half> o;
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 t = unpack_f16x2(w[i]);
+        o.v[2 * i] = t.x;
+        o.v[2 * i + 1] = t.y;
+    }
+    return o;
+}
 template <typename T> __device__ __forceinline__ void store_vec(T *p, const Vec<T> &x);
 template <> __device__ __forceinline__ void store_vec<float>(float *p, const Vec<float> &x) {
     *reinterpret_cast<float4 *>(p) = make_float4(x.v[0], x.v[1], x.v[2], x.v[3]);
@@ -124,6 +155,15 @@ template <> __device__ __forceinline__ void store_vec<__nv_bfloat16>(__nv_bfloat
     r.y = pack_bf16x2(x.v[2], x.v[3]);
     r.z = pack_bf16x2(x.v[4], x.v[5]);
     r.w = pack_bf16x2(x.v[6], x.v[7]);
+    *reinterpret_cast<uint4 *>(p) = r;
+}
+
+template <> __device__ __forceinline__ void store_vec<__half>(__half *p, const Vec<__half> &x) {
+    uint4 r;
+    r.x = pack_f16x2(x.v[0], x.v[1]);
+    r.y = pack_f16x2(x.v[2], x.v[3]);
+    r.z = pack_f16x2(x.v[4], x.v[5]);
+    r.w = pack_f16x2(x.v[6], x.v[7]);
     *reinterpret_cast<uint4 *>(p) = r;
 }
 

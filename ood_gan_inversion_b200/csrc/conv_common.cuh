@@ -61,6 +61,14 @@ static inline ConvGeom make_geom(int batch, int h, int w, int cin, int cout, int
         p.oh = h; p.ow = w; p.py = p.px = 0; p.ntaps = 1;
         p.dy[0] = p.dx[0] = 0; p.wt[0] = 0;
         p.m_total = batch * h * w;
+    } else if (transposed == 6) {
+        // 1x1 stride-2 convolution (one tap, no padding): out[y,x] = W . in[2y, 2x] -- the shortcut convolutions of the encoder's
+        // down-sampling bottlenecks (helpers.py:483-486: Conv2d(in, depth, (1,1), stride) + BatchNorm2d)
+        g.OH = (h - 1) / 2 + 1; g.OW = (w - 1) / 2 + 1; g.sy = g.sx = 1; g.isy = g.isx = 2; g.nphases = 1;
+        ConvPhase &p = g.ph[0];
+        p.oh = g.OH; p.ow = g.OW; p.py = p.px = 0; p.ntaps = 1;
+        p.dy[0] = p.dx[0] = 0; p.wt[0] = 0;
+        p.m_total = batch * p.oh * p.ow;
     } else if (transposed == 3) {
         // stride-2 pad-1 3x3 conv: out[y,x] = sum in[2y+ky-1, 2x+kx-1] * W[ky,kx] -- the down-sampling convolutions of the
         // E4E encoder (GradualStyleBlock psp_encoders.py:41-48, bottleneck_IR_SE helpers.py:488-491)

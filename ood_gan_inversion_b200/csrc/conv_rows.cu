@@ -400,7 +400,7 @@ int conv3x3_rows(const ood_conv3x3_args &a, cudaStream_t st, int *handled) {
     // PReLU convolutions (the encoder's 64-channel layers at 128 / 256 px) stay on the generic tiles.  A PReLU form of this
     // epilogue was built and measured: 0.22 -> 0.37 ms (4 launches at 128 px: 64 strips for 148 SMs), 0.19 -> 0.22 ms at
     // 256 px, and its extra live registers made the <64,64> instance spill (512 px generator layer 0.48 -> 0.82 ms) -- removed.
-    if (a.transposed || a.dtype != OOD_BF16 || a.out_f32 || a.act == 2 || a.groups > 1 || a.acc_in || a.tiled || a.stats_out) return OOD_OK;
+    if (a.transposed || a.dtype != OOD_BF16 || a.out_dtype == OOD_F16 || a.out_f32 || a.act == 2 || a.groups > 1 || a.acc_in || a.tiled || a.stats_out) return OOD_OK;
     if (!((a.cin == 32 || a.cin == 64) && (a.cout == 32 || a.cout == 64) && a.cin >= a.cout)) return OOD_OK;
     if (a.w % 128 != 0 || a.h < 3 || (int64_t)a.batch * a.h * a.w >= (1LL << 31)) return OOD_OK;
     static EncodeFn encode = nullptr;

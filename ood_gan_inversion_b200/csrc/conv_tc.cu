@@ -36,6 +36,7 @@ struct TcParams {
     TcPhase ph[4];
     ConvEpilogue ep;
     int out_bf16;                   // storage type of out_y / out_ys
+    int in_f16, out_f16;            // OOD_F16 operands (idesc A/B format) / half-precision outputs (epilogue pack)
 };
 
 // ---------------------------------------------------------------------------------------------- PTX wrappers
@@ -225,6 +226,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
+            // instruction descriptor: A / B format field 1 = bf16, 0 = f16 (bits 7..9 and 10..12)
+            const uint32_t idesc = p.in_f16 ? (Cfg::kIdesc & ~((1u << 7) | (1u << 10))) : Cfg::kIdesc;
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
                 const TileCoord tc = decode_tile(p, tile, BN);
                 const int kiters = p.ph[tc.phase].ntaps * kchunks;
@@ -238,7 +241,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const uint64_t db = make_smem_desc<BK * 2>(smem_u32(sB + stage * Cfg::kBBytes));
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k)
-                        umma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), Cfg::kIdesc, (it | k) != 0);
+                        umma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (it | k) != 0);
                     umma_commit(&empty[stage]);          // frees the smem slot when these MMAs retire
                     if (++stage == S) { stage = 0; phase ^= 1; }
                 }
@@ -328,6 +331,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // would wait for the loads)
             // (Measured and not kept: requesting the next chunk's TMEM load before processing the current one -- a second 32-register
             // buffer in the plain kernels -- left the half-K convolutions at 384 / 406 us and made the C=128 ones 5-9 % slower.)
+            const bool of16 = p.out_f16 != 0;
+            auto pk2 = [&](float lo, float hi) -> uint32_t { return of16 ? pack_f16x2(lo, hi) : pack_bf16x2(lo, hi); };
             auto do_chunk = [&](const int ch, float4 (&cur)[8], float4 (&nxt)[8]) {
                 uint32_t r[32];
                 if (SEED && seed && ch + 1 < BN / 32) {
@@ -416,10 +421,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             __nv_bfloat16 *o = (__nv_bfloat16 *)p.ep.out_y + cpix * p.cout + n;      // 64-byte aligned (cout, n % 32 == 0)
 #pragma unroll
                             for (int j = 0; j < 2; ++j)
-                                st_global_256(o + 16 * j, pack_bf16x2(v[16 * j], v[16 * j + 1]), pack_bf16x2(v[16 * j + 2], v[16 * j + 3]),
-                                              pack_bf16x2(v[16 * j + 4], v[16 * j + 5]), pack_bf16x2(v[16 * j + 6], v[16 * j + 7]),
-                                              pack_bf16x2(v[16 * j + 8], v[16 * j + 9]), pack_bf16x2(v[16 * j + 10], v[16 * j + 11]),
-                                              pack_bf16x2(v[16 * j + 12], v[16 * j + 13]), pack_bf16x2(v[16 * j + 14], v[16 * j + 15]));
+                                st_global_256(o + 16 * j, pk2(v[16 * j], v[16 * j + 1]), pk2(v[16 * j + 2], v[16 * j + 3]),
+                                              pk2(v[16 * j + 4], v[16 * j + 5]), pk2(v[16 * j + 6], v[16 * j + 7]),
+                                              pk2(v[16 * j + 8], v[16 * j + 9]), pk2(v[16 * j + 10], v[16 * j + 11]),
+                                              pk2(v[16 * j + 12], v[16 * j + 13]), pk2(v[16 * j + 14], v[16 * j + 15]));
                         }
                     }
                     if (p.ep.out_ys) {
@@ -432,10 +437,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         __nv_bfloat16 *o = (__nv_bfloat16 *)p.ep.out_ys + cpix * p.cout + n;
 #pragma unroll
                         for (int j = 0; j < 2; ++j)
-                            st_global_256(o + 16 * j, pack_bf16x2(v[16 * j], v[16 * j + 1]), pack_bf16x2(v[16 * j + 2], v[16 * j + 3]),
-                                          pack_bf16x2(v[16 * j + 4], v[16 * j + 5]), pack_bf16x2(v[16 * j + 6], v[16 * j + 7]),
-                                          pack_bf16x2(v[16 * j + 8], v[16 * j + 9]), pack_bf16x2(v[16 * j + 10], v[16 * j + 11]),
-                                          pack_bf16x2(v[16 * j + 12], v[16 * j + 13]), pack_bf16x2(v[16 * j + 14], v[16 * j + 15]));
+                            st_global_256(o + 16 * j, pk2(v[16 * j], v[16 * j + 1]), pk2(v[16 * j + 2], v[16 * j + 3]),
+                                          pk2(v[16 * j + 4], v[16 * j + 5]), pk2(v[16 * j + 6], v[16 * j + 7]),
+                                          pk2(v[16 * j + 8], v[16 * j + 9]), pk2(v[16 * j + 10], v[16 * j + 11]),
+                                          pk2(v[16 * j + 12], v[16 * j + 13]), pk2(v[16 * j + 14], v[16 * j + 15]));
                     }
                 }
                 if constexpr (STATS) {
@@ -579,7 +584,7 @@ static void plan_tiles(const ood_conv3x3_args &a, const ConvGeom &g, TcParams &p
     p.NB = TBM / (p.TW * p.TH);
     p.nphases = g.nphases;
     p.groups = groups; p.gbatch = a.batch / groups; p.in_shared = a.in_shared ? 1 : 0;
-    p.wtaps = a.transposed == 4 ? 1 : (a.transposed == 5 ? 4 : 9);
+    p.wtaps = (a.transposed == 4 || a.transposed == 6) ? 1 : (a.transposed == 5 ? 4 : 9);
     const int bn_min = (a.acc_in || a.tiled || a.stats_out) ? 128 : 64;
     int tiles = 0;
     for (;;) {
@@ -603,7 +608,9 @@ static void plan_tiles(const ood_conv3x3_args &a, const ConvGeom &g, TcParams &p
 }
 
 int conv3x3_tc(const ood_conv3x3_args &a, cudaStream_t st) {
-    OOD_REQUIRE(a.dtype == OOD_BF16, "conv3x3 tc: storage type must be bf16");
+    OOD_REQUIRE(a.dtype == OOD_BF16 || a.dtype == OOD_F16, "conv3x3 tc: storage type must be bf16 or f16");
+    OOD_REQUIRE(a.out_dtype == 0 || a.out_dtype == OOD_BF16 || a.out_dtype == OOD_F16, "conv3x3 tc: out_dtype must be 0, OOD_BF16 or OOD_F16");
+    OOD_REQUIRE(!a.stats_out || (a.dtype == OOD_BF16 && a.out_dtype != OOD_F16), "conv3x3 tc: the fused statistics are built for bf16 outputs");
     OOD_REQUIRE(a.cin % 32 == 0 && a.cout % 32 == 0, "conv3x3 tc: cin and cout must be multiples of 32 (got %d, %d)", a.cin, a.cout);
     OOD_REQUIRE(((uintptr_t)a.in % 16 == 0) && ((uintptr_t)a.weight % 16 == 0), "conv3x3 tc: operands must be 16-byte aligned");
     EncodeTiledFn encode = get_encode_fn();
@@ -626,6 +633,8 @@ int conv3x3_tc(const ood_conv3x3_args &a, cudaStream_t st) {
     OOD_REQUIRE(!a.rgb_out || (p.n_tiles_n == 1 && !a.transposed), "conv3x3 tc: the fused ToRGB epilogue needs Co == tile N (Co <= 256) and the stride-1 form");
     p.ep = make_epilogue(a, a.out_f32);
     p.out_bf16 = 1;
+    p.in_f16 = a.dtype == OOD_F16;
+    p.out_f16 = (a.out_dtype ? a.out_dtype : a.dtype) == OOD_F16;
     OOD_REQUIRE(!a.acc_in || (uintptr_t)a.acc_in % 16 == 0, "conv3x3 tc: acc_in must be 16-byte aligned");
     OOD_REQUIRE((uintptr_t)a.out_y % 32 == 0 && (uintptr_t)a.out_ys % 32 == 0, "conv3x3 tc: outputs must be 32-byte aligned (256-bit stores)");
 
@@ -636,7 +645,7 @@ int conv3x3_tc(const ood_conv3x3_args &a, cudaStream_t st) {
         // with element stride s the box spans s*(n-1)+1 tensor elements and delivers n of them to shared memory
         cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)(g.isx * (p.TW - 1) + 1), (cuuint32_t)(g.isy * (p.TH - 1) + 1), (cuuint32_t)p.NB};
         cuuint32_t es[4] = {1, (cuuint32_t)g.isx, (cuuint32_t)g.isy, 1};
-        CUresult r = encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(a.in), dims, strides, box, es,
+        CUresult r = encode(&tmA, a.dtype == OOD_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(a.in), dims, strides, box, es,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { set_error("conv3x3 tc: activation tensor map encode failed (%d)", (int)r); return OOD_ERR_CUDA; }
@@ -647,13 +656,13 @@ int conv3x3_tc(const ood_conv3x3_args &a, cudaStream_t st) {
         cuuint64_t strides[2] = {(cuuint64_t)a.cin * 2, ncols * a.cin * 2};
         cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)BN, 1};
         cuuint32_t es[3] = {1, 1, 1};
-        CUresult r = encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void *>(a.weight), dims, strides, box, es,
+        CUresult r = encode(&tmB, a.dtype == OOD_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void *>(a.weight), dims, strides, box, es,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { set_error("conv3x3 tc: weight tensor map encode failed (%d)", (int)r); return OOD_ERR_CUDA; }
     }
     if (a.stats_out) {  // fused output statistics: wide tiles, one image per tile, single phase
-        OOD_REQUIRE(a.stats_ws && !a.acc_in && !a.out_ys && !a.out_f32 && a.out_y && groups == 1 && (a.transposed == 0 || a.transposed == 3 || a.transposed == 4) &&
+        OOD_REQUIRE(a.stats_ws && !a.acc_in && !a.out_ys && !a.out_f32 && a.out_y && groups == 1 && (a.transposed == 0 || a.transposed == 3 || a.transposed == 4 || a.transposed == 6) &&
                     p.NB == 1 && BK == 64 && (BN == 256 || BN == 128),
                     "conv3x3 tc: stats_out needs the stride-1 / stride-2 pad-1 / 1x1 form, bf16 out_y only, cin %% 64 == 0, cout %% 128 == 0 and >= 128 output pixels");
         p.ep.stat_partial = a.stats_ws;
@@ -688,7 +697,7 @@ int conv3x3_tc(const ood_conv3x3_args &a, cudaStream_t st) {
 
 extern "C" int64_t ood_conv3x3_stats_workspace(int batch, int h, int w, int cin, int cout, int transposed) {
     using namespace ood;
-    if (batch <= 0 || h <= 0 || w <= 0 || cin <= 0 || cout <= 0 || cout % 128 != 0 || (transposed != 0 && transposed != 3 && transposed != 4)) return 0;
+    if (batch <= 0 || h <= 0 || w <= 0 || cin <= 0 || cout <= 0 || cout % 128 != 0 || (transposed != 0 && transposed != 3 && transposed != 4 && transposed != 6)) return 0;
     ood_conv3x3_args a{};
     a.batch = batch; a.h = h; a.w = w; a.cin = cin; a.cout = cout; a.transposed = transposed;
     float dummy = 0.f;
@@ -703,7 +712,7 @@ extern "C" int64_t ood_conv3x3_stats_workspace(int batch, int h, int w, int cin,
 
 extern "C" int64_t ood_conv3x3_tiled_bytes(int batch, int h, int w, int cin, int cout, int transposed) {
     using namespace ood;
-    if (batch <= 0 || h <= 0 || w <= 0 || cin <= 0 || cout <= 0 || cout % 128 != 0 || transposed == 1 || transposed < 0 || transposed > 4) return 0;
+    if (batch <= 0 || h <= 0 || w <= 0 || cin <= 0 || cout <= 0 || cout % 128 != 0 || transposed == 1 || transposed == 5 || transposed < 0 || transposed > 6) return 0;
     ood_conv3x3_args a{};
     a.batch = batch; a.h = h; a.w = w; a.cin = cin; a.cout = cout; a.transposed = transposed; a.tiled = 1;
     const ConvGeom g = make_geom(batch, h, w, cin, cout, transposed);
@@ -725,7 +734,7 @@ extern "C" int ood_conv3x3(const ood_conv3x3_args *a, void *stream) {
     OOD_REQUIRE(a->out_y || a->out_ys || a->rgb_out, "conv3x3: no output requested");
     OOD_REQUIRE(!a->rgb_out || (a->rgb_w && a->rgb_bias && a->act == 1 && a->h % 2 == 0 && a->w % 2 == 0), "conv3x3: fused ToRGB needs rgb_w, rgb_bias, act=1 and even sizes");
     OOD_REQUIRE(!a->out_ys || a->s_next, "conv3x3: out_ys needs s_next");
-    OOD_REQUIRE(a->transposed >= 0 && a->transposed <= 5, "conv3x3: transposed must be 0..5");
+    OOD_REQUIRE(a->transposed >= 0 && a->transposed <= 6, "conv3x3: transposed must be 0..6");
     OOD_REQUIRE((a->transposed != 1 && a->transposed != 5) || (!a->out_ys && !a->act && !a->noise && !a->bias && !a->d),
                 "conv3x3: the transposed form writes raw accumulators (the epilogue follows the blur)");
     OOD_REQUIRE(a->transposed != 2 || (a->h % 2 == 1 && a->w % 2 == 1 && a->h >= 3 && a->w >= 3 && !a->noise),

@@ -43,7 +43,17 @@ template <> __device__ __forceinline__ void enc_load<__nv_bfloat16>(const __nv_b
     const uint4 r = __ldg(reinterpret_cast<const uint4 *>(p));
     dst[0] = unpack_bf16x2(r.x); dst[1] = unpack_bf16x2(r.y); dst[2] = unpack_bf16x2(r.z); dst[3] = unpack_bf16x2(r.w);
 }
+template <> __device__ __forceinline__ void enc_load<__half>(const __half *p, float2 *dst) {
+    const uint4 r = __ldg(reinterpret_cast<const uint4 *>(p));
+    dst[0] = unpack_f16x2(r.x); dst[1] = unpack_f16x2(r.y); dst[2] = unpack_f16x2(r.z); dst[3] = unpack_f16x2(r.w);
+}
 template <typename T> __device__ __forceinline__ void enc_store(T *p, const float2 *v);
+template <> __device__ __forceinline__ void enc_store<__half>(__half *p, const float2 *v) {
+    uint4 r;
+    r.x = pack_f16x2(v[0].x, v[0].y); r.y = pack_f16x2(v[1].x, v[1].y);
+    r.z = pack_f16x2(v[2].x, v[2].y); r.w = pack_f16x2(v[3].x, v[3].y);
+    *reinterpret_cast<uint4 *>(p) = r;
+}
 template <> __device__ __forceinline__ void enc_store<float>(float *p, const float2 *v) {
     *reinterpret_cast<float4 *>(p) = make_float4(v[0].x, v[0].y, v[1].x, v[1].y);
 }
@@ -228,7 +238,7 @@ extern "C" int ood_se_residual(const void *v, const float *gate, const void *sho
                                int shortcut_f32, int out_f32, void *stream) {
     using namespace ood;
     OOD_REQUIRE(v && (out || t_next) && batch > 0 && batch <= 65535 && h > 0 && w > 0, "se_residual: bad arguments");
-    OOD_REQUIRE(dtype == OOD_F32 || dtype == OOD_BF16, "se_residual: bad dtype");
+    OOD_REQUIRE(dtype == OOD_F32 || dtype == OOD_BF16 || dtype == OOD_F16, "se_residual: bad dtype");
     OOD_REQUIRE(sc_stride == 1 || sc_stride == 2, "se_residual: shortcut stride must be 1 or 2");
     OOD_REQUIRE(!t_next || (bn_g && bn_h), "se_residual: t_next needs the affine coefficients");
     const int N = dtype == OOD_F32 ? 4 : 8;
@@ -242,6 +252,15 @@ extern "C" int ood_se_residual(const void *v, const float *gate, const void *sho
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == OOD_F32) {
         se_residual_kernel<float, false, false><<<grid, 256, 0, st>>>((const float *)v, gate, shortcut, sc_stride, bn_g, bn_h, out, (float *)t_next, h, w, channels, chunk);
+    } else if (dtype == OOD_F16) {
+        const __half *vv = (const __half *)v;
+        __half *tn = (__half *)t_next;
+#define OOD_SE(SF, OF) se_residual_kernel<__half, SF, OF><<<grid, 256, 0, st>>>(vv, gate, shortcut, sc_stride, bn_g, bn_h, out, tn, h, w, channels, chunk)
+        if (shortcut_f32 && out_f32) OOD_SE(true, true);
+        else if (shortcut_f32) OOD_SE(true, false);
+        else if (out_f32) OOD_SE(false, true);
+        else OOD_SE(false, false);
+#undef OOD_SE
     } else {
         const __nv_bfloat16 *vv = (const __nv_bfloat16 *)v;
         __nv_bfloat16 *tn = (__nv_bfloat16 *)t_next;

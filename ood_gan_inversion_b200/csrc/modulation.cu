@@ -112,6 +112,7 @@ extern "C" int ood_pack_conv_weight(const float *w, void *out, int cout, int cin
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == OOD_F32) pack_weight_kernel<float><<<ceil_div(n, 256), 256, 0, st>>>(w, (float *)out, cout, cin, taps, ci_major_out);
     else if (dtype == OOD_BF16) pack_weight_kernel<__nv_bfloat16><<<ceil_div(n, 256), 256, 0, st>>>(w, (__nv_bfloat16 *)out, cout, cin, taps, ci_major_out);
+    else if (dtype == OOD_F16) pack_weight_kernel<__half><<<ceil_div(n, 256), 256, 0, st>>>(w, (__half *)out, cout, cin, taps, ci_major_out);
     else OOD_REQUIRE(false, "pack_conv_weight: bad dtype");
     return check_launch("pack_conv_weight");
 }

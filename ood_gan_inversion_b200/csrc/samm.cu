@@ -457,13 +457,14 @@ extern "C" int ood_bicubic_up_add(const void *x, const void *y, void *out, int b
                                   int channels, int dtype, void *stream) {
     using namespace ood;
     OOD_REQUIRE(x && out && batch > 0 && batch <= 65535 && h > 0 && w > 0 && H > 0 && W > 0, "bicubic_up_add: bad arguments");
-    OOD_REQUIRE(dtype == OOD_F32 || dtype == OOD_BF16, "bicubic_up_add: bad dtype");
+    OOD_REQUIRE(dtype == OOD_F32 || dtype == OOD_BF16 || dtype == OOD_F16, "bicubic_up_add: bad dtype");
     const int N = dtype == OOD_F32 ? 4 : 8;
     OOD_REQUIRE(channels % N == 0, "bicubic_up_add: channels (%d) must be a multiple of %d", channels, N);
     const int64_t work = (int64_t)H * W * (channels / N);
     dim3 grid((unsigned)std::min<int64_t>((work + 255) / 256, kNumSMs * 16), batch);
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == OOD_F32) bicubic_up_add_kernel<float><<<grid, 256, 0, st>>>((const float *)x, (const float *)y, (float *)out, h, w, H, W, channels);
+    else if (dtype == OOD_F16) bicubic_up_add_kernel<__half><<<grid, 256, 0, st>>>((const __half *)x, (const __half *)y, (__half *)out, h, w, H, W, channels);
     else bicubic_up_add_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16 *)x, (const __nv_bfloat16 *)y, (__nv_bfloat16 *)out, h, w, H, W, channels);
     return check_launch("bicubic_up_add");
 }

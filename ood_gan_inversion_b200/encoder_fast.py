@@ -5,8 +5,8 @@ e4e_arch.py:256-258).  The trunk's 48 stride-1 / stride-2 3x3 convolutions and t
 GradualStyleBlocks run on the tcgen05 implicit-GEMM kernel (`ood_conv3x3`, forms 0 and 3) with their PReLU / folded
 BatchNorm bias / LeakyReLU fused into the epilogue; the squeeze-excite gate and the residual sum (which also emits the
 next block's BatchNorm) are `ood_se_gate` / `ood_se_residual`; the 3->64 input convolution runs with its input channels
-zero-padded to 32, the lateral 1x1 convolutions on the 1x1 form; the residual stream is kept in fp32.  What stays cuDNN: the
-three 1x1 stride-2 shortcut convolutions.
+zero-padded to 32, the lateral 1x1 convolutions and the heads' closing EqualLinear on the (grouped) 1x1 form, the three 1x1
+stride-2 shortcut convolutions on its strided form; the residual stream is kept in fp32.  No cuDNN / cuBLAS call is left.
 
 Built from (and numerically checked against) `encoder.Encoder4Editing`; eval-mode BatchNorms are folded in fp32.
 """
@@ -19,6 +19,12 @@ from torch.nn import functional as F
 from . import kernels as K
 
 _SE_MEAN_FROM_CONV = os.environ.get('OOD_SE_MEAN_FROM_CONV', '0') != '0'       # A/B switch (profiles/microbench_r01b.txt)
+# Storage type of the encoder's activations and weights on the tensor-core path.  IEEE half, not bf16: every activation here is
+# behind an eval-mode BatchNorm (O(1) values, far inside the half range; conversions saturate), the tcgen05 pipe runs f16 and
+# bf16 at the same rate, and 11 significant bits instead of 8 cut the W+ error against the fp32 reference from 0.9 % to ~0.1 %
+# rel-L2 -- with bf16 the encoder's latents were the largest single term of the pipeline's image error (scripts/diag_bf16_budget.py:
+# 0.0148 max-abs all-bf16 against 0.0091 with fp32 latents, batch 8).  OOD_ENCODER_DTYPE=bf16 restores the old route for A/B runs.
+ENC_DT = torch.bfloat16 if os.environ.get('OOD_ENCODER_DTYPE', 'f16') == 'bf16' else torch.float16
 
 
 def _bn_affine(bn):
@@ -27,7 +33,7 @@ def _bn_affine(bn):
 
 
 def _pack(w):
-    return K.pack_conv_weight(w.float().contiguous(), torch.bfloat16, False)
+    return K.pack_conv_weight(w.float().contiguous(), ENC_DT, False)
 
 
 def _nhwc(t):
@@ -57,10 +63,12 @@ class _Block:
         if isinstance(blk.shortcut_layer, nn.Sequential):
             conv, bn = list(blk.shortcut_layer.children())
             g, h = _bn_affine(bn)
-            sc = nn.Conv2d(conv.in_channels, conv.out_channels, 1, conv.stride, bias=True).to(conv.weight.device)
-            sc.weight = nn.Parameter(conv.weight.detach().float() * g.reshape(-1, 1, 1, 1), requires_grad=False)
-            sc.bias = nn.Parameter(h, requires_grad=False)
-            self.shortcut = sc.to(torch.bfloat16).to(memory_format=torch.channels_last)
+            # Conv2d(in, depth, 1, stride, bias=False) + BatchNorm2d (helpers.py:483-486), folded: the 1x1 (stride-2) form of the
+            # tcgen05 kernel reads every second pixel of every second row through the TMA element strides
+            if conv.stride[0] not in (1, 2):
+                raise NotImplementedError('FastEncoder: shortcut stride must be 1 or 2')
+            self.shortcut = (K.pack_conv1x1_weight(conv.weight.detach().float() * g.reshape(-1, 1, 1, 1), ENC_DT, False), h,
+                             conv.out_channels, 6 if conv.stride[0] == 2 else 4)
 
 
 class _HeadGroup:
@@ -79,7 +87,9 @@ class _HeadGroup:
             b = torch.stack([c[d].bias.detach().float() for c in chains]).contiguous()           # [n, Co]
             slope = torch.full_like(b, 0.01)                                                     # nn.LeakyReLU()
             self.layers.append((w, b, slope, chains[0][d].out_channels))
-        self.lw = torch.stack([h.linear.weight.detach().float() * h.linear.scale for h in heads]).contiguous()       # [n, out, in]
+        # the closing EqualLinear of every head (psp_encoders.py:50-55) as ONE grouped 1x1 launch: pack [n][out][in]
+        self.lw = torch.cat([K.pack_conv1x1_weight(h.linear.weight.detach().float() * h.linear.scale, ENC_DT, False)
+                             for h in heads], 0).contiguous()
         self.lb = torch.stack([h.linear.bias.detach().float() * h.linear.lr_mul for h in heads]).contiguous()        # [n, out]
 
     def __call__(self, x):
@@ -87,8 +97,9 @@ class _HeadGroup:
         b = x.shape[0]
         for d, (w, bias, slope, co) in enumerate(self.layers):
             x, _ = K.conv3x3(x, w, co, transposed=3, bias=bias, prelu=slope, tag='encoder_conv', groups=self.n, in_shared=(d == 0))
-        x = x.reshape(self.n, b, self.out_c).float()
-        return torch.baddbmm(self.lb[:, None, :], x, self.lw.transpose(1, 2))
+        y, _ = K.conv3x3(x.reshape(self.n * b, 1, 1, self.out_c), self.lw, self.out_c, transposed=4, bias=self.lb, tag='encoder_conv',
+                         groups=self.n, out_f32=True)
+        return y.reshape(self.n, b, self.out_c)
 
 
 class FastEncoder:
@@ -110,7 +121,7 @@ class FastEncoder:
                             _HeadGroup(styles[self.middle_ind:])]
         self.lat = []                                        # lateral 1x1 convolutions (bias in the epilogue)
         for lat in (enc.latlayer1, enc.latlayer2):
-            self.lat.append((K.pack_conv1x1_weight(lat.weight.detach(), torch.bfloat16, False), lat.bias.detach().float().contiguous(),
+            self.lat.append((K.pack_conv1x1_weight(lat.weight.detach(), ENC_DT, False), lat.bias.detach().float().contiguous(),
                              lat.out_channels))
         self.progressive_stage = enc.progressive_stage
 
@@ -119,11 +130,18 @@ class FastEncoder:
         return K.conv3x3(x, w, co, transposed=4, bias=b, tag='encoder_conv')[0]
 
     @torch.no_grad()
-    def __call__(self, x, return_feats=False, **kwargs):
-        if not x.is_cuda:
-            raise RuntimeError('ood_gan_inversion_b200 is CUDA-only')
-        xp = torch.zeros(x.shape[0], x.shape[2], x.shape[3], 32, device=x.device, dtype=torch.bfloat16)
-        xp[..., :3] = x.permute(0, 2, 3, 1)
+    def __call__(self, x, return_feats=False, thumb=None, **kwargs):
+        """x: fp32 NCHW [B,3,256,256] (the module's input), or thumb: the same image as the first convolution's operand, bf16 NHWC
+        [B,256,256,32] with channels 3..31 zero (kernels.thumbnail_nhwc: resize + layout + cast + padding in one pass)."""
+        if thumb is not None:
+            xp = thumb
+            if xp.dtype != ENC_DT or xp.dim() != 4 or xp.shape[-1] != 32 or not xp.is_contiguous():
+                raise ValueError(f'FastEncoder: thumb must be a contiguous {ENC_DT} NHWC tensor with 32 channels')
+        else:
+            if not x.is_cuda:
+                raise RuntimeError('ood_gan_inversion_b200 is CUDA-only')
+            xp = torch.zeros(x.shape[0], x.shape[2], x.shape[3], 32, device=x.device, dtype=ENC_DT)
+            xp[..., :3] = x.permute(0, 2, 3, 1)
         x0, _ = K.conv3x3(xp, self.first_w, self.first_c, bias=self.first_b, prelu=self.first_slope, tag='encoder_conv')
         feats = [_nchw(x0)]
         # The residual stream `cur` is fp32 from the first block on (out_f32): rounding the running sum to bf16 after each of
@@ -143,13 +161,16 @@ class FastEncoder:
                 st = K.in_stats(v)
             gate = K.se_gate(st, blk.se1, blk.se2)
             if blk.shortcut is not None:
-                sc, ss = _nhwc(blk.shortcut(_nchw(cur.to(torch.bfloat16)))), 1
+                # the blocks with a shortcut convolution (3, 7, 21) follow the tapped blocks: their bf16 input is already there
+                w_sc, b_sc, c_sc, form = blk.shortcut
+                src = taps[i - 1] if (i - 1) in taps else cur.to(ENC_DT)
+                sc, ss = K.conv3x3(src, w_sc, c_sc, transposed=form, bias=b_sc, tag='encoder_conv')[0], 1
             else:
                 sc, ss = cur, blk.stride                                   # MaxPool2d(1, s): strided read
             nxt = self.blocks[i + 1].bn1 if i + 1 < len(self.blocks) else (None, None)
             cur, t = K.se_residual(v, gate, sc, ss, nxt[0], nxt[1], out_f32=True)
             if i in (2, 6, 20, 23):
-                taps[i] = cur.to(torch.bfloat16)
+                taps[i] = cur.to(ENC_DT)
                 feats.append(_nchw(taps[i]))
         c1, c2, c3 = taps[6], taps[20], taps[23]
         # psp_encoders.py:199-214: w_i = w_0 + head_i(features); heads beyond the progressive stage repeat w_0

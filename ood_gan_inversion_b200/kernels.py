@@ -8,7 +8,7 @@ import math
 import torch
 
 from . import _lib
-from ._lib import BF16, F32, BlurActArgs, ConvArgs, check
+from ._lib import BF16, F16, F32, BlurActArgs, ConvArgs, check
 
 FIR_1331 = (1.0, 3.0, 3.0, 1.0)
 
@@ -63,7 +63,9 @@ def _dt(t):
         return F32
     if t.dtype == torch.bfloat16:
         return BF16
-    raise RuntimeError(f'ood_gan_inversion_b200: unsupported dtype {t.dtype} (float32 and bfloat16 only)')
+    if t.dtype == torch.float16:      # the encoder path (OOD_F16): conv3x3 impl 0, in_stats, se_residual, bicubic_up_add, thumbnail_nhwc
+        return F16
+    raise RuntimeError(f'ood_gan_inversion_b200: unsupported dtype {t.dtype} (float32, bfloat16; float16 on the encoder kernels)')
 
 
 def _ptr(t):
@@ -202,6 +204,19 @@ def nchw_to_nhwc(x, scale_bc=None, dtype=torch.bfloat16, batch=None):
     return out
 
 
+def thumbnail_nhwc(x, size=(256, 256), cp=32, dtype=torch.bfloat16):
+    """x fp32 NCHW [B,3,H,W] -> `dtype` NHWC [B,oh,ow,cp]: F.interpolate(x, size, mode='bilinear') (e4e_arch.py:256) written as the
+    encoder's first-convolution operand (channels 3..cp-1 zero)."""
+    _cuda(x)
+    x = _f32c(x)
+    b, c, h, w = x.shape
+    oh, ow = size
+    out = torch.empty(b, oh, ow, cp, device=x.device, dtype=dtype)
+    with _timed('thumbnail', b * (4 * c * oh * ow * 4 + oh * ow * cp * out.element_size())):
+        check(_lib.lib().ood_thumbnail_nhwc(_ptr(x), _ptr(out), b, c, h, w, oh, ow, cp, _dt(out), _stream()), 'thumbnail_nhwc')
+    return out
+
+
 def nhwc_to_nchw(x):
     _cuda(x)
     x = x.contiguous()
@@ -288,22 +303,29 @@ def torgb_weight(w, s, scale=None):
 # ----------------------------------------------------------------------------------------------- convolution
 def conv3x3(x, weight, cout, transposed=False, impl=0, d=None, noise=None, noise_w=None, bias=None, s_next=None,
             act=False, want_y=True, want_ys=False, out_f32=False, prelu=None, rgb=None, tag=None, groups=1, in_shared=False,
-            acc_in=None, tiled=False, stats_eps=None):
+            acc_in=None, tiled=False, stats_eps=None, out_dtype=None):
     """x NHWC [B,H,W,Ci] pre-modulated; weight packed for `impl`.  Returns (y, ys) (None where not requested).
     rgb=(wrgb [B,3,Co], bias [3], skip NCHW fp32 or None, up taps): fused ToRGB, returns (y, ys, rgb_out NCHW fp32).
     acc_in: fp32 NHWC [B,OH,OW,Co] seed added to the accumulator before the epilogue (tcgen05 path).
     tiled: acc_in, and y when out_f32, are flat fp32 tensors in the kernel's tile order (ood_conv3x3_tiled_bytes): the fast form
     of a seed that only ever travels between two launches with the same geometry.
     stats_eps: also return [B,Co,2] = (mean, rstd) of y as stored, computed in the epilogue -> (y, ys, stats); use
-    conv3x3_stats_ok() for the envelope."""
+    conv3x3_stats_ok() for the envelope.
+    out_dtype: storage type of y / ys when it differs from x's (torch.bfloat16 or torch.float16; tcgen05 path)."""
     _cuda(x, weight, d, noise, noise_w, bias, s_next, acc_in)
     assert x.is_contiguous()
+    if weight.dtype != x.dtype and impl == 0:
+        raise RuntimeError(f'ood_gan_inversion_b200: conv3x3 operands differ in type ({x.dtype} activations, {weight.dtype} weights)')
+    odt = x.dtype if out_dtype is None else out_dtype
+    if odt != x.dtype and (impl != 0 or odt not in (torch.bfloat16, torch.float16) or x.dtype == torch.float32):
+        raise RuntimeError('ood_gan_inversion_b200: conv3x3 out_dtype is a bf16 <-> f16 switch of the tcgen05 path')
     b, h, w, cin = x.shape
     if in_shared:            # grouped form on a shared input: every group convolves the same [images, ...] tensor
         b = b * groups
-    transposed = int(transposed)      # 0 stride-1 | 1 stride-2 transposed | 2 stride-2 valid (data gradient of 1) | 3 stride-2 pad-1
+    transposed = int(transposed)      # 0 stride-1 | 1 stride-2 transposed | 2 stride-2 valid (data gradient of 1) | 3 stride-2 pad-1 | 4 1x1 | 5 fused 1 | 6 1x1 stride-2
     oh, ow = {0: (h, w), 1: (2 * h + 1, 2 * w + 1), 2: ((h - 1) // 2, (w - 1) // 2),
-              3: ((h - 1) // 2 + 1, (w - 1) // 2 + 1), 4: (h, w), 5: (2 * h + 1, 2 * w + 1)}[transposed]
+              3: ((h - 1) // 2 + 1, (w - 1) // 2 + 1), 4: (h, w), 5: (2 * h + 1, 2 * w + 1),
+              6: ((h - 1) // 2 + 1, (w - 1) // 2 + 1)}[transposed]
     nt = 0
     if tiled:
         nt = _lib.lib().ood_conv3x3_tiled_bytes(b, h, w, cin, cout, transposed) // 4
@@ -312,12 +334,13 @@ def conv3x3(x, weight, cout, transposed=False, impl=0, d=None, noise=None, noise
     if tiled and out_f32 and want_y:
         y = torch.empty(nt, device=x.device, dtype=torch.float32)
     else:
-        y = torch.empty(b, oh, ow, cout, device=x.device, dtype=torch.float32 if out_f32 else x.dtype) if want_y else None
-    ys = torch.empty(b, oh, ow, cout, device=x.device, dtype=x.dtype) if want_ys else None
+        y = torch.empty(b, oh, ow, cout, device=x.device, dtype=torch.float32 if out_f32 else odt) if want_y else None
+    ys = torch.empty(b, oh, ow, cout, device=x.device, dtype=odt) if want_ys else None
     nbs = _noise_bstride(noise, b, oh, ow)
     a = ConvArgs(_ptr(x), _ptr(weight), _ptr(y), _ptr(ys), _ptr(d), _ptr(noise), nbs, _ptr(noise_w), _ptr(bias), _ptr(s_next),
                  b, h, w, cin, cout, int(transposed), 2 if prelu is not None else int(act), impl, _dt(x), int(out_f32), _ptr(prelu))
     a.groups, a.in_shared = int(groups), int(bool(in_shared))
+    a.out_dtype = 0 if odt == x.dtype else (F16 if odt == torch.float16 else BF16)
     if acc_in is not None:
         assert acc_in.dtype == torch.float32 and acc_in.is_contiguous()
         assert tuple(acc_in.shape) == ((nt,) if tiled else (b, oh, ow, cout))
@@ -340,7 +363,7 @@ def conv3x3(x, weight, cout, transposed=False, impl=0, d=None, noise=None, noise
         a.rgb_taps = (C.c_float * 4)(*rtaps)
     # algorithmic work: 2*B*Co*Ci*9*H*W with H, W the INPUT size for the transposed form
     px = h * w if transposed in (0, 1, 5) else oh * ow
-    with _timed(tag or ('conv3x3_tc' if impl == 0 else 'conv3x3_simt'), 2.0 * b * cout * cin * (1 if transposed == 4 else 9) * px):
+    with _timed(tag or ('conv3x3_tc' if impl == 0 else 'conv3x3_simt'), 2.0 * b * cout * cin * (1 if transposed in (4, 6) else 9) * px):
         check(_lib.lib().ood_conv3x3(C.byref(a), _stream()), 'conv3x3')
     if rgb is not None:
         return y, ys, rgb_out

@@ -836,3 +836,70 @@ def test_conv3x3_encoder_epilogues_on_wide_images(case):
     torch.testing.assert_close(nchw(y2), F.prelu(raw + bias[None, :, None, None], slope), rtol=2e-2, atol=2e-2)
     y3, _ = K().conv3x3(nhwc(x, dt), wp, co, impl=0, bias=bias.to(DEV))
     torch.testing.assert_close(nchw(y3), raw + bias[None, :, None, None], rtol=2e-2, atol=2e-2)
+
+
+@pytest.mark.parametrize('impl', [0, 1])
+@pytest.mark.parametrize('case', [dict(b=2, h=16, w=16, ci=64, co=128), dict(b=3, h=9, w=13, ci=128, co=256), dict(b=1, h=128, w=128, ci=64, co=128),
+                                  dict(b=16, h=2, w=2, ci=256, co=512)])
+def test_conv1x1_stride2(impl, case):
+    """ood_conv3x3(transposed=6): out[y,x] = W . in[2y,2x] + bias == F.conv2d(kernel 1, stride 2): the shortcut convolution of the
+    encoder's down-sampling bottlenecks (e4e helpers.py:483-486) on the TMA element strides (odd sizes: last row / column kept)."""
+    b, h, w_, ci, co = case['b'], case['h'], case['w'], case['ci'], case['co']
+    dt = torch.bfloat16 if impl == 0 else torch.float32
+    x = rnd(b, ci, h, w_, seed=1).to(dt).float()
+    w = (rnd(co, ci, 1, 1, seed=2) / ci ** 0.5).to(dt).float()
+    bias = rnd(co, seed=3)
+    from ood_gan_inversion_b200 import kernels as K
+    y, _ = K.conv3x3(x.permute(0, 2, 3, 1).contiguous().to(dt).to(DEV), K.pack_conv1x1_weight(w.to(DEV), dt, impl == 1), co, transposed=6,
+                     impl=impl, bias=bias.to(DEV), out_f32=(impl == 0))
+    ref = torch.nn.functional.conv2d(x.double(), w.double(), bias.double(), stride=2).float()
+    assert y.shape == (b, (h - 1) // 2 + 1, (w_ - 1) // 2 + 1, co)
+    torch.testing.assert_close(y.float().permute(0, 3, 1, 2).cpu(), ref, rtol=1e-4, atol=2e-3)
+
+
+@pytest.mark.parametrize('hw,size', [((1024, 1024), (256, 256)), ((300, 420), (256, 256)), ((256, 256), (256, 256)), ((100, 64), (256, 256))])
+def test_thumbnail_nhwc(hw, size):
+    """ood_thumbnail_nhwc == F.interpolate(x, size, mode='bilinear') (OOD_faceGAN_e4e_arch.py:256) in NHWC with channels 3..31 zero:
+    down-scaling (the 2x2 centre mean at 4:1), non-integer ratios, identity and up-scaling; fp32 exact to rounding, bf16 = its cast."""
+    from ood_gan_inversion_b200 import kernels as K
+    x = rnd(2, 3, *hw, seed=5).to(DEV)
+    ref = F.interpolate(x, size, mode='bilinear')
+    for dt in (torch.float32, torch.bfloat16):
+        out = K.thumbnail_nhwc(x, size, 32, dt)
+        assert out.shape == (2, size[0], size[1], 32) and out.dtype == dt
+        assert float(out[..., 3:].abs().max()) == 0.0
+        got = out[..., :3].float().permute(0, 3, 1, 2)
+        if dt == torch.float32:
+            torch.testing.assert_close(got, ref, rtol=1e-5, atol=1e-6)
+        else:
+            torch.testing.assert_close(got, ref.to(dt).float(), rtol=1e-2, atol=1e-2)
+    if hw == (1024, 1024):
+        blocks = x.reshape(2, 3, 256, 4, 256, 4)[:, :, :, 1:3, :, 1:3].mean((3, 5))
+        torch.testing.assert_close(K.thumbnail_nhwc(x, size, 32, torch.float32)[..., :3].permute(0, 3, 1, 2), blocks, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize('case', [dict(b=2, h=16, w=16, ci=64, co=128, form=0), dict(b=2, h=17, w=13, ci=128, co=64, form=3),
+                                  dict(b=3, h=8, w=8, ci=64, co=256, form=4), dict(b=2, h=12, w=12, ci=32, co=32, form=0)])
+def test_conv3x3_f16_storage(case):
+    """OOD_F16 operands on the tcgen05 path (the encoder's storage type): same kernel, A/B format field of the instruction
+    descriptor = f16, half-precision epilogue pack (saturating); out_dtype switches the output between f16 and bf16."""
+    from ood_gan_inversion_b200 import kernels as K
+    b, h, w_, ci, co, form = (case[k] for k in ('b', 'h', 'w', 'ci', 'co', 'form'))
+    k = 1 if form == 4 else 3
+    x = rnd(b, ci, h, w_, seed=1).half().float()
+    w = (rnd(co, ci, k, k, seed=2) / (ci * k * k) ** 0.5).half().float()
+    bias = rnd(co, seed=3)
+    xp = x.permute(0, 2, 3, 1).contiguous().half().to(DEV)
+    wp = K.pack_conv1x1_weight(w.to(DEV), torch.float16, False) if form == 4 else K.pack_conv_weight(w.to(DEV), torch.float16, False)
+    ref = F.conv2d(x.double(), w.double(), bias.double(), stride=2 if form == 3 else 1, padding=0 if form == 4 else 1).float()
+    y32, _ = K.conv3x3(xp, wp, co, transposed=form, bias=bias.to(DEV), out_f32=True)
+    torch.testing.assert_close(y32.permute(0, 3, 1, 2).cpu(), ref, rtol=1e-4, atol=1e-4)
+    y16, _ = K.conv3x3(xp, wp, co, transposed=form, bias=bias.to(DEV))
+    assert y16.dtype == torch.float16
+    torch.testing.assert_close(y16.float().permute(0, 3, 1, 2).cpu(), ref, rtol=2e-3, atol=2e-3)
+    yb, _ = K.conv3x3(xp, wp, co, transposed=form, bias=bias.to(DEV), out_dtype=torch.bfloat16)
+    assert yb.dtype == torch.bfloat16
+    torch.testing.assert_close(yb.float().permute(0, 3, 1, 2).cpu(), ref, rtol=1e-2, atol=1e-2)
+    # saturation instead of inf
+    big, _ = K.conv3x3(xp, wp, co, transposed=form, bias=torch.full((co,), 1e6, device=DEV))
+    assert torch.isfinite(big.float()).all() and float(big.float().max()) == 65504.0

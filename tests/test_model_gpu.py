@@ -195,7 +195,7 @@ def test_ood_pipeline_bf16_vs_oracle(batch):
     """Full 1024 px pipeline, bf16 storage, against the fp32 oracle on the same device (TF32 off, same seed => same noise).
     north_star: image max-abs < 2e-2 and PSNR >= 40 dB.  Every side output is asserted too: the W+ codes (`lats`), the four
     accumulated alignment fields aligns[1..4] = (dx, dy, alpha) and the composed mask aligns[1024].  Bounds on the side
-    outputs are 2x the largest value measured on B200 over the three batches (profiles/README.md, round 2)."""
+    outputs are 2x the largest value measured on B200 over the three batches (round 2)."""
     out, lats, aligns, ref, rlats, raligns = _bf16_pipeline_case(batch)
     err, p = float((out - ref).abs().max()), psnr(out, ref)
     lat_err = float((lats - rlats).abs().max())
@@ -222,12 +222,13 @@ def test_ood_pipeline_bf16_vs_oracle(batch):
     assert mask_err < ALPHA_BOUND
 
 
-# measured on B200 (round 2, B = 2 / 16 / 32): lats rel-L2 0.0090 / 0.0090 / 0.0090, max-abs 0.016 / 0.017 / 0.017; flow max-abs
-# 0.010 / 0.012 / 0.014 (the finest level; 0.003-0.004 at 32 px) with mean 1e-4-scale, alpha 0.010 / 0.016 / 0.016, mask 0.006 /
-# 0.012 / 0.012; image 0.0114 / 0.0172 / 0.0178 and 62 dB.  The max over 4 M field elements sits on the few pixels where a
-# bf16-rounded AlignNet output crosses a clip or tanh knee; the means are asserted as well.
-LAT_REL_BOUND, LAT_ABS_BOUND, FLOW_BOUND, ALPHA_BOUND = 2e-2, 4e-2, 2.8e-2, 3.2e-2
-FLOW_MEAN_BOUND, ALPHA_MEAN_BOUND = 2e-3, 4e-3
+# measured on B200 (round 2, B = 2 / 16 / 32, encoder in f16 storage): image max-abs 0.0066 / 0.0097 / 0.0130 and 67 dB; lats rel-L2
+# 0.0011, max-abs 0.0018 / 0.0023 / 0.0022; flow max-abs 0.0065 / 0.0077 / 0.0088 (finest level; 0.002-0.003 at 32 px), mean 2.5e-4..3.4e-4;
+# alpha 0.0068 / 0.0089 / 0.0109, mean 6e-4..9e-4; mask 0.0041 / 0.0061 / 0.0078.  (With the encoder in bf16 the same cases measured
+# 0.0114 / 0.0172-0.0214 / 0.0178 on the image and 0.9 % on the latents: profiles/r02_parity_batches.txt.)  The max over 4 M field
+# elements sits on the few pixels where a bf16-rounded AlignNet output crosses a clip or tanh knee; the means are asserted as well.
+LAT_REL_BOUND, LAT_ABS_BOUND, FLOW_BOUND, ALPHA_BOUND = 2.5e-3, 5e-3, 1.8e-2, 2.2e-2
+FLOW_MEAN_BOUND, ALPHA_MEAN_BOUND = 7e-4, 1.8e-3
 
 
 def test_fast_encoder_bf16_vs_oracle():
@@ -246,7 +247,7 @@ def test_fast_encoder_bf16_vs_oracle():
                                                                                    float((w - w_ref).abs().max())))
     for a, b in zip(feats, f_ref):
         assert a.shape == b.shape
-    assert max(errs) < 1e-2
+    assert max(errs) < 2.5e-3          # measured 1.1e-3 (w), 3e-4 .. 1.0e-3 (features); 9e-3 with bf16 storage
 
 
 def test_generic_callback_protocol():
