@@ -288,8 +288,22 @@ int ood_tap_sum_shortcut(const float *proj, float *out, float *shortcut, int bat
 int ood_se_gate(const float *stats, const float *w1, const float *w2, float *gate, int batch, int channels, int reduced,
                 void *stream);
 int ood_se_residual(const void *v, const float *gate, const void *shortcut, int sc_stride, const float *bn_g,
-                    const float *bn_h, void *out, void *t_next, int batch, int h, int w, int channels, int dtype,
+                    const float *bn_h, void *out, void *t_next, void *out_lp, int batch, int h, int w, int channels, int dtype,
                     int shortcut_f32, int out_f32, void *stream);
+/*      out_lp (or NULL): `out` once more in the storage type `dtype` -- the tapped feature maps (psp_encoders.py:185-192) when the
+ *                       residual stream itself is kept in fp32.
+ *      ood_latent_assemble: the W+ assembly of Encoder4Editing.forward (psp_encoders.py:199-214) and of the arch (e4e_arch.py:261):
+ *                       heads [n_styles][B][D] fp32 = the style heads' outputs; out[b,i,:] = heads[0][b] + (1 <= i <= stage ? heads[i][b] : 0)
+ *                       + avg[:] + delta[i,:]  (avg [D], delta [n_styles,D]; either may be NULL). */
+int ood_latent_assemble(const float *heads, const float *avg, const float *delta, float *out, int batch, int n_styles, int dim,
+                        int stage, void *stream);
+/*      ood_alignnet_head_weights (a11): per-sample 1x1 projection weights of the AlignNet's 2C -> 3 head with the affine
+ *                       InstanceNorm in front of it folded in (SAMM/helpers.py:85-109; e4e/encoders/helpers.py:436-441):
+ *                       wps[b,r,c] = w27[r,c] * rstd[b,c]*in_w[c]  (rows 27..29 = w1[r-27,c] when w1 is given), bias[b,r] = sum_c
+ *                       w27[r,c] * (in_b[c] - mean[b,c]*rstd[b,c]*in_w[c]);  stats [B,C,2] = {mean, rstd}; w27 [32,C], w1 [3,C] fp32;
+ *                       wps [B,32,C] in `dtype` (OOD_BF16 | OOD_F32), bias [B,32] fp32. */
+int ood_alignnet_head_weights(const float *stats, const float *in_w, const float *in_b, const float *w27, const float *w1,
+                              void *wps, float *bias, int batch, int channels, int dtype, void *stream);
 
 /* ---- a14. backward of the synthesis path for optimisation-based inversion (autograd through model.py:233-372; weights frozen).
  *      ood_act_bwd : gv = gy*sqrt2*(y>0 ? 1 : 0.2) (gate on the saved OUTPUT, fused_bias_act_kernel.cu:36-47);  g = gv*d[b,c];

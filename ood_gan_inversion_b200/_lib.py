@@ -62,8 +62,10 @@ _SIGS = {
     'ood_tap_sum': ([c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p], c_int),
     'ood_tap_sum_shortcut': ([c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p], c_int),
     'ood_se_gate': ([c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p], c_int),
-    'ood_se_residual': ([c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+    'ood_se_residual': ([c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                         c_int, c_int, c_int, c_void_p], c_int),
+    'ood_latent_assemble': ([c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p], c_int),
+    'ood_alignnet_head_weights': ([c_void_p] * 7 + [c_int, c_int, c_int, c_void_p], c_int),
     'ood_bicubic_up_add': ([c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p], c_int),
     'ood_warp_mix_bwd': ([c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p], c_int),
     'ood_mask_blend_bwd': ([c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p], c_int),

@@ -171,10 +171,13 @@ class ood_faceGAN_e4e(nn.Module):
         return self._callback(image, **kwargs)
 
     # ---- forward -------------------------------------------------------------------------------------------------
-    def encode(self, x):
+    def encode(self, x, with_offsets=False):
         """E4E encoder on the bilinear 256x256 thumbnail -> (w [B,18,512] fp32, feats).  e4e_arch.py:256-258.
-        bf16 mode runs a cached inference copy on this library's kernels (encoder_fast.FastEncoder)."""
+        bf16 mode runs a cached inference copy on this library's kernels (encoder_fast.FastEncoder).
+        with_offsets=True returns (w + avg_latent + delta_latent, feats, True) when the offsets (e4e_arch.py:261) could be added
+        inside the W+ assembly kernel (bf16 mode, nothing to differentiate), else (w, feats, False)."""
         bf16 = sg.get_precision() == 'bf16'
+        fold = bool(with_offsets) and bf16 and not (torch.is_grad_enabled() and (self.delta_latent.requires_grad or self.avg_latent.requires_grad))
         with torch.no_grad():
             self.encoder.eval()
             if bf16:
@@ -185,11 +188,14 @@ class ood_faceGAN_e4e(nn.Module):
                 enc = self._enc_infer[1]
                 enc.progressive_stage = self.encoder.progressive_stage
                 # bilinear 1024 -> 256 thumbnail, NHWC, bf16, channels padded to the first convolution's K granule: one kernel
-                w, feats = enc(None, return_feats=True, thumb=K.thumbnail_nhwc(x.detach(), dtype=encoder_fast.ENC_DT))
+                w, feats = enc(None, return_feats=True, thumb=K.thumbnail_nhwc(x.detach(), dtype=encoder_fast.ENC_DT),
+                               avg=self.avg_latent.detach() if fold else None, delta=self.delta_latent.detach()[0] if fold else None)
             else:
                 small = F.interpolate(x, (256, 256), mode='bilinear')
                 with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
                     w, feats = self.encoder(small, return_feats=True)
+        if with_offsets:
+            return w.float(), feats, fold
         return w.float(), feats
 
     def _feats_conv_nhwc(self, i, feat):
@@ -214,8 +220,9 @@ class ood_faceGAN_e4e(nn.Module):
         if step is not None:
             self.update_stage(step, kwargs.get('logger', None))
         bf16 = sg.get_precision() == 'bf16'
-        lats, feats = self.encode(x)
-        lats = lats + self.avg_latent.reshape(1, 1, -1) + self.delta_latent
+        lats, feats, offsets_in = self.encode(x, with_offsets=True)
+        if not offsets_in:
+            lats = lats + self.avg_latent.reshape(1, 1, -1) + self.delta_latent
         truncation = kwargs.get('truncation', 1.0)
         if truncation < 1.0:
             lats = self.avg_latent.reshape(1, 1, -1) * (1. - truncation) + (lats * truncation)

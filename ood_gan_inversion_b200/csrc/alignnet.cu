@@ -541,3 +541,52 @@ extern "C" int ood_in_apply(const void *x, const float *st2, const float *w, con
     else in_apply_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16 *)x, st2, w, bias, (__nv_bfloat16 *)out, pixels, channels, chunk);
     return check_launch("in_apply");
 }
+
+// Per-sample weights of the AlignNet's 2C -> 3 head as a 1x1 projection (SAMM/helpers.py:85-109; bottleneck_IR res_layer[0..1] of
+// the second block, e4e/encoders/helpers.py:436-441): the affine InstanceNorm in front of the 3x3 convolution is folded into it,
+//   W27 . (g*x + h) = (W27 diag(g_b)) . x + W27 . h_b,   g_b = rstd_b * in_w,  h_b = in_b - mean_b * g_b     (st = {mean, rstd}),
+// so the normalised copy of x is never written.  Rows 27..29 optionally carry the bottleneck's 1x1 shortcut convolution on the
+// UN-normalised x (w1, no g, no bias), rows 30..31 are zero.  One block per image; replaces seven ATen launches per cycle.
+namespace ood {
+template <typename T>
+__global__ void __launch_bounds__(256) head_weights_kernel(const float *__restrict__ st, const float *__restrict__ in_w,
+                                                            const float *__restrict__ in_b, const float *__restrict__ w27,
+                                                            const float *__restrict__ w1, T *__restrict__ wps, float *__restrict__ bias, int C) {
+    extern __shared__ float hw_s[];          // g[C], h[C]
+    float *g = hw_s, *h = hw_s + C;
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int c = tid; c < C; c += blockDim.x) {
+        const float mean = st[((int64_t)b * C + c) * 2], rstd = st[((int64_t)b * C + c) * 2 + 1];
+        const float gg = rstd * in_w[c];
+        g[c] = gg;
+        h[c] = in_b[c] - mean * gg;
+    }
+    __syncthreads();
+    for (int i = tid; i < 32 * C; i += blockDim.x) {
+        const int r = i / C, c = i - r * C;
+        float v = w27[i] * g[c];
+        if (w1 && r >= 27 && r < 30) v = w1[(r - 27) * C + c];
+        wps[(int64_t)b * 32 * C + i] = from_f32<T>(v);
+    }
+    for (int r = warp; r < 32; r += blockDim.x / 32) {
+        float sacc = 0.f;
+        for (int c = lane; c < C; c += 32) sacc = fmaf(h[c], w27[r * C + c], sacc);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
+        if (lane == 0) bias[b * 32 + r] = sacc;
+    }
+}
+}  // namespace ood
+
+extern "C" int ood_alignnet_head_weights(const float *stats, const float *in_w, const float *in_b, const float *w27, const float *w1,
+                                         void *wps, float *bias, int batch, int channels, int dtype, void *stream) {
+    using namespace ood;
+    OOD_REQUIRE(stats && in_w && in_b && w27 && wps && bias && batch > 0 && channels > 0, "alignnet_head_weights: bad arguments");
+    const size_t smem = (size_t)channels * 2 * sizeof(float);
+    OOD_REQUIRE(smem <= 48 * 1024, "alignnet_head_weights: too many channels (%d)", channels);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (dtype == OOD_BF16) head_weights_kernel<__nv_bfloat16><<<batch, 256, smem, s>>>(stats, in_w, in_b, w27, w1, (__nv_bfloat16 *)wps, bias, channels);
+    else if (dtype == OOD_F32) head_weights_kernel<float><<<batch, 256, smem, s>>>(stats, in_w, in_b, w27, w1, (float *)wps, bias, channels);
+    else OOD_REQUIRE(false, "alignnet_head_weights: bad dtype");
+    return check_launch("alignnet_head_weights");
+}

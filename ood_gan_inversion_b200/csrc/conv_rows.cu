@@ -8,7 +8,13 @@
 //   * each input row segment [130 px x Ci] is loaded ONCE into a ring of row buffers; the three vertical taps are three
 //     ring slots, the three horizontal taps are the SAME buffer addressed with the descriptor start shifted by one pixel
 //     row (the swizzle is a function of the absolute shared-memory address, verified by scripts/probe_umma_shift.py);
-//   * accumulators: 4 TMEM buffers of Co columns, so the epilogue of row y overlaps the MMAs of rows y+1..y+3.
+//   * the three VERTICAL taps ride in the MMA's N dimension: an input row r feeds output rows r+1, r, r-1 (ky = 0, 1, 2), whose
+//     accumulators are consecutive Co-column blocks of a TMEM ring (newer rows at lower columns), so ONE tcgen05.mma of
+//     N = 3*Co per (horizontal tap, k-step) updates all three: 3*Ci/16 + 1 instructions per row instead of 9*Ci/16, each reading
+//     its A tile from shared memory once for three times the math (round 1: the single issuing thread spent ~1600 cycles per
+//     128-pixel row tile on 18 N = 32 instructions and the layer sat at 0.36 of the HBM roofline).  The first instruction of a
+//     row is split in two because only its ky = 0 block starts a new accumulator (accumulate = 0);
+//   * accumulators: a ring of 8 TMEM blocks of Co columns, so the epilogue of row y overlaps the MMAs of the following rows.
 // Activation traffic drops from 9x to (1 + 2/32)x; the layer becomes HBM-bound as it should be.
 #include <cuda.h>
 
@@ -17,9 +23,9 @@
 namespace ood {
 namespace rows {
 
-constexpr int kThreads = 320;          // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two groups: low / high half of the channels)
+constexpr int kThreads = 320;          // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two groups of four warps: even / odd output rows)
 constexpr int kStripRows = 32;
-constexpr int kNAcc = 4;
+constexpr int kNAcc = 8;            // TMEM accumulator ring: blocks of Co columns, output row n lives in block kNAcc-1 - n % kNAcc
 constexpr int kRowPx = 130;
 
 struct RowParams {
@@ -43,6 +49,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         "{\n.reg .pred p;\nRW_LOOP:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra RW_DONE;\nbra RW_LOOP;\nRW_DONE:\n}\n" ::"r"(smem_u32(bar)),
         "r"(parity)
         : "memory");
+}
+// one lane of a converged warp (elect.sync): code under this predicate is known to ptxas to run on a single thread, so the operands
+// of tcgen05.mma / TMA instructions stay in uniform registers instead of being elected and broadcast per instruction
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -122,7 +135,9 @@ struct Cfg {
     static constexpr int kRing = CI == 64 ? 5 : 8;
     static constexpr int kTmemCols = kNAcc * CO < 32 ? 32 : kNAcc * CO;
     static constexpr int kOutTile = 128 * CO * 2;                             // one staged output row tile (bf16)
-    static constexpr int kSmem = 9 * kWStride + kRing * kRowStride + 4 * kOutTile + 1024 + 512 + 2048;   // staging: 2 buffers x (y, ys); + RGB partials
+    static constexpr int kStg = CO == 64 ? 1 : 2;                             // staging buffers per epilogue group (shared-memory budget)
+    static constexpr int kSmem = 9 * kWStride + kRing * kRowStride + 2 * kStg * 2 * kOutTile + 1024 + 512 + 2 * 3 * CO * 4;   // staging: 2 groups x kStg x (y, ys); barriers; coefficients
+    static_assert(kWStride == kWTile, "the ky blocks of a horizontal tap must be contiguous (one N = 3*Co operand)");
     static constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(CO >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 };
 
@@ -143,16 +158,17 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(rows_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t *sW = smem;
     uint8_t *sR = smem + 9 * C::kWStride;
-    uint8_t *sO = sR + C::kRing * C::kRowStride;                  // staging: [2][128 px][CO] bf16, TMA-store swizzle
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sO + 4 * C::kOutTile);
+    constexpr int NSTG = C::kStg;
+    uint8_t *sO = sR + C::kRing * C::kRowStride;                  // staging: [group][NSTG][y, ys][128 px][CO] bf16, TMA-store swizzle
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sO + 2 * NSTG * 2 * C::kOutTile);
     uint64_t *full = bars, *empty = bars + C::kRing, *tfull = bars + 2 * C::kRing, *tempty = tfull + kNAcc, *wbar = tempty + kNAcc;
     uint32_t *tmem_holder = reinterpret_cast<uint32_t *>(wbar + 1);
-    float *sRGB = reinterpret_cast<float *>(bars) + 128;          // [128 px][3]: fused-ToRGB partial sums of the upper channel half
+    float *sCoef = reinterpret_cast<float *>(bars) + 128;         // [group][d, bias, s_next][CO]: epilogue coefficients of the current strip
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == 0 && lane == 0) {
         for (int i = 0; i < C::kRing; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-        for (int i = 0; i < kNAcc; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
+        for (int i = 0; i < kNAcc; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
         mbar_init(wbar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -179,9 +195,9 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
     if (warp == 0) {
         // ===================================================== TMA producer
-        if (lane == 0) {
+        if (elect_one()) {
             mbar_expect_tx(wbar, 9 * C::kWTile);
-            for (int t = 0; t < 9; ++t) tma_load_3d(sW + t * C::kWStride, &tmB, wbar, 0, 0, t);
+            for (int t = 0; t < 9; ++t) tma_load_3d(sW + ((t % 3) * 3 + t / 3) * C::kWStride, &tmB, wbar, 0, 0, t);     // smem order [kx][ky]: the ky blocks of one kx are one B operand
             Ring ring{0, 0, C::kRing};
             for (int strip = blockIdx.x; strip < p.total_strips; strip += gridDim.x) {
                 int b, ya, x0, nrows;
@@ -196,63 +212,77 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
     } else if (warp == 1) {
         // ===================================================== MMA issuer
-        if (lane == 0) {
+        if (elect_one()) {
             mbar_wait(wbar, 0);
             tc_fence_after();
-            Ring base{0, 0, C::kRing};
-            int acc = 0;
-            uint32_t acc_phase = 0;
+            Ring ring{0, 0, C::kRing};
+            uint32_t n0 = 0;                                       // output rows issued so far by this CTA (all strips)
             // descriptor halves: hi = {SBO, version, swizzle} is common to A and B (same row pitch); lo = start address >> 4
             const uint64_t dproto = make_desc<C::ROWB>(0);
             const uint32_t desc_hi = (uint32_t)(dproto >> 32);
             const uint32_t ring_lo = (uint32_t)dproto | ((smem_u32(sR) >> 4) & 0x3FFF);
             const uint32_t w_lo = (uint32_t)dproto | ((smem_u32(sW) >> 4) & 0x3FFF);
+            constexpr uint32_t kIdescNoN = C::kIdesc & ~(0x3Fu << 17);
+            // blocks [sblk, sblk + nb) of the accumulator ring (mod kNAcc) += A . B[rows of nb consecutive ky blocks]
+            auto issue = [&](int sblk, int nb, uint32_t a_lo, uint32_t b_lo, uint32_t accumulate) {
+                const int first = min(nb, kNAcc - sblk);
+                umma_bf16_split(tmem_base + (uint32_t)(sblk * CO), a_lo, desc_hi, b_lo, desc_hi, kIdescNoN | ((uint32_t)((first * CO) >> 3) << 17), accumulate);
+                if (first < nb)
+                    umma_bf16_split(tmem_base, a_lo, desc_hi, b_lo + (uint32_t)((first * C::kWTile) >> 4), desc_hi,
+                                    kIdescNoN | ((uint32_t)(((nb - first) * CO) >> 3) << 17), accumulate);
+            };
+            auto blk_of = [](uint32_t n) { return (int)(kNAcc - 1 - (n % kNAcc)); };
             for (int strip = blockIdx.x; strip < p.total_strips; strip += gridDim.x) {
                 int b, ya, x0, nrows;
                 strip_coords(strip, b, ya, x0, nrows);
-                for (int j = 0; j < nrows; ++j) {
-                    const Ring r0 = base, r1 = r0.next(), r2 = r1.next();
-                    if (j == 0) { mbar_wait(&full[r0.slot], r0.phase); mbar_wait(&full[r1.slot], r1.phase); }
-                    mbar_wait(&full[r2.slot], r2.phase);
-                    mbar_wait(&tempty[acc], acc_phase ^ 1);
+                for (int i = 0; i < nrows + 2; ++i) {              // input row ya - 1 + i feeds output rows i - ky, ky = 0..2
+                    const int k_lo = max(0, i - (nrows - 1)), k_hi = min(i, 2);
+                    mbar_wait(&full[ring.slot], ring.phase);
+                    if (k_lo == 0) {                               // output row i starts here: its block must have been drained
+                        const uint32_t n = n0 + (uint32_t)i;
+                        mbar_wait(&tempty[blk_of(n)], ((n / kNAcc) & 1) ^ 1);
+                    }
                     tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + acc * CO;
-                    const uint32_t a_lo[3] = {ring_lo + (uint32_t)r0.slot * (C::kRowStride >> 4), ring_lo + (uint32_t)r1.slot * (C::kRowStride >> 4),
-                                              ring_lo + (uint32_t)r2.slot * (C::kRowStride >> 4)};
+                    const int sblk = blk_of(n0 + (uint32_t)(i - k_lo));
+                    const int nb = k_hi - k_lo + 1;
+                    const uint32_t a_row = ring_lo + (uint32_t)ring.slot * (C::kRowStride >> 4);
 #pragma unroll
-                    for (int dy = 0; dy < 3; ++dy)
+                    for (int dx = 0; dx < 3; ++dx)
 #pragma unroll
-                        for (int dx = 0; dx < 3; ++dx)
-#pragma unroll
-                            for (int k = 0; k < CI / 16; ++k)
-                                umma_bf16_split(d_tmem, a_lo[dy] + (uint32_t)((dx * C::ROWB + k * 32) >> 4), desc_hi,
-                                                w_lo + (uint32_t)(((dy * 3 + dx) * C::kWStride + k * 32) >> 4), desc_hi, C::kIdesc,
-                                                (dy | dx | k) != 0 ? 1u : 0u);
-                    umma_commit(&empty[r0.slot]);                 // input row (y-1) has no later consumer
-                    if (j == nrows - 1) { umma_commit(&empty[r1.slot]); umma_commit(&empty[r2.slot]); }
-                    umma_commit(&tfull[acc]);
-                    if (++acc == kNAcc) { acc = 0; acc_phase ^= 1; }
-                    base.advance();
+                        for (int k = 0; k < CI / 16; ++k) {
+                            const uint32_t a_lo = a_row + (uint32_t)((dx * C::ROWB + k * 32) >> 4);
+                            const uint32_t b_lo = w_lo + (uint32_t)(((dx * 3 + k_lo) * C::kWTile + k * 32) >> 4);
+                            if (dx == 0 && k == 0 && k_lo == 0) {
+                                issue(sblk, 1, a_lo, b_lo, 0u);                                   // the new row's accumulator: overwrite
+                                if (nb > 1) issue((sblk + 1) % kNAcc, nb - 1, a_lo, b_lo + (uint32_t)(C::kWTile >> 4), 1u);
+                            } else {
+                                issue(sblk, nb, a_lo, b_lo, 1u);
+                            }
+                        }
+                    umma_commit(&empty[ring.slot]);               // every input row is consumed by exactly one group of MMAs
+                    if (i >= 2) umma_commit(&tfull[blk_of(n0 + (uint32_t)(i - 2))]);      // output row i - 2 is complete
+                    ring.advance();
                 }
-                base.advance();
-                base.advance();
+                n0 += (uint32_t)nrows;
             }
         }
     } else {
-        // ===================================================== epilogue: 8 warps.  TMEM lane quadrant = warp % 4; group g = low / high
-        // half of the output channels, so a thread owns ONE pixel x CH channels and the per-(b, channel) coefficients of
-        // a whole strip live in registers (the single-group version was latency-bound: one warp per scheduler, 425
-        // dependent instructions per row tile).
-        constexpr int CH = CO / 2;
+        // ===================================================== epilogue: two independent groups of four warps (TMEM lane quadrant =
+        // warp % 4), ALTERNATE output rows: while one group waits for its accumulator, its TMEM load or its barrier, the other
+        // one computes -- the single eight-warp group of round 1 went through every row tile in lock step (two 256-thread
+        // barriers per tile) and was latency-bound at ~1300 cycles per tile against an HBM floor of ~730.  A thread owns ONE
+        // pixel and all CO channels; the per-(image, channel) coefficients of the strip sit in shared memory (broadcast reads).
         const int quad = warp & 3;
         const int grp = (warp - 2) >> 2;
         const int m = quad * 32 + lane;
-        const int n0 = grp * CH;
-        const bool issuer = (m == 0 && grp == 0);
+        const int gt = (int)threadIdx.x - 64 - grp * 128;           // thread index inside the group
+        const bool issuer = gt == 0;
+        const int bar_id = 1 + grp;
         const float nw = (p.ep.noise && p.ep.noise_w) ? *p.ep.noise_w : 0.f;
-        int acc = 0;
-        uint32_t acc_phase = 0;
-        int sbuf = 0;                                   // staging buffer of this tile (double buffered)
+        float *coef = sCoef + grp * 3 * CO;                         // d[CO], bias[CO], s_next[CO] of the current strip's image
+        uint8_t *stage0 = sO + grp * (NSTG * 2 * C::kOutTile);
+        uint32_t nrow0 = 0;                                         // output rows of the strips before this one (all groups count alike)
+        uint32_t tile_ctr = 0;                                      // row tiles this group has staged (staging buffer parity)
         // swizzled staging row of this pixel (matches the SWIZZLE_128B / SWIZZLE_64B mode of the store maps)
         const uint32_t row_off = (uint32_t)m * (CO * 2);
         const uint32_t swz = CO == 64 ? (uint32_t)(m & 7) : (uint32_t)((m >> 1) & 3);
@@ -260,88 +290,74 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             int b, ya, x0, nrows;
             strip_coords(strip, b, ya, x0, nrows);
             const int X = x0 + m;
-            float dreg[CH], breg[CH], sreg[CH];
-#pragma unroll
-            for (int q = 0; q < CH; ++q) {
-                dreg[q] = p.ep.d ? __ldg(p.ep.d + (int64_t)b * CO + n0 + q) : 1.f;
-                breg[q] = p.ep.bias ? __ldg(p.ep.bias + n0 + q) : 0.f;
-                sreg[q] = p.ep.out_ys ? __ldg(p.ep.s_next + (int64_t)b * CO + n0 + q) : 1.f;
+            asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");           // the previous strip's coefficients are no longer read
+            for (int q = gt; q < CO; q += 128) {
+                coef[q] = p.ep.d ? __ldg(p.ep.d + (int64_t)b * CO + q) : 1.f;
+                coef[CO + q] = p.ep.bias ? __ldg(p.ep.bias + q) : 0.f;
+                coef[2 * CO + q] = p.ep.out_ys ? __ldg(p.ep.s_next + (int64_t)b * CO + q) : 1.f;
             }
-            // noise is streamed from HBM (4 B per pixel): prefetch it two row tiles ahead, or its ~1 us latency lands on the
-            // critical path of every tile (ncu: 28 % of all stall samples sat on the first use of this load)
+            asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+            const int j0 = (int)((nrow0 ^ (uint32_t)grp) & 1u);      // first row of this strip whose global index has this group's parity
+            // noise is streamed from HBM (4 B per pixel): prefetch it two of this group's rows ahead, or its ~1 us latency lands on
+            // the critical path of every tile
             const float *nzp = p.ep.noise ? p.ep.noise + b * p.ep.noise_bstride + (int64_t)ya * p.w + X : nullptr;
-            float nz0 = (nzp && 0 < nrows) ? __ldg(nzp) : 0.f;
-            float nz1 = (nzp && 1 < nrows) ? __ldg(nzp + p.w) : 0.f;
-            for (int j = 0; j < nrows; ++j) {
-                const int Y = ya + j;
-                const int64_t pix = ((int64_t)b * p.h + Y) * p.w + X;
-                const float nz_raw = nz0;
+            float nz0 = (nzp && j0 < nrows) ? __ldg(nzp + (int64_t)j0 * p.w) : 0.f;
+            float nz1 = (nzp && j0 + 2 < nrows) ? __ldg(nzp + (int64_t)(j0 + 2) * p.w) : 0.f;
+            for (int j = j0; j < nrows; j += 2) {
+                const uint32_t n = nrow0 + (uint32_t)j;
+                const int acc = (int)(kNAcc - 1 - (n % kNAcc));
+                const int pix0 = (int)(((int64_t)b * p.h + ya + j) * p.w + x0);
+                const float nz = nw * nz0;
                 nz0 = nz1;
-                nz1 = (nzp && j + 2 < nrows) ? __ldg(nzp + (int64_t)(j + 2) * p.w) : 0.f;
-                // fused ToRGB: bias + upsampled-skip term does not depend on this tile's MMAs -> issue its loads now
-                float rgb_tail[3] = {0.f, 0.f, 0.f};
-                if (p.ep.rgb_out && grp == 0) {
-#pragma unroll
-                    for (int k = 0; k < 3; ++k) rgb_tail[k] = rgb_finish(p.ep, 0.f, b, k, Y, X, p.h, p.w);
+                nz1 = (nzp && j + 4 < nrows) ? __ldg(nzp + (int64_t)(j + 4) * p.w) : 0.f;
+                uint8_t *sY = stage0 + (tile_ctr % NSTG) * 2 * C::kOutTile, *sYS = sY + C::kOutTile;
+                if (NSTG == 1) {        // one staging buffer: the store issued for the previous tile must have finished READING it
+                    if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
                 }
-                // the stores issued two tiles ago (same staging buffer) must have finished READING it
-                if (issuer) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-                uint8_t *sY = sO + sbuf * 2 * C::kOutTile, *sYS = sY + C::kOutTile;
-                asm volatile("bar.sync 1, 256;" ::: "memory");
-                mbar_wait(&tfull[acc], acc_phase);
+                mbar_wait(&tfull[acc], (n / kNAcc) & 1);
                 tc_fence_after();
-                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * CO + n0;
-                uint32_t r[CH];
-                if constexpr (CH == 32) tmem_ld32(taddr, r); else tmem_ld16(taddr, r);
+                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * CO;
+                uint32_t r[CO];
+#pragma unroll
+                for (int c = 0; c < CO / 32; ++c) tmem_ld32(taddr + c * 32, r + c * 32);
                 tmem_ld_wait();
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&tempty[acc]);           // TMEM buffer free: the MMA warp may start row y+4
-                float v[CH];
-                const float nz = nw * nz_raw;
+                if (lane == 0) mbar_arrive(&tempty[acc]);           // TMEM block free: the MMA warp may start row n + kNAcc
 #pragma unroll
-                for (int q = 0; q < CH; ++q) {
-                    v[q] = fmaf(__uint_as_float(r[q]), dreg[q], breg[q] + nz);
-
-                    if (p.ep.act == 1) v[q] = lrelu_sqrt2(v[q]);
-                }
-                float rgbp[3] = {0.f, 0.f, 0.f};
-                if (p.ep.rgb_out) {          // fused ToRGB: this thread's CH channels of the unscaled activation
+                for (int q = 0; q < CO / 8; ++q) {
+                    float v[8];
 #pragma unroll
-                    for (int k = 0; k < 3; ++k) {
-                        const float4 *wp = reinterpret_cast<const float4 *>(p.ep.rgb_w + ((int64_t)b * 3 + k) * CO + n0);
-#pragma unroll
-                        for (int q = 0; q < CH / 4; ++q) {
-                            const float4 t = __ldg(wp + q);
-                            rgbp[k] = fmaf(v[4 * q], t.x, fmaf(v[4 * q + 1], t.y, fmaf(v[4 * q + 2], t.z, fmaf(v[4 * q + 3], t.w, rgbp[k]))));
-                        }
+                    for (int h2 = 0; h2 < 2; ++h2) {
+                        const float4 dd = *reinterpret_cast<const float4 *>(coef + 8 * q + 4 * h2);
+                        const float4 bb = *reinterpret_cast<const float4 *>(coef + CO + 8 * q + 4 * h2);
+                        v[4 * h2 + 0] = fmaf(__uint_as_float(r[8 * q + 4 * h2 + 0]), dd.x, bb.x + nz);
+                        v[4 * h2 + 1] = fmaf(__uint_as_float(r[8 * q + 4 * h2 + 1]), dd.y, bb.y + nz);
+                        v[4 * h2 + 2] = fmaf(__uint_as_float(r[8 * q + 4 * h2 + 2]), dd.z, bb.z + nz);
+                        v[4 * h2 + 3] = fmaf(__uint_as_float(r[8 * q + 4 * h2 + 3]), dd.w, bb.w + nz);
                     }
-                    if (grp == 1) { sRGB[m * 3 + 0] = rgbp[0]; sRGB[m * 3 + 1] = rgbp[1]; sRGB[m * 3 + 2] = rgbp[2]; }
-                }
-                if (p.ep.out_y) {
+                    if (p.ep.act == 1) {
 #pragma unroll
-                    for (int q = 0; q < CH / 8; ++q) {
-                        const uint32_t chunk = ((uint32_t)(grp * (CH / 8) + q)) ^ swz;
+                        for (int e = 0; e < 8; ++e) v[e] = lrelu_sqrt2(v[e]);
+                    }
+                    const uint32_t chunk = (uint32_t)q ^ swz;
+                    if (p.ep.out_y)
                         *reinterpret_cast<uint4 *>(sY + row_off + chunk * 16) =
-                            make_uint4(pack_bf16x2(v[8 * q], v[8 * q + 1]), pack_bf16x2(v[8 * q + 2], v[8 * q + 3]),
-                                       pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), pack_bf16x2(v[8 * q + 6], v[8 * q + 7]));
-                    }
-                }
-                if (p.ep.out_ys) {
-#pragma unroll
-                    for (int q = 0; q < CH; ++q) v[q] *= sreg[q];
-#pragma unroll
-                    for (int q = 0; q < CH / 8; ++q) {
-                        const uint32_t chunk = ((uint32_t)(grp * (CH / 8) + q)) ^ swz;
+                            make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+                    if (p.ep.out_ys) {
+                        const float4 s0 = *reinterpret_cast<const float4 *>(coef + 2 * CO + 8 * q), s1 = *reinterpret_cast<const float4 *>(coef + 2 * CO + 8 * q + 4);
                         *reinterpret_cast<uint4 *>(sYS + row_off + chunk * 16) =
-                            make_uint4(pack_bf16x2(v[8 * q], v[8 * q + 1]), pack_bf16x2(v[8 * q + 2], v[8 * q + 3]),
-                                       pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), pack_bf16x2(v[8 * q + 6], v[8 * q + 7]));
+                            make_uint4(pack_bf16x2(v[0] * s0.x, v[1] * s0.y), pack_bf16x2(v[2] * s0.z, v[3] * s0.w),
+                                       pack_bf16x2(v[4] * s1.x, v[5] * s1.y), pack_bf16x2(v[6] * s1.z, v[7] * s1.w));
                     }
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy STS -> visible to the TMA store
-                asm volatile("bar.sync 1, 256;" ::: "memory");
+                // two staging buffers: the store of the previous tile (other buffer) has finished reading before anyone writes that
+                // buffer again in the next tile -- one wait by the issuing thread here, published by the barrier below
+                if (NSTG == 2 && issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
                 if (issuer) {                                        // 128 px x CO channels are CONTIGUOUS in NHWC: one bulk store each
-                    const int pix0 = (int)(pix - m);
                     if (p.ep.out_y)
                         asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                                      ::"l"(&tmY), "r"(smem_u32(sY)), "r"(0), "r"(pix0) : "memory");
@@ -350,18 +366,13 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                                      ::"l"(&tmYS), "r"(smem_u32(sYS)), "r"(0), "r"(pix0) : "memory");
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
-                if (p.ep.rgb_out && grp == 0) {                      // lower half + upper half (smem) + bias + upsampled skip
-#pragma unroll
-                    for (int k = 0; k < 3; ++k)
-                        p.ep.rgb_out[((int64_t)b * 3 + k) * p.h * p.w + (int64_t)Y * p.w + X] = rgbp[k] + sRGB[m * 3 + k] + rgb_tail[k];
-                }
-                sbuf ^= 1;
-                if (++acc == kNAcc) { acc = 0; acc_phase ^= 1; }
+                ++tile_ctr;
             }
+            nrow0 += (uint32_t)nrows;
         }
+        if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // this group's stores have reached global memory
     }
 
-    if (warp == 4 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // the thread (group 0, m == 0) that issued the stores
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
@@ -400,7 +411,7 @@ int conv3x3_rows(const ood_conv3x3_args &a, cudaStream_t st, int *handled) {
     // PReLU convolutions (the encoder's 64-channel layers at 128 / 256 px) stay on the generic tiles.  A PReLU form of this
     // epilogue was built and measured: 0.22 -> 0.37 ms (4 launches at 128 px: 64 strips for 148 SMs), 0.19 -> 0.22 ms at
     // 256 px, and its extra live registers made the <64,64> instance spill (512 px generator layer 0.48 -> 0.82 ms) -- removed.
-    if (a.transposed || a.dtype != OOD_BF16 || a.out_dtype == OOD_F16 || a.out_f32 || a.act == 2 || a.groups > 1 || a.acc_in || a.tiled || a.stats_out) return OOD_OK;
+    if (a.transposed || a.dtype != OOD_BF16 || a.out_dtype == OOD_F16 || a.out_f32 || a.act == 2 || a.groups > 1 || a.acc_in || a.tiled || a.stats_out || a.rgb_out) return OOD_OK;
     if (!((a.cin == 32 || a.cin == 64) && (a.cout == 32 || a.cout == 64) && a.cin >= a.cout)) return OOD_OK;
     if (a.w % 128 != 0 || a.h < 3 || (int64_t)a.batch * a.h * a.w >= (1LL << 31)) return OOD_OK;
     static EncodeFn encode = nullptr;

@@ -72,7 +72,7 @@ template <typename T, bool SF, bool OF>
 __global__ void __launch_bounds__(256) se_residual_kernel(const T *__restrict__ v, const float *__restrict__ gate,
                                                            const void *__restrict__ sc_, int ss, const float *__restrict__ bn_g,
                                                            const float *__restrict__ bn_h, void *__restrict__ out_,
-                                                           T *__restrict__ tn, int H, int W, int C, int64_t chunk) {
+                                                           T *__restrict__ tn, T *__restrict__ out_lp, int H, int W, int C, int64_t chunk) {
     constexpr int N = Vec<T>::N, N2 = N / 2;
     const int b = blockIdx.y;
     const int cv = C / N;
@@ -122,6 +122,7 @@ __global__ void __launch_bounds__(256) se_residual_kernel(const T *__restrict__ 
                 enc_store<T>((T *)out_ + off, x);
             }
         }
+        if (out_lp) enc_store<T>(out_lp + off, x);       // the residual stream in the storage type: the tapped feature maps
         if (tn) {
 #pragma unroll
             for (int j = 0; j < N2; ++j) x[j] = fma2(x[j], bg[j], bh[j]);
@@ -196,6 +197,23 @@ __global__ void __launch_bounds__(TSX * TSY) tap_sum_tile_kernel(const float *__
     }
 }
 
+// W+ assembly of Encoder4Editing.forward (psp_encoders.py:199-214) and of the arch (OOD_faceGAN_e4e_arch.py:261):
+//   w[b,0] = head_0;  w[b,i] = head_0 + head_i for 1 <= i <= stage, head_0 beyond;  out = w + avg[d] + delta[i,d]
+// heads: [n_styles][B][D] fp32 (the grouped EqualLinear outputs, one row block per head; heads beyond `stage` are not read).
+__global__ void __launch_bounds__(256) latent_assemble_kernel(const float *__restrict__ heads, const float *__restrict__ avg,
+                                                               const float *__restrict__ delta, float *__restrict__ out, int B, int n, int D,
+                                                               int stage) {
+    const int64_t total = (int64_t)B * n * D;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int d = (int)(i % D), st = (int)((i / D) % n), b = (int)(i / ((int64_t)D * n));
+        float v = heads[(int64_t)b * D + d];
+        if (st >= 1 && st <= stage) v += heads[((int64_t)st * B + b) * D + d];
+        if (avg) v += avg[d];
+        if (delta) v += delta[(int64_t)st * D + d];
+        out[i] = v;
+    }
+}
+
 static int launch_tap_sum(const float *proj, float *out, float *sc, int batch, int h, int w, int cp, cudaStream_t st) {
     OOD_REQUIRE(proj && out && batch > 0 && batch <= 65535 && h > 0 && w > 0 && cp >= (sc ? 30 : 27) && (int64_t)h * w < (1LL << 30),
                 "tap_sum: bad arguments");
@@ -234,10 +252,10 @@ extern "C" int ood_se_gate(const float *stats, const float *w1, const float *w2,
 }
 
 extern "C" int ood_se_residual(const void *v, const float *gate, const void *shortcut, int sc_stride, const float *bn_g,
-                               const float *bn_h, void *out, void *t_next, int batch, int h, int w, int channels, int dtype,
+                               const float *bn_h, void *out, void *t_next, void *out_lp, int batch, int h, int w, int channels, int dtype,
                                int shortcut_f32, int out_f32, void *stream) {
     using namespace ood;
-    OOD_REQUIRE(v && (out || t_next) && batch > 0 && batch <= 65535 && h > 0 && w > 0, "se_residual: bad arguments");
+    OOD_REQUIRE(v && (out || t_next || out_lp) && batch > 0 && batch <= 65535 && h > 0 && w > 0, "se_residual: bad arguments");
     OOD_REQUIRE(dtype == OOD_F32 || dtype == OOD_BF16 || dtype == OOD_F16, "se_residual: bad dtype");
     OOD_REQUIRE(sc_stride == 1 || sc_stride == 2, "se_residual: shortcut stride must be 1 or 2");
     OOD_REQUIRE(!t_next || (bn_g && bn_h), "se_residual: t_next needs the affine coefficients");
@@ -251,11 +269,11 @@ extern "C" int ood_se_residual(const void *v, const float *gate, const void *sho
     dim3 grid((unsigned)((P + chunk - 1) / chunk), batch);
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == OOD_F32) {
-        se_residual_kernel<float, false, false><<<grid, 256, 0, st>>>((const float *)v, gate, shortcut, sc_stride, bn_g, bn_h, out, (float *)t_next, h, w, channels, chunk);
+        se_residual_kernel<float, false, false><<<grid, 256, 0, st>>>((const float *)v, gate, shortcut, sc_stride, bn_g, bn_h, out, (float *)t_next, (float *)out_lp, h, w, channels, chunk);
     } else if (dtype == OOD_F16) {
         const __half *vv = (const __half *)v;
         __half *tn = (__half *)t_next;
-#define OOD_SE(SF, OF) se_residual_kernel<__half, SF, OF><<<grid, 256, 0, st>>>(vv, gate, shortcut, sc_stride, bn_g, bn_h, out, tn, h, w, channels, chunk)
+#define OOD_SE(SF, OF) se_residual_kernel<__half, SF, OF><<<grid, 256, 0, st>>>(vv, gate, shortcut, sc_stride, bn_g, bn_h, out, tn, (__half *)out_lp, h, w, channels, chunk)
         if (shortcut_f32 && out_f32) OOD_SE(true, true);
         else if (shortcut_f32) OOD_SE(true, false);
         else if (out_f32) OOD_SE(false, true);
@@ -264,7 +282,7 @@ extern "C" int ood_se_residual(const void *v, const float *gate, const void *sho
     } else {
         const __nv_bfloat16 *vv = (const __nv_bfloat16 *)v;
         __nv_bfloat16 *tn = (__nv_bfloat16 *)t_next;
-#define OOD_SE(SF, OF) se_residual_kernel<__nv_bfloat16, SF, OF><<<grid, 256, 0, st>>>(vv, gate, shortcut, sc_stride, bn_g, bn_h, out, tn, h, w, channels, chunk)
+#define OOD_SE(SF, OF) se_residual_kernel<__nv_bfloat16, SF, OF><<<grid, 256, 0, st>>>(vv, gate, shortcut, sc_stride, bn_g, bn_h, out, tn, (__nv_bfloat16 *)out_lp, h, w, channels, chunk)
         if (shortcut_f32 && out_f32) OOD_SE(true, true);
         else if (shortcut_f32) OOD_SE(true, false);
         else if (out_f32) OOD_SE(false, true);
@@ -272,4 +290,14 @@ extern "C" int ood_se_residual(const void *v, const float *gate, const void *sho
 #undef OOD_SE
     }
     return check_launch("se_residual");
+}
+
+extern "C" int ood_latent_assemble(const float *heads, const float *avg, const float *delta, float *out, int batch, int n_styles, int dim,
+                                   int stage, void *stream) {
+    using namespace ood;
+    OOD_REQUIRE(heads && out && batch > 0 && n_styles > 0 && dim > 0 && stage >= 0, "latent_assemble: bad arguments");
+    const int64_t total = (int64_t)batch * n_styles * dim;
+    latent_assemble_kernel<<<(unsigned)std::min<int64_t>((total + 255) / 256, kNumSMs * 8), 256, 0, (cudaStream_t)stream>>>(heads, avg, delta, out, batch,
+                                                                                                                   n_styles, dim, stage);
+    return check_launch("latent_assemble");
 }

@@ -92,13 +92,13 @@ class _HeadGroup:
                              for h in heads], 0).contiguous()
         self.lb = torch.stack([h.linear.bias.detach().float() * h.linear.lr_mul for h in heads]).contiguous()        # [n, out]
 
-    def __call__(self, x):
-        """x NHWC [B,S,S,512] -> [n, B, 512] fp32 latents"""
+    def __call__(self, x, out=None):
+        """x NHWC [B,S,S,512] -> [n, B, 512] fp32 latents (written into `out`, a contiguous [n, B, 512] fp32 slice, when given)"""
         b = x.shape[0]
         for d, (w, bias, slope, co) in enumerate(self.layers):
             x, _ = K.conv3x3(x, w, co, transposed=3, bias=bias, prelu=slope, tag='encoder_conv', groups=self.n, in_shared=(d == 0))
         y, _ = K.conv3x3(x.reshape(self.n * b, 1, 1, self.out_c), self.lw, self.out_c, transposed=4, bias=self.lb, tag='encoder_conv',
-                         groups=self.n, out_f32=True)
+                         groups=self.n, out_f32=True, out=None if out is None else out.view(self.n * b, 1, 1, self.out_c))
         return y.reshape(self.n, b, self.out_c)
 
 
@@ -130,9 +130,10 @@ class FastEncoder:
         return K.conv3x3(x, w, co, transposed=4, bias=b, tag='encoder_conv')[0]
 
     @torch.no_grad()
-    def __call__(self, x, return_feats=False, thumb=None, **kwargs):
+    def __call__(self, x, return_feats=False, thumb=None, avg=None, delta=None, **kwargs):
         """x: fp32 NCHW [B,3,256,256] (the module's input), or thumb: the same image as the first convolution's operand, bf16 NHWC
-        [B,256,256,32] with channels 3..31 zero (kernels.thumbnail_nhwc: resize + layout + cast + padding in one pass)."""
+        [B,256,256,32] with channels 3..31 zero (kernels.thumbnail_nhwc: resize + layout + cast + padding in one pass).
+        avg [1,512] / delta [1,18,512]: the arch's latent offsets (e4e_arch.py:261), added inside the W+ assembly kernel."""
         if thumb is not None:
             xp = thumb
             if xp.dtype != ENC_DT or xp.dim() != 4 or xp.shape[-1] != 32 or not xp.is_contiguous():
@@ -168,27 +169,22 @@ class FastEncoder:
             else:
                 sc, ss = cur, blk.stride                                   # MaxPool2d(1, s): strided read
             nxt = self.blocks[i + 1].bn1 if i + 1 < len(self.blocks) else (None, None)
-            cur, t = K.se_residual(v, gate, sc, ss, nxt[0], nxt[1], out_f32=True)
-            if i in (2, 6, 20, 23):
-                taps[i] = cur.to(ENC_DT)
+            if i in (2, 6, 20, 23):              # tapped blocks: the fp32 stream once more in the storage type, from the same pass
+                cur, t, taps[i] = K.se_residual(v, gate, sc, ss, nxt[0], nxt[1], out_f32=True, want_lp=True)
                 feats.append(_nchw(taps[i]))
+            else:
+                cur, t = K.se_residual(v, gate, sc, ss, nxt[0], nxt[1], out_f32=True)
         c1, c2, c3 = taps[6], taps[20], taps[23]
         # psp_encoders.py:199-214: w_i = w_0 + head_i(features); heads beyond the progressive stage repeat w_0
         stage = self.progressive_stage.value
-        coarse = self.head_groups[0](c3)                                   # [3, B, 512]
-        w0 = coarse[0]
-        w = [w0] * self.style_count
-        for i in range(1, min(stage + 1, self.coarse_ind)):
-            w[i] = w0 + coarse[i]
+        b = c3.shape[0]
+        heads = torch.empty(self.style_count, b, self.head_groups[0].out_c, device=c3.device, dtype=torch.float32)
+        self.head_groups[0](c3, out=heads[:self.coarse_ind])                   # [3, B, 512]
         if stage >= self.coarse_ind:
             p2 = K.bicubic_up_add(c3, self._lateral(0, c2))
-            mid = self.head_groups[1](p2)
-            for i in range(self.coarse_ind, min(stage + 1, self.middle_ind)):
-                w[i] = w0 + mid[i - self.coarse_ind]
+            self.head_groups[1](p2, out=heads[self.coarse_ind:self.middle_ind])
         if stage >= self.middle_ind:
             p1 = K.bicubic_up_add(p2, self._lateral(1, c1))
-            fine = self.head_groups[2](p1)
-            for i in range(self.middle_ind, min(stage + 1, self.style_count)):
-                w[i] = w0 + fine[i - self.middle_ind]
-        w = torch.stack(w, dim=1)
+            self.head_groups[2](p1, out=heads[self.middle_ind:])
+        w = K.latent_assemble(heads, min(stage, self.style_count - 1), avg, delta)
         return (w, feats) if return_feats else w

@@ -303,7 +303,7 @@ def torgb_weight(w, s, scale=None):
 # ----------------------------------------------------------------------------------------------- convolution
 def conv3x3(x, weight, cout, transposed=False, impl=0, d=None, noise=None, noise_w=None, bias=None, s_next=None,
             act=False, want_y=True, want_ys=False, out_f32=False, prelu=None, rgb=None, tag=None, groups=1, in_shared=False,
-            acc_in=None, tiled=False, stats_eps=None, out_dtype=None):
+            acc_in=None, tiled=False, stats_eps=None, out_dtype=None, out=None):
     """x NHWC [B,H,W,Ci] pre-modulated; weight packed for `impl`.  Returns (y, ys) (None where not requested).
     rgb=(wrgb [B,3,Co], bias [3], skip NCHW fp32 or None, up taps): fused ToRGB, returns (y, ys, rgb_out NCHW fp32).
     acc_in: fp32 NHWC [B,OH,OW,Co] seed added to the accumulator before the epilogue (tcgen05 path).
@@ -311,7 +311,8 @@ def conv3x3(x, weight, cout, transposed=False, impl=0, d=None, noise=None, noise
     of a seed that only ever travels between two launches with the same geometry.
     stats_eps: also return [B,Co,2] = (mean, rstd) of y as stored, computed in the epilogue -> (y, ys, stats); use
     conv3x3_stats_ok() for the envelope.
-    out_dtype: storage type of y / ys when it differs from x's (torch.bfloat16 or torch.float16; tcgen05 path)."""
+    out_dtype: storage type of y / ys when it differs from x's (torch.bfloat16 or torch.float16; tcgen05 path).
+    out: a preallocated contiguous tensor to receive y (shape / dtype checked)."""
     _cuda(x, weight, d, noise, noise_w, bias, s_next, acc_in)
     assert x.is_contiguous()
     if weight.dtype != x.dtype and impl == 0:
@@ -335,6 +336,11 @@ def conv3x3(x, weight, cout, transposed=False, impl=0, d=None, noise=None, noise
         y = torch.empty(nt, device=x.device, dtype=torch.float32)
     else:
         y = torch.empty(b, oh, ow, cout, device=x.device, dtype=torch.float32 if out_f32 else odt) if want_y else None
+    if out is not None:
+        _cuda(out)
+        if y is None or out.shape != y.shape or out.dtype != y.dtype or not out.is_contiguous():
+            raise RuntimeError(f'ood_gan_inversion_b200: conv3x3 out= must be a contiguous {None if y is None else (tuple(y.shape), y.dtype)} tensor')
+        y = out
     ys = torch.empty(b, oh, ow, cout, device=x.device, dtype=odt) if want_ys else None
     nbs = _noise_bstride(noise, b, oh, ow)
     a = ConvArgs(_ptr(x), _ptr(weight), _ptr(y), _ptr(ys), _ptr(d), _ptr(noise), nbs, _ptr(noise_w), _ptr(bias), _ptr(s_next),
@@ -654,9 +660,10 @@ def se_gate(stats, w1, w2):
     return gate
 
 
-def se_residual(v, gate=None, shortcut=None, sc_stride=1, bn_g=None, bn_h=None, want_out=True, out_f32=False):
-    """v NHWC; out = v*gate + shortcut[:, ::s, ::s]; optionally t_next = out*bn_g + bn_h.  Returns (out, t_next).
-    With bf16 activations the shortcut may be fp32 and `out` can be requested in fp32 (fp32 residual stream)."""
+def se_residual(v, gate=None, shortcut=None, sc_stride=1, bn_g=None, bn_h=None, want_out=True, out_f32=False, want_lp=False):
+    """v NHWC; out = v*gate + shortcut[:, ::s, ::s]; optionally t_next = out*bn_g + bn_h.  Returns (out, t_next), or with
+    want_lp (out, t_next, out_lp): `out` once more in v's storage type (the tapped feature maps of an fp32 residual stream).
+    With bf16 / f16 activations the shortcut may be fp32 and `out` can be requested in fp32 (fp32 residual stream)."""
     _cuda(v, gate, shortcut, bn_g, bn_h)
     assert v.is_contiguous() and (shortcut is None or shortcut.is_contiguous())
     b, h, w, c = v.shape
@@ -667,13 +674,46 @@ def se_residual(v, gate=None, shortcut=None, sc_stride=1, bn_g=None, bn_h=None, 
     out_f32 = bool(out_f32) and v.dtype != torch.float32
     out = torch.empty(v.shape, device=v.device, dtype=torch.float32 if out_f32 else v.dtype) if want_out else None
     tn = torch.empty_like(v) if bn_g is not None else None
+    lp = torch.empty_like(v) if want_lp else None
     es = _esize(v)
     nbytes = b * h * w * c * (es + (0 if shortcut is None else (4 if sc_f32 else es)) + (0 if out is None else (4 if out_f32 else es)) +
-                              (0 if tn is None else es))
+                              (0 if tn is None else es) + (0 if lp is None else es))
     with _timed('se_residual', nbytes):
         check(_lib.lib().ood_se_residual(_ptr(v), _ptr(gate), _ptr(shortcut), int(sc_stride), _ptr(bn_g), _ptr(bn_h), _ptr(out),
-                                         _ptr(tn), b, h, w, c, _dt(v), int(sc_f32), int(out_f32), _stream()), 'se_residual')
-    return out, tn
+                                         _ptr(tn), _ptr(lp), b, h, w, c, _dt(v), int(sc_f32), int(out_f32), _stream()), 'se_residual')
+    return (out, tn, lp) if want_lp else (out, tn)
+
+
+def latent_assemble(heads, stage, avg=None, delta=None):
+    """heads fp32 [n_styles, B, D] (the style heads' outputs) -> W+ codes [B, n_styles, D]: w_0 = head_0, w_i = head_0 + head_i up to
+    the progressive stage and head_0 beyond (psp_encoders.py:199-214), plus avg [D] and delta [n_styles, D] when given
+    (OOD_faceGAN_e4e_arch.py:261)."""
+    _cuda(heads, avg, delta)
+    assert heads.dtype == torch.float32 and heads.is_contiguous() and heads.dim() == 3
+    n, b, dim = heads.shape
+    avg, delta = _f32c(avg), _f32c(delta)
+    if avg is not None:
+        avg = avg.reshape(-1)
+        assert avg.numel() == dim
+    if delta is not None:
+        delta = delta.reshape(-1, dim)
+        assert delta.shape[0] == n
+    out = torch.empty(b, n, dim, device=heads.device, dtype=torch.float32)
+    check(_lib.lib().ood_latent_assemble(_ptr(heads), _ptr(avg), _ptr(delta), _ptr(out), b, n, dim, int(stage), _stream()), 'latent_assemble')
+    return out
+
+
+def alignnet_head_weights(stats, in_w, in_b, w27, w1=None, dtype=torch.bfloat16):
+    """-> (wps [B,32,C] `dtype`, bias [B,32] fp32): the AlignNet head's per-sample projection weights with the affine InstanceNorm folded
+    in (see ood_b200.h); stats [B,C,2] = {mean, rstd}; w27 [32,C]; w1 [3,C] rides in rows 27..29 when given."""
+    _cuda(stats, in_w, in_b, w27, w1)
+    b, c, _ = stats.shape
+    assert stats.dtype == torch.float32 and stats.is_contiguous() and w27.shape == (32, c) and w27.is_contiguous()
+    wps = torch.empty(b, 32, c, device=stats.device, dtype=dtype)
+    bias = torch.empty(b, 32, device=stats.device, dtype=torch.float32)
+    check(_lib.lib().ood_alignnet_head_weights(_ptr(stats), _ptr(_f32c(in_w)), _ptr(_f32c(in_b)), _ptr(w27), _ptr(_f32c(w1)), _ptr(wps), _ptr(bias),
+                                               b, c, _dt(wps), _stream()), 'alignnet_head_weights')
+    return wps, bias
 
 
 def mask_blend(fields, x, gen, want_alpha=True):

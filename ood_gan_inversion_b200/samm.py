@@ -166,15 +166,10 @@ class AlignNet(nn.Module):
         if impl == 0:
             # InstanceNorm(out0) folded into the projection: W27 . (g*out0 + h) = (W27 diag(g_b)) . out0 + W27 . h_b -- one weight
             # set per sample (grouped form, groups = batch) and a per-sample bias, so the normalised copy is never written
-            g = st[..., 1] * f(b1.res_layer[0].weight)                                   # [B, 2C]
-            h = f(b1.res_layer[0].bias) - st[..., 0] * g
             # rows 27..29 of the projection: the bottleneck's 1x1 shortcut convolution on the UN-normalised out0 (no g, no bias),
             # so out0 is read once for both branches; ood_tap_sum_shortcut hands those channels back as planes
-            wps = pk['w27'].unsqueeze(0) * g.unsqueeze(1)                                 # [B, 32, 2C] = [groups][1 tap][Co][Ci]
-            if _FOLD_SHORTCUT:
-                wps[:, 27:30] = pk['w1']
-            x, _ = K.conv3x3(out0, wps.to(torch.bfloat16), pk['cp'], transposed=4, impl=0, out_f32=True, groups=b,
-                             bias=(h @ pk['w27'].t()).contiguous())
+            wps, hb = K.alignnet_head_weights(st, b1.res_layer[0].weight, b1.res_layer[0].bias, pk['w27'], pk['w1'] if _FOLD_SHORTCUT else None)
+            x, _ = K.conv3x3(out0, wps, pk['cp'], transposed=4, impl=0, out_f32=True, groups=b, bias=hb)       # [groups][1 tap][Co][Ci]
             if _FOLD_SHORTCUT:
                 res, sc = K.tap_sum(x, shortcut=True)
             else:

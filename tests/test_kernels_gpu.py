@@ -903,3 +903,45 @@ def test_conv3x3_f16_storage(case):
     # saturation instead of inf
     big, _ = K.conv3x3(xp, wp, co, transposed=form, bias=torch.full((co,), 1e6, device=DEV))
     assert torch.isfinite(big.float()).all() and float(big.float().max()) == 65504.0
+
+
+def test_encoder_glue_kernels():
+    """ood_latent_assemble (psp_encoders.py:199-214 + e4e_arch.py:261), ood_alignnet_head_weights (the InstanceNorm folded into the
+    AlignNet head's projection) and se_residual's out_lp copy against their torch formulas."""
+    from ood_gan_inversion_b200 import kernels as K
+    n, b, dim = 18, 3, 512
+    heads, avg, delta = rnd(n, b, dim, seed=1).to(DEV), rnd(1, dim, seed=2).to(DEV), rnd(1, n, dim, seed=3).to(DEV)
+    for stage in (0, 2, 6, 17):
+        w = [heads[0]] * n
+        for i in range(1, stage + 1):
+            w[i] = heads[0] + heads[i]
+        ref = torch.stack(w, 1)
+        torch.testing.assert_close(K.latent_assemble(heads, stage), ref, rtol=0, atol=0)
+        torch.testing.assert_close(K.latent_assemble(heads, stage, avg, delta[0]), ref + avg.reshape(1, 1, -1) + delta, rtol=1e-6, atol=1e-6)
+    c = 256
+    st = torch.stack([rnd(b, c, seed=4), rnd(b, c, seed=5).abs() + 0.5], -1).contiguous().to(DEV)
+    in_w, in_b = rnd(c, seed=6).to(DEV), rnd(c, seed=7).to(DEV)
+    w27 = torch.zeros(32, c)
+    w27[:27] = rnd(27, c, seed=8)
+    w27, w1 = w27.to(DEV), rnd(3, c, seed=9).to(DEV)
+    g = st[..., 1] * in_w
+    h = in_b - st[..., 0] * g
+    ref_w = w27.unsqueeze(0) * g.unsqueeze(1)
+    for fold in (False, True):
+        wps, bias = K.alignnet_head_weights(st, in_w, in_b, w27, w1 if fold else None, dtype=torch.float32)
+        r = ref_w.clone()
+        if fold:
+            r[:, 27:30] = w1
+        torch.testing.assert_close(wps, r, rtol=1e-6, atol=1e-6)
+        torch.testing.assert_close(bias, h @ w27.t(), rtol=1e-4, atol=1e-4)
+    wps16, _ = K.alignnet_head_weights(st, in_w, in_b, w27, w1)
+    assert wps16.dtype == torch.bfloat16
+    torch.testing.assert_close(wps16.float(), r.to(torch.bfloat16).float(), rtol=0, atol=0)
+    for dt in (torch.bfloat16, torch.float16):
+        v = rnd(2, 6, 5, 64, seed=10).to(dt).to(DEV)
+        sc = rnd(2, 6, 5, 64, seed=11).to(DEV)
+        gate = torch.rand(2, 64, generator=torch.Generator().manual_seed(12)).to(DEV)
+        out, t, lp = K.se_residual(v, gate, sc, 1, torch.ones(64, device=DEV), torch.zeros(64, device=DEV), out_f32=True, want_lp=True)
+        ref_o = v.float() * gate[:, None, None, :] + sc
+        torch.testing.assert_close(out, ref_o, rtol=1e-6, atol=1e-6)
+        assert lp.dtype == dt and torch.equal(lp, ref_o.to(dt)) and torch.equal(t, lp)
