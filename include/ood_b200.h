@@ -363,6 +363,20 @@ int ood_warp_mix(const void *gen, const float *field, void *out, int batch, int 
 int ood_mask_blend(const float *const *fields_host, const int *field_sizes_host, int n_fields, const float *x,
                    const float *gen, float *out, float *alpha_out, int batch, int size, void *stream);
 
+/* ---- a14 / f3: elementwise building blocks of the differentiable alignment path (autograd through SAMM/helpers.py:85-109,149-179
+ *      and e4e/encoders/helpers.py:426-448) on NHWC activations, dtype OOD_F32 | OOD_BF16.
+ *      ood_nhwc_affine2: out[b,p,off_out+c] = a[b,c]*x1[b,p,off1+c] + b[b,c]*x2[b,p,off2+c] + c[b,c] for c < channels, every operand a
+ *                        channel slice (offset) of a tensor with `pitch` channels per pixel; x2 / a / b / c may be NULL (no second
+ *                        operand, 1, 1, 0).  The combine step of the InstanceNorm backward, residual sums / differences, channel
+ *                        concatenation and its adjoint.
+ *      ood_prelu:        g == NULL: out = x > 0 ? x : slope[c]*x;  else the backward out = g * (x > 0 ? 1 : slope[c]).
+ *      ood_tap_gather:   adjoint of ood_tap_sum: out[b,y,x,3t+k] = g[b,k,y-dy_t,x-dx_t] (zero outside; channels 27..cp-1 zero). */
+int ood_nhwc_affine2(const void *x1, int pitch1, int off1, const void *x2, int pitch2, int off2, const float *a, const float *b,
+                     const float *c, void *out, int pitch_out, int off_out, int batch, int64_t pixels, int channels, int dtype,
+                     void *stream);
+int ood_prelu(const void *x, const void *g, const float *slope, void *out, int64_t pixels_total, int channels, int dtype, void *stream);
+int ood_tap_gather(const float *g, void *out, int batch, int h, int w, int cp, int dtype, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -89,6 +89,10 @@ _SIGS = {
     'ood_alignnet_res0_stats': ([c_void_p] * 10 + [c_float, c_int, c_i64, c_int, c_int, c_void_p], c_int),
     'ood_in_apply': ([c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_i64, c_int, c_int, c_void_p], c_int),
     'ood_warp_mix': ([c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p], c_int),
+    'ood_nhwc_affine2': ([c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_i64, c_int, c_int,
+                          c_void_p], c_int),
+    'ood_prelu': ([c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_int, c_int, c_void_p], c_int),
+    'ood_tap_gather': ([c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p], c_int),
     'ood_mask_blend': ([C.POINTER(c_void_p), C.POINTER(c_int), c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                         c_void_p], c_int),
 }

@@ -39,7 +39,7 @@ class _AlignCallback:
         if self.owner.strict_rng:       # the reference evaluates randn_like(image) eagerly (e4e_arch.py:234)
             b, h, w, c = image_nhwc.shape
             torch.empty(b, c, h, w, device=image_nhwc.device, dtype=torch.float32).normal_()
-        aligned, field = mod.forward_nhwc(feat, image_nhwc, coarse)
+        aligned, field = mod.forward_nhwc(feat, image_nhwc, coarse)      # differentiable when image / coarse field / feat carry a graph
         self.owner.aligns[ind] = field
         return aligned
 
@@ -132,7 +132,12 @@ class ood_faceGAN_e4e(nn.Module):
             self.avg_latent.data = torch.load(avg_latent_pth, map_location='cpu')
         if delta_latent_pth is not None:
             self.delta_latent.data = torch.load(delta_latent_pth, map_location='cpu')
-        self.eval_path_length = bool(eval_path_length) if eval_path_length is not None else False
+        # e4e_arch.py:146-151: at the Inference stage with modulation the reference marks the encoder's codes as requiring grad,
+        # so that a forward outside torch.no_grad() builds the graph of the whole pipeline w.r.t. them (path-length evaluation)
+        if eval_path_length is not None:
+            self.eval_path_length = bool(eval_path_length)
+        else:
+            self.eval_path_length = bool(enable_modulation) and self.encoder.progressive_stage == ProgressiveStage.Inference
         self.strict_rng = False          # True: replay the reference's RNG stream bit-for-bit (wasted draws included)
         self._callback = _AlignCallback(self)
         self.feats, self.lats, self.ori_lats = None, None, None
@@ -171,13 +176,14 @@ class ood_faceGAN_e4e(nn.Module):
         return self._callback(image, **kwargs)
 
     # ---- forward -------------------------------------------------------------------------------------------------
-    def encode(self, x, with_offsets=False):
+    def encode(self, x, with_offsets=False, fold_offsets=True):
         """E4E encoder on the bilinear 256x256 thumbnail -> (w [B,18,512] fp32, feats).  e4e_arch.py:256-258.
         bf16 mode runs a cached inference copy on this library's kernels (encoder_fast.FastEncoder).
         with_offsets=True returns (w + avg_latent + delta_latent, feats, True) when the offsets (e4e_arch.py:261) could be added
         inside the W+ assembly kernel (bf16 mode, nothing to differentiate), else (w, feats, False)."""
         bf16 = sg.get_precision() == 'bf16'
-        fold = bool(with_offsets) and bf16 and not (torch.is_grad_enabled() and (self.delta_latent.requires_grad or self.avg_latent.requires_grad))
+        fold = bool(with_offsets) and bool(fold_offsets) and bf16 and \
+            not (torch.is_grad_enabled() and (self.delta_latent.requires_grad or self.avg_latent.requires_grad))
         with torch.no_grad():
             self.encoder.eval()
             if bf16:
@@ -220,7 +226,10 @@ class ood_faceGAN_e4e(nn.Module):
         if step is not None:
             self.update_stage(step, kwargs.get('logger', None))
         bf16 = sg.get_precision() == 'bf16'
-        lats, feats, offsets_in = self.encode(x, with_offsets=True)
+        grad_route = torch.is_grad_enabled() and (self.eval_path_length or self.delta_latent.requires_grad)
+        lats, feats, offsets_in = self.encode(x, with_offsets=True, fold_offsets=not grad_route)
+        if grad_route and self.eval_path_length:
+            lats.requires_grad = True                   # e4e_arch.py:258-259
         if not offsets_in:
             lats = lats + self.avg_latent.reshape(1, 1, -1) + self.delta_latent
         truncation = kwargs.get('truncation', 1.0)
@@ -249,7 +258,11 @@ class ood_faceGAN_e4e(nn.Module):
             if keys:
                 fields = [self.aligns[k] for k in keys]
                 for _ in range(self.blend_cnt):
-                    out, alpha = K.mask_blend(fields, x.detach(), out)
+                    if torch.is_grad_enabled() and (out.requires_grad or any(f.requires_grad for f in fields)):
+                        from . import samm_grad
+                        out, alpha = samm_grad.mask_blend(fields, x.detach(), out)      # backward: ood_mask_blend_bwd
+                    else:
+                        out, alpha = K.mask_blend(fields, x.detach(), out)
                 self.aligns[1024] = alpha.expand(-1, 3, -1, -1)    # 3-channel view, not materialised
         return out, lats
 

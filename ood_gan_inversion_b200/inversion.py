@@ -105,6 +105,12 @@ class LatentInverter:
 
 def invert(gen, target, base_latent, steps=500, lr=0.01, shared_delta=False, noise=None, group=None):
     """Config 4 in one call: `steps` Adam steps of pixel-MSE inversion of `target` through `gen` (frozen)."""
-    for p in gen.parameters():
-        p.requires_grad_(False)
-    return LatentInverter(generator_synthesizer(gen, noise), lr=lr, shared_delta=shared_delta, group=group).run(target, base_latent, steps)
+    params = list(gen.parameters())
+    was = [p.requires_grad for p in params]
+    for p in params:
+        p.requires_grad_(False)                    # the generator is frozen for the run (options/train/E4E_Face.yml:123-125) ...
+    try:
+        return LatentInverter(generator_synthesizer(gen, noise), lr=lr, shared_delta=shared_delta, group=group).run(target, base_latent, steps)
+    finally:
+        for p, r in zip(params, was):
+            p.requires_grad_(r)                    # ... and handed back as it was

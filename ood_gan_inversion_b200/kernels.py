@@ -782,6 +782,43 @@ def conv_scale(cin, k):
     return 1.0 / math.sqrt(cin * k * k)
 
 
+# ----------------------------------------------------------------------------------------------- differentiable-path blocks
+def affine2(x1, x2=None, a=None, b=None, c=None, out=None, channels=None, off1=0, off2=0, off_out=0):
+    """out[..., off_out:off_out+C] = a[b,c]*x1[..., off1:off1+C] + b[b,c]*x2[..., off2:off2+C] + c[b,c] on NHWC tensors (a, b, c: fp32
+    [B,C] or None = 1, 1, 0).  `out` defaults to a new [B,H,W,C] tensor; slices let one call write half of a concatenation."""
+    _cuda(x1, x2, a, b, c, out)
+    assert x1.is_contiguous() and (x2 is None or (x2.is_contiguous() and x2.dtype == x1.dtype and x2.shape[:3] == x1.shape[:3]))
+    bsz, h, w, p1 = x1.shape
+    C_ = channels if channels is not None else p1 - off1
+    if out is None:
+        out = torch.empty(bsz, h, w, C_ + off_out, device=x1.device, dtype=x1.dtype)
+    assert out.is_contiguous() and out.dtype == x1.dtype and out.shape[:3] == x1.shape[:3]
+    for t in (a, b, c):
+        assert t is None or (t.dtype == torch.float32 and t.is_contiguous() and tuple(t.shape) == (bsz, C_))
+    check(_lib.lib().ood_nhwc_affine2(_ptr(x1), p1, off1, _ptr(x2), 0 if x2 is None else x2.shape[3], off2, _ptr(a), _ptr(b), _ptr(c), _ptr(out),
+                                      out.shape[3], off_out, bsz, h * w, C_, _dt(x1), _stream()), 'nhwc_affine2')
+    return out
+
+
+def prelu(x, slope, g=None):
+    """NHWC x, slope fp32 [C]: PReLU(x); with g: the backward g * (x > 0 ? 1 : slope)."""
+    _cuda(x, slope, g)
+    assert x.is_contiguous() and (g is None or (g.is_contiguous() and g.dtype == x.dtype and g.shape == x.shape))
+    out = torch.empty_like(x)
+    check(_lib.lib().ood_prelu(_ptr(x), _ptr(g), _ptr(_f32c(slope)), _ptr(out), x.numel() // x.shape[-1], x.shape[-1], _dt(x), _stream()), 'prelu')
+    return out
+
+
+def tap_gather(g, cp=32, dtype=torch.float32):
+    """Adjoint of tap_sum: g fp32 NCHW [B,3,H,W] -> NHWC [B,H,W,cp] `dtype`, channel 3*tap + colour (see ood_b200.h)."""
+    _cuda(g)
+    g = _f32c(g)
+    b, _, h, w = g.shape
+    out = torch.empty(b, h, w, cp, device=g.device, dtype=dtype)
+    check(_lib.lib().ood_tap_gather(_ptr(g), _ptr(out), b, h, w, cp, _dt(out), _stream()), 'tap_gather')
+    return out
+
+
 # ---- device guard over every public wrapper (ADVICE round 1: a model on cuda:1 in a process whose current device is cuda:0) ----
 def _install_device_guard():
     import types

@@ -188,6 +188,35 @@ class AlignNet(nn.Module):
             return r2, sc, coef
         return r2 * coef[:, :, 0, None, None] + sc * coef[:, :, 1, None, None] + coef[:, :, 2, None, None]
 
+    def raw_diff(self, cur, enc):
+        """Differentiable form of raw_nhwc (NHWC cur, enc -> pre-activation field [B,3,R,R] fp32) for the gradient path: the same
+        arithmetic, un-fused, as a graph of diff_ops Functions (every 2C-channel pass forward and backward is a kernel of this
+        library; the 3-channel fp32 tail -- PReLU(3), conv3x3(3 -> 3), two InstanceNorm(3) -- is plain torch ops on [B,3,R,R]).
+        Gradients flow to `cur` (and to `enc` if it requires grad); see diff_ops for the weight-gradient status."""
+        from . import diff_ops as D
+        if not self.fused_ok():
+            raise NotImplementedError('ood_gan_inversion_b200: the differentiable AlignNet needs the default configuration (diff_fAndg, no biases)')
+        b0, b1 = self.body[0], self.body[1]
+        eps = self.norm.eps
+        c_hat = D.inst_norm(cur, None, None, eps)
+        with torch.set_grad_enabled(enc.requires_grad):
+            e_hat = D.inst_norm(enc, None, None, eps)
+        z = D.cat(D.sub(c_hat, e_hat), e_hat)                                    # SAMM/helpers.py:96-101
+        n0, n4 = b0.res_layer[0], b0.res_layer[4]
+        u = D.inst_norm(z, n0.weight, n0.bias, n0.eps)
+        h = D.prelu(D.conv(u, b0.res_layer[1].weight), b0.res_layer[2].weight)
+        v = D.inst_norm(D.conv(h, b0.res_layer[3].weight), n4.weight, n4.bias, n4.eps)
+        out0 = D.add(z, v)                                                      # bottleneck_IR with the identity shortcut
+        m0 = b1.res_layer[0]
+        res = D.head27(D.inst_norm(out0, m0.weight, m0.bias, m0.eps), b1.res_layer[1].weight)      # fp32 [B,3,R,R]
+        sc = D.shortcut3(out0, b1.shortcut_layer[0].weight)
+        n_res, n_sc = b1.res_layer[4], b1.shortcut_layer[1]
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+            r = F.conv2d(F.prelu(res, b1.res_layer[2].weight.float()), b1.res_layer[3].weight.float(), padding=1)
+        r = F.instance_norm(r, weight=n_res.weight.float(), bias=n_res.bias.float(), eps=n_res.eps)
+        s = F.instance_norm(sc, weight=n_sc.weight.float(), bias=n_sc.bias.float(), eps=n_sc.eps)
+        return s + r
+
     def forward(self, source, target, **kwargs):
         z = self.raw(source, target)
         return torch.cat([self.tanh(z[:, 0:1]) * self.scale, self.tanh(z[:, 1:2]) * self.scale, self.sigmoid(z[:, 2:])], dim=1)
@@ -240,6 +269,22 @@ class SPM_Warp(nn.Module):
             cur = K.warp_mix(target_nhwc, acc)
         return cur, acc
 
+    def forward_nhwc_diff(self, source, target_nhwc, aligned=None):
+        """forward_nhwc for the gradient path (SAMM/helpers.py:149-179 under autograd): differentiable in the generator features
+        `target_nhwc`, in the coarser level's field `aligned` (its alpha channel) and in `source` if it requires grad.  Forward and
+        backward of the gather / field steps are ood_warp_mix(_bwd) / ood_field_step(_bwd) (samm_grad)."""
+        from . import samm_grad
+        if self.blur.taps is None:
+            raise NotImplementedError('ood_gan_inversion_b200: SPM_Warp needs a 4-tap blur kernel')
+        src = source.to(target_nhwc.dtype).permute(0, 2, 3, 1).contiguous()
+        cur, acc = target_nhwc, None
+        for k in range(self.cycle_align):
+            z = self.body.raw_diff(cur, src)
+            last = k == self.cycle_align - 1
+            acc = samm_grad.field_step(z, acc, aligned if last else None, self.scale)
+            cur = samm_grad.warp_mix(target_nhwc, acc)
+        return cur, acc
+
     def forward(self, source, target, style=None, aligned=None):
         """Reference contract: NCHW fp32 in, (aligned_target NCHW fp32, field) out."""
         t = K.nchw_to_nhwc(target, None, sg._act_dtype())
@@ -267,6 +312,8 @@ class StyledscaleNshfitBlock(nn.Module):
     def forward_nhwc(self, x, image_nhwc, aligned=None):
         if self.alignment is None:
             return x, None
+        if torch.is_grad_enabled() and (image_nhwc.requires_grad or (aligned is not None and aligned.requires_grad) or x.requires_grad):
+            return self.alignment.forward_nhwc_diff(x, image_nhwc, aligned)
         return self.alignment.forward_nhwc(x, image_nhwc, aligned)
 
     def forward(self, x, styles, **kwargs):

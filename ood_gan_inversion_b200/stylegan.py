@@ -417,6 +417,9 @@ class ToRGB(nn.Module):
         return self.run_nhwc(_to_nhwc(input, None, self.conv.cin_p), style, skip)
 
 
+_WARNED_FROZEN = False
+
+
 class Generator(nn.Module):
     """model.py:375-585: same constructor / forward contract; the synthesis runs on the NHWC kernel pipeline."""
 
@@ -505,20 +508,53 @@ class Generator(nn.Module):
     def _synthesis(self, latent, noise, conditions, cond_layers, return_features, kwargs):
         if not latent.is_cuda:
             raise RuntimeError('ood_gan_inversion_b200 is CUDA-only: move the generator and latents to a CUDA device')
-        if torch.is_grad_enabled() and latent.requires_grad:
-            # optimisation-based inversion: differentiable w.r.t. the W+ latents (weights frozen), hand-written backward
-            if (cond_layers is not None and conditions is not None) or kwargs.get('features_in', None) is not None or return_features:
-                raise NotImplementedError('ood_gan_inversion_b200: the differentiable path covers the plain synthesis '
-                                          '(no alignment callback / features_in / return_features)')
-            from .synthesis_grad import synthesis
+        has_cond = cond_layers is not None and conditions is not None
+        grad_route = torch.is_grad_enabled() and (latent.requires_grad or bool(kwargs.get('differentiable', False)))
+        if torch.is_grad_enabled() and not grad_route and any(p.requires_grad for p in self.parameters()):
+            global _WARNED_FROZEN
+            if not _WARNED_FROZEN:
+                _WARNED_FROZEN = True
+                import warnings
+                warnings.warn('ood_gan_inversion_b200: generator parameters require grad, but this path treats the generator as frozen '
+                              '(options/train/E4E_Face.yml:123-125) -- the output carries no gradient to them; call '
+                              'requires_grad_(False) on the generator, or run under torch.no_grad(), to silence this', stacklevel=3)
+        if grad_route:
+            if kwargs.get('features_in', None) is not None:
+                raise NotImplementedError('ood_gan_inversion_b200: the differentiable path does not take features_in (Feature-Style encoder hook)')
             b = latent.shape[0]
             nz = []
             for li in range(self.num_layers):
                 res = 2 ** ((li + 5) // 2)
                 n = noise[li]
+                if has_cond and li in cond_layers:
+                    n = conditions[cond_layers.index(li)][1]            # a conditioned up-conv (layer index == latent index): its noise
+                                                                        # is conditions[ci][1], drawn when None (model.py:558-571, 277-292)
                 nz.append(n.detach().float().contiguous() if n is not None else
                           torch.empty(b, 1, res, res, device=latent.device, dtype=torch.float32).normal_())
-            return synthesis(self, latent, nz), None
+            if not has_cond and not return_features:
+                # optimisation-based inversion of the plain synthesis: ONE Function, hand-written backward (synthesis_grad)
+                from .synthesis_grad import synthesis
+                return synthesis(self, latent, nz), None
+            # something to differentiate through between the layers (alignment callback, returned features): layer-wise graph
+            from . import synthesis_diff
+            hooks = {}
+            if has_cond:
+                lat_f = latent.float()
+                for ci, i in enumerate(cond_layers):
+                    if conditions[ci][1] is not None or not kwargs.get('callback', None):
+                        continue
+                    j = i                                        # latent index i = 1 + 2*blk is also the layer index of that up-conv
+                    kw = dict(kwargs)
+                    kw.update({'index': ci, 'style': lat_f[:, i]})
+                    conv1 = self.convs[j - 1]
+                    if not hasattr(kw['callback'], 'aligned_nhwc'):
+                        raise NotImplementedError('ood_gan_inversion_b200: the differentiable path needs a callback that exposes aligned_nhwc '
+                                                  '(this package\'s arch); a foreign NCHW callback would cut the graph')
+                    hook, _ = _callback_hook(conv1.noise, nz[j], kw, conv1.conv.out_channel)
+                    hooks[j] = hook
+            image, y = synthesis_diff.synthesis(self, latent, nz, hooks, return_features)
+            feat = _to_nchw(y, self.convs[-1].conv.out_channel if self.log_size > 2 else self.conv1.conv.out_channel) if return_features else None
+            return image, feat
         lat = latent.detach().float().contiguous()
         b = lat.shape[0]
         dev = lat.device

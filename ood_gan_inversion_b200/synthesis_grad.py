@@ -78,6 +78,10 @@ class SynthesisFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_image):
+        if ctx.saved is None:
+            raise RuntimeError('ood_gan_inversion_b200: SynthesisFn.backward ran twice: the saved activations are freed after the first '
+                               'backward (retain_graph / double backward are not supported on this path; the layer-wise graph of '
+                               'synthesis_diff supports retain_graph)')
         gen, S = ctx.gen, ctx.saved
         layers = [gen.conv1] + list(gen.convs)
         rgbs = [gen.to_rgb1] + list(gen.to_rgbs)
