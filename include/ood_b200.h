@@ -377,6 +377,15 @@ int ood_nhwc_affine2(const void *x1, int pitch1, int off1, const void *x2, int p
 int ood_prelu(const void *x, const void *g, const float *slope, void *out, int64_t pixels_total, int channels, int dtype, void *stream);
 int ood_tap_gather(const float *g, void *out, int batch, int h, int w, int cp, int dtype, void *stream);
 
+/* ---- f3: weight gradient of the shared-weight convolution (the AlignNet's plain Conv2d layers, SAMM/helpers.py:85-109, trained by
+ *      src/models/OOD_faceGAN_model.py:663-789) on tcgen05: gw[o,i,ky,kx] = sum_{b,y,x} g[b,y,x,o] * x[b,y+ky-1,x+kx-1,i] (zero padding),
+ *      g NHWC bf16 [B,H,W,cout], x NHWC bf16 [B,H,W,cin], gw fp32 [cout_real][cin_real][taps] (taps = 9: 3x3 pad 1; 1: 1x1), channel
+ *      counts beyond *_real are padding.  cout % 128 == 0, cin % 64 == 0, w a divisor or a multiple of 64 (and h of 64 / w).  Deterministic
+ *      (K slices summed in a fixed order).  workspace: ood_conv_wgrad_workspace() bytes (0 = outside the envelope). */
+int64_t ood_conv_wgrad_workspace(int batch, int h, int w, int cin, int cout, int taps);
+int ood_conv_wgrad(const void *g, const void *x, float *workspace, float *gw, int batch, int h, int w, int cin, int cout, int taps,
+                   int cin_real, int cout_real, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

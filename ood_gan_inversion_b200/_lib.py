@@ -93,6 +93,8 @@ _SIGS = {
                           c_void_p], c_int),
     'ood_prelu': ([c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_int, c_int, c_void_p], c_int),
     'ood_tap_gather': ([c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p], c_int),
+    'ood_conv_wgrad_workspace': ([c_int] * 6, c_i64),
+    'ood_conv_wgrad': ([c_void_p, c_void_p, c_void_p, c_void_p] + [c_int] * 8 + [c_void_p], c_int),
     'ood_mask_blend': ([C.POINTER(c_void_p), C.POINTER(c_int), c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                         c_void_p], c_int),
 }

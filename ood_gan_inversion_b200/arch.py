@@ -219,6 +219,15 @@ class ood_faceGAN_e4e(nn.Module):
             y, _ = K.conv3x3(x, w, conv.out_channels, transposed=4, bias=b, tag='encoder_conv', out_dtype=torch.bfloat16)
         return y.permute(0, 3, 1, 2)
 
+    def _feats_conv_diff(self, i, feat):
+        """feats_conv[i] on the gradient path (the reference trains it together with `modulation`: options/train/E4E_Face.yml:123-125
+        fixes only the generator and the encoder): 1x1 convolution + bias as diff_ops Functions, so that its weight / bias gradients
+        come from ood_conv_wgrad and the bias reduction.  The encoder features themselves are constants (e4e_arch.py:256-258)."""
+        from . import diff_ops as D
+        conv = self.feats_conv[i]
+        x = feat.detach().permute(0, 2, 3, 1).contiguous().to(sg._act_dtype())
+        return D.bias_add(D.conv(x, conv.weight, '1x1'), conv.bias).permute(0, 3, 1, 2)
+
     def forward(self, x, **kwargs):
         if kwargs.get('random_gen', False):
             return self.random_gen(batch_size=kwargs.get('batch_size', 1), gen=kwargs.get('gen', True))
@@ -239,7 +248,10 @@ class ood_faceGAN_e4e(nn.Module):
         if self.modulation is None:
             out, _ = self.generator(lats, input_is_tensor=True, input_is_latent=True)
             return out, lats
-        if bf16:
+        train_feats = torch.is_grad_enabled() and any(p.requires_grad for p in self.feats_conv.parameters())
+        if train_feats:
+            self.feats = [self._feats_conv_diff(i, feats[i]) for i in range(4)]
+        elif bf16:
             self.feats = [self._feats_conv_nhwc(i, feats[i]) for i in range(4)]
         else:
             with torch.no_grad(), torch.backends.cudnn.flags(enabled=True, allow_tf32=False):

@@ -11,8 +11,10 @@ whose forward AND backward are kernels of libood_b200 (there is no torch fallbac
     Head27 / Shortcut3   the AlignNet's 2C -> 3 3x3 head (projection + tap_sum; backward tap_gather + 1x1) and its 1x1 shortcut
 
 Reference: torch.autograd through src/ops/SAMM/helpers.py:85-109 (AlignNet), e4e/encoders/helpers.py:426-448 (bottleneck_IR).
-Weight gradients: InstNorm / Shortcut3 return them (they fall out of the same reductions); Conv / Head27 / PReLU raise if their
-weights require grad (the pixel-contraction weight-gradient kernel is SURVEY section 8f rank 3, not built).
+Weight gradients (the training step of src/models/OOD_faceGAN_model.py:663-789): InstNorm / Shortcut3 / bias
+gradients fall out of the same reductions; Conv / Head27 use the tcgen05 pixel-contraction kernel (ood_conv_wgrad: both operands
+MN-major straight from NHWC, deterministic K slices); PReLU slopes = one extra reduction.  They are computed only for parameters that
+require grad, so the latent-only inversion path pays nothing for them.
 """
 import torch
 from torch.autograd import Function
@@ -81,21 +83,48 @@ def _packs(weight, kind):
     return hit
 
 
+def wgrad(g, x, taps, cout, cin):
+    """Weight gradient [cout, cin, k, k] of a shared-weight convolution from NHWC g (output gradient) and x (input).  bf16 storage:
+    one ood_conv_wgrad call.  fp32 storage (the parity mode): the tensor cores take bf16 operands, so each fp32 operand is split
+    into a bf16 head and a bf16 remainder and the three significant products are accumulated (hi*hi + hi*lo + lo*hi: ~2^-16
+    relative, against 2^-9 for a plain cast)."""
+    g, x = g.contiguous(), x.contiguous()
+    if g.dtype == torch.bfloat16:
+        return K.conv_wgrad(g, x.to(torch.bfloat16), taps, cout, cin)
+    gh, xh = g.to(torch.bfloat16), x.to(torch.bfloat16)
+    gl, xl = (g - gh.float()).to(torch.bfloat16), (x - xh.float()).to(torch.bfloat16)
+    return K.conv_wgrad(gh, xh, taps, cout, cin) + K.conv_wgrad(gh, xl, taps, cout, cin) + K.conv_wgrad(gl, xh, taps, cout, cin)
+
+
+def wgrad_ok(g_channels, x_channels, h, w):
+    return g_channels % 128 == 0 and x_channels % 64 == 0 and ((w <= 64 and 64 % w == 0 and h % (64 // w) == 0) or (w > 64 and w % 64 == 0))
+
+
 class _Conv(Function):
     @staticmethod
     def forward(ctx, x, weight, kind):
         fwd, bwd = _packs(weight, kind)
-        ctx.bwd, ctx.kind, ctx.cin = bwd, kind, x.shape[-1]
-        y, _ = K.conv3x3(x.contiguous(), fwd, weight.shape[0], transposed=4 if kind == '1x1' else 0, impl=sg._impl())
+        x = x.contiguous()
+        ctx.bwd, ctx.kind, ctx.cin, ctx.wshape = bwd, kind, x.shape[-1], tuple(weight.shape)
+        ctx.save_for_backward(x if weight.requires_grad else None)
+        y, _ = K.conv3x3(x, fwd, weight.shape[0], transposed=4 if kind == '1x1' else 0, impl=sg._impl())
         return y
 
     @staticmethod
     def backward(ctx, g):
+        g = g.contiguous()
+        gw = None
         if ctx.needs_input_grad[1]:
-            raise NotImplementedError('ood_gan_inversion_b200: weight gradient of the shared-weight convolution (SURVEY 8f rank 3) is not built; '
-                                      'freeze the AlignNet weights (requires_grad_(False)) to differentiate w.r.t. latents / features')
-        gx, _ = K.conv3x3(g.contiguous(), ctx.bwd, ctx.cin, transposed=4 if ctx.kind == '1x1' else 0, impl=sg._impl())
-        return gx, None, None
+            x, = ctx.saved_tensors
+            co, ci = ctx.wshape[:2]
+            if not wgrad_ok(g.shape[-1], x.shape[-1], x.shape[1], x.shape[2]):
+                raise NotImplementedError(f'ood_gan_inversion_b200: conv weight gradient outside the tcgen05 kernel envelope (Co {g.shape[-1]}, Ci {x.shape[-1]}, '
+                                          f'{x.shape[1]}x{x.shape[2]}): needs Co % 128 == 0, Ci % 64 == 0 and 64-pixel patches')
+            gw = wgrad(g, x, 1 if ctx.kind == '1x1' else 9, co, ci)
+        gx = None
+        if ctx.needs_input_grad[0]:
+            gx, _ = K.conv3x3(g, ctx.bwd, ctx.cin, transposed=4 if ctx.kind == '1x1' else 0, impl=sg._impl())
+        return gx, gw, None
 
 
 def conv(x, weight, kind='3x3'):
@@ -113,9 +142,13 @@ class _PReLU(Function):
     @staticmethod
     def backward(ctx, g):
         x, slope = ctx.saved_tensors
-        if ctx.needs_input_grad[1]:
-            raise NotImplementedError('ood_gan_inversion_b200: PReLU slope gradient is not built (freeze the AlignNet weights)')
-        return K.prelu(x, slope.detach(), g=g.contiguous().to(x.dtype)), None
+        g = g.contiguous().to(x.dtype)
+        gs = None
+        if ctx.needs_input_grad[1]:               # d/dslope[c] = sum g * min(x, 0):  min(x, 0) = x - relu(x)
+            relu = K.prelu(x, torch.zeros_like(slope, dtype=torch.float32))
+            neg = K.affine2(x, relu, None, torch.full((x.shape[0], x.shape[-1]), -1.0, device=x.device))
+            gs = K.dot_reduce(g, neg).sum(0).to(slope.dtype)
+        return K.prelu(x, slope.detach(), g=g), gs
 
 
 def prelu(x, slope):
@@ -185,15 +218,26 @@ class _Head27(Function):
         dt, cim = sg._act_dtype(), sg.get_precision() == 'fp32'
         proj, _ = K.conv3x3(x, K.pack_conv1x1_weight(w27, dt, cim), 32, transposed=4, impl=sg._impl(), out_f32=True)
         ctx.w27, ctx.c, ctx.dt, ctx.cim = w27, x.shape[-1], dt, cim
+        ctx.save_for_backward(x if weight.requires_grad else None)
         return K.tap_sum(proj)
 
     @staticmethod
     def backward(ctx, g):
+        gw = None
         if ctx.needs_input_grad[1]:
-            raise NotImplementedError('ood_gan_inversion_b200: weight gradient of the AlignNet head is not built (freeze the AlignNet weights)')
-        gp = K.tap_gather(g, 32, ctx.dt)                                                # [B,H,W,32]
-        gx, _ = K.conv3x3(gp, K.pack_conv1x1_weight(ctx.w27.t().contiguous(), ctx.dt, ctx.cim), ctx.c, transposed=4, impl=sg._impl())
-        return gx, None
+            # gW27[r, c] = sum_p G[p, r] * x[p, c]: the pixel contraction with the roles swapped (rows = the 2C channels of x, columns =
+            # the gathered taps, padded to 64), then back to Conv2d's [3, 2C, 3, 3]: row 3*tap + colour
+            x, = ctx.saved_tensors
+            if not wgrad_ok(x.shape[-1], 64, x.shape[1], x.shape[2]):
+                raise NotImplementedError('ood_gan_inversion_b200: AlignNet head weight gradient outside the tcgen05 kernel envelope')
+            g64 = K.tap_gather(g, 64, ctx.dt)
+            gm = wgrad(x, g64, 1, x.shape[-1], 64)[:, :27, 0, 0]                         # [2C, 27]
+            gw = gm.t().reshape(3, 3, 3, -1).permute(2, 3, 0, 1).contiguous()          # [ky, kx, colour, c] -> [colour, c, ky, kx]
+        gx = None
+        if ctx.needs_input_grad[0]:
+            gp = K.tap_gather(g, 32, ctx.dt)                                            # [B,H,W,32]
+            gx, _ = K.conv3x3(gp, K.pack_conv1x1_weight(ctx.w27.t().contiguous(), ctx.dt, ctx.cim), ctx.c, transposed=4, impl=sg._impl())
+        return gx, gw
 
 
 def head27(x, weight):
@@ -220,3 +264,24 @@ class _Shortcut3(Function):
 
 def shortcut3(x, weight):
     return _Shortcut3.apply(x, weight)
+
+
+class _BiasAdd(Function):
+    """y = x + bias[c] (NHWC)."""
+
+    @staticmethod
+    def forward(ctx, x, bias):
+        b, c = x.shape[0], x.shape[-1]
+        return K.affine2(x.contiguous(), None, None, None, bias.detach().float().reshape(1, -1).expand(b, -1).contiguous())
+
+    @staticmethod
+    def backward(ctx, g):
+        gb = None
+        if ctx.needs_input_grad[1]:
+            g = g.contiguous()
+            gb = K.in_stats(g)[..., 0].sum(0) * float(g.shape[1] * g.shape[2])
+        return (g if ctx.needs_input_grad[0] else None), gb
+
+
+def bias_add(x, bias):
+    return _BiasAdd.apply(x, bias)

@@ -819,6 +819,25 @@ def tap_gather(g, cp=32, dtype=torch.float32):
     return out
 
 
+def conv_wgrad(g, x, taps=9, cout=None, cin=None):
+    """Weight gradient of a shared-weight convolution: g NHWC bf16 [B,H,W,Co_p] (gradient of the output), x NHWC bf16 [B,H,W,Ci_p] (its
+    input) -> fp32 [cout, cin, k, k] (k = 3 for taps 9, pad 1; 1 for taps 1), PyTorch's Conv2d weight layout.  tcgen05, deterministic."""
+    _cuda(g, x)
+    assert g.is_contiguous() and x.is_contiguous() and g.dtype == torch.bfloat16 and x.dtype == torch.bfloat16 and g.shape[:3] == x.shape[:3]
+    b, h, w, co_p = g.shape
+    ci_p = x.shape[3]
+    cout, cin = cout or co_p, cin or ci_p
+    nws = _lib.lib().ood_conv_wgrad_workspace(b, h, w, ci_p, co_p, taps) // 4
+    if nws <= 0:
+        raise RuntimeError(f'ood_gan_inversion_b200: conv_wgrad envelope: cout % 128 == 0, cin % 64 == 0, 64-pixel patches (got {co_p}, {ci_p}, {h}x{w})')
+    ws = torch.empty(nws, device=g.device, dtype=torch.float32)
+    k = 3 if taps == 9 else 1
+    out = torch.empty(cout, cin, k, k, device=g.device, dtype=torch.float32)
+    with _timed('conv_wgrad', 2.0 * b * h * w * co_p * ci_p * taps):
+        check(_lib.lib().ood_conv_wgrad(_ptr(g), _ptr(x), _ptr(ws), _ptr(out), b, h, w, ci_p, co_p, taps, cin, cout, _stream()), 'conv_wgrad')
+    return out
+
+
 # ---- device guard over every public wrapper (ADVICE round 1: a model on cuda:1 in a process whose current device is cuda:0) ----
 def _install_device_guard():
     import types

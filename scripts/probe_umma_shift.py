@@ -1,8 +1,15 @@
 """GPU probe: tcgen05 descriptor start shifted by whole rows inside a swizzled TMA tile (sliding-window conv design)."""
-import ctypes as C, sys, torch
+import ctypes as C, os, subprocess, sys, torch
 sys.path.insert(0, '.')
-from ood_gan_inversion_b200 import _lib
-lib = C.CDLL(_lib.LIB_PATH)
+# the probe kernel is NOT part of libood_b200.so: it is built here into its own library, next to the product one (for its error helpers)
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+SO = os.path.join(ROOT, 'gpurun_out', 'libood_probe.so')
+os.makedirs(os.path.dirname(SO), exist_ok=True)
+subprocess.check_call(['/usr/local/cuda/bin/nvcc', '-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-std=c++17', '-Xcompiler', '-fPIC', '-shared',
+                       '-I', os.path.join(ROOT, 'ood_gan_inversion_b200', 'csrc'), os.path.join(HERE, 'probes', 'debug_umma.cu'),
+                       os.path.join(ROOT, 'ood_gan_inversion_b200', 'csrc', 'core.cu'), '-o', SO])
+lib = C.CDLL(SO)
 fn = lib.ood_debug_umma_shift
 fn.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
 fn.restype = C.c_int

@@ -1,4 +1,4 @@
-// Debug probe (not part of the product path): does a tcgen05 shared-memory descriptor whose start address is shifted by
+// Debug probe (NOT linked into libood_b200.so; built by scripts/probe_umma_shift.py into its own library): does a tcgen05 shared-memory descriptor whose start address is shifted by
 // whole rows inside a TMA-written swizzled tile address the shifted rows?  Used to validate the sliding-window conv.
 // A: [rows][K=BK] bf16 written by TMA (SW128 for BK=64, SW64 for BK=32); B: identity [N=BK][BK] -> D[m][n] = A[m+shift][n].
 #include <cuda.h>

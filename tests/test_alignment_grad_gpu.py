@@ -257,3 +257,53 @@ def test_arch_forward_builds_the_graph_like_the_reference():
     with torch.no_grad():
         out2, _ = net(x)
     assert not out2.requires_grad
+
+
+@pytest.mark.parametrize('case', [dict(b=2, h=16, w=16, ci=64, co=128, taps=9), dict(b=1, h=8, w=64, ci=64, co=128, taps=1),
+                                  dict(b=2, h=32, w=32, ci=256, co=256, taps=9), dict(b=1, h=16, w=128, ci=128, co=128, taps=9),
+                                  dict(b=3, h=4, w=16, ci=192, co=384, taps=9)])
+def test_conv_wgrad_tcgen05(case):
+    """ood_conv_wgrad (tcgen05, MN-major operands straight from NHWC, K = all pixels in deterministic slices) == autograd's weight
+    gradient of conv2d (pad 1 / 1x1) on the same bf16-rounded operands; bit-identical from run to run."""
+    from ood_gan_inversion_b200 import kernels as K
+    b, h, w, ci, co, taps = (case[k] for k in ('b', 'h', 'w', 'ci', 'co', 'taps'))
+    g = rnd(b, co, h, w, seed=1).bfloat16().float().to(DEV)
+    x = rnd(b, ci, h, w, seed=2).bfloat16().float().to(DEV)
+    k = 3 if taps == 9 else 1
+    wt = torch.zeros(co, ci, k, k, device=DEV, dtype=torch.float64, requires_grad=True)
+    F.conv2d(x.double(), wt, padding=k // 2).backward(g.double())
+    gn, xn = nhwc(g).bfloat16(), nhwc(x).bfloat16()
+    out = K.conv_wgrad(gn, xn, taps)
+    assert out.shape == (co, ci, k, k)
+    close(out, wt.grad.float(), 1e-4, 1e-5, scale=wt.grad)
+    assert torch.equal(out, K.conv_wgrad(gn, xn, taps))
+
+
+def test_alignment_parameter_gradients_vs_oracle_autograd():
+    """Training side: gradients of every AlignNet parameter (convolutions through ood_conv_wgrad, InstanceNorm affine
+    pairs, PReLU slopes, the 3-channel tail) through two alignment cycles against torch.autograd of the oracle."""
+    c, r, b = 64, 16, 2
+    blk, sd = _samm_block(c, seed=3)
+    params = {n: p for n, p in blk.named_parameters() if n.startswith('alignment.body')}
+    for p in params.values():
+        p.requires_grad_(True)
+    gen0, enc0 = rnd(b, c, r, r, seed=1), rnd(b, c, r, r, seed=2)
+    g_al, g_f = rnd(b, c, r, r, seed=4).to(DEV), rnd(b, 3, r, r, seed=5).to(DEV)
+    sdr = {k: (v.clone().requires_grad_(True) if k in params else v) for k, v in sd.items()}
+    al_r, f_r = osamm.spm_warp(sdr, 'alignment.', enc0.to(DEV), gen0.to(DEV), None, 0.08, 2)
+    names = sorted(params)
+    gr = torch.autograd.grad((al_r * g_al).sum() + (f_r * g_f).sum(), [sdr[n] for n in names])
+    gen_o = nhwc(gen0).to(DEV).requires_grad_(True)
+    al_o, f_o = blk.forward_nhwc(enc0.to(DEV), gen_o, None)
+    ((nchw(al_o) * g_al).sum() + (f_o * g_f).sum()).backward()
+    worst = 0.0
+    top = max(float(r.norm()) for r in gr)
+    for n, ref in zip(names, gr):
+        got = params[n].grad
+        assert got is not None and got.shape == ref.shape, n
+        # body.0.res_layer.4.bias shifts every channel of out0 by a constant, which the two InstanceNorms behind it remove: its true
+        # gradient is zero and both sides hold rounding noise (~1e-7 of the largest gradient), hence the absolute floor
+        rel = float((got - ref).norm() / (ref.norm() + 1e-4 * top))
+        worst = max(worst, rel)
+        assert rel < 5e-3, (n, rel, float(ref.norm()), top)
+    print(f'AlignNet parameter gradients ({len(names)} tensors): worst rel-L2 {worst:.3g}')
