@@ -307,3 +307,33 @@ def test_alignment_parameter_gradients_vs_oracle_autograd():
         worst = max(worst, rel)
         assert rel < 5e-3, (n, rel, float(ref.norm()), top)
     print(f'AlignNet parameter gradients ({len(names)} tensors): worst rel-L2 {worst:.3g}')
+
+
+def test_training_step_of_the_arch():
+    """training.generator_step on the drop-in arch (bf16 storage, two alignment levels): the reference's fix list leaves `modulation`
+    and `feats_conv` trainable (E4E_Face.yml:123-125); every parameter of the two active AlignNets and of the feats_conv layers they
+    read gets a finite gradient, and a few Adam steps on a fixed batch reduce the pixel loss."""
+    import ood_gan_inversion_b200.stylegan as sg
+    from ood_gan_inversion_b200.arch import ood_faceGAN_e4e
+    from ood_gan_inversion_b200.training import apply_fix_list, generator_step, GradAllReduce
+    sg.set_precision('bf16')
+    sd = oood.synthetic_ood_state(1024, seed=0)
+    net = ood_faceGAN_e4e(out_size=1024, style_dim=512, encoder='E4E', enable_modulation=True, warp_scale=0.08, cycle_align=2,
+                          blend_with_gen=True, ModSize=64, eval_path_length=False)
+    net.load_state_dict(sd, strict=True)
+    net = net.to(DEV).eval()
+    trainable = apply_fix_list(net)
+    names = [n for n, _ in trainable]
+    assert all(n.startswith(('modulation', 'feats_conv', 'delta_latent')) for n in names)
+    x = F.interpolate(rnd(2, 3, 64, 64, seed=2), (1024, 1024), mode='bicubic', align_corners=False).clamp(-1, 1).to(DEV)
+    target = (0.8 * x).detach()
+    opt = torch.optim.Adam([p for _, p in trainable], lr=2e-3)
+    sync = GradAllReduce([p for _, p in trainable])                  # world size 1: a no-op, exercised for its API
+    torch.manual_seed(5)
+    losses = [float(generator_step(net, x, target, opt, sync=sync)) for _ in range(4)]
+    print('training losses', losses)
+    active = [n for n in names if n.startswith(('modulation.3.alignment.body', 'modulation.2.alignment.body', 'feats_conv.3', 'feats_conv.2'))]
+    got = dict(trainable)
+    assert active and all(got[n].grad is not None and torch.isfinite(got[n].grad).all() for n in active)
+    assert any(float(got[n].grad.abs().max()) > 0 for n in active if 'res_layer.1.weight' in n)
+    assert losses[-1] < losses[0]

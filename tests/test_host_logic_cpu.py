@@ -222,3 +222,69 @@ def test_bench_product_arm_has_no_cpu_fallback():
         pytest.skip('CPU-only check')
     r = _run_bench('--steps', '1', '--warmup', '0', '--no-cpu-baseline')
     assert r.returncode != 0 and 'no CPU fallback' in r.stderr and '{' not in r.stdout
+
+
+def _grad_allreduce_worker(rank, world, port, out):
+    import torch.distributed as dist
+    from ood_gan_inversion_b200.training import GradAllReduce
+    dist.init_process_group('gloo', init_method=f'tcp://127.0.0.1:{port}', rank=rank, world_size=world)
+    try:
+        torch.manual_seed(0)
+        net = torch.nn.Sequential(torch.nn.Linear(64, 300), torch.nn.ReLU(), torch.nn.Linear(300, 200), torch.nn.ReLU(), torch.nn.Linear(200, 8))
+        unused = torch.nn.Parameter(torch.ones(5))                    # never receives a gradient
+        params = list(net.parameters()) + [unused]
+        sync = GradAllReduce(params, bucket_mb=0.1)                   # ~26k floats per bucket: several buckets
+        assert len(sync.buckets) >= 3
+        xs = torch.randn(8, 64, generator=torch.Generator().manual_seed(1))
+        ys = torch.randn(8, 8, generator=torch.Generator().manual_seed(2))
+        lo, hi = rank * 4, rank * 4 + 4
+        for step in range(2):                                         # two steps: the hook state resets
+            for p in params:
+                p.grad = None
+            torch.nn.functional.mse_loss(net(xs[lo:hi]), ys[lo:hi]).backward()
+            sync.finish()
+        got = [p.grad.clone() for p in params]
+        for p in params:
+            p.grad = None
+        torch.nn.functional.mse_loss(net(xs), ys).backward()          # the full batch on one process
+        ok = all(torch.allclose(g, p.grad if p.grad is not None else torch.zeros_like(p), rtol=1e-5, atol=1e-6) for g, p in zip(got, params))
+        out.put((rank, ok, len(sync.buckets)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_grad_allreduce_buckets_gloo_world2():
+    """training.GradAllReduce (SURVEY 8e: the training path's one collective): bucketed, hook-launched all-reduce over gloo, world size 2;
+    the averaged shard gradients equal the full-batch gradient, unused parameters average to zero, state resets between steps."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    out = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_grad_allreduce_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [out.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok, _ in res), res
+
+
+def test_apply_fix_list_matches_the_reference_yml():
+    """options/train/E4E_Face.yml:123-125: generator, avg_latent and encoder are frozen; modulation and feats_conv train."""
+    from ood_gan_inversion_b200.training import apply_fix_list
+
+    class Tiny(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.generator = torch.nn.Linear(2, 2)
+            self.encoder = torch.nn.Linear(2, 2)
+            self.modulation = torch.nn.ModuleList([torch.nn.Linear(2, 2)])
+            self.feats_conv = torch.nn.ModuleList([torch.nn.Conv2d(2, 2, 1)])
+            self.avg_latent = torch.nn.Parameter(torch.zeros(1, 2))
+            self.delta_latent = torch.nn.Parameter(torch.zeros(1, 18, 2))
+    net = Tiny()
+    names = [n for n, _ in apply_fix_list(net)]
+    assert all(n.startswith(('modulation', 'feats_conv', 'delta_latent')) for n in names) and any(n.startswith('modulation') for n in names)
+    assert not net.generator.weight.requires_grad and not net.avg_latent.requires_grad and net.feats_conv[0].bias.requires_grad
+    names = [n for n, _ in apply_fix_list(net, grad=('encoder',))]
+    assert any(n.startswith('encoder') for n in names)
