@@ -295,6 +295,12 @@ int ood_se_residual(const void *v, const float *gate, const void *shortcut, int 
  *      ood_latent_assemble: the W+ assembly of Encoder4Editing.forward (psp_encoders.py:199-214) and of the arch (e4e_arch.py:261):
  *                       heads [n_styles][B][D] fp32 = the style heads' outputs; out[b,i,:] = heads[0][b] + (1 <= i <= stage ? heads[i][b] : 0)
  *                       + avg[:] + delta[i,:]  (avg [D], delta [n_styles,D]; either may be NULL). */
+/*      ood_se_tail:     ood_in_stats + ood_se_gate + ood_se_residual of one bottleneck in ONE launch (a cluster of 8 thread blocks per image
+ *                       exchanges the channel sums through distributed shared memory): out (fp32) = v * sigmoid(w2 . relu(w1 . mean_hw(v)))
+ *                       + shortcut, t_next / out_lp as in ood_se_residual.  dtype OOD_BF16 | OOD_F16. */
+int ood_se_tail(const void *v, const float *w1, const float *w2, const void *shortcut, int sc_stride, const float *bn_g, const float *bn_h,
+                float *out, void *t_next, void *out_lp, int batch, int h, int w, int channels, int reduced, int dtype, int shortcut_f32,
+                void *stream);
 int ood_latent_assemble(const float *heads, const float *avg, const float *delta, float *out, int batch, int n_styles, int dim,
                         int stage, void *stream);
 /*      ood_alignnet_head_weights (a11): per-sample 1x1 projection weights of the AlignNet's 2C -> 3 head with the affine

@@ -11,6 +11,7 @@ namespace ood {
 
 struct ConvPhase {
     int oh, ow;           // phase output grid
+    int oy0, ox0;         // origin of the grid (a phase may cover a sub-rectangle: grid point (oy0 + i, ox0 + j))
     int py, px;           // output offset
     int ntaps;
     int dy[9], dx[9], wt[9];
@@ -107,6 +108,26 @@ static inline ConvGeom make_geom(int batch, int h, int w, int cin, int cout, int
                     }
                 p.m_total = batch * p.oh * p.ow;
             }
+    }
+    return g;
+}
+
+// The stride-2 transposed convolution (form 1) in three parts whose phase grids are exact powers of two.  The four parity phases of a
+// 2^k input have (2^k + 1 - py) x (2^k + 1 - px) outputs: rectangular 128-pixel M tiles quantise 65 columns to 128 (half-empty tiles:
+// the 512-channel layers ran at 0.43-0.48 of the tensor peak at 32-128 px).  part 0: every phase restricted to its 2^k x 2^k
+// interior; part 1: the last output row Y = 2h (phases py = 0 at oy = h); part 2: the last output column X = 2w without the corner
+// (phases px = 0 at ox = w, oy < h).  Same taps, same weights, same arithmetic per output as make_geom(transposed = 1).
+static inline ConvGeom make_geom_transposed_part(int batch, int h, int w, int cin, int cout, int part) {
+    const ConvGeom full = make_geom(batch, h, w, cin, cout, 1);
+    ConvGeom g = full;
+    g.nphases = 0;
+    for (int i = 0; i < 4; ++i) {
+        ConvPhase p = full.ph[i];
+        if (part == 0) { p.oh = h; p.ow = w; }
+        else if (part == 1) { if (p.py != 0) continue; p.oy0 = h; p.oh = 1; }                     // ow stays w + 1 - px: the corner lives here
+        else { if (p.px != 0) continue; p.ox0 = w; p.ow = 1; p.oh = h; }
+        p.m_total = batch * p.oh * p.ow;
+        g.ph[g.nphases++] = p;
     }
     return g;
 }

@@ -19,7 +19,7 @@ constexpr int TBM = 128;            // UMMA M
 // threads: warp0 TMA, warp1 MMA (+TMEM alloc), then EPW epilogue warps (template parameter of the kernel)
 
 struct TcPhase {
-    int oh, ow, py, px, ntaps;
+    int oh, ow, oy0, ox0, py, px, ntaps;
     int dy[9], dx[9], wt[9];
     int tiles_x, tiles_y, tiles_b;
     int tile_begin;                 // first global tile id of this phase
@@ -167,7 +167,7 @@ __device__ __forceinline__ TileCoord decode_tile(const TcParams &p, int tile, in
     const int tx = mt % P.tiles_x, ty = (mt / P.tiles_x) % P.tiles_y, tb = mt / (P.tiles_x * P.tiles_y);
     const int tiles_bg = P.tiles_b / p.groups;          // M tiles never straddle a group
     tc.group = tb / tiles_bg; tc.bl0 = (tb - tc.group * tiles_bg) * p.NB;
-    tc.phase = ph; tc.b0 = tc.group * p.gbatch + tc.bl0; tc.y0 = ty * p.TH; tc.x0 = tx * p.TW; tc.n0 = nt * BN;
+    tc.phase = ph; tc.b0 = tc.group * p.gbatch + tc.bl0; tc.y0 = P.oy0 + ty * p.TH; tc.x0 = P.ox0 + tx * p.TW; tc.n0 = nt * BN;
     return tc;
 }
 
@@ -270,7 +270,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const TileCoord tc = decode_tile(p, tile, BN);
             const TcPhase &P = p.ph[tc.phase];
             const int b = tc.b0 + nb, oy = tc.y0 + ty, ox = tc.x0 + tx;
-            const bool valid = tc.bl0 + nb < p.gbatch && oy < P.oh && ox < P.ow;
+            const bool valid = tc.bl0 + nb < p.gbatch && oy < P.oy0 + P.oh && ox < P.ox0 + P.ow;
             const int gofs = tc.group * p.cout;           // per-group bias / PReLU slopes: [groups][Co]
             const int Y = oy * p.sy + P.py, X = ox * p.sx + P.px;
             const int64_t pix = ((int64_t)b * p.OH + Y) * p.OW + X;
@@ -601,7 +601,7 @@ static void plan_tiles(const ood_conv3x3_args &a, const ConvGeom &g, TcParams &p
         for (int i = 0; i < g.nphases; ++i) {
             TcPhase &P = p.ph[i];
             const ConvPhase &G = g.ph[i];
-            P.oh = G.oh; P.ow = G.ow; P.py = G.py; P.px = G.px; P.ntaps = G.ntaps;
+            P.oh = G.oh; P.ow = G.ow; P.oy0 = G.oy0; P.ox0 = G.ox0; P.py = G.py; P.px = G.px; P.ntaps = G.ntaps;
             for (int t = 0; t < 9; ++t) { P.dy[t] = G.dy[t]; P.dx[t] = G.dx[t]; P.wt[t] = G.wt[t]; }
             P.tiles_x = ceil_div(G.ow, p.TW); P.tiles_y = ceil_div(G.oh, p.TH); P.tiles_b = groups * ceil_div(p.gbatch, p.NB);
             P.tile_begin = tiles;
@@ -615,7 +615,25 @@ static void plan_tiles(const ood_conv3x3_args &a, const ConvGeom &g, TcParams &p
     p.total_tiles = tiles;
 }
 
+static int conv3x3_tc_geom(const ood_conv3x3_args &a, const ConvGeom &g, cudaStream_t st);
+
+static bool pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
 int conv3x3_tc(const ood_conv3x3_args &a, cudaStream_t st) {
+    // stride-2 transposed convolution of a power-of-two input: interior + last row + last column, each with exact tiles
+    static int split_t = -1;
+    if (split_t < 0) { const char *e = getenv("OOD_SPLIT_TRANSPOSED"); split_t = (e && e[0] == '0') ? 0 : 1; }
+    if (a.transposed == 1 && split_t && pow2(a.h) && pow2(a.w) && a.h >= 16 && a.w >= 16 && !a.acc_in && !a.tiled && !a.stats_out && a.groups <= 1) {
+        for (int part = 0; part < 3; ++part) {
+            const int rc = conv3x3_tc_geom(a, make_geom_transposed_part(a.batch, a.h, a.w, a.cin, a.cout, part), st);
+            if (rc != OOD_OK) return rc;
+        }
+        return OOD_OK;
+    }
+    return conv3x3_tc_geom(a, make_geom(a.batch, a.h, a.w, a.cin, a.cout, a.transposed), st);
+}
+
+static int conv3x3_tc_geom(const ood_conv3x3_args &a, const ConvGeom &g, cudaStream_t st) {
     OOD_REQUIRE(a.dtype == OOD_BF16 || a.dtype == OOD_F16, "conv3x3 tc: storage type must be bf16 or f16");
     OOD_REQUIRE(a.out_dtype == 0 || a.out_dtype == OOD_BF16 || a.out_dtype == OOD_F16, "conv3x3 tc: out_dtype must be 0, OOD_BF16 or OOD_F16");
     OOD_REQUIRE(!a.stats_out || (a.dtype == OOD_BF16 && a.out_dtype != OOD_F16), "conv3x3 tc: the fused statistics are built for bf16 outputs");
@@ -632,7 +650,6 @@ int conv3x3_tc(const ood_conv3x3_args &a, cudaStream_t st) {
     OOD_REQUIRE(!(a.acc_in || a.tiled) || (a.cout % 128 == 0 && a.transposed != 1),
                 "conv3x3 tc: acc_in / tiled need cout %% 128 == 0 (got %d) and a single-phase form", a.cout);
     OOD_REQUIRE(!a.tiled || a.acc_in || (a.out_f32 && a.out_y), "conv3x3 tc: tiled = 1 without a tile-order tensor (acc_in, or out_y with out_f32)");
-    const ConvGeom g = make_geom(a.batch, a.h, a.w, a.cin, a.cout, a.transposed);
     const int BK = (a.cin % 64 == 0) ? 64 : 32;
     int BN = 0;
 

@@ -6,7 +6,11 @@
 //   se_residual: out = v * gate + shortcut(x) in one pass, which also emits the NEXT block's BN1(out) so that the
 //                normalised copy never costs a pass of its own.
 // PyTorch runs this tail as ~8 elementwise / reduction kernels per block (24 blocks).
+#include <cooperative_groups.h>
+
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace ood {
 
@@ -197,6 +201,116 @@ __global__ void __launch_bounds__(TSX * TSY) tap_sum_tile_kernel(const float *__
     }
 }
 
+// The whole squeeze-excite tail of a bottleneck in ONE launch (helpers.py:59-76 + :494-501): channel means of v over the pixels, the
+// two-layer gate, out = v * gate + shortcut, the next block's BatchNorm and the tapped copy.  Round 1 ran it as four launches
+// (statistics partial + finalise, gate, residual) on tensors of 8-33 MB: 96 launches per step whose ramp-up and tail, not their
+// bytes, cost ~1.4 ms.  Here a thread-block CLUSTER of 8 CTAs owns one image: every CTA sums its pixel chunk per channel, the
+// partial sums are exchanged through distributed shared memory (cluster barrier, fixed rank order: every CTA computes the same
+// gate, bit for bit), and the second pass re-reads v (it was just written by the convolution: an L2 hit).
+constexpr int kSeCluster = 8;
+template <typename T, bool SF>
+__global__ void __cluster_dims__(kSeCluster, 1, 1) __launch_bounds__(256)
+se_tail_kernel(const T *__restrict__ v, const float *__restrict__ w1, const float *__restrict__ w2, const void *__restrict__ sc_, int ss,
+               const float *__restrict__ bn_g, const float *__restrict__ bn_h, float *__restrict__ out, T *__restrict__ tn, T *__restrict__ out_lp,
+               int H, int W, int C, int Cr) {
+    constexpr int N = Vec<T>::N, N2 = N / 2;
+    extern __shared__ float se_s[];                   // part[C] | mean[C] | hid[Cr] | gate[C] | red[lanes][C]
+    float *part = se_s, *mean = se_s + C, *hid = se_s + 2 * C, *gate_s = hid + Cr, *red = gate_s + C;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int b = blockIdx.y, rank = (int)cluster.block_rank();
+    const int cv = C / N, lanes = blockDim.x / cv;
+    const int vec = threadIdx.x % cv, lane = threadIdx.x / cv;
+    const int c = vec * N;
+    const int64_t P = (int64_t)H * W;
+    const int64_t chunk = (P + kSeCluster - 1) / kSeCluster;
+    const int64_t p0 = (int64_t)rank * chunk, p1 = min(p0 + chunk, P);
+    // ---- pass 1: per-channel sums of this CTA's pixels
+    float2 acc[N2];
+#pragma unroll
+    for (int j = 0; j < N2; ++j) acc[j] = f2(0.f);
+    if (lane < lanes) {
+        for (int64_t p = p0 + lane; p < p1; p += lanes) {
+            float2 x[N2];
+            enc_load<T>(v + ((int64_t)b * P + p) * C + c, x);
+#pragma unroll
+            for (int j = 0; j < N2; ++j) acc[j] = add2(acc[j], x[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < N2; ++j) { red[lane * C + c + 2 * j] = acc[j].x; red[lane * C + c + 2 * j + 1] = acc[j].y; }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < C; i += blockDim.x) {
+        float s = 0.f;
+        for (int l = 0; l < lanes; ++l) s += red[l * C + i];
+        part[i] = s;
+    }
+    cluster.sync();
+    // ---- the gate, computed identically by every CTA of the cluster from the 8 partial sums (fixed order)
+    for (int i = threadIdx.x; i < C; i += blockDim.x) {
+        float s = 0.f;
+#pragma unroll
+        for (int r = 0; r < kSeCluster; ++r) s += cluster.map_shared_rank(part, r)[i];
+        mean[i] = s / (float)P;
+    }
+    cluster.sync();                                   // every remote read of `part` is done (no CTA may run ahead and exit)
+    {
+        const int wlane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        for (int j = warp; j < Cr; j += blockDim.x / 32) {
+            const float *wr = w1 + (int64_t)j * C;
+            float s = 0.f;
+            for (int i = wlane; i < C; i += 32) s = fmaf(wr[i], mean[i], s);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (wlane == 0) hid[j] = fmaxf(s, 0.f);
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < C; i += blockDim.x) {
+            const float *wr = w2 + (int64_t)i * Cr;
+            float s = 0.f;
+            for (int j = 0; j < Cr; ++j) s = fmaf(wr[j], hid[j], s);
+            gate_s[i] = 1.f / (1.f + __expf(-s));
+        }
+        __syncthreads();
+    }
+    // ---- pass 2: out = v * gate + shortcut (fp32 stream), next block's BatchNorm, tapped copy
+    if (lane >= lanes) return;
+    float2 g[N2], bg[N2], bh[N2];
+#pragma unroll
+    for (int j = 0; j < N2; ++j) {
+        g[j] = make_float2(gate_s[c + 2 * j], gate_s[c + 2 * j + 1]);
+        bg[j] = tn ? make_float2(bn_g[c + 2 * j], bn_g[c + 2 * j + 1]) : f2(1.f);
+        bh[j] = tn ? make_float2(bn_h[c + 2 * j], bn_h[c + 2 * j + 1]) : f2(0.f);
+    }
+    const int Ws = W * ss;
+    for (int64_t p = p0 + lane; p < p1; p += lanes) {
+        const int64_t off = ((int64_t)b * P + p) * C + c;
+        float2 x[N2];
+        enc_load<T>(v + off, x);
+        int64_t soff = off;
+        if (ss != 1) {
+            const int y = (int)(p / W), xx = (int)(p - (int64_t)y * W);
+            soff = (((int64_t)b * H * ss + (int64_t)y * ss) * Ws + (int64_t)xx * ss) * C + c;
+        }
+        float2 s[N2];
+        if (SF) {
+#pragma unroll
+            for (int q = 0; q < N / 4; ++q) enc_load<float>((const float *)sc_ + soff + 4 * q, s + 2 * q);
+        } else {
+            enc_load<T>((const T *)sc_ + soff, s);
+        }
+#pragma unroll
+        for (int j = 0; j < N2; ++j) x[j] = fma2(x[j], g[j], s[j]);
+#pragma unroll
+        for (int q = 0; q < N / 4; ++q) enc_store<float>(out + off + 4 * q, x + 2 * q);
+        if (out_lp) enc_store<T>(out_lp + off, x);
+        if (tn) {
+#pragma unroll
+            for (int j = 0; j < N2; ++j) x[j] = fma2(x[j], bg[j], bh[j]);
+            enc_store<T>(tn + off, x);
+        }
+    }
+}
+
 // W+ assembly of Encoder4Editing.forward (psp_encoders.py:199-214) and of the arch (OOD_faceGAN_e4e_arch.py:261):
 //   w[b,0] = head_0;  w[b,i] = head_0 + head_i for 1 <= i <= stage, head_0 beyond;  out = w + avg[d] + delta[i,d]
 // heads: [n_styles][B][D] fp32 (the grouped EqualLinear outputs, one row block per head; heads beyond `stage` are not read).
@@ -300,4 +414,30 @@ extern "C" int ood_latent_assemble(const float *heads, const float *avg, const f
     latent_assemble_kernel<<<(unsigned)std::min<int64_t>((total + 255) / 256, kNumSMs * 8), 256, 0, (cudaStream_t)stream>>>(heads, avg, delta, out, batch,
                                                                                                                    n_styles, dim, stage);
     return check_launch("latent_assemble");
+}
+
+extern "C" int ood_se_tail(const void *v, const float *w1, const float *w2, const void *shortcut, int sc_stride, const float *bn_g, const float *bn_h,
+                           float *out, void *t_next, void *out_lp, int batch, int h, int w, int channels, int reduced, int dtype, int shortcut_f32,
+                           void *stream) {
+    using namespace ood;
+    OOD_REQUIRE(v && w1 && w2 && shortcut && out && batch > 0 && batch <= 65535 && h > 0 && w > 0 && reduced > 0, "se_tail: bad arguments");
+    OOD_REQUIRE(dtype == OOD_BF16 || dtype == OOD_F16, "se_tail: storage type must be bf16 or f16 (fp32 residual stream out)");
+    OOD_REQUIRE(sc_stride == 1 || sc_stride == 2, "se_tail: shortcut stride must be 1 or 2");
+    OOD_REQUIRE(!t_next || (bn_g && bn_h), "se_tail: t_next needs the affine coefficients");
+    OOD_REQUIRE(channels % 8 == 0 && channels / 8 <= 256 && 256 % (channels / 8) == 0, "se_tail: channels (%d) must be 8 * a divisor of 256", channels);
+    const int lanes = 256 / (channels / 8);
+    const size_t smem = (size_t)(3 * channels + reduced + lanes * channels) * sizeof(float);
+    OOD_REQUIRE(smem <= 200 * 1024, "se_tail: too many channels (%d)", channels);
+    dim3 grid(kSeCluster, batch);
+    cudaStream_t st = (cudaStream_t)stream;
+#define OOD_SET(T, SF)                                                                                                              \
+    do {                                                                                                                            \
+        auto kern = se_tail_kernel<T, SF>;                                                                                          \
+        if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                   \
+        kern<<<grid, 256, smem, st>>>((const T *)v, w1, w2, shortcut, sc_stride, bn_g, bn_h, out, (T *)t_next, (T *)out_lp, h, w, channels, reduced); \
+    } while (0)
+    if (dtype == OOD_F16) { if (shortcut_f32) OOD_SET(__half, true); else OOD_SET(__half, false); }
+    else { if (shortcut_f32) OOD_SET(__nv_bfloat16, true); else OOD_SET(__nv_bfloat16, false); }
+#undef OOD_SET
+    return check_launch("se_tail");
 }

@@ -684,6 +684,24 @@ def se_residual(v, gate=None, shortcut=None, sc_stride=1, bn_g=None, bn_h=None, 
     return (out, tn, lp) if want_lp else (out, tn)
 
 
+def se_tail(v, w1, w2, shortcut, sc_stride=1, bn_g=None, bn_h=None, want_lp=False):
+    """The squeeze-excite tail of an IR-SE bottleneck in one launch: v NHWC (bf16 / f16) -> (out fp32 = v * gate + shortcut[:, ::s, ::s],
+    t_next = out*bn_g + bn_h in v's type or None, out_lp = out in v's type or None); gate = sigmoid(w2 . relu(w1 . mean_hw(v)))."""
+    _cuda(v, w1, w2, shortcut, bn_g, bn_h)
+    assert v.is_contiguous() and shortcut.is_contiguous() and shortcut.dtype in (v.dtype, torch.float32)
+    b, h, w, c = v.shape
+    assert shortcut.shape == (b, h * sc_stride, w * sc_stride, c), 'shortcut must be exactly stride x the output size'
+    out = torch.empty(b, h, w, c, device=v.device, dtype=torch.float32)
+    tn = torch.empty_like(v) if bn_g is not None else None
+    lp = torch.empty_like(v) if want_lp else None
+    es = _esize(v)
+    nbytes = b * h * w * c * (2 * es + shortcut.element_size() + 4 + (0 if tn is None else es) + (0 if lp is None else es))
+    with _timed('se_tail', nbytes):
+        check(_lib.lib().ood_se_tail(_ptr(v), _ptr(w1), _ptr(w2), _ptr(shortcut), int(sc_stride), _ptr(bn_g), _ptr(bn_h), _ptr(out), _ptr(tn), _ptr(lp),
+                                     b, h, w, c, w1.shape[0], _dt(v), int(shortcut.dtype == torch.float32), _stream()), 'se_tail')
+    return out, tn, lp
+
+
 def latent_assemble(heads, stage, avg=None, delta=None):
     """heads fp32 [n_styles, B, D] (the style heads' outputs) -> W+ codes [B, n_styles, D]: w_0 = head_0, w_i = head_0 + head_i up to
     the progressive stage and head_0 beyond (psp_encoders.py:199-214), plus avg [D] and delta [n_styles, D] when given

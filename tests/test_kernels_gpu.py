@@ -945,3 +945,46 @@ def test_encoder_glue_kernels():
         ref_o = v.float() * gate[:, None, None, :] + sc
         torch.testing.assert_close(out, ref_o, rtol=1e-6, atol=1e-6)
         assert lp.dtype == dt and torch.equal(lp, ref_o.to(dt)) and torch.equal(t, lp)
+
+
+@pytest.mark.parametrize('dt', [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize('case', [dict(b=3, h=8, w=8, c=256, stride=1, sc_f32=True, tap=True), dict(b=2, h=6, w=10, c=64, stride=2, sc_f32=False, tap=False),
+                                  dict(b=16, h=4, w=4, c=512, stride=1, sc_f32=True, tap=False), dict(b=1, h=33, w=17, c=128, stride=2, sc_f32=True, tap=True)])
+def test_se_tail_cluster_kernel(dt, case):
+    """ood_se_tail (one launch, a cluster of 8 CTAs per image, channel sums through distributed shared memory) == in_stats -> se_gate ->
+    se_residual, and == the torch formula of SEModule + residual (helpers.py:59-76, 494-501)."""
+    from ood_gan_inversion_b200 import kernels as K
+    b, h, w, c, stride = (case[k] for k in ('b', 'h', 'w', 'c', 'stride'))
+    cr = c // 16
+    v = rnd(b, h, w, c, seed=1).to(dt).to(DEV)
+    sc = rnd(b, h * stride, w * stride, c, seed=2)
+    sc = (sc if case['sc_f32'] else sc.to(dt)).to(DEV)
+    w1, w2 = (rnd(cr, c, seed=3) / c ** 0.5).to(DEV), (rnd(c, cr, seed=4) / cr ** 0.5).to(DEV)
+    bn_g, bn_h = (1 + 0.1 * rnd(c, seed=5)).to(DEV), (0.1 * rnd(c, seed=6)).to(DEV)
+    out, tn, lp = K.se_tail(v, w1, w2, sc, stride, bn_g, bn_h, want_lp=case['tap'])
+    mean = v.float().mean((1, 2))
+    gate = torch.sigmoid(torch.relu(mean @ w1.t()) @ w2.t())
+    ref = v.float() * gate[:, None, None, :] + sc.float()[:, ::stride, ::stride]
+    torch.testing.assert_close(out, ref, rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(tn.float(), (ref * bn_g + bn_h).to(dt).float(), rtol=1e-2, atol=1e-2)
+    if case['tap']:
+        torch.testing.assert_close(lp.float(), ref.to(dt).float(), rtol=1e-2, atol=1e-2)
+    g2 = K.se_gate(K.in_stats(v), w1, w2)
+    r = K.se_residual(v, g2, sc, stride, bn_g, bn_h, out_f32=True)
+    torch.testing.assert_close(out, r[0], rtol=1e-5, atol=1e-5)
+    assert torch.equal(out, K.se_tail(v, w1, w2, sc, stride, bn_g, bn_h)[0])          # deterministic
+
+
+@pytest.mark.parametrize('case', [dict(b=2, h=64, w=64, ci=128, co=128), dict(b=1, h=16, w=32, ci=64, co=256), dict(b=3, h=32, w=16, ci=64, co=64),
+                                  dict(b=1, h=128, w=128, ci=64, co=64)])
+def test_conv_transposed_split_into_exact_tiles(case, monkeypatch):
+    """Form 1 on a power-of-two input runs as interior + last row + last column (conv_common.cuh: make_geom_transposed_part): every one
+    of the (2h+1) x (2w+1) outputs is written exactly once and equals conv_transpose2d(stride 2); identical to the unsplit route."""
+    b, h, w_, ci, co = case['b'], case['h'], case['w'], case['ci'], case['co']
+    x, w = rnd(b, ci, h, w_, seed=1).bfloat16().float(), (0.2 * rnd(co, ci, 3, 3, seed=2)).bfloat16().float()
+    wp = K().pack_conv_weight(w.to(DEV), torch.bfloat16, False)
+    xn = nhwc(x, torch.bfloat16)
+    y, _ = K().conv3x3(xn, wp, co, transposed=True, impl=0, out_f32=True)
+    assert y.shape == (b, 2 * h + 1, 2 * w_ + 1, co)
+    ref = conv_ref(x.double(), w.double(), True).float()
+    torch.testing.assert_close(nchw(y), ref, rtol=1e-4, atol=2e-3)
