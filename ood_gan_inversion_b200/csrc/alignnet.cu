@@ -562,13 +562,15 @@ __global__ void __launch_bounds__(256) head_weights_kernel(const float *__restri
         h[c] = in_b[c] - mean * gg;
     }
     __syncthreads();
-    for (int i = tid; i < 32 * C; i += blockDim.x) {
+    // blockIdx.y owns rows [r0, r0 + rows): 8 row groups per image, so that 16 images fill 128 SMs instead of 16
+    const int rows = 32 / gridDim.y, r0 = blockIdx.y * rows;
+    for (int i = r0 * C + tid; i < (r0 + rows) * C; i += blockDim.x) {
         const int r = i / C, c = i - r * C;
         float v = w27[i] * g[c];
         if (w1 && r >= 27 && r < 30) v = w1[(r - 27) * C + c];
         wps[(int64_t)b * 32 * C + i] = from_f32<T>(v);
     }
-    for (int r = warp; r < 32; r += blockDim.x / 32) {
+    for (int r = r0 + warp; r < r0 + rows; r += blockDim.x / 32) {
         float sacc = 0.f;
         for (int c = lane; c < C; c += 32) sacc = fmaf(h[c], w27[r * C + c], sacc);
 #pragma unroll
@@ -585,8 +587,9 @@ extern "C" int ood_alignnet_head_weights(const float *stats, const float *in_w, 
     const size_t smem = (size_t)channels * 2 * sizeof(float);
     OOD_REQUIRE(smem <= 48 * 1024, "alignnet_head_weights: too many channels (%d)", channels);
     cudaStream_t s = (cudaStream_t)stream;
-    if (dtype == OOD_BF16) head_weights_kernel<__nv_bfloat16><<<batch, 256, smem, s>>>(stats, in_w, in_b, w27, w1, (__nv_bfloat16 *)wps, bias, channels);
-    else if (dtype == OOD_F32) head_weights_kernel<float><<<batch, 256, smem, s>>>(stats, in_w, in_b, w27, w1, (float *)wps, bias, channels);
+    const dim3 hgrid(batch, 8);
+    if (dtype == OOD_BF16) head_weights_kernel<__nv_bfloat16><<<hgrid, 256, smem, s>>>(stats, in_w, in_b, w27, w1, (__nv_bfloat16 *)wps, bias, channels);
+    else if (dtype == OOD_F32) head_weights_kernel<float><<<hgrid, 256, smem, s>>>(stats, in_w, in_b, w27, w1, (float *)wps, bias, channels);
     else OOD_REQUIRE(false, "alignnet_head_weights: bad dtype");
     return check_launch("alignnet_head_weights");
 }

@@ -208,8 +208,9 @@ __global__ void __launch_bounds__(TSX * TSY) tap_sum_tile_kernel(const float *__
 // partial sums are exchanged through distributed shared memory (cluster barrier, fixed rank order: every CTA computes the same
 // gate, bit for bit), and the second pass re-reads v (it was just written by the convolution: an L2 hit).
 constexpr int kSeCluster = 8;
+constexpr int kSeThreads = 1024;      // many pixel lanes per CTA: the passes are chains of dependent L2 round trips, a thread should own few pixels
 template <typename T, bool SF>
-__global__ void __cluster_dims__(kSeCluster, 1, 1) __launch_bounds__(256)
+__global__ void __cluster_dims__(kSeCluster, 1, 1) __launch_bounds__(kSeThreads)
 se_tail_kernel(const T *__restrict__ v, const float *__restrict__ w1, const float *__restrict__ w2, const void *__restrict__ sc_, int ss,
                const float *__restrict__ bn_g, const float *__restrict__ bn_h, float *__restrict__ out, T *__restrict__ tn, T *__restrict__ out_lp,
                int H, int W, int C, int Cr) {
@@ -229,6 +230,7 @@ se_tail_kernel(const T *__restrict__ v, const float *__restrict__ w1, const floa
 #pragma unroll
     for (int j = 0; j < N2; ++j) acc[j] = f2(0.f);
     if (lane < lanes) {
+#pragma unroll 4
         for (int64_t p = p0 + lane; p < p1; p += lanes) {
             float2 x[N2];
             enc_load<T>(v + ((int64_t)b * P + p) * C + c, x);
@@ -282,6 +284,7 @@ se_tail_kernel(const T *__restrict__ v, const float *__restrict__ w1, const floa
         bh[j] = tn ? make_float2(bn_h[c + 2 * j], bn_h[c + 2 * j + 1]) : f2(0.f);
     }
     const int Ws = W * ss;
+#pragma unroll 2
     for (int64_t p = p0 + lane; p < p1; p += lanes) {
         const int64_t off = ((int64_t)b * P + p) * C + c;
         float2 x[N2];
@@ -425,7 +428,7 @@ extern "C" int ood_se_tail(const void *v, const float *w1, const float *w2, cons
     OOD_REQUIRE(sc_stride == 1 || sc_stride == 2, "se_tail: shortcut stride must be 1 or 2");
     OOD_REQUIRE(!t_next || (bn_g && bn_h), "se_tail: t_next needs the affine coefficients");
     OOD_REQUIRE(channels % 8 == 0 && channels / 8 <= 256 && 256 % (channels / 8) == 0, "se_tail: channels (%d) must be 8 * a divisor of 256", channels);
-    const int lanes = 256 / (channels / 8);
+    const int lanes = kSeThreads / (channels / 8);
     const size_t smem = (size_t)(3 * channels + reduced + lanes * channels) * sizeof(float);
     OOD_REQUIRE(smem <= 200 * 1024, "se_tail: too many channels (%d)", channels);
     dim3 grid(kSeCluster, batch);
@@ -434,7 +437,7 @@ extern "C" int ood_se_tail(const void *v, const float *w1, const float *w2, cons
     do {                                                                                                                            \
         auto kern = se_tail_kernel<T, SF>;                                                                                          \
         if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                   \
-        kern<<<grid, 256, smem, st>>>((const T *)v, w1, w2, shortcut, sc_stride, bn_g, bn_h, out, (T *)t_next, (T *)out_lp, h, w, channels, reduced); \
+        kern<<<grid, kSeThreads, smem, st>>>((const T *)v, w1, w2, shortcut, sc_stride, bn_g, bn_h, out, (T *)t_next, (T *)out_lp, h, w, channels, reduced); \
     } while (0)
     if (dtype == OOD_F16) { if (shortcut_f32) OOD_SET(__half, true); else OOD_SET(__half, false); }
     else { if (shortcut_f32) OOD_SET(__nv_bfloat16, true); else OOD_SET(__nv_bfloat16, false); }
