@@ -285,15 +285,16 @@ def sharded_batch_leg(net, global_batch, chunk, steps, rank, world, dev, barrier
         torch.manual_seed(3000 + rank)
         pipe = PipelinedForward(fn, x_dev[:sizes[0]], depth=2, warmup=1)
 
-        def host_pass():
+        def host_pass():                      # consecutive batches stream through the two-graph pipeline: no drain between passes
             for a, b in bounds:
                 pipe.submit(x_host[a:b], out_host[a:b])
-            pipe.synchronize()
         host_pass()
+        pipe.synchronize()
         barrier()
         e0.record()
         for _ in range(steps):
             host_pass()
+        pipe.synchronize()
         e1.record()
         barrier()
         ms2 = reduce_max(e0.elapsed_time(e1))
