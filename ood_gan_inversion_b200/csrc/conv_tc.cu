@@ -616,6 +616,7 @@ static void plan_tiles(const ood_conv3x3_args &a, const ConvGeom &g, TcParams &p
 }
 
 static int conv3x3_tc_geom(const ood_conv3x3_args &a, const ConvGeom &g, cudaStream_t st);
+int convt_rows_interior(const ood_conv3x3_args &a, cudaStream_t st, int *handled);      // convt_rows.cu
 
 static bool pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
@@ -623,8 +624,15 @@ int conv3x3_tc(const ood_conv3x3_args &a, cudaStream_t st) {
     // stride-2 transposed convolution of a power-of-two input: interior + last row + last column, each with exact tiles
     static int split_t = -1;
     if (split_t < 0) { const char *e = getenv("OOD_SPLIT_TRANSPOSED"); split_t = (e && e[0] == '0') ? 0 : 1; }
-    if (a.transposed == 1 && split_t && pow2(a.h) && pow2(a.w) && a.h >= 16 && a.w >= 16 && !a.acc_in && !a.tiled && !a.stats_out && a.groups <= 1) {
+    const bool rows_shape = a.cin == 64 && a.cout == 32 && a.w % 128 == 0 && a.h >= 2;        // convt_rows.cu takes the interior of this layer
+    if (a.transposed == 1 && split_t && ((pow2(a.h) && pow2(a.w) && a.h >= 16 && a.w >= 16) || rows_shape) && !a.acc_in && !a.tiled && !a.stats_out && a.groups <= 1) {
         for (int part = 0; part < 3; ++part) {
+            if (part == 0) {        // the 64 -> 32 layer at 1024 px: row-streaming kernel for the interior
+                int handled = 0;
+                const int rc = convt_rows_interior(a, st, &handled);
+                if (rc != OOD_OK) return rc;
+                if (handled) continue;
+            }
             const int rc = conv3x3_tc_geom(a, make_geom_transposed_part(a.batch, a.h, a.w, a.cin, a.cout, part), st);
             if (rc != OOD_OK) return rc;
         }

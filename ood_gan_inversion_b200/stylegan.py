@@ -29,6 +29,7 @@ _PRECISION = os.environ.get('OOD_B200_PRECISION', 'bf16')
 # up-sampling layers with at most this many output channels use the fused-phase transposed convolution (conv3x3 form 5): the
 # zero-padded weight blocks cost 1.8x the MACs, which only the HBM / per-tile-overhead bound small-channel layers can afford
 _FUSED_T_MAX_CO = int(os.environ.get('OOD_FUSED_T_MAX_CO', 64))
+_CONVT_ROWS = os.environ.get('OOD_CONVT_ROWS', '1') != '0'      # the row-streaming transposed kernel for the 64 -> 32 layer (csrc/convt_rows.cu)
 
 
 def set_precision(p):
@@ -222,8 +223,10 @@ class ModulatedConv2d(nn.Module):
                 mw = _pad_dim(self.modulation.weight.detach().float(), 0, cin_p).contiguous()
                 mb = _pad_dim(self.modulation.bias.detach().float() * self.modulation.lr_mul, 0, cin_p).contiguous()
                 # small-channel up-sampling layers (512 / 1024 px): fused-phase transposed form (conv3x3 transposed=5)
+                # (the 64 -> 32 layer has its own row-streaming kernel behind form 1: csrc/convt_rows.cu)
                 self._cache['fused_t'] = K.pack_convt_fused(wp) if (self.upsample and self.kernel_size == 3 and _PRECISION == 'bf16'
-                                                                      and cout_p <= _FUSED_T_MAX_CO and cin_p % 32 == 0) else None
+                                                                      and cout_p <= _FUSED_T_MAX_CO and cin_p % 32 == 0
+                                                                      and not (_CONVT_ROWS and cin_p == 64 and cout_p == 32)) else None
             self._cache['k'] = (key, (wp, wsq, mw, mb))
             hit = self._cache['k']
         return hit[1]

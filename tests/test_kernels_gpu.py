@@ -988,3 +988,21 @@ def test_conv_transposed_split_into_exact_tiles(case, monkeypatch):
     assert y.shape == (b, 2 * h + 1, 2 * w_ + 1, co)
     ref = conv_ref(x.double(), w.double(), True).float()
     torch.testing.assert_close(nchw(y), ref, rtol=1e-4, atol=2e-3)
+
+
+@pytest.mark.parametrize('case', [dict(b=2, h=32, w=128), dict(b=1, h=40, w=256), dict(b=3, h=7, w=128), dict(b=1, h=64, w=128)])
+def test_conv_transposed_row_streaming_kernel(case, monkeypatch):
+    """convt_rows.cu (64 -> 32 channels, W % 128 == 0): phases in the MMA N dimension, every input row loaded once, two output rows per
+    position row through bulk stores; interior by this kernel, last row / column by the generic tiles; equals conv_transpose2d(stride 2)."""
+    monkeypatch.setenv('OOD_ROWS_MIN_STRIPS', '1')
+    b, h, w_, ci, co = case['b'], case['h'], case['w'], 64, 32
+    x, w = rnd(b, ci, h, w_, seed=1).bfloat16().float(), (0.2 * rnd(co, ci, 3, 3, seed=2)).bfloat16().float()
+    wp = K().pack_conv_weight(w.to(DEV), torch.bfloat16, False)
+    y, _ = K().conv3x3(nhwc(x, torch.bfloat16), wp, co, transposed=True, impl=0)
+    assert y.shape == (b, 2 * h + 1, 2 * w_ + 1, co) and y.dtype == torch.bfloat16
+    ref = conv_ref(x.double(), w.double(), True).float()
+    torch.testing.assert_close(nchw(y), ref, rtol=1e-2, atol=0.08)
+    # same values as the generic tiles (both round fp32 accumulators of the same products to bf16)
+    monkeypatch.setenv('OOD_ROWS_MIN_STRIPS', '100000000')
+    y2, _ = K().conv3x3(nhwc(x, torch.bfloat16), wp, co, transposed=True, impl=0)
+    torch.testing.assert_close(y.float(), y2.float(), rtol=1e-2, atol=2e-2)
