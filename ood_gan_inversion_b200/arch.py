@@ -208,7 +208,7 @@ class ood_faceGAN_e4e(nn.Module):
         """feats_conv[i] (1x1 convolution + bias, e4e_arch.py:109-113) on the tcgen05 1x1 form; NCHW view of an NHWC result."""
         conv = self.feats_conv[i]
         dt = feat.dtype if feat.dtype in (torch.bfloat16, torch.float16) else torch.bfloat16      # the encoder's storage type
-        key = (conv.weight.device, conv.weight._version, conv.bias._version, dt)
+        key = (conv.weight.device, conv.weight._version, conv.weight.data_ptr(), conv.bias._version, conv.bias.data_ptr(), dt)
         cache = self.__dict__.setdefault('_fc_cache', {})
         if cache.get(i, (None,))[0] != key:
             with torch.no_grad():

@@ -37,7 +37,8 @@ def _fold_sequential(seq):
 
 
 def state_key(module):
-    return tuple(p._version for p in module.parameters()) + tuple(b._version for b in module.buffers())
+    """Cache key of a module's state: versions AND storage addresses (`p.data = t`, how checkpoints are often loaded, keeps the version)."""
+    return tuple((p._version, p.data_ptr()) for p in module.parameters()) + tuple((b._version, b.data_ptr()) for b in module.buffers())
 
 
 @torch.no_grad()

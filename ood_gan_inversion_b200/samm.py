@@ -103,7 +103,7 @@ class AlignNet(nn.Module):
     def _packed(self):
         b0, b1 = self.body[0], self.body[1]
         params = [b0.res_layer[1].weight, b0.res_layer[3].weight, b1.res_layer[1].weight, b1.shortcut_layer[0].weight]
-        key = (sg.get_precision(), params[0].device) + tuple(p._version for p in params)
+        key = (sg.get_precision(), params[0].device) + tuple((p._version, p.data_ptr()) for p in params)
         hit = getattr(self, '_pk', None)
         if hit is None or hit[0] != key:
             with torch.no_grad():

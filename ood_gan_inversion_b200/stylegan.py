@@ -207,8 +207,8 @@ class ModulatedConv2d(nn.Module):
     def packed(self):
         """(packed conv weight for the active precision, Wsq[Co,Ci] or None, fp32 mod weight, fp32 mod bias); channel
         dimensions zero-padded to the kernel granule."""
-        key = (_PRECISION, self.weight.device, self.weight._version, self.modulation.weight._version,
-               self.modulation.bias._version)
+        key = (_PRECISION, self.weight.device, self.weight._version, self.weight.data_ptr(), self.modulation.weight._version,
+               self.modulation.weight.data_ptr(), self.modulation.bias._version, self.modulation.bias.data_ptr())
         hit = self._cache.get('k')
         if hit is None or hit[0] != key:
             with torch.no_grad():

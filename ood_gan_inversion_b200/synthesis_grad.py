@@ -16,7 +16,7 @@ from . import stylegan as sg
 
 def _bwd_weights(conv):
     """Packed data-gradient weights of a ModulatedConv2d, cached on the module."""
-    key = (sg.get_precision(), conv.weight.device, conv.weight._version)
+    key = (sg.get_precision(), conv.weight.device, conv.weight._version, conv.weight.data_ptr())
     hit = conv._cache.get('bwd')
     if hit is None or hit[0] != key:
         with torch.no_grad():
