@@ -136,7 +136,7 @@ struct Cfg {
     static constexpr int kTmemCols = kNAcc * CO < 32 ? 32 : kNAcc * CO;
     static constexpr int kOutTile = 128 * CO * 2;                             // one staged output row tile (bf16)
     static constexpr int kStg = CO == 64 ? 1 : 2;                             // staging buffers per epilogue group (shared-memory budget)
-    static constexpr int kSmem = 9 * kWStride + kRing * kRowStride + 2 * kStg * 2 * kOutTile + 1024 + 512 + 2 * 3 * CO * 4;   // staging: 2 groups x kStg x (y, ys); barriers; coefficients
+    static constexpr int kSmem = 9 * kWStride + kRing * kRowStride + 2 * kStg * 2 * kOutTile + 1024 + 512 + 2 * 6 * CO * 4;   // staging: 2 groups x kStg x (y, ys); barriers; coefficients (+ ToRGB weights)
     static_assert(kWStride == kWTile, "the ky blocks of a horizontal tap must be contiguous (one N = 3*Co operand)");
     static constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(CO >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 };
@@ -279,7 +279,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const bool issuer = gt == 0;
         const int bar_id = 1 + grp;
         const float nw = (p.ep.noise && p.ep.noise_w) ? *p.ep.noise_w : 0.f;
-        float *coef = sCoef + grp * 3 * CO;                         // d[CO], bias[CO], s_next[CO] of the current strip's image
+        float *coef = sCoef + grp * 6 * CO;                         // d[CO], bias[CO], s_next[CO], rgb_w[3][CO] of the current strip's image
         uint8_t *stage0 = sO + grp * (NSTG * 2 * C::kOutTile);
         uint32_t nrow0 = 0;                                         // output rows of the strips before this one (all groups count alike)
         uint32_t tile_ctr = 0;                                      // row tiles this group has staged (staging buffer parity)
@@ -295,6 +295,10 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 coef[q] = p.ep.d ? __ldg(p.ep.d + (int64_t)b * CO + q) : 1.f;
                 coef[CO + q] = p.ep.bias ? __ldg(p.ep.bias + q) : 0.f;
                 coef[2 * CO + q] = p.ep.out_ys ? __ldg(p.ep.s_next + (int64_t)b * CO + q) : 1.f;
+                if (p.ep.rgb_out) {
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) coef[(3 + k) * CO + q] = __ldg(p.ep.rgb_w + ((int64_t)b * 3 + k) * CO + q);
+                }
             }
             asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
             const int j0 = (int)((nrow0 ^ (uint32_t)grp) & 1u);      // first row of this strip whose global index has this group's parity
@@ -311,6 +315,12 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 nz0 = nz1;
                 nz1 = (nzp && j + 4 < nrows) ? __ldg(nzp + (int64_t)(j + 4) * p.w) : 0.f;
                 uint8_t *sY = stage0 + (tile_ctr % NSTG) * 2 * C::kOutTile, *sYS = sY + C::kOutTile;
+                // fused ToRGB (model.py:363-372): bias + up-FIR of the previous level's RGB do not depend on this tile's MMAs -> their loads go first
+                float rgb[3] = {0.f, 0.f, 0.f};
+                if (p.ep.rgb_out) {
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) rgb[k] = rgb_finish(p.ep, 0.f, b, k, ya + j, X, p.h, p.w);
+                }
                 if (NSTG == 1) {        // one staging buffer: the store issued for the previous tile must have finished READING it
                     if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                     asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
@@ -341,6 +351,13 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
                         for (int e = 0; e < 8; ++e) v[e] = lrelu_sqrt2(v[e]);
                     }
+                    if (p.ep.rgb_out) {          // this pixel's 8 channels of the unscaled activation x the three colour rows
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) {
+                            const float4 w0 = *reinterpret_cast<const float4 *>(coef + (3 + k) * CO + 8 * q), w1 = *reinterpret_cast<const float4 *>(coef + (3 + k) * CO + 8 * q + 4);
+                            rgb[k] = fmaf(v[0], w0.x, fmaf(v[1], w0.y, fmaf(v[2], w0.z, fmaf(v[3], w0.w, fmaf(v[4], w1.x, fmaf(v[5], w1.y, fmaf(v[6], w1.z, fmaf(v[7], w1.w, rgb[k]))))))));
+                        }
+                    }
                     const uint32_t chunk = (uint32_t)q ^ swz;
                     if (p.ep.out_y)
                         *reinterpret_cast<uint4 *>(sY + row_off + chunk * 16) =
@@ -351,6 +368,10 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             make_uint4(pack_bf16x2(v[0] * s0.x, v[1] * s0.y), pack_bf16x2(v[2] * s0.z, v[3] * s0.w),
                                        pack_bf16x2(v[4] * s1.x, v[5] * s1.y), pack_bf16x2(v[6] * s1.z, v[7] * s1.w));
                     }
+                }
+                if (p.ep.rgb_out) {          // consecutive lanes = consecutive pixels of a colour plane
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) p.ep.rgb_out[((int64_t)b * 3 + k) * p.h * p.w + (int64_t)(ya + j) * p.w + X] = rgb[k];
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy STS -> visible to the TMA store
                 // two staging buffers: the store of the previous tile (other buffer) has finished reading before anyone writes that
@@ -411,7 +432,7 @@ int conv3x3_rows(const ood_conv3x3_args &a, cudaStream_t st, int *handled) {
     // PReLU convolutions (the encoder's 64-channel layers at 128 / 256 px) stay on the generic tiles.  A PReLU form of this
     // epilogue was built and measured: 0.22 -> 0.37 ms (4 launches at 128 px: 64 strips for 148 SMs), 0.19 -> 0.22 ms at
     // 256 px, and its extra live registers made the <64,64> instance spill (512 px generator layer 0.48 -> 0.82 ms) -- removed.
-    if (a.transposed || a.dtype != OOD_BF16 || a.out_dtype == OOD_F16 || a.out_f32 || a.act == 2 || a.groups > 1 || a.acc_in || a.tiled || a.stats_out || a.rgb_out) return OOD_OK;
+    if (a.transposed || a.dtype != OOD_BF16 || a.out_dtype == OOD_F16 || a.out_f32 || a.act == 2 || a.groups > 1 || a.acc_in || a.tiled || a.stats_out) return OOD_OK;
     if (!((a.cin == 32 || a.cin == 64) && (a.cout == 32 || a.cout == 64) && a.cin >= a.cout)) return OOD_OK;
     if (a.w % 128 != 0 || a.h < 3 || (int64_t)a.batch * a.h * a.w >= (1LL << 31)) return OOD_OK;
     static EncodeFn encode = nullptr;
