@@ -18,6 +18,7 @@ B=16 cap rows64 'conv_rows_kernel<.int.64, .int.64' 4 python scripts/rows_bench.
 cap modconv_plain 'conv_tc_kernel' 3 python scripts/modconv_ncu.py plain
 cap modconv_up 'conv_tc_kernel' 9 python scripts/modconv_ncu.py transposed
 cap wgrad 'wgrad_tc_kernel' 3 python scripts/modconv_ncu.py wgrad
+cap convt_rows 'convt_rows_kernel' 3 python scripts/convT_bench.py
 python scripts/kernel_sweep.py --out gpurun_out/sweep_r02.json > gpurun_out/sweep_r02.log 2>&1
 python scripts/rows_bench.py > gpurun_out/rows_bench_r02.txt 2>&1
 python scripts/convT_bench.py >> gpurun_out/rows_bench_r02.txt 2>&1
