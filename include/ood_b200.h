@@ -245,8 +245,12 @@ int ood_bicubic_up_add(const void *x, const void *y, void *out, int batch, int h
  *      gradient); x, gen, gout fp32 [B,3,S,S] -> gx, ggen fp32 [B,3,S,S] (written; either may be NULL). */
 int ood_warp_mix_bwd(const void *gen, const float *field, const void *gout, float *ggen, float *gfield, int batch, int h, int w,
                      int channels, int dtype, void *stream);
+/*      workspace (fp32, n_fields * B * S * S elements) selects the DETERMINISTIC two-stage form: per-pixel gradients of the up-sampled
+ *      masks, then the adjoint of the bilinear up-sampling as a gather per mask cell (one warp per cell, fixed order); NULL = the
+ *      atomic form (shared-memory windows per block + global atomics; gfields ZERO-INITIALISED by the caller). */
 int ood_mask_blend_bwd(const float *const *fields_host, float *const *gfields_host, const int *field_sizes_host, int n_fields,
-                       const float *x, const float *gen, const float *gout, float *gx, float *ggen, int batch, int size, void *stream);
+                       const float *x, const float *gen, const float *gout, float *gx, float *ggen, float *workspace, int batch, int size,
+                       void *stream);
 
 /*      ood_field_step_bwd (section 8b prm_bwd): backward of ood_field_step in its plain form (z only, no folded norms): heads
  *      (tanh * scale, tanh * scale, sigmoid) + 4x4 FIR + accumulate / clip / PRM + bicubic coarse PRM (SAMM/helpers.py:62-77,

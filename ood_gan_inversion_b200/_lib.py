@@ -69,7 +69,7 @@ _SIGS = {
     'ood_alignnet_head_weights': ([c_void_p] * 7 + [c_int, c_int, c_int, c_void_p], c_int),
     'ood_bicubic_up_add': ([c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p], c_int),
     'ood_warp_mix_bwd': ([c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p], c_int),
-    'ood_mask_blend_bwd': ([c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p], c_int),
+    'ood_mask_blend_bwd': ([c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p], c_int),
     'ood_field_step_bwd': ([c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                            c_void_p, c_void_p], c_int),
     'ood_img2tensor_u8': ([c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_float, c_void_p], c_int),

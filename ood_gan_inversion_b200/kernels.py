@@ -778,8 +778,9 @@ def warp_mix_bwd(gen, field, gout):
     return ggen, gfield
 
 
-def mask_blend_bwd(fields, x, gen, gout, want_gx=True, want_ggen=True):
-    """Backward of mask_blend: fields list of fp32 [B,3,r,r]; x, gen, gout fp32 [B,3,S,S] -> (gx, ggen, [gfields])."""
+def mask_blend_bwd(fields, x, gen, gout, want_gx=True, want_ggen=True, deterministic=True):
+    """Backward of mask_blend: fields list of fp32 [B,3,r,r]; x, gen, gout fp32 [B,3,S,S] -> (gx, ggen, [gfields]).
+    deterministic (default): two-stage gather form with a [n,B,S,S] fp32 workspace; False: the atomic form."""
     _cuda(x, gen, gout, *fields)
     fields = [_f32c(f) for f in fields]
     x, gen, gout = _f32c(x), _f32c(gen), _f32c(gout)
@@ -791,7 +792,8 @@ def mask_blend_bwd(fields, x, gen, gout, want_gx=True, want_ggen=True):
     ptrs = (C.c_void_p * n)(*[f.data_ptr() for f in fields])
     gptrs = (C.c_void_p * n)(*[g.data_ptr() for g in gfields])
     sizes = (C.c_int * n)(*[f.shape[-1] for f in fields])
-    check(_lib.lib().ood_mask_blend_bwd(ptrs, gptrs, sizes, n, _ptr(x), _ptr(gen), _ptr(gout), _ptr(gx), _ptr(ggen), b, s, _stream()),
+    ws = torch.empty(n, b, s, s, device=x.device, dtype=torch.float32) if deterministic else None
+    check(_lib.lib().ood_mask_blend_bwd(ptrs, gptrs, sizes, n, _ptr(x), _ptr(gen), _ptr(gout), _ptr(gx), _ptr(ggen), _ptr(ws), b, s, _stream()),
           'mask_blend_bwd')
     return gx, ggen, gfields
 

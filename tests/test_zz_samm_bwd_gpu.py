@@ -55,6 +55,13 @@ def test_mask_blend_bwd(size, levels):
     out.backward(gout)
     for a, r in zip(ours, ref_in):
         torch.testing.assert_close(a.grad, r.grad, rtol=1e-4, atol=1e-4)
+    # the two forms of the level gradients: deterministic gather (default; bit-identical from run to run) and shared-memory-window atomics
+    from ood_gan_inversion_b200 import kernels as K
+    args = ([t.detach() for t in ours[2:]], ours[0].detach(), ours[1].detach(), gout)
+    d1, d2, at = K.mask_blend_bwd(*args), K.mask_blend_bwd(*args), K.mask_blend_bwd(*args, deterministic=False)
+    for a, b_, c in zip(d1[2], d2[2], at[2]):
+        assert torch.equal(a, b_)
+        torch.testing.assert_close(c, a, rtol=1e-4, atol=1e-4)
 
 
 @pytest.mark.parametrize('r,with_prev,with_coarse', [(12, False, False), (32, True, False), (50, True, True), (9, False, True)])
