@@ -24,7 +24,7 @@ namespace ood {
 namespace rows {
 
 constexpr int kThreads = 320;          // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two groups of four warps: even / odd output rows)
-constexpr int kStripRows = 32;
+constexpr int kStripRows = 32;          // default; launches with few pixels use 16 or 8 rows per strip so that there is a strip per SM
 constexpr int kNAcc = 8;            // TMEM accumulator ring: blocks of Co columns, output row n lives in block kNAcc-1 - n % kNAcc
 constexpr int kRowPx = 130;
 
@@ -32,6 +32,8 @@ struct RowParams {
     int batch, h, w, tiles_x, strips_y, total_strips;
     ConvEpilogue ep;
     int cout;
+    int strip_rows;        // output rows per strip
+    int in_f16, out_f16;   // OOD_F16 operands (instruction-descriptor format) / half-precision outputs (the encoder's storage type)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -136,7 +138,7 @@ struct Cfg {
     static constexpr int kTmemCols = kNAcc * CO < 32 ? 32 : kNAcc * CO;
     static constexpr int kOutTile = 128 * CO * 2;                             // one staged output row tile (bf16)
     static constexpr int kStg = CO == 64 ? 1 : 2;                             // staging buffers per epilogue group (shared-memory budget)
-    static constexpr int kSmem = 9 * kWStride + kRing * kRowStride + 2 * kStg * 2 * kOutTile + 1024 + 512 + 2 * 6 * CO * 4;   // staging: 2 groups x kStg x (y, ys); barriers; coefficients (+ ToRGB weights)
+    static constexpr int kSmem = 9 * kWStride + kRing * kRowStride + 2 * kStg * 2 * kOutTile + 1024 + 512 + 2 * 7 * CO * 4;   // staging: 2 groups x kStg x (y, ys); barriers; coefficients (+ ToRGB weights, PReLU slopes)
     static_assert(kWStride == kWTile, "the ky blocks of a horizontal tap must be contiguous (one N = 3*Co operand)");
     static constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(CO >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 };
@@ -149,7 +151,7 @@ struct Ring {
     __device__ __forceinline__ Ring next() const { Ring r = *this; r.advance(); return r; }
 };
 
-template <int CI, int CO>
+template <int CI, int CO, bool ENC>   // ENC: the encoder's variant (f16 operands / outputs, PReLU); the generator's instances compile without it
 __global__ void __launch_bounds__(kThreads, 1)
 conv_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmYS, const RowParams p) {
@@ -188,9 +190,10 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         int r = strip / p.tiles_x;
         const int sy = r % p.strips_y;
         b = r / p.strips_y;
-        ya = sy * kStripRows;
+        const int strip_rows = ENC ? p.strip_rows : kStripRows;
+        ya = sy * strip_rows;
         x0 = tx * 128;
-        nrows = min(kStripRows, p.h - ya);
+        nrows = min(strip_rows, p.h - ya);
     };
 
     if (warp == 0) {
@@ -222,7 +225,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const uint32_t desc_hi = (uint32_t)(dproto >> 32);
             const uint32_t ring_lo = (uint32_t)dproto | ((smem_u32(sR) >> 4) & 0x3FFF);
             const uint32_t w_lo = (uint32_t)dproto | ((smem_u32(sW) >> 4) & 0x3FFF);
-            constexpr uint32_t kIdescNoN = C::kIdesc & ~(0x3Fu << 17);
+            const uint32_t kIdescNoN = (C::kIdesc & ~(0x3Fu << 17)) & ((ENC && p.in_f16) ? ~((1u << 7) | (1u << 10)) : ~0u);       // A / B format: 1 = bf16, 0 = f16
             // blocks [sblk, sblk + nb) of the accumulator ring (mod kNAcc) += A . B[rows of nb consecutive ky blocks]
             auto issue = [&](int sblk, int nb, uint32_t a_lo, uint32_t b_lo, uint32_t accumulate) {
                 const int first = min(nb, kNAcc - sblk);
@@ -279,7 +282,9 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const bool issuer = gt == 0;
         const int bar_id = 1 + grp;
         const float nw = (p.ep.noise && p.ep.noise_w) ? *p.ep.noise_w : 0.f;
-        float *coef = sCoef + grp * 6 * CO;                         // d[CO], bias[CO], s_next[CO], rgb_w[3][CO] of the current strip's image
+        float *coef = sCoef + grp * 7 * CO;                         // d[CO], bias[CO], s_next[CO], rgb_w[3][CO], prelu[CO] of the current strip's image
+        const bool of16 = ENC && p.out_f16 != 0;
+        auto pk2 = [&](float lo, float hi) -> uint32_t { return of16 ? pack_f16x2(lo, hi) : pack_bf16x2(lo, hi); };
         uint8_t *stage0 = sO + grp * (NSTG * 2 * C::kOutTile);
         uint32_t nrow0 = 0;                                         // output rows of the strips before this one (all groups count alike)
         uint32_t tile_ctr = 0;                                      // row tiles this group has staged (staging buffer parity)
@@ -295,6 +300,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 coef[q] = p.ep.d ? __ldg(p.ep.d + (int64_t)b * CO + q) : 1.f;
                 coef[CO + q] = p.ep.bias ? __ldg(p.ep.bias + q) : 0.f;
                 coef[2 * CO + q] = p.ep.out_ys ? __ldg(p.ep.s_next + (int64_t)b * CO + q) : 1.f;
+                if (ENC) coef[6 * CO + q] = p.ep.act == 2 ? __ldg(p.ep.prelu + q) : 1.f;
                 if (p.ep.rgb_out) {
 #pragma unroll
                     for (int k = 0; k < 3; ++k) coef[(3 + k) * CO + q] = __ldg(p.ep.rgb_w + ((int64_t)b * 3 + k) * CO + q);
@@ -350,6 +356,11 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     if (p.ep.act == 1) {
 #pragma unroll
                         for (int e = 0; e < 8; ++e) v[e] = lrelu_sqrt2(v[e]);
+                    } else if (ENC && p.ep.act == 2) {          // PReLU (the encoder's bottlenecks, helpers.py:436-441)
+                        const float4 p0 = *reinterpret_cast<const float4 *>(coef + 6 * CO + 8 * q), p1 = *reinterpret_cast<const float4 *>(coef + 6 * CO + 8 * q + 4);
+                        const float sl[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) v[e] = v[e] > 0.f ? v[e] : v[e] * sl[e];
                     }
                     if (p.ep.rgb_out) {          // this pixel's 8 channels of the unscaled activation x the three colour rows
 #pragma unroll
@@ -361,12 +372,11 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     const uint32_t chunk = (uint32_t)q ^ swz;
                     if (p.ep.out_y)
                         *reinterpret_cast<uint4 *>(sY + row_off + chunk * 16) =
-                            make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+                            make_uint4(pk2(v[0], v[1]), pk2(v[2], v[3]), pk2(v[4], v[5]), pk2(v[6], v[7]));
                     if (p.ep.out_ys) {
                         const float4 s0 = *reinterpret_cast<const float4 *>(coef + 2 * CO + 8 * q), s1 = *reinterpret_cast<const float4 *>(coef + 2 * CO + 8 * q + 4);
                         *reinterpret_cast<uint4 *>(sYS + row_off + chunk * 16) =
-                            make_uint4(pack_bf16x2(v[0] * s0.x, v[1] * s0.y), pack_bf16x2(v[2] * s0.z, v[3] * s0.w),
-                                       pack_bf16x2(v[4] * s1.x, v[5] * s1.y), pack_bf16x2(v[6] * s1.z, v[7] * s1.w));
+                            make_uint4(pk2(v[0] * s0.x, v[1] * s0.y), pk2(v[2] * s0.z, v[3] * s0.w), pk2(v[4] * s1.x, v[5] * s1.y), pk2(v[6] * s1.z, v[7] * s1.w));
                     }
                 }
                 if (p.ep.rgb_out) {          // consecutive lanes = consecutive pixels of a colour plane
@@ -406,11 +416,11 @@ typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, voi
                              const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                              CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-template <int CI, int CO>
+template <int CI, int CO, bool ENC>
 static int launch(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap &tmY, const CUtensorMap &tmYS, const RowParams &p,
                   cudaStream_t st) {
     using C = Cfg<CI, CO>;
-    auto kern = conv_rows_kernel<CI, CO>;
+    auto kern = conv_rows_kernel<CI, CO, ENC>;
     static DeviceOnce attr;
     if (attr.first()) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem);
@@ -429,10 +439,14 @@ static int launch(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensor
 int conv3x3_rows(const ood_conv3x3_args &a, cudaStream_t st, int *handled) {
     using namespace rows;
     *handled = 0;
-    // PReLU convolutions (the encoder's 64-channel layers at 128 / 256 px) stay on the generic tiles.  A PReLU form of this
-    // epilogue was built and measured: 0.22 -> 0.37 ms (4 launches at 128 px: 64 strips for 148 SMs), 0.19 -> 0.22 ms at
-    // 256 px, and its extra live registers made the <64,64> instance spill (512 px generator layer 0.48 -> 0.82 ms) -- removed.
-    if (a.transposed || a.dtype != OOD_BF16 || a.out_dtype == OOD_F16 || a.out_f32 || a.act == 2 || a.groups > 1 || a.acc_in || a.tiled || a.stats_out) return OOD_OK;
+    // Round 1 kept the encoder's PReLU convolutions (64 channels at 128 / 256 px) on the generic tiles: a PReLU form of the old epilogue was slower
+    // and made <64,64> spill.  With the round-2 epilogue (coefficients in shared memory) and strips of 8 / 16 rows for launches with few pixels they
+    // run here, in the encoder's f16 storage (OOD_ROWS_ENCODER=0 restores the generic route).
+    static int enc_rows = -1;
+    if (enc_rows < 0) { const char *e = getenv("OOD_ROWS_ENCODER"); enc_rows = (e && e[0] == '0') ? 0 : 1; }
+    const bool f16 = a.dtype == OOD_F16;
+    if (a.transposed || (a.dtype != OOD_BF16 && !f16) || a.out_f32 || a.groups > 1 || a.acc_in || a.tiled || a.stats_out) return OOD_OK;
+    if ((f16 || a.act == 2) && !enc_rows) return OOD_OK;
     if (!((a.cin == 32 || a.cin == 64) && (a.cout == 32 || a.cout == 64) && a.cin >= a.cout)) return OOD_OK;
     if (a.w % 128 != 0 || a.h < 3 || (int64_t)a.batch * a.h * a.w >= (1LL << 31)) return OOD_OK;
     static EncodeFn encode = nullptr;
@@ -449,7 +463,7 @@ int conv3x3_rows(const ood_conv3x3_args &a, cudaStream_t st, int *handled) {
         cuuint64_t strides[3] = {(cuuint64_t)a.cin * 2, (cuuint64_t)a.w * a.cin * 2, (cuuint64_t)a.h * a.w * a.cin * 2};
         cuuint32_t box[4] = {(cuuint32_t)a.cin, (cuuint32_t)kRowPx, 1, 1};
         cuuint32_t es[4] = {1, 1, 1, 1};
-        if (encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(a.in), dims, strides, box, es,
+        if (encode(&tmA, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(a.in), dims, strides, box, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
             return OOD_OK;
     }
@@ -458,7 +472,7 @@ int conv3x3_rows(const ood_conv3x3_args &a, cudaStream_t st, int *handled) {
         cuuint64_t strides[2] = {(cuuint64_t)a.cin * 2, (cuuint64_t)a.cout * a.cin * 2};
         cuuint32_t box[3] = {(cuuint32_t)a.cin, (cuuint32_t)a.cout, 1};
         cuuint32_t es[3] = {1, 1, 1};
-        if (encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void *>(a.weight), dims, strides, box, es,
+        if (encode(&tmB, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void *>(a.weight), dims, strides, box, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
             return OOD_OK;
     }
@@ -479,7 +493,12 @@ int conv3x3_rows(const ood_conv3x3_args &a, cudaStream_t st, int *handled) {
     RowParams p{};
     p.batch = a.batch; p.h = a.h; p.w = a.w; p.cout = a.cout;
     p.tiles_x = a.w / 128;
-    p.strips_y = ceil_div(a.h, kStripRows);
+    p.in_f16 = f16;
+    p.out_f16 = (a.out_dtype ? a.out_dtype : a.dtype) == OOD_F16;
+    p.strip_rows = kStripRows;
+    const bool enc = f16 || p.out_f16 || a.act == 2;
+    while (enc && p.strip_rows > 8 && (int64_t)p.tiles_x * ceil_div(a.h, p.strip_rows) * a.batch < kNumSMs) p.strip_rows >>= 1;      // a strip per SM if the image allows
+    p.strips_y = ceil_div(a.h, p.strip_rows);
     const int64_t total = (int64_t)p.tiles_x * p.strips_y * a.batch;
     if (total >= (1LL << 31)) return OOD_OK;
     {   // fewer strips than SMs (e.g. 64 at 128 px, batch 16): the generic tiles fill the GPU.  OOD_ROWS_MIN_STRIPS overrides
@@ -491,9 +510,14 @@ int conv3x3_rows(const ood_conv3x3_args &a, cudaStream_t st, int *handled) {
     p.total_strips = (int)total;
     p.ep = make_epilogue(a, 0);
     *handled = 1;
-    if (a.cin == 64 && a.cout == 64) return launch<64, 64>(tmA, tmB, tmY, tmYS, p, st);
-    if (a.cin == 64 && a.cout == 32) return launch<64, 32>(tmA, tmB, tmY, tmYS, p, st);
-    return launch<32, 32>(tmA, tmB, tmY, tmYS, p, st);
+    if (enc) {          // encoder variant: only the 64 -> 64 layers exist (psp_encoders.py:128-131 input layer + the first IR-SE stage)
+        if (a.cin == 64 && a.cout == 64) return launch<64, 64, true>(tmA, tmB, tmY, tmYS, p, st);
+        *handled = 0;
+        return OOD_OK;
+    }
+    if (a.cin == 64 && a.cout == 64) return launch<64, 64, false>(tmA, tmB, tmY, tmYS, p, st);
+    if (a.cin == 64 && a.cout == 32) return launch<64, 32, false>(tmA, tmB, tmY, tmYS, p, st);
+    return launch<32, 32, false>(tmA, tmB, tmY, tmYS, p, st);
 }
 
 }  // namespace ood

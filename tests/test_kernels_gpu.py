@@ -905,6 +905,34 @@ def test_conv3x3_f16_storage(case):
     assert torch.isfinite(big.float()).all() and float(big.float().max()) == 65504.0
 
 
+@pytest.mark.parametrize('case', [dict(b=2, h=40, w=128, dt='f16', act=2), dict(b=1, h=19, w=256, dt='f16', act=0),
+                                  dict(b=3, h=9, w=128, dt='bf16', act=2), dict(b=5, h=128, w=128, dt='f16', act=2)])
+def test_conv3x3_row_sliding_kernel_encoder_variant(case, monkeypatch):
+    """The encoder's 64 -> 64 convolutions (psp_encoders.py:128-131, helpers.py:114-119 at 256 / 128 px) on the row-sliding kernel:
+    f16 operands and outputs, PReLU or bias-only epilogue, strips of 32 / 16 / 8 rows (a strip per SM when the image allows), against
+    the fp64 formula."""
+    from ood_gan_inversion_b200 import kernels as K
+    monkeypatch.setenv('OOD_ROWS_MIN_STRIPS', '1')
+    b, h, w_, act = case['b'], case['h'], case['w'], case['act']
+    dt = torch.float16 if case['dt'] == 'f16' else torch.bfloat16
+    x = rnd(b, 64, h, w_, seed=1).to(dt).float()
+    w = (rnd(64, 64, 3, 3, seed=2) / 24.0).to(dt).float()
+    bias, slope = rnd(64, seed=3), 0.25 + 0.2 * rnd(64, seed=4)
+    xp = x.permute(0, 2, 3, 1).contiguous().to(dt).to(DEV)
+    wp = K.pack_conv_weight(w.to(DEV), dt, False)
+    ref = F.conv2d(x.double(), w.double(), bias.double(), padding=1)
+    if act == 2:
+        ref = torch.where(ref > 0, ref, ref * slope.double().reshape(1, -1, 1, 1))
+    y, _ = K.conv3x3(xp, wp, 64, bias=bias.to(DEV), **(dict(prelu=slope.to(DEV)) if act == 2 else {}))
+    assert y.dtype == dt
+    tol = dict(rtol=2e-3, atol=2e-3) if dt == torch.float16 else dict(rtol=1e-2, atol=1e-2)
+    torch.testing.assert_close(y.float().permute(0, 3, 1, 2).cpu(), ref.float(), **tol)
+    if dt == torch.float16:          # the bf16 copy the alignment consumes (arch._feats_conv_nhwc)
+        yb, _ = K.conv3x3(xp, wp, 64, bias=bias.to(DEV), out_dtype=torch.bfloat16, **(dict(prelu=slope.to(DEV)) if act == 2 else {}))
+        assert yb.dtype == torch.bfloat16
+        torch.testing.assert_close(yb.float().permute(0, 3, 1, 2).cpu(), ref.float(), rtol=1e-2, atol=1e-2)
+
+
 def test_encoder_glue_kernels():
     """ood_latent_assemble (psp_encoders.py:199-214 + e4e_arch.py:261), ood_alignnet_head_weights (the InstanceNorm folded into the
     AlignNet head's projection) and se_residual's out_lp copy against their torch formulas."""
