@@ -159,11 +159,12 @@ typedef struct {
      * per warp instruction; the tile order makes the same access one contiguous 512-byte run (measured on the 256 px
      * AlignNet level: seeded half convolution 898 us with an NHWC seed against 505 us without any seed). */
     int tiled;
-    /* fused output statistics (tcgen05 path; stride-1 / 1x1 form, bf16 out_y only, cin % 64 == 0, cout % 128 == 0, h*w >= 128):
+    /* fused output statistics (tcgen05 path; stride-1 / stride-2 pad-1 / 1x1 forms, out_y only (bf16 or f16), cin % 64 == 0, cout % 128 == 0, h*w >= 128):
      * stats_out [B,Co,2] = {mean, rsqrt(biased variance + stats_eps)} over the pixels of every output channel of out_y AS
      * STORED -- the statistics of the InstanceNorm2d that follows the convolution (bottleneck_IR res_layer[4],
      * e4e/encoders/helpers.py:436-441) from the epilogue instead of a pass over out_y.  Deterministic (fixed-order sums).
-     * stats_ws: ood_conv3x3_stats_workspace() bytes. */
+     * stats_ws: ood_conv3x3_stats_workspace() bytes.  stats_ws without stats_out: only the per-tile sums [B][tiles][Co][2] = {sum, 0}
+     * are left in the workspace (no second moment, no finalise launch) -- the pooled sums of the encoder's squeeze-excite tail (ood_se_apply). */
     float *stats_out, *stats_ws;
     float stats_eps;
     /* storage type of out_y / out_ys when it differs from `dtype` (tcgen05 path): 0 = same as dtype, OOD_BF16 or OOD_F16.  The
@@ -305,6 +306,13 @@ int ood_se_residual(const void *v, const float *gate, const void *shortcut, int 
 int ood_se_tail(const void *v, const float *w1, const float *w2, const void *shortcut, int sc_stride, const float *bn_g, const float *bn_h,
                 float *out, void *t_next, void *out_lp, int batch, int h, int w, int channels, int reduced, int dtype, int shortcut_f32,
                 void *stream);
+/*      ood_se_apply:    ood_se_tail when the channel sums of v already exist: tile_sums = the stats_ws of the ood_conv3x3 call that wrote v
+ *                       (stats_out = NULL: per-tile sums only), [B][tiles][C][2] with tiles = workspace bytes / (B*C*8).  One streaming pass on a
+ *                       full grid (no pooling pass, no cluster); every block derives its image's gate from the tile sums in a fixed order.
+ *                       channels in {64,128,256,512}. */
+int ood_se_apply(const void *v, const float *tile_sums, int tiles, const float *w1, const float *w2, const void *shortcut, int sc_stride,
+                 const float *bn_g, const float *bn_h, float *out, void *t_next, void *out_lp, int batch, int h, int w, int channels,
+                 int reduced, int dtype, int shortcut_f32, void *stream);
 int ood_latent_assemble(const float *heads, const float *avg, const float *delta, float *out, int batch, int n_styles, int dim,
                         int stage, void *stream);
 /*      ood_alignnet_head_weights (a11): per-sample 1x1 projection weights of the AlignNet's 2C -> 3 head with the affine

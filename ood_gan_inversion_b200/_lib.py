@@ -65,6 +65,7 @@ _SIGS = {
     'ood_se_residual': ([c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                         c_int, c_int, c_int, c_void_p], c_int),
     'ood_se_tail': ([c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p] + [c_int] * 7 + [c_void_p], c_int),
+    'ood_se_apply': ([c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p] + [c_int] * 7 + [c_void_p], c_int),
     'ood_latent_assemble': ([c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p], c_int),
     'ood_alignnet_head_weights': ([c_void_p] * 7 + [c_int, c_int, c_int, c_void_p], c_int),
     'ood_bicubic_up_add': ([c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p], c_int),

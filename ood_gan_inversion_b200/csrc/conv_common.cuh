@@ -142,6 +142,7 @@ struct ConvEpilogue {
     const float *prelu;     // [Co], act == 2
     const float *acc_in;    // fp32 NHWC [B,OH,OW,Co] added to the accumulator first (tcgen05 path), or null
     float *stat_partial;    // STATS kernels: [B][m tiles per image][Co][2] partial moments of the stored output
+    int stat_sums_only;     // STATS kernels: only the sums (the second moment's transpose-reduce is skipped, its slot is written as 0)
     int tiled;              // acc_in / fp32 out_y in tile order: float4 index ((tile*(BN/32) + chunk)*8 + j)*128 + row
     // fused ToRGB (model.py:363-372): rgb_out[b,k,Y,X] = sum_o y[o]*rgb_w[b,k,o] + rgb_bias[k] + up2fir(rgb_skip)[b,k,Y,X]
     const float *rgb_w, *rgb_bias, *rgb_skip;

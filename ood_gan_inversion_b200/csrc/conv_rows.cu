@@ -445,7 +445,7 @@ int conv3x3_rows(const ood_conv3x3_args &a, cudaStream_t st, int *handled) {
     static int enc_rows = -1;
     if (enc_rows < 0) { const char *e = getenv("OOD_ROWS_ENCODER"); enc_rows = (e && e[0] == '0') ? 0 : 1; }
     const bool f16 = a.dtype == OOD_F16;
-    if (a.transposed || (a.dtype != OOD_BF16 && !f16) || a.out_f32 || a.groups > 1 || a.acc_in || a.tiled || a.stats_out) return OOD_OK;
+    if (a.transposed || (a.dtype != OOD_BF16 && !f16) || a.out_f32 || a.groups > 1 || a.acc_in || a.tiled || a.stats_out || a.stats_ws) return OOD_OK;
     if ((f16 || a.act == 2) && !enc_rows) return OOD_OK;
     if (!((a.cin == 32 || a.cin == 64) && (a.cout == 32 || a.cout == 64) && a.cin >= a.cout)) return OOD_OK;
     if (a.w % 128 != 0 || a.h < 3 || (int64_t)a.batch * a.h * a.w >= (1LL << 31)) return OOD_OK;

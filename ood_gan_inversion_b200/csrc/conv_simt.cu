@@ -126,7 +126,7 @@ int conv3x3_simt(const ood_conv3x3_args &a, cudaStream_t st) {
     OOD_REQUIRE(!a.rgb_out, "conv3x3 simt: the fused ToRGB epilogue exists on the tcgen05 path only");
     OOD_REQUIRE(a.groups <= 1, "conv3x3 simt: the grouped form exists on the tcgen05 path only");
     OOD_REQUIRE(a.transposed != 5, "conv3x3 simt: the fused-phase transposed form (5) exists on the tcgen05 path only; use form 1");
-    OOD_REQUIRE(!a.acc_in && !a.tiled && !a.stats_out, "conv3x3 simt: the accumulator seed (acc_in), the tile-order tensors and the fused statistics exist on the tcgen05 path only");
+    OOD_REQUIRE(!a.acc_in && !a.tiled && !a.stats_out && !a.stats_ws, "conv3x3 simt: the accumulator seed (acc_in), the tile-order tensors and the fused statistics exist on the tcgen05 path only");
     p.ep = make_epilogue(a, 1);
     int mmax = 0;
     for (int i = 0; i < p.g.nphases; ++i) mmax = std::max(mmax, p.g.ph[i].m_total);

@@ -452,26 +452,40 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                 }
                 if constexpr (STATS) {
-                    // moments of this warp's 32 pixels for the chunk's 32 channels, of the values as stored (bf16): a
+                    // moments of this warp's 32 pixels for the chunk's 32 channels, of the values as stored (bf16 / f16): a
                     // transpose-reduce over the lanes (31 shuffles per moment) leaves channel `lane` in element 0
-                    float q[32], q2[32];
+                    float q[32];
+                    auto lane_transpose_sum = [&]() {
+#pragma unroll
+                        for (int o = 16; o >= 1; o >>= 1) {
+                            const bool up = lane & o;
+#pragma unroll
+                            for (int i = 0; i < o; ++i) {
+                                const float s1 = up ? q[i] : q[i + o], k1 = up ? q[i + o] : q[i];
+                                q[i] = k1 + __shfl_xor_sync(0xffffffffu, s1, o);
+                            }
+                        }
+                    };
+                    float sum1, sum2 = 0.f;
 #pragma unroll
                     for (int j = 0; j < 32; j += 2) {
-                        const float2 t = valid ? unpack_bf16x2(pack_bf16x2(v[j], v[j + 1])) : make_float2(0.f, 0.f);
-                        q[j] = t.x; q[j + 1] = t.y; q2[j] = t.x * t.x; q2[j + 1] = t.y * t.y;
+                        const float2 t = !valid ? make_float2(0.f, 0.f) : of16 ? unpack_f16x2(pack_f16x2(v[j], v[j + 1])) : unpack_bf16x2(pack_bf16x2(v[j], v[j + 1]));
+                        q[j] = t.x; q[j + 1] = t.y;
                     }
+                    if (!p.ep.stat_sums_only) {          // second moment first (q is rebuilt from the same rounded values afterwards)
 #pragma unroll
-                    for (int o = 16; o >= 1; o >>= 1) {
-                        const bool up = lane & o;
+                        for (int j = 0; j < 32; ++j) q[j] *= q[j];
+                        lane_transpose_sum();
+                        sum2 = q[0];
 #pragma unroll
-                        for (int i = 0; i < o; ++i) {
-                            const float s1 = up ? q[i] : q[i + o], k1 = up ? q[i + o] : q[i];
-                            const float s2 = up ? q2[i] : q2[i + o], k2 = up ? q2[i + o] : q2[i];
-                            q[i] = k1 + __shfl_xor_sync(0xffffffffu, s1, o);
-                            q2[i] = k2 + __shfl_xor_sync(0xffffffffu, s2, o);
+                        for (int j = 0; j < 32; j += 2) {
+                            const float2 t = !valid ? make_float2(0.f, 0.f) : of16 ? unpack_f16x2(pack_f16x2(v[j], v[j + 1])) : unpack_bf16x2(pack_bf16x2(v[j], v[j + 1]));
+                            q[j] = t.x; q[j + 1] = t.y;
                         }
                     }
-                    *reinterpret_cast<float2 *>(stat_red + ((quad * BN) + ch * 32 + lane) * 2) = make_float2(q[0], q2[0]);
+                    lane_transpose_sum();
+                    sum1 = q[0];
+                    *reinterpret_cast<float2 *>(stat_red + ((quad * BN) + ch * 32 + lane) * 2) = make_float2(sum1, sum2);
                 }
             };
             if constexpr (SEED) {
@@ -593,7 +607,7 @@ static void plan_tiles(const ood_conv3x3_args &a, const ConvGeom &g, TcParams &p
     p.nphases = g.nphases;
     p.groups = groups; p.gbatch = a.batch / groups; p.in_shared = a.in_shared ? 1 : 0;
     p.wtaps = (a.transposed == 4 || a.transposed == 6) ? 1 : (a.transposed == 5 ? 4 : 9);
-    const int bn_min = (a.acc_in || a.tiled || a.stats_out) ? 128 : 64;
+    const int bn_min = (a.acc_in || a.tiled || a.stats_out || a.stats_ws) ? 128 : 64;
     int tiles = 0;
     for (;;) {
         p.n_tiles_n = ncols / BN;
@@ -625,7 +639,7 @@ int conv3x3_tc(const ood_conv3x3_args &a, cudaStream_t st) {
     static int split_t = -1;
     if (split_t < 0) { const char *e = getenv("OOD_SPLIT_TRANSPOSED"); split_t = (e && e[0] == '0') ? 0 : 1; }
     const bool rows_shape = a.cin == 64 && a.cout == 32 && a.w % 128 == 0 && a.h >= 2;        // convt_rows.cu takes the interior of this layer
-    if (a.transposed == 1 && split_t && ((pow2(a.h) && pow2(a.w) && a.h >= 16 && a.w >= 16) || rows_shape) && !a.acc_in && !a.tiled && !a.stats_out && a.groups <= 1) {
+    if (a.transposed == 1 && split_t && ((pow2(a.h) && pow2(a.w) && a.h >= 16 && a.w >= 16) || rows_shape) && !a.acc_in && !a.tiled && !a.stats_out && !a.stats_ws && a.groups <= 1) {
         for (int part = 0; part < 3; ++part) {
             if (part == 0) {        // the 64 -> 32 layer at 1024 px: row-streaming kernel for the interior
                 int handled = 0;
@@ -644,7 +658,6 @@ int conv3x3_tc(const ood_conv3x3_args &a, cudaStream_t st) {
 static int conv3x3_tc_geom(const ood_conv3x3_args &a, const ConvGeom &g, cudaStream_t st) {
     OOD_REQUIRE(a.dtype == OOD_BF16 || a.dtype == OOD_F16, "conv3x3 tc: storage type must be bf16 or f16");
     OOD_REQUIRE(a.out_dtype == 0 || a.out_dtype == OOD_BF16 || a.out_dtype == OOD_F16, "conv3x3 tc: out_dtype must be 0, OOD_BF16 or OOD_F16");
-    OOD_REQUIRE(!a.stats_out || (a.dtype == OOD_BF16 && a.out_dtype != OOD_F16), "conv3x3 tc: the fused statistics are built for bf16 outputs");
     OOD_REQUIRE(a.cin % 32 == 0 && a.cout % 32 == 0, "conv3x3 tc: cin and cout must be multiples of 32 (got %d, %d)", a.cin, a.cout);
     OOD_REQUIRE(((uintptr_t)a.in % 16 == 0) && ((uintptr_t)a.weight % 16 == 0), "conv3x3 tc: operands must be 16-byte aligned");
     EncodeTiledFn encode = get_encode_fn();
@@ -653,7 +666,7 @@ static int conv3x3_tc_geom(const ood_conv3x3_args &a, const ConvGeom &g, cudaStr
     const int groups = a.groups > 1 ? a.groups : 1;
     OOD_REQUIRE(a.batch % groups == 0, "conv3x3 tc: batch (%d) must be a multiple of groups (%d)", a.batch, groups);
     OOD_REQUIRE(groups == 1 || (!a.d && !a.noise && !a.out_ys && !a.rgb_out), "conv3x3 tc: the grouped form supports bias / activation epilogues only");
-    OOD_REQUIRE(a.transposed != 5 || (groups == 1 && !a.acc_in && !a.tiled && !a.stats_out && !a.rgb_out),
+    OOD_REQUIRE(a.transposed != 5 || (groups == 1 && !a.acc_in && !a.tiled && !a.stats_out && !a.stats_ws && !a.rgb_out),
                 "conv3x3 tc: the fused-phase transposed form takes no seed / tile-order / statistics / ToRGB options");
     OOD_REQUIRE(!(a.acc_in || a.tiled) || (a.cout % 128 == 0 && a.transposed != 1),
                 "conv3x3 tc: acc_in / tiled need cout %% 128 == 0 (got %d) and a single-phase form", a.cout);
@@ -694,13 +707,15 @@ static int conv3x3_tc_geom(const ood_conv3x3_args &a, const ConvGeom &g, cudaStr
                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { set_error("conv3x3 tc: weight tensor map encode failed (%d)", (int)r); return OOD_ERR_CUDA; }
     }
-    if (a.stats_out) {  // fused output statistics: wide tiles, one image per tile, single phase
+    if (a.stats_out || a.stats_ws) {  // fused output statistics: wide tiles, one image per tile, single phase (stats_out == NULL: the per-tile sums only)
         OOD_REQUIRE(a.stats_ws && !a.acc_in && !a.out_ys && !a.out_f32 && a.out_y && groups == 1 && (a.transposed == 0 || a.transposed == 3 || a.transposed == 4 || a.transposed == 6) &&
                     p.NB == 1 && BK == 64 && (BN == 256 || BN == 128),
                     "conv3x3 tc: stats_out needs the stride-1 / stride-2 pad-1 / 1x1 form, bf16 out_y only, cin %% 64 == 0, cout %% 128 == 0 and >= 128 output pixels");
         p.ep.stat_partial = a.stats_ws;
+        p.ep.stat_sums_only = a.stats_out == nullptr;
         const int rc = BN == 256 ? launch_tc<256, 64, false, true>(tmA, tmB, p, st) : launch_tc<128, 64, false, true>(tmA, tmB, p, st);
         if (rc != OOD_OK) return rc;
+        if (!a.stats_out) return OOD_OK;
         in_finalize_launch(a.stats_ws, a.stats_out, (int64_t)g.OH * g.OW, a.cout, p.ph[0].tiles_x * p.ph[0].tiles_y, a.stats_eps, a.batch, st);
         return check_launch("conv3x3 tc stats", 1);
     }

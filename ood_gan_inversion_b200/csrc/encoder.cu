@@ -51,6 +51,13 @@ template <> __device__ __forceinline__ void enc_load<__half>(const __half *p, fl
     const uint4 r = __ldg(reinterpret_cast<const uint4 *>(p));
     dst[0] = unpack_f16x2(r.x); dst[1] = unpack_f16x2(r.y); dst[2] = unpack_f16x2(r.z); dst[3] = unpack_f16x2(r.w);
 }
+template <typename T> __device__ __forceinline__ void unpack8(const uint4 &r, float2 *dst);
+template <> __device__ __forceinline__ void unpack8<__nv_bfloat16>(const uint4 &r, float2 *dst) {
+    dst[0] = unpack_bf16x2(r.x); dst[1] = unpack_bf16x2(r.y); dst[2] = unpack_bf16x2(r.z); dst[3] = unpack_bf16x2(r.w);
+}
+template <> __device__ __forceinline__ void unpack8<__half>(const uint4 &r, float2 *dst) {
+    dst[0] = unpack_f16x2(r.x); dst[1] = unpack_f16x2(r.y); dst[2] = unpack_f16x2(r.z); dst[3] = unpack_f16x2(r.w);
+}
 template <typename T> __device__ __forceinline__ void enc_store(T *p, const float2 *v);
 template <> __device__ __forceinline__ void enc_store<__half>(__half *p, const float2 *v) {
     uint4 r;
@@ -314,6 +321,123 @@ se_tail_kernel(const T *__restrict__ v, const float *__restrict__ w1, const floa
     }
 }
 
+// The squeeze-excite tail when the channel SUMS already exist: the convolution that wrote v left per-tile channel sums in its
+// statistics workspace (conv3x3 stats_ws, [B][tiles][C][2], conv_tc.cu STATS), so the pooling pass, the cluster and its barriers
+// go away and what is left is one streaming pass on a full-width grid.  A thread owns PER (pixel, 8-channel vector) cells: it
+// REQUESTS their v / shortcut values first, then every block derives the gate of its image (tile sums -> mean -> two-layer MLP,
+// fixed order: all blocks of an image compute the same bits) while those loads are in flight, then applies it.
+constexpr int kSaThreads = 512;
+template <typename T, bool SF, int PER>
+__global__ void __launch_bounds__(kSaThreads, 2)
+se_apply_kernel(const T *__restrict__ v, const float2 *__restrict__ partial, int ntiles, const float *__restrict__ w1, const float *__restrict__ w2,
+                const void *__restrict__ sc_, int ss, const float *__restrict__ bn_g, const float *__restrict__ bn_h, float *__restrict__ out,
+                T *__restrict__ tn, T *__restrict__ out_lp, int H, int W, int C, int Cr) {
+    constexpr int N = Vec<T>::N, N2 = N / 2;
+    static_assert(N == 8, "16-bit storage");
+    extern __shared__ float sa_s[];                   // mean[C] | hid[Cr] | gate[C] | red[groups][C]
+    float *mean = sa_s, *hid = sa_s + C, *gate_s = hid + Cr, *red = gate_s + C;
+    const int b = blockIdx.y;
+    const int cv = C / N, lanes = kSaThreads / cv;
+    const int vec = threadIdx.x % cv, lane = threadIdx.x / cv;
+    const int c = vec * N;
+    const int P = H * W, Ws = W * ss;
+    // ---- 1. request this thread's cells (kept packed until the gate exists: 4 + 8 registers per cell)
+    uint4 xr[PER], sr[PER][SF ? 2 : 1];
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+        const int p = (blockIdx.x * PER + k) * lanes + lane;
+        if (p < P) {
+            const int64_t off = ((int64_t)b * P + p) * C + c;
+            xr[k] = __ldg(reinterpret_cast<const uint4 *>(v + off));
+            int64_t soff = off;
+            if (ss != 1) {
+                const int y = p / W, xx = p - y * W;
+                soff = (((int64_t)b * H * ss + (int64_t)y * ss) * Ws + (int64_t)xx * ss) * C + c;
+            }
+            if (SF) {
+                sr[k][0] = __ldg(reinterpret_cast<const uint4 *>((const float *)sc_ + soff));
+                sr[k][SF ? 1 : 0] = __ldg(reinterpret_cast<const uint4 *>((const float *)sc_ + soff + 4));
+            } else {
+                sr[k][0] = __ldg(reinterpret_cast<const uint4 *>((const T *)sc_ + soff));
+            }
+        }
+    }
+    // the gate's weights are cold (every bottleneck has its own): ask L2 for them now, they are needed two barriers from here
+    for (int i = threadIdx.x * 32; i < C * Cr; i += kSaThreads * 32) {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(w1 + i));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(w2 + i));
+    }
+    // ---- 2. channel means from the convolution's tile sums
+    {
+        const int groups = kSaThreads / C, i = threadIdx.x % C, tg = threadIdx.x / C;          // C <= 512 divides 512 (host check)
+        float a = 0.f;
+#pragma unroll 4
+        for (int t = tg; t < ntiles; t += groups) a += __ldg(&partial[((int64_t)b * ntiles + t) * C + i].x);
+        red[tg * C + i] = a;
+        __syncthreads();
+        if (threadIdx.x < C) {
+            float m = 0.f;
+            for (int g = 0; g < groups; ++g) m += red[g * C + threadIdx.x];
+            mean[threadIdx.x] = m / (float)P;
+        }
+        __syncthreads();
+    }
+    // ---- 3. the gate (SEModule, helpers.py:59-76)
+    {
+        const int wlane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        for (int j = warp; j < Cr; j += kSaThreads / 32) {
+            const float *wr = w1 + (int64_t)j * C;
+            float a = 0.f;
+            for (int i = wlane; i < C; i += 32) a = fmaf(wr[i], mean[i], a);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+            if (wlane == 0) hid[j] = fmaxf(a, 0.f);
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < C; i += kSaThreads) {
+            const float *wr = w2 + (int64_t)i * Cr;
+            float a = 0.f;
+            for (int j = 0; j < Cr; ++j) a = fmaf(wr[j], hid[j], a);
+            gate_s[i] = 1.f / (1.f + __expf(-a));
+        }
+        __syncthreads();
+    }
+    // ---- 4. out = v * gate + shortcut (fp32 stream), next block's BatchNorm, tapped copy
+    float2 g[N2], bg[N2], bh[N2];
+#pragma unroll
+    for (int j = 0; j < N2; ++j) {
+        g[j] = make_float2(gate_s[c + 2 * j], gate_s[c + 2 * j + 1]);
+        bg[j] = tn ? make_float2(bn_g[c + 2 * j], bn_g[c + 2 * j + 1]) : f2(1.f);
+        bh[j] = tn ? make_float2(bn_h[c + 2 * j], bn_h[c + 2 * j + 1]) : f2(0.f);
+    }
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+        const int p = (blockIdx.x * PER + k) * lanes + lane;
+        if (p >= P) continue;
+        const int64_t off = ((int64_t)b * P + p) * C + c;
+        float2 x[N2], s[N2];
+        unpack8<T>(xr[k], x);
+        if (SF) {
+            s[0] = make_float2(__uint_as_float(sr[k][0].x), __uint_as_float(sr[k][0].y));
+            s[1] = make_float2(__uint_as_float(sr[k][0].z), __uint_as_float(sr[k][0].w));
+            s[2] = make_float2(__uint_as_float(sr[k][SF ? 1 : 0].x), __uint_as_float(sr[k][SF ? 1 : 0].y));
+            s[3] = make_float2(__uint_as_float(sr[k][SF ? 1 : 0].z), __uint_as_float(sr[k][SF ? 1 : 0].w));
+        } else {
+            unpack8<T>(sr[k][0], s);
+        }
+#pragma unroll
+        for (int j = 0; j < N2; ++j) x[j] = fma2(x[j], g[j], s[j]);
+#pragma unroll
+        for (int q = 0; q < N / 4; ++q) enc_store<float>(out + off + 4 * q, x + 2 * q);
+        if (out_lp) enc_store<T>(out_lp + off, x);
+        if (tn) {
+#pragma unroll
+            for (int j = 0; j < N2; ++j) x[j] = fma2(x[j], bg[j], bh[j]);
+            enc_store<T>(tn + off, x);
+        }
+    }
+}
+
 // W+ assembly of Encoder4Editing.forward (psp_encoders.py:199-214) and of the arch (OOD_faceGAN_e4e_arch.py:261):
 //   w[b,0] = head_0;  w[b,i] = head_0 + head_i for 1 <= i <= stage, head_0 beyond;  out = w + avg[d] + delta[i,d]
 // heads: [n_styles][B][D] fp32 (the grouped EqualLinear outputs, one row block per head; heads beyond `stage` are not read).
@@ -443,4 +567,34 @@ extern "C" int ood_se_tail(const void *v, const float *w1, const float *w2, cons
     else { if (shortcut_f32) OOD_SET(__nv_bfloat16, true); else OOD_SET(__nv_bfloat16, false); }
 #undef OOD_SET
     return check_launch("se_tail");
+}
+
+extern "C" int ood_se_apply(const void *v, const float *tile_sums, int tiles, const float *w1, const float *w2, const void *shortcut, int sc_stride,
+                            const float *bn_g, const float *bn_h, float *out, void *t_next, void *out_lp, int batch, int h, int w, int channels,
+                            int reduced, int dtype, int shortcut_f32, void *stream) {
+    using namespace ood;
+    OOD_REQUIRE(v && tile_sums && tiles > 0 && w1 && w2 && shortcut && out && batch > 0 && batch <= 65535 && h > 0 && w > 0 && reduced > 0,
+                "se_apply: bad arguments");
+    OOD_REQUIRE(dtype == OOD_BF16 || dtype == OOD_F16, "se_apply: storage type must be bf16 or f16 (fp32 residual stream out)");
+    OOD_REQUIRE(sc_stride == 1 || sc_stride == 2, "se_apply: shortcut stride must be 1 or 2");
+    OOD_REQUIRE(!t_next || (bn_g && bn_h), "se_apply: t_next needs the affine coefficients");
+    OOD_REQUIRE(channels >= 64 && channels <= kSaThreads && kSaThreads % channels == 0, "se_apply: channels (%d) must be 64, 128, 256 or 512", channels);
+    OOD_REQUIRE((int64_t)h * w < (1LL << 30), "se_apply: image too large");
+    const int lanes = kSaThreads / (channels / 8);
+    const int P = h * w;
+    const size_t smem = (size_t)(2 * channels + reduced + (kSaThreads / channels) * channels) * sizeof(float);
+    // two cells per thread while that still is one resident wave (2 blocks of 512 threads per SM), four otherwise
+    int per = (int64_t)ceil_div(P, lanes * 2) * batch <= 2 * kNumSMs ? 2 : 4;
+    if (const char *e = getenv("OOD_SE_APPLY_PER")) per = atoi(e) == 2 ? 2 : 4;          // measurement switch
+    dim3 grid(ceil_div(P, lanes * per), batch);
+    cudaStream_t st = (cudaStream_t)stream;
+#define OOD_SA(T, SF, PER)                                                                                                               \
+    se_apply_kernel<T, SF, PER><<<grid, kSaThreads, smem, st>>>((const T *)v, (const float2 *)tile_sums, tiles, w1, w2, shortcut, sc_stride, bn_g, \
+                                                                bn_h, out, (T *)t_next, (T *)out_lp, h, w, channels, reduced)
+#define OOD_SA2(T, SF) do { if (per == 2) OOD_SA(T, SF, 2); else OOD_SA(T, SF, 4); } while (0)
+    if (dtype == OOD_F16) { if (shortcut_f32) OOD_SA2(__half, true); else OOD_SA2(__half, false); }
+    else { if (shortcut_f32) OOD_SA2(__nv_bfloat16, true); else OOD_SA2(__nv_bfloat16, false); }
+#undef OOD_SA2
+#undef OOD_SA
+    return check_launch("se_apply");
 }

@@ -18,6 +18,8 @@ from torch.nn import functional as F
 
 from . import kernels as K
 
+_SE_SUMS = os.environ.get('OOD_SE_SUMS', '1') != '0'         # A/B switch: pooled sums from the second convolution's epilogue + ood_se_apply (stages 2-4)
+_SE_SUMS_MIN_C = int(os.environ.get('OOD_SE_SUMS_MIN_C', 256))   # 128 channels (64 px): the sums force 128-wide tiles on the convolution, +11 us for -10 us
 _SE_FUSED = os.environ.get('OOD_SE_FUSED', '1') != '0'       # A/B switch: the one-launch squeeze-excite tail (ood_se_tail) vs the four-launch route
 # Storage type of the encoder's activations and weights on the tensor-core path.  IEEE half, not bf16: every activation here is
 # behind an eval-mode BatchNorm (O(1) values, far inside the half range; conversions saturate), the tcgen05 pipe runs f16 and
@@ -154,7 +156,12 @@ class FastEncoder:
         for i, blk in enumerate(self.blocks):
             u, _ = K.conv3x3(t, blk.w1, blk.depth, prelu=blk.slope, tag='encoder_conv')
             form = 3 if blk.stride == 2 else 0
-            v, _ = K.conv3x3(u, blk.w2, blk.depth, transposed=form, bias=blk.b2, tag='encoder_conv')
+            sums = None
+            if _SE_SUMS and blk.depth >= _SE_SUMS_MIN_C and K.conv3x3_stats_ok(u, blk.depth, form):
+                # SEModule's global average pool (helpers.py:59-76) rides in this convolution's epilogue: per-tile channel sums
+                v, _, sums = K.conv3x3(u, blk.w2, blk.depth, transposed=form, bias=blk.b2, tag='encoder_conv', tile_sums=True)
+            else:
+                v, _ = K.conv3x3(u, blk.w2, blk.depth, transposed=form, bias=blk.b2, tag='encoder_conv')
             if blk.shortcut is not None:
                 # the blocks with a shortcut convolution (3, 7, 21) follow the tapped blocks: their bf16 input is already there
                 w_sc, b_sc, c_sc, sform = blk.shortcut
@@ -164,7 +171,9 @@ class FastEncoder:
                 sc, ss = cur, blk.stride                                   # MaxPool2d(1, s): strided read
             nxt = self.blocks[i + 1].bn1 if i + 1 < len(self.blocks) else (None, None)
             tap = i in (2, 6, 20, 23)            # tapped blocks: the fp32 stream once more in the storage type, from the same pass
-            if _SE_FUSED:
+            if sums is not None:
+                cur, t, lp = K.se_apply(v, sums, blk.se1, blk.se2, sc, ss, nxt[0], nxt[1], want_lp=tap)
+            elif _SE_FUSED:
                 # SEModule's global average pool + gate MLP + residual + next BatchNorm (helpers.py:59-76, 494-501): one cluster launch
                 cur, t, lp = K.se_tail(v, blk.se1, blk.se2, sc, ss, nxt[0], nxt[1], want_lp=tap)
             else:

@@ -303,14 +303,15 @@ def torgb_weight(w, s, scale=None):
 # ----------------------------------------------------------------------------------------------- convolution
 def conv3x3(x, weight, cout, transposed=False, impl=0, d=None, noise=None, noise_w=None, bias=None, s_next=None,
             act=False, want_y=True, want_ys=False, out_f32=False, prelu=None, rgb=None, tag=None, groups=1, in_shared=False,
-            acc_in=None, tiled=False, stats_eps=None, out_dtype=None, out=None):
+            acc_in=None, tiled=False, stats_eps=None, out_dtype=None, out=None, tile_sums=False):
     """x NHWC [B,H,W,Ci] pre-modulated; weight packed for `impl`.  Returns (y, ys) (None where not requested).
     rgb=(wrgb [B,3,Co], bias [3], skip NCHW fp32 or None, up taps): fused ToRGB, returns (y, ys, rgb_out NCHW fp32).
     acc_in: fp32 NHWC [B,OH,OW,Co] seed added to the accumulator before the epilogue (tcgen05 path).
     tiled: acc_in, and y when out_f32, are flat fp32 tensors in the kernel's tile order (ood_conv3x3_tiled_bytes): the fast form
     of a seed that only ever travels between two launches with the same geometry.
     stats_eps: also return [B,Co,2] = (mean, rstd) of y as stored, computed in the epilogue -> (y, ys, stats); use
-    conv3x3_stats_ok() for the envelope.
+    conv3x3_stats_ok() for the envelope.  tile_sums=True: (y, ys, ws) with ws = the epilogue's per-tile channel sums [B, tiles, Co, 2]
+    (sum of y as stored, 0), no finalise launch: the pooled sums for se_apply().
     out_dtype: storage type of y / ys when it differs from x's (torch.bfloat16 or torch.float16; tcgen05 path).
     out: a preallocated contiguous tensor to receive y (shape / dtype checked)."""
     _cuda(x, weight, d, noise, noise_w, bias, s_next, acc_in)
@@ -360,6 +361,13 @@ def conv3x3(x, weight, cout, transposed=False, impl=0, d=None, noise=None, noise
         ws = torch.empty(nws, device=x.device, dtype=torch.float32)
         st = torch.empty(b, cout, 2, device=x.device, dtype=torch.float32)
         a.stats_ws, a.stats_out, a.stats_eps = _ptr(ws), _ptr(st), float(stats_eps)
+    if tile_sums:
+        assert stats_eps is None
+        nws = _lib.lib().ood_conv3x3_stats_workspace(b, h, w, cin, cout, transposed) // 4
+        if nws <= 0:
+            raise RuntimeError('ood_gan_inversion_b200: conv3x3 fused statistics are outside their envelope (see ood_b200.h)')
+        st = torch.empty(b, nws // (b * cout * 2), cout, 2, device=x.device, dtype=torch.float32)
+        a.stats_ws = _ptr(st)
     rgb_out = None
     if rgb is not None:
         wrgb, rbias, rskip, rtaps = rgb
@@ -373,15 +381,16 @@ def conv3x3(x, weight, cout, transposed=False, impl=0, d=None, noise=None, noise
         check(_lib.lib().ood_conv3x3(C.byref(a), _stream()), 'conv3x3')
     if rgb is not None:
         return y, ys, rgb_out
-    if stats_eps is not None:
+    if stats_eps is not None or tile_sums:
         return y, ys, st
     return y, ys
 
 
 def conv3x3_stats_ok(x, cout, transposed=0):
-    """True when conv3x3(..., stats_eps=...) is available for this input (tcgen05 path, bf16, wide tiles, one image per tile)."""
+    """True when conv3x3(..., stats_eps=... / tile_sums=True) is available for this input (tcgen05 path, 16-bit storage, wide tiles, one
+    image per tile)."""
     b, h, w, cin = x.shape
-    return x.dtype == torch.bfloat16 and cin % 64 == 0 and \
+    return x.dtype in (torch.bfloat16, torch.float16) and cin % 64 == 0 and \
         _lib.lib().ood_conv3x3_stats_workspace(b, h, w, cin, cout, int(transposed)) > 0
 
 
@@ -699,6 +708,26 @@ def se_tail(v, w1, w2, shortcut, sc_stride=1, bn_g=None, bn_h=None, want_lp=Fals
     with _timed('se_tail', nbytes):
         check(_lib.lib().ood_se_tail(_ptr(v), _ptr(w1), _ptr(w2), _ptr(shortcut), int(sc_stride), _ptr(bn_g), _ptr(bn_h), _ptr(out), _ptr(tn), _ptr(lp),
                                      b, h, w, c, w1.shape[0], _dt(v), int(shortcut.dtype == torch.float32), _stream()), 'se_tail')
+    return out, tn, lp
+
+
+def se_apply(v, tile_sums, w1, w2, shortcut, sc_stride=1, bn_g=None, bn_h=None, want_lp=False):
+    """se_tail() with the pooling already done: tile_sums [B, tiles, C, 2] from the conv3x3(..., tile_sums=True) call that wrote v."""
+    _cuda(v, tile_sums, w1, w2, shortcut, bn_g, bn_h)
+    assert v.is_contiguous() and shortcut.is_contiguous() and shortcut.dtype in (v.dtype, torch.float32)
+    b, h, w, c = v.shape
+    assert shortcut.shape == (b, h * sc_stride, w * sc_stride, c), 'shortcut must be exactly stride x the output size'
+    assert tile_sums.dtype == torch.float32 and tile_sums.is_contiguous() and tile_sums.dim() == 4 and tile_sums.shape[0] == b and \
+        tuple(tile_sums.shape[2:]) == (c, 2)
+    out = torch.empty(b, h, w, c, device=v.device, dtype=torch.float32)
+    tn = torch.empty_like(v) if bn_g is not None else None
+    lp = torch.empty_like(v) if want_lp else None
+    es = _esize(v)
+    nbytes = b * h * w * c * (es + shortcut.element_size() + 4 + (0 if tn is None else es) + (0 if lp is None else es))
+    with _timed('se_apply', nbytes):
+        check(_lib.lib().ood_se_apply(_ptr(v), _ptr(tile_sums), tile_sums.shape[1], _ptr(w1), _ptr(w2), _ptr(shortcut), int(sc_stride), _ptr(bn_g),
+                                      _ptr(bn_h), _ptr(out), _ptr(tn), _ptr(lp), b, h, w, c, w1.shape[0], _dt(v),
+                                      int(shortcut.dtype == torch.float32), _stream()), 'se_apply')
     return out, tn, lp
 
 

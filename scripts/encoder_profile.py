@@ -41,3 +41,28 @@ for name, v in sorted(prof.items(), key=lambda kv: -kv[1]['ms']):
     rate = work / v['ms'] / 1e9 if v['ms'] > 0 else 0
     print(f"{v['ms']:8.3f} ms {v['launches']:4d}x  {rate:9.1f} G/s  {name}")
 print('sum', tot)
+
+# the encoder alone as a CUDA graph (how it runs inside the step): ms per replay
+K.conv3x3 = orig
+encoder_fast.K.conv3x3 = orig
+s = torch.cuda.Stream()
+with torch.cuda.stream(s):
+    for _ in range(3):
+        fast(x, return_feats=True)
+    s.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=s):
+        out = fast(x, return_feats=True)
+    for _ in range(5):
+        g.replay()
+    ts = []
+    for _ in range(7):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(s)
+        for _ in range(20):
+            g.replay()
+        e1.record(s)
+        s.synchronize()
+        ts.append(e0.elapsed_time(e1) / 20)
+ts.sort()
+print(f'encoder as a graph: best {ts[0]:.3f} ms, median {ts[len(ts) // 2]:.3f} ms per replay (batch 16)')

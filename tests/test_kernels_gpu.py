@@ -1003,6 +1003,49 @@ def test_se_tail_cluster_kernel(dt, case):
     assert torch.equal(out, K.se_tail(v, w1, w2, sc, stride, bn_g, bn_h)[0])          # deterministic
 
 
+@pytest.mark.parametrize('per', ['2', '4'])
+@pytest.mark.parametrize('dt', [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize('case', [dict(b=3, h=32, w=32, ci=256, co=256, form=0, sc_f32=True, tap=True), dict(b=2, h=33, w=17, ci=128, co=128, form=3, sc_f32=False, tap=False),
+                                  dict(b=2, h=16, w=16, ci=512, co=512, form=0, sc_f32=True, tap=False), dict(b=5, h=64, w=64, ci=64, co=128, form=3, sc_f32=True, tap=True)])
+def test_se_apply_from_the_convolution_tile_sums(case, dt, per, monkeypatch):
+    """The encoder's squeeze-excite tail with the pooling in the producing convolution's epilogue (helpers.py:59-76, 494-501): conv3x3(...,
+    tile_sums=True) leaves per-tile channel sums of v AS STORED (f16 or bf16), ood_se_apply turns them into the gate and applies it in one
+    streaming pass.  Checked against the torch formula on the stored v, against the cluster kernel (ood_se_tail), for determinism, and
+    the tile sums against a direct sum."""
+    from ood_gan_inversion_b200 import kernels as K
+    monkeypatch.setenv('OOD_SE_APPLY_PER', per)
+    b, h, w_, ci, c, form = (case[k] for k in ('b', 'h', 'w', 'ci', 'co', 'form'))
+    u = rnd(b, h, w_, ci, seed=1).to(dt).to(DEV)
+    wt = (rnd(c, ci, 3, 3, seed=2) / (3 * ci ** 0.5)).to(dt).float()
+    wp = K.pack_conv_weight(wt.to(DEV), dt, False)
+    bias = rnd(c, seed=7).to(DEV)
+    assert K.conv3x3_stats_ok(u, c, form)
+    v, _, sums = K.conv3x3(u, wp, c, transposed=form, bias=bias, tile_sums=True)
+    v0, _ = K.conv3x3(u, wp, c, transposed=form, bias=bias)
+    assert torch.equal(v, v0) and v.dtype == dt
+    oh, ow = v.shape[1], v.shape[2]
+    torch.testing.assert_close(sums[..., 0].sum(1), v.float().sum((1, 2)), rtol=1e-4, atol=1e-2)
+    stride = 2 if form == 3 else 1
+    cr = c // 16
+    sc = rnd(b, oh * stride, ow * stride, c, seed=3)
+    sc = (sc if case['sc_f32'] else sc.to(dt)).to(DEV)
+    w1, w2 = (rnd(cr, c, seed=4) / c ** 0.5).to(DEV), (rnd(c, cr, seed=5) / cr ** 0.5).to(DEV)
+    bn_g, bn_h = (1 + 0.1 * rnd(c, seed=6)).to(DEV), (0.1 * rnd(c, seed=8)).to(DEV)
+    out, tn, lp = K.se_apply(v, sums, w1, w2, sc, stride, bn_g, bn_h, want_lp=case['tap'])
+    gate = torch.sigmoid(torch.relu(v.float().mean((1, 2)) @ w1.t()) @ w2.t())
+    ref = v.float() * gate[:, None, None, :] + sc.float()[:, ::stride, ::stride]
+    torch.testing.assert_close(out, ref, rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(tn.float(), (ref * bn_g + bn_h).to(dt).float(), rtol=1e-2, atol=1e-2)
+    if case['tap']:
+        torch.testing.assert_close(lp.float(), ref.to(dt).float(), rtol=1e-2, atol=1e-2)
+    else:
+        assert lp is None
+    torch.testing.assert_close(out, K.se_tail(v, w1, w2, sc, stride, bn_g, bn_h)[0], rtol=1e-5, atol=1e-5)
+    assert torch.equal(out, K.se_apply(v, sums, w1, w2, sc, stride, bn_g, bn_h)[0])          # deterministic
+    out2, tn2, _ = K.se_apply(v, sums, w1, w2, sc, stride)                                  # last block: no following BatchNorm
+    assert tn2 is None and torch.equal(out2, out)
+
+
 @pytest.mark.parametrize('case', [dict(b=2, h=64, w=64, ci=128, co=128), dict(b=1, h=16, w=32, ci=64, co=256), dict(b=3, h=32, w=16, ci=64, co=64),
                                   dict(b=1, h=128, w=128, ci=64, co=64)])
 def test_conv_transposed_split_into_exact_tiles(case, monkeypatch):
