@@ -96,6 +96,55 @@ __device__ __forceinline__ void tmem_alloc(uint32_t *holder_smem, uint32_t ncols
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
+// ---- CTA pairs (cta_group::2): two CTAs of a cluster run ONE 256-row MMA; each holds its own 128 rows of A and HALF of the B tile
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same shared-memory offset in the CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA loads of a CTA pair: the bytes land in THIS CTA's shared memory, the transaction count on the LEADER's barrier (bar_cluster)
+__device__ __forceinline__ void tma_load_4d_pair(void *dst, const CUtensorMap *map, uint32_t bar_cluster, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_pair(void *dst, const CUtensorMap *map, uint32_t bar_cluster, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t *holder_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(holder_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrives (when the MMAs issued so far retire) on the barrier at this shared-memory offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
 // D[tmem] (+)= A[smem] * B[smem]^T, bf16 inputs, fp32 accumulate
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -136,10 +185,10 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
     return d;
 }
 
-template <int BN, int BK>
+template <int BN, int BK, bool CTA2 = false>
 struct TcCfg {
     static constexpr int kABytes = TBM * BK * 2;
-    static constexpr int kBBytes = BN * BK * 2;
+    static constexpr int kBBytes = (CTA2 ? BN / 2 : BN) * BK * 2;          // CTA pairs: a CTA holds half of the N tile's weight rows (6 stages instead of 4 at BN = 256)
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kStages = (200 * 1024 / kStageBytes) > 8 ? 8 : (200 * 1024 / kStageBytes);
     static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
@@ -176,10 +225,13 @@ __device__ __forceinline__ TileCoord decode_tile(const TcParams &p, int tile, in
 // EPW: epilogue warps, 4 or 8.  A warp reads the TMEM lane quadrant warp % 4; with 8 warps two warps share a quadrant and
 // take alternate 32-column chunks -- for tiles whose K is short (the fused-phase transposed form, K = 4 shifts) the epilogue,
 // not the MMA, sets the tile period.
-template <int BN, int BK, bool SEED = false, bool STATS = false, int EPW = 4>
+// CTA2: the CTAs 2c, 2c+1 form a cluster and work on the M tiles 2m, 2m+1 of one N tile as ONE tcgen05.mma.cta_group::2 of 256 rows:
+// every CTA loads its own A tile and half of the B tile (half the weight bytes per SM from L2 and from shared memory), CTA 0 of
+// the pair issues the MMAs for both, each CTA's TMEM receives its own 128 rows and its epilogue warps drain them as before.
+template <int BN, int BK, bool SEED = false, bool STATS = false, int EPW = 4, bool CTA2 = false>
 __global__ void __launch_bounds__(64 + 32 * EPW, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
-    using Cfg = TcCfg<BN, BK>;
+    using Cfg = TcCfg<BN, BK, CTA2>;
     constexpr int S = Cfg::kStages;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -194,16 +246,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kchunks = p.cin / BK;
 
+    const uint32_t cta_rank = CTA2 ? cluster_ctarank() : 0u;
+    // work items of this CTA: tiles, or (CTA2) pairs of M-adjacent tiles of which this CTA takes the one of its rank
+    const int n_items = CTA2 ? p.total_tiles >> 1 : p.total_tiles;
+    const int item0 = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, item_step = CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    auto item_tile = [&](int q) -> int {
+        if (!CTA2) return q;
+        return (2 * (q / p.n_tiles_n) + (int)cta_rank) * p.n_tiles_n + q % p.n_tiles_n;
+    };
+
     if (warp == 0 && lane == 0) {
         for (int i = 0; i < S; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], EPW); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], CTA2 ? 2 * EPW : EPW); }      // pair: both CTAs' epilogue warps arrive on the leader's
         fence_barrier_init();
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
     }
-    if (warp == 1) tmem_alloc(tmem_holder, Cfg::kTmemCols);
+    if (warp == 1) { if (CTA2) tmem_alloc_pair(tmem_holder, Cfg::kTmemCols); else tmem_alloc(tmem_holder, Cfg::kTmemCols); }
     tc_fence_before();
-    __syncthreads();
+    if (CTA2) cluster_sync_all(); else __syncthreads();       // pair: the peer's barriers must exist before anything is signalled across
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
 
@@ -212,16 +273,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            for (int q = item0; q < n_items; q += item_step) {
+                const int tile = item_tile(q);
                 const TileCoord tc = decode_tile(p, tile, BN);
                 const TcPhase &P = p.ph[tc.phase];
                 for (int t = 0; t < P.ntaps; ++t) {
                     for (int kc = 0; kc < kchunks; ++kc) {
                         mbar_wait(&empty[stage], phase ^ 1);
-                        mbar_expect_tx(&full[stage], Cfg::kStageBytes);
-                        tma_load_4d(sA + stage * Cfg::kABytes, &tmA, &full[stage], kc * BK, tc.x0 * p.isx + P.dx[t], tc.y0 * p.isy + P.dy[t],
-                                    p.in_shared ? tc.bl0 : tc.b0);
-                        tma_load_3d(sB + stage * Cfg::kBBytes, &tmB, &full[stage], kc * BK, tc.n0, P.wt[t] + tc.group * p.wtaps);
+                        if constexpr (CTA2) {
+                            // both CTAs' bytes are counted on the leader's barrier (its producer announces the sum)
+                            if (cta_rank == 0) mbar_expect_tx(&full[stage], 2 * Cfg::kStageBytes);
+                            const uint32_t lbar = mapa_u32(smem_u32(&full[stage]), 0);
+                            tma_load_4d_pair(sA + stage * Cfg::kABytes, &tmA, lbar, kc * BK, tc.x0 * p.isx + P.dx[t], tc.y0 * p.isy + P.dy[t], tc.b0);
+                            tma_load_3d_pair(sB + stage * Cfg::kBBytes, &tmB, lbar, kc * BK, tc.n0 + (int)cta_rank * (BN / 2), P.wt[t]);
+                        } else {
+                            mbar_expect_tx(&full[stage], Cfg::kStageBytes);
+                            tma_load_4d(sA + stage * Cfg::kABytes, &tmA, &full[stage], kc * BK, tc.x0 * p.isx + P.dx[t], tc.y0 * p.isy + P.dy[t],
+                                        p.in_shared ? tc.bl0 : tc.b0);
+                            tma_load_3d(sB + stage * Cfg::kBBytes, &tmB, &full[stage], kc * BK, tc.n0, P.wt[t] + tc.group * p.wtaps);
+                        }
                         if (++stage == S) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -229,14 +299,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
     } else if (warp == 1) {
         // ===================================================== MMA issuer
-        if (elect_one()) {
+        if ((!CTA2 || cta_rank == 0) && elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            // instruction descriptor: A / B format field 1 = bf16, 0 = f16 (bits 7..9 and 10..12)
-            const uint32_t idesc = p.in_f16 ? (Cfg::kIdesc & ~((1u << 7) | (1u << 10))) : Cfg::kIdesc;
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            // instruction descriptor: A / B format field 1 = bf16, 0 = f16 (bits 7..9 and 10..12); pair: M = 256
+            constexpr uint32_t kIdescM = CTA2 ? ((Cfg::kIdesc & ~(0x1Fu << 24)) | ((uint32_t)(2 * TBM >> 4) << 24)) : Cfg::kIdesc;
+            const uint32_t idesc = p.in_f16 ? (kIdescM & ~((1u << 7) | (1u << 10))) : kIdescM;
+            for (int q = item0; q < n_items; q += item_step) {
+                const int tile = item_tile(q);
                 const TileCoord tc = decode_tile(p, tile, BN);
                 const int kiters = p.ph[tc.phase].ntaps * kchunks;
                 mbar_wait(&tempty[acc], acc_phase ^ 1);
@@ -248,12 +320,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const uint64_t da = make_smem_desc<BK * 2>(smem_u32(sA + stage * Cfg::kABytes));
                     const uint64_t db = make_smem_desc<BK * 2>(smem_u32(sB + stage * Cfg::kBBytes));
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k)
-                        umma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (it | k) != 0);
-                    umma_commit(&empty[stage]);          // frees the smem slot when these MMAs retire
+                    for (int k = 0; k < BK / 16; ++k) {
+                        if constexpr (CTA2) umma_bf16_pair(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (it | k) != 0);
+                        else umma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (it | k) != 0);
+                    }
+                    if constexpr (CTA2) umma_commit_pair(&empty[stage]); else umma_commit(&empty[stage]);          // frees the smem slot (of both CTAs) when these MMAs retire
                     if (++stage == S) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&tfull[acc]);                // accumulator complete -> epilogue
+                if constexpr (CTA2) umma_commit_pair(&tfull[acc]); else umma_commit(&tfull[acc]);                // accumulator complete -> epilogue (of both CTAs)
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
@@ -266,7 +340,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const float nw = (p.ep.noise && p.ep.noise_w) ? *p.ep.noise_w : 0.f;
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        for (int q = item0; q < n_items; q += item_step) {
+            const int tile = item_tile(q);
             const TileCoord tc = decode_tile(p, tile, BN);
             const TcPhase &P = p.ph[tc.phase];
             const int b = tc.b0 + nb, oy = tc.y0 + ty, ox = tc.x0 + tx;
@@ -320,10 +395,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 // ahead), and for this CTA's first tile at its start; the register prefetch below then only covers an L2 hit
                 const int64_t blk = (int64_t)BN * TBM * sizeof(float);
                 const char *base = reinterpret_cast<const char *>(p.ep.acc_in);
-                if (tile == (int)blockIdx.x)
+                if (q == item0)
                     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(base + (int64_t)tile * blk), "r"((uint32_t)blk) : "memory");
-                if (tile + (int)gridDim.x < p.total_tiles)
-                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(base + (int64_t)(tile + gridDim.x) * blk), "r"((uint32_t)blk) : "memory");
+                if (q + item_step < n_items)
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(base + (int64_t)item_tile(q + item_step) * blk), "r"((uint32_t)blk) : "memory");
             }
             float4 sd[8], sdn[8] = {};
             if (SEED && seed) {
@@ -520,16 +595,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[acc]);
+            if (lane == 0) {
+                if constexpr (CTA2) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[acc]), 0));      // the leader's MMA thread waits for both CTAs' drains
+                else mbar_arrive(&tempty[acc]);
+            }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }
 
     tc_fence_before();
-    __syncthreads();
+    if (CTA2) cluster_sync_all(); else __syncthreads();       // pair: no CTA may exit while its peer can still signal into it
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, Cfg::kTmemCols);
+        if (CTA2) tmem_dealloc_pair(tmem_base, Cfg::kTmemCols); else tmem_dealloc(tmem_base, Cfg::kTmemCols);
     }
 }
 
@@ -552,11 +630,12 @@ static EncodeTiledFn get_encode_fn() {
 
 static int pow2_ceil(int v) { int r = 1; while (r < v) r <<= 1; return r; }
 
-template <int BN, int BK, bool SEED = false, bool STATS = false, int EPW = 4>
+template <int BN, int BK, bool SEED = false, bool STATS = false, int EPW = 4, bool CTA2 = false>
 static int launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, const TcParams &p, cudaStream_t st) {
-    using Cfg = TcCfg<BN, BK>;
+    using Cfg = TcCfg<BN, BK, CTA2>;
     static_assert(EPW == 4 || (EPW == 8 && !SEED && !STATS), "8 epilogue warps: plain kernels only");
-    auto kern = conv_tc_kernel<BN, BK, SEED, STATS, EPW>;
+    static_assert(!CTA2 || (EPW == 4 && BK == 64 && BN >= 128), "CTA pairs: wide tiles, four epilogue warps");
+    auto kern = conv_tc_kernel<BN, BK, SEED, STATS, EPW, CTA2>;
     constexpr int kSmem = Cfg::kSmemBytes + (STATS ? Cfg::kStatBytes : 0);
     static_assert(kSmem <= 227 * 1024, "shared memory budget");
     static DeviceOnce attr_set;
@@ -567,6 +646,18 @@ static int launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, const TcPar
     int dev = 0, sms = kNumSMs;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if constexpr (CTA2) {
+        const int grid = std::min(p.total_tiles, sms) & ~1;
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(64 + 32 * EPW); cfg.dynamicSmemBytes = kSmem; cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p);
+        if (e != cudaSuccess) { set_error("conv3x3 tc: CTA-pair launch: %s", cudaGetErrorString(e)); return OOD_ERR_CUDA; }
+        return check_launch("conv3x3 tc pair");
+    }
     const int grid = std::min(p.total_tiles, sms);
     kern<<<grid, 64 + 32 * EPW, kSmem, st>>>(tmA, tmB, p);
     return check_launch("conv3x3 tc");
@@ -684,6 +775,14 @@ static int conv3x3_tc_geom(const ood_conv3x3_args &a, const ConvGeom &g, cudaStr
     OOD_REQUIRE(!a.acc_in || (uintptr_t)a.acc_in % 16 == 0, "conv3x3 tc: acc_in must be 16-byte aligned");
     OOD_REQUIRE((uintptr_t)a.out_y % 32 == 0 && (uintptr_t)a.out_ys % 32 == 0, "conv3x3 tc: outputs must be 32-byte aligned (256-bit stores)");
 
+    // CTA pairs (cta_group::2): single-phase, ungrouped launches of wide tiles with an even number of M tiles and at least a tile per SM
+    // OOD_CTA2: 0 off, 1 (default) = the 256-wide tiles, 2 = the 128-wide tiles too (measured slower); OOD_CTA2_MIN_TILES: launches with fewer tiles stay single-CTA
+    // (read per call: the parity tests switch them inside one process)
+    const char *e2 = getenv("OOD_CTA2"), *e2m = getenv("OOD_CTA2_MIN_TILES");
+    const int cta2_mode = e2 ? atoi(e2) : 1, cta2_min = e2m ? atoi(e2m) : 2 * kNumSMs;
+    const int m_tiles = p.ph[0].tiles_x * p.ph[0].tiles_y * p.ph[0].tiles_b;
+    const bool pair = cta2_mode > 0 && p.nphases == 1 && groups == 1 && !p.in_shared && !p.fused && BK == 64 && (BN == 256 || BN == 128) &&
+                      m_tiles % 2 == 0 && p.total_tiles >= cta2_min && (cta2_mode > 1 || BN == 256);
     CUtensorMap tmA, tmB;
     {
         cuuint64_t dims[4] = {(cuuint64_t)a.cin, (cuuint64_t)a.w, (cuuint64_t)a.h, (cuuint64_t)(p.in_shared ? p.gbatch : a.batch)};
@@ -700,7 +799,7 @@ static int conv3x3_tc_geom(const ood_conv3x3_args &a, const ConvGeom &g, cudaStr
         const cuuint64_t ncols = (cuuint64_t)(p.fused ? 4 * a.cout : a.cout);
         cuuint64_t dims[3] = {(cuuint64_t)a.cin, ncols, (cuuint64_t)(p.wtaps * groups)};
         cuuint64_t strides[2] = {(cuuint64_t)a.cin * 2, ncols * a.cin * 2};
-        cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)BN, 1};
+        cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)(pair ? BN / 2 : BN), 1};          // pair: every CTA loads half of the N tile's rows
         cuuint32_t es[3] = {1, 1, 1};
         CUresult r = encode(&tmB, a.dtype == OOD_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void *>(a.weight), dims, strides, box, es,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
@@ -713,13 +812,15 @@ static int conv3x3_tc_geom(const ood_conv3x3_args &a, const ConvGeom &g, cudaStr
                     "conv3x3 tc: stats_out needs the stride-1 / stride-2 pad-1 / 1x1 form, bf16 out_y only, cin %% 64 == 0, cout %% 128 == 0 and >= 128 output pixels");
         p.ep.stat_partial = a.stats_ws;
         p.ep.stat_sums_only = a.stats_out == nullptr;
-        const int rc = BN == 256 ? launch_tc<256, 64, false, true>(tmA, tmB, p, st) : launch_tc<128, 64, false, true>(tmA, tmB, p, st);
+        const int rc = pair ? (BN == 256 ? launch_tc<256, 64, false, true, 4, true>(tmA, tmB, p, st) : launch_tc<128, 64, false, true, 4, true>(tmA, tmB, p, st))
+                            : (BN == 256 ? launch_tc<256, 64, false, true>(tmA, tmB, p, st) : launch_tc<128, 64, false, true>(tmA, tmB, p, st));
         if (rc != OOD_OK) return rc;
         if (!a.stats_out) return OOD_OK;
         in_finalize_launch(a.stats_ws, a.stats_out, (int64_t)g.OH * g.OW, a.cout, p.ph[0].tiles_x * p.ph[0].tiles_y, a.stats_eps, a.batch, st);
         return check_launch("conv3x3 tc stats", 1);
     }
     if (a.acc_in) {     // seeded accumulators: built for the wide tiles only (the AlignNet convolutions)
+        if (pair) return BN == 256 ? launch_tc<256, 64, true, false, 4, true>(tmA, tmB, p, st) : launch_tc<128, 64, true, false, 4, true>(tmA, tmB, p, st);
         if (BN == 256 && BK == 64) return launch_tc<256, 64, true>(tmA, tmB, p, st);
         if (BN == 128 && BK == 64) return launch_tc<128, 64, true>(tmA, tmB, p, st);
         set_error("conv3x3 tc: acc_in needs cin %% 64 == 0 and a 128- or 256-wide N tile (cout %% 128 == 0), got cin %d cout %d", a.cin, a.cout);
@@ -733,6 +834,7 @@ static int conv3x3_tc_geom(const ood_conv3x3_args &a, const ConvGeom &g, cudaStr
         OOD_TC_CASE8(256, 64); OOD_TC_CASE8(128, 64); OOD_TC_CASE8(256, 32); OOD_TC_CASE8(128, 32);
 #undef OOD_TC_CASE8
     }
+    if (pair) return BN == 256 ? launch_tc<256, 64, false, false, 4, true>(tmA, tmB, p, st) : launch_tc<128, 64, false, false, 4, true>(tmA, tmB, p, st);
 #define OOD_TC_CASE(bn, bk) if (BN == bn && BK == bk) return launch_tc<bn, bk>(tmA, tmB, p, st)
     OOD_TC_CASE(256, 64); OOD_TC_CASE(128, 64); OOD_TC_CASE(64, 64); OOD_TC_CASE(32, 64);
     OOD_TC_CASE(256, 32); OOD_TC_CASE(128, 32); OOD_TC_CASE(64, 32); OOD_TC_CASE(32, 32);

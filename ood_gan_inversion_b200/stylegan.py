@@ -30,6 +30,7 @@ _PRECISION = os.environ.get('OOD_B200_PRECISION', 'bf16')
 # zero-padded weight blocks cost 1.8x the MACs, which only the HBM / per-tile-overhead bound small-channel layers can afford
 _FUSED_T_MAX_CO = int(os.environ.get('OOD_FUSED_T_MAX_CO', 64))
 _FUSE_RGB_ROWS = os.environ.get('OOD_FUSE_RGB_ROWS', '0') != '0'  # ToRGB in the row-sliding kernel's epilogue (512 / 1024 px layers): measured, OFF (see _synthesis)
+_FUSE_RGB_TC = os.environ.get('OOD_FUSE_RGB_TC', '1') != '0'    # ToRGB in the generic tiles' epilogue (128 / 256 channels); A/B switch
 _CONVT_ROWS = os.environ.get('OOD_CONVT_ROWS', '1') != '0'      # the row-streaming transposed kernel for the 64 -> 32 layer (csrc/convt_rows.cu)
 
 
@@ -624,7 +625,7 @@ class Generator(nn.Module):
             # for 0.43 ms of ToRGB removed, 639.5 -> 625.6 images/s on the same box (OOD_FUSE_RGB_ROWS=1 repeats the experiment)
             rows_ok = _FUSE_RGB_ROWS and co in (32, 64) and conv2.conv.cin_p == co and res % 128 == 0 and \
                 b * ((res + 31) // 32) * (res // 128) >= int(os.environ.get('OOD_ROWS_MIN_STRIPS', 148))
-            fuse = _PRECISION == 'bf16' and (128 <= co <= 256 or rows_ok) and co == conv2.conv.out_channel and len(to_rgb.taps_up) == 4 and res % 2 == 0
+            fuse = _PRECISION == 'bf16' and (128 <= co <= 256 and _FUSE_RGB_TC or rows_ok) and co == conv2.conv.out_channel and len(to_rgb.taps_up) == 4 and res % 2 == 0
             if fuse:
                 y, ys, skip = conv2.run_nhwc(y1s, lat[:, i + 1], draw(noise[2 + 2 * blk], res), s_next=s_next, want_y=need_y,
                                              want_ys=not last, d=d2, rgb=to_rgb.fused_args(lat[:, i + 2], skip))

@@ -695,6 +695,61 @@ def test_conv3x3_seeded_accumulator(case):
                     acc_in=seed)
 
 
+@pytest.mark.parametrize('case', [dict(b=2, h=64, w=128, ci=128, co=256, form=0), dict(b=4, h=64, w=64, ci=64, co=128, form=0),
+                                  dict(b=2, h=63, w=50, ci=64, co=512, form=0), dict(b=4, h=128, w=128, ci=128, co=128, form=3),
+                                  dict(b=8, h=64, w=32, ci=256, co=256, form=4), dict(b=2, h=64, w=128, ci=64, co=256, form=0, f16=True)])
+def test_conv3x3_cta_pair_kernel(case, monkeypatch):
+    """conv_tc_kernel<CTA2>: two CTAs of a cluster run one tcgen05.mma.cta_group::2 (M = 256: each CTA's own 128 pixels, half of the
+    weight tile per CTA, multicast commits, the leader's barriers).  Same arithmetic as the single-CTA kernel -> bit-identical
+    outputs for every epilogue variant (plain with d / noise / bias / activation / s_next, fp32 tile-order seed, fused statistics),
+    and the fp64 formula within the storage rounding."""
+    b, h, w_, ci, co, form = (case[k] for k in ('b', 'h', 'w', 'ci', 'co', 'form'))
+    dt = torch.float16 if case.get('f16') else torch.bfloat16
+    k = 1 if form == 4 else 3
+    x = rnd(b, ci, h, w_, seed=1).to(dt).float()
+    wt = (rnd(co, ci, k, k, seed=2) / (ci * k * k) ** 0.5).to(dt).float()
+    from ood_gan_inversion_b200 import kernels as KK
+    wp = KK.pack_conv1x1_weight(wt.to(DEV), dt, False) if form == 4 else KK.pack_conv_weight(wt.to(DEV), dt, False)
+    xn = nhwc(x, dt)
+    stride = 2 if form == 3 else 1
+    torch.backends.cudnn.allow_tf32 = False          # launches of >= 100 tiles (narrower tiles below that): the fp32 formula on the device
+    ref = F.conv2d(x.to(DEV), wt.to(DEV), stride=stride, padding=0 if form == 4 else 1).cpu()
+    oh, ow = ref.shape[2], ref.shape[3]
+    d, bias, s_next = 0.5 + torch.rand(b, co, generator=g(3)), rnd(co, seed=4), 1 + 0.3 * rnd(b, co, seed=5)
+    noise, nw = rnd(b, 1, oh, ow, seed=6), torch.tensor([0.37])
+    slope = 0.25 + 0.1 * rnd(co, seed=7)
+    full = dict(transposed=form, impl=0, d=d.to(DEV), noise=noise.to(DEV), noise_w=nw.to(DEV), bias=bias.to(DEV), s_next=s_next.to(DEV), act=True,
+                want_y=True, want_ys=True)
+
+    def run():
+        out = {}
+        out['y'], out['ys'] = KK.conv3x3(xn, wp, co, **full)
+        out['f32'], _ = KK.conv3x3(xn, wp, co, transposed=form, impl=0, out_f32=True)
+        if form != 3:       # a second convolution seeded with the first one's accumulators (tile order and NHWC)
+            seed_t, _ = KK.conv3x3(xn, wp, co, transposed=form, impl=0, out_f32=True, tiled=True)
+            out['seeded_t'], _ = KK.conv3x3(xn, wp, co, transposed=form, impl=0, prelu=slope.to(DEV), acc_in=seed_t, tiled=True)
+            out['seeded'], _ = KK.conv3x3(xn, wp, co, transposed=form, impl=0, prelu=slope.to(DEV), acc_in=out['f32'])
+        if KK.conv3x3_stats_ok(xn, co, form):
+            out['sy'], _, out['st'] = KK.conv3x3(xn, wp, co, transposed=form, impl=0, bias=bias.to(DEV), stats_eps=1e-5)
+            out['ty'], _, out['sums'] = KK.conv3x3(xn, wp, co, transposed=form, impl=0, bias=bias.to(DEV), tile_sums=True)
+        torch.cuda.synchronize()
+        return out
+
+    monkeypatch.setenv('OOD_CTA2', '0')
+    single = run()
+    monkeypatch.setenv('OOD_CTA2', '2')
+    monkeypatch.setenv('OOD_CTA2_MIN_TILES', '2')
+    pair = run()
+    assert set(single) == set(pair) and 'y' in pair
+    for name in single:
+        assert torch.equal(single[name], pair[name]), name
+    yref = oops.fused_leaky_relu(ref * d[:, :, None, None] + nw * noise, bias)
+    tol = dict(rtol=2e-2, atol=3e-2) if dt == torch.bfloat16 else dict(rtol=4e-3, atol=4e-3)
+    torch.testing.assert_close(nchw(pair['y']), yref, **tol)
+    torch.testing.assert_close(nchw(pair['ys']), yref * s_next[:, :, None, None], **tol)
+    torch.testing.assert_close(nchw(pair['f32']), ref, rtol=1e-3, atol=1e-3)
+
+
 @pytest.mark.parametrize('dtype,c', [(torch.float32, 32), (torch.bfloat16, 64), (torch.bfloat16, 128)])
 def test_alignnet_split_front_and_fused_statistics(dtype, c):
     b, h, w = 2, 37, 53
