@@ -701,10 +701,10 @@ def main():
             dist.destroy_process_group()
         return 0
 
-    def ncu_traffic(name):
+    def ncu_traffic(name, summary='ncu_r01_summary.json'):
         """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the kernel family from the committed ncu --set full capture."""
         try:
-            d = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'profiles', 'ncu_r01_summary.json')))[name]
+            d = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'profiles', summary)))[name]
             unit = dict(byte=1.0, Kbyte=1e3, Mbyte=1e6, Gbyte=1e9)
             tot = 0.0
             for k in ('dram_read', 'dram_write'):
@@ -732,8 +732,9 @@ def main():
                          d2h_bytes_per_step=out_host.numel() * 4, ms_per_step=ms_e2e / args.steps),
                 gpu_launches=int(launches),
                 roofline=dict(kernel='conv_tc_kernel (tcgen05 implicit-GEMM 3x3 modulated conv)', bound='tensor', achieved=conv_tf,
-                              peak=pk['tf_sus'], unit='TFLOP/s', frac=conv_tf / pk['tf_sus'], traffic=ncu_traffic('conv256'),
-                              traffic_note='DRAM bytes of one conv_tc_kernel<256,64,STATS> launch (AlignNet 1024->1024 ch at 64 px: 1.24 TFLOP, 0.29 GB of activations + weights algorithmic; L2 hit 96 %), profiles/ncu_r01_conv256_raw.csv',
+                              peak=pk['tf_sus'], unit='TFLOP/s', frac=conv_tf / pk['tf_sus'],
+                              traffic=ncu_traffic('conv256_pair', 'ncu_r02_summary.json') or ncu_traffic('conv256'),
+                              traffic_note='DRAM bytes of one conv_tc_kernel<256,64,STATS,CTA pair> launch (AlignNet 1024->1024 ch at 64 px, batch 16: 1.24 TFLOP, 0.29 GB of activations + weights algorithmic), profiles/ncu_r02_conv256_pair_raw.csv (round-1 single-CTA capture: ncu_r01_conv256_raw.csv)',
                               peak_source=pk['src'] + ', sustained figure (kernel timed inside a long step)',
                               share_of_step=conv['ms'] / prof_steps / max(step_ms, 1e-9), launches_per_step=conv['launches'] / prof_steps,
                               timing='CUDA events around every launch in an eager pass of the same step, same process'),

@@ -185,16 +185,17 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
     return d;
 }
 
-template <int BN, int BK, bool CTA2 = false>
+template <int BN, int BK, bool CTA2 = false, bool TP = false>      // TP: the STATS kernels of the pair form keep a [4 warps][32 px][36] fp32 transpose buffer
 struct TcCfg {
     static constexpr int kABytes = TBM * BK * 2;
     static constexpr int kBBytes = (CTA2 ? BN / 2 : BN) * BK * 2;          // CTA pairs: a CTA holds half of the N tile's weight rows (6 stages instead of 4 at BN = 256)
     static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kStages = (200 * 1024 / kStageBytes) > 8 ? 8 : (200 * 1024 / kStageBytes);
+    static constexpr int kTpBytes = TP ? 4 * 32 * 36 * 4 : 0;
+    static constexpr int kStages = ((200 * 1024 - kTpBytes) / kStageBytes) > 8 ? 8 : ((200 * 1024 - kTpBytes) / kStageBytes);
     static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
     static constexpr int kEpiVecs = 7;                       // bias, prelu, d, s_next, rgb_w[3]: BN floats each, double buffered
     static constexpr int kEpiBytes = 2 * kEpiVecs * BN * 4;
-    static constexpr int kStatBytes = 4 * BN * 2 * 4;        // STATS kernels: [epilogue warp][channel][sum, sum of squares]
+    static constexpr int kStatBytes = 4 * BN * 2 * 4 + kTpBytes;        // STATS kernels: [epilogue warp][channel][sum, sum of squares] (+ transpose buffer)
     static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kEpiBytes;
     static constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
 };
@@ -231,7 +232,7 @@ __device__ __forceinline__ TileCoord decode_tile(const TcParams &p, int tile, in
 template <int BN, int BK, bool SEED = false, bool STATS = false, int EPW = 4, bool CTA2 = false>
 __global__ void __launch_bounds__(64 + 32 * EPW, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
-    using Cfg = TcCfg<BN, BK, CTA2>;
+    using Cfg = TcCfg<BN, BK, CTA2, STATS && CTA2>;
     constexpr int S = Cfg::kStages;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -242,6 +243,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t *tmem_holder = reinterpret_cast<uint32_t *>(bars + 2 * S + 4);
     float *epi_vecs = reinterpret_cast<float *>(smem + S * Cfg::kStageBytes + 256);
     float *stat_red = epi_vecs + 2 * Cfg::kEpiVecs * BN;     // STATS kernels only (the launch adds kStatBytes)
+    float *stat_tp = stat_red + 4 * BN * 2;                  // STATS kernels of the pair form: per-warp transpose buffer
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kchunks = p.cin / BK;
@@ -526,7 +528,29 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                           pk2(v[16 * j + 12], v[16 * j + 13]), pk2(v[16 * j + 14], v[16 * j + 15]));
                     }
                 }
-                if constexpr (STATS) {
+                if constexpr (STATS && CTA2) {
+                    // moments of this warp's 32 pixels for the chunk's 32 channels, of the values as stored: transposed through shared memory
+                    // (lane = pixel writes its 32 channels, pitch 36 floats: conflict-free 16-byte stores and 4-byte column reads; lane =
+                    // channel then sums its column in pixel order).  A third of the instructions of the shuffle transpose below, which at
+                    // 256 channels / 256 px made the epilogue, not the MMAs, set the tile period (1061 vs 802 us for the plain kernel).
+                    float *tp = stat_tp + quad * (32 * 36);
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float2 a = !valid ? make_float2(0.f, 0.f) : of16 ? unpack_f16x2(pack_f16x2(v[j], v[j + 1])) : unpack_bf16x2(pack_bf16x2(v[j], v[j + 1]));
+                        const float2 c = !valid ? make_float2(0.f, 0.f) : of16 ? unpack_f16x2(pack_f16x2(v[j + 2], v[j + 3])) : unpack_bf16x2(pack_bf16x2(v[j + 2], v[j + 3]));
+                        *reinterpret_cast<float4 *>(tp + lane * 36 + j) = make_float4(a.x, a.y, c.x, c.y);
+                    }
+                    __syncwarp();
+                    float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
+#pragma unroll
+                    for (int pp = 0; pp < 32; pp += 2) {
+                        const float t0 = tp[pp * 36 + lane], t1 = tp[(pp + 1) * 36 + lane];
+                        s1a += t0; s1b += t1;
+                        s2a = fmaf(t0, t0, s2a); s2b = fmaf(t1, t1, s2b);
+                    }
+                    __syncwarp();
+                    *reinterpret_cast<float2 *>(stat_red + ((quad * BN) + ch * 32 + lane) * 2) = make_float2(s1a + s1b, p.ep.stat_sums_only ? 0.f : s2a + s2b);
+                } else if constexpr (STATS) {
                     // moments of this warp's 32 pixels for the chunk's 32 channels, of the values as stored (bf16 / f16): a
                     // transpose-reduce over the lanes (31 shuffles per moment) leaves channel `lane` in element 0
                     float q[32];
@@ -632,7 +656,7 @@ static int pow2_ceil(int v) { int r = 1; while (r < v) r <<= 1; return r; }
 
 template <int BN, int BK, bool SEED = false, bool STATS = false, int EPW = 4, bool CTA2 = false>
 static int launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, const TcParams &p, cudaStream_t st) {
-    using Cfg = TcCfg<BN, BK, CTA2>;
+    using Cfg = TcCfg<BN, BK, CTA2, STATS && CTA2>;
     static_assert(EPW == 4 || (EPW == 8 && !SEED && !STATS), "8 epilogue warps: plain kernels only");
     static_assert(!CTA2 || (EPW == 4 && BK == 64 && BN >= 128), "CTA pairs: wide tiles, four epilogue warps");
     auto kern = conv_tc_kernel<BN, BK, SEED, STATS, EPW, CTA2>;

@@ -15,6 +15,7 @@ cap() {   # name regex skip command...
 }
 B=16 cap rows32 'conv_rows_kernel<.int.32, .int.32' 4 python scripts/rows_bench.py
 B=16 cap rows64 'conv_rows_kernel<.int.64, .int.64' 4 python scripts/rows_bench.py
+cap conv256_pair 'conv_tc_kernel' 3 python scripts/modconv_ncu.py alignnet
 cap modconv_plain 'conv_tc_kernel' 3 python scripts/modconv_ncu.py plain
 cap modconv_up 'conv_tc_kernel' 9 python scripts/modconv_ncu.py transposed
 cap wgrad 'wgrad_tc_kernel' 3 python scripts/modconv_ncu.py wgrad
