@@ -29,7 +29,7 @@ _PRECISION = os.environ.get('OOD_B200_PRECISION', 'bf16')
 # up-sampling layers with at most this many output channels use the fused-phase transposed convolution (conv3x3 form 5): the
 # zero-padded weight blocks cost 1.8x the MACs, which only the HBM / per-tile-overhead bound small-channel layers can afford
 _FUSED_T_MAX_CO = int(os.environ.get('OOD_FUSED_T_MAX_CO', 64))
-_FUSE_RGB_ROWS = os.environ.get('OOD_FUSE_RGB_ROWS', '0') != '0'  # ToRGB in the row-sliding kernel's epilogue (512 / 1024 px layers): measured, OFF (see _synthesis)
+_FUSE_RGB_ROWS = int(os.environ.get('OOD_FUSE_RGB_ROWS', '0'))  # ToRGB in the row-sliding kernel's epilogue (512 / 1024 px layers): measured, OFF (see _synthesis)
 _FUSE_RGB_TC = os.environ.get('OOD_FUSE_RGB_TC', '1') != '0'    # ToRGB in the generic tiles' epilogue (128 / 256 channels); A/B switch
 _CONVT_ROWS = os.environ.get('OOD_CONVT_ROWS', '1') != '0'      # the row-streaming transposed kernel for the 64 -> 32 layer (csrc/convt_rows.cu)
 
@@ -622,8 +622,9 @@ class Generator(nn.Module):
             # 128/256 channels: the generic tiles' epilogue.  32/64 channels at 512 / 1024 px (the row-sliding kernel): NOT fused by default -- that
             # kernel is bound by its epilogue, and the per-thread dot products + skip taps cost it more than the separate ToRGB pass costs:
             # round 1 measured 0.9 -> 1.8 ms with the eight-warp epilogue; round 2 with the one-pixel-per-thread epilogue: conv time 14.0 -> 15.0 ms
-            # for 0.43 ms of ToRGB removed, 639.5 -> 625.6 images/s on the same box (OOD_FUSE_RGB_ROWS=1 repeats the experiment)
-            rows_ok = _FUSE_RGB_ROWS and co in (32, 64) and conv2.conv.cin_p == co and res % 128 == 0 and \
+            # for 0.43 ms of ToRGB removed, 639.5 -> 625.6 images/s on the same box (OOD_FUSE_RGB_ROWS=1 repeats the experiment; =2 fuses only the last
+            # layer, whose activation is then not written at all: conv +0.85 ms for 0.30 ms of ToRGB, 676-689 -> 661-669 images/s)
+            rows_ok = (_FUSE_RGB_ROWS == 1 or _FUSE_RGB_ROWS == 2 and last and not need_y) and co in (32, 64) and conv2.conv.cin_p == co and res % 128 == 0 and \
                 b * ((res + 31) // 32) * (res // 128) >= int(os.environ.get('OOD_ROWS_MIN_STRIPS', 148))
             fuse = _PRECISION == 'bf16' and (128 <= co <= 256 and _FUSE_RGB_TC or rows_ok) and co == conv2.conv.out_channel and len(to_rgb.taps_up) == 4 and res % 2 == 0
             if fuse:
