@@ -395,6 +395,42 @@ def parity_leg(net, state, x, dev, seed=123):
     return res
 
 
+def fp32_mode_leg(net, state, x, dev, batch=2, steps=2):
+    """The fp32 parity mode (SIMT FFMA convolutions, fp32 storage; `set_precision('fp32')`) as a product mode: images/s at a small batch
+    and its max-abs against the fp32 oracle (tolerance 1e-3).  Outside every timed region of the headline; eager launches."""
+    import torch
+    import ood_gan_inversion_b200.stylegan as sg
+    from oracle import ood as oood
+    tf = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    strict = net.strict_rng
+    xb = x[:batch].contiguous()
+    try:
+        sg.set_precision('fp32')
+        net.strict_rng = True
+        torch.manual_seed(7)
+        out, _ = net(xb)
+        torch.manual_seed(7)
+        ref, _, _ = oood.ood_forward(state, xb, size=SIZE, strict_rng=True)
+        err = float((out - ref).abs().max())
+        net.strict_rng = strict
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            net(xb)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        return dict(value=batch / (ms * 1e-3), unit=UNIT, batch=batch, steps=steps, ms_per_step=ms, max_abs_vs_oracle=err, tolerance=1e-3,
+                    ok=bool(err < 1e-3), note='parity mode: fp32 storage, SIMT FFMA convolutions (csrc/conv_simt.cu), PyTorch encoder modules; eager')
+    finally:
+        net.strict_rng = strict
+        sg.set_precision('bf16')
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf
+
+
 def main_config(world, batch, launch):
     """`config` of the JSON line (both arms print the same one): BASELINE configs[1]."""
     return dict(workload=WORKLOAD, batch_per_gpu=batch, global_batch=batch * world, size=SIZE, cycle_align=2, mod_size=256,
@@ -752,6 +788,7 @@ def main():
         state_dev = {k: v.detach() for k, v in net.state_dict().items()}
         for key, leg in (('parity', lambda: parity_leg(net, state_dev, x_dev, dev)),
                          ('gpu_reference', lambda: gpu_reference_leg(state_dev, dev)),
+                         ('fp32_mode', lambda: fp32_mode_leg(net, state_dev, x_dev, dev)),
                          ('config4', lambda: inversion_leg(dev))):
             try:
                 torch.cuda.empty_cache()
