@@ -333,6 +333,15 @@ int64_t ood_bwd_workspace(int batch, int64_t pixels, int channels, int k);
 int ood_act_bwd(const void *gy, const void *y, const float *d, const float *bias, const float *noise, int64_t noise_bstride,
                 const float *noise_w, void *g, float *workspace, float *gd, int batch, int64_t pixels, int channels, int dtype,
                 void *stream);
+/*      ood_act_bwd_fused: one pass per layer of the latent-gradient chain instead of torgb_bwd + act_bwd + dot_reduce:
+ *          gy = g_in * g_scale[b,c] + sum_k g_rgb[b,k,p] * wrgb[b,k,c];   g = gy * lrelu'(y) * sqrt2 * d
+ *          sums [B,C,K]: K = 2 {gd (as ood_act_bwd), sum_pix g_in*y} or, with g_rgb, K = 5 {.., sum_pix g_rgb_k * y, k = 0..2}
+ *      g_in: the UNSCALED data gradient written by the convolution of the layer above (out_y without s_next; NULL for the top layer),
+ *      g_scale [B,C]: that layer's input modulation (NULL = 1); g_rgb [B,3,P] fp32 / wrgb [B,3,C]: this level's ToRGB gradient (or NULL).
+ *      workspace: ood_bwd_workspace(batch, pixels, channels, K) bytes.  Deterministic two-stage reductions. */
+int ood_act_bwd_fused(const void *g_in, const float *g_scale, const float *g_rgb, const float *wrgb, const void *y, const float *d,
+                      const float *bias, const float *noise, int64_t noise_bstride, const float *noise_w, void *g, float *workspace,
+                      float *sums, int batch, int64_t pixels, int channels, int dtype, void *stream);
 int ood_dot_reduce(const void *a, const void *b, float *workspace, float *out, int batch, int64_t pixels, int channels,
                    int dtype, void *stream);
 int ood_torgb_bwd(const float *g_rgb, const float *wrgb, const void *y, const void *g_in, void *g_out, float *workspace,

@@ -66,6 +66,7 @@ _SIGS = {
                         c_int, c_int, c_int, c_void_p], c_int),
     'ood_se_tail': ([c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p] + [c_int] * 7 + [c_void_p], c_int),
     'ood_se_apply': ([c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p] + [c_int] * 7 + [c_void_p], c_int),
+    'ood_act_bwd_fused': ([c_void_p] * 8 + [c_i64, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_i64, c_int, c_int, c_void_p], c_int),
     'ood_latent_assemble': ([c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p], c_int),
     'ood_alignnet_head_weights': ([c_void_p] * 7 + [c_int, c_int, c_int, c_void_p], c_int),
     'ood_bicubic_up_add': ([c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p], c_int),

@@ -113,6 +113,145 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const T *__restrict__ gy, 
     block_reduce_store<N>(acc, 1, red, partial + (((int64_t)b * nchunks + chunk) * C), C, cv, lanes, lane, vec, active);
 }
 
+// ---- one pass per layer of the latent-gradient chain: the ToRGB data gradient, the activation backward
+// and the three pixel reductions that the separate kernels above computed in four passes (torgb_bwd_y, torgb_wgrad, act_bwd, dot_reduce):
+//     gy    = g_in * g_scale[b,c]  +  sum_k g_rgb[b,k,p] * wrgb[b,k,c]      g_in = the UNSCALED data gradient of the layer above (dL/d(s*y))
+//     g     = gy * gate * d                                                  (input of this layer's data-gradient convolution)
+//     sums[b,c] = { sum gv*acc (gd numerator), sum g_in * y (the style gradient of the layer above), sum g_rgb_k * y (k = 0..2) }
+// g_in and y are read once, gy is never written, the convolution above writes one tensor (unscaled) instead of two.
+template <typename T> __device__ __forceinline__ void bw_unpack(const uint4 &r, float2 *dst);
+template <> __device__ __forceinline__ void bw_unpack<float>(const uint4 &r, float2 *dst) {
+    dst[0] = make_float2(__uint_as_float(r.x), __uint_as_float(r.y)); dst[1] = make_float2(__uint_as_float(r.z), __uint_as_float(r.w));
+}
+template <> __device__ __forceinline__ void bw_unpack<__nv_bfloat16>(const uint4 &r, float2 *dst) {
+    dst[0] = unpack_bf16x2(r.x); dst[1] = unpack_bf16x2(r.y); dst[2] = unpack_bf16x2(r.z); dst[3] = unpack_bf16x2(r.w);
+}
+
+// a shared-memory read the compiler may not hoist out of the pixel loop (the point of keeping a coefficient there is NOT to hold it in a register)
+__device__ __forceinline__ float2 lds_f2(const float *p) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+    return v;
+}
+
+// MODE 0: one pixel per trip; 1: two pixels per trip; 2: two pixels per trip, d and -bias read from shared memory in the loop (register relief)
+template <typename T, bool RGB, int MODE>
+__global__ void __launch_bounds__(256, 2) act_bwd_fused_kernel(const T *__restrict__ g_in, const float *__restrict__ g_scale, const float *__restrict__ g_rgb,
+                                                                const float *__restrict__ wrgb, const T *__restrict__ y, const float *__restrict__ d,
+                                                                const float *__restrict__ bias, const float *__restrict__ noise, int64_t noise_bstride,
+                                                                const float *__restrict__ noise_w, T *__restrict__ g, float *__restrict__ partial, int64_t P,
+                                                                int C, int nchunks, int chunk_px) {
+    constexpr int N = Vec<T>::N, N2 = N / 2, K = RGB ? 5 : 2;
+    extern __shared__ float red[];
+    const int cv = C / N, lanes = 256 / cv;
+    const int vec = threadIdx.x % cv, lane = threadIdx.x / cv;
+    const bool active = lane < lanes;
+    const int b = blockIdx.y, chunk = blockIdx.x, c = vec * N;
+    const float nw = (noise && noise_w) ? *noise_w : 0.f;
+    // the three colour rows of this image's ToRGB weights live in shared memory during the pixel loop (the reduction buffer is free until
+    // the loop ends): 24 registers less per thread, which is what keeps two blocks resident per SM.  (Measured and not kept: ALL coefficients
+    // in shared memory behind non-hoistable loads plus a two-slot register ring of raw loads -- 6.6 -> 8.4 ms per step for the 17 launches.)
+    float *cw = red, *cd = red + 3 * C, *cnb = red + 4 * C;
+    if (RGB || MODE == 2) {
+        if (RGB)
+            for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) cw[i] = wrgb[(int64_t)b * 3 * C + i];
+        if (MODE == 2)
+            for (int i = threadIdx.x; i < C; i += blockDim.x) { cd[i] = d ? d[(int64_t)b * C + i] : 1.f; cnb[i] = bias ? -bias[i] : 0.f; }
+        __syncthreads();
+    }
+    float acc[K][N];
+    float2 a_gd[N2], a_dot[N2], a_w[RGB ? 3 : 1][N2], d2[N2], nb2[N2], sc2[N2];
+#pragma unroll
+    for (int j = 0; j < N2; ++j) {
+        a_gd[j] = a_dot[j] = f2(0.f);
+        d2[j] = (MODE != 2 && active && d) ? make_float2(d[(int64_t)b * C + c + 2 * j], d[(int64_t)b * C + c + 2 * j + 1]) : f2(1.f);
+        nb2[j] = (MODE != 2 && active && bias) ? make_float2(-bias[c + 2 * j], -bias[c + 2 * j + 1]) : f2(0.f);
+        sc2[j] = (active && g_scale) ? make_float2(g_scale[(int64_t)b * C + c + 2 * j], g_scale[(int64_t)b * C + c + 2 * j + 1]) : f2(1.f);
+#pragma unroll
+        for (int k = 0; k < (RGB ? 3 : 1); ++k) a_w[k][j] = f2(0.f);
+    }
+    if (active) {
+        const int64_t p0 = (int64_t)chunk * chunk_px, p1 = min(p0 + chunk_px, P);
+        const int64_t stride = (int64_t)lanes * C;
+        const int64_t base = ((int64_t)b * P + p0 + lane) * C + c;
+        const T *gp = g_in ? g_in + base : nullptr, *yp = y + base;
+        T *op = g + base;
+        const float *np = noise ? noise + b * noise_bstride + p0 + lane : nullptr;
+        const float *rp = RGB ? g_rgb + (int64_t)b * 3 * P + p0 + lane : nullptr;
+        constexpr float kGp = kSqrt2, kGn = 0.2f * kSqrt2, kIp = 1.f / kSqrt2, kIn = 1.f / (0.2f * kSqrt2);
+        // two pixels per trip: all loads of both are issued before the first is processed (the compiler's own unrolling put the second
+        // pixel's loads behind the first one's store: one 44-byte request per thread in flight, 0.55 of the HBM peak at 16 warps per SM)
+        struct Raw { uint4 g, y; float r0, r1, r2, nz; };
+        auto fetch = [&](int64_t p, int k, Raw &q) {
+            if (p >= p1) return;
+            q.g = gp ? __ldg(reinterpret_cast<const uint4 *>(gp + k * stride)) : make_uint4(0u, 0u, 0u, 0u);
+            q.y = __ldg(reinterpret_cast<const uint4 *>(yp + k * stride));
+            q.nz = np ? __ldg(np + k * lanes) : 0.f;
+            if (RGB) { q.r0 = __ldg(rp + k * lanes); q.r1 = __ldg(rp + k * lanes + P); q.r2 = __ldg(rp + k * lanes + 2 * P); }
+        };
+        auto process = [&](const Raw &q, T *dst) {
+            float2 gv[N2], yv[N2], o[N2];
+            bw_unpack<T>(q.g, gv);
+            bw_unpack<T>(q.y, yv);
+            const float2 nz = f2(-nw * q.nz);
+            const float2 r0 = f2(q.r0), r1 = f2(q.r1), r2 = f2(q.r2);
+#pragma unroll
+            for (int j = 0; j < N2; ++j) {
+                a_dot[j] = fma2(gv[j], yv[j], a_dot[j]);
+                float2 gy = mul2(gv[j], sc2[j]);
+                if (RGB) {
+                    const float2 w0 = lds_f2(cw + c + 2 * j), w1 = lds_f2(cw + C + c + 2 * j), w2 = lds_f2(cw + 2 * C + c + 2 * j);
+                    gy = fma2(r0, w0, fma2(r1, w1, fma2(r2, w2, gy)));
+                    a_w[0][j] = fma2(r0, yv[j], a_w[0][j]);
+                    a_w[1][j] = fma2(r1, yv[j], a_w[1][j]);
+                    a_w[2][j] = fma2(r2, yv[j], a_w[2][j]);
+                }
+                const bool px = yv[j].x > 0.f, py = yv[j].y > 0.f;
+                const float2 gate = make_float2(px ? kGp : kGn, py ? kGp : kGn), inv = make_float2(px ? kIp : kIn, py ? kIp : kIn);
+                const float2 gvv = mul2(gy, gate);
+                const float2 v = fma2(yv[j], inv, add2(nz, MODE == 2 ? lds_f2(cnb + c + 2 * j) : nb2[j]));       // v - nz*nw - bias = acc * d
+                a_gd[j] = fma2(gvv, v, a_gd[j]);
+                o[j] = mul2(gvv, MODE == 2 ? lds_f2(cd + c + 2 * j) : d2[j]);
+            }
+            bw_store<T>(dst, o);
+        };
+        if (MODE == 0) {
+            for (int64_t p = p0 + lane; p < p1; p += lanes) {
+                Raw qa = {};
+                fetch(p, 0, qa);
+                process(qa, op);
+                if (gp) gp += stride;
+                yp += stride; op += stride;
+                if (np) np += lanes;
+                if (RGB) rp += lanes;
+            }
+        } else {
+            for (int64_t p = p0 + lane; p < p1; p += 2 * lanes) {
+                Raw qa = {}, qb = {};
+                fetch(p, 0, qa);
+                fetch(p + lanes, 1, qb);
+                process(qa, op);
+                if (p + lanes < p1) process(qb, op + stride);
+                if (gp) gp += 2 * stride;
+                yp += 2 * stride; op += 2 * stride;
+                if (np) np += 2 * lanes;
+                if (RGB) rp += 2 * lanes;
+            }
+        }
+    }
+    if (RGB || MODE == 2) __syncthreads();          // every thread is done with the coefficients in `red`
+#pragma unroll
+    for (int j = 0; j < N2; ++j) {
+        acc[0][2 * j] = a_gd[j].x; acc[0][2 * j + 1] = a_gd[j].y;
+        acc[1][2 * j] = a_dot[j].x; acc[1][2 * j + 1] = a_dot[j].y;
+        if (RGB) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { acc[(RGB ? 2 : 0) + k][2 * j] = a_w[k][j].x; acc[(RGB ? 2 : 0) + k][2 * j + 1] = a_w[k][j].y; }
+        }
+    }
+    block_reduce_store<N>(acc, K, red, partial + (((int64_t)b * nchunks + chunk) * C) * K, C, cv, lanes, lane, vec, active);
+}
+
 // ---- sum_pix a*b per (b,c)
 template <typename T>
 __global__ void __launch_bounds__(256) dot_partial_kernel(const T *__restrict__ a, const T *__restrict__ bb,
@@ -149,14 +288,14 @@ __global__ void __launch_bounds__(256) dot_partial_kernel(const T *__restrict__ 
 
 // out[b,c,k] = sum_chunks partial[b][chunk][c*K+k] * (div ? 1/div[b,c] : 1)
 __global__ void reduce_partials_kernel(const float *__restrict__ partial, const float *__restrict__ div, float *__restrict__ out,
-                                       int C, int K, int nchunks, int64_t total) {
+                                       int C, int K, int nchunks, int64_t total, int div_first_only = 0) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;    // b*C*K + c*K + k
     if (i >= total) return;
     const int64_t b = i / ((int64_t)C * K);
     const int64_t r = i % ((int64_t)C * K);
     double s = 0;
     for (int k = 0; k < nchunks; ++k) s += partial[((b * nchunks + k) * C) * K + r];
-    if (div) s /= div[b * C + r / K];
+    if (div && (!div_first_only || r % K == 0)) s /= div[b * C + r / K];
     out[i] = (float)s;
 }
 
@@ -304,4 +443,40 @@ extern "C" int ood_torgb_bwd(const float *g_rgb, const float *wrgb, const void *
     const int64_t total = (int64_t)batch * channels * 3;
     reduce_partials_kernel<<<ceil_div(total, 256), 256, 0, s>>>(workspace, nullptr, g_wrgb, channels, 3, nch, total);
     return check_launch("torgb_bwd", 3);
+}
+
+extern "C" int ood_act_bwd_fused(const void *g_in, const float *g_scale, const float *g_rgb, const float *wrgb, const void *y, const float *d,
+                                 const float *bias, const float *noise, int64_t noise_bstride, const float *noise_w, void *g, float *workspace,
+                                 float *sums, int batch, int64_t pixels, int channels, int dtype, void *stream) {
+    using namespace ood;
+    OOD_REQUIRE(y && g && workspace && sums && batch > 0 && batch <= 65535 && pixels > 0, "act_bwd_fused: bad arguments");
+    OOD_REQUIRE(g_in || g_rgb, "act_bwd_fused: no incoming gradient (g_in and g_rgb are both NULL)");
+    OOD_REQUIRE(!g_rgb || wrgb, "act_bwd_fused: g_rgb needs wrgb");
+    OOD_REQUIRE(dtype == OOD_F32 || dtype == OOD_BF16, "act_bwd_fused: bad dtype");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int nch = bwd_chunks(pixels, batch), cpx = bwd_chunk_px(pixels, batch);
+    dim3 grid(nch, batch);
+    const int N = dtype == OOD_F32 ? 4 : 8, K = g_rgb ? 5 : 2;
+    if (int rc = (dtype == OOD_F32 ? check_vec<float>("act_bwd_fused", channels) : check_vec<__nv_bfloat16>("act_bwd_fused", channels))) return rc;
+    const size_t smem = std::max((size_t)(256 / (channels / N)) * channels * K, (size_t)5 * channels) * sizeof(float);
+    // the bf16 ToRGB variant is the one short of registers: OOD_ABF_MODE picks its loop form (0 / 1 / 2, see the kernel; measured per Adam step at batch 32:
+    // 6.65 / 7.56 / 7.38 ms for the 17 launches -- the two-pixel forms spill); the others run two pixels per trip
+    int mode = 0;
+    if (const char *e = getenv("OOD_ABF_MODE")) mode = atoi(e);
+#define OOD_ABF(T, RGB, MODE)                                                                                                               \
+    do {                                                                                                                                    \
+        auto kern = act_bwd_fused_kernel<T, RGB, MODE>;                                                                                     \
+        if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                           \
+        kern<<<grid, 256, smem, s>>>((const T *)g_in, g_scale, g_rgb, wrgb, (const T *)y, d, bias, noise, noise_bstride, noise_w, (T *)g, workspace, \
+                                     pixels, channels, nch, cpx);                                                                           \
+    } while (0)
+    if (dtype == OOD_F32) { if (g_rgb) OOD_ABF(float, true, 1); else OOD_ABF(float, false, 1); }
+    else if (!g_rgb) OOD_ABF(__nv_bfloat16, false, 1);
+    else if (mode == 0) OOD_ABF(__nv_bfloat16, true, 0);
+    else if (mode == 1) OOD_ABF(__nv_bfloat16, true, 1);
+    else OOD_ABF(__nv_bfloat16, true, 2);
+#undef OOD_ABF
+    const int64_t total = (int64_t)batch * channels * K;
+    reduce_partials_kernel<<<ceil_div(total, 256), 256, 0, s>>>(workspace, d, sums, channels, K, nch, total, 1);
+    return check_launch("act_bwd_fused", 2);
 }

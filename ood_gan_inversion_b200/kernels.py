@@ -506,6 +506,29 @@ def act_bwd(gy, y, d, bias, noise, noise_w):
     return g, gd
 
 
+def act_bwd_fused(g_in, g_scale, rgb, y, d, bias, noise, noise_w):
+    """One pass per layer of the latent-gradient chain (ood_act_bwd_fused): gy = g_in * g_scale + ToRGB gradient, then act_bwd.
+    g_in NHWC (unscaled data gradient of the layer above) or None; g_scale [B,C] or None; rgb = (g_rgb [B,3,H,W] fp32, wrgb [B,3,C]) or None.
+    Returns (g NHWC, gd [B,C], dot [B,C] = sum_pix g_in*y, g_wrgb [B,3,C] or None)."""
+    g_rgb, wrgb = rgb if rgb is not None else (None, None)
+    _cuda(g_in, g_scale, g_rgb, wrgb, y, d, bias, noise, noise_w)
+    assert y.is_contiguous() and (g_in is None or (g_in.is_contiguous() and g_in.dtype == y.dtype and g_in.shape == y.shape))
+    assert g_in is not None or g_rgb is not None
+    b, h, w, c = y.shape
+    g_rgb, wrgb, g_scale = _f32c(g_rgb), _f32c(wrgb), _f32c(g_scale)
+    if g_rgb is not None:
+        assert g_rgb.shape == (b, 3, h, w) and wrgb.shape == (b, 3, c)
+    k = 5 if g_rgb is not None else 2
+    g = torch.empty_like(y)
+    sums = torch.empty(b, c, k, device=y.device, dtype=torch.float32)
+    nbs = _noise_bstride(noise, b, h, w)
+    ws = _bwd_ws(b, h * w, c, k, y.device)
+    with _timed('act_bwd_fused', b * h * w * (c * _esize(y) * (3 if g_in is not None else 2) + (12 if g_rgb is not None else 0))):
+        check(_lib.lib().ood_act_bwd_fused(_ptr(g_in), _ptr(g_scale), _ptr(g_rgb), _ptr(wrgb), _ptr(y), _ptr(d), _ptr(bias), _ptr(noise), nbs,
+                                           _ptr(noise_w), _ptr(g), _ptr(ws), _ptr(sums), b, h * w, c, _dt(y), _stream()), 'act_bwd_fused')
+    return g, sums[..., 0], sums[..., 1], (sums[..., 2:5].permute(0, 2, 1) if k == 5 else None)
+
+
 def dot_reduce(a, x):
     """sum over pixels of a*x per (b, c): NHWC, NHWC -> [B,C] fp32"""
     _cuda(a, x)

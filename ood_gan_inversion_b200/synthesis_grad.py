@@ -8,10 +8,14 @@ kernel, transposed / flipped weights; the stride-2 transposed conv's gradient is
 reductions for the style and demodulation gradients -- no weight-gradient GEMM, no saved
 per-sample weights, activations saved once in the storage type.
 """
+import os
+
 import torch
 
 from . import kernels as K
 from . import stylegan as sg
+
+_FUSED_BWD = os.environ.get('OOD_FUSED_BWD', '1') != '0'      # A/B switch: one fused pass per layer (ood_act_bwd_fused) vs torgb_bwd + act_bwd + dot_reduce
 
 
 def _bwd_weights(conv):
@@ -121,6 +125,55 @@ class SynthesisFn(torch.autograd.Function):
             gs = (g_wrgb * wp.unsqueeze(0)).sum(1) * tr.conv.scale
             add_style_grad(1 if r == 0 else 1 + 2 * r, gs, tr.conv)
             return gy
+
+        if _FUSED_BWD:
+            # One streaming pass per layer (ood_act_bwd_fused) instead of torgb_bwd (2 kernels) + act_bwd + dot_reduce: the data-gradient
+            # convolution of layer j writes ONE tensor, the unscaled dL/d(s*x); the pass of the layer below applies s on load, adds the ToRGB
+            # gradient of its level, gates, and returns the three reductions -- among them sum_pix gxs_j * x_j, layer j's style gradient,
+            # because x_j IS the saved output of the layer below.  10 -> 4 tensor passes per ToRGB layer, 7 -> 4 for the others.
+            def layer_bwd(j, g_in, g_scale, rgb, pending):
+                m = layers[j]
+                conv = m.conv
+                s, d = S['sd'][j]
+                nw = m.noise.weight.detach().float()
+                bias = m.activate.bias.detach().float().contiguous()
+                g_pre, gd, dot, g_w = K.act_bwd_fused(g_in, g_scale, rgb, S['y'][j], d, bias, S['noise'][j], nw)
+                if pending is not None:                                   # the layer above: its input was this layer's output
+                    finish_style(pending, dot)
+                wd = _bwd_weights(conv)
+                if conv.upsample:
+                    g_t, _, _ = K.blur_act(g_pre, list(reversed(conv.blur.taps)), act=False, want_img=True, pad=(2, 2))
+                    gxs, _ = K.conv3x3(g_t, wd, conv.cin_p, transposed=2, impl=impl, want_y=True, want_ys=False)
+                else:
+                    gxs, _ = K.conv3x3(g_pre, wd, conv.cin_p, impl=impl, want_y=True, want_ys=False)
+                return gxs, g_w, (j, s, d, gd)
+
+            def finish_style(pending, dot):
+                j, s, d, gd = pending
+                conv = layers[j].conv
+                _, wsq, _, _ = conv.packed()
+                add_style_grad(j, dot - s * ((gd * d.pow(3)) @ wsq), conv)
+
+            def rgb_style(r, g_w):
+                tr = rgbs[r]
+                wp, _, _, _ = tr.conv.packed()                                # [3, Ci_p]
+                add_style_grad(1 if r == 0 else 1 + 2 * r, (g_w * wp.unsqueeze(0)).sum(1) * tr.conv.scale, tr.conv)
+
+            g_skip = g_image.detach().float().contiguous()
+            gxs, pending = None, None
+            for blk in reversed(range(n_blocks)):
+                j1, j2 = 1 + 2 * blk, 2 + 2 * blk
+                tr = rgbs[1 + blk]
+                gxs, g_w, pending = layer_bwd(j2, gxs, None if pending is None else pending[1], (g_skip, S['wrgb'][1 + blk]), pending)
+                rgb_style(1 + blk, g_w)
+                k2 = tr.upsample.kernel.detach().float()
+                g_skip = K.upfirdn2d_nchw(g_skip, torch.flip(k2, [0, 1]), 1, 1, 2, 2, 1, 1, 1, 1)     # adjoint of up=2, pad (2,1)
+                gxs, _, pending = layer_bwd(j1, gxs, pending[1], None, pending)
+            gxs, g_w, pending = layer_bwd(0, gxs, None if pending is None else pending[1], (g_skip, S['wrgb'][0]), pending)
+            rgb_style(0, g_w)
+            finish_style(pending, K.dot_reduce(gxs, S['x_const']))           # the constant input has no layer below it
+            ctx.saved = None
+            return g_lat.to(ctx.lat_dtype), None, None
 
         g_skip = g_image.detach().float().contiguous()
         gy_next = None

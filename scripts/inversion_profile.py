@@ -1,48 +1,48 @@
-"""Per-kernel timing of one Adam step of BASELINE config 4 (W+ inversion, 1024 px, batch 32, bf16)."""
-import os
-import sys
-
-import torch
-import torch.nn.functional as F
-
+"""Per-launch timing of one Adam step of W+ inversion (BASELINE configs[3]: 1024 px, batch 32, bf16) with the convolutions tagged by shape."""
+import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from ood_gan_inversion_b200 import kernels as K, stylegan as sg  # noqa: E402
-from ood_gan_inversion_b200.synth import synthetic_faces, synthetic_init  # noqa: E402
-
-batch = int(sys.argv[1]) if len(sys.argv) > 1 else 32
+import torch
+from ood_gan_inversion_b200 import kernels as K, stylegan as sg
+from ood_gan_inversion_b200.inversion import LatentInverter, generator_synthesizer
+from ood_gan_inversion_b200.synth import synthetic_faces, synthetic_init
+import ood_gan_inversion_b200.synthesis_grad as SG
 sg.set_precision('bf16')
-gen = synthetic_init(sg.Generator(1024, 512, 8), seed=0).cuda()
+B = int(os.environ.get('B', 32))
+dev = 'cuda'
+orig = K.conv3x3
+
+
+def tagged(x, weight, cout, transposed=False, **kw):
+    base = kw.get('tag') or 'conv'
+    kw['tag'] = f'{base} ci{x.shape[3]} co{cout} {x.shape[1]}px form{int(transposed)}' + ('+ys' if kw.get('want_ys') else '') + ('+f32' if kw.get('out_f32') else '')
+    return orig(x, weight, cout, transposed=transposed, **kw)
+
+
+K.conv3x3 = tagged
+for m in (sg, SG):
+    if hasattr(m, 'K'):
+        m.K.conv3x3 = tagged
+torch.manual_seed(0)
+gen = synthetic_init(sg.Generator(1024, 512, 8), seed=0).to(dev)
 for p in gen.parameters():
     p.requires_grad_(False)
-target = synthetic_faces(batch, 1024, seed=3, device='cuda')
-lat = torch.zeros(batch, 18, 512, device='cuda', requires_grad=True)
-opt = torch.optim.Adam([lat], lr=0.01)
-
-
-def step():
-    opt.zero_grad(set_to_none=True)
-    img, _ = gen(lat, input_is_tensor=True, input_is_latent=True, randomize_noise=False)
-    loss = F.mse_loss(img, target)
-    loss.backward()
-    opt.step()
-
-
-for _ in range(3):
-    step()
+target = synthetic_faces(B, 1024, seed=3, device=dev)
+lat0 = torch.zeros(B, 18, 512, device=dev)
+inv = LatentInverter(generator_synthesizer(gen), lr=0.01)
+inv.run(target, lat0, 2)
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
-for _ in range(5):
-    step()
+inv.run(target, lat0, 3)
 e1.record()
 torch.cuda.synchronize()
-print('ms per step (no per-launch events):', e0.elapsed_time(e1) / 5)
+print(f'{e0.elapsed_time(e1) / 3:.2f} ms per Adam step (batch {B})')
 K.profile_begin()
-step()
+inv.run(target, lat0, 1)
 torch.cuda.synchronize()
 prof = K.profile_end()
-tot = 0
-for name, v in sorted(prof.items(), key=lambda kv: -kv[1]['ms']):
-    tot += v['ms']
-    print(f"{v['ms']:8.3f} ms {v['launches']:4d}x  {v['work'] / v['ms'] / 1e9 if v['ms'] else 0:9.1f} G/s  {name}")
-print('sum of library kernels', tot)
+tot = sum(v['ms'] for v in prof.values())
+print(f'sum of library kernel times {tot:.3f} ms')
+for name, v in sorted(prof.items(), key=lambda kv: -kv[1]['ms'])[:45]:
+    rate = v['work'] / v['ms'] / 1e9 if v['ms'] > 0 else 0
+    print(f"{v['ms']:8.3f} ms {100 * v['ms'] / tot:5.1f}% {v['launches']:4d}x {rate:10.1f} {'TFLOP/s' if 'conv' in name else 'GB/s'}  {name}")

@@ -92,6 +92,53 @@ def test_act_bwd_dot_torgb_bwd_vs_autograd():
     torch.testing.assert_close(gw_k.cpu(), gw_ref, rtol=1e-4, atol=1e-3)
 
 
+@pytest.mark.parametrize('dt', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('case', [dict(b=2, c=32, h=19, w=23, rgb=True, gin=True), dict(b=3, c=64, h=16, w=16, rgb=False, gin=True),
+                                  dict(b=2, c=512, h=8, w=8, rgb=True, gin=False), dict(b=1, c=128, h=33, w=9, rgb=True, gin=True)])
+def test_act_bwd_fused_equals_the_separate_kernels(case, dt):
+    """ood_act_bwd_fused (one pass: scale of the incoming unscaled gradient + ToRGB data gradient + activation backward + the gd / style /
+    ToRGB-weight reductions) against torgb_bwd -> act_bwd -> dot_reduce and against autograd (model.py:277-292, 353-372)."""
+    b, c, h, w = (case[k] for k in ('b', 'c', 'h', 'w'))
+    acc = rnd(b, c, h, w, seed=1).requires_grad_(True)
+    d = (0.5 + rnd(b, c, seed=2).abs()).requires_grad_(True)
+    bias, noise, nw = rnd(c, seed=3), rnd(b, 1, h, w, seed=4), torch.tensor([0.3])
+    y = oops.fused_leaky_relu(acc * d[:, :, None, None] + nw * noise, bias)
+    yq = y.detach().to(dt).float()                                   # the saved activation in the storage type
+    g_in = rnd(b, c, h, w, seed=5).to(dt).float() if case['gin'] else None
+    s_up = 0.5 + rnd(b, c, seed=6).abs()
+    g_rgb, wrgb = (rnd(b, 3, h, w, seed=7), rnd(b, 3, c, seed=8)) if case['rgb'] else (None, None)
+    gy = torch.zeros(b, c, h, w)
+    if g_in is not None:
+        gy = gy + g_in * s_up[:, :, None, None]
+    if g_rgb is not None:
+        gy = gy + torch.einsum('bkhw,bkc->bchw', g_rgb, wrgb)
+    to = lambda t: None if t is None else t.to(DEV)
+    g, gd, dot, gw = K().act_bwd_fused(None if g_in is None else nhwc(g_in).to(dt), to(s_up) if g_in is not None else None,
+                                       None if g_rgb is None else (to(g_rgb), to(wrgb)), nhwc(yq).to(dt), d.detach().to(DEV), to(bias), to(noise), to(nw))
+    # reference: the same formulas on the stored y (gate on its sign, pre-activation re-derived from it)
+    gate = torch.where(yq > 0, torch.tensor(2 ** 0.5), torch.tensor(0.2 * 2 ** 0.5))
+    gv = gy * gate
+    v = yq / gate - nw * noise - bias[None, :, None, None]
+    tol = dict(rtol=1e-4, atol=1e-4) if dt == torch.float32 else dict(rtol=2e-2, atol=2e-2)
+    torch.testing.assert_close(nchw(g), gv * d.detach()[:, :, None, None], **tol)
+    red = dict(rtol=1e-3, atol=1e-3 * h * w ** 0.5)
+    torch.testing.assert_close(gd.cpu(), (gv * v).sum((2, 3)) / d.detach(), **red)
+    torch.testing.assert_close(dot.cpu(), (g_in * yq).sum((2, 3)) if g_in is not None else torch.zeros(b, c), **red)
+    if g_rgb is not None:
+        torch.testing.assert_close(gw.cpu(), torch.einsum('bkhw,bchw->bkc', g_rgb, yq), **red)
+    else:
+        assert gw is None
+    if dt == torch.float32 and g_in is not None and g_rgb is not None:        # and the chain of separate kernels, fp32: same numbers
+        gy_k, gw_k = K().torgb_bwd(to(g_rgb), to(wrgb), nhwc(yq), nhwc(g_in * s_up[:, :, None, None]))
+        g_k, gd_k = K().act_bwd(gy_k, nhwc(yq), d.detach().to(DEV), to(bias), to(noise), to(nw))
+        torch.testing.assert_close(g, g_k, rtol=1e-5, atol=1e-5)
+        torch.testing.assert_close(gd, gd_k, rtol=1e-4, atol=1e-4)
+        torch.testing.assert_close(gw, gw_k, rtol=1e-4, atol=1e-4)
+        torch.testing.assert_close(dot, K().dot_reduce(nhwc(g_in), nhwc(yq)), rtol=1e-5, atol=1e-4)
+    assert torch.equal(g, K().act_bwd_fused(None if g_in is None else nhwc(g_in).to(dt), to(s_up) if g_in is not None else None,
+                                            None if g_rgb is None else (to(g_rgb), to(wrgb)), nhwc(yq).to(dt), d.detach().to(DEV), to(bias), to(noise), to(nw))[0])
+
+
 def _latent_grad_case(size, batch, precision):
     import ood_gan_inversion_b200.stylegan as sg
     sg.set_precision(precision)
