@@ -24,6 +24,8 @@ python scripts/kernel_sweep.py --out gpurun_out/sweep_r02.json > gpurun_out/swee
 python scripts/rows_bench.py > gpurun_out/rows_bench_r02.txt 2>&1
 python scripts/convT_bench.py >> gpurun_out/rows_bench_r02.txt 2>&1
 python scripts/step_profile.py > gpurun_out/step_profile_r02.txt 2>&1
+python scripts/inversion_profile.py > gpurun_out/inversion_profile_r02.txt 2>&1
+python scripts/se_bench.py > gpurun_out/se_bench_r02.txt 2>&1
 tail -3 gpurun_out/bench_r02_default_run.err
 cut -c1-400 gpurun_out/bench_r02_default_run.json
 ls -la gpurun_out | tail -30

@@ -52,7 +52,7 @@ with open(os.path.join(P, 'launches_r02_summary.csv'), 'w') as f:
     for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         f.write(f'{v[0]},{v[1] / 1e6:.4f},{v[1] / tot:.4f},"{k}"\n')
 shutil.copy(os.path.join(G, 'launches_r02.csv'), os.path.join(P, 'launches_r02.csv'))
-for name in ('bench_r02_default_run.json', 'sweep_r02.json', 'rows_bench_r02.txt', 'step_profile_r02.txt', 'ncu_r02_rows32.ncu-rep', 'ncu_r02_convt_rows.ncu-rep'):
+for name in ('bench_r02_default_run.json', 'sweep_r02.json', 'rows_bench_r02.txt', 'step_profile_r02.txt', 'inversion_profile_r02.txt', 'se_bench_r02.txt', 'ncu_r02_rows32.ncu-rep', 'ncu_r02_convt_rows.ncu-rep'):
     if os.path.exists(os.path.join(G, name)):
         shutil.copy(os.path.join(G, name), os.path.join(P, name))
 print(open(os.path.join(P, 'launches_r02_summary.csv')).read()[:1500])
