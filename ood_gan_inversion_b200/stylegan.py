@@ -623,7 +623,9 @@ class Generator(nn.Module):
             # kernel is bound by its epilogue, and the per-thread dot products + skip taps cost it more than the separate ToRGB pass costs:
             # round 1 measured 0.9 -> 1.8 ms with the eight-warp epilogue; round 2 with the one-pixel-per-thread epilogue: conv time 14.0 -> 15.0 ms
             # for 0.43 ms of ToRGB removed, 639.5 -> 625.6 images/s on the same box (OOD_FUSE_RGB_ROWS=1 repeats the experiment; =2 fuses only the last
-            # layer, whose activation is then not written at all: conv +0.85 ms for 0.30 ms of ToRGB, 676-689 -> 661-669 images/s)
+            # layer, whose activation is then not written at all: conv +0.85 ms for 0.30 ms of ToRGB, 676-689 -> 661-669 images/s; ncu source page of
+            # that kernel (RGB=1 scripts/rows_bench.py: 1293 us against 474 + 290 us separately): 29 % of the stall samples sit on the first use of the
+            # up-sampled skip taps, requesting them a row ahead did not move it -- the compiler keeps the dependent FMAs next to the loads)
             rows_ok = (_FUSE_RGB_ROWS == 1 or _FUSE_RGB_ROWS == 2 and last and not need_y) and co in (32, 64) and conv2.conv.cin_p == co and res % 128 == 0 and \
                 b * ((res + 31) // 32) * (res // 128) >= int(os.environ.get('OOD_ROWS_MIN_STRIPS', 148))
             fuse = _PRECISION == 'bf16' and (128 <= co <= 256 and _FUSE_RGB_TC or rows_ok) and co == conv2.conv.out_channel and len(to_rgb.taps_up) == 4 and res % 2 == 0

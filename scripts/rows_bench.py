@@ -30,6 +30,11 @@ for ci, co, r, ys in [(32, 32, 1024, False), (64, 64, 512, True), (64, 32, 1024,
     d, bias, sn = torch.rand(b, co, device='cuda') + 0.5, torch.randn(co, device='cuda'), torch.rand(b, co, device='cuda') + 0.5
     noise, nw = torch.randn(b, 1, r, r, device='cuda'), torch.tensor([0.1], device='cuda')
     fn = lambda: K.conv3x3(x, wp, co, d=d, noise=noise, noise_w=nw, bias=bias, s_next=sn if ys else None, act=True, want_y=True, want_ys=ys)
+    if os.environ.get('RGB'):          # the last layer with ToRGB in the epilogue: no activation written at all
+        wrgb = K.torgb_weight(torch.randn(3, co, device='cuda'), torch.rand(b, co, device='cuda') + 0.5)
+        rb, skip = torch.randn(3, device='cuda'), torch.randn(b, 3, r // 2, r // 2, device='cuda')
+        fn = lambda: K.conv3x3(x, wp, co, d=d, noise=noise, noise_w=nw, bias=bias, act=True, want_y=False, want_ys=False,
+                               rgb=(wrgb, rb, skip, K.fir_taps(gain=2.0)))
     best, med = timeit(fn)
     byt = b * r * r * (ci + co * (2 if ys else 1)) * 2 + b * r * r * 4
     fl = 2.0 * b * co * ci * 9 * r * r
