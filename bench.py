@@ -757,8 +757,8 @@ def main():
     blur_gbs = blur['work'] / (blur['ms'] * 1e-3) / 1e9 if blur['ms'] > 0 else 0.0
     step_ms = ms_max / args.steps
     kern = {k: dict(ms_per_step=v['ms'] / prof_steps, launches_per_step=v['launches'] / prof_steps,
-                    achieved=(v['work'] / (v['ms'] * 1e-3) / (1e12 if 'conv' in k else 1e9)) if v['ms'] > 0 else 0.0,
-                    unit='TFLOP/s' if 'conv' in k else 'GB/s') for k, v in prof.items()}
+                    achieved=(v['work'] / (v['ms'] * 1e-3) / (1e12 if ('conv' in k and 'rows' not in k) else 1e9)) if v['ms'] > 0 else 0.0,
+                    unit='TFLOP/s' if ('conv' in k and 'rows' not in k) else 'GB/s') for k, v in prof.items()}
     line = dict(metric=METRIC, value=world * args.steps * B / (ms_max * 1e-3), unit=UNIT, n_gpus=world, steps=args.steps,
                 warmup=max(args.warmup, 3), ms_per_step=step_ms, higher_is_better=True, scaling='weak', vs_baseline=None,
                 dtype='bf16', data='synthetic',
@@ -767,7 +767,7 @@ def main():
                 e2e=dict(value=world * args.steps * B / (ms_e2e * 1e-3), unit=UNIT, h2d_bytes_per_step=x_host.numel() * 4,
                          d2h_bytes_per_step=out_host.numel() * 4, ms_per_step=ms_e2e / args.steps),
                 gpu_launches=int(launches),
-                roofline=dict(kernel='conv_tc_kernel (tcgen05 implicit-GEMM 3x3 modulated conv)', bound='tensor', achieved=conv_tf,
+                roofline=dict(kernel='conv_tc_kernel (tcgen05 implicit-GEMM convolutions of the generator and the AlignNet; the HBM-bound row kernels conv_rows / convt_rows are listed separately under kernels.conv3x3_rows)', bound='tensor', achieved=conv_tf,
                               peak=pk['tf_sus'], unit='TFLOP/s', frac=conv_tf / pk['tf_sus'],
                               traffic=ncu_traffic('conv256_pair', 'ncu_r02_summary.json') or ncu_traffic('conv256'),
                               traffic_note='DRAM bytes of one conv_tc_kernel<256,64,STATS,CTA pair> launch (AlignNet 1024->1024 ch at 64 px, batch 16: 1.24 TFLOP, 0.29 GB of activations + weights algorithmic), profiles/ncu_r02_conv256_pair_raw.csv (round-1 single-CTA capture: ncu_r01_conv256_raw.csv)',

@@ -45,6 +45,9 @@ const char *ood_last_error(void);
 int ood_device_is_sm100(void);
 /* number of kernels this library has launched in this process (monotonic; bench.py reports the difference). */
 unsigned long long ood_launch_count(void);
+/* which kernel family the calling thread's last ood_conv3x3 ran on: 0 generic tcgen05 tiles (conv_tc.cu), 1 row-sliding kernel (conv_rows.cu),
+ * 2 row-streaming transposed kernel for the interior (convt_rows.cu), 3 SIMT.  For per-kernel accounting (bench.py), not for control flow. */
+int ood_last_conv_route(void);
 
 /* ---- a1. upfirdn2d on NCHW planes: replaces upfirdn2d_op.upfirdn2d (upfirdn2d.cpp:12-23) with minor==1,
  *      which is the only form the Python wrapper issues (upfirdn2d.py:103).  Generic in every parameter

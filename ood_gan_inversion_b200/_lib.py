@@ -34,6 +34,7 @@ _SIGS = {
     'ood_last_error': ([], C.c_char_p),
     'ood_device_is_sm100': ([], c_int),
     'ood_launch_count': ([], C.c_ulonglong),
+    'ood_last_conv_route': ([], c_int),
     'ood_upfirdn2d': ([c_void_p, c_void_p, c_void_p, c_i64] + [c_int] * 12 + [c_int, c_void_p], c_int),
     'ood_fused_bias_act': ([c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_int, c_i64, c_int, c_int, c_float, c_float,
                             c_int, c_void_p], c_int),

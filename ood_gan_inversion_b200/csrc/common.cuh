@@ -49,6 +49,7 @@ struct DeviceOnce {
     } while (0)
 
 constexpr int kNumSMs = 148;
+extern thread_local int g_conv_route;      // which kernel family the last ood_conv3x3 of this thread ran on (ood_last_conv_route)
 constexpr float kSqrt2 = 1.4142135623730951f;
 
 static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }

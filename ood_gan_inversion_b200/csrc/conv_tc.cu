@@ -760,7 +760,7 @@ int conv3x3_tc(const ood_conv3x3_args &a, cudaStream_t st) {
                 int handled = 0;
                 const int rc = convt_rows_interior(a, st, &handled);
                 if (rc != OOD_OK) return rc;
-                if (handled) continue;
+                if (handled) { g_conv_route = 2; continue; }
             }
             const int rc = conv3x3_tc_geom(a, make_geom_transposed_part(a.batch, a.h, a.w, a.cin, a.cout, part), st);
             if (rc != OOD_OK) return rc;
@@ -916,13 +916,15 @@ extern "C" int ood_conv3x3(const ood_conv3x3_args *a, void *stream) {
     OOD_REQUIRE(!(a->out_f32 && a->out_ys), "conv3x3: out_f32 applies to out_y only");
     OOD_REQUIRE(a->act >= 0 && a->act <= 2 && (a->act != 2 || a->prelu_slope), "conv3x3: act must be 0, 1 or 2 (PReLU needs prelu_slope)");
     cudaStream_t st = (cudaStream_t)stream;
+    g_conv_route = 3;
     if (a->impl == 1) return conv3x3_simt(*a, st);
     OOD_REQUIRE(a->impl == 0, "conv3x3: impl must be 0 (tcgen05) or 1 (simt)");
+    g_conv_route = 0;
     if (!ood_device_is_sm100()) { set_error("conv3x3: the tcgen05 path needs an sm_100 device"); return OOD_ERR_DEVICE; }
     {   // high-resolution small-channel layers: row-sliding kernel (conv_rows.cu); anything else: the generic tiles below
         int handled = 0;
         const int rc = conv3x3_rows(*a, st, &handled);
-        if (handled) return rc;
+        if (handled) { g_conv_route = 1; return rc; }
     }
     return conv3x3_tc(*a, st);
 }

@@ -30,6 +30,9 @@ extern "C" int ood_version(void) { return 100; }
 
 extern "C" unsigned long long ood_launch_count(void) { return ood::g_launches; }
 
+namespace ood { thread_local int g_conv_route = 0; }
+extern "C" int ood_last_conv_route(void) { return ood::g_conv_route; }
+
 extern "C" const char *ood_last_error(void) { return ood::g_err; }
 
 extern "C" int ood_device_is_sm100(void) {

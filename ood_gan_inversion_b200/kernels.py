@@ -46,6 +46,7 @@ class _timed:
         if self.on:
             self.e0, self.e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             self.e0.record()
+        return self
 
     def __exit__(self, *exc):
         if self.on and _prof is not None:
@@ -377,8 +378,13 @@ def conv3x3(x, weight, cout, transposed=False, impl=0, d=None, noise=None, noise
         a.rgb_taps = (C.c_float * 4)(*rtaps)
     # algorithmic work: 2*B*Co*Ci*9*H*W with H, W the INPUT size for the transposed form
     px = h * w if transposed in (0, 1, 5) else oh * ow
-    with _timed(tag or ('conv3x3_tc' if impl == 0 else 'conv3x3_simt'), 2.0 * b * cout * cin * (1 if transposed in (4, 6) else 9) * px):
+    with _timed(tag or ('conv3x3_tc' if impl == 0 else 'conv3x3_simt'), 2.0 * b * cout * cin * (1 if transposed in (4, 6) else 9) * px) as tm:
         check(_lib.lib().ood_conv3x3(C.byref(a), _stream()), 'conv3x3')
+        if tm.on and tag is None and _lib.lib().ood_last_conv_route() in (1, 2):
+            # the HBM-bound row kernels (conv_rows.cu / convt_rows.cu) are accounted in bytes under their own name: input + every output tensor + noise
+            out_bytes = sum(t.numel() * t.element_size() for t in (y, ys) if t is not None)
+            tm.name = 'conv3x3_rows'
+            tm.work = float(b * h * w * cin * _esize(x) + out_bytes + (b * oh * ow * 4 if noise is not None else 0))
     if rgb is not None:
         return y, ys, rgb_out
     if stats_eps is not None or tile_sums:
