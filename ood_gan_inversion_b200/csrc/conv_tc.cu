@@ -254,7 +254,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int item0 = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, item_step = CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     auto item_tile = [&](int q) -> int {
         if (!CTA2) return q;
-        return (2 * (q / p.n_tiles_n) + (int)cta_rank) * p.n_tiles_n + q % p.n_tiles_n;
+        int ph = 0;                                     // every phase has an even number of M tiles (host check): pair q of phase ph starts at tile_begin / 2
+#pragma unroll
+        for (int i = 1; i < 4; ++i)
+            if (i < p.nphases && 2 * q >= p.ph[i].tile_begin) ph = i;
+        const int lq = q - (p.ph[ph].tile_begin >> 1);
+        return p.ph[ph].tile_begin + (2 * (lq / p.n_tiles_n) + (int)cta_rank) * p.n_tiles_n + lq % p.n_tiles_n;
     };
 
     if (warp == 0 && lane == 0) {
@@ -799,14 +804,15 @@ static int conv3x3_tc_geom(const ood_conv3x3_args &a, const ConvGeom &g, cudaStr
     OOD_REQUIRE(!a.acc_in || (uintptr_t)a.acc_in % 16 == 0, "conv3x3 tc: acc_in must be 16-byte aligned");
     OOD_REQUIRE((uintptr_t)a.out_y % 32 == 0 && (uintptr_t)a.out_ys % 32 == 0, "conv3x3 tc: outputs must be 32-byte aligned (256-bit stores)");
 
-    // CTA pairs (cta_group::2): single-phase, ungrouped launches of wide tiles with an even number of M tiles and at least a tile per SM
+    // CTA pairs (cta_group::2): ungrouped launches of wide tiles with an even number of M tiles in every phase and at least two tiles per SM
     // OOD_CTA2: 0 off, 1 (default) = the 256-wide tiles, 2 = the 128-wide tiles too (measured slower); OOD_CTA2_MIN_TILES: launches with fewer tiles stay single-CTA
     // (read per call: the parity tests switch them inside one process)
     const char *e2 = getenv("OOD_CTA2"), *e2m = getenv("OOD_CTA2_MIN_TILES");
     const int cta2_mode = e2 ? atoi(e2) : 1, cta2_min = e2m ? atoi(e2m) : 2 * kNumSMs;
-    const int m_tiles = p.ph[0].tiles_x * p.ph[0].tiles_y * p.ph[0].tiles_b;
-    const bool pair = cta2_mode > 0 && p.nphases == 1 && groups == 1 && !p.in_shared && !p.fused && BK == 64 && (BN == 256 || BN == 128) &&
-                      m_tiles % 2 == 0 && p.total_tiles >= cta2_min && (cta2_mode > 1 || BN == 256);
+    bool m_even = true;                                 // per phase: the two CTAs of a pair take M-adjacent tiles of one phase and one N tile
+    for (int i = 0; i < p.nphases; ++i) m_even = m_even && (p.ph[i].tiles_x * p.ph[i].tiles_y * p.ph[i].tiles_b) % 2 == 0;
+    const bool pair = cta2_mode > 0 && groups == 1 && !p.in_shared && !p.fused && BK == 64 && (BN == 256 || BN == 128) &&
+                      m_even && p.total_tiles >= cta2_min && (cta2_mode > 1 || BN == 256);
     CUtensorMap tmA, tmB;
     {
         cuuint64_t dims[4] = {(cuuint64_t)a.cin, (cuuint64_t)a.w, (cuuint64_t)a.h, (cuuint64_t)(p.in_shared ? p.gbatch : a.batch)};

@@ -756,6 +756,28 @@ def test_conv3x3_cta_pair_kernel(case, monkeypatch):
     torch.testing.assert_close(nchw(pair['f32']), ref, rtol=1e-3, atol=1e-3)
 
 
+@pytest.mark.parametrize('case', [dict(b=2, h=64, w=64, ci=128, co=256), dict(b=2, h=32, w=64, ci=64, co=512), dict(b=3, h=40, w=24, ci=64, co=256)])
+def test_conv_transposed_cta_pair_kernel(case, monkeypatch):
+    """The stride-2 transposed form (four parity phases, model.py:246-258) on CTA pairs: the two CTAs of a pair take M-adjacent tiles of ONE
+    phase, so every phase needs an even number of M tiles (the third case has odd phases and must fall back).  Bit-identical to the
+    single-CTA launch and equal to conv_transpose2d."""
+    b, h, w_, ci, co = (case[k] for k in ('b', 'h', 'w', 'ci', 'co'))
+    x, w = rnd(b, ci, h, w_, seed=1).bfloat16().float(), (0.2 * rnd(co, ci, 3, 3, seed=2)).bfloat16().float()
+    wp = K().pack_conv_weight(w.to(DEV), torch.bfloat16, False)
+    xn = nhwc(x, torch.bfloat16)
+    monkeypatch.setenv('OOD_CTA2', '0')
+    y0, _ = K().conv3x3(xn, wp, co, transposed=True, impl=0, out_f32=True)
+    monkeypatch.setenv('OOD_CTA2', '2')
+    monkeypatch.setenv('OOD_CTA2_MIN_TILES', '2')
+    y1, _ = K().conv3x3(xn, wp, co, transposed=True, impl=0, out_f32=True)
+    yb, _ = K().conv3x3(xn, wp, co, transposed=True, impl=0)
+    torch.cuda.synchronize()
+    assert y1.shape == (b, 2 * h + 1, 2 * w_ + 1, co) and torch.equal(y0, y1)
+    ref = conv_ref(x.double(), w.double(), True).float()
+    torch.testing.assert_close(nchw(y1), ref, rtol=1e-4, atol=2e-3)
+    torch.testing.assert_close(nchw(yb), ref, rtol=2e-2, atol=5e-2)
+
+
 @pytest.mark.parametrize('dtype,c', [(torch.float32, 32), (torch.bfloat16, 64), (torch.bfloat16, 128)])
 def test_alignnet_split_front_and_fused_statistics(dtype, c):
     b, h, w = 2, 37, 53
