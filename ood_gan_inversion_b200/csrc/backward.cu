@@ -134,7 +134,7 @@ __device__ __forceinline__ float2 lds_f2(const float *p) {
     return v;
 }
 
-// MODE 0: one pixel per trip; 1: two pixels per trip; 2: two pixels per trip, d and -bias read from shared memory in the loop (register relief)
+// MODE 0: one pixel per trip; 1: two pixels per trip (all loads of both pixels issued before the first is processed)
 template <typename T, bool RGB, int MODE>
 __global__ void __launch_bounds__(256, 2) act_bwd_fused_kernel(const T *__restrict__ g_in, const float *__restrict__ g_scale, const float *__restrict__ g_rgb,
                                                                 const float *__restrict__ wrgb, const T *__restrict__ y, const float *__restrict__ d,
@@ -151,12 +151,9 @@ __global__ void __launch_bounds__(256, 2) act_bwd_fused_kernel(const T *__restri
     // the three colour rows of this image's ToRGB weights live in shared memory during the pixel loop (the reduction buffer is free until
     // the loop ends): 24 registers less per thread, which is what keeps two blocks resident per SM.  (Measured and not kept: ALL coefficients
     // in shared memory behind non-hoistable loads plus a two-slot register ring of raw loads -- 6.6 -> 8.4 ms per step for the 17 launches.)
-    float *cw = red, *cd = red + 3 * C, *cnb = red + 4 * C;
-    if (RGB || MODE == 2) {
-        if (RGB)
-            for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) cw[i] = wrgb[(int64_t)b * 3 * C + i];
-        if (MODE == 2)
-            for (int i = threadIdx.x; i < C; i += blockDim.x) { cd[i] = d ? d[(int64_t)b * C + i] : 1.f; cnb[i] = bias ? -bias[i] : 0.f; }
+    float *cw = red;
+    if (RGB) {
+        for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) cw[i] = wrgb[(int64_t)b * 3 * C + i];
         __syncthreads();
     }
     float acc[K][N];
@@ -164,8 +161,8 @@ __global__ void __launch_bounds__(256, 2) act_bwd_fused_kernel(const T *__restri
 #pragma unroll
     for (int j = 0; j < N2; ++j) {
         a_gd[j] = a_dot[j] = f2(0.f);
-        d2[j] = (MODE != 2 && active && d) ? make_float2(d[(int64_t)b * C + c + 2 * j], d[(int64_t)b * C + c + 2 * j + 1]) : f2(1.f);
-        nb2[j] = (MODE != 2 && active && bias) ? make_float2(-bias[c + 2 * j], -bias[c + 2 * j + 1]) : f2(0.f);
+        d2[j] = (active && d) ? make_float2(d[(int64_t)b * C + c + 2 * j], d[(int64_t)b * C + c + 2 * j + 1]) : f2(1.f);
+        nb2[j] = (active && bias) ? make_float2(-bias[c + 2 * j], -bias[c + 2 * j + 1]) : f2(0.f);
         sc2[j] = (active && g_scale) ? make_float2(g_scale[(int64_t)b * C + c + 2 * j], g_scale[(int64_t)b * C + c + 2 * j + 1]) : f2(1.f);
 #pragma unroll
         for (int k = 0; k < (RGB ? 3 : 1); ++k) a_w[k][j] = f2(0.f);
@@ -209,9 +206,9 @@ __global__ void __launch_bounds__(256, 2) act_bwd_fused_kernel(const T *__restri
                 const bool px = yv[j].x > 0.f, py = yv[j].y > 0.f;
                 const float2 gate = make_float2(px ? kGp : kGn, py ? kGp : kGn), inv = make_float2(px ? kIp : kIn, py ? kIp : kIn);
                 const float2 gvv = mul2(gy, gate);
-                const float2 v = fma2(yv[j], inv, add2(nz, MODE == 2 ? lds_f2(cnb + c + 2 * j) : nb2[j]));       // v - nz*nw - bias = acc * d
+                const float2 v = fma2(yv[j], inv, add2(nz, nb2[j]));       // v - nz*nw - bias = acc * d
                 a_gd[j] = fma2(gvv, v, a_gd[j]);
-                o[j] = mul2(gvv, MODE == 2 ? lds_f2(cd + c + 2 * j) : d2[j]);
+                o[j] = mul2(gvv, d2[j]);
             }
             bw_store<T>(dst, o);
         };
@@ -239,7 +236,7 @@ __global__ void __launch_bounds__(256, 2) act_bwd_fused_kernel(const T *__restri
             }
         }
     }
-    if (RGB || MODE == 2) __syncthreads();          // every thread is done with the coefficients in `red`
+    if (RGB) __syncthreads();          // every thread is done with the weights in `red`
 #pragma unroll
     for (int j = 0; j < N2; ++j) {
         acc[0][2 * j] = a_gd[j].x; acc[0][2 * j + 1] = a_gd[j].y;
@@ -458,11 +455,10 @@ extern "C" int ood_act_bwd_fused(const void *g_in, const float *g_scale, const f
     dim3 grid(nch, batch);
     const int N = dtype == OOD_F32 ? 4 : 8, K = g_rgb ? 5 : 2;
     if (int rc = (dtype == OOD_F32 ? check_vec<float>("act_bwd_fused", channels) : check_vec<__nv_bfloat16>("act_bwd_fused", channels))) return rc;
-    const size_t smem = std::max((size_t)(256 / (channels / N)) * channels * K, (size_t)5 * channels) * sizeof(float);
-    // the bf16 ToRGB variant is the one short of registers: OOD_ABF_MODE picks its loop form (0 / 1 / 2, see the kernel; measured per Adam step at batch 32:
-    // 6.65 / 7.56 / 7.38 ms for the 17 launches -- the two-pixel forms spill); the others run two pixels per trip
-    int mode = 0;
-    if (const char *e = getenv("OOD_ABF_MODE")) mode = atoi(e);
+    const size_t smem = (size_t)(256 / (channels / N)) * channels * K * sizeof(float);
+    // loop form: two pixels per trip (all loads of both issued first) everywhere except the bf16 ToRGB variant, which is the one short of registers
+    // (measured per Adam step at batch 32 for the 17 launches: one pixel per trip 6.65 ms; two pixels 7.56 ms; two pixels with d / -bias read from
+    // shared memory in the loop 7.38 ms -- both two-pixel forms spill at the 128-register cap)
 #define OOD_ABF(T, RGB, MODE)                                                                                                               \
     do {                                                                                                                                    \
         auto kern = act_bwd_fused_kernel<T, RGB, MODE>;                                                                                     \
@@ -472,9 +468,7 @@ extern "C" int ood_act_bwd_fused(const void *g_in, const float *g_scale, const f
     } while (0)
     if (dtype == OOD_F32) { if (g_rgb) OOD_ABF(float, true, 1); else OOD_ABF(float, false, 1); }
     else if (!g_rgb) OOD_ABF(__nv_bfloat16, false, 1);
-    else if (mode == 0) OOD_ABF(__nv_bfloat16, true, 0);
-    else if (mode == 1) OOD_ABF(__nv_bfloat16, true, 1);
-    else OOD_ABF(__nv_bfloat16, true, 2);
+    else OOD_ABF(__nv_bfloat16, true, 0);
 #undef OOD_ABF
     const int64_t total = (int64_t)batch * channels * K;
     reduce_partials_kernel<<<ceil_div(total, 256), 256, 0, s>>>(workspace, d, sums, channels, K, nch, total, 1);
