@@ -347,6 +347,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const float nw = (p.ep.noise && p.ep.noise_w) ? *p.ep.noise_w : 0.f;
         int acc = 0;
         uint32_t acc_phase = 0;
+        int skn0 = -2, skn1 = -2, skb0 = -2, skb1 = -2;      // what the two staged epilogue-vector buffers hold: (group, N tile), image
         for (int q = item0; q < n_items; q += item_step) {
             const int tile = item_tile(q);
             const TileCoord tc = decode_tile(p, tile, BN);
@@ -364,7 +365,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // vectors (d, s_next, rgb_w) are tile-uniform only when a tile holds one image (NB == 1); otherwise they stay global.
             float *sv = epi_vecs + acc * (Cfg::kEpiVecs * BN);
             const bool stg = p.NB == 1;
-            {
+            // ... and only when they differ from what this buffer already holds: short-K launches (the 1x1 convolutions: one k-step per tile) have no
+            // MMA time to hide the loads and the barrier behind, and their vectors (bias / PReLU, or one image's d / s_next) rarely change between tiles
+            const int key_b = (stg && (p.ep.d || p.ep.out_ys || p.ep.rgb_out)) ? tc.b0 : -1;
+            const int key_n = tc.n0 + gofs * 4;              // n0 < cout <= gofs step: distinct per (group, N tile)
+            const bool restage = (acc ? skn1 : skn0) != key_n || (acc ? skb1 : skb0) != key_b;
+            if (restage) {
+                (acc ? skn1 : skn0) = key_n; (acc ? skb1 : skb0) = key_b;
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * EPW) : "memory");      // every epilogue warp is done reading the buffer's previous contents
                 const int et = threadIdx.x - 64;
                 for (int i = et; i < BN; i += 32 * EPW) {
                     const int n = tc.n0 + i;
