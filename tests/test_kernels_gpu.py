@@ -1016,6 +1016,32 @@ def test_conv3x3_row_sliding_kernel_encoder_variant(case, monkeypatch):
         torch.testing.assert_close(yb.float().permute(0, 3, 1, 2).cpu(), ref.float(), rtol=1e-2, atol=1e-2)
 
 
+def test_round2_entry_points_reject_bad_arguments():
+    """The entry points added in round 2 fail loudly outside their envelopes (no silent fallback): ood_se_apply (channel counts, tile-sum shape),
+    conv3x3 tile sums / statistics (narrow or grouped launches), ood_act_bwd_fused (no incoming gradient, mismatched shapes)."""
+    from ood_gan_inversion_b200 import kernels as K
+    v = rnd(2, 8, 8, 96, seed=1).half().to(DEV)
+    sums = torch.zeros(2, 1, 96, 2, device=DEV)
+    w1, w2 = rnd(6, 96, seed=2).to(DEV), rnd(96, 6, seed=3).to(DEV)
+    with pytest.raises(RuntimeError):                       # 96 channels: not 64 / 128 / 256 / 512
+        K.se_apply(v, sums, w1, w2, v.float())
+    v2 = rnd(2, 8, 8, 128, seed=1).half().to(DEV)
+    with pytest.raises(AssertionError):                     # tile sums of another tensor
+        K.se_apply(v2, sums, rnd(8, 128, seed=2).to(DEV), rnd(128, 8, seed=3).to(DEV), v2.float())
+    x = rnd(1, 8, 8, 64, seed=4).bfloat16().to(DEV)
+    wp = K.pack_conv_weight(rnd(64, 64, 3, 3, seed=5).to(DEV), torch.bfloat16, False)
+    assert not K.conv3x3_stats_ok(x, 64)                     # 64 output channels: no 128-wide tile
+    with pytest.raises(RuntimeError):
+        K.conv3x3(x, wp, 64, tile_sums=True)
+    y = rnd(2, 8, 8, 32, seed=6).bfloat16().to(DEV)
+    d = torch.ones(2, 32, device=DEV)
+    with pytest.raises(AssertionError):                     # neither g_in nor a ToRGB gradient
+        K.act_bwd_fused(None, None, None, y, d, None, None, None)
+    with pytest.raises(AssertionError):                     # g_in of another shape
+        K.act_bwd_fused(rnd(2, 8, 4, 32, seed=7).bfloat16().to(DEV), None, None, y, d, None, None, None)
+    torch.cuda.synchronize()
+
+
 def test_encoder_glue_kernels():
     """ood_latent_assemble (psp_encoders.py:199-214 + e4e_arch.py:261), ood_alignnet_head_weights (the InstanceNorm folded into the
     AlignNet head's projection) and se_residual's out_lp copy against their torch formulas."""
