@@ -308,7 +308,7 @@ def sharded_batch_leg(net, global_batch, chunk, steps, rank, world, dev, barrier
 
 def inversion_leg(dev, batch=32, steps=5):
     """BASELINE configs[3] ("Config 4"): Adam on W+ at 1024 px through this package's forward + hand-written backward
-    (inversion.LatentInverter, bf16 storage), `steps` timed steps after a 2-step warm-up run."""
+    (inversion.LatentInverter, bf16 storage), `steps` timed steps after a 3-step warm-up run."""
     import torch
     from ood_gan_inversion_b200 import stylegan as sg
     from ood_gan_inversion_b200.inversion import LatentInverter, generator_synthesizer
@@ -321,7 +321,7 @@ def inversion_leg(dev, batch=32, steps=5):
         target = synthetic_faces(batch, SIZE, seed=3, device=dev)
         lat0 = torch.zeros(batch, 18, 512, device=dev)
         inv = LatentInverter(generator_synthesizer(gen), lr=0.01)
-        inv.run(target, lat0, 2)
+        inv.run(target, lat0, 3)                         # warm-up: kernels loaded, the caching allocator at its steady state
         torch.cuda.synchronize(dev)
         torch.cuda.reset_peak_memory_stats(dev)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -249,6 +249,159 @@ __global__ void __launch_bounds__(256, 2) act_bwd_fused_kernel(const T *__restri
     block_reduce_store<N>(acc, K, red, partial + (((int64_t)b * nchunks + chunk) * C) * K, C, cv, lanes, lane, vec, active);
 }
 
+// ---- the same pass with its two big operands staged through shared memory by bulk copies (cp.async.bulk, mbarrier ring):
+// a chunk of pixels of one image is a CONTIGUOUS byte range of g_in and of y (NHWC), so thread 0 streams it in 8 KB pieces into a
+// four-slot ring (it refills the slot the block finished one trip ago) while the eight warps read their 16-byte vectors from shared memory.  The register form above keeps one 44-byte
+// request per thread in flight (128 registers, 16 warps per SM: 0.55 of the HBM peak); here the bytes in flight are the ring (2 x 64 KB per SM).
+constexpr int kAbfStages = 4, kAbfIters = 2;                 // iterations (256 vectors each) per ring slot
+constexpr int kAbfSlotBytes = kAbfIters * 256 * 16;          // per operand
+template <typename T, bool RGB>
+__global__ void __launch_bounds__(256, 2) act_bwd_fused_staged_kernel(const T *__restrict__ g_in, const float *__restrict__ g_scale, const float *__restrict__ g_rgb,
+                                                                       const float *__restrict__ wrgb, const T *__restrict__ y, const float *__restrict__ d,
+                                                                       const float *__restrict__ bias, const float *__restrict__ noise, int64_t noise_bstride,
+                                                                       const float *__restrict__ noise_w, T *__restrict__ g, float *__restrict__ partial, int64_t P,
+                                                                       int C, int nchunks, int chunk_px) {
+    constexpr int N = Vec<T>::N, N2 = N / 2, K = RGB ? 5 : 2;
+    extern __shared__ __align__(128) uint8_t abf_raw[];
+    uint8_t *ring = abf_raw;                                              // [stage][g | y][kAbfSlotBytes]
+    float *red = reinterpret_cast<float *>(abf_raw);                      // the reduction buffer reuses the ring after the pixel loop
+    float *cw = reinterpret_cast<float *>(abf_raw + kAbfStages * 2 * kAbfSlotBytes);          // ToRGB colour rows [3][C]
+    uint64_t *full = reinterpret_cast<uint64_t *>(cw + 3 * C), *empty = full + kAbfStages;
+    const int cv = C / N, lanes = 256 / cv;
+    const int vec = threadIdx.x % cv, lane = threadIdx.x / cv;
+    const bool active = lane < lanes;
+    const int b = blockIdx.y, chunk = blockIdx.x, c = vec * N;
+    const float nw = (noise && noise_w) ? *noise_w : 0.f;
+    const int64_t p0 = (int64_t)chunk * chunk_px, p1 = min(p0 + chunk_px, P);
+    const int n_px = (int)(p1 - p0);
+    const int px_slot = kAbfIters * lanes;                               // pixels per ring slot
+    const int n_slots = (n_px + px_slot - 1) / px_slot;
+    const size_t px_bytes = (size_t)C * sizeof(T);
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kAbfStages; ++i) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(&full[i])));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(&empty[i])));
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (RGB)
+        for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) cw[i] = wrgb[(int64_t)b * 3 * C + i];
+    __syncthreads();
+    auto mbar_wait = [](uint64_t *bar, uint32_t parity) {
+        asm volatile("{\n.reg .pred p;\nABW:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra ABD;\nbra ABW;\nABD:\n}\n" ::"r"(
+                         (uint32_t)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+    };
+    float acc[K][N];
+    float2 a_gd[N2], a_dot[N2], a_w[RGB ? 3 : 1][N2];
+#pragma unroll
+    for (int j = 0; j < N2; ++j) {
+        a_gd[j] = a_dot[j] = f2(0.f);
+#pragma unroll
+        for (int k = 0; k < (RGB ? 3 : 1); ++k) a_w[k][j] = f2(0.f);
+    }
+    const uint8_t *gsrc = g_in ? reinterpret_cast<const uint8_t *>(g_in) + ((int64_t)b * P + p0) * px_bytes : nullptr;
+    const uint8_t *ysrc = reinterpret_cast<const uint8_t *>(y) + ((int64_t)b * P + p0) * px_bytes;
+    auto fill = [&](int k) {            // thread 0: bulk copies of ring slot k % stages
+        const int slot = k % kAbfStages;
+        const int px = min(px_slot, n_px - k * px_slot);
+        const uint32_t bytes = (uint32_t)(px * px_bytes);
+        const uint32_t fb = (uint32_t)__cvta_generic_to_shared(&full[slot]);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fb), "r"(gsrc ? 2 * bytes : bytes) : "memory");
+        uint8_t *dst = ring + (size_t)slot * 2 * kAbfSlotBytes;
+        if (gsrc)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             (uint32_t)__cvta_generic_to_shared(dst)), "l"(gsrc + (size_t)k * px_slot * px_bytes), "r"(bytes), "r"(fb) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         (uint32_t)__cvta_generic_to_shared(dst + kAbfSlotBytes)), "l"(ysrc + (size_t)k * px_slot * px_bytes), "r"(bytes), "r"(fb) : "memory");
+    };
+    if (threadIdx.x == 0)
+        for (int k = 0; k < min(kAbfStages, n_slots); ++k) fill(k);
+    {
+        float2 d2[N2], nb2[N2], sc2[N2];
+#pragma unroll
+        for (int j = 0; j < N2; ++j) {
+            d2[j] = (active && d) ? make_float2(d[(int64_t)b * C + c + 2 * j], d[(int64_t)b * C + c + 2 * j + 1]) : f2(1.f);
+            nb2[j] = (active && bias) ? make_float2(-bias[c + 2 * j], -bias[c + 2 * j + 1]) : f2(0.f);
+            sc2[j] = (active && g_scale) ? make_float2(g_scale[(int64_t)b * C + c + 2 * j], g_scale[(int64_t)b * C + c + 2 * j + 1]) : f2(1.f);
+        }
+        constexpr float kGp = kSqrt2, kGn = 0.2f * kSqrt2, kIp = 1.f / kSqrt2, kIn = 1.f / (0.2f * kSqrt2);
+        const float *np = noise ? noise + b * noise_bstride + p0 : nullptr;
+        const float *rp = RGB ? g_rgb + (int64_t)b * 3 * P + p0 : nullptr;
+        T *gout = g + ((int64_t)b * P + p0) * C;
+        for (int k = 0; k < n_slots; ++k) {
+            const int slot = k % kAbfStages;
+            if (threadIdx.x == 0 && k >= 1 && k - 1 + kAbfStages < n_slots) {          // refill the slot of the previous trip once all eight warps have let go of it
+                mbar_wait(&empty[(k - 1) % kAbfStages], ((k - 1) / kAbfStages) & 1);
+                fill(k - 1 + kAbfStages);
+            }
+            // the small per-pixel planes (noise, the three ToRGB gradient planes) come through the ordinary load path: requested before the wait
+            float nzv[kAbfIters], r0v[kAbfIters], r1v[kAbfIters], r2v[kAbfIters];
+#pragma unroll
+            for (int u = 0; u < kAbfIters; ++u) {
+                const int px = (k * kAbfIters + u) * lanes + lane;
+                const bool ok = active && px < n_px;
+                nzv[u] = (ok && np) ? __ldg(np + px) : 0.f;
+                r0v[u] = (RGB && ok) ? __ldg(rp + px) : 0.f;
+                r1v[u] = (RGB && ok) ? __ldg(rp + P + px) : 0.f;
+                r2v[u] = (RGB && ok) ? __ldg(rp + 2 * P + px) : 0.f;
+            }
+            mbar_wait(&full[slot], (k / kAbfStages) & 1);
+            const uint8_t *sg = ring + (size_t)slot * 2 * kAbfSlotBytes, *sy = sg + kAbfSlotBytes;
+#pragma unroll
+            for (int u = 0; u < kAbfIters; ++u) {
+                const int px = (k * kAbfIters + u) * lanes + lane;
+                const bool ok = active && px < n_px;
+                uint4 gq = make_uint4(0u, 0u, 0u, 0u), yq = make_uint4(0u, 0u, 0u, 0u);
+                if (ok) {
+                    const size_t off = ((size_t)(u * lanes + lane) * C + c) * sizeof(T);
+                    if (g_in) gq = *reinterpret_cast<const uint4 *>(sg + off);
+                    yq = *reinterpret_cast<const uint4 *>(sy + off);
+                }
+                if (u == kAbfIters - 1) {          // the slot's last shared-memory read: hand it back to the producer
+                    __syncwarp();
+                    if ((threadIdx.x & 31) == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((uint32_t)__cvta_generic_to_shared(&empty[slot])) : "memory");
+                }
+                if (!ok) continue;
+                float2 gv[N2], yv[N2], o[N2];
+                bw_unpack<T>(gq, gv);
+                bw_unpack<T>(yq, yv);
+                const float2 nz = f2(-nw * nzv[u]);
+                const float2 r0 = f2(r0v[u]), r1 = f2(r1v[u]), r2 = f2(r2v[u]);
+#pragma unroll
+                for (int j = 0; j < N2; ++j) {
+                    a_dot[j] = fma2(gv[j], yv[j], a_dot[j]);
+                    float2 gy = mul2(gv[j], sc2[j]);
+                    if (RGB) {
+                        const float2 w0 = lds_f2(cw + c + 2 * j), w1 = lds_f2(cw + C + c + 2 * j), w2 = lds_f2(cw + 2 * C + c + 2 * j);
+                        gy = fma2(r0, w0, fma2(r1, w1, fma2(r2, w2, gy)));
+                        a_w[0][j] = fma2(r0, yv[j], a_w[0][j]);
+                        a_w[1][j] = fma2(r1, yv[j], a_w[1][j]);
+                        a_w[2][j] = fma2(r2, yv[j], a_w[2][j]);
+                    }
+                    const bool pxp = yv[j].x > 0.f, pyp = yv[j].y > 0.f;
+                    const float2 gate = make_float2(pxp ? kGp : kGn, pyp ? kGp : kGn), inv = make_float2(pxp ? kIp : kIn, pyp ? kIp : kIn);
+                    const float2 gvv = mul2(gy, gate);
+                    const float2 v = fma2(yv[j], inv, add2(nz, nb2[j]));       // v - nz*nw - bias = acc * d
+                    a_gd[j] = fma2(gvv, v, a_gd[j]);
+                    o[j] = mul2(gvv, d2[j]);
+                }
+                bw_store<T>(gout + (int64_t)px * C + c, o);
+            }
+        }
+    }
+    __syncthreads();          // every slot has been consumed: the ring becomes the reduction buffer
+#pragma unroll
+    for (int j = 0; j < N2; ++j) {
+        acc[0][2 * j] = a_gd[j].x; acc[0][2 * j + 1] = a_gd[j].y;
+        acc[1][2 * j] = a_dot[j].x; acc[1][2 * j + 1] = a_dot[j].y;
+        if (RGB) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { acc[(RGB ? 2 : 0) + k][2 * j] = a_w[k][j].x; acc[(RGB ? 2 : 0) + k][2 * j + 1] = a_w[k][j].y; }
+        }
+    }
+    block_reduce_store<N>(acc, K, red, partial + (((int64_t)b * nchunks + chunk) * C) * K, C, cv, lanes, lane, vec, active);
+}
+
 // ---- sum_pix a*b per (b,c)
 template <typename T>
 __global__ void __launch_bounds__(256) dot_partial_kernel(const T *__restrict__ a, const T *__restrict__ bb,
@@ -466,9 +619,27 @@ extern "C" int ood_act_bwd_fused(const void *g_in, const float *g_scale, const f
         kern<<<grid, 256, smem, s>>>((const T *)g_in, g_scale, g_rgb, wrgb, (const T *)y, d, bias, noise, noise_bstride, noise_w, (T *)g, workspace, \
                                      pixels, channels, nch, cpx);                                                                           \
     } while (0)
-    if (dtype == OOD_F32) { if (g_rgb) OOD_ABF(float, true, 1); else OOD_ABF(float, false, 1); }
+    // the staged form (bulk copies into a shared-memory ring) for chunks long enough to fill the ring; OOD_ABF_STAGED=0 keeps the register form
+    static int staged = -1;
+    if (staged < 0) { const char *e = getenv("OOD_ABF_STAGED"); staged = (e && e[0] == '0') ? 0 : 1; }
+    const size_t smem_st = (size_t)kAbfStages * 2 * kAbfSlotBytes + (size_t)3 * channels * sizeof(float) + 2 * kAbfStages * sizeof(uint64_t);
+    const bool use_staged = staged && cpx >= 2 * kAbfStages * kAbfIters * (256 / (channels / N)) && (size_t)(256 / (channels / N)) * channels * K * sizeof(float) <= (size_t)kAbfStages * 2 * kAbfSlotBytes &&
+                            ((uintptr_t)y % 16 == 0) && ((uintptr_t)g_in % 16 == 0);
+#define OOD_ABFS(T, RGB)                                                                                                                    \
+    do {                                                                                                                                    \
+        auto kern = act_bwd_fused_staged_kernel<T, RGB>;                                                                                    \
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_st);                                              \
+        kern<<<grid, 256, smem_st, s>>>((const T *)g_in, g_scale, g_rgb, wrgb, (const T *)y, d, bias, noise, noise_bstride, noise_w, (T *)g, workspace, \
+                                        pixels, channels, nch, cpx);                                                                        \
+    } while (0)
+    if (use_staged) {
+        if (dtype == OOD_F32) { if (g_rgb) OOD_ABFS(float, true); else OOD_ABFS(float, false); }
+        else { if (g_rgb) OOD_ABFS(__nv_bfloat16, true); else OOD_ABFS(__nv_bfloat16, false); }
+    }
+    else if (dtype == OOD_F32) { if (g_rgb) OOD_ABF(float, true, 1); else OOD_ABF(float, false, 1); }
     else if (!g_rgb) OOD_ABF(__nv_bfloat16, false, 1);
     else OOD_ABF(__nv_bfloat16, true, 0);
+#undef OOD_ABFS
 #undef OOD_ABF
     const int64_t total = (int64_t)batch * channels * K;
     reduce_partials_kernel<<<ceil_div(total, 256), 256, 0, s>>>(workspace, d, sums, channels, K, nch, total, 1);
