@@ -620,10 +620,11 @@ extern "C" int ood_act_bwd_fused(const void *g_in, const float *g_scale, const f
                                      pixels, channels, nch, cpx);                                                                           \
     } while (0)
     // the staged form (bulk copies into a shared-memory ring) for chunks long enough to fill the ring; OOD_ABF_STAGED=0 keeps the register form
-    static int staged = -1;
-    if (staged < 0) { const char *e = getenv("OOD_ABF_STAGED"); staged = (e && e[0] == '0') ? 0 : 1; }
+    // (read per call: =2 forces it on short chunks too, which is how the parity tests reach its partial-slot paths)
+    const char *es = getenv("OOD_ABF_STAGED");
+    const int staged = es ? atoi(es) : 1;
     const size_t smem_st = (size_t)kAbfStages * 2 * kAbfSlotBytes + (size_t)3 * channels * sizeof(float) + 2 * kAbfStages * sizeof(uint64_t);
-    const bool use_staged = staged && cpx >= 2 * kAbfStages * kAbfIters * (256 / (channels / N)) && (size_t)(256 / (channels / N)) * channels * K * sizeof(float) <= (size_t)kAbfStages * 2 * kAbfSlotBytes &&
+    const bool use_staged = staged && (staged > 1 || cpx >= 2 * kAbfStages * kAbfIters * (256 / (channels / N))) && (size_t)(256 / (channels / N)) * channels * K * sizeof(float) <= (size_t)kAbfStages * 2 * kAbfSlotBytes &&
                             ((uintptr_t)y % 16 == 0) && ((uintptr_t)g_in % 16 == 0);
 #define OOD_ABFS(T, RGB)                                                                                                                    \
     do {                                                                                                                                    \

@@ -92,12 +92,15 @@ def test_act_bwd_dot_torgb_bwd_vs_autograd():
     torch.testing.assert_close(gw_k.cpu(), gw_ref, rtol=1e-4, atol=1e-3)
 
 
+@pytest.mark.parametrize('staged', ['0', '2'])
 @pytest.mark.parametrize('dt', [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize('case', [dict(b=2, c=32, h=19, w=23, rgb=True, gin=True), dict(b=3, c=64, h=16, w=16, rgb=False, gin=True),
-                                  dict(b=2, c=512, h=8, w=8, rgb=True, gin=False), dict(b=1, c=128, h=33, w=9, rgb=True, gin=True)])
-def test_act_bwd_fused_equals_the_separate_kernels(case, dt):
+                                  dict(b=2, c=512, h=8, w=8, rgb=True, gin=False), dict(b=1, c=128, h=33, w=9, rgb=True, gin=True),
+                                  dict(b=40, c=32, h=64, w=96, rgb=True, gin=True), dict(b=36, c=64, h=37, w=53, rgb=False, gin=True)])
+def test_act_bwd_fused_equals_the_separate_kernels(case, dt, staged, monkeypatch):
     """ood_act_bwd_fused (one pass: scale of the incoming unscaled gradient + ToRGB data gradient + activation backward + the gd / style /
-    ToRGB-weight reductions) against torgb_bwd -> act_bwd -> dot_reduce and against autograd (model.py:277-292, 353-372)."""
+    ToRGB-weight reductions) against torgb_bwd -> act_bwd -> dot_reduce and against autograd (model.py:277-292, 353-372); both loop forms."""
+    monkeypatch.setenv('OOD_ABF_STAGED', staged)          # 0: the register form; 2: the bulk-copy ring form on every shape (partial slots, short chunks, many-slot chunks)
     b, c, h, w = (case[k] for k in ('b', 'c', 'h', 'w'))
     acc = rnd(b, c, h, w, seed=1).requires_grad_(True)
     d = (0.5 + rnd(b, c, seed=2).abs()).requires_grad_(True)
