@@ -447,7 +447,8 @@ int conv3x3_rows(const ood_conv3x3_args &a, cudaStream_t st, int *handled) {
     const bool f16 = a.dtype == OOD_F16;
     if (a.transposed || (a.dtype != OOD_BF16 && !f16) || a.out_f32 || a.groups > 1 || a.acc_in || a.tiled || a.stats_out || a.stats_ws) return OOD_OK;
     if ((f16 || a.act == 2) && !enc_rows) return OOD_OK;
-    if (!((a.cin == 32 || a.cin == 64) && (a.cout == 32 || a.cout == 64) && a.cin >= a.cout)) return OOD_OK;
+    // Ci >= Co for the generator's layers; the encoder's input layer (3 channels padded to 32 -> 64, psp_encoders.py:128-131) is the one 32 -> 64 case
+    if (!((a.cin == 32 || a.cin == 64) && (a.cout == 32 || a.cout == 64) && (a.cin >= a.cout || ((f16 || a.act == 2) && enc_rows)))) return OOD_OK;
     if (a.w % 128 != 0 || a.h < 3 || (int64_t)a.batch * a.h * a.w >= (1LL << 31)) return OOD_OK;
     static EncodeFn encode = nullptr;
     if (!encode) {
@@ -510,8 +511,9 @@ int conv3x3_rows(const ood_conv3x3_args &a, cudaStream_t st, int *handled) {
     p.total_strips = (int)total;
     p.ep = make_epilogue(a, 0);
     *handled = 1;
-    if (enc) {          // encoder variant: only the 64 -> 64 layers exist (psp_encoders.py:128-131 input layer + the first IR-SE stage)
+    if (enc) {          // encoder variant: the 32 -> 64 input layer (psp_encoders.py:128-131) and the 64 -> 64 layers of the first IR-SE stage
         if (a.cin == 64 && a.cout == 64) return launch<64, 64, true>(tmA, tmB, tmY, tmYS, p, st);
+        if (a.cin == 32 && a.cout == 64) return launch<32, 64, true>(tmA, tmB, tmY, tmYS, p, st);
         *handled = 0;
         return OOD_OK;
     }

@@ -989,7 +989,8 @@ def test_conv3x3_f16_storage(case):
 
 
 @pytest.mark.parametrize('case', [dict(b=2, h=40, w=128, dt='f16', act=2), dict(b=1, h=19, w=256, dt='f16', act=0),
-                                  dict(b=3, h=9, w=128, dt='bf16', act=2), dict(b=5, h=128, w=128, dt='f16', act=2)])
+                                  dict(b=3, h=9, w=128, dt='bf16', act=2), dict(b=5, h=128, w=128, dt='f16', act=2),
+                                  dict(b=2, h=37, w=256, dt='f16', act=2, ci=32), dict(b=1, h=64, w=128, dt='bf16', act=2, ci=32)])
 def test_conv3x3_row_sliding_kernel_encoder_variant(case, monkeypatch):
     """The encoder's 64 -> 64 convolutions (psp_encoders.py:128-131, helpers.py:114-119 at 256 / 128 px) on the row-sliding kernel:
     f16 operands and outputs, PReLU or bias-only epilogue, strips of 32 / 16 / 8 rows (a strip per SM when the image allows), against
@@ -998,8 +999,9 @@ def test_conv3x3_row_sliding_kernel_encoder_variant(case, monkeypatch):
     monkeypatch.setenv('OOD_ROWS_MIN_STRIPS', '1')
     b, h, w_, act = case['b'], case['h'], case['w'], case['act']
     dt = torch.float16 if case['dt'] == 'f16' else torch.bfloat16
-    x = rnd(b, 64, h, w_, seed=1).to(dt).float()
-    w = (rnd(64, 64, 3, 3, seed=2) / 24.0).to(dt).float()
+    ci = case.get('ci', 64)              # 32: the encoder's input layer (3 image channels padded to 32 -> 64)
+    x = rnd(b, ci, h, w_, seed=1).to(dt).float()
+    w = (rnd(64, ci, 3, 3, seed=2) / 24.0).to(dt).float()
     bias, slope = rnd(64, seed=3), 0.25 + 0.2 * rnd(64, seed=4)
     xp = x.permute(0, 2, 3, 1).contiguous().to(dt).to(DEV)
     wp = K.pack_conv_weight(w.to(DEV), dt, False)
