@@ -14,8 +14,13 @@ The synthesis itself is `Generator.forward` of this package: with a latent that 
 backward of synthesis_grad.SynthesisFn (CUDA only; there is no CPU fallback).  `synthesize` can be replaced by any
 differentiable callable latent -> image, which is how the host-side logic is tested without a GPU.
 """
+import os
+
 import torch
 import torch.distributed as dist
+
+_GRAPH = os.environ.get('OOD_INVERSION_GRAPH', '1') != '0'      # replay the Adam step as a CUDA graph (see LatentInverter.run)
+_GRAPH_EAGER_STEPS = 3                                           # eager steps before the capture (lazy initialisation, allocator steady state)
 
 
 def _world(group):
@@ -60,8 +65,9 @@ class LatentInverter:
                         same number of images, as sharding.shard_bounds gives for a divisible batch).
     """
 
-    def __init__(self, synthesize, lr=0.01, shared_delta=False, loss=mse_loss, group=None, betas=(0.9, 0.999)):
+    def __init__(self, synthesize, lr=0.01, shared_delta=False, loss=mse_loss, group=None, betas=(0.9, 0.999), graph=None):
         self.synthesize, self.lr, self.shared_delta, self.loss, self.group, self.betas = synthesize, lr, shared_delta, loss, group, betas
+        self.graph = _GRAPH if graph is None else bool(graph)
 
     def _check_equal_shards(self, n_local, device):
         if _world(self.group) == 1:
@@ -83,11 +89,15 @@ class LatentInverter:
             leaf = torch.zeros((1,) + tuple(base.shape[1:]), device=base.device, dtype=base.dtype, requires_grad=True)
         else:
             leaf = base.clone().requires_grad_(True)
-        opt = torch.optim.Adam([leaf], lr=self.lr, betas=self.betas)
         world = _world(self.group)
+        # One Adam step is a fixed sequence of ~170 launches (forward, hand-written backward, the optimizer's foreach kernels): after a few eager
+        # steps it is captured into a CUDA graph and replayed -- same kernels, same order, same numbers; the eager step spends ~10 % of its
+        # time between launches.  Not with a per-step callback, and not when the step contains a collective (shared offset across ranks).
+        use_graph = self.graph and leaf.is_cuda and callback is None and not (self.shared_delta and world > 1) and steps > _GRAPH_EAGER_STEPS + 1
+        opt = torch.optim.Adam([leaf], lr=self.lr, betas=self.betas, capturable=bool(use_graph))
         losses = []
-        for i in range(steps):
-            opt.zero_grad(set_to_none=True)
+
+        def step():
             latent = base + leaf if self.shared_delta else leaf
             loss = self.loss(self.synthesize(latent), target)
             loss.backward()
@@ -95,9 +105,27 @@ class LatentInverter:
                 dist.all_reduce(leaf.grad, op=dist.ReduceOp.SUM, group=self.group)      # 36 KB at [1,18,512] fp32
                 leaf.grad.div_(world)
             opt.step()
-            losses.append(loss.detach())
+            return loss.detach()
+
+        n_eager = _GRAPH_EAGER_STEPS if use_graph else steps
+        for i in range(n_eager):
+            opt.zero_grad(set_to_none=True)
+            loss = step()
+            losses.append(loss)
             if callback is not None:
-                callback(i, loss.detach(), leaf.detach())
+                callback(i, loss, leaf.detach())
+        if use_graph:
+            dev = leaf.device
+            torch.cuda.synchronize(dev)
+            graph = torch.cuda.CUDAGraph()
+            opt.zero_grad(set_to_none=True)                       # the captured backward allocates leaf.grad inside the graph's pool
+            with torch.cuda.graph(graph):
+                static_loss = step()
+            for i in range(n_eager, steps):
+                graph.replay()
+                losses.append(static_loss.clone())
+            torch.cuda.current_stream(dev).synchronize()
+            del graph
         self.delta = leaf.detach() if self.shared_delta else None         # the shared offset itself (bit-identical on every rank)
         out = (base + leaf.detach()) if self.shared_delta else leaf.detach()
         return out, [float(l) for l in losses]

@@ -241,13 +241,13 @@ def test_inversion_api_per_image_and_shared_delta():
                                           size, randomize_noise=False)
     lat, losses = invert(gen, target, lat0, steps=steps, lr=0.01)
     assert lat.shape == lat0.shape and losses[-1] < losses[0]
-    oracle = LatentInverter(lambda l: ostyle.generator_forward(sdd, l, size, randomize_noise=False), lr=0.01)
+    oracle = LatentInverter(lambda l: ostyle.generator_forward(sdd, l, size, randomize_noise=False), lr=0.01, graph=False)
     lat_o, losses_o = oracle.run(target, lat0, steps)
     torch.testing.assert_close(torch.tensor(losses), torch.tensor(losses_o), rtol=1e-3, atol=1e-6)
     assert float((lat - lat_o).abs().max()) < 5e-3
     inv = LatentInverter(generator_synthesizer(gen), lr=0.01, shared_delta=True)
     lat_d, losses_d = inv.run(target, lat0, steps)
-    oracle_d = LatentInverter(lambda l: ostyle.generator_forward(sdd, l, size, randomize_noise=False), lr=0.01, shared_delta=True)
+    oracle_d = LatentInverter(lambda l: ostyle.generator_forward(sdd, l, size, randomize_noise=False), lr=0.01, shared_delta=True, graph=False)
     _, losses_od = oracle_d.run(target, lat0, steps)
     assert inv.delta.shape == (1, gen.n_latent, 512) and losses_d[-1] < losses_d[0]
     torch.testing.assert_close(torch.tensor(losses_d), torch.tensor(losses_od), rtol=1e-3, atol=1e-6)
@@ -256,3 +256,33 @@ def test_inversion_api_per_image_and_shared_delta():
     diff = (inv.delta - oracle_d.delta).abs()
     assert float(diff.mean()) < 5e-4 and float(diff.max()) < 3e-2
     sg.set_precision('bf16')
+
+
+@pytest.mark.parametrize('shared', [False, True])
+def test_inversion_graph_replay_equals_the_eager_loop(shared):
+    """LatentInverter replays the Adam step as a CUDA graph after three eager steps (inversion.py): the same kernels in the same order; the
+    loss curve and the final codes follow the all-eager run."""
+    import ood_gan_inversion_b200.stylegan as sg
+    from ood_gan_inversion_b200.inversion import LatentInverter, generator_synthesizer
+    sg.set_precision('bf16')
+    size, batch, steps = 64, 3, 11
+    gen = sg.Generator(size, 512, 8).to(DEV)
+    gen.load_state_dict(ostyle.synthetic_generator_state(size, seed=7))
+    for p in gen.parameters():
+        p.requires_grad_(False)
+    lat0 = 0.5 * torch.randn(batch, gen.n_latent, 512, generator=torch.Generator().manual_seed(8)).to(DEV)
+    target = (0.3 * torch.randn(batch, 3, size, size, generator=torch.Generator().manual_seed(9))).to(DEV)
+    runs = []
+    for graph in (False, True):
+        inv = LatentInverter(generator_synthesizer(gen), lr=0.01, shared_delta=shared, graph=graph)
+        lat, losses = inv.run(target, lat0, steps)
+        runs.append((lat.clone(), losses))
+    # same kernels in the same order; the two runs still differ in the optimizer: capturable Adam keeps `step` and the bias corrections on the
+    # device in fp32, the eager one computes them in Python doubles -- a last-digit difference per update that Adam's normalisation can amplify on
+    # elements whose gradient sits at the rounding noise (see test_inversion_api_per_image_and_shared_delta)
+    assert len(runs[1][1]) == steps
+    torch.testing.assert_close(torch.tensor(runs[1][1]), torch.tensor(runs[0][1]), rtol=1e-3, atol=1e-6)
+    diff = (runs[0][0] - runs[1][0]).abs()
+    assert float(diff.mean()) < 5e-4 and float(diff.max()) < 3e-2
+    assert runs[1][1][-1] < runs[1][1][0]
+
