@@ -324,25 +324,23 @@ def inversion_leg(dev, batch=32, steps=5):
         inv.run(target, lat0, 3)                         # warm-up: kernels loaded, the caching allocator at its steady state
         torch.cuda.synchronize(dev)
         torch.cuda.reset_peak_memory_stats(dev)
-        # LatentInverter replays the Adam step as a CUDA graph after three eager steps (BASELINE's config runs 500 steps: the capture is a fixed
-        # cost).  ms per step = the difference of two runs of different length, so that the eager steps and the capture drop out.
-        n_short, n_long = 6, 6 + 4 * steps
-
-        def timed(n):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            _, ls = inv.run(target, lat0, n)
-            e1.record()
-            torch.cuda.synchronize(dev)
-            return e0.elapsed_time(e1), ls
-        t_short, _ = timed(n_short)
-        t_long, losses = timed(n_long)
-    ms = (t_long - t_short) / (n_long - n_short)
+        # One run of LatentInverter, timed as a whole with CUDA events (eager launches, the default).  With OOD_INVERSION_GRAPH=1 the run replays the
+        # Adam step as a CUDA graph after three eager steps; ms per step is then the device time of the replayed steps (events inside run()).
+        n_run = 3 + 4 * steps
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _, losses = inv.run(target, lat0, n_run)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        run_ms = e0.elapsed_time(e1)
+        tm = inv.timing
+    n_timed = tm['replay_steps'] if tm['replay_steps'] else n_run
+    ms = (tm['replay_ms'] if tm['replay_steps'] else run_ms) / n_timed
     res = dict(workload=f'W+ latent inversion, 1024 px, Adam lr 0.01, pixel MSE, batch {batch}, bf16 (BASELINE configs[3])', batch=batch,
-               steps=n_long - n_short, ms_per_step=ms, steps_per_s=1e3 / ms, image_steps_per_s=batch * 1e3 / ms, loss_first=losses[0],
+               steps=n_timed, ms_per_step=ms, steps_per_s=1e3 / ms, image_steps_per_s=batch * 1e3 / ms, loss_first=losses[0],
                loss_last=losses[-1], peak_mem_gib=torch.cuda.max_memory_allocated(dev) / 2 ** 30,
-               timing=f'(run of {n_long} steps - run of {n_short} steps) / {n_long - n_short}: the three eager steps and the graph capture of a run cancel',
-               run_ms=dict(short=t_short, long=t_long))
+               timing=('CUDA events around the graph-replayed steps of one run' if tm['replay_steps'] else 'CUDA events around an all-eager run'),
+               run=dict(steps=n_run, ms=run_ms, eager_steps=tm['eager_steps'], note='whole run incl. the eager steps and the graph capture'))
     del gen, inv, target
     torch.cuda.empty_cache()
     return res

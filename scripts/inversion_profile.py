@@ -36,7 +36,13 @@ e0.record()
 inv.run(target, lat0, 3)
 e1.record()
 torch.cuda.synchronize()
-print(f'{e0.elapsed_time(e1) / 3:.2f} ms per Adam step (batch {B})')
+print(f'{e0.elapsed_time(e1) / 3:.2f} ms per Adam step, eager launches (batch {B})')
+
+
+inv.run(target, lat0, 28)
+tm = inv.timing
+if tm['replay_steps']:
+    print(f"{tm['replay_ms'] / tm['replay_steps']:.2f} ms per Adam step replayed as a CUDA graph ({tm['replay_steps']} replays after {tm['eager_steps']} eager steps)")
 K.profile_begin()
 inv.run(target, lat0, 1)
 torch.cuda.synchronize()
